@@ -1,0 +1,594 @@
+// ref_driver.cc — oracle/_ref/liboracle_ref.so: the REFERENCE's own YaspGrid code driven through
+// oracle/oracle_api.h. TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// Built by oracle/Makefile from the sources where they lie under /root/reference:
+//   dune/grid/yaspgrid.hh, dune/grid/yaspgrid/{coordinates,torus,partitioning,ygrid,yaspgridgeometry,
+//   yaspgridentity,yaspgridintersection,yaspgridintersectioniterator,yaspgridleveliterator,
+//   yaspgridindexsets,yaspgrididset,yaspgridentityseed,yaspgridhierarchiciterator}.hh,
+//   dune/grid/common/{gridenums,exceptions,datahandleif,mapper,mcmgmapper,capabilities,backuprestore}.hh
+// are included unmodified; dune-common, dune-geometry and MPI (absent from this image) are replaced
+// by the stand-ins in oracle/ref/shim (ranks = threads of this process, see shim/mpi.h).
+// Every loop below is written the way a dune-grid user writes it: per-entity iterators,
+// per-intersection facade calls, a CommDataHandleIF data handle.
+#define HAVE_MPI 1
+#include <dune/grid/yaspgrid.hh>
+#include <dune/grid/common/mcmgmapper.hh>
+
+#include <chrono>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <memory>
+#include <string>
+#include <thread>
+
+#include "../oracle_api.h"
+#include "../common/fv_problem.hh"
+#include "../common/multilinear.hh"
+
+namespace {
+
+thread_local std::string g_err;
+
+struct WorldBase {
+  int P = 1;
+  int gdim = 0;
+  virtual ~WorldBase() {}
+  virtual int maxLevel() = 0;
+  virtual void torusDims(int*) = 0;
+  virtual void domainSize(double*) = 0;
+  virtual int64_t size(int rank, int level, int codim) = 0;
+  virtual int nbs(int rank) = 0;
+  virtual int overlapSize(int level) = 0;
+  virtual int boxes(int rank, int level, int codim, int* out) = 0;
+  virtual int list(int rank, int level, int codim, int which, int* out, int cap) = 0;
+  virtual int coordinates(int rank, int level, int axis, double* out, int* first) = 0;
+  virtual int64_t entities(int rank, int level, int codim, int pit, uint32_t*, uint8_t*, int32_t*, double*, double*, double*, double*) = 0;
+  virtual int64_t subindices(int rank, int level, int pit, int cc, uint32_t*) = 0;
+  virtual int64_t mapperSize(int rank, int level, const uint32_t* block) = 0;
+  virtual int64_t mapperIndex(int rank, int level, const uint32_t* block, int codim, int pit, uint32_t*) = 0;
+  virtual int64_t mapperSubIndex(int rank, int level, const uint32_t* block, int pit, int cc, uint32_t*) = 0;
+  virtual int64_t intersections(int rank, int level, int pit, uint8_t*, uint8_t*, int32_t*, int32_t*, double*, double*, double*) = 0;
+  virtual int64_t geometryEval(int rank, int level, int pit, int nqp, const double* qp, double*, double*, double*) = 0;
+  virtual int64_t geogridEval(int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
+                              double*, double*, double*, double*, double*) = 0;
+  virtual int64_t communicate(int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* items) = 0;
+  virtual int fvInit(int rank, int level, int problem, const double* params, double* c) = 0;
+  virtual double fvRun(int level, int problem, const double* params, double** c, double** upd, int steps, double* dt_last) = 0;
+};
+
+// run f(rank) on P threads (ranks of the in-process MPI); rethrow the first exception text
+template<class F>
+void on_all_ranks(int P, F&& f) {
+  if (P == 1) { f(0); return; }
+  std::vector<std::thread> th;
+  std::vector<std::string> errs(P);
+  for (int p = 0; p < P; ++p)
+    th.emplace_back([&, p] {
+      try { f(p); }
+      catch (const std::exception& e) { errs[p] = e.what(); if (errs[p].empty()) errs[p] = "exception"; }
+      catch (...) { errs[p] = "unknown exception"; }
+    });
+  for (auto& t : th) t.join();
+  for (int p = 0; p < P; ++p)
+    if (!errs[p].empty()) { Dune::Exception e; e.message(errs[p]); throw e; }
+}
+
+// compile-time dispatch over (codim, PartitionIteratorType)
+template<int dim, int cd, class F>
+void dispatch_pit(int pit, F&& f) {
+  using namespace Dune;
+  switch (pit) {
+    case Interior_Partition:       f(std::integral_constant<int,cd>(), std::integral_constant<PartitionIteratorType,Interior_Partition>()); break;
+    case InteriorBorder_Partition: f(std::integral_constant<int,cd>(), std::integral_constant<PartitionIteratorType,InteriorBorder_Partition>()); break;
+    case Overlap_Partition:        f(std::integral_constant<int,cd>(), std::integral_constant<PartitionIteratorType,Overlap_Partition>()); break;
+    case OverlapFront_Partition:   f(std::integral_constant<int,cd>(), std::integral_constant<PartitionIteratorType,OverlapFront_Partition>()); break;
+    case All_Partition:            f(std::integral_constant<int,cd>(), std::integral_constant<PartitionIteratorType,All_Partition>()); break;
+    case Ghost_Partition:          f(std::integral_constant<int,cd>(), std::integral_constant<PartitionIteratorType,Ghost_Partition>()); break;
+    default: DUNE_THROW(Dune::GridError, "bad partition iterator type " << pit);
+  }
+}
+template<int dim, class F>
+void dispatch(int codim, int pit, F&& f) {
+  if (codim == 0) dispatch_pit<dim,0>(pit, f);
+  else if (codim == 1) dispatch_pit<dim,1>(pit, f);
+  else if (codim == 2) { if constexpr (dim >= 2) dispatch_pit<dim,2>(pit, f); }
+  else if (codim == 3) { if constexpr (dim >= 3) dispatch_pit<dim,3>(pit, f); }
+  else DUNE_THROW(Dune::GridError, "bad codim " << codim);
+}
+
+// the data handle: flat arrays indexed by an MCMG mapper, modelled on the reference's own
+// NumPyCommDataHandle (dune/python/grid/numpycommdatahandle.hh:41-142): per entity, for each array,
+// for each mapper index of the entity, for each item -> one write / one read+combine.
+template<class Mapper>
+class ArrayDataHandle : public Dune::CommDataHandleIF<ArrayDataHandle<Mapper>, double> {
+public:
+  ArrayDataHandle(const Mapper& m, const uint32_t* block, int narrays, double* const* arrays, const int* items, int op)
+    : mapper_(m), block_(block), n_(narrays), arrays_(arrays), items_(items), op_(op), itemSize_(0), written(0)
+  { for (int a = 0; a < n_; ++a) itemSize_ += items_[a]; }
+  bool contains(int /*dim*/, int codim) const { return block_[codim] > 0; }
+  bool fixedSize(int, int) const { return true; }
+  template<class Entity> std::size_t size(const Entity& e) const { return mapper_.size(e.type())*itemSize_; }
+  template<class Buf, class Entity> void gather(Buf& buf, const Entity& e) const {
+    for (int a = 0; a < n_; ++a)
+      for (const auto index : mapper_.indices(e))
+        for (int i = 0; i < items_[a]; ++i) { buf.write(arrays_[a][std::size_t(index)*items_[a]+i]); ++written; }
+  }
+  template<class Buf, class Entity> void scatter(Buf& buf, const Entity& e, std::size_t) {
+    for (int a = 0; a < n_; ++a)
+      for (const auto index : mapper_.indices(e))
+        for (int i = 0; i < items_[a]; ++i) {
+          double& local = arrays_[a][std::size_t(index)*items_[a]+i];
+          double remote; buf.read(remote);
+          local = (op_ == 1) ? remote+local : remote;
+        }
+  }
+  mutable int64_t written;
+private:
+  const Mapper& mapper_; const uint32_t* block_; int n_; double* const* arrays_; const int* items_; int op_; std::size_t itemSize_;
+};
+
+template<int dim, class CC>
+struct World : WorldBase {
+  typedef Dune::YaspGrid<dim,CC> Grid;
+  typedef typename Grid::LevelGridView GV;
+  typedef Dune::MultipleCodimMultipleGeomTypeMapper<GV> Mapper;
+  std::unique_ptr<vmpi_world> vw;
+  std::vector<vmpi_rank> rk;
+  std::vector<std::unique_ptr<Grid>> grids;
+  Dune::Yasp::DefaultPartitioning<dim> defPart;
+  Dune::Yasp::PowerDPartitioning<dim> powPart;
+  std::unique_ptr<Dune::Yasp::FixedSizePartitioning<dim>> fixPart;
+
+  World(const orc_spec& s, int nranks) {
+    P = nranks; gdim = dim;
+    vw.reset(new vmpi_world(P)); rk.resize(P); grids.resize(P);
+    for (int p = 0; p < P; ++p) rk[p] = vmpi_rank{vw.get(), p};
+    const Dune::Yasp::Partitioning<dim>* part = &defPart;
+    if (s.partitioner == 1) part = &powPart;
+    if (s.partitioner == 2) {
+      std::array<int,dim> fd; for (int i = 0; i < dim; ++i) fd[i] = s.fixed_dims[i];
+      fixPart.reset(new Dune::Yasp::FixedSizePartitioning<dim>(fd)); part = fixPart.get();
+    }
+    std::array<int,dim> N; for (int i = 0; i < dim; ++i) N[i] = s.N[i];
+    std::bitset<dim> per(s.periodic);
+    on_all_ranks(P, [&](int p) {
+      typename Grid::Communication comm(&rk[p]);
+      if constexpr (std::is_same_v<CC, Dune::EquidistantCoordinates<double,dim>>) {
+        Dune::FieldVector<double,dim> L; for (int i = 0; i < dim; ++i) L[i] = s.upper[i];
+        grids[p].reset(new Grid(L, N, per, s.overlap, comm, part));
+      } else if constexpr (std::is_same_v<CC, Dune::EquidistantOffsetCoordinates<double,dim>>) {
+        Dune::FieldVector<double,dim> lo, up; for (int i = 0; i < dim; ++i) { lo[i] = s.lower[i]; up[i] = s.upper[i]; }
+        grids[p].reset(new Grid(lo, up, N, per, s.overlap, comm, part));
+      } else {
+        std::array<std::vector<double>,dim> c;
+        for (int i = 0; i < dim; ++i) c[i].assign(s.tensor[i], s.tensor[i]+s.N[i]+1);
+        grids[p].reset(new Grid(c, per, s.overlap, comm, part));
+      }
+      grids[p]->refineOptions(s.keep_overlap != 0);
+      if (s.refine > 0) grids[p]->globalRefine(s.refine);
+    });
+  }
+
+  Grid& g(int rank) { return *grids[rank]; }
+  int maxLevel() override { return g(0).maxLevel(); }
+  void torusDims(int* d) override { for (int i = 0; i < dim; ++i) d[i] = g(0).torus().dims(i); }
+  void domainSize(double* L) override { for (int i = 0; i < dim; ++i) L[i] = g(0).domainSize()[i]; }
+  int64_t size(int rank, int level, int codim) override { return g(rank).size(level, codim); }
+  int nbs(int rank) override { return int(g(rank).numBoundarySegments()); }
+  int overlapSize(int level) override { return g(0).overlapSize(level, 0); }
+
+  int boxes(int rank, int level, int codim, int* out) override {
+    auto gl = g(rank).begin(level);
+    int k = 0;
+    for (auto it = gl->overlapfront[codim].dataBegin(); it != gl->overlapfront[codim].dataEnd(); ++it, ++k) {
+      int* o = out + 26*k;
+      std::array<int,dim> zero; zero.fill(0); (void)zero;
+      o[0] = int(it->shift().to_ulong());
+      std::array<int,dim> org = it->origin();
+      o[1] = gl->overlapfront[codim].superindex(org, k);          // index offset of the component
+      const Dune::YGridComponent<CC>* b[4] = { &*it, gl->overlap[codim].dataBegin()+k,
+                                               gl->interiorborder[codim].dataBegin()+k, gl->interior[codim].dataBegin()+k };
+      for (int q = 0; q < 4; ++q)
+        for (int i = 0; i < 3; ++i) {
+          o[2+6*q+i]   = i < dim ? b[q]->origin(i) : 0;
+          o[2+6*q+3+i] = i < dim ? b[q]->size(i) : 1;
+        }
+    }
+    return k;
+  }
+
+  int list(int rank, int level, int codim, int which, int* out, int cap) override {
+    auto gl = g(rank).begin(level);
+    const Dune::YGridList<CC>* l = nullptr;
+    switch (which) {
+      case 0: l = &gl->send_overlapfront_overlapfront[codim]; break;
+      case 1: l = &gl->recv_overlapfront_overlapfront[codim]; break;
+      case 2: l = &gl->send_overlap_overlapfront[codim]; break;
+      case 3: l = &gl->recv_overlapfront_overlap[codim]; break;
+      case 4: l = &gl->send_interiorborder_interiorborder[codim]; break;
+      case 5: l = &gl->recv_interiorborder_interiorborder[codim]; break;
+      case 6: l = &gl->send_interiorborder_overlapfront[codim]; break;
+      case 7: l = &gl->recv_overlapfront_interiorborder[codim]; break;
+      default: return -1;
+    }
+    int n = 0;
+    for (auto is = l->begin(); is != l->end(); ++is, ++n) {
+      if (n >= cap) continue;
+      int* o = out + 10*n;
+      o[0] = is->rank; o[1] = is->distance; o[2] = int(is->grid.shift().to_ulong());
+      typename Dune::YGrid<CC>::Iterator it(is->yg);
+      o[3] = it.superindex() - is->grid.superindex(is->grid.origin());   // the artificial index offset
+      for (int i = 0; i < 3; ++i) { o[4+i] = i < dim ? is->grid.origin(i) : 0; o[7+i] = i < dim ? is->grid.size(i) : 1; }
+    }
+    return n;
+  }
+
+  int coordinates(int rank, int level, int axis, double* out, int* first) override {
+    auto gl = g(rank).begin(level);
+    const auto& b = *gl->overlapfront[dim].dataBegin();     // vertex box = all stored vertex indices
+    *first = b.origin(axis);
+    for (int i = 0; i < b.size(axis); ++i) out[i] = gl->coords.coordinate(axis, b.origin(axis)+i);
+    return b.size(axis);
+  }
+
+  int64_t entities(int rank, int level, int codim, int pit, uint32_t* index, uint8_t* ptype, int32_t* coord,
+                   double* lower, double* upper, double* center, double* volume) override {
+    int64_t n = 0;
+    Grid& gr = g(rank);
+    const auto& is = gr.levelIndexSet(level);
+    dispatch<dim>(codim, pit, [&](auto cdc, auto pitc) {
+      constexpr int cd = decltype(cdc)::value;
+      constexpr Dune::PartitionIteratorType pt = decltype(pitc)::value;
+      auto end = gr.template lend<cd,pt>(level);
+      for (auto it = gr.template lbegin<cd,pt>(level); it != end; ++it, ++n) {
+        const auto& e = *it;
+        if (index) index[n] = is.index(e);
+        if (ptype) ptype[n] = uint8_t(e.partitionType());
+        if (coord) for (int i = 0; i < dim; ++i) coord[n*dim+i] = e.impl().transformingsubiterator().coord(i);
+        if (lower || upper || center || volume) {
+          auto geo = e.geometry();
+          if (lower) { auto c = geo.corner(0); for (int i = 0; i < dim; ++i) lower[n*dim+i] = c[i]; }
+          if (upper) { auto c = geo.corner(geo.corners()-1); for (int i = 0; i < dim; ++i) upper[n*dim+i] = c[i]; }
+          if (center) { auto c = geo.center(); for (int i = 0; i < dim; ++i) center[n*dim+i] = c[i]; }
+          if (volume) volume[n] = geo.volume();
+        }
+      }
+    });
+    return n;
+  }
+
+  int64_t subindices(int rank, int level, int pit, int cc, uint32_t* out) override {
+    int64_t n = 0;
+    Grid& gr = g(rank);
+    const auto& is = gr.levelIndexSet(level);
+    dispatch<dim>(0, pit, [&](auto, auto pitc) {
+      constexpr Dune::PartitionIteratorType pt = decltype(pitc)::value;
+      auto end = gr.template lend<0,pt>(level);
+      for (auto it = gr.template lbegin<0,pt>(level); it != end; ++it, ++n) {
+        const auto& e = *it;
+        const int ns = e.subEntities(cc);
+        for (int i = 0; i < ns; ++i) out[n*ns+i] = is.subIndex(e, i, cc);
+      }
+    });
+    return n;
+  }
+
+  Mapper makeMapper(int rank, int level, const uint32_t* block) {
+    std::array<uint32_t,4> b{{0,0,0,0}};
+    for (int i = 0; i <= dim; ++i) b[i] = block[i];
+    return Mapper(g(rank).levelGridView(level), [b](Dune::GeometryType gt, int dimgrid) { return std::size_t(b[dimgrid - int(gt.dim())]); });
+  }
+  int64_t mapperSize(int rank, int level, const uint32_t* block) override { return makeMapper(rank, level, block).size(); }
+  int64_t mapperIndex(int rank, int level, const uint32_t* block, int codim, int pit, uint32_t* out) override {
+    Mapper m = makeMapper(rank, level, block);
+    Grid& gr = g(rank);
+    int64_t n = 0;
+    dispatch<dim>(codim, pit, [&](auto cdc, auto pitc) {
+      constexpr int cd = decltype(cdc)::value;
+      constexpr Dune::PartitionIteratorType pt = decltype(pitc)::value;
+      auto end = gr.template lend<cd,pt>(level);
+      for (auto it = gr.template lbegin<cd,pt>(level); it != end; ++it, ++n) out[n] = m.index(*it);
+    });
+    return n;
+  }
+  int64_t mapperSubIndex(int rank, int level, const uint32_t* block, int pit, int cc, uint32_t* out) override {
+    Mapper m = makeMapper(rank, level, block);
+    Grid& gr = g(rank);
+    int64_t n = 0;
+    dispatch<dim>(0, pit, [&](auto, auto pitc) {
+      constexpr Dune::PartitionIteratorType pt = decltype(pitc)::value;
+      auto end = gr.template lend<0,pt>(level);
+      for (auto it = gr.template lbegin<0,pt>(level); it != end; ++it, ++n) {
+        const auto& e = *it;
+        const int ns = e.subEntities(cc);
+        for (int i = 0; i < ns; ++i) out[n*ns+i] = m.subIndex(e, i, cc);
+      }
+    });
+    return n;
+  }
+
+  int64_t intersections(int rank, int level, int pit, uint8_t* neighbor, uint8_t* boundary, int32_t* outside, int32_t* bsi,
+                        double* normal, double* fcenter, double* fvolume) override {
+    Grid& gr = g(rank);
+    GV gv = gr.levelGridView(level);
+    const auto& is = gr.levelIndexSet(level);
+    int64_t n = 0;
+    dispatch<dim>(0, pit, [&](auto, auto pitc) {
+      constexpr Dune::PartitionIteratorType pt = decltype(pitc)::value;
+      auto end = gr.template lend<0,pt>(level);
+      for (auto it = gr.template lbegin<0,pt>(level); it != end; ++it, ++n) {
+        const auto& e = *it;
+        auto iend = gv.iend(e);
+        for (auto iit = gv.ibegin(e); iit != iend; ++iit) {
+          const auto& in = *iit;
+          const int64_t k = n*2*dim + in.indexInInside();
+          if (neighbor) neighbor[k] = in.neighbor();
+          if (boundary) boundary[k] = in.boundary();
+          if (outside) outside[k] = in.neighbor() ? int32_t(is.index(in.outside())) : -1;
+          if (bsi) bsi[k] = in.boundary() ? in.boundarySegmentIndex() : -1;
+          if (normal) { auto nn = in.centerUnitOuterNormal(); for (int i = 0; i < dim; ++i) normal[k*dim+i] = nn[i]; }
+          if (fcenter || fvolume) {
+            auto geo = in.geometry();
+            if (fcenter) { auto c = geo.center(); for (int i = 0; i < dim; ++i) fcenter[k*dim+i] = c[i]; }
+            if (fvolume) fvolume[k] = geo.volume();
+          }
+        }
+      }
+    });
+    return n;
+  }
+
+  int64_t geometryEval(int rank, int level, int pit, int nqp, const double* qp, double* global, double* jit, double* detJ) override {
+    Grid& gr = g(rank);
+    int64_t n = 0;
+    dispatch<dim>(0, pit, [&](auto, auto pitc) {
+      constexpr Dune::PartitionIteratorType pt = decltype(pitc)::value;
+      auto end = gr.template lend<0,pt>(level);
+      for (auto it = gr.template lbegin<0,pt>(level); it != end; ++it, ++n) {
+        auto geo = it->geometry();
+        for (int q = 0; q < nqp; ++q) {
+          Dune::FieldVector<double,dim> x; for (int i = 0; i < dim; ++i) x[i] = qp[q*dim+i];
+          const int64_t k = n*nqp + q;
+          if (global) { auto y = geo.global(x); for (int i = 0; i < dim; ++i) global[k*dim+i] = y[i]; }
+          if (jit) { auto J = geo.jacobianInverseTransposed(x); for (int i = 0; i < dim; ++i) for (int j = 0; j < dim; ++j) jit[(k*dim+i)*dim+j] = J[i][j]; }
+          if (detJ) detJ[k] = geo.integrationElement(x);
+        }
+      }
+    });
+    return n;
+  }
+
+  // GeometryGrid<YaspGrid, AnalyticalCoordFunction>: corners = F(hostGeometry.corner(i))
+  // (reference geometrygrid/cornerstorage.hh:54-60, hostcorners.hh:40-43, coordfunctioncaller.hh:40-43), geometry =
+  // MultiLinearGeometry over those corners (geometrygrid/geometry.hh:66,197-204) — the multilinear part is the
+  // restatement in oracle/common/multilinear.hh (dune-geometry is not vendored).
+  int64_t geogridEval(int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
+                      double* corners, double* global, double* jt, double* jit, double* detJ) override {
+    Grid& gr = g(rank);
+    int64_t n = 0;
+    constexpr int nc = 1 << dim;
+    dispatch<dim>(0, pit, [&](auto, auto pitc) {
+      constexpr Dune::PartitionIteratorType pt = decltype(pitc)::value;
+      auto end = gr.template lend<0,pt>(level);
+      for (auto it = gr.template lbegin<0,pt>(level); it != end; ++it, ++n) {
+        auto hostGeo = it->geometry();
+        double c[nc][dim];
+        for (int k = 0; k < nc; ++k) {
+          auto hc = hostGeo.corner(k);
+          double x[dim]; for (int i = 0; i < dim; ++i) x[i] = hc[i];
+          orc::deformation(def, params, dim, x, c[k]);
+          if (corners) for (int i = 0; i < dim; ++i) corners[(n*nc+k)*dim+i] = c[k][i];
+        }
+        for (int q = 0; q < nqp; ++q) {
+          const int64_t k = n*nqp + q;
+          const double* x = qp + q*dim;
+          double J[dim][dim], Ji[dim][dim], y[dim];
+          if (global) { orc::multilinear_global<dim>(c, x, y); for (int i = 0; i < dim; ++i) global[k*dim+i] = y[i]; }
+          orc::multilinear_jt<dim>(c, x, J);
+          if (jt) for (int i = 0; i < dim; ++i) for (int j = 0; j < dim; ++j) jt[(k*dim+i)*dim+j] = J[i][j];
+          if (jit) { orc::right_inv<dim>(J, Ji); for (int i = 0; i < dim; ++i) for (int j = 0; j < dim; ++j) jit[(k*dim+i)*dim+j] = Ji[i][j]; }
+          if (detJ) detJ[k] = orc::sqrt_det_aat<dim>(J);
+        }
+      }
+    });
+    return n;
+  }
+
+  int64_t communicate(int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* items) override {
+    std::vector<int64_t> sent(P, 0);
+    on_all_ranks(P, [&](int p) {
+      Mapper m = makeMapper(p, level, block);
+      ArrayDataHandle<Mapper> dh(m, block, narrays, arrays + std::size_t(p)*narrays, items, op);
+      g(p).levelGridView(level).communicate(dh, Dune::InterfaceType(iftype), Dune::CommunicationDirection(dir));
+      sent[p] = dh.written;
+    });
+    int64_t s = 0; for (auto v : sent) s += v;
+    return s;
+  }
+
+  int fvInit(int rank, int level, int problem, const double* params, double* c) override {
+    Grid& gr = g(rank);
+    GV gv = gr.levelGridView(level);
+    Mapper m(gv, Dune::mcmgElementLayout());
+    for (auto it = gv.template begin<0>(); it != gv.template end<0>(); ++it) {
+      auto x = it->geometry().center();
+      c[m.index(*it)] = orc::fv_initial(problem, params, dim, x.data());
+    }
+    return 0;
+  }
+
+  // One explicit upwind finite-volume step per rank, in the style of dune-grid-howto's parallel evolve
+  // (not vendored in the reference; definition in SURVEY.md §8d): element loop over the interior
+  // partition, intersection loop, mapper lookups, then communicate(InteriorBorder_All, Forward).
+  double fvRun(int level, int problem, const double* params, double** c, double** upd, int steps, double* dt_last) override {
+    std::vector<double> dts(P, 0.0);
+    auto t0 = std::chrono::steady_clock::now();
+    on_all_ranks(P, [&](int p) {
+      Grid& gr = g(p);
+      GV gv = gr.levelGridView(level);
+      Mapper mapper(gv, Dune::mcmgElementLayout());
+      const uint32_t block[4] = {1,0,0,0};
+      const int items[1] = {1};
+      std::vector<double> update(mapper.size(), 0.0);
+      double* cc = c[p];
+      for (int s = 0; s < steps; ++s) {
+        double dt = std::numeric_limits<double>::infinity();
+        auto endit = gv.template end<0,Dune::Interior_Partition>();
+        for (auto it = gv.template begin<0,Dune::Interior_Partition>(); it != endit; ++it) {
+          const auto& e = *it;
+          const double volume = e.geometry().volume();
+          const auto i = mapper.index(e);
+          double sumfactor = 0.0, u = 0.0;
+          auto isend = gv.iend(e);
+          for (auto is = gv.ibegin(e); is != isend; ++is) {
+            const auto& in = *is;
+            auto igeo = in.geometry();
+            auto fc = igeo.center();
+            auto nrm = in.centerUnitOuterNormal();
+            Dune::FieldVector<double,dim> vel;
+            orc::fv_velocity(problem, params, dim, fc.data(), vel.data());
+            const double factor = (vel*nrm)*igeo.volume()/volume;
+            if (factor >= 0) { sumfactor += factor; u -= cc[i]*factor; }
+            else if (in.neighbor()) { const auto j = mapper.index(in.outside()); u -= cc[j]*factor; }
+            else if (in.boundary()) { u -= orc::fv_boundary(problem, params, dim, fc.data())*factor; }
+          }
+          update[i] = u;
+          dt = std::min(dt, 1.0/sumfactor);
+        }
+        dt = gr.comm().min(dt);
+        dt *= 0.99;
+        for (auto it = gv.template begin<0,Dune::Interior_Partition>(); it != endit; ++it) {
+          const auto i = mapper.index(*it);
+          cc[i] += dt*update[i];
+        }
+        ArrayDataHandle<Mapper> dh(mapper, block, 1, &cc, items, 0);
+        gv.communicate(dh, Dune::InteriorBorder_All_Interface, Dune::ForwardCommunication);
+        dts[p] = dt;
+      }
+      if (upd && upd[p]) std::memcpy(upd[p], update.data(), update.size()*sizeof(double));
+    });
+    auto t1 = std::chrono::steady_clock::now();
+    if (dt_last) *dt_last = dts[0];
+    return std::chrono::duration<double>(t1-t0).count();
+  }
+};
+
+template<int dim>
+WorldBase* make_world(const orc_spec& s, int nranks) {
+  switch (s.coord_mode) {
+    case 0: return new World<dim, Dune::EquidistantCoordinates<double,dim>>(s, nranks);
+    case 1: return new World<dim, Dune::EquidistantOffsetCoordinates<double,dim>>(s, nranks);
+    case 2: return new World<dim, Dune::TensorProductCoordinates<double,dim>>(s, nranks);
+  }
+  DUNE_THROW(Dune::GridError, "bad coord_mode " << s.coord_mode);
+}
+
+template<class F, class R>
+R guarded(R onerr, F&& f) {
+  try { g_err.clear(); return f(); }
+  catch (const std::exception& e) { g_err = e.what(); if (g_err.empty()) g_err = "exception"; }
+  catch (...) { g_err = "unknown exception"; }
+  return onerr;
+}
+inline WorldBase* W(void* w) { return static_cast<WorldBase*>(w); }
+
+template<int d>
+int partition_d(const int* N, int P, int overlap, int partitioner, const int* fixed, int* out) {
+  std::array<int,d> size, dims, fd;
+  for (int i = 0; i < d; ++i) { size[i] = N[i]; fd[i] = fixed ? fixed[i] : 1; }
+  if (partitioner == 0) Dune::Yasp::DefaultPartitioning<d>().partition(size, P, dims, overlap);
+  else if (partitioner == 1) Dune::Yasp::PowerDPartitioning<d>().partition(size, P, dims, overlap);
+  else Dune::Yasp::FixedSizePartitioning<d>(fd).partition(size, P, dims, overlap);
+  for (int i = 0; i < d; ++i) out[i] = dims[i];
+  return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* orc_kind(void) { return "reference"; }
+const char* orc_last_error(void) { return g_err.c_str(); }
+
+int orc_partition(int dim, const int* N, int P, int overlap, int partitioner, const int* fixed, int* dims_out) {
+  return guarded(-1, [&] {
+    switch (dim) {
+      case 1: return partition_d<1>(N, P, overlap, partitioner, fixed, dims_out);
+      case 2: return partition_d<2>(N, P, overlap, partitioner, fixed, dims_out);
+      case 3: return partition_d<3>(N, P, overlap, partitioner, fixed, dims_out);
+      case 4: return partition_d<4>(N, P, overlap, partitioner, fixed, dims_out);
+    }
+    return -1;
+  });
+}
+int orc_entity_shift(int dim, int i, int cc) {
+  switch (dim) { case 1: return int(Dune::Yasp::entityShift<1>(i,cc).to_ulong()); case 2: return int(Dune::Yasp::entityShift<2>(i,cc).to_ulong());
+                 case 3: return int(Dune::Yasp::entityShift<3>(i,cc).to_ulong()); case 4: return int(Dune::Yasp::entityShift<4>(i,cc).to_ulong()); }
+  return -1;
+}
+int orc_entity_move(int dim, int i, int cc) {
+  switch (dim) { case 1: return int(Dune::Yasp::entityMove<1>(i,cc).to_ulong()); case 2: return int(Dune::Yasp::entityMove<2>(i,cc).to_ulong());
+                 case 3: return int(Dune::Yasp::entityMove<3>(i,cc).to_ulong()); case 4: return int(Dune::Yasp::entityMove<4>(i,cc).to_ulong()); }
+  return -1;
+}
+int orc_sub_entities(int dim, int d, int c) {
+  switch (dim) { case 1: return Dune::Yasp::subEnt<1>(d,c); case 2: return Dune::Yasp::subEnt<2>(d,c);
+                 case 3: return Dune::Yasp::subEnt<3>(d,c); case 4: return Dune::Yasp::subEnt<4>(d,c); }
+  return -1;
+}
+
+void* orc_create(const orc_spec* spec, int nranks) {
+  return guarded((void*)nullptr, [&]() -> void* {
+    if (spec->dim == 2) return make_world<2>(*spec, nranks);
+    if (spec->dim == 3) return make_world<3>(*spec, nranks);
+    DUNE_THROW(Dune::GridError, "oracle supports dim 2 and 3");
+  });
+}
+void orc_destroy(void* w) { delete W(w); }
+int orc_max_level(void* w) { return W(w)->maxLevel(); }
+void orc_torus_dims(void* w, int* d) { W(w)->torusDims(d); }
+void orc_domain_size(void* w, double* L) { W(w)->domainSize(L); }
+int64_t orc_size(void* w, int rank, int level, int codim) { return guarded(int64_t(-1), [&]{ return W(w)->size(rank, level, codim); }); }
+int orc_num_boundary_segments(void* w, int rank) { return W(w)->nbs(rank); }
+int orc_overlap_size(void* w, int level) { return guarded(-1, [&]{ return W(w)->overlapSize(level); }); }
+int orc_boxes(void* w, int rank, int level, int codim, int* out) { return guarded(-1, [&]{ return W(w)->boxes(rank, level, codim, out); }); }
+int orc_list(void* w, int rank, int level, int codim, int which, int* out, int cap) { return guarded(-1, [&]{ return W(w)->list(rank, level, codim, which, out, cap); }); }
+int orc_coordinates(void* w, int rank, int level, int axis, double* out, int* first) { return guarded(-1, [&]{ return W(w)->coordinates(rank, level, axis, out, first); }); }
+int64_t orc_entities(void* w, int rank, int level, int codim, int pit, uint32_t* index, uint8_t* ptype, int32_t* coord,
+                     double* lower, double* upper, double* center, double* volume) {
+  return guarded(int64_t(-1), [&]{ return W(w)->entities(rank, level, codim, pit, index, ptype, coord, lower, upper, center, volume); });
+}
+int64_t orc_subindices(void* w, int rank, int level, int pit, int cc, uint32_t* out) { return guarded(int64_t(-1), [&]{ return W(w)->subindices(rank, level, pit, cc, out); }); }
+int64_t orc_mapper_size(void* w, int rank, int level, const uint32_t* block) { return guarded(int64_t(-1), [&]{ return W(w)->mapperSize(rank, level, block); }); }
+int64_t orc_mapper_index(void* w, int rank, int level, const uint32_t* block, int codim, int pit, uint32_t* out) {
+  return guarded(int64_t(-1), [&]{ return W(w)->mapperIndex(rank, level, block, codim, pit, out); });
+}
+int64_t orc_mapper_subindex(void* w, int rank, int level, const uint32_t* block, int pit, int cc, uint32_t* out) {
+  return guarded(int64_t(-1), [&]{ return W(w)->mapperSubIndex(rank, level, block, pit, cc, out); });
+}
+int64_t orc_intersections(void* w, int rank, int level, int pit, uint8_t* neighbor, uint8_t* boundary, int32_t* outside, int32_t* bsi,
+                          double* normal, double* fc, double* fv) {
+  return guarded(int64_t(-1), [&]{ return W(w)->intersections(rank, level, pit, neighbor, boundary, outside, bsi, normal, fc, fv); });
+}
+int64_t orc_geometry_eval(void* w, int rank, int level, int pit, int nqp, const double* qp, double* global, double* jit, double* detJ) {
+  return guarded(int64_t(-1), [&]{ return W(w)->geometryEval(rank, level, pit, nqp, qp, global, jit, detJ); });
+}
+int64_t orc_geogrid_eval(void* w, int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
+                         double* corners, double* global, double* jt, double* jit, double* detJ) {
+  return guarded(int64_t(-1), [&]{ return W(w)->geogridEval(rank, level, pit, def, params, nqp, qp, corners, global, jt, jit, detJ); });
+}
+int64_t orc_communicate(void* w, int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* items) {
+  return guarded(int64_t(-1), [&]{ return W(w)->communicate(level, block, iftype, dir, op, narrays, arrays, items); });
+}
+int orc_fv_init(void* w, int rank, int level, int problem, const double* params, double* c) {
+  return guarded(-1, [&]{ return W(w)->fvInit(rank, level, problem, params, c); });
+}
+double orc_fv_step(void* w, int level, int problem, const double* params, double** c, double** upd) {
+  return guarded(-1.0, [&]{ double dt = 0; W(w)->fvRun(level, problem, params, c, upd, 1, &dt); return dt; });
+}
+double orc_fv_run(void* w, int level, int problem, const double* params, double** c, int steps, double* dt_last) {
+  return guarded(-1.0, [&]{ return W(w)->fvRun(level, problem, params, c, nullptr, steps, dt_last); });
+}
+
+} // extern "C"
