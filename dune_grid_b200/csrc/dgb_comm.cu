@@ -1,0 +1,378 @@
+// dgb_comm.cu — GridView::communicate for mapper-indexed device arrays.
+//
+// Reference: YaspGrid::communicateCodim (dune/grid/yaspgrid.hh:1490-1730) allocates a buffer per neighbour box
+// on every call, packs entity by entity through the data-handle facade, and exchanges with MPI_Isend/Irecv
+// (torus.hh:387-440). Here an exchange PLAN is built once per (level, layout, interface, direction, item sizes):
+// all send boxes of all codims are packed by ONE kernel into one contiguous device buffer (one segment per
+// peer rank, message layout identical to the reference's: codim dim..0, boxes in list order, entities x-fastest,
+// per entity array-major / block-major / item-minor), segments travel as one ncclSend/ncclRecv pair per peer
+// inside a single group over NVLink, and ONE kernel scatters (set or add) every received segment. Messages
+// to the own rank (periodic wrap on a 1-wide torus direction, torus.hh:395-403) are copied device-to-device.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <algorithm>
+#include <sstream>
+#include "dgb_internal.hh"
+#include "dgb_device.cuh"
+#include "dgb_comm.hh"
+
+namespace dgb {
+
+// ---- NCCL through dlopen: libdgb.so must load on a CPU-only box and must share the process's NCCL ------
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) { error = std::string("cannot load libnccl: ") + dlerror(); return false; }
+#define DGB_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); if (!field) { error = std::string("libnccl lacks ") + name; lib = nullptr; return false; }
+    DGB_SYM(GetUniqueId, "ncclGetUniqueId") DGB_SYM(CommInitRank, "ncclCommInitRank") DGB_SYM(CommDestroy, "ncclCommDestroy")
+    DGB_SYM(Send, "ncclSend") DGB_SYM(Recv, "ncclRecv") DGB_SYM(AllReduce, "ncclAllReduce")
+    DGB_SYM(GroupStart, "ncclGroupStart") DGB_SYM(GroupEnd, "ncclGroupEnd") DGB_SYM(GetErrorString, "ncclGetErrorString")
+#undef DGB_SYM
+    return true;
+  }
+};
+static NcclApi g_nccl;
+
+#define DGB_NCCL(call) do { ncclResult_t r__ = (call); if (r__ != ncclSuccess) \
+  return dgb::fail(DGB_ENCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r__)); } while (0)
+
+} // namespace dgb
+
+struct dgb_comm { ncclComm_t comm; int rank, nranks; };
+
+namespace dgb {
+
+// ---- device side ------------------------------------------------------------------------------------------
+struct ArrayTable { int n; int per_entity; double* ptr[8]; int item[8]; };
+
+static constexpr int PACK_THREADS = 256;
+
+// grid.y = box, grid.x strides over the box's doubles. Thread t of a box handles buffer double t:
+// entity e = t / per_entity (x fastest inside the box), then (array, block entry, item) in reference order.
+template<int MODE>   // 0 pack (gather), 1 unpack set, 2 unpack add
+__global__ void __launch_bounds__(PACK_THREADS) k_halo(const PlanBox* __restrict__ boxes, const ArrayTable arrays, double* __restrict__ buffer) {
+  const PlanBox b = boxes[blockIdx.y];
+  const long long total = b.count*arrays.per_entity;
+  for (long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x*blockDim.x) {
+    const long long e = t / arrays.per_entity;
+    int r = int(t - e*arrays.per_entity);
+    const int i0 = int(e % b.size[0]); const long long q = e / b.size[0];
+    const int i1 = int(q % b.size[1]); const int i2 = int(q / b.size[1]);
+    const long long local = ((long long)(b.origin[2]+i2-b.of_origin[2])*b.of_size[1] + (b.origin[1]+i1-b.of_origin[1]))*b.of_size[0]
+                            + (b.origin[0]+i0-b.of_origin[0]);
+    const unsigned idx = (b.index_base + unsigned(local))*b.block + b.map_offset;
+    // (array a, entry r inside the array's block*item run)
+    int a = 0;
+    while (r >= int(b.block)*arrays.item[a]) { r -= int(b.block)*arrays.item[a]; ++a; }
+    double* p = arrays.ptr[a] + (size_t)idx*arrays.item[a] + r;
+    double* w = buffer + b.buf_offset + t;
+    if (MODE == 0) *w = *p;
+    else if (MODE == 1) *p = *w;
+    else *p = *w + *p;
+  }
+}
+
+// ---- plan construction (host) -------------------------------------------------------------------------
+static void add_boxes(const dgb_grid* g, int level, int codim, int which, const dgb_mapper& m, int per_entity_codim,
+                      std::vector<PlanBox>& boxes, std::vector<int>& peer) {
+  std::vector<ListEntry> l;
+  comm_list(g->me, g->all, level, codim, which, l);
+  const LevelBoxes& lb = g->me.levels[level].b;
+  for (const ListEntry& e : l) {
+    PlanBox b;
+    const dgb_component& c = lb.comp[lb.comp_begin[codim] + lb.shiftmap[e.shift]];
+    const dgb_box& of = c.box[DGB_BOX_OVERLAPFRONT];
+    for (int i = 0; i < 3; ++i) { b.origin[i] = e.box.origin[i]; b.size[i] = e.box.size[i]; b.of_origin[i] = of.origin[i]; b.of_size[i] = of.size[i]; }
+    b.count = 1; for (int i = 0; i < lb.dim; ++i) b.count *= e.box.size[i];
+    for (int i = lb.dim; i < 3; ++i) { b.size[i] = 1; b.of_size[i] = 1; b.origin[i] = 0; b.of_origin[i] = 0; }
+    b.index_base = unsigned(e.index_offset);
+    b.block = m.block[codim]; b.map_offset = m.offset[codim];
+    b.buf_offset = 0;
+    (void)per_entity_codim;
+    boxes.push_back(b);
+    peer.push_back(e.rank);
+  }
+}
+
+std::shared_ptr<CommPlan> build_plan(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir,
+                                     const int32_t* item_sizes, int narrays) {
+  auto plan = std::make_shared<CommPlan>();
+  const int dim = g->me.spec.dim;
+  int sendWhich, recvWhich;
+  switch (iftype) {                                   // yaspgrid.hh:1506-1525
+    case DGB_InteriorBorder_InteriorBorder_Interface: sendWhich = 4; recvWhich = 5; break;
+    case DGB_InteriorBorder_All_Interface: sendWhich = 6; recvWhich = 7; break;
+    case DGB_Overlap_OverlapFront_Interface: case DGB_Overlap_All_Interface: sendWhich = 2; recvWhich = 3; break;
+    case DGB_All_All_Interface: sendWhich = 0; recvWhich = 1; break;
+    default: throw ArgError("unknown interface type");
+  }
+  if (dir == DGB_BackwardCommunication) std::swap(sendWhich, recvWhich);       // :1528-1529
+  else if (dir != DGB_ForwardCommunication) throw ArgError("unknown communication direction");
+  int items = 0; for (int a = 0; a < narrays; ++a) items += item_sizes[a];
+  std::vector<PlanBox> sb, rb; std::vector<int> sp, rp;
+  for (int codim = dim; codim >= 0; --codim) {        // YaspCommunicateMeta: codim dim..0 (:122-143)
+    if (m.block[codim] == 0) continue;                // DataHandle::contains
+    add_boxes(g, level, codim, sendWhich, m, items, sb, sp);
+    add_boxes(g, level, codim, recvWhich, m, items, rb, rp);
+  }
+  // group by peer (stable): one contiguous segment per peer, box order inside a segment = list order
+  auto layout = [&](std::vector<PlanBox>& boxes, const std::vector<int>& peer, std::vector<CommPlan::Segment>& segs, long long& total) {
+    std::vector<int> peers(peer);
+    std::sort(peers.begin(), peers.end()); peers.erase(std::unique(peers.begin(), peers.end()), peers.end());
+    long long off = 0;
+    for (int p : peers) {
+      CommPlan::Segment s; s.peer = p; s.offset = off;
+      for (std::size_t k = 0; k < boxes.size(); ++k) if (peer[k] == p) {
+        boxes[k].buf_offset = off;
+        off += boxes[k].count*(long long)boxes[k].block*items;
+      }
+      s.count = off - s.offset;
+      segs.push_back(s);
+    }
+    total = off;
+  };
+  layout(sb, sp, plan->sendSeg, plan->sendTotal);
+  layout(rb, rp, plan->recvSeg, plan->recvTotal);
+  plan->nSendBoxes = int(sb.size()); plan->nRecvBoxes = int(rb.size());
+  plan->maxSendBox = 0; plan->maxRecvBox = 0;
+  for (auto& b : sb) plan->maxSendBox = std::max(plan->maxSendBox, b.count*(long long)b.block*items);
+  for (auto& b : rb) plan->maxRecvBox = std::max(plan->maxRecvBox, b.count*(long long)b.block*items);
+  plan->items = items;
+  // Unpack hazards: the reference scatters recv boxes one after another (yaspgrid.hh:1694-1729), so when two boxes
+  // of one component overlap (border/front entities shared by several neighbours) the later one wins (set) or the
+  // sums accumulate in list order (add). Boxes are therefore scheduled in "waves": a box runs one wave after the
+  // last earlier box it overlaps; boxes of one wave are disjoint and share a launch.
+  std::vector<int> wave(rb.size(), 0);
+  auto overlaps = [&](const PlanBox& a, const PlanBox& b) {
+    if (a.index_base != b.index_base || a.map_offset != b.map_offset) return false;       // different component / codim
+    for (int i = 0; i < 3; ++i)
+      if (a.origin[i]+a.size[i] <= b.origin[i] || b.origin[i]+b.size[i] <= a.origin[i]) return false;
+    return true;
+  };
+  int nwaves = rb.empty() ? 0 : 1;
+  for (std::size_t k = 0; k < rb.size(); ++k)
+    for (std::size_t j = 0; j < k; ++j)
+      if (overlaps(rb[j], rb[k])) { wave[k] = std::max(wave[k], wave[j]+1); nwaves = std::max(nwaves, wave[k]+1); }
+  std::vector<PlanBox> ordered;
+  plan->recvWaveEnd.clear();
+  for (int w = 0; w < nwaves; ++w) {
+    for (std::size_t k = 0; k < rb.size(); ++k) if (wave[k] == w) ordered.push_back(rb[k]);
+    plan->recvWaveEnd.push_back(int(ordered.size()));
+  }
+  plan->hostSend = sb; plan->hostRecv = ordered;
+  return plan;
+}
+
+int CommPlan::upload() {
+  if (uploaded) return DGB_OK;
+  if (int rc = require_device()) return rc;
+  if (nSendBoxes) { DGB_CUDA(cudaMalloc(&dSendBoxes, nSendBoxes*sizeof(PlanBox)));
+                    DGB_CUDA(cudaMemcpy(dSendBoxes, hostSend.data(), nSendBoxes*sizeof(PlanBox), cudaMemcpyHostToDevice)); }
+  if (nRecvBoxes) { DGB_CUDA(cudaMalloc(&dRecvBoxes, nRecvBoxes*sizeof(PlanBox)));
+                    DGB_CUDA(cudaMemcpy(dRecvBoxes, hostRecv.data(), nRecvBoxes*sizeof(PlanBox), cudaMemcpyHostToDevice)); }
+  if (sendTotal) DGB_CUDA(cudaMalloc(&dSendBuf, sendTotal*sizeof(double)));
+  if (recvTotal) DGB_CUDA(cudaMalloc(&dRecvBuf, recvTotal*sizeof(double)));
+  uploaded = true;
+  return DGB_OK;
+}
+CommPlan::~CommPlan() {
+  if (dSendBoxes) cudaFree(dSendBoxes);
+  if (dRecvBoxes) cudaFree(dRecvBoxes);
+  if (dSendBuf) cudaFree(dSendBuf);
+  if (dRecvBuf) cudaFree(dRecvBuf);
+}
+
+static dim3 halo_grid(long long maxBox, int nBoxes) {
+  long long bx = (maxBox + PACK_THREADS - 1)/PACK_THREADS;
+  if (bx > 2048) bx = 2048;
+  if (bx < 1) bx = 1;
+  return dim3((unsigned)bx, (unsigned)nBoxes, 1);
+}
+
+static int make_table(const CommPlan& plan, double* const* d_arrays, const int32_t* item_sizes, int narrays, ArrayTable& at) {
+  if (narrays > 8) return fail(DGB_EARG, "at most 8 arrays per communicate call");
+  at.n = narrays; at.per_entity = 0;
+  for (int a = 0; a < narrays; ++a) { at.ptr[a] = d_arrays[a]; at.item[a] = item_sizes[a]; }
+  for (int a = narrays; a < 8; ++a) { at.ptr[a] = nullptr; at.item[a] = 1 << 30; }
+  (void)plan;
+  return DGB_OK;
+}
+
+// boxes of one launch share the mapper block size (per-entity run length) and, for unpack, the wave
+static void launch_boxes(CommPlan& plan, const ArrayTable& at, int mode, const std::vector<PlanBox>& host, PlanBox* dev, double* buf,
+                         const std::vector<int>* waveEnd, cudaStream_t stream) {
+  std::size_t k = 0, wv = 0;
+  while (k < host.size()) {
+    std::size_t limit = host.size();
+    if (waveEnd) { while (wv < waveEnd->size() && std::size_t((*waveEnd)[wv]) <= k) ++wv; limit = std::size_t((*waveEnd)[wv]); }
+    std::size_t e = k; long long mx = 0;
+    while (e < limit && host[e].block == host[k].block) { mx = std::max(mx, host[e].count*(long long)host[e].block*plan.items); ++e; }
+    ArrayTable t = at; t.per_entity = int(host[k].block)*plan.items;
+    dim3 grid = halo_grid(mx, int(e-k));
+    if (mode == 0) k_halo<0><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf);
+    else if (mode == 1) k_halo<1><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf);
+    else k_halo<2><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf);
+    ++plan.launches;
+    k = e;
+  }
+}
+
+int plan_pack(CommPlan& plan, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream) {
+  if (int rc = plan.upload()) return rc;
+  ArrayTable at; if (int rc = make_table(plan, d_arrays, item_sizes, narrays, at)) return rc;
+  if (plan.nSendBoxes) launch_boxes(plan, at, 0, plan.hostSend, plan.dSendBoxes, plan.dSendBuf, nullptr, stream);
+  DGB_CUDA(cudaGetLastError());
+  return DGB_OK;
+}
+
+int plan_unpack(CommPlan& plan, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream) {
+  if (int rc = plan.upload()) return rc;
+  ArrayTable at; if (int rc = make_table(plan, d_arrays, item_sizes, narrays, at)) return rc;
+  if (plan.nRecvBoxes) launch_boxes(plan, at, op == DGB_OP_ADD ? 2 : 1, plan.hostRecv, plan.dRecvBoxes, plan.dRecvBuf, &plan.recvWaveEnd, stream);
+  DGB_CUDA(cudaGetLastError());
+  return DGB_OK;
+}
+
+// the exchange itself; `arrays` are device pointers
+int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays,
+             dgb_comm* comm, cudaStream_t stream) {
+  bool remote = false;
+  for (auto& s : plan.sendSeg) if (s.peer != myrank) remote = true;
+  for (auto& s : plan.recvSeg) if (s.peer != myrank) remote = true;
+  if (remote && !comm) return fail(DGB_EARG, "this exchange has remote partners: a dgb_comm is required");
+  if (int rc = plan_pack(plan, d_arrays, item_sizes, narrays, stream)) return rc;
+  int64_t bytes = 0;
+  if (remote) {
+    DGB_NCCL(g_nccl.GroupStart());
+    for (auto& s : plan.sendSeg) if (s.peer != myrank) { DGB_NCCL(g_nccl.Send(plan.dSendBuf + s.offset, s.count, ncclDouble, s.peer, comm->comm, stream)); bytes += s.count*8; }
+    for (auto& s : plan.recvSeg) if (s.peer != myrank) DGB_NCCL(g_nccl.Recv(plan.dRecvBuf + s.offset, s.count, ncclDouble, s.peer, comm->comm, stream));
+    DGB_NCCL(g_nccl.GroupEnd());
+  }
+  for (auto& s : plan.sendSeg) if (s.peer == myrank) {
+    for (auto& r : plan.recvSeg) if (r.peer == myrank) {
+      if (r.count != s.count) return fail(DGB_EGRID, "local sends/receives do not match in exchange");
+      DGB_CUDA(cudaMemcpyAsync(plan.dRecvBuf + r.offset, plan.dSendBuf + s.offset, s.count*sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    }
+  }
+  g->lastBytesSent = bytes;
+  return plan_unpack(plan, op, d_arrays, item_sizes, narrays, stream);
+}
+
+int get_plan(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir, const int32_t* item_sizes, int narrays,
+             std::shared_ptr<CommPlan>& out) {
+  std::ostringstream key;
+  key << level << '|' << iftype << '|' << dir;
+  for (int c = 0; c < 4; ++c) key << '|' << m.block[c] << ':' << m.offset[c];
+  for (int a = 0; a < narrays; ++a) key << '|' << item_sizes[a];
+  std::lock_guard<std::mutex> lk(g->mtx);
+  auto it = g->plans.find(key.str());
+  if (it == g->plans.end()) it = g->plans.emplace(key.str(), build_plan(g, level, m, iftype, dir, item_sizes, narrays)).first;
+  out = it->second;
+  return DGB_OK;
+}
+
+int nccl_allreduce(double* d, int op, dgb_comm* comm, cudaStream_t stream) {
+  if (!comm || comm->nranks == 1) return DGB_OK;
+  DGB_NCCL(g_nccl.AllReduce(d, d, 1, ncclDouble, op == 0 ? ncclMin : ncclMax, comm->comm, stream));
+  return DGB_OK;
+}
+
+} // namespace dgb
+
+using namespace dgb;
+
+extern "C" {
+
+int dgb_comm_unique_id(void* id128) {
+  if (!g_nccl.load()) return fail(DGB_ENCCL, g_nccl.error);
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  DGB_NCCL(g_nccl.GetUniqueId(reinterpret_cast<ncclUniqueId*>(id128)));
+  return DGB_OK;
+}
+
+int dgb_comm_init(const void* id128, int rank, int nranks, dgb_comm** out) {
+  if (int rc = require_device()) return rc;
+  if (!g_nccl.load()) return fail(DGB_ENCCL, g_nccl.error);
+  ncclUniqueId id; memcpy(&id, id128, sizeof(id));
+  ncclComm_t c;
+  DGB_NCCL(g_nccl.CommInitRank(&c, nranks, id, rank));
+  *out = new dgb_comm{c, rank, nranks};
+  return DGB_OK;
+}
+
+int dgb_comm_destroy(dgb_comm* c) {
+  if (!c) return DGB_OK;
+  g_nccl.CommDestroy(c->comm);
+  delete c;
+  return DGB_OK;
+}
+
+int dgb_communicate(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int dir, int op, double* const* d_arrays,
+                    const int32_t* item_sizes, int narrays, dgb_comm* comm, void* stream) {
+  return guarded([&]() -> int {
+    if (level < 0 || level >= int(g->me.levels.size())) throw RangeError("level out of range");
+    if (narrays < 1) throw ArgError("no arrays");
+    if (op != DGB_OP_SET && op != DGB_OP_ADD) throw ArgError("unknown combine op");
+    std::shared_ptr<CommPlan> plan;
+    if (int rc = get_plan(g, level, *m, iftype, dir, item_sizes, narrays, plan)) return rc;
+    return run_plan(g, *plan, g->me.rank, op, d_arrays, item_sizes, narrays, comm, (cudaStream_t)stream);
+  });
+}
+
+int dgb_comm_plan_info(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int dir, const int32_t* item_sizes, int narrays,
+                       int64_t* out, int cap) {
+  return guarded([&]() -> int {
+    if (level < 0 || level >= int(g->me.levels.size())) throw RangeError("level out of range");
+    std::shared_ptr<CommPlan> plan;
+    if (int rc = get_plan(g, level, *m, iftype, dir, item_sizes, narrays, plan)) return rc;
+    const int need = 2 + 3*int(plan->sendSeg.size() + plan->recvSeg.size());
+    if (cap < need) throw ArgError("plan_info: output too small");
+    out[0] = int64_t(plan->sendSeg.size()); out[1] = int64_t(plan->recvSeg.size());
+    int64_t* o = out + 2;
+    for (auto& s : plan->sendSeg) { *o++ = s.peer; *o++ = s.offset; *o++ = s.count; }
+    for (auto& s : plan->recvSeg) { *o++ = s.peer; *o++ = s.offset; *o++ = s.count; }
+    return DGB_OK;
+  });
+}
+
+int dgb_comm_pack(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int dir, double* const* d_arrays,
+                  const int32_t* item_sizes, int narrays, double** d_sendbuf, double** d_recvbuf, void* stream) {
+  return guarded([&]() -> int {
+    if (level < 0 || level >= int(g->me.levels.size())) throw RangeError("level out of range");
+    std::shared_ptr<CommPlan> plan;
+    if (int rc = get_plan(g, level, *m, iftype, dir, item_sizes, narrays, plan)) return rc;
+    if (int rc = plan_pack(*plan, d_arrays, item_sizes, narrays, (cudaStream_t)stream)) return rc;
+    if (d_sendbuf) *d_sendbuf = plan->dSendBuf;
+    if (d_recvbuf) *d_recvbuf = plan->dRecvBuf;
+    return DGB_OK;
+  });
+}
+
+int dgb_comm_unpack(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int dir, int op, double* const* d_arrays,
+                    const int32_t* item_sizes, int narrays, void* stream) {
+  return guarded([&]() -> int {
+    if (level < 0 || level >= int(g->me.levels.size())) throw RangeError("level out of range");
+    if (op != DGB_OP_SET && op != DGB_OP_ADD) throw ArgError("unknown combine op");
+    std::shared_ptr<CommPlan> plan;
+    if (int rc = get_plan(g, level, *m, iftype, dir, item_sizes, narrays, plan)) return rc;
+    return plan_unpack(*plan, op, d_arrays, item_sizes, narrays, (cudaStream_t)stream);
+  });
+}
+
+int dgb_allreduce_min(double* d_value, dgb_comm* comm, void* stream) { return nccl_allreduce(d_value, 0, comm, (cudaStream_t)stream); }
+int dgb_allreduce_max(double* d_value, dgb_comm* comm, void* stream) { return nccl_allreduce(d_value, 1, comm, (cudaStream_t)stream); }
+
+} // extern "C"

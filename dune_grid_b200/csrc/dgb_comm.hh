@@ -1,0 +1,42 @@
+// dgb_comm.hh — exchange plan shared between dgb_comm.cu and dgb_fv.cu (internal).
+#ifndef DGB_COMM_HH
+#define DGB_COMM_HH
+#include <memory>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/dgb.h"
+
+struct dgb_grid;
+struct dgb_comm;
+
+namespace dgb {
+// one box of an exchange plan: the entities of a sub-box of one shift component
+struct PlanBox {
+  int origin[3], size[3];
+  int of_origin[3], of_size[3];     // enclosing overlapfront box of the component
+  long long buf_offset;             // first double of this box in the send/recv buffer
+  long long count;                  // entities
+  unsigned index_base;              // mapper: index = (component offset + local superindex)*block + offset
+  unsigned block, map_offset;
+};
+struct CommPlan {
+  struct Segment { int peer; long long offset, count; };     // doubles
+  std::vector<Segment> sendSeg, recvSeg;
+  long long sendTotal = 0, recvTotal = 0, maxSendBox = 0, maxRecvBox = 0;
+  int nSendBoxes = 0, nRecvBoxes = 0, items = 0;
+  std::vector<PlanBox> hostSend, hostRecv;               // hostRecv is ordered by unpack wave
+  std::vector<int> recvWaveEnd;                          // end index (exclusive) of each wave in hostRecv
+  PlanBox* dSendBoxes = nullptr; PlanBox* dRecvBoxes = nullptr;
+  double* dSendBuf = nullptr; double* dRecvBuf = nullptr;
+  bool uploaded = false;
+  long long launches = 0;
+  int upload();
+  ~CommPlan();
+};
+int get_plan(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir, const int32_t* item_sizes, int narrays,
+             std::shared_ptr<CommPlan>& out);
+int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays,
+             dgb_comm* comm, cudaStream_t stream);
+int nccl_allreduce(double* d, int op /*0 min, 1 max*/, dgb_comm* comm, cudaStream_t stream);
+}
+#endif

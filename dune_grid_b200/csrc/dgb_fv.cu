@@ -1,0 +1,389 @@
+// dgb_fv.cu — the explicit first-order upwind finite-volume transport step as ONE
+// fused device kernel per time step: element loop + intersection loop + mapper index arithmetic + axis-aligned
+// geometry + CFL reduction, followed by communicate(InteriorBorder_All_Interface, ForwardCommunication).
+//
+// CPU structure being replaced (dune-grid-howto style, restated in oracle/ref/ref_driver.cc fvRun): pass 1 walks
+// elements(gv, interior) and intersections(gv,e), writes update[i] and the local dt; comm().min(dt); pass 2 does
+// c += dt*update; then gv.communicate(...). Bytes per cell there: read c + neighbours, write update, read update,
+// read+write c = 40 B. Here: read c (8 B) + write c_new (8 B) = 16 B per cell per step; neighbour values come from
+// L1/L2. The CFL bound depends only on geometry and velocity (not on c), so the kernel of step n also reduces
+// max_i(sum of outflow factors) for step n+1 (velocities are time independent); one geometry-only bootstrap
+// reduction precedes the first step. min_i fl(1/s_i) == fl(1/max_i s_i) because correctly rounded division is monotone.
+#include "dgb_internal.hh"
+#include "dgb_device.cuh"
+#include "dgb_comm.hh"
+
+namespace dgb {
+
+struct FvProblem { int id; double p[12]; };
+
+// velocity, inflow value and initial value: device restatement of oracle/common/fv_problem.hh
+template<int DIM>
+__device__ __forceinline__ void fv_velocity(const FvProblem& q, const double* x, double* u) {
+  if (q.id == 1) {
+    u[0] = -q.p[0]*(x[1]-0.5);
+    u[1] =  q.p[0]*(x[0]-0.5);
+    if (DIM > 2) u[2] = 0.0;
+  } else {
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) u[i] = q.p[i];
+  }
+}
+__device__ __forceinline__ double fv_boundary(const FvProblem& q, const double*) { return q.p[3]; }
+template<int DIM>
+__device__ __forceinline__ double fv_initial(const FvProblem& q, const double* x) {
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) { const double d = x[i]-q.p[4+i]; s += d*d; }
+  const double r = sqrt(s);
+  return (r > q.p[7] && r < q.p[8]) ? 1.0 : 0.0;
+}
+
+static constexpr int FBX = 128, FBY = 4;
+
+struct FvRegion { int origin[3], size[3]; };         // cells to update (a sub-box of the interior box)
+
+// per-axis tables for DGB_FV_SEPARABLE: reciprocal cell widths, cell centres and vertex coordinates
+struct FvTables { const double* rw[3]; const double* xc[3]; const double* xv[3]; int first[3]; };
+
+struct FvArgs {
+  FvRegion region;
+  FvProblem problem;
+  FvTables tab;
+  const double* c;       // field at t_n, indexed by the element index (overlapfront array)
+  double* cnew;          // field at t_{n+1} (NULL: reduction only)
+  double* update;        // optional: materialise the update array
+  const double* slotIn;  // max_i sum_out of this step (produced by the previous launch)
+  double* slotOut;       // max_i sum_out for the next step
+  double* slotZero;      // slot to clear for the step after next
+  double* dtOut;         // dt actually used
+};
+
+// EXACT: the arithmetic of the per-entity CPU loop, operation by operation (bit-identical results).
+// SEPARABLE: face factor (u.n)|F|/|V| = (u.n)/w_dir taken from per-axis reciprocal tables (<= 2 ulp difference).
+template<int DIM, int MODE, bool REDUCE_ONLY>
+__global__ void __launch_bounds__(FBX*FBY) k_fv_step(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a) {
+  const int i0 = blockIdx.x*FBX + threadIdx.x;
+  const int i1 = blockIdx.y*FBY + threadIdx.y;
+  const int i2 = blockIdx.z;
+  const bool active = i0 < a.region.size[0] && i1 < a.region.size[1];
+  double sum = 0.0;
+  if (active) {
+    const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+    int coord[3];
+    coord[0] = a.region.origin[0] + i0; coord[1] = a.region.origin[1] + i1; coord[2] = DIM > 2 ? a.region.origin[2] + i2 : 0;
+    long long stride[3]; stride[0] = 1; stride[1] = of.size[0]; stride[2] = (long long)of.size[0]*of.size[1];
+    long long idx = 0;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) idx += (coord[i]-of.origin[i])*stride[i];
+    double ll[DIM], ur[DIM], w[DIM], xc[DIM], rw[DIM];
+    double vol = 1.0;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      if (MODE == DGB_FV_SEPARABLE) {
+        const int t = coord[i]-a.tab.first[i];
+        ll[i] = __ldg(a.tab.xv[i]+t); ur[i] = __ldg(a.tab.xv[i]+t+1);
+        xc[i] = __ldg(a.tab.xc[i]+t); rw[i] = __ldg(a.tab.rw[i]+t);
+      } else {
+        ll[i] = vertex_coord(v, i, coord[i]); ur[i] = vertex_coord(v, i, coord[i]+1);
+        w[i] = ur[i]-ll[i]; vol *= w[i];
+        xc[i] = 0.5*(ll[i]+ur[i]);
+      }
+    }
+    const double ci = REDUCE_ONLY ? 0.0 : __ldg(a.c + idx);
+    double upd = 0.0;
+#pragma unroll
+    for (int dir = 0; dir < DIM; ++dir) {
+      double area = 1.0;
+      if (MODE == DGB_FV_EXACT) {
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) if (i != dir) area *= w[i];
+      }
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        double fc[DIM], u[DIM];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) fc[i] = (i == dir) ? (side ? ur[i] : ll[i]) : xc[i];
+        fv_velocity<DIM>(a.problem, fc, u);
+        const double un = side ? u[dir] : -u[dir];
+        const double factor = (MODE == DGB_FV_EXACT) ? (un*area)/vol : un*rw[dir];
+        if (factor >= 0.0) {
+          sum += factor;
+          if (!REDUCE_ONLY) upd -= ci*factor;
+        } else if (!REDUCE_ONLY) {
+          if (face_neighbor(v, coord, dir, side)) {
+            const double cj = __ldg(a.c + idx + (side ? stride[dir] : -stride[dir]));
+            upd -= cj*factor;
+          } else if (face_boundary(v, coord, dir, side)) {
+            upd -= fv_boundary(a.problem, fc)*factor;
+          }
+        }
+      }
+    }
+    if (!REDUCE_ONLY) {
+      const double dt = 0.99*(1.0/(*a.slotIn));
+      if (a.update) a.update[idx] = upd;
+      if (a.cnew) a.cnew[idx] = ci + dt*upd;
+      if (a.dtOut && i0 == 0 && i1 == 0 && i2 == 0) *a.dtOut = dt;
+    }
+  }
+  // block max of the outflow sums -> one atomic per block (warp shuffles, then shared memory across the warps)
+  for (int off = 16; off > 0; off >>= 1) sum = fmax(sum, __shfl_down_sync(0xffffffffu, sum, off));
+  __shared__ double part[FBX*FBY/32];
+  const int tid = threadIdx.y*FBX + threadIdx.x;
+  if ((tid & 31) == 0) part[tid >> 5] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int k = 0; k < FBX*FBY/32; ++k) m = fmax(m, part[k]);
+    if (m > 0.0) atomic_max_nonneg(a.slotOut, m);
+    if (a.slotZero && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *a.slotZero = 0.0;
+  }
+}
+
+// initial condition at the cell centres of all stored cells (geometry().center(), periodic wrap included)
+template<int DIM>
+__global__ void __launch_bounds__(FBX*FBY) k_fv_init(const __grid_constant__ dgb_view v, const FvProblem q, double* c) {
+  const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+  const int i0 = blockIdx.x*FBX + threadIdx.x, i1 = blockIdx.y*FBY + threadIdx.y, i2 = blockIdx.z;
+  if (i0 >= of.size[0] || i1 >= of.size[1]) return;
+  int coord[3] = { of.origin[0]+i0, of.origin[1]+i1, DIM > 2 ? of.origin[2]+i2 : 0 };
+  double x[DIM];
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) {
+    const double sh = periodic_shift(v, i, coord[i]);
+    double lo = vertex_coord(v, i, coord[i]), hi = vertex_coord(v, i, coord[i]+1);
+    if (sh != 0.0) { lo += sh; hi += sh; }
+    x[i] = 0.5*(lo+hi);
+  }
+  c[((long long)i2*of.size[1] + i1)*of.size[0] + i0] = fv_initial<DIM>(q, x);
+}
+
+// per-axis tables of the separable mode
+__global__ void k_fv_tables(const __grid_constant__ dgb_view v, int axis, int first, int ncells, double* rw, double* xc, double* xv) {
+  const int t = blockIdx.x*blockDim.x + threadIdx.x;
+  if (t > ncells) return;
+  const double lo = vertex_coord(v, axis, first+t);
+  xv[t] = lo;
+  if (t < ncells) {
+    const double hi = vertex_coord(v, axis, first+t+1);
+    rw[t] = 1.0/(hi-lo);
+    xc[t] = 0.5*(lo+hi);
+  }
+}
+
+} // namespace dgb
+
+using namespace dgb;
+
+struct dgb_fv {
+  dgb_grid* grid = nullptr;
+  dgb_comm* comm = nullptr;
+  int level = 0, mode = 0;
+  dgb_view view;
+  dgb_mapper mapper;
+  FvProblem problem;
+  FvTables tab;
+  double* dTables = nullptr;
+  double* dSlots = nullptr;        // 3 rotating max-sum slots + dt
+  long long step = 0;
+  bool bootstrapped = false;
+  int64_t launches = 0;
+  std::shared_ptr<CommPlan> plan;
+  double* dStage[2] = {nullptr, nullptr};     // device staging for the host-buffer entry point
+  size_t stageBytes = 0;
+};
+
+namespace dgb {
+
+template<bool REDUCE_ONLY>
+static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
+  const dgb_view& v = fv->view;
+  dim3 block(FBX, FBY, 1);
+  dim3 grid((a.region.size[0]+FBX-1)/FBX, (a.region.size[1]+FBY-1)/FBY, v.dim > 2 ? a.region.size[2] : 1);
+  if (a.region.size[0] <= 0 || a.region.size[1] <= 0 || (v.dim > 2 && a.region.size[2] <= 0)) return DGB_OK;
+  if (v.dim == 3) {
+    if (fv->mode == DGB_FV_EXACT) k_fv_step<3, DGB_FV_EXACT, REDUCE_ONLY><<<grid, block, 0, stream>>>(v, a);
+    else k_fv_step<3, DGB_FV_SEPARABLE, REDUCE_ONLY><<<grid, block, 0, stream>>>(v, a);
+  } else {
+    if (fv->mode == DGB_FV_EXACT) k_fv_step<2, DGB_FV_EXACT, REDUCE_ONLY><<<grid, block, 0, stream>>>(v, a);
+    else k_fv_step<2, DGB_FV_SEPARABLE, REDUCE_ONLY><<<grid, block, 0, stream>>>(v, a);
+  }
+  ++fv->launches;
+  DGB_CUDA(cudaGetLastError());
+  return DGB_OK;
+}
+
+static FvArgs base_args(dgb_fv* fv) {
+  FvArgs a{};
+  const dgb_box& in = fv->view.comp[0].box[DGB_BOX_INTERIOR];
+  for (int i = 0; i < 3; ++i) { a.region.origin[i] = in.origin[i]; a.region.size[i] = i < fv->view.dim ? in.size[i] : 1; }
+  a.problem = fv->problem; a.tab = fv->tab;
+  return a;
+}
+
+// geometry-only reduction that seeds the first step's dt
+static int bootstrap(dgb_fv* fv, cudaStream_t stream) {
+  DGB_CUDA(cudaMemsetAsync(fv->dSlots, 0, 4*sizeof(double), stream));
+  FvArgs a = base_args(fv);
+  a.slotOut = fv->dSlots + 0;
+  if (int rc = launch_step<true>(fv, a, stream)) return rc;
+  if (int rc = nccl_allreduce(fv->dSlots + 0, 1, fv->comm, stream)) return rc;
+  fv->bootstrapped = true; fv->step = 0;
+  return DGB_OK;
+}
+
+} // namespace dgb
+
+extern "C" {
+
+int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host, int nparams, int mode, dgb_comm* comm, dgb_fv** out) {
+  return guarded([&]() -> int {
+    if (int rc = require_device()) return rc;
+    if (problem < 0 || problem > 1) throw ArgError("unknown problem id");
+    if (mode != DGB_FV_EXACT && mode != DGB_FV_SEPARABLE) throw ArgError("unknown fv mode");
+    if (nparams > 12) throw ArgError("at most 12 problem parameters");
+    std::unique_ptr<dgb_fv> fv(new dgb_fv);
+    fv->grid = g; fv->comm = comm; fv->level = level; fv->mode = mode;
+    if (int rc = make_view(g, level, &fv->view)) return rc;
+    if (g->me.nranks > 1 && !comm) throw ArgError("a dgb_comm is required on a multi-rank grid");
+    const uint32_t block[4] = {1,0,0,0};
+    dgb_mapper_init(&fv->view, block, &fv->mapper);
+    fv->problem.id = problem;
+    for (int i = 0; i < 12; ++i) fv->problem.p[i] = i < nparams ? params_host[i] : 0.0;
+    DGB_CUDA(cudaMalloc(&fv->dSlots, 4*sizeof(double)));
+    DGB_CUDA(cudaMemset(fv->dSlots, 0, 4*sizeof(double)));
+    // per-axis tables over the stored cell range
+    const dgb_view& v = fv->view;
+    const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+    size_t total = 0;
+    for (int i = 0; i < v.dim; ++i) total += 3*(size_t(of.size[i])+1);
+    DGB_CUDA(cudaMalloc(&fv->dTables, total*sizeof(double)));
+    double* p = fv->dTables;
+    for (int i = 0; i < 3; ++i) { fv->tab.rw[i] = fv->tab.xc[i] = fv->tab.xv[i] = nullptr; fv->tab.first[i] = 0; }
+    for (int i = 0; i < v.dim; ++i) {
+      const int n = of.size[i];
+      double* rw = p; double* xc = p + (n+1); double* xv = p + 2*(n+1);
+      p += 3*(n+1);
+      k_fv_tables<<<(n+1+127)/128, 128>>>(v, i, of.origin[i], n, rw, xc, xv);
+      fv->tab.rw[i] = rw; fv->tab.xc[i] = xc; fv->tab.xv[i] = xv; fv->tab.first[i] = of.origin[i];
+      ++fv->launches;
+    }
+    DGB_CUDA(cudaGetLastError());
+    DGB_CUDA(cudaDeviceSynchronize());
+    const int32_t items[1] = {1};
+    if (int rc = get_plan(g, level, fv->mapper, DGB_InteriorBorder_All_Interface, DGB_ForwardCommunication, items, 1, fv->plan)) return rc;
+    *out = fv.release();
+    return DGB_OK;
+  });
+}
+
+int dgb_fv_destroy(dgb_fv* fv) {
+  if (!fv) return DGB_OK;
+  if (fv->dSlots) cudaFree(fv->dSlots);
+  if (fv->dTables) cudaFree(fv->dTables);
+  for (int i = 0; i < 2; ++i) if (fv->dStage[i]) cudaFree(fv->dStage[i]);
+  delete fv;
+  return DGB_OK;
+}
+
+int dgb_fv_init_field(dgb_fv* fv, double* d_c, void* stream) {
+  const dgb_view& v = fv->view;
+  if (v.coord_mode == DGB_COORD_TENSORPRODUCT) for (int i = 0; i < v.dim; ++i) if (!v.tensor[i]) return fail(DGB_ECUDA, "tensor coordinates are not on the device");
+  const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+  dim3 block(FBX, FBY, 1), grid((of.size[0]+FBX-1)/FBX, (of.size[1]+FBY-1)/FBY, v.dim > 2 ? of.size[2] : 1);
+  if (v.dim == 3) k_fv_init<3><<<grid, block, 0, (cudaStream_t)stream>>>(v, fv->problem, d_c);
+  else k_fv_init<2><<<grid, block, 0, (cudaStream_t)stream>>>(v, fv->problem, d_c);
+  ++fv->launches;
+  DGB_CUDA(cudaGetLastError());
+  return DGB_OK;
+}
+
+int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!fv->bootstrapped) if (int rc = bootstrap(fv, stream)) return rc;
+  const long long n = fv->step;
+  FvArgs a = base_args(fv);
+  a.c = d_c_in; a.cnew = d_c_out;
+  a.slotIn = fv->dSlots + (n % 3); a.slotOut = fv->dSlots + ((n+1) % 3); a.slotZero = fv->dSlots + ((n+2) % 3);
+  a.dtOut = fv->dSlots + 3;
+  if (int rc = launch_step<false>(fv, a, stream)) return rc;
+  if (int rc = nccl_allreduce(fv->dSlots + ((n+1) % 3), 1, fv->comm, stream)) return rc;
+  // refresh the overlap cells of c_out: communicate(InteriorBorder_All_Interface, ForwardCommunication), set
+  if (fv->plan->nSendBoxes || fv->plan->nRecvBoxes) {
+    const int32_t items[1] = {1};
+    double* arrays[1] = { d_c_out };
+    const long long before = fv->plan->launches;
+    if (int rc = run_plan(fv->grid, *fv->plan, fv->view.rank, DGB_OP_SET, arrays, items, 1, fv->comm, stream)) return rc;
+    fv->launches += fv->plan->launches - before;
+  }
+  fv->step = n+1;
+  return DGB_OK;
+}
+
+int dgb_fv_bootstrap_local(dgb_fv* fv, double** d_pending_max, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DGB_CUDA(cudaMemsetAsync(fv->dSlots, 0, 4*sizeof(double), stream));
+  FvArgs a = base_args(fv);
+  a.slotOut = fv->dSlots + 0;
+  if (int rc = launch_step<true>(fv, a, stream)) return rc;
+  fv->bootstrapped = true; fv->step = 0;
+  if (d_pending_max) *d_pending_max = fv->dSlots + 0;
+  return DGB_OK;
+}
+
+int dgb_fv_step_local(dgb_fv* fv, const double* d_c_in, double* d_c_out, double** d_pending_max, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!fv->bootstrapped) return fail(DGB_EARG, "dgb_fv_step_local: call dgb_fv_bootstrap_local (and reduce its result over ranks) first");
+  const long long n = fv->step;
+  FvArgs a = base_args(fv);
+  a.c = d_c_in; a.cnew = d_c_out;
+  a.slotIn = fv->dSlots + (n % 3); a.slotOut = fv->dSlots + ((n+1) % 3); a.slotZero = fv->dSlots + ((n+2) % 3);
+  a.dtOut = fv->dSlots + 3;
+  if (int rc = launch_step<false>(fv, a, stream)) return rc;
+  if (d_pending_max) *d_pending_max = fv->dSlots + ((n+1) % 3);
+  fv->step = n+1;
+  return DGB_OK;
+}
+
+int dgb_fv_update(dgb_fv* fv, const double* d_c_in, double* d_update, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!fv->bootstrapped) if (int rc = bootstrap(fv, stream)) return rc;
+  // same kernel, update array materialised, nothing advanced: the reduction goes to a scratch slot that is re-zeroed
+  const long long n = fv->step;
+  FvArgs a = base_args(fv);
+  a.c = d_c_in; a.update = d_update;
+  a.slotIn = fv->dSlots + (n % 3); a.slotOut = fv->dSlots + ((n+2) % 3); a.dtOut = fv->dSlots + 3;
+  if (int rc = launch_step<false>(fv, a, stream)) return rc;
+  DGB_CUDA(cudaMemsetAsync(fv->dSlots + ((n+2) % 3), 0, sizeof(double), stream));
+  return DGB_OK;
+}
+
+int dgb_fv_last_dt(dgb_fv* fv, double* dt_host, void* stream) {
+  DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 3, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  DGB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return DGB_OK;
+}
+
+int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* dt_host, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int64_t n = 0; dgb_view_size(&fv->view, 0, &n);
+  const size_t bytes = size_t(n)*sizeof(double);
+  if (fv->stageBytes < bytes) {
+    for (int i = 0; i < 2; ++i) { if (fv->dStage[i]) cudaFree(fv->dStage[i]); fv->dStage[i] = nullptr; }
+    DGB_CUDA(cudaMalloc(&fv->dStage[0], bytes));
+    DGB_CUDA(cudaMalloc(&fv->dStage[1], bytes));
+    fv->stageBytes = bytes;
+  }
+  DGB_CUDA(cudaMemcpyAsync(fv->dStage[0], h_c_in, bytes, cudaMemcpyHostToDevice, stream));
+  // every stored cell of the result is written: interior cells by the kernel, overlap cells by the exchange
+  if (int rc = dgb_fv_step(fv, fv->dStage[0], fv->dStage[1], stream)) return rc;
+  DGB_CUDA(cudaMemcpyAsync(h_c_out, fv->dStage[1], bytes, cudaMemcpyDeviceToHost, stream));
+  if (dt_host) DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 3, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  DGB_CUDA(cudaStreamSynchronize(stream));
+  return DGB_OK;
+}
+
+int dgb_fv_launch_count(const dgb_fv* fv, int64_t* kernels) { *kernels = fv->launches; return DGB_OK; }
+
+} // extern "C"

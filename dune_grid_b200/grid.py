@@ -1,0 +1,447 @@
+"""Host-side mirror of the reference's operator surface for the YaspGrid leaf-sweep path, on top of the
+C ABI (include/dgb.h). Names follow dune-grid: YaspGrid(...).leafGridView()/levelGridView(l), GridView.size,
+.elements(), .intersections(), .communicate(), MultipleCodimMultipleGeomTypeMapper(gv, layout).index()/size(),
+geometry().global_()/jacobianInverseTransposed()/integrationElement(). Per-entity calls of the reference
+(dune/grid/common/gridview.hh, entity.hh, intersection.hh, geometry.hh, mcmgmapper.hh) become per-view bulk
+calls that return CUDA tensors in the reference's iteration order. torch is only the allocator / stream
+provider here; all arithmetic happens in libdgb.so's CUDA kernels."""
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import check, lib
+
+# dune/grid/common/gridenums.hh
+(Interior_Partition, InteriorBorder_Partition, Overlap_Partition, OverlapFront_Partition, All_Partition,
+ Ghost_Partition) = range(6)
+InteriorEntity, BorderEntity, OverlapEntity, FrontEntity, GhostEntity = range(5)
+(InteriorBorder_InteriorBorder_Interface, InteriorBorder_All_Interface, Overlap_OverlapFront_Interface,
+ Overlap_All_Interface, All_All_Interface) = range(5)
+ForwardCommunication, BackwardCommunication = 0, 1
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise capi.DgbError(capi.ECUDA, "no CUDA device: dune_grid_b200 has no CPU fallback")
+
+
+class YaspGrid:
+    """Dune::YaspGrid<dim, Coordinates> (dune/grid/yaspgrid.hh:164). coordinates: 'equidistant'
+    (L=upper), 'equidistantoffset' (lower, upper) or 'tensorproduct' (coords = list of arrays)."""
+
+    def __init__(self, dim=None, N=None, upper=None, lower=None, coords=None, periodic=0, overlap=1,
+                 coordinates="equidistant", rank=0, nranks=1, partitioner="default", fixed_dims=None, comm=None):
+        mode = {"equidistant": 0, "equidistantoffset": 1, "tensorproduct": 2}[coordinates]
+        s = capi.GridSpec()
+        self._keep = []
+        if mode == 2:
+            dim = len(coords)
+            N = [len(c) - 1 for c in coords]
+            for i, c in enumerate(coords):
+                a = np.ascontiguousarray(c, dtype=np.float64)
+                self._keep.append(a)
+                s.tensor[i] = a.ctypes.data_as(C.POINTER(C.c_double))
+        s.dim, s.coord_mode = dim, mode
+        if isinstance(periodic, (list, tuple)):
+            periodic = sum(1 << i for i, p in enumerate(periodic) if p)
+        for i in range(3):
+            s.N[i] = N[i] if i < dim else 1
+            s.lower[i] = (lower[i] if lower is not None and i < dim else 0.0)
+            s.upper[i] = (upper[i] if upper is not None and i < dim else 1.0)
+            s.fixed_dims[i] = fixed_dims[i] if fixed_dims is not None and i < dim else 1
+        s.periodic, s.overlap = periodic, overlap
+        s.partitioner = {"default": 0, "powerd": 1, "fixed": 2}[partitioner]
+        self.dim, self.rank, self.nranks, self.comm = dim, rank, nranks, comm
+        self.spec = s
+        self.h = C.c_void_p()
+        check(lib.dgb_grid_create(C.byref(s), rank, nranks, C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib.dgb_grid_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def refineOptions(self, keepPhysicalOverlap: bool):
+        check(lib.dgb_grid_refine_options(self.h, int(keepPhysicalOverlap)))
+
+    def globalRefine(self, refCount: int):
+        check(lib.dgb_grid_global_refine(self.h, refCount))
+
+    @property
+    def maxLevel(self):
+        m = C.c_int(0)
+        check(lib.dgb_grid_max_level(self.h, C.byref(m)))
+        return m.value
+
+    def torusDims(self):
+        d = (C.c_int32 * 3)(1, 1, 1)
+        check(lib.dgb_grid_torus_dims(self.h, d))
+        return tuple(d)[:self.dim]
+
+    def numBoundarySegments(self):
+        n = C.c_int64(0)
+        check(lib.dgb_grid_num_boundary_segments(self.h, C.byref(n)))
+        return n.value
+
+    def domainSize(self):
+        d = (C.c_double * 3)()
+        check(lib.dgb_grid_domain_size(self.h, d))
+        return np.array(d[:self.dim])
+
+    def leafGridView(self):
+        return GridView(self, None)
+
+    def levelGridView(self, level):
+        return GridView(self, level)
+
+    def commList(self, level, codim, which):
+        cap = 4096
+        out = (C.c_int32 * (cap * 10))()
+        n = C.c_int(0)
+        check(lib.dgb_view_comm_list(self.h, level, codim, which, out, cap, C.byref(n)))
+        return np.ctypeslib.as_array(out)[:n.value * 10].reshape(n.value, 10).copy()
+
+
+class GridView:
+    """Dune::GridView of a YaspGrid level (leaf == finest level; dune/grid/common/gridview.hh:65-398)."""
+
+    def __init__(self, grid: YaspGrid, level: Optional[int]):
+        self.grid = grid
+        self.v = capi.View()
+        if level is None:
+            check(lib.dgb_view_leaf(grid.h, C.byref(self.v)))
+        else:
+            check(lib.dgb_view_level(grid.h, level, C.byref(self.v)))
+        self.dim, self.level = self.v.dim, self.v.level
+
+    def size(self, codim, partition=All_Partition):
+        n = C.c_int64(0)
+        check(lib.dgb_view_partition_size(C.byref(self.v), codim, partition, C.byref(n)))
+        return n.value
+
+    def overlapSize(self, codim=0):
+        n = C.c_int(0)
+        check(lib.dgb_view_overlap_size(C.byref(self.v), codim, C.byref(n)))
+        return n.value
+
+    def ghostSize(self, codim=0):
+        return 0
+
+    def boxes(self, codim):
+        """host view of the nested partition boxes (for tests): list of dicts per shift component"""
+        v, res = self.v, []
+        for j in range(v.comp_begin[codim], v.comp_begin[codim + 1]):
+            c = v.comp[j]
+            d = {"shift": c.shift, "offset": c.index_offset[0]}
+            for q, name in enumerate(["overlapfront", "overlap", "interiorborder", "interior"]):
+                d[name] = (tuple(c.box[q].origin), tuple(c.box[q].size))
+            res.append(d)
+        return res
+
+    def coordinates(self, axis):
+        """vertex coordinates along `axis` over the stored vertex range (host arithmetic of the descriptor)"""
+        v = self.v
+        b = v.comp[v.comp_begin[self.dim]].box[0]
+        first, n = b.origin[axis], b.size[axis]
+        idx = np.arange(first, first + n)
+        if v.coord_mode == 0:
+            return first, idx * v.h[axis]
+        if v.coord_mode == 1:
+            return first, v.origin[axis] + idx * v.h[axis]
+        arr = np.ctypeslib.as_array(v.tensor_host[axis], shape=(v.tensor_size[axis],))
+        return first, arr[idx - v.tensor_offset[axis]].copy()
+
+    # ---- bulk sweeps -----------------------------------------------------------------------------------------
+    def elements(self, codim=0, partition=All_Partition, geometry=True, coord=False):
+        """for (e : elements(gv, partition)) -> dict of CUDA tensors: index, partitionType, [coord], lower, upper,
+        center (dim x n), volume"""
+        _require_cuda()
+        torch = _torch()
+        n, d = self.size(codim, partition), self.dim
+        dev = "cuda"
+        r = {"index": torch.empty(n, dtype=torch.int32, device=dev), "partitionType": torch.empty(n, dtype=torch.uint8, device=dev)}
+        if coord:
+            r["coord"] = torch.empty((d, n), dtype=torch.int32, device=dev)
+        if geometry:
+            for k in ("lower", "upper", "center"):
+                r[k] = torch.empty((d, n), dtype=torch.float64, device=dev)
+            r["volume"] = torch.empty(n, dtype=torch.float64, device=dev)
+        check(lib.dgb_elements_materialize(C.byref(self.v), codim, partition, _ptr(r["index"]), _ptr(r["partitionType"]),
+                                           _ptr(r.get("coord")), _ptr(r.get("lower")), _ptr(r.get("upper")),
+                                           _ptr(r.get("center")), _ptr(r.get("volume")), _stream()))
+        return r
+
+    def intersections(self, partition=All_Partition, geometry=True):
+        """for (is : intersections(gv, e)) for all cells: neighbor, boundary, outside (index or -1),
+        boundarySegmentIndex (or -1): (2dim x n); center (2dim x dim x n), volume (2dim x n)"""
+        _require_cuda()
+        torch = _torch()
+        n, d = self.size(0, partition), self.dim
+        dev = "cuda"
+        r = {"neighbor": torch.empty((2 * d, n), dtype=torch.uint8, device=dev),
+             "boundary": torch.empty((2 * d, n), dtype=torch.uint8, device=dev),
+             "outside": torch.empty((2 * d, n), dtype=torch.int32, device=dev),
+             "boundarySegmentIndex": torch.empty((2 * d, n), dtype=torch.int32, device=dev)}
+        if geometry:
+            r["center"] = torch.empty((2 * d, d, n), dtype=torch.float64, device=dev)
+            r["volume"] = torch.empty((2 * d, n), dtype=torch.float64, device=dev)
+        check(lib.dgb_intersections_materialize(C.byref(self.v), partition, _ptr(r["neighbor"]), _ptr(r["boundary"]),
+                                                _ptr(r["outside"]), _ptr(r["boundarySegmentIndex"]),
+                                                _ptr(r.get("center")), _ptr(r.get("volume")), _stream()))
+        return r
+
+    def centerUnitOuterNormal(self, k):
+        """YaspIntersection::centerUnitOuterNormal (yaspgridintersection.hh:177-182): +-e_dir, independent of the cell"""
+        n = np.zeros(self.dim)
+        n[k // 2] = 1.0 if k % 2 else -1.0
+        return n
+
+    def geometry(self, qp, partition=All_Partition):
+        """Geometry::global / jacobianInverseTransposed / integrationElement at local points qp (nqp x dim)"""
+        _require_cuda()
+        torch = _torch()
+        qp = np.ascontiguousarray(qp, dtype=np.float64).reshape(-1, self.dim)
+        n, d, nq = self.size(0, partition), self.dim, qp.shape[0]
+        r = {"global": torch.empty((nq, d, n), dtype=torch.float64, device="cuda"),
+             "jacobianInverseTransposed": torch.empty((nq, d, d, n), dtype=torch.float64, device="cuda"),
+             "integrationElement": torch.empty((nq, n), dtype=torch.float64, device="cuda")}
+        check(lib.dgb_geometry_eval(C.byref(self.v), partition, nq, qp.ctypes.data_as(C.POINTER(C.c_double)), _ptr(r["global"]),
+                                    _ptr(r["jacobianInverseTransposed"]), _ptr(r["integrationElement"]), _stream()))
+        return r
+
+    def geometryGrid(self, deformation, params, qp, partition=All_Partition, corners=True):
+        """GeometryGrid<YaspGrid, F> geometries: corners (2^dim x dim x n), global, jacobianTransposed,
+        jacobianInverseTransposed, integrationElement at local points qp"""
+        _require_cuda()
+        torch = _torch()
+        qp = np.ascontiguousarray(qp, dtype=np.float64).reshape(-1, self.dim)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        n, d, nq = self.size(0, partition), self.dim, qp.shape[0]
+        r = {"global": torch.empty((nq, d, n), dtype=torch.float64, device="cuda"),
+             "jacobianTransposed": torch.empty((nq, d, d, n), dtype=torch.float64, device="cuda"),
+             "jacobianInverseTransposed": torch.empty((nq, d, d, n), dtype=torch.float64, device="cuda"),
+             "integrationElement": torch.empty((nq, n), dtype=torch.float64, device="cuda")}
+        if corners:
+            r["corners"] = torch.empty((1 << d, d, n), dtype=torch.float64, device="cuda")
+        check(lib.dgb_geogrid_eval(C.byref(self.v), partition, deformation, params.ctypes.data_as(C.POINTER(C.c_double)), params.size,
+                                   nq, qp.ctypes.data_as(C.POINTER(C.c_double)), _ptr(r.get("corners")), _ptr(r["global"]),
+                                   _ptr(r["jacobianTransposed"]), _ptr(r["jacobianInverseTransposed"]),
+                                   _ptr(r["integrationElement"]), _stream()))
+        return r
+
+    def geometryGridVolume(self, deformation, params, qp, weights, partition=All_Partition):
+        _require_cuda()
+        torch = _torch()
+        qp = np.ascontiguousarray(qp, dtype=np.float64).reshape(-1, self.dim)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        out = torch.zeros(1, dtype=torch.float64, device="cuda")
+        check(lib.dgb_geogrid_volume(C.byref(self.v), partition, deformation, params.ctypes.data_as(C.POINTER(C.c_double)), params.size,
+                                     qp.shape[0], qp.ctypes.data_as(C.POINTER(C.c_double)), w.ctypes.data_as(C.POINTER(C.c_double)),
+                                     _ptr(out), _stream()))
+        return out
+
+    def communicate(self, mapper, arrays, iftype, direction, op="set", item_sizes=None):
+        """gv.communicate(dataHandle, iftype, dir) with the data handle 'arrays indexed by mapper' and the
+        combine operation op in {'set','add'} (dune/python/grid/mapper.hh:117-137)"""
+        _require_cuda()
+        arrays = list(arrays)
+        if item_sizes is None:
+            item_sizes = [int(a.numel() // max(1, mapper.size)) for a in arrays]
+        ptrs = (C.c_void_p * len(arrays))(*[a.data_ptr() for a in arrays])
+        items = (C.c_int32 * len(arrays))(*item_sizes)
+        comm = self.grid.comm.h if self.grid.comm is not None else None
+        check(lib.dgb_communicate(self.grid.h, self.level, C.byref(mapper.m), iftype, direction, {"set": 0, "add": 1}[op],
+                                  ptrs, items, len(arrays), comm, _stream()))
+
+
+    # ---- the phases of communicate, for other transports and single-device rank emulation -----------------
+    def _items(self, mapper, arrays, item_sizes):
+        arrays = list(arrays)
+        if item_sizes is None:
+            item_sizes = [int(a.numel() // max(1, mapper.size)) for a in arrays]
+        ptrs = (C.c_void_p * len(arrays))(*[a.data_ptr() for a in arrays])
+        return arrays, ptrs, (C.c_int32 * len(arrays))(*item_sizes)
+
+    def commPlan(self, mapper, iftype, direction, item_sizes):
+        """(send segments, recv segments), each a list of (peer, offset, count) in doubles"""
+        items = (C.c_int32 * len(item_sizes))(*item_sizes)
+        out = (C.c_int64 * 1024)()
+        check(lib.dgb_comm_plan_info(self.grid.h, self.level, C.byref(mapper.m), iftype, direction, items, len(item_sizes), out, 1024))
+        ns, nr = out[0], out[1]
+        seg = [(int(out[2 + 3 * k]), int(out[3 + 3 * k]), int(out[4 + 3 * k])) for k in range(ns + nr)]
+        return seg[:ns], seg[ns:]
+
+    def commPack(self, mapper, arrays, iftype, direction, item_sizes=None):
+        """returns (sendbuf_ptr, recvbuf_ptr) device addresses of the library-owned exchange buffers"""
+        _require_cuda()
+        arrays, ptrs, items = self._items(mapper, arrays, item_sizes)
+        sb, rb = C.c_void_p(), C.c_void_p()
+        check(lib.dgb_comm_pack(self.grid.h, self.level, C.byref(mapper.m), iftype, direction, ptrs, items, len(arrays),
+                                C.byref(sb), C.byref(rb), _stream()))
+        return sb.value or 0, rb.value or 0
+
+    def commUnpack(self, mapper, arrays, iftype, direction, op="set", item_sizes=None):
+        _require_cuda()
+        arrays, ptrs, items = self._items(mapper, arrays, item_sizes)
+        check(lib.dgb_comm_unpack(self.grid.h, self.level, C.byref(mapper.m), iftype, direction, {"set": 0, "add": 1}[op],
+                                  ptrs, items, len(arrays), _stream()))
+
+
+class MultipleCodimMultipleGeomTypeMapper:
+    """Dune::MultipleCodimMultipleGeomTypeMapper<GV> (dune/grid/common/mcmgmapper.hh). layout = block size per
+    codimension (Yasp has one geometry type per codim)."""
+
+    def __init__(self, gv: GridView, layout: Sequence[int]):
+        self.gv = gv
+        b = list(layout) + [0] * (4 - len(layout))
+        self.m = capi.Mapper()
+        check(lib.dgb_mapper_init(C.byref(gv.v), (C.c_uint32 * 4)(*b), C.byref(self.m)))
+
+    @property
+    def size(self):
+        return int(self.m.size)
+
+    def index(self, codim=0, partition=All_Partition):
+        _require_cuda()
+        torch = _torch()
+        out = torch.empty(self.gv.size(codim, partition), dtype=torch.int32, device="cuda")
+        check(lib.dgb_mapper_index(C.byref(self.gv.v), C.byref(self.m), codim, partition, _ptr(out), _stream()))
+        return out
+
+    def subIndex(self, cc, partition=All_Partition):
+        _require_cuda()
+        torch = _torch()
+        from math import comb
+        ns = comb(self.gv.dim, cc) << cc
+        out = torch.empty((ns, self.gv.size(0, partition)), dtype=torch.int32, device="cuda")
+        check(lib.dgb_mapper_subindex(C.byref(self.gv.v), C.byref(self.m), cc, partition, _ptr(out), _stream()))
+        return out
+
+    def communicate(self, iftype, direction, op, *arrays):
+        self.gv.communicate(self, arrays, iftype, direction, op)
+
+
+def mcmgElementLayout(dim):
+    return [1] + [0] * dim
+
+
+def mcmgVertexLayout(dim):
+    return [0] * dim + [1]
+
+
+class Communicator:
+    """NCCL communicator for the torus exchange (replaces the MPI communicator handed to YaspGrid)."""
+
+    def __init__(self, rank, nranks, unique_id: bytes):
+        self.h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        check(lib.dgb_comm_init(buf, rank, nranks, C.byref(self.h)))
+        self.rank, self.nranks = rank, nranks
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib.dgb_comm_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls):
+        """bootstrap over an initialised torch.distributed process group (plumbing only)"""
+        torch = _torch()
+        import torch.distributed as dist
+        rank, n = dist.get_rank(), dist.get_world_size()
+        ids = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        return cls(rank, n, ids[0])
+
+    def close(self):
+        if self.h:
+            lib.dgb_comm_destroy(self.h)
+            self.h = None
+
+
+class FiniteVolume:
+    """The explicit upwind finite-volume transport functor of SURVEY.md §8d on a level view."""
+
+    def __init__(self, grid: YaspGrid, level=None, problem=0, params=(1, 1, 1, 0, .25, .25, .25, .125, .2), mode="separable"):
+        _require_cuda()
+        self.grid = grid
+        level = grid.maxLevel if level is None else level
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self.h = C.c_void_p()
+        comm = grid.comm.h if grid.comm is not None else None
+        check(lib.dgb_fv_create(grid.h, level, problem, p.ctypes.data_as(C.POINTER(C.c_double)), p.size,
+                                {"exact": 0, "separable": 1}[mode], comm, C.byref(self.h)))
+        self.gv = grid.levelGridView(level)
+        self.ncells = self.gv.size(0)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib.dgb_fv_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def initial(self):
+        torch = _torch()
+        c = torch.empty(self.ncells, dtype=torch.float64, device="cuda")
+        check(lib.dgb_fv_init_field(self.h, _ptr(c), _stream()))
+        return c
+
+    def step(self, c_in, c_out):
+        check(lib.dgb_fv_step(self.h, _ptr(c_in), _ptr(c_out), _stream()))
+
+    def bootstrap_local(self):
+        p = C.c_void_p()
+        check(lib.dgb_fv_bootstrap_local(self.h, C.byref(p), _stream()))
+        return p.value
+
+    def step_local(self, c_in, c_out):
+        """kernel only (no exchange, no reduction over ranks); returns the device address of the pending max"""
+        p = C.c_void_p()
+        check(lib.dgb_fv_step_local(self.h, _ptr(c_in), _ptr(c_out), C.byref(p), _stream()))
+        return p.value
+
+    def update(self, c_in):
+        torch = _torch()
+        u = torch.zeros(self.ncells, dtype=torch.float64, device="cuda")
+        check(lib.dgb_fv_update(self.h, _ptr(c_in), _ptr(u), _stream()))
+        return u
+
+    def last_dt(self):
+        dt = C.c_double(0)
+        check(lib.dgb_fv_last_dt(self.h, C.byref(dt), _stream()))
+        return dt.value
+
+    def step_host(self, h_in, h_out):
+        """same step on host tensors (pinned or pageable): H2D + step + D2H inside the call"""
+        dt = C.c_double(0)
+        check(lib.dgb_fv_step_host(self.h, C.c_void_p(h_in.data_ptr()), C.c_void_p(h_out.data_ptr()), C.byref(dt), _stream()))
+        return dt.value
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        check(lib.dgb_fv_launch_count(self.h, C.byref(n)))
+        return n.value

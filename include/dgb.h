@@ -1,0 +1,208 @@
+/* dgb.h — C ABI of libdgb.so, the B200-native bulk implementation of dune-grid's YaspGrid leaf-sweep
+ * hot path. Plain C types only; every data buffer is caller-owned DEVICE memory unless a
+ * parameter says "host". All functions return DGB_OK (0) or a negative error code; the message is
+ * available from dgb_last_error() (thread-local). Work is enqueued on the caller's CUDA stream
+ * (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream) and functions return
+ * before the device has finished, except where a host result is returned.
+ *
+ * There is NO CPU fallback: any entry point that needs the device fails with DGB_ECUDA when no CUDA
+ * device is usable. Descriptor-only queries (create/refine/view/mapper_init/sizes/lists) are pure host
+ * arithmetic and work without a GPU.
+ *
+ * The reference has no FFI for this path (it is a C++ template facade); each entry point below cites
+ * the reference interface it replaces (paths relative to the dune-grid source tree).
+ */
+#ifndef DGB_H
+#define DGB_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGB_MAX_DIM 3
+#define DGB_MAX_COMP 8              /* 2^dim shift components (yaspgrid.hh:199-206) */
+
+enum { DGB_OK = 0,
+       DGB_EGRID = -1,              /* Dune::GridError   (yaspgrid.hh:788,1053,1219; partitioning.hh:66,137) */
+       DGB_ERANGE = -2,             /* Dune::RangeError  (yaspgrid.hh:1745,1817) */
+       DGB_EARG = -3,               /* Dune::Exception   (torus.hh:87; partitioning.hh:159) / bad argument */
+       DGB_ECUDA = -4, DGB_ENCCL = -5, DGB_ENOTIMPL = -6 };
+
+/* coordinate containers: dune/grid/yaspgrid/coordinates.hh:27,129,243 */
+enum { DGB_COORD_EQUIDISTANT = 0, DGB_COORD_EQUIDISTANT_OFFSET = 1, DGB_COORD_TENSORPRODUCT = 2 };
+/* partitioners: dune/grid/yaspgrid/partitioning.hh:45,122,145 */
+enum { DGB_PART_DEFAULT = 0, DGB_PART_POWER_D = 1, DGB_PART_FIXED = 2 };
+/* dune/grid/common/gridenums.hh — identical numeric values */
+enum { DGB_InteriorEntity = 0, DGB_BorderEntity = 1, DGB_OverlapEntity = 2, DGB_FrontEntity = 3, DGB_GhostEntity = 4 };
+enum { DGB_InteriorBorder_InteriorBorder_Interface = 0, DGB_InteriorBorder_All_Interface = 1,
+       DGB_Overlap_OverlapFront_Interface = 2, DGB_Overlap_All_Interface = 3, DGB_All_All_Interface = 4 };
+enum { DGB_Interior_Partition = 0, DGB_InteriorBorder_Partition = 1, DGB_Overlap_Partition = 2,
+       DGB_OverlapFront_Partition = 3, DGB_All_Partition = 4, DGB_Ghost_Partition = 5 };
+enum { DGB_ForwardCommunication = 0, DGB_BackwardCommunication = 1 };
+enum { DGB_OP_SET = 0, DGB_OP_ADD = 1 };       /* dune/python/grid/mapper.hh:117-137 commOp */
+/* index of the four nested partition boxes of a component (yaspgrid.hh:199-206) */
+enum { DGB_BOX_OVERLAPFRONT = 0, DGB_BOX_OVERLAP = 1, DGB_BOX_INTERIORBORDER = 2, DGB_BOX_INTERIOR = 3 };
+
+const char* dgb_last_error(void);
+const char* dgb_version(void);
+int dgb_device_count(int* n);                       /* DGB_ECUDA if the CUDA runtime cannot see a device */
+
+/* ---- grid life cycle: YaspGrid constructors yaspgrid.hh:904-909 (equidistant), :974-980 (offset), :1043-1047
+ *      (tensor product); refineOptions :1270; globalRefine :1216 -------------------------------------------- */
+typedef struct dgb_grid_spec {
+  int32_t dim;                      /* 2 or 3 */
+  int32_t coord_mode;               /* DGB_COORD_* */
+  double  lower[DGB_MAX_DIM];       /* offset mode: lower left corner */
+  double  upper[DGB_MAX_DIM];       /* equidistant: L; offset: upper right corner */
+  int32_t N[DGB_MAX_DIM];           /* coarse cells per direction */
+  const double* tensor[DGB_MAX_DIM];/* HOST pointers, N[i]+1 monotone coordinates (tensor mode) */
+  uint32_t periodic;                /* bit i: direction i periodic */
+  int32_t overlap;
+  int32_t partitioner;              /* DGB_PART_* */
+  int32_t fixed_dims[DGB_MAX_DIM];  /* DGB_PART_FIXED */
+} dgb_grid_spec;
+
+typedef struct dgb_grid dgb_grid;
+int dgb_grid_create(const dgb_grid_spec* spec, int rank, int nranks, dgb_grid** out);
+int dgb_grid_destroy(dgb_grid* g);
+int dgb_grid_refine_options(dgb_grid* g, int keepPhysicalOverlap);
+int dgb_grid_global_refine(dgb_grid* g, int refCount);
+int dgb_grid_max_level(const dgb_grid* g, int* maxLevel);
+int dgb_grid_torus_dims(const dgb_grid* g, int32_t* dims);             /* torus.hh:112 */
+int dgb_grid_num_boundary_segments(const dgb_grid* g, int64_t* n);     /* yaspgrid.hh:1456 */
+int dgb_grid_domain_size(const dgb_grid* g, double* L);                /* yaspgrid.hh:1462 */
+/* standalone processor-grid choice, partitioning.hh:56-117 */
+int dgb_partition(int dim, const int32_t* N, int P, int overlap, int partitioner, const int32_t* fixed, int32_t* dims_out);
+
+/* ---- views: Grid::leafGridView/levelGridView (common/grid.hh:878-891). A view is a POD descriptor that is
+ *      copied by value into kernel parameters; leaf == level(maxLevel) for Yasp (yaspgrid.hh:1356-1381). ---- */
+typedef struct dgb_box { int32_t origin[DGB_MAX_DIM]; int32_t size[DGB_MAX_DIM]; } dgb_box;
+typedef struct dgb_component {
+  uint32_t shift;                   /* bit i set <=> entities extend along axis i (ygrid.hh:155-165) */
+  int32_t  codim;
+  int32_t  index_offset[4];         /* per partition box kind: YGrid::_indexOffset of this component (ygrid.hh:771-791) */
+  dgb_box  box[4];                  /* DGB_BOX_*; index arithmetic always uses box[0] as the enclosing array */
+} dgb_component;
+typedef struct dgb_view {
+  int32_t dim, level, rank, nranks;
+  int32_t N[DGB_MAX_DIM];           /* cells of the whole level (yaspgrid.hh:264) */
+  uint32_t periodic;
+  int32_t overlap;                  /* overlap width on this level */
+  int32_t ncomp;                    /* 2^dim */
+  int32_t comp_begin[DGB_MAX_DIM+2];/* components of codim c are comp[comp_begin[c] .. comp_begin[c+1]) in ascending shift */
+  int32_t shiftmap[DGB_MAX_COMP];   /* shift bits -> component number inside its codim (ygrid.hh:567) */
+  dgb_component comp[DGB_MAX_COMP];
+  /* coordinates (coordinates.hh): vertex coordinate along axis d at GLOBAL index i */
+  int32_t coord_mode;
+  double  h[DGB_MAX_DIM];           /* equidistant modes */
+  double  origin[DGB_MAX_DIM];      /* offset mode */
+  const double* tensor[DGB_MAX_DIM];/* DEVICE pointers (tensor mode), entry 0 = global index tensor_offset[d] */
+  const double* tensor_host[DGB_MAX_DIM];
+  int32_t tensor_offset[DGB_MAX_DIM];
+  int32_t tensor_size[DGB_MAX_DIM]; /* number of stored coordinates */
+  double  L[DGB_MAX_DIM];           /* domain size, periodic wrap shift (yaspgridentity.hh:497-510) */
+  /* boundary segments are numbered on the level-0 local box (yaspgridintersection.hh:105-162) */
+  int32_t bs_origin[DGB_MAX_DIM], bs_size[DGB_MAX_DIM], bs_sides[DGB_MAX_DIM];
+  int32_t N0[DGB_MAX_DIM];
+} dgb_view;
+
+int dgb_view_leaf(const dgb_grid* g, dgb_view* v);
+int dgb_view_level(const dgb_grid* g, int level, dgb_view* v);        /* DGB_ERANGE like yaspgrid.hh:1745 */
+int dgb_view_size(const dgb_view* v, int codim, int64_t* n);          /* GridView::size(codim), yaspgrid.hh:1425 */
+int dgb_view_partition_size(const dgb_view* v, int codim, int pitype, int64_t* n);  /* length of begin<cd,pit>..end */
+int dgb_view_overlap_size(const dgb_view* v, int codim, int* n);      /* gridview.hh overlapSize, yaspgrid.hh:1399 */
+int dgb_view_ghost_size(const dgb_view* v, int codim, int* n);        /* always 0, yaspgrid.hh:1413 */
+/* send/recv box lists of communicate (yaspgrid.hh:208-226,561-671). which: 0 send_of_of 1 recv_of_of 2 send_o_of
+ * 3 recv_of_o 4 send_ib_ib 5 recv_ib_ib 6 send_ib_of 7 recv_of_ib. Entry = 10 ints: rank, distance, shift,
+ * indexOffset, origin[3], size[3]. Host arithmetic only — no messages are exchanged to build them. */
+int dgb_view_comm_list(const dgb_grid* g, int level, int codim, int which, int32_t* out, int cap, int* count);
+
+/* ---- mapper: MultipleCodimMultipleGeomTypeMapper (common/mcmgmapper.hh:212-249,373-407). block[codim] replaces
+ *      MCMGLayout (Yasp has one geometry type per codim, yaspgridindexsets.hh:90-93). ------------------------- */
+typedef struct dgb_mapper { int32_t dim; uint32_t block[4]; uint32_t offset[4]; uint32_t size; } dgb_mapper;
+#define DGB_INVALID_OFFSET 0xffffffffu
+int dgb_mapper_init(const dgb_view* v, const uint32_t* block, dgb_mapper* m);
+int dgb_mapper_size(const dgb_mapper* m, int64_t* n);
+/* mapper.index(e) for every entity of begin<codim,pitype>()..end() in iteration order -> d_out[n] */
+int dgb_mapper_index(const dgb_view* v, const dgb_mapper* m, int codim, int pitype, uint32_t* d_out, void* stream);
+/* mapper.subIndex(e,i,cc) for every cell of the partition -> d_out[i*n + cell] (sub-entity major) */
+int dgb_mapper_subindex(const dgb_view* v, const dgb_mapper* m, int cc, int pitype, uint32_t* d_out, void* stream);
+
+/* ---- element sweep (rangegenerators.hh:881 elements(gv); yaspgridentity.hh:270-305,480-514; AxisAlignedCubeGeometry).
+ *      All outputs are optional (NULL = skip), in iteration order of the partition; vector quantities are stored
+ *      component-major: out[d*n + e]. index = indexSet.index(e). ------------------------------------------------ */
+int dgb_elements_materialize(const dgb_view* v, int codim, int pitype,
+                             uint32_t* d_index, uint8_t* d_ptype, int32_t* d_coord,
+                             double* d_lower, double* d_upper, double* d_center, double* d_volume, void* stream);
+/* ---- intersection sweep (rangegenerators.hh:845 intersections(gv,e); yaspgridintersection.hh:40-288). Per cell of the
+ *      partition and face k in reference order (dir=k/2, side=k%2): out[k*n + cell]; face centre out[(k*dim+d)*n + cell].
+ *      outside = indexSet.index(outside()) if neighbor() else -1; bsi = boundarySegmentIndex() if boundary() else -1. */
+int dgb_intersections_materialize(const dgb_view* v, int pitype,
+                                  uint8_t* d_neighbor, uint8_t* d_boundary, int32_t* d_outside, int32_t* d_bsi,
+                                  double* d_center, double* d_volume, void* stream);
+/* ---- Geometry::global / jacobianInverseTransposed / integrationElement at nqp local points (host array nqp*dim) for all
+ *      cells of the partition: global[(q*dim+d)*n+e], jit[((q*dim+r)*dim+c)*n+e], detJ[q*n+e] (common/geometry.hh:194-371) */
+int dgb_geometry_eval(const dgb_view* v, int pitype, int nqp, const double* qp_host,
+                      double* d_global, double* d_jit, double* d_detJ, void* stream);
+/* ---- GeometryGrid over the Yasp host view with a compiled-in analytic coordinate function
+ *      (geometrygrid/cornerstorage.hh:54-60, coordfunctioncaller.hh:40-43, geometry.hh:197-204). deformation: 0 identity,
+ *      1 the sine field of SURVEY.md §8d config 5 (amplitude params_host[0]). corners[(k*dim+d)*n+e], jt like jit. */
+int dgb_geogrid_eval(const dgb_view* v, int pitype, int deformation, const double* params_host, int nparams,
+                     int nqp, const double* qp_host, double* d_corners, double* d_global, double* d_jt, double* d_jit,
+                     double* d_detJ, void* stream);
+/* reduction variant: sum over cells and points of weight_q * detJ -> *d_sum (one double, device) */
+int dgb_geogrid_volume(const dgb_view* v, int pitype, int deformation, const double* params_host, int nparams,
+                       int nqp, const double* qp_host, const double* weights_host, double* d_sum, void* stream);
+
+/* ---- communication: GridView::communicate(DataHandle, InterfaceType, CommunicationDirection) (gridview.hh:334,
+ *      yaspgrid.hh:1470-1730) for flat arrays indexed by a mapper, the shape of the reference's own
+ *      NumPyCommDataHandle (dune/python/grid/numpycommdatahandle.hh:41-142). Collective over all ranks. ---------- */
+typedef struct dgb_comm dgb_comm;
+int dgb_comm_unique_id(void* id128);                                   /* 128-byte ncclUniqueId, rank 0 */
+int dgb_comm_init(const void* id128, int rank, int nranks, dgb_comm** out);
+int dgb_comm_destroy(dgb_comm* c);
+int dgb_communicate(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int dir, int op,
+                    double* const* d_arrays, const int32_t* item_sizes, int narrays, dgb_comm* comm, void* stream);
+/* The three phases of dgb_communicate as separate calls, for transports other than NCCL (e.g. the reference's MPI
+ * Torus) and for tests that emulate several ranks on one device. Buffers are owned by the library.
+ * plan_info: out[0]=#send segments, out[1]=#recv segments, then per segment (peer, offset, count) in doubles, send
+ * segments first; cap = capacity of out in int64. pack fills the send buffer (returned in *d_sendbuf); unpack scatters
+ * the recv buffer (*d_recvbuf must have been filled by the transport). */
+int dgb_comm_plan_info(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int dir,
+                       const int32_t* item_sizes, int narrays, int64_t* out, int cap);
+int dgb_comm_pack(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int dir, double* const* d_arrays,
+                  const int32_t* item_sizes, int narrays, double** d_sendbuf, double** d_recvbuf, void* stream);
+int dgb_comm_unpack(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int dir, int op, double* const* d_arrays,
+                    const int32_t* item_sizes, int narrays, void* stream);
+int dgb_allreduce_min(double* d_value, dgb_comm* comm, void* stream);  /* comm().min(x), yaspgrid.hh:1316 pattern */
+int dgb_allreduce_max(double* d_value, dgb_comm* comm, void* stream);
+/* bytes this rank sent in the most recent dgb_communicate / fv step exchange (for NVLink GB/s reporting) */
+int dgb_comm_last_bytes(const dgb_grid* g, int64_t* bytes);
+
+/* ---- the finite-volume transport functor: element loop + intersection loop + mapper +
+ *      geometry + CFL min-reduction + communicate(InteriorBorder_All_Interface, ForwardCommunication). -------------- */
+typedef struct dgb_fv dgb_fv;
+enum { DGB_FV_EXACT = 0,           /* per-cell arithmetic in the reference order: bit-identical to the CPU oracle */
+       DGB_FV_SEPARABLE = 1 };     /* tensor-product factorised face factors: <= 1e-13 relative */
+int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host, int nparams, int mode,
+                  dgb_comm* comm, dgb_fv** out);
+int dgb_fv_destroy(dgb_fv* fv);
+int dgb_fv_init_field(dgb_fv* fv, double* d_c, void* stream);          /* c0 at the cell centres, all stored cells */
+/* one step: c_out = c_in + dt*update(c_in) on interior cells, halo of c_out refreshed, dt = 0.99*min(1/sum_out) */
+int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream);
+/* the kernel of dgb_fv_step alone: no halo exchange, no reduction across ranks. *d_pending_max then points at the
+ * device double holding this rank's max outflow sum, which the caller must max-reduce over ranks before the next
+ * step (dgb_fv_step does both itself). For transports other than NCCL and single-device rank emulation. */
+int dgb_fv_step_local(dgb_fv* fv, const double* d_c_in, double* d_c_out, double** d_pending_max, void* stream);
+int dgb_fv_bootstrap_local(dgb_fv* fv, double** d_pending_max, void* stream);
+int dgb_fv_last_dt(dgb_fv* fv, double* dt_host, void* stream);         /* synchronises the stream */
+/* optional: also materialise the update array (tests) */
+int dgb_fv_update(dgb_fv* fv, const double* d_c_in, double* d_update, void* stream);
+/* the same step on HOST buffers (pinned or pageable): H2D copy of c, step, D2H copy of the result */
+int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* dt_host, void* stream);
+int dgb_fv_launch_count(const dgb_fv* fv, int64_t* kernels);           /* kernels launched by this object so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGB_H */

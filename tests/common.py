@@ -1,0 +1,53 @@
+"""Shared helpers of the test-suite: build the same grid in the product (dune_grid_b200, through the C ABI)
+and in a CPU oracle (oracle/oracle.py) from one configuration dict."""
+import numpy as np
+
+from oracle import oracle as orc
+
+
+def oracle_kinds():
+    """oracles that are built here: 'ref' = the reference's own headers (oracle/_ref), 'port' = the restatement"""
+    return [k for k in ("ref", "port") if orc.available(k)]
+
+
+def best_oracle():
+    kinds = oracle_kinds()
+    assert kinds, "no CPU oracle built: run `make -C oracle` (python -c 'import __graft_entry__ as g; g.build()')"
+    return orc.load(kinds[0])
+
+
+def graded(n, r=1.005, lo=0.0, hi=1.0):
+    """geometric grading x_{i+1} = x_i + h0 r^i scaled to [lo, hi] (cf. utility/tensorgridfactory.hh:197)"""
+    w = r ** np.arange(n)
+    x = np.concatenate([[0.0], np.cumsum(w)])
+    return lo + (hi - lo) * x / x[-1]
+
+
+def make_cfg(dim=3, N=(4, 4, 4), mode=0, lower=None, upper=None, tensor=None, periodic=0, overlap=1,
+             partitioner=0, fixed_dims=None, refine=0, keep=1):
+    lower = tuple(lower) if lower is not None else (0.0,) * dim
+    upper = tuple(upper) if upper is not None else (1.0,) * dim
+    if mode == 2 and tensor is None:
+        tensor = [graded(N[i], 1.0 + 0.01 * (i + 1), lower[i], upper[i]) for i in range(dim)]
+    return dict(dim=dim, N=tuple(N[:dim]), mode=mode, lower=lower, upper=upper, tensor=tensor, periodic=periodic,
+                overlap=overlap, partitioner=partitioner, fixed_dims=fixed_dims, refine=refine, keep=keep)
+
+
+def oracle_world(o, cfg, P):
+    s = orc.Spec(dim=cfg["dim"], N=cfg["N"], coord_mode=cfg["mode"], lower=cfg["lower"], upper=cfg["upper"],
+                 tensor=cfg["tensor"], periodic=cfg["periodic"], overlap=cfg["overlap"], partitioner=cfg["partitioner"],
+                 fixed_dims=cfg["fixed_dims"] or (1, 1, 1), refine=cfg["refine"], keep_overlap=cfg["keep"])
+    return o.world(s, P)
+
+
+def product_grid(cfg, rank, P, comm=None):
+    import dune_grid_b200 as dg
+    g = dg.YaspGrid(dim=cfg["dim"], N=cfg["N"], lower=cfg["lower"], upper=cfg["upper"], coords=cfg["tensor"] if cfg["mode"] == 2 else None,
+                    periodic=cfg["periodic"], overlap=cfg["overlap"],
+                    coordinates=["equidistant", "equidistantoffset", "tensorproduct"][cfg["mode"]],
+                    rank=rank, nranks=P, partitioner=["default", "powerd", "fixed"][cfg["partitioner"]],
+                    fixed_dims=cfg["fixed_dims"], comm=comm)
+    g.refineOptions(bool(cfg["keep"]))
+    if cfg["refine"]:
+        g.globalRefine(cfg["refine"])
+    return g

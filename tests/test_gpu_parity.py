@@ -1,0 +1,175 @@
+"""GPU parity tests proper: every bulk sweep of libdgb (called through the C ABI) against the CPU oracle on the
+same grids. Integers (indices, mapper numbering, partition types, neighbour tables, boundary-segment ids) must be
+bit-exact; axis-aligned geometry is bit-exact too (same expressions, FMA contraction off on both sides);
+GeometryGrid's J^-T and the separable FV mode are checked to 1e-13 relative as north_star allows.
+The reference's own invariants (test/checkindexset.hh, checkintersectionit.hh, gridcheck.hh:844-925,
+checkpartition.hh) are re-expressed as bulk checks in test_gpu_invariants.py."""
+import numpy as np
+import pytest
+
+from tests.common import best_oracle, make_cfg, oracle_world, product_grid
+
+pytestmark = pytest.mark.gpu
+
+ALL_PARTITIONS = [0, 1, 2, 3, 4, 5]
+
+CASES = [
+    (make_cfg(dim=2, N=(8, 4)), 1), (make_cfg(dim=2, N=(8, 4)), 2),
+    (make_cfg(dim=3, N=(8, 4, 4)), 2),
+    (make_cfg(dim=2, N=(8, 4), mode=1, lower=(-1.0, -0.5), upper=(1.0, 0.5), refine=1, keep=0), 2),
+    (make_cfg(dim=3, N=(8, 4, 4), mode=2, tensor=[np.array([-1, -.5, -.25, -.125, 0, .125, .25, .5, 1.0]),
+                                                  np.array([-1, -.5, 0, .5, 1.0]), np.array([-1, -.5, 0, .5, 1.0])]), 2),
+    (make_cfg(dim=3, N=(12, 10, 9), periodic=5, overlap=2, upper=(1.0, 2.0, 3.0)), 4),
+    (make_cfg(dim=2, N=(13, 7), periodic=3, refine=1), 1),
+    (make_cfg(dim=3, N=(6, 5, 4), periodic=7, mode=2), 1),
+    (make_cfg(dim=3, N=(10, 6, 7), periodic=2, mode=2, refine=1, keep=0), 4),
+    (make_cfg(dim=3, N=(9, 8, 8), overlap=0), 4),
+    (make_cfg(dim=3, N=(10, 10, 10), upper=(0.3, 0.7, 1.9)), 8),
+]
+IDS = [f"case{i}" for i in range(len(CASES))]
+
+
+def np_(t):
+    return t.cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return best_oracle()
+
+
+@pytest.mark.parametrize("cfg,P", CASES, ids=IDS)
+def test_entities(oracle, cfg, P):
+    w = oracle_world(oracle, cfg, P)
+    d = cfg["dim"]
+    for r in range(P):
+        g = product_grid(cfg, r, P)
+        for lvl in range(cfg["refine"] + 1):
+            gv = g.levelGridView(lvl)
+            for codim in range(d + 1):
+                for pit in ALL_PARTITIONS:
+                    ref = w.entities(r, lvl, codim, pit)
+                    got = gv.elements(codim, pit, coord=True)
+                    n = len(ref["index"])
+                    assert gv.size(codim, pit) == n
+                    assert np.array_equal(np_(got["index"]).view(np.uint32), ref["index"]), (r, lvl, codim, pit)
+                    assert np.array_equal(np_(got["partitionType"]), ref["ptype"])
+                    assert np.array_equal(np_(got["coord"]).T, ref["coord"])
+                    for k in ("lower", "upper", "center"):
+                        assert np.array_equal(np_(got[k]).T, ref[k]), (r, lvl, codim, pit, k)
+                    assert np.array_equal(np_(got["volume"]), ref["volume"])
+    w.close()
+
+
+@pytest.mark.parametrize("cfg,P", CASES, ids=IDS)
+def test_mapper_and_subindices(oracle, cfg, P):
+    import dune_grid_b200 as dg
+    w = oracle_world(oracle, cfg, P)
+    d = cfg["dim"]
+    layouts = [dg.mcmgElementLayout(d), dg.mcmgVertexLayout(d), [1] * (d + 1), [2, 0, 3, 1][:d + 1]]
+    for r in range(P):
+        g = product_grid(cfg, r, P)
+        lvl = cfg["refine"]
+        gv = g.levelGridView(lvl)
+        for layout in layouts:
+            m = dg.MultipleCodimMultipleGeomTypeMapper(gv, layout)
+            assert m.size == w.mapper_size(r, lvl, layout)
+            for codim in range(d + 1):
+                if layout[codim] == 0:
+                    with pytest.raises(dg.capi.DgbError):
+                        m.index(codim)
+                    continue
+                for pit in (0, 1, 4):
+                    assert np.array_equal(np_(m.index(codim, pit)).view(np.uint32), w.mapper_index(r, lvl, layout, codim, pit)), (layout, codim, pit)
+                for pit in (0, 4):
+                    assert np.array_equal(np_(m.subIndex(codim, pit)).view(np.uint32).T, w.mapper_subindex(r, lvl, layout, codim, pit))
+        # plain index-set subIndex (layout all ones has offsets; use per-codim layouts with block 1)
+        for cc in range(d + 1):
+            lay = [0] * (d + 1)
+            lay[cc] = 1
+            m = dg.MultipleCodimMultipleGeomTypeMapper(gv, lay)
+            assert np.array_equal(np_(m.subIndex(cc, 4)).view(np.uint32).T, w.subindices(r, lvl, cc, 4))
+    w.close()
+
+
+@pytest.mark.parametrize("cfg,P", CASES, ids=IDS)
+def test_intersections(oracle, cfg, P):
+    w = oracle_world(oracle, cfg, P)
+    d = cfg["dim"]
+    for r in range(P):
+        g = product_grid(cfg, r, P)
+        for lvl in range(cfg["refine"] + 1):
+            gv = g.levelGridView(lvl)
+            for pit in (0, 2, 4):
+                ref = w.intersections(r, lvl, pit)
+                got = gv.intersections(pit)
+                assert np.array_equal(np_(got["neighbor"]).T, ref["neighbor"]), (r, lvl, pit)
+                assert np.array_equal(np_(got["boundary"]).T, ref["boundary"])
+                assert np.array_equal(np_(got["outside"]).T, ref["outside"])
+                assert np.array_equal(np_(got["boundarySegmentIndex"]).T, ref["bsi"])
+                assert np.array_equal(np.transpose(np_(got["center"]), (2, 0, 1)), ref["center"])
+                assert np.array_equal(np_(got["volume"]).T, ref["volume"])
+                for k in range(2 * d):
+                    assert np.array_equal(ref["normal"][:, k, :], np.broadcast_to(gv.centerUnitOuterNormal(k), ref["normal"][:, k, :].shape))
+    w.close()
+
+
+def gauss_points(dim, n1d):
+    x, wts = np.polynomial.legendre.leggauss(n1d)
+    x = 0.5 * (x + 1.0)
+    wts = 0.5 * wts
+    grids = np.meshgrid(*([x] * dim), indexing="ij")
+    pts = np.stack([gq.T.reshape(-1) for gq in grids], axis=1)       # axis 0 fastest
+    wg = np.meshgrid(*([wts] * dim), indexing="ij")
+    ww = np.prod(np.stack([gq.T.reshape(-1) for gq in wg], axis=1), axis=1)
+    return pts, ww
+
+
+@pytest.mark.parametrize("cfg,P", CASES[:8], ids=IDS[:8])
+def test_geometry_at_quadrature_points(oracle, cfg, P):
+    w = oracle_world(oracle, cfg, P)
+    d = cfg["dim"]
+    qp, _ = gauss_points(d, 2)
+    for r in range(P):
+        g = product_grid(cfg, r, P)
+        lvl = cfg["refine"]
+        gv = g.levelGridView(lvl)
+        ref = w.geometry_eval(r, lvl, qp, 4)
+        got = gv.geometry(qp, 4)
+        assert np.array_equal(np.transpose(np_(got["global"]), (2, 0, 1)), ref["global"])
+        assert np.array_equal(np.transpose(np_(got["jacobianInverseTransposed"]), (3, 0, 1, 2)), ref["jit"])
+        assert np.array_equal(np_(got["integrationElement"]).T, ref["detJ"])
+    w.close()
+
+
+@pytest.mark.parametrize("cfg,P", [CASES[0], CASES[2], CASES[4], CASES[6], CASES[8]], ids=["c0", "c2", "c4", "c6", "c8"])
+def test_geometrygrid(oracle, cfg, P):
+    """GeometryGrid over the Yasp host view (config 5 of BASELINE.json at small size). global / jacobianTransposed /
+    integrationElement follow the same operation order as the oracle's MultiLinearGeometry restatement; the analytic
+    deformation uses sin(), whose device implementation differs from glibc's by <= 2 ulp, so everything is compared
+    to 1e-13 relative (of the largest entry of the quantity), as north_star states."""
+    w = oracle_world(oracle, cfg, P)
+    d = cfg["dim"]
+    qp, wts = gauss_points(d, 2)
+    for deformation, params in ((0, [0.0]), (1, [0.05])):
+        for r in range(P):
+            g = product_grid(cfg, r, P)
+            for lvl in range(cfg["refine"] + 1):
+                gv = g.levelGridView(lvl)
+                ref = w.geogrid_eval(r, lvl, deformation, params, qp, 0)
+                got = gv.geometryGrid(deformation, params, qp, 0)
+                pairs = [(np.transpose(np_(got["corners"]), (2, 0, 1)), ref["corners"]),
+                         (np.transpose(np_(got["global"]), (2, 0, 1)), ref["global"]),
+                         (np.transpose(np_(got["jacobianTransposed"]), (3, 0, 1, 2)), ref["jt"]),
+                         (np.transpose(np_(got["jacobianInverseTransposed"]), (3, 0, 1, 2)), ref["jit"]),
+                         (np_(got["integrationElement"]).T, ref["detJ"])]
+                for a, b in pairs:
+                    scale = np.abs(b).max() if b.size else 1.0
+                    assert np.abs(a - b).max(initial=0.0) <= 1e-13 * scale
+                if deformation == 0:
+                    assert np.array_equal(pairs[0][0], pairs[0][1]) and np.array_equal(pairs[1][0], pairs[1][1])
+                    assert np.array_equal(pairs[2][0], pairs[2][1]) and np.array_equal(pairs[4][0], pairs[4][1])
+                vol = float(np_(gv.geometryGridVolume(deformation, params, qp, wts, 0))[0])
+                refvol = float((ref["detJ"] * wts[None, :]).sum())
+                assert abs(vol - refvol) <= 1e-12 * max(1.0, abs(refvol))
+    w.close()
