@@ -43,12 +43,29 @@ class ClockSampler:
         self.index, self.proc, self.path = index, None, None
 
     def start(self):
+        """start sampling and wait until the first sample has been written, so that the samples counted later
+        (those after `self.skip`) lie inside the timed region"""
+        self._start()
+        self.skip = 0
+        if not self.proc:
+            return
+        t0 = time.time()
+        while time.time() - t0 < 2.0:
+            try:
+                self.skip = sum(1 for _ in open(self.path))
+            except Exception:
+                self.skip = 0
+            if self.skip > 0:
+                break
+            time.sleep(0.02)
+
+    def _start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -64,7 +81,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         try:
-            for line in open(self.path):
+            for ln, line in enumerate(open(self.path)):
+                if ln < getattr(self, "skip", 0):
+                    continue
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
@@ -227,9 +246,9 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             P = feasible_ranks(args.ref_size, min(cores, 64))
-            val, kind, secs = cpu_reference_run(args.ref_size, P, 2, 1)
+            val, kind, secs = cpu_reference_run(args.ref_size, P, 8, 1)
             line["cpu_baseline"] = {"value": val, "unit": "cells/s", "cores": P, "kind": kind,
-                                    "sample": f"2 FV steps on a {args.ref_size}^3 YaspGrid, {P} ranks (threads) of {cores} host cores, {secs:.1f} s"}
+                                    "sample": f"8 FV steps on a {args.ref_size}^3 YaspGrid, {P} ranks (threads) of {cores} host cores, {secs:.1f} s"}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -240,12 +259,12 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="separable", choices=["separable", "exact"])
     ap.add_argument("--size", type=int, default=0, help="override the cube edge (default 512 at N=1, 1024 at N>1)")
-    ap.add_argument("--ref-size", type=int, default=192, help="cube edge of the bounded CPU sample")
+    ap.add_argument("--ref-size", type=int, default=256, help="cube edge of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -9,6 +9,7 @@
 // L1/L2. The CFL bound depends only on geometry and velocity (not on c), so the kernel of step n also reduces
 // max_i(sum of outflow factors) for step n+1 (velocities are time independent); one geometry-only bootstrap
 // reduction precedes the first step. min_i fl(1/s_i) == fl(1/max_i s_i) because correctly rounded division is monotone.
+#include <cstdlib>
 #include "dgb_internal.hh"
 #include "dgb_device.cuh"
 #include "dgb_comm.hh"
@@ -141,6 +142,121 @@ __global__ void __launch_bounds__(FBX*FBY) k_fv_step(const __grid_constant__ dgb
   }
 }
 
+// ---- 3-D production kernel: z-marching --------------------------------------------------------------------
+// A CTA owns an (MBX x MBY) column tile of the region and marches over ZC consecutive z-planes. Everything that
+// does not depend on z (x/y coordinates, reciprocal widths, x/y neighbour and boundary flags, velocity terms that
+// are z-invariant, the time step) is computed once per thread; the z-neighbours of a cell are carried in registers
+// (c_below, c_here, c_above), so each cell costs ONE streaming load of the plane above plus the x/y inflow
+// neighbours, which hit L1/L2 (they are the streaming loads of adjacent threads / rows). HBM traffic stays at
+// 8 B read + 8 B write per cell; the CFL max is reduced per thread over its column, then once per CTA.
+static constexpr int MBX = 128, MBY = 4;
+
+template<int PROBLEM>
+__device__ __forceinline__ void fv_velocity3(const FvProblem& q, const double* x, double* u) {
+  if (PROBLEM == 1) { u[0] = -q.p[0]*(x[1]-0.5); u[1] = q.p[0]*(x[0]-0.5); u[2] = 0.0; }
+  else { u[0] = q.p[0]; u[1] = q.p[1]; u[2] = q.p[2]; }
+}
+
+template<int MODE, int PROBLEM, bool REDUCE_ONLY>
+__global__ void __launch_bounds__(MBX*MBY) k_fv_march(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a, const int zc) {
+  const int i0 = blockIdx.x*MBX + threadIdx.x;
+  const int i1 = blockIdx.y*MBY + threadIdx.y;
+  const int z0 = blockIdx.z*zc;
+  const int zn = min(zc, a.region.size[2]-z0);
+  double sum_max = 0.0;
+  if (i0 < a.region.size[0] && i1 < a.region.size[1]) {
+    const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+    const dgb_box& ov = v.comp[0].box[DGB_BOX_OVERLAP];
+    const int cx = a.region.origin[0]+i0, cy = a.region.origin[1]+i1, cz0 = a.region.origin[2]+z0;
+    const long long sy = of.size[0], sz = (long long)of.size[0]*of.size[1];
+    const long long idx0 = (long long)(cz0-of.origin[2])*sz + (long long)(cy-of.origin[1])*sy + (cx-of.origin[0]);
+    // z-invariant geometry of the column
+    double llx, urx, lly, ury, xcx, xcy, rwx = 0.0, rwy = 0.0, wx = 0.0, wy = 0.0;
+    if (MODE == DGB_FV_SEPARABLE) {
+      const int tx = cx-a.tab.first[0], ty = cy-a.tab.first[1];
+      llx = __ldg(a.tab.xv[0]+tx); urx = __ldg(a.tab.xv[0]+tx+1); xcx = __ldg(a.tab.xc[0]+tx); rwx = __ldg(a.tab.rw[0]+tx);
+      lly = __ldg(a.tab.xv[1]+ty); ury = __ldg(a.tab.xv[1]+ty+1); xcy = __ldg(a.tab.xc[1]+ty); rwy = __ldg(a.tab.rw[1]+ty);
+    } else {
+      llx = vertex_coord(v, 0, cx); urx = vertex_coord(v, 0, cx+1); wx = urx-llx; xcx = 0.5*(llx+urx);
+      lly = vertex_coord(v, 1, cy); ury = vertex_coord(v, 1, cy+1); wy = ury-lly; xcy = 0.5*(lly+ury);
+    }
+    // neighbour / boundary flags of the four x/y faces (yaspgridintersection.hh:62-82)
+    const bool nbx0 = cx > ov.origin[0] && cx <= ov.origin[0]+ov.size[0]-1;
+    const bool nbx1 = cx+1 > ov.origin[0] && cx+1 <= ov.origin[0]+ov.size[0]-1;
+    const bool nby0 = cy > ov.origin[1] && cy <= ov.origin[1]+ov.size[1]-1;
+    const bool nby1 = cy+1 > ov.origin[1] && cy+1 <= ov.origin[1]+ov.size[1]-1;
+    const bool perx = v.periodic & 1u, pery = v.periodic >> 1 & 1u, perz = v.periodic >> 2 & 1u;
+    const bool bdx0 = !perx && cx == 0, bdx1 = !perx && cx+1 == v.N[0];
+    const bool bdy0 = !pery && cy == 0, bdy1 = !pery && cy+1 == v.N[1];
+    const double dt = REDUCE_ONLY ? 0.0 : 0.99*(1.0/(*a.slotIn));
+    const double* p = a.c + idx0;
+    double c_below = 0.0, c_here = 0.0, c_above = 0.0;
+    if (!REDUCE_ONLY) {
+      const bool nb_first = cz0 > ov.origin[2] && cz0 <= ov.origin[2]+ov.size[2]-1;
+      if (nb_first) c_below = __ldg(p - sz);
+      c_here = __ldg(p);
+    }
+    double llz = (MODE == DGB_FV_SEPARABLE) ? __ldg(a.tab.xv[2]+(cz0-a.tab.first[2])) : vertex_coord(v, 2, cz0);
+    for (int k = 0; k < zn; ++k) {
+      const int cz = cz0+k;
+      double urz, xcz, rwz = 0.0, wz = 0.0;
+      if (MODE == DGB_FV_SEPARABLE) {
+        const int tz = cz-a.tab.first[2];
+        urz = __ldg(a.tab.xv[2]+tz+1); xcz = __ldg(a.tab.xc[2]+tz); rwz = __ldg(a.tab.rw[2]+tz);
+      } else {
+        urz = vertex_coord(v, 2, cz+1); wz = urz-llz; xcz = 0.5*(llz+urz);
+      }
+      const bool nbz0 = cz > ov.origin[2] && cz <= ov.origin[2]+ov.size[2]-1;
+      const bool nbz1 = cz+1 > ov.origin[2] && cz+1 <= ov.origin[2]+ov.size[2]-1;
+      const bool bdz0 = !perz && cz == 0, bdz1 = !perz && cz+1 == v.N[2];
+      if (!REDUCE_ONLY && nbz1) c_above = __ldg(p + sz);
+      double vol = 1.0, ax = 1.0, ay = 1.0, az = 1.0;
+      if (MODE == DGB_FV_EXACT) { vol = (wx*wy)*wz; ax = wy*wz; ay = wx*wz; az = wx*wy; }
+      double sum = 0.0, upd = 0.0;
+      // one face: un = u.n, factor = un*|F|/|V|; outflow uses the cell value, inflow the neighbour or boundary value
+#define DGB_FACE(DIRX, SIDE, FCX, FCY, FCZ, AREA, RW, NB, BD, CJ)                                             \
+      {                                                                                                        \
+        const double fc[3] = { FCX, FCY, FCZ };                                                                \
+        double u[3]; fv_velocity3<PROBLEM>(a.problem, fc, u);                                                  \
+        const double un = (SIDE) ? u[DIRX] : -u[DIRX];                                                         \
+        const double factor = (MODE == DGB_FV_EXACT) ? (un*(AREA))/vol : un*(RW);                              \
+        if (factor >= 0.0) { sum += factor; if (!REDUCE_ONLY) upd -= c_here*factor; }                          \
+        else if (!REDUCE_ONLY) {                                                                               \
+          if (NB) upd -= (CJ)*factor;                                                                          \
+          else if (BD) upd -= fv_boundary(a.problem, fc)*factor;                                               \
+        }                                                                                                      \
+      }
+      DGB_FACE(0, 0, llx, xcy, xcz, ax, rwx, nbx0, bdx0, __ldg(p - 1))
+      DGB_FACE(0, 1, urx, xcy, xcz, ax, rwx, nbx1, bdx1, __ldg(p + 1))
+      DGB_FACE(1, 0, xcx, lly, xcz, ay, rwy, nby0, bdy0, __ldg(p - sy))
+      DGB_FACE(1, 1, xcx, ury, xcz, ay, rwy, nby1, bdy1, __ldg(p + sy))
+      DGB_FACE(2, 0, xcx, xcy, llz, az, rwz, nbz0, bdz0, c_below)
+      DGB_FACE(2, 1, xcx, xcy, urz, az, rwz, nbz1, bdz1, c_above)
+#undef DGB_FACE
+      sum_max = fmax(sum_max, sum);
+      if (!REDUCE_ONLY) {
+        const long long idx = idx0 + (long long)k*sz;
+        if (a.update) a.update[idx] = upd;
+        if (a.cnew) a.cnew[idx] = c_here + dt*upd;
+        c_below = c_here; c_here = c_above;
+      }
+      p += sz; llz = urz;
+    }
+    if (!REDUCE_ONLY && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = dt;
+  }
+  for (int off = 16; off > 0; off >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, off));
+  __shared__ double part[MBX*MBY/32];
+  const int tid = threadIdx.y*MBX + threadIdx.x;
+  if ((tid & 31) == 0) part[tid >> 5] = sum_max;
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int k = 0; k < MBX*MBY/32; ++k) m = fmax(m, part[k]);
+    if (m > 0.0) atomic_max_nonneg(a.slotOut, m);
+    if (a.slotZero && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *a.slotZero = 0.0;
+  }
+}
+
 // initial condition at the cell centres of all stored cells (geometry().center(), periodic wrap included)
 template<int DIM>
 __global__ void __launch_bounds__(FBX*FBY) k_fv_init(const __grid_constant__ dgb_view v, const FvProblem q, double* c) {
@@ -180,6 +296,7 @@ struct dgb_fv {
   dgb_grid* grid = nullptr;
   dgb_comm* comm = nullptr;
   int level = 0, mode = 0;
+  int zchunk = 32;               // planes marched by one CTA of the 3-D kernel (DGB_FV_ZCHUNK overrides)
   dgb_view view;
   dgb_mapper mapper;
   FvProblem problem;
@@ -203,8 +320,17 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
   dim3 grid((a.region.size[0]+FBX-1)/FBX, (a.region.size[1]+FBY-1)/FBY, v.dim > 2 ? a.region.size[2] : 1);
   if (a.region.size[0] <= 0 || a.region.size[1] <= 0 || (v.dim > 2 && a.region.size[2] <= 0)) return DGB_OK;
   if (v.dim == 3) {
-    if (fv->mode == DGB_FV_EXACT) k_fv_step<3, DGB_FV_EXACT, REDUCE_ONLY><<<grid, block, 0, stream>>>(v, a);
-    else k_fv_step<3, DGB_FV_SEPARABLE, REDUCE_ONLY><<<grid, block, 0, stream>>>(v, a);
+    const int zc = fv->zchunk;
+    dim3 mblock(MBX, MBY, 1);
+    dim3 mgrid((a.region.size[0]+MBX-1)/MBX, (a.region.size[1]+MBY-1)/MBY, (a.region.size[2]+zc-1)/zc);
+    const bool exact = fv->mode == DGB_FV_EXACT;
+    if (fv->problem.id == 1) {
+      if (exact) k_fv_march<DGB_FV_EXACT, 1, REDUCE_ONLY><<<mgrid, mblock, 0, stream>>>(v, a, zc);
+      else k_fv_march<DGB_FV_SEPARABLE, 1, REDUCE_ONLY><<<mgrid, mblock, 0, stream>>>(v, a, zc);
+    } else {
+      if (exact) k_fv_march<DGB_FV_EXACT, 0, REDUCE_ONLY><<<mgrid, mblock, 0, stream>>>(v, a, zc);
+      else k_fv_march<DGB_FV_SEPARABLE, 0, REDUCE_ONLY><<<mgrid, mblock, 0, stream>>>(v, a, zc);
+    }
   } else {
     if (fv->mode == DGB_FV_EXACT) k_fv_step<2, DGB_FV_EXACT, REDUCE_ONLY><<<grid, block, 0, stream>>>(v, a);
     else k_fv_step<2, DGB_FV_SEPARABLE, REDUCE_ONLY><<<grid, block, 0, stream>>>(v, a);
@@ -245,6 +371,7 @@ int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host
     if (nparams > 12) throw ArgError("at most 12 problem parameters");
     std::unique_ptr<dgb_fv> fv(new dgb_fv);
     fv->grid = g; fv->comm = comm; fv->level = level; fv->mode = mode;
+    if (const char* e = getenv("DGB_FV_ZCHUNK")) { int z = atoi(e); if (z > 0) fv->zchunk = z; }
     if (int rc = make_view(g, level, &fv->view)) return rc;
     if (g->me.nranks > 1 && !comm) throw ArgError("a dgb_comm is required on a multi-rank grid");
     const uint32_t block[4] = {1,0,0,0};
