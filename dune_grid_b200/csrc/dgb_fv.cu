@@ -58,6 +58,7 @@ struct FvArgs {
   double* slotOut;       // max_i sum_out for the next step
   double* slotZero;      // slot to clear for the step after next
   double* dtOut;         // dt actually used
+  const double* consts;  // device constants {0, boundary value} (upwind sources of faces without a stored neighbour)
 };
 
 // EXACT: the arithmetic of the per-entity CPU loop, operation by operation (bit-identical results).
@@ -142,25 +143,26 @@ __global__ void __launch_bounds__(FBX*FBY) k_fv_step(const __grid_constant__ dgb
   }
 }
 
-// ---- 3-D production kernel: z-marching --------------------------------------------------------------------
-// A CTA owns an (MBX x MBY) column tile of the region and marches over ZC consecutive z-planes. Everything that
+// ---- 3-D production kernel: z-marching with a register prefetch queue ---------------------------------------
+// A CTA owns a (BX x BY) column tile of the region and marches over ZC consecutive z-planes. Everything that
 // does not depend on z (x/y coordinates, reciprocal widths, x/y neighbour and boundary flags, velocity terms that
 // are z-invariant, the time step) is computed once per thread; the z-neighbours of a cell are carried in registers
-// (c_below, c_here, c_above), so each cell costs ONE streaming load of the plane above plus the x/y inflow
-// neighbours, which hit L1/L2 (they are the streaming loads of adjacent threads / rows). HBM traffic stays at
-// 8 B read + 8 B write per cell; the CFL max is reduced per thread over its column, then once per CTA.
-static constexpr int MBX = 128, MBY = 4;
-
+// (c_below, c_here, c_above). The value of the plane above is not loaded when it is needed but PF planes ahead,
+// into a register queue: every thread keeps PF+1 independent 8-byte loads in flight, which is what covers the
+// HBM latency (Little's law: 6.5 TB/s x ~0.8 us = 5 MB in flight = 35 KB per SM = 1024 threads x (PF+1) x 8 B
+// for PF = 4). The x/y inflow neighbours are the streaming loads of adjacent threads / rows issued PF iterations
+// earlier, so they hit L1 (tile interior) or L2 (tile edge). HBM traffic stays at 8 B read + 8 B write per cell;
+// the CFL max is reduced per thread over its column, then by warp shuffles, then once per CTA.
 template<int PROBLEM>
 __device__ __forceinline__ void fv_velocity3(const FvProblem& q, const double* x, double* u) {
   if (PROBLEM == 1) { u[0] = -q.p[0]*(x[1]-0.5); u[1] = q.p[0]*(x[0]-0.5); u[2] = 0.0; }
   else { u[0] = q.p[0]; u[1] = q.p[1]; u[2] = q.p[2]; }
 }
 
-template<int MODE, int PROBLEM, bool REDUCE_ONLY>
-__global__ void __launch_bounds__(MBX*MBY) k_fv_march(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a, const int zc) {
-  const int i0 = blockIdx.x*MBX + threadIdx.x;
-  const int i1 = blockIdx.y*MBY + threadIdx.y;
+template<int MODE, int PROBLEM, bool REDUCE_ONLY, int PF, int BX, int BY>
+__global__ void __launch_bounds__(BX*BY) k_fv_march(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a, const int zc) {
+  const int i0 = blockIdx.x*BX + threadIdx.x;
+  const int i1 = blockIdx.y*BY + threadIdx.y;
   const int z0 = blockIdx.z*zc;
   const int zn = min(zc, a.region.size[2]-z0);
   double sum_max = 0.0;
@@ -190,11 +192,17 @@ __global__ void __launch_bounds__(MBX*MBY) k_fv_march(const __grid_constant__ dg
     const bool bdy0 = !pery && cy == 0, bdy1 = !pery && cy+1 == v.N[1];
     const double dt = REDUCE_ONLY ? 0.0 : 0.99*(1.0/(*a.slotIn));
     const double* p = a.c + idx0;
+    // last plane offset (relative to cz0) that holds a stored cell this thread may read: the plane above the
+    // chunk if it exists (yaspgridintersection.hh:75-82, neighbor() of the +z face)
+    const int kload = min(zn, ov.origin[2]+ov.size[2]-1-cz0);
     double c_below = 0.0, c_here = 0.0, c_above = 0.0;
+    double q[PF > 0 ? PF : 1];
     if (!REDUCE_ONLY) {
       const bool nb_first = cz0 > ov.origin[2] && cz0 <= ov.origin[2]+ov.size[2]-1;
       if (nb_first) c_below = __ldg(p - sz);
       c_here = __ldg(p);
+#pragma unroll
+      for (int j = 0; j < PF; ++j) q[j] = (1+j <= kload) ? __ldg(p + (long long)(1+j)*sz) : 0.0;
     }
     double llz = (MODE == DGB_FV_SEPARABLE) ? __ldg(a.tab.xv[2]+(cz0-a.tab.first[2])) : vertex_coord(v, 2, cz0);
     for (int k = 0; k < zn; ++k) {
@@ -209,7 +217,14 @@ __global__ void __launch_bounds__(MBX*MBY) k_fv_march(const __grid_constant__ dg
       const bool nbz0 = cz > ov.origin[2] && cz <= ov.origin[2]+ov.size[2]-1;
       const bool nbz1 = cz+1 > ov.origin[2] && cz+1 <= ov.origin[2]+ov.size[2]-1;
       const bool bdz0 = !perz && cz == 0, bdz1 = !perz && cz+1 == v.N[2];
-      if (!REDUCE_ONLY && nbz1) c_above = __ldg(p + sz);
+      if (!REDUCE_ONLY) {
+        if (PF > 0) {
+          c_above = q[0];
+#pragma unroll
+          for (int j = 0; j+1 < PF; ++j) q[j] = q[j+1];
+          q[PF > 0 ? PF-1 : 0] = (k+1+PF <= kload) ? __ldg(p + (long long)(1+PF)*sz) : 0.0;
+        } else if (nbz1) c_above = __ldg(p + sz);
+      }
       double vol = 1.0, ax = 1.0, ay = 1.0, az = 1.0;
       if (MODE == DGB_FV_EXACT) { vol = (wx*wy)*wz; ax = wy*wz; ay = wx*wz; az = wx*wy; }
       double sum = 0.0, upd = 0.0;
@@ -235,9 +250,8 @@ __global__ void __launch_bounds__(MBX*MBY) k_fv_march(const __grid_constant__ dg
 #undef DGB_FACE
       sum_max = fmax(sum_max, sum);
       if (!REDUCE_ONLY) {
-        const long long idx = idx0 + (long long)k*sz;
-        if (a.update) a.update[idx] = upd;
-        if (a.cnew) a.cnew[idx] = c_here + dt*upd;
+        if (a.update) a.update[idx0 + (long long)k*sz] = upd;
+        if (a.cnew) __stcs(a.cnew + idx0 + (long long)k*sz, c_here + dt*upd);
         c_below = c_here; c_here = c_above;
       }
       p += sz; llz = urz;
@@ -245,13 +259,236 @@ __global__ void __launch_bounds__(MBX*MBY) k_fv_march(const __grid_constant__ dg
     if (!REDUCE_ONLY && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = dt;
   }
   for (int off = 16; off > 0; off >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, off));
-  __shared__ double part[MBX*MBY/32];
-  const int tid = threadIdx.y*MBX + threadIdx.x;
+  __shared__ double part[BX*BY/32];
+  const int tid = threadIdx.y*BX + threadIdx.x;
   if ((tid & 31) == 0) part[tid >> 5] = sum_max;
   __syncthreads();
   if (tid == 0) {
     double m = 0.0;
-    for (int k = 0; k < MBX*MBY/32; ++k) m = fmax(m, part[k]);
+    for (int k = 0; k < BX*BY/32; ++k) m = fmax(m, part[k]);
+    if (m > 0.0) atomic_max_nonneg(a.slotOut, m);
+    if (a.slotZero && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *a.slotZero = 0.0;
+  }
+}
+
+// ---- 3-D separable-mode production kernel -------------------------------------------------------------------
+// Same decomposition as k_fv_march, specialised for DGB_FV_SEPARABLE with a velocity field that does not depend
+// on z (both compiled-in problems): the four x/y face factors (u.n)/w, their upwind decisions, the neighbour /
+// boundary classification of those faces and the partial CFL sum are then properties of the COLUMN and are
+// evaluated once per thread; per cell only  value*factor  products remain. The arithmetic per cell keeps the
+// reference order  upd = ((((((0 - t0) - t1) - t2) - t3) - t4) - t5),  t_k = c_upwind(k) * factor(k)  (faces in
+// intersection order -x,+x,-y,+y,-z,+z), so results equal the general kernel's bit for bit.
+//  * CFL: the sum of a cell is  sxy + [uz != 0] |uz|*rw(z)  with at most one z face flowing out; rounded addition
+//    and multiplication are monotone, so its maximum over the column is taken at the largest rw(z) of the chunk,
+//    which one warp-wide max finds before the loop - the loop body carries no reduction at all.
+//  * Fast path (warps in which every lane has, per axis, one inflow and one outflow face and the direction is the
+//    same for all 32 lanes - every warp of a uniform flow): the loop is instantiated per direction triple, so no
+//    per-face select or predicate remains. The upwind x/y values are read through per-lane pointers that advance
+//    by one plane per cell, or by nothing when they point at the boundary value b (inflow through the physical
+//    boundary) or at 0 (no neighbour and no boundary: overlap 0), so boundary columns need no special code.
+//    A zero velocity component counts as "positive": its two terms are +-0 and change nothing.
+//  * Slow path (mixed, converging or diverging warps): per-lane flags, same arithmetic.
+//  * The PF-deep register queue of planes above is indexed statically (the k loop is unrolled PF times).
+struct FvSepLane {
+  double f0, f1, f2, f3, un4, un5, dt, zhigh;
+  const double* p; double* w;
+  const double* px; const double* py;       // upwind x / y neighbour (or constant) of the current cell
+  long long sx8, sy8;                        // their strides per plane in bytes (plane size, or 0 for constants)
+  long long sz8;
+  const double* rwz;
+  int zn, kload;
+};
+
+template<int PF, bool DX, bool DY, bool DZ>
+__device__ __forceinline__ void fv_sep_fast(FvSepLane L, double c_below, double c_here, double (&q)[8]) {
+  const char* p = reinterpret_cast<const char*>(L.p);
+  const char* pn = p + (1+PF)*L.sz8;
+  char* w = reinterpret_cast<char*>(L.w);
+  const char* px = reinterpret_cast<const char*>(L.px);
+  const char* py = reinterpret_cast<const char*>(L.py);
+  const double* rwz = L.rwz;
+#define DGB_FAST_CELL(SLOT, GUARD)                                                                             \
+  {                                                                                                            \
+    const double c_above = SLOT;                                                                               \
+    if (!(GUARD) || k+1+PF <= L.kload) SLOT = __ldg(reinterpret_cast<const double*>(pn)); else SLOT = L.zhigh; \
+    const double rw = __ldg(rwz);                                                                              \
+    const double nx = __ldg(reinterpret_cast<const double*>(px)), ny = __ldg(reinterpret_cast<const double*>(py)); \
+    double upd = 0.0 - (DX ? nx : c_here)*L.f0;                                                                \
+    upd -= (DX ? c_here : nx)*L.f1;                                                                            \
+    upd -= (DY ? ny : c_here)*L.f2;                                                                            \
+    upd -= (DY ? c_here : ny)*L.f3;                                                                            \
+    upd -= (DZ ? c_below : c_here)*(L.un4*rw);                                                                 \
+    upd -= (DZ ? c_here : c_above)*(L.un5*rw);                                                                 \
+    __stcs(reinterpret_cast<double*>(w), c_here + L.dt*upd);                                                   \
+    c_below = c_here; c_here = c_above;                                                                        \
+    p += L.sz8; pn += L.sz8; w += L.sz8; px += L.sx8; py += L.sy8; ++rwz; ++k;                                 \
+  }
+  int k = 0;
+  const int kmain = max(0, min(L.zn, L.kload-PF)/PF*PF);
+  while (k < kmain) {
+    DGB_FAST_CELL(q[0], false)
+    if (PF > 1) DGB_FAST_CELL(q[1], false)
+    if (PF > 2) DGB_FAST_CELL(q[2], false)
+    if (PF > 3) DGB_FAST_CELL(q[3], false)
+    if (PF > 4) DGB_FAST_CELL(q[4], false)
+    if (PF > 5) DGB_FAST_CELL(q[5], false)
+    if (PF > 6) DGB_FAST_CELL(q[6], false)
+    if (PF > 7) DGB_FAST_CELL(q[7], false)
+  }
+  while (k < L.zn) {
+    DGB_FAST_CELL(q[0], true)
+    if (PF > 1 && k < L.zn) DGB_FAST_CELL(q[1], true)
+    if (PF > 2 && k < L.zn) DGB_FAST_CELL(q[2], true)
+    if (PF > 3 && k < L.zn) DGB_FAST_CELL(q[3], true)
+    if (PF > 4 && k < L.zn) DGB_FAST_CELL(q[4], true)
+    if (PF > 5 && k < L.zn) DGB_FAST_CELL(q[5], true)
+    if (PF > 6 && k < L.zn) DGB_FAST_CELL(q[6], true)
+    if (PF > 7 && k < L.zn) DGB_FAST_CELL(q[7], true)
+  }
+#undef DGB_FAST_CELL
+}
+
+// per-lane upwind flags: bit m (m<4): face m flows out; bit 4+m: the upwind value of face m is a stored neighbour;
+// alt[m]: the boundary value otherwise (0: the face contributes nothing)
+template<int PF>
+__device__ __noinline__ void fv_sep_slow(FvSepLane L, double c_below, double c_here, double (&q)[8], unsigned flags,
+                                         double alt0, double alt1, double alt2, double alt3, int sy) {
+  const double* p = L.p; double* w = L.w;
+  const long long sz = L.sz8/8;
+  const bool self4 = L.un4 >= 0.0, self5 = L.un5 >= 0.0;                 // widths are positive: sign(un*rw) = sign(un)
+  for (int k = 0; k < L.zn; ++k) {
+    const double c_above = q[0];
+#pragma unroll
+    for (int j = 0; j+1 < PF; ++j) q[j] = q[j+1];
+    q[PF-1] = (k+1+PF <= L.kload) ? __ldg(p + (1+PF)*sz) : L.zhigh;
+    const double rw = __ldg(L.rwz + k);
+    double val, upd;
+    val = alt0; if (flags & 16u) val = __ldg(p - 1);   if (flags & 1u) val = c_here; upd = 0.0 - val*L.f0;
+    val = alt1; if (flags & 32u) val = __ldg(p + 1);   if (flags & 2u) val = c_here; upd -= val*L.f1;
+    val = alt2; if (flags & 64u) val = __ldg(p - sy);  if (flags & 4u) val = c_here; upd -= val*L.f2;
+    val = alt3; if (flags & 128u) val = __ldg(p + sy); if (flags & 8u) val = c_here; upd -= val*L.f3;
+    upd -= (self4 ? c_here : c_below)*(L.un4*rw);
+    upd -= (self5 ? c_here : c_above)*(L.un5*rw);
+    __stcs(w, c_here + L.dt*upd);
+    c_below = c_here; c_here = c_above;
+    p += sz; w += sz;
+  }
+}
+
+template<int PROBLEM, int PF, int BX, int BY, int MINB>
+__global__ void __launch_bounds__(BX*BY, MINB) k_fv_march_sep(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a, const int zc) {
+  static_assert(PF >= 1 && PF <= 8, "prefetch depth");
+  const int i0 = blockIdx.x*BX + threadIdx.x;
+  const int i1 = blockIdx.y*BY + threadIdx.y;
+  const int z0 = blockIdx.z*zc;
+  const int zn = min(zc, a.region.size[2]-z0);
+  const int cz0 = a.region.origin[2]+z0;
+  const bool active = i0 < a.region.size[0] && i1 < a.region.size[1];
+  // largest reciprocal z width of the chunk (one table entry per lane, warp max)
+  const double* rwz = a.tab.rw[2] + (cz0-a.tab.first[2]);
+  double rwmax = 0.0;
+  for (int k = threadIdx.x & 31; k < zn; k += 32) rwmax = fmax(rwmax, __ldg(rwz + k));
+  for (int o = 16; o > 0; o >>= 1) rwmax = fmax(rwmax, __shfl_xor_sync(0xffffffffu, rwmax, o));
+  double sum_max = 0.0;
+  FvSepLane L;
+  L.f0 = L.f1 = L.f2 = L.f3 = L.un4 = L.un5 = 0.0;
+  double alt0 = 0, alt1 = 0, alt2 = 0, alt3 = 0;
+  unsigned flags = 0;
+  const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+  const dgb_box& ov = v.comp[0].box[DGB_BOX_OVERLAP];
+  const int sy = of.size[0];
+  const long long sz = (long long)sy*of.size[1];
+  const bool perz = v.periodic >> 2 & 1u;
+  const int ovz0 = ov.origin[2], ovz1 = ovz0 + ov.size[2]-1;              // neighbor(): ovz0 < cz+side <= ovz1
+  const double bval = fv_boundary(a.problem, nullptr);
+  const int cx = a.region.origin[0]+i0, cy = a.region.origin[1]+i1;
+  if (active) {
+    const int tx = cx-a.tab.first[0], ty = cy-a.tab.first[1];
+    const double llx = __ldg(a.tab.xv[0]+tx), urx = __ldg(a.tab.xv[0]+tx+1), xcx = __ldg(a.tab.xc[0]+tx), rwx = __ldg(a.tab.rw[0]+tx);
+    const double lly = __ldg(a.tab.xv[1]+ty), ury = __ldg(a.tab.xv[1]+ty+1), xcy = __ldg(a.tab.xc[1]+ty), rwy = __ldg(a.tab.rw[1]+ty);
+    const double xcz = __ldg(a.tab.xc[2]+(cz0-a.tab.first[2]));          // any z: the velocity does not depend on it
+    const bool perx = v.periodic & 1u, pery = v.periodic >> 1 & 1u;
+    double sxy = 0.0;
+#define DGB_COLFACE(K, F, ALT, DIRX, SIDE, FCX, FCY, RW, NB, BD)                                               \
+    {                                                                                                          \
+      const double fc[3] = { FCX, FCY, xcz };                                                                  \
+      double u[3]; fv_velocity3<PROBLEM>(a.problem, fc, u);                                                    \
+      const double un = (SIDE) ? u[DIRX] : -u[DIRX];                                                           \
+      F = un*(RW);                                                                                             \
+      if (F >= 0.0) { sxy += F; flags |= 1u << K; }                                                            \
+      else if (NB) flags |= 16u << K;                                                                          \
+      else if (BD) { ALT = bval; flags |= 256u << K; }                                                         \
+    }
+    DGB_COLFACE(0, L.f0, alt0, 0, 0, llx, xcy, rwx, cx > ov.origin[0] && cx <= ov.origin[0]+ov.size[0]-1, !perx && cx == 0)
+    DGB_COLFACE(1, L.f1, alt1, 0, 1, urx, xcy, rwx, cx+1 > ov.origin[0] && cx+1 <= ov.origin[0]+ov.size[0]-1, !perx && cx+1 == v.N[0])
+    DGB_COLFACE(2, L.f2, alt2, 1, 0, xcx, lly, rwy, cy > ov.origin[1] && cy <= ov.origin[1]+ov.size[1]-1, !pery && cy == 0)
+    DGB_COLFACE(3, L.f3, alt3, 1, 1, xcx, ury, rwy, cy+1 > ov.origin[1] && cy+1 <= ov.origin[1]+ov.size[1]-1, !pery && cy+1 == v.N[1])
+#undef DGB_COLFACE
+    {
+      const double fc[3] = { xcx, xcy, xcz };
+      double u[3]; fv_velocity3<PROBLEM>(a.problem, fc, u);
+      L.un4 = -u[2]; L.un5 = u[2];
+    }
+    // CFL sum of the column: faces in order, the z faces with the largest reciprocal width of the chunk
+    double sum = sxy;
+    if (L.un4 >= 0.0) sum += L.un4*rwmax;
+    if (L.un5 >= 0.0) sum += L.un5*rwmax;
+    sum_max = sum;
+  }
+  // direction per axis: 1 = positive (inflow through the low face; also zero velocity), 0 = negative, 2 = neither
+  int dx = 2, dy = 2, dz = 2;
+  if (active) {
+    const bool o0 = flags & 1u, o1 = flags & 2u, o2 = flags & 4u, o3 = flags & 8u;
+    if ((!o0 && o1) || (o0 && o1 && L.f0 == 0.0 && L.f1 == 0.0)) dx = 1; else if (o0 && !o1) dx = 0;
+    if ((!o2 && o3) || (o2 && o3 && L.f2 == 0.0 && L.f3 == 0.0)) dy = 1; else if (o2 && !o3) dy = 0;
+    if (L.un5 >= 0.0) dz = 1; else dz = 0;                                // un4 = -un5: one of them is < 0 unless both are 0
+  }
+  const unsigned amask = __ballot_sync(0xffffffffu, active);
+  const int lead = amask ? __ffs(amask)-1 : 0;
+  const int ldx = __shfl_sync(0xffffffffu, dx, lead), ldy = __shfl_sync(0xffffffffu, dy, lead), ldz = __shfl_sync(0xffffffffu, dz, lead);
+  const bool fast = __all_sync(0xffffffffu, !active || (dx == ldx && dy == ldy && dz == ldz && dx != 2 && dy != 2));
+  if (active) {
+    // value seen through the bottom face of the lowest / the top face of the highest cell of the stored box
+    const double zlow = (!perz && ovz0 == 0) ? bval : 0.0;
+    L.zhigh = (!perz && ovz1+1 == v.N[2]) ? bval : 0.0;
+    L.dt = 0.99*(1.0/(*a.slotIn));
+    const long long idx0 = (long long)(cz0-of.origin[2])*sz + (long long)(cy-of.origin[1])*sy + (cx-of.origin[0]);
+    L.p = a.c + idx0; L.w = a.cnew + idx0; L.sz8 = sz*8; L.rwz = rwz; L.zn = zn;
+    L.kload = min(zn, ovz1-cz0);                                          // last plane offset holding a stored cell
+    const double c_below = (cz0 > ovz0) ? __ldg(L.p - sz) : zlow;
+    const double c_here = __ldg(L.p);
+    double q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = (j < PF && 1+j <= L.kload) ? __ldg(L.p + (long long)(1+j)*sz) : L.zhigh;
+    if (fast) {
+      // upwind x / y sources: stored neighbour (advances with the column), boundary value or zero (fixed address)
+      const double* consts = a.consts;                                    // consts[0] = 0, consts[1] = boundary value
+      const int mx = dx ? 0 : 1, my = dy ? 2 : 3;                         // inflow face of the axis
+      if (flags >> (4+mx) & 1u) { L.px = L.p + (dx ? -1 : 1); L.sx8 = L.sz8; }
+      else { L.px = consts + (flags >> (8+mx) & 1u); L.sx8 = 0; }
+      if (flags >> (4+my) & 1u) { L.py = L.p + (dy ? -sy : sy); L.sy8 = L.sz8; }
+      else { L.py = consts + (flags >> (8+my) & 1u); L.sy8 = 0; }
+      switch (ldx*4 + ldy*2 + ldz) {
+        case 0: fv_sep_fast<PF, false, false, false>(L, c_below, c_here, q); break;
+        case 1: fv_sep_fast<PF, false, false, true>(L, c_below, c_here, q); break;
+        case 2: fv_sep_fast<PF, false, true, false>(L, c_below, c_here, q); break;
+        case 3: fv_sep_fast<PF, false, true, true>(L, c_below, c_here, q); break;
+        case 4: fv_sep_fast<PF, true, false, false>(L, c_below, c_here, q); break;
+        case 5: fv_sep_fast<PF, true, false, true>(L, c_below, c_here, q); break;
+        case 6: fv_sep_fast<PF, true, true, false>(L, c_below, c_here, q); break;
+        default: fv_sep_fast<PF, true, true, true>(L, c_below, c_here, q); break;
+      }
+    } else fv_sep_slow<PF>(L, c_below, c_here, q, flags, alt0, alt1, alt2, alt3, sy);
+    if (a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = L.dt;
+  }
+  for (int o = 16; o > 0; o >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, o));
+  __shared__ double part[BX*BY/32];
+  const int tid = threadIdx.y*BX + threadIdx.x;
+  if ((tid & 31) == 0) part[tid >> 5] = sum_max;
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int k = 0; k < BX*BY/32; ++k) m = fmax(m, part[k]);
     if (m > 0.0) atomic_max_nonneg(a.slotOut, m);
     if (a.slotZero && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *a.slotZero = 0.0;
   }
@@ -297,12 +534,13 @@ struct dgb_fv {
   dgb_comm* comm = nullptr;
   int level = 0, mode = 0;
   int zchunk = 32;               // planes marched by one CTA of the 3-D kernel (DGB_FV_ZCHUNK overrides)
+  int variant = 0;               // tuning variant of the 3-D kernel (DGB_FV_VARIANT overrides), see march_variants
   dgb_view view;
   dgb_mapper mapper;
   FvProblem problem;
   FvTables tab;
   double* dTables = nullptr;
-  double* dSlots = nullptr;        // 3 rotating max-sum slots + dt
+  double* dSlots = nullptr;        // 3 rotating max-sum slots + dt + the constants {0, boundary value}
   long long step = 0;
   bool bootstrapped = false;
   int64_t launches = 0;
@@ -321,16 +559,47 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
   if (a.region.size[0] <= 0 || a.region.size[1] <= 0 || (v.dim > 2 && a.region.size[2] <= 0)) return DGB_OK;
   if (v.dim == 3) {
     const int zc = fv->zchunk;
-    dim3 mblock(MBX, MBY, 1);
-    dim3 mgrid((a.region.size[0]+MBX-1)/MBX, (a.region.size[1]+MBY-1)/MBY, (a.region.size[2]+zc-1)/zc);
     const bool exact = fv->mode == DGB_FV_EXACT;
-    if (fv->problem.id == 1) {
-      if (exact) k_fv_march<DGB_FV_EXACT, 1, REDUCE_ONLY><<<mgrid, mblock, 0, stream>>>(v, a, zc);
-      else k_fv_march<DGB_FV_SEPARABLE, 1, REDUCE_ONLY><<<mgrid, mblock, 0, stream>>>(v, a, zc);
+    const int pb = fv->problem.id == 1 ? 1 : 0;
+#define DGB_MARCH(MODE_, PROB_, PF_, BX_, BY_)                                                                       \
+    { dim3 mblock(BX_, BY_, 1);                                                                                      \
+      dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
+      k_fv_march<MODE_, PROB_, REDUCE_ONLY, PF_, BX_, BY_><<<mgrid, mblock, 0, stream>>>(v, a, zc); }
+    if (exact) {
+      if (pb) DGB_MARCH(DGB_FV_EXACT, 1, 4, 128, 4) else DGB_MARCH(DGB_FV_EXACT, 0, 4, 128, 4)
+    } else if (REDUCE_ONLY || a.update || !a.cnew) {
+      if (pb) DGB_MARCH(DGB_FV_SEPARABLE, 1, 4, 128, 4) else DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4)
     } else {
-      if (exact) k_fv_march<DGB_FV_EXACT, 0, REDUCE_ONLY><<<mgrid, mblock, 0, stream>>>(v, a, zc);
-      else k_fv_march<DGB_FV_SEPARABLE, 0, REDUCE_ONLY><<<mgrid, mblock, 0, stream>>>(v, a, zc);
+#define DGB_SEP(PF_, BX_, BY_, MINB_)                                                                                \
+    { dim3 mblock(BX_, BY_, 1);                                                                                      \
+      dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
+      if (pb) k_fv_march_sep<1, PF_, BX_, BY_, MINB_><<<mgrid, mblock, 0, stream>>>(v, a, zc);                       \
+      else k_fv_march_sep<0, PF_, BX_, BY_, MINB_><<<mgrid, mblock, 0, stream>>>(v, a, zc); }
+      switch (fv->variant) {                  // tuning variants (prefetch depth, tile, occupancy target)
+        default:
+        case 0: DGB_SEP(4, 128, 4, 2) break;
+        case 1: DGB_SEP(1, 128, 4, 2) break;
+        case 2: DGB_SEP(2, 128, 4, 2) break;
+        case 3: DGB_SEP(8, 128, 4, 2) break;
+        case 4: DGB_SEP(4, 64, 8, 2) break;
+        case 5: DGB_SEP(4, 32, 16, 2) break;
+        case 6: DGB_SEP(4, 64, 4, 4) break;
+        case 7: DGB_SEP(8, 64, 4, 4) break;
+        case 8: DGB_SEP(4, 128, 2, 4) break;
+        case 9: DGB_SEP(8, 128, 2, 4) break;
+        case 10: DGB_SEP(2, 128, 4, 3) break;
+        case 11: DGB_SEP(4, 128, 4, 3) break;
+        case 12: DGB_SEP(2, 128, 2, 6) break;
+        case 13: DGB_SEP(4, 128, 2, 6) break;
+        case 14: DGB_SEP(4, 256, 2, 2) break;
+        case 15: DGB_SEP(6, 128, 4, 2) break;
+        case 16: DGB_SEP(2, 128, 4, 4) break;
+        case 17: DGB_SEP(2, 128, 2, 8) break;
+        case 99: DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4) break;          // the general kernel, for comparison
+      }
+#undef DGB_SEP
     }
+#undef DGB_MARCH
   } else {
     if (fv->mode == DGB_FV_EXACT) k_fv_step<2, DGB_FV_EXACT, REDUCE_ONLY><<<grid, block, 0, stream>>>(v, a);
     else k_fv_step<2, DGB_FV_SEPARABLE, REDUCE_ONLY><<<grid, block, 0, stream>>>(v, a);
@@ -344,7 +613,7 @@ static FvArgs base_args(dgb_fv* fv) {
   FvArgs a{};
   const dgb_box& in = fv->view.comp[0].box[DGB_BOX_INTERIOR];
   for (int i = 0; i < 3; ++i) { a.region.origin[i] = in.origin[i]; a.region.size[i] = i < fv->view.dim ? in.size[i] : 1; }
-  a.problem = fv->problem; a.tab = fv->tab;
+  a.problem = fv->problem; a.tab = fv->tab; a.consts = fv->dSlots + 4;
   return a;
 }
 
@@ -372,14 +641,16 @@ int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host
     std::unique_ptr<dgb_fv> fv(new dgb_fv);
     fv->grid = g; fv->comm = comm; fv->level = level; fv->mode = mode;
     if (const char* e = getenv("DGB_FV_ZCHUNK")) { int z = atoi(e); if (z > 0) fv->zchunk = z; }
+    if (const char* e = getenv("DGB_FV_VARIANT")) fv->variant = atoi(e);
     if (int rc = make_view(g, level, &fv->view)) return rc;
     if (g->me.nranks > 1 && !comm) throw ArgError("a dgb_comm is required on a multi-rank grid");
     const uint32_t block[4] = {1,0,0,0};
     dgb_mapper_init(&fv->view, block, &fv->mapper);
     fv->problem.id = problem;
     for (int i = 0; i < 12; ++i) fv->problem.p[i] = i < nparams ? params_host[i] : 0.0;
-    DGB_CUDA(cudaMalloc(&fv->dSlots, 4*sizeof(double)));
-    DGB_CUDA(cudaMemset(fv->dSlots, 0, 4*sizeof(double)));
+    DGB_CUDA(cudaMalloc(&fv->dSlots, 6*sizeof(double)));
+    DGB_CUDA(cudaMemset(fv->dSlots, 0, 6*sizeof(double)));
+    DGB_CUDA(cudaMemcpy(fv->dSlots + 5, &fv->problem.p[3], sizeof(double), cudaMemcpyHostToDevice));   // {0, b}: FvArgs::consts
     // per-axis tables over the stored cell range
     const dgb_view& v = fv->view;
     const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
