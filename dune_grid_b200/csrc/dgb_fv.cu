@@ -290,86 +290,81 @@ __global__ void __launch_bounds__(BX*BY) k_fv_march(const __grid_constant__ dgb_
 //  * Slow path (mixed, converging or diverging warps): per-lane flags, same arithmetic.
 //  * The PF-deep register queue of planes above is indexed statically (the k loop is unrolled PF times).
 struct FvSepLane {
-  double f0, f1, f2, f3, un4, un5, dt, zhigh;
-  const double* p; double* w;
-  const double* px; const double* py;       // upwind x / y neighbour (or constant) of the current cell
-  long long sx8, sy8;                        // their strides per plane in bytes (plane size, or 0 for constants)
-  long long sz8;
-  const double* rwz;
-  int zn, kload;
+  double f0, f1, f2, f3;       // x/y face factors in intersection order (0 for an inflow face without stored neighbour)
+  double tbx, tby;             // constant term b*factor of an x / y inflow face on the physical boundary, else 0
+  double un5, dt;              // +z normal velocity (that of -z is its negative), time step
+  const double* p;             // current cell in c; the cell of cnew is at byte offset dw (uniform)
+  int ox, oy;                  // element offsets of the upwind x / y neighbour (0 when there is none)
 };
 
 template<int PF, bool DX, bool DY, bool DZ>
-__device__ __forceinline__ void fv_sep_fast(FvSepLane L, double c_below, double c_here, double (&q)[8]) {
-  const char* p = reinterpret_cast<const char*>(L.p);
-  const char* pn = p + (1+PF)*L.sz8;
-  char* w = reinterpret_cast<char*>(L.w);
-  const char* px = reinterpret_cast<const char*>(L.px);
-  const char* py = reinterpret_cast<const char*>(L.py);
-  const double* rwz = L.rwz;
+__device__ __forceinline__ void fv_sep_fast(FvSepLane L, double c_below, double c_here, double q0, double q1, double q2, double q3,
+                                            double q4, double q5, double q6, double q7, const double zhigh, const long long sz,
+                                            const long long dw, const double* rwz, const int zn, const int kload) {
+  const double* p = L.p;
 #define DGB_FAST_CELL(SLOT, GUARD)                                                                             \
   {                                                                                                            \
     const double c_above = SLOT;                                                                               \
-    if (!(GUARD) || k+1+PF <= L.kload) SLOT = __ldg(reinterpret_cast<const double*>(pn)); else SLOT = L.zhigh; \
-    const double rw = __ldg(rwz);                                                                              \
-    const double nx = __ldg(reinterpret_cast<const double*>(px)), ny = __ldg(reinterpret_cast<const double*>(py)); \
+    if (!(GUARD) || k+1+PF <= kload) SLOT = __ldg(p + (1+PF)*sz); else SLOT = zhigh;                           \
+    const double f5 = L.un5*__ldg(rwz + k);                                                                    \
+    const double nx = __ldg(p + L.ox), ny = __ldg(p + L.oy);                                                   \
     double upd = 0.0 - (DX ? nx : c_here)*L.f0;                                                                \
+    if (DX) upd -= L.tbx;                                                                                      \
     upd -= (DX ? c_here : nx)*L.f1;                                                                            \
+    if (!DX) upd -= L.tbx;                                                                                     \
     upd -= (DY ? ny : c_here)*L.f2;                                                                            \
+    if (DY) upd -= L.tby;                                                                                      \
     upd -= (DY ? c_here : ny)*L.f3;                                                                            \
-    upd -= (DZ ? c_below : c_here)*(L.un4*rw);                                                                 \
-    upd -= (DZ ? c_here : c_above)*(L.un5*rw);                                                                 \
-    __stcs(reinterpret_cast<double*>(w), c_here + L.dt*upd);                                                   \
+    if (!DY) upd -= L.tby;                                                                                     \
+    upd -= (DZ ? c_below : c_here)*(-f5);                                                                      \
+    upd -= (DZ ? c_here : c_above)*f5;                                                                         \
+    __stcs(reinterpret_cast<double*>(reinterpret_cast<char*>(const_cast<double*>(p)) + dw), c_here + L.dt*upd); \
     c_below = c_here; c_here = c_above;                                                                        \
-    p += L.sz8; pn += L.sz8; w += L.sz8; px += L.sx8; py += L.sy8; ++rwz; ++k;                                 \
+    p += sz; ++k;                                                                                              \
   }
   int k = 0;
-  const int kmain = max(0, min(L.zn, L.kload-PF)/PF*PF);
+  const int kmain = max(0, min(zn, kload-PF)/PF*PF);
   while (k < kmain) {
-    DGB_FAST_CELL(q[0], false)
-    if (PF > 1) DGB_FAST_CELL(q[1], false)
-    if (PF > 2) DGB_FAST_CELL(q[2], false)
-    if (PF > 3) DGB_FAST_CELL(q[3], false)
-    if (PF > 4) DGB_FAST_CELL(q[4], false)
-    if (PF > 5) DGB_FAST_CELL(q[5], false)
-    if (PF > 6) DGB_FAST_CELL(q[6], false)
-    if (PF > 7) DGB_FAST_CELL(q[7], false)
+    DGB_FAST_CELL(q0, false)
+    if (PF > 1) DGB_FAST_CELL(q1, false)
+    if (PF > 2) DGB_FAST_CELL(q2, false)
+    if (PF > 3) DGB_FAST_CELL(q3, false)
+    if (PF > 4) DGB_FAST_CELL(q4, false)
+    if (PF > 5) DGB_FAST_CELL(q5, false)
+    if (PF > 6) DGB_FAST_CELL(q6, false)
+    if (PF > 7) DGB_FAST_CELL(q7, false)
   }
-  while (k < L.zn) {
-    DGB_FAST_CELL(q[0], true)
-    if (PF > 1 && k < L.zn) DGB_FAST_CELL(q[1], true)
-    if (PF > 2 && k < L.zn) DGB_FAST_CELL(q[2], true)
-    if (PF > 3 && k < L.zn) DGB_FAST_CELL(q[3], true)
-    if (PF > 4 && k < L.zn) DGB_FAST_CELL(q[4], true)
-    if (PF > 5 && k < L.zn) DGB_FAST_CELL(q[5], true)
-    if (PF > 6 && k < L.zn) DGB_FAST_CELL(q[6], true)
-    if (PF > 7 && k < L.zn) DGB_FAST_CELL(q[7], true)
+  while (k < zn) {
+    DGB_FAST_CELL(q0, true)
+    if (PF > 1 && k < zn) DGB_FAST_CELL(q1, true)
+    if (PF > 2 && k < zn) DGB_FAST_CELL(q2, true)
+    if (PF > 3 && k < zn) DGB_FAST_CELL(q3, true)
+    if (PF > 4 && k < zn) DGB_FAST_CELL(q4, true)
+    if (PF > 5 && k < zn) DGB_FAST_CELL(q5, true)
+    if (PF > 6 && k < zn) DGB_FAST_CELL(q6, true)
+    if (PF > 7 && k < zn) DGB_FAST_CELL(q7, true)
   }
 #undef DGB_FAST_CELL
 }
 
 // per-lane upwind flags: bit m (m<4): face m flows out; bit 4+m: the upwind value of face m is a stored neighbour;
-// alt[m]: the boundary value otherwise (0: the face contributes nothing)
-template<int PF>
-__device__ __noinline__ void fv_sep_slow(FvSepLane L, double c_below, double c_here, double (&q)[8], unsigned flags,
-                                         double alt0, double alt1, double alt2, double alt3, int sy) {
-  const double* p = L.p; double* w = L.w;
-  const long long sz = L.sz8/8;
-  const bool self4 = L.un4 >= 0.0, self5 = L.un5 >= 0.0;                 // widths are positive: sign(un*rw) = sign(un)
-  for (int k = 0; k < L.zn; ++k) {
-    const double c_above = q[0];
-#pragma unroll
-    for (int j = 0; j+1 < PF; ++j) q[j] = q[j+1];
-    q[PF-1] = (k+1+PF <= L.kload) ? __ldg(p + (1+PF)*sz) : L.zhigh;
-    const double rw = __ldg(L.rwz + k);
+// alt[m]: the boundary value otherwise (0: the face contributes nothing). No prefetch queue: this path is rare.
+__device__ __noinline__ void fv_sep_slow(const double* p, double* w, double f0, double f1, double f2, double f3, double un4, double un5,
+                                         double dt, double c_below, double zhigh, unsigned flags, double alt0, double alt1, double alt2,
+                                         double alt3, int sy, long long sz, const double* rwz, int zn, int kload) {
+  const bool self4 = un4 >= 0.0, self5 = un5 >= 0.0;                     // widths are positive: sign(un*rw) = sign(un)
+  double c_here = __ldg(p);
+  for (int k = 0; k < zn; ++k) {
+    const double c_above = (k+1 <= kload) ? __ldg(p + sz) : zhigh;
+    const double rw = __ldg(rwz + k);
     double val, upd;
-    val = alt0; if (flags & 16u) val = __ldg(p - 1);   if (flags & 1u) val = c_here; upd = 0.0 - val*L.f0;
-    val = alt1; if (flags & 32u) val = __ldg(p + 1);   if (flags & 2u) val = c_here; upd -= val*L.f1;
-    val = alt2; if (flags & 64u) val = __ldg(p - sy);  if (flags & 4u) val = c_here; upd -= val*L.f2;
-    val = alt3; if (flags & 128u) val = __ldg(p + sy); if (flags & 8u) val = c_here; upd -= val*L.f3;
-    upd -= (self4 ? c_here : c_below)*(L.un4*rw);
-    upd -= (self5 ? c_here : c_above)*(L.un5*rw);
-    __stcs(w, c_here + L.dt*upd);
+    val = alt0; if (flags & 16u) val = __ldg(p - 1);   if (flags & 1u) val = c_here; upd = 0.0 - val*f0;
+    val = alt1; if (flags & 32u) val = __ldg(p + 1);   if (flags & 2u) val = c_here; upd -= val*f1;
+    val = alt2; if (flags & 64u) val = __ldg(p - sy);  if (flags & 4u) val = c_here; upd -= val*f2;
+    val = alt3; if (flags & 128u) val = __ldg(p + sy); if (flags & 8u) val = c_here; upd -= val*f3;
+    upd -= (self4 ? c_here : c_below)*(un4*rw);
+    upd -= (self5 ? c_here : c_above)*(un5*rw);
+    __stcs(w, c_here + dt*upd);
     c_below = c_here; c_here = c_above;
     p += sz; w += sz;
   }
@@ -390,10 +385,8 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_march_sep(const __grid_const
   for (int k = threadIdx.x & 31; k < zn; k += 32) rwmax = fmax(rwmax, __ldg(rwz + k));
   for (int o = 16; o > 0; o >>= 1) rwmax = fmax(rwmax, __shfl_xor_sync(0xffffffffu, rwmax, o));
   double sum_max = 0.0;
-  FvSepLane L;
-  L.f0 = L.f1 = L.f2 = L.f3 = L.un4 = L.un5 = 0.0;
-  double alt0 = 0, alt1 = 0, alt2 = 0, alt3 = 0;
-  unsigned flags = 0;
+  double f0 = 0, f1 = 0, f2 = 0, f3 = 0, un4 = 0, un5 = 0, alt0 = 0, alt1 = 0, alt2 = 0, alt3 = 0;
+  unsigned flags = 0;                 // bit m: face m flows out; 4+m: upwind value is a stored neighbour; 8+m: boundary value
   const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
   const dgb_box& ov = v.comp[0].box[DGB_BOX_OVERLAP];
   const int sy = of.size[0];
@@ -419,29 +412,29 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_march_sep(const __grid_const
       else if (NB) flags |= 16u << K;                                                                          \
       else if (BD) { ALT = bval; flags |= 256u << K; }                                                         \
     }
-    DGB_COLFACE(0, L.f0, alt0, 0, 0, llx, xcy, rwx, cx > ov.origin[0] && cx <= ov.origin[0]+ov.size[0]-1, !perx && cx == 0)
-    DGB_COLFACE(1, L.f1, alt1, 0, 1, urx, xcy, rwx, cx+1 > ov.origin[0] && cx+1 <= ov.origin[0]+ov.size[0]-1, !perx && cx+1 == v.N[0])
-    DGB_COLFACE(2, L.f2, alt2, 1, 0, xcx, lly, rwy, cy > ov.origin[1] && cy <= ov.origin[1]+ov.size[1]-1, !pery && cy == 0)
-    DGB_COLFACE(3, L.f3, alt3, 1, 1, xcx, ury, rwy, cy+1 > ov.origin[1] && cy+1 <= ov.origin[1]+ov.size[1]-1, !pery && cy+1 == v.N[1])
+    DGB_COLFACE(0, f0, alt0, 0, 0, llx, xcy, rwx, cx > ov.origin[0] && cx <= ov.origin[0]+ov.size[0]-1, !perx && cx == 0)
+    DGB_COLFACE(1, f1, alt1, 0, 1, urx, xcy, rwx, cx+1 > ov.origin[0] && cx+1 <= ov.origin[0]+ov.size[0]-1, !perx && cx+1 == v.N[0])
+    DGB_COLFACE(2, f2, alt2, 1, 0, xcx, lly, rwy, cy > ov.origin[1] && cy <= ov.origin[1]+ov.size[1]-1, !pery && cy == 0)
+    DGB_COLFACE(3, f3, alt3, 1, 1, xcx, ury, rwy, cy+1 > ov.origin[1] && cy+1 <= ov.origin[1]+ov.size[1]-1, !pery && cy+1 == v.N[1])
 #undef DGB_COLFACE
     {
       const double fc[3] = { xcx, xcy, xcz };
       double u[3]; fv_velocity3<PROBLEM>(a.problem, fc, u);
-      L.un4 = -u[2]; L.un5 = u[2];
+      un4 = -u[2]; un5 = u[2];
     }
     // CFL sum of the column: faces in order, the z faces with the largest reciprocal width of the chunk
     double sum = sxy;
-    if (L.un4 >= 0.0) sum += L.un4*rwmax;
-    if (L.un5 >= 0.0) sum += L.un5*rwmax;
+    if (un4 >= 0.0) sum += un4*rwmax;
+    if (un5 >= 0.0) sum += un5*rwmax;
     sum_max = sum;
   }
   // direction per axis: 1 = positive (inflow through the low face; also zero velocity), 0 = negative, 2 = neither
   int dx = 2, dy = 2, dz = 2;
   if (active) {
     const bool o0 = flags & 1u, o1 = flags & 2u, o2 = flags & 4u, o3 = flags & 8u;
-    if ((!o0 && o1) || (o0 && o1 && L.f0 == 0.0 && L.f1 == 0.0)) dx = 1; else if (o0 && !o1) dx = 0;
-    if ((!o2 && o3) || (o2 && o3 && L.f2 == 0.0 && L.f3 == 0.0)) dy = 1; else if (o2 && !o3) dy = 0;
-    if (L.un5 >= 0.0) dz = 1; else dz = 0;                                // un4 = -un5: one of them is < 0 unless both are 0
+    if ((!o0 && o1) || (o0 && o1 && f0 == 0.0 && f1 == 0.0)) dx = 1; else if (o0 && !o1) dx = 0;
+    if ((!o2 && o3) || (o2 && o3 && f2 == 0.0 && f3 == 0.0)) dy = 1; else if (o2 && !o3) dy = 0;
+    dz = (un5 >= 0.0) ? 1 : 0;                                            // un4 = -un5
   }
   const unsigned amask = __ballot_sync(0xffffffffu, active);
   const int lead = amask ? __ffs(amask)-1 : 0;
@@ -450,40 +443,298 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_march_sep(const __grid_const
   if (active) {
     // value seen through the bottom face of the lowest / the top face of the highest cell of the stored box
     const double zlow = (!perz && ovz0 == 0) ? bval : 0.0;
-    L.zhigh = (!perz && ovz1+1 == v.N[2]) ? bval : 0.0;
-    L.dt = 0.99*(1.0/(*a.slotIn));
+    const double zhigh = (!perz && ovz1+1 == v.N[2]) ? bval : 0.0;
+    const double dt = 0.99*(1.0/(*a.slotIn));
     const long long idx0 = (long long)(cz0-of.origin[2])*sz + (long long)(cy-of.origin[1])*sy + (cx-of.origin[0]);
-    L.p = a.c + idx0; L.w = a.cnew + idx0; L.sz8 = sz*8; L.rwz = rwz; L.zn = zn;
-    L.kload = min(zn, ovz1-cz0);                                          // last plane offset holding a stored cell
-    const double c_below = (cz0 > ovz0) ? __ldg(L.p - sz) : zlow;
-    const double c_here = __ldg(L.p);
-    double q[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) q[j] = (j < PF && 1+j <= L.kload) ? __ldg(L.p + (long long)(1+j)*sz) : L.zhigh;
+    const double* p = a.c + idx0;
+    const int kload = min(zn, ovz1-cz0);                                  // last plane offset holding a stored cell
+    const double c_below = (cz0 > ovz0) ? __ldg(p - sz) : zlow;
     if (fast) {
-      // upwind x / y sources: stored neighbour (advances with the column), boundary value or zero (fixed address)
-      const double* consts = a.consts;                                    // consts[0] = 0, consts[1] = boundary value
+      FvSepLane L;
+      L.f0 = f0; L.f1 = f1; L.f2 = f2; L.f3 = f3; L.un5 = un5; L.dt = dt; L.p = p;
+      // upwind x / y sources: a stored neighbour; else the own cell with factor 0 plus the constant boundary term
       const int mx = dx ? 0 : 1, my = dy ? 2 : 3;                         // inflow face of the axis
-      if (flags >> (4+mx) & 1u) { L.px = L.p + (dx ? -1 : 1); L.sx8 = L.sz8; }
-      else { L.px = consts + (flags >> (8+mx) & 1u); L.sx8 = 0; }
-      if (flags >> (4+my) & 1u) { L.py = L.p + (dy ? -sy : sy); L.sy8 = L.sz8; }
-      else { L.py = consts + (flags >> (8+my) & 1u); L.sy8 = 0; }
-      switch (ldx*4 + ldy*2 + ldz) {
-        case 0: fv_sep_fast<PF, false, false, false>(L, c_below, c_here, q); break;
-        case 1: fv_sep_fast<PF, false, false, true>(L, c_below, c_here, q); break;
-        case 2: fv_sep_fast<PF, false, true, false>(L, c_below, c_here, q); break;
-        case 3: fv_sep_fast<PF, false, true, true>(L, c_below, c_here, q); break;
-        case 4: fv_sep_fast<PF, true, false, false>(L, c_below, c_here, q); break;
-        case 5: fv_sep_fast<PF, true, false, true>(L, c_below, c_here, q); break;
-        case 6: fv_sep_fast<PF, true, true, false>(L, c_below, c_here, q); break;
-        default: fv_sep_fast<PF, true, true, true>(L, c_below, c_here, q); break;
+      L.ox = dx ? -1 : 1; L.oy = dy ? -sy : sy; L.tbx = 0.0; L.tby = 0.0;
+      if (!(flags >> (4+mx) & 1u) && !(flags >> mx & 1u)) {               // inflow, no stored neighbour
+        L.ox = 0; L.tbx = (flags >> (8+mx) & 1u) ? bval*(dx ? f0 : f1) : 0.0;
+        if (dx) L.f0 = 0.0; else L.f1 = 0.0;
       }
-    } else fv_sep_slow<PF>(L, c_below, c_here, q, flags, alt0, alt1, alt2, alt3, sy);
-    if (a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = L.dt;
+      if (!(flags >> (4+my) & 1u) && !(flags >> my & 1u)) {
+        L.oy = 0; L.tby = (flags >> (8+my) & 1u) ? bval*(dy ? f2 : f3) : 0.0;
+        if (dy) L.f2 = 0.0; else L.f3 = 0.0;
+      }
+      if (flags >> mx & 1u) L.ox = 0;                                     // zero velocity: both faces "flow out" with factor +-0
+      if (flags >> my & 1u) L.oy = 0;
+      const double c_here = __ldg(p);
+      double q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[j] = (j < PF && 1+j <= kload) ? __ldg(p + (long long)(1+j)*sz) : zhigh;
+      const long long dw = reinterpret_cast<const char*>(a.cnew) - reinterpret_cast<const char*>(a.c);
+#define DGB_GO(A, B, C) fv_sep_fast<PF, A, B, C>(L, c_below, c_here, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], zhigh, sz, dw, rwz, zn, kload)
+      switch (ldx*4 + ldy*2 + ldz) {
+        case 0: DGB_GO(false, false, false); break;
+        case 1: DGB_GO(false, false, true); break;
+        case 2: DGB_GO(false, true, false); break;
+        case 3: DGB_GO(false, true, true); break;
+        case 4: DGB_GO(true, false, false); break;
+        case 5: DGB_GO(true, false, true); break;
+        case 6: DGB_GO(true, true, false); break;
+        default: DGB_GO(true, true, true); break;
+      }
+#undef DGB_GO
+    } else fv_sep_slow(p, a.cnew + idx0, f0, f1, f2, f3, un4, un5, dt, c_below, zhigh, flags, alt0, alt1, alt2, alt3, sy, sz, rwz, zn, kload);
+    if (a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = dt;
   }
   for (int o = 16; o > 0; o >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, o));
   __shared__ double part[BX*BY/32];
   const int tid = threadIdx.y*BX + threadIdx.x;
+  if ((tid & 31) == 0) part[tid >> 5] = sum_max;
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int k = 0; k < BX*BY/32; ++k) m = fmax(m, part[k]);
+    if (m > 0.0) atomic_max_nonneg(a.slotOut, m);
+    if (a.slotZero && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *a.slotZero = 0.0;
+  }
+}
+
+// ---- 3-D separable-mode kernel, shared-memory plane ring ------------------------------------------------------
+// Same arithmetic as k_fv_march_sep, different data path: the CTA's (BX x BY) tile of every z-plane, with a
+// one-cell halo in x and y, is staged in a ring of D+2 shared-memory slots by cp.async (LDGSTS, 8-byte
+// granularity: the rows of a stored box with odd width, e.g. 513 on a partitioned grid, are only 8-byte aligned,
+// which rules out TMA boxes and 16-byte copies). D planes are in flight per CTA independent of the register
+// budget; the x/y upwind neighbours and the plane above are read from shared memory, so a cell costs one global
+// load (plus the halo share), three shared loads and one store. One __syncthreads per plane publishes the slot.
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+// per-thread operands of the ring loop
+struct FvRingLane {
+  double f0, f1, f2, f3, tbx, tby, un5, dt;   // as FvSepLane
+  double c_below, zhigh;
+  const double* g;                            // own column in c, plane 0 of the chunk
+  double* w;                                  // own column in cnew
+  double* own;                                // own cell in slot 0 of the ring
+  int ox, oy;                                 // shared-memory element offsets of the upwind x / y neighbour (0: none)
+  unsigned halo;                              // bit 0..3: this thread also stages the -x,+x,-y,+y halo cell of its plane
+  bool active;
+};
+// slow path extras
+struct FvRingSlow { double alt0, alt1, alt2, alt3, un4; unsigned flags; };
+
+// MODE 0..7: direction triple DX*4+DY*2+DZ of the fast path; 8: per-lane flags
+template<int D, int BX, int BY, int MODE>
+__device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, const long long sz, const int sy, const double* rwz,
+                                             const int zn, const int kload) {
+  constexpr int R = D+2, PX = BX+2, PY = BY+2, SLOT = PX*PY;
+  constexpr bool DX = MODE & 4, DY = MODE & 2, DZ = MODE & 1;
+  const double* gl = L.g + (long long)(D+1)*sz;          // next plane to stage
+  double c_below = L.c_below, c_here = 0.0;
+  const bool self4 = S.un4 >= 0.0, self5 = L.un5 >= 0.0;
+  // stage plane k+1+D into the slot that plane k-1 occupied (its readers passed the barrier of iteration k)
+#define DGB_RING_ISSUE(K, SLOTIDX)                                                                             \
+  {                                                                                                            \
+    if (L.active && (K)+1+D <= kload) {                                                                        \
+      double* dst = L.own + (SLOTIDX)*SLOT;                                                                    \
+      cp_async8(dst, gl);                                                                                      \
+      if (L.halo) {                                                                                            \
+        if (L.halo & 1u) cp_async8(dst - 1, gl - 1);                                                           \
+        if (L.halo & 2u) cp_async8(dst + 1, gl + 1);                                                           \
+        if (L.halo & 4u) cp_async8(dst - PX, gl - sy);                                                         \
+        if (L.halo & 8u) cp_async8(dst + PX, gl + sy);                                                         \
+      }                                                                                                        \
+    }                                                                                                          \
+    cp_async_commit();                                                                                         \
+    gl += sz;                                                                                                  \
+  }
+#define DGB_RING_CELL(K, J)                                                                                    \
+  {                                                                                                            \
+    cp_async_wait<D-1>();                                                                                      \
+    __syncthreads();                                                                                           \
+    DGB_RING_ISSUE(K, ((J)+R-1) % R)                                                                           \
+    if (L.active) {                                                                                            \
+      const double* cur = L.own + (J)*SLOT;                                                                    \
+      const double* nxt = L.own + (((J)+1) % R)*SLOT;                                                          \
+      if ((K) == 0) c_here = *cur;                                                                             \
+      const double c_above = ((K)+1 <= kload) ? *nxt : L.zhigh;                                                \
+      const double rw = __ldg(rwz + (K));                                                                      \
+      double upd;                                                                                              \
+      if (MODE < 8) {                                                                                          \
+        const double f5 = L.un5*rw;                                                                            \
+        const double nx = cur[L.ox], ny = cur[L.oy];                                                           \
+        upd = 0.0 - (DX ? nx : c_here)*L.f0;                                                                   \
+        if (DX) upd -= L.tbx;                                                                                  \
+        upd -= (DX ? c_here : nx)*L.f1;                                                                        \
+        if (!DX) upd -= L.tbx;                                                                                 \
+        upd -= (DY ? ny : c_here)*L.f2;                                                                        \
+        if (DY) upd -= L.tby;                                                                                  \
+        upd -= (DY ? c_here : ny)*L.f3;                                                                        \
+        if (!DY) upd -= L.tby;                                                                                 \
+        upd -= (DZ ? c_below : c_here)*(-f5);                                                                  \
+        upd -= (DZ ? c_here : c_above)*f5;                                                                     \
+      } else {                                                                                                 \
+        double val;                                                                                            \
+        val = S.alt0; if (S.flags & 16u) val = cur[-1];   if (S.flags & 1u) val = c_here; upd = 0.0 - val*L.f0; \
+        val = S.alt1; if (S.flags & 32u) val = cur[1];    if (S.flags & 2u) val = c_here; upd -= val*L.f1;     \
+        val = S.alt2; if (S.flags & 64u) val = cur[-PX];  if (S.flags & 4u) val = c_here; upd -= val*L.f2;     \
+        val = S.alt3; if (S.flags & 128u) val = cur[PX];  if (S.flags & 8u) val = c_here; upd -= val*L.f3;     \
+        upd -= (self4 ? c_here : c_below)*(S.un4*rw);                                                          \
+        upd -= (self5 ? c_here : c_above)*(L.un5*rw);                                                          \
+      }                                                                                                        \
+      __stcs(L.w, c_here + L.dt*upd);                                                                          \
+      c_below = c_here; c_here = c_above;                                                                      \
+      L.w += sz;                                                                                               \
+    }                                                                                                          \
+  }
+  int kb = 0;
+  for (; kb + R <= zn; kb += R) {                        // whole turns of the ring: slot indices are literals
+#pragma unroll
+    for (int j = 0; j < R; ++j) DGB_RING_CELL(kb+j, j)
+  }
+#pragma unroll
+  for (int j = 0; j < R; ++j) if (kb+j < zn) DGB_RING_CELL(kb+j, j)
+#undef DGB_RING_CELL
+#undef DGB_RING_ISSUE
+}
+
+template<int PROBLEM, int D, int BX, int BY, int MINB>
+__global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a, const int zc) {
+  constexpr int R = D+2, PX = BX+2, PY = BY+2, SLOT = PX*PY;
+  extern __shared__ double ring[];                     // [R][PY][PX]
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i0 = blockIdx.x*BX + tx;
+  const int i1 = blockIdx.y*BY + ty;
+  const int z0 = blockIdx.z*zc;
+  const int zn = min(zc, a.region.size[2]-z0);
+  const int cz0 = a.region.origin[2]+z0;
+  const bool active = i0 < a.region.size[0] && i1 < a.region.size[1];
+  const double* rwz = a.tab.rw[2] + (cz0-a.tab.first[2]);
+  double rwmax = 0.0;
+  for (int k = tx & 31; k < zn; k += 32) rwmax = fmax(rwmax, __ldg(rwz + k));
+  for (int o = 16; o > 0; o >>= 1) rwmax = fmax(rwmax, __shfl_xor_sync(0xffffffffu, rwmax, o));
+  double sum_max = 0.0;
+  double f0 = 0, f1 = 0, f2 = 0, f3 = 0, un4 = 0, un5 = 0, alt0 = 0, alt1 = 0, alt2 = 0, alt3 = 0;
+  unsigned flags = 0;                 // bit m: face m flows out; 4+m: upwind value is a stored neighbour; 8+m: boundary value
+  const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+  const dgb_box& ov = v.comp[0].box[DGB_BOX_OVERLAP];
+  const int sy = of.size[0];
+  const long long sz = (long long)sy*of.size[1];
+  const bool perz = v.periodic >> 2 & 1u;
+  const int ovz0 = ov.origin[2], ovz1 = ovz0 + ov.size[2]-1;
+  const double bval = fv_boundary(a.problem, nullptr);
+  const int cx = a.region.origin[0]+i0, cy = a.region.origin[1]+i1;
+  if (active) {
+    const int ttx = cx-a.tab.first[0], tty = cy-a.tab.first[1];
+    const double llx = __ldg(a.tab.xv[0]+ttx), urx = __ldg(a.tab.xv[0]+ttx+1), xcx = __ldg(a.tab.xc[0]+ttx), rwx = __ldg(a.tab.rw[0]+ttx);
+    const double lly = __ldg(a.tab.xv[1]+tty), ury = __ldg(a.tab.xv[1]+tty+1), xcy = __ldg(a.tab.xc[1]+tty), rwy = __ldg(a.tab.rw[1]+tty);
+    const double xcz = __ldg(a.tab.xc[2]+(cz0-a.tab.first[2]));
+    const bool perx = v.periodic & 1u, pery = v.periodic >> 1 & 1u;
+    double sxy = 0.0;
+#define DGB_COLFACE(K, F, ALT, DIRX, SIDE, FCX, FCY, RW, NB, BD)                                               \
+    {                                                                                                          \
+      const double fc[3] = { FCX, FCY, xcz };                                                                  \
+      double u[3]; fv_velocity3<PROBLEM>(a.problem, fc, u);                                                    \
+      const double un = (SIDE) ? u[DIRX] : -u[DIRX];                                                           \
+      F = un*(RW);                                                                                             \
+      if (F >= 0.0) { sxy += F; flags |= 1u << K; }                                                            \
+      else if (NB) flags |= 16u << K;                                                                          \
+      else if (BD) { ALT = bval; flags |= 256u << K; }                                                         \
+    }
+    DGB_COLFACE(0, f0, alt0, 0, 0, llx, xcy, rwx, cx > ov.origin[0] && cx <= ov.origin[0]+ov.size[0]-1, !perx && cx == 0)
+    DGB_COLFACE(1, f1, alt1, 0, 1, urx, xcy, rwx, cx+1 > ov.origin[0] && cx+1 <= ov.origin[0]+ov.size[0]-1, !perx && cx+1 == v.N[0])
+    DGB_COLFACE(2, f2, alt2, 1, 0, xcx, lly, rwy, cy > ov.origin[1] && cy <= ov.origin[1]+ov.size[1]-1, !pery && cy == 0)
+    DGB_COLFACE(3, f3, alt3, 1, 1, xcx, ury, rwy, cy+1 > ov.origin[1] && cy+1 <= ov.origin[1]+ov.size[1]-1, !pery && cy+1 == v.N[1])
+#undef DGB_COLFACE
+    {
+      const double fc[3] = { xcx, xcy, xcz };
+      double u[3]; fv_velocity3<PROBLEM>(a.problem, fc, u);
+      un4 = -u[2]; un5 = u[2];
+    }
+    double sum = sxy;
+    if (un4 >= 0.0) sum += un4*rwmax;
+    if (un5 >= 0.0) sum += un5*rwmax;
+    sum_max = sum;
+  }
+  int dx = 2, dy = 2, dz = 2;
+  if (active) {
+    const bool o0 = flags & 1u, o1 = flags & 2u, o2 = flags & 4u, o3 = flags & 8u;
+    if ((!o0 && o1) || (o0 && o1 && f0 == 0.0 && f1 == 0.0)) dx = 1; else if (o0 && !o1) dx = 0;
+    if ((!o2 && o3) || (o2 && o3 && f2 == 0.0 && f3 == 0.0)) dy = 1; else if (o2 && !o3) dy = 0;
+    dz = (un5 >= 0.0) ? 1 : 0;
+  }
+  // one code path per CTA (the loop contains barriers): fast only if every active thread agrees on the directions
+  __shared__ int s_pat[2];
+  if (tx == 0 && ty == 0) { s_pat[0] = -1; s_pat[1] = 1; }
+  __syncthreads();
+  if (active && s_pat[0] == -1) s_pat[0] = dx*4 + dy*2 + dz;              // any active thread's triple (races are benign)
+  __syncthreads();
+  const int cand = s_pat[0];
+  if (active && (dx == 2 || dy == 2 || dx*4 + dy*2 + dz != cand)) s_pat[1] = 0;
+  __syncthreads();
+  const int pat = (s_pat[1] && cand >= 0) ? cand : 8;
+
+  FvRingLane L; FvRingSlow S;
+  L.active = active;
+  L.f0 = f0; L.f1 = f1; L.f2 = f2; L.f3 = f3; L.un5 = un5; L.tbx = 0.0; L.tby = 0.0; L.ox = 0; L.oy = 0;
+  S.alt0 = alt0; S.alt1 = alt1; S.alt2 = alt2; S.alt3 = alt3; S.un4 = un4; S.flags = flags;
+  const double zlow = (!perz && ovz0 == 0) ? bval : 0.0;
+  L.zhigh = (!perz && ovz1+1 == v.N[2]) ? bval : 0.0;
+  L.dt = 0.99*(1.0/(*a.slotIn));
+  const long long idx0 = active ? (long long)(cz0-of.origin[2])*sz + (long long)(cy-of.origin[1])*sy + (cx-of.origin[0]) : 0;
+  L.g = a.c + idx0; L.w = a.cnew + idx0;
+  const int kload = min(zn, ovz1-cz0);                   // last plane offset holding stored cells
+  L.own = ring + (ty+1)*PX + (tx+1);
+  // halo duties: the upwind value of a face on the tile edge is a stored neighbour outside the tile
+  L.halo = 0;
+  if (active) {
+    if (tx == 0 && (flags & 16u)) L.halo |= 1u;
+    if ((tx == BX-1 || i0 == a.region.size[0]-1) && (flags & 32u)) L.halo |= 2u;
+    if (ty == 0 && (flags & 64u)) L.halo |= 4u;
+    if ((ty == BY-1 || i1 == a.region.size[1]-1) && (flags & 128u)) L.halo |= 8u;
+  }
+  // prologue: planes 0..D of the chunk
+#pragma unroll
+  for (int j = 0; j <= D; ++j) {
+    if (active && j <= kload) {
+      const double* src = L.g + (long long)j*sz;
+      double* dst = L.own + j*SLOT;
+      cp_async8(dst, src);
+      if (L.halo & 1u) cp_async8(dst - 1, src - 1);
+      if (L.halo & 2u) cp_async8(dst + 1, src + 1);
+      if (L.halo & 4u) cp_async8(dst - PX, src - sy);
+      if (L.halo & 8u) cp_async8(dst + PX, src + sy);
+    }
+    cp_async_commit();
+  }
+  L.c_below = (active && cz0 > ovz0) ? __ldg(L.g - sz) : zlow;
+  if (active && pat < 8) {
+    const int mx = dx ? 0 : 1, my = dy ? 2 : 3;
+    L.ox = dx ? -1 : 1; L.oy = dy ? -PX : PX;
+    if (!(flags >> (4+mx) & 1u) && !(flags >> mx & 1u)) { L.ox = 0; L.tbx = (flags >> (8+mx) & 1u) ? bval*(dx ? f0 : f1) : 0.0; if (dx) L.f0 = 0.0; else L.f1 = 0.0; }
+    if (!(flags >> (4+my) & 1u) && !(flags >> my & 1u)) { L.oy = 0; L.tby = (flags >> (8+my) & 1u) ? bval*(dy ? f2 : f3) : 0.0; if (dy) L.f2 = 0.0; else L.f3 = 0.0; }
+    if (flags >> mx & 1u) L.ox = 0;
+    if (flags >> my & 1u) L.oy = 0;
+  }
+  switch (pat) {
+    case 0: fv_ring_loop<D, BX, BY, 0>(L, S, sz, sy, rwz, zn, kload); break;
+    case 1: fv_ring_loop<D, BX, BY, 1>(L, S, sz, sy, rwz, zn, kload); break;
+    case 2: fv_ring_loop<D, BX, BY, 2>(L, S, sz, sy, rwz, zn, kload); break;
+    case 3: fv_ring_loop<D, BX, BY, 3>(L, S, sz, sy, rwz, zn, kload); break;
+    case 4: fv_ring_loop<D, BX, BY, 4>(L, S, sz, sy, rwz, zn, kload); break;
+    case 5: fv_ring_loop<D, BX, BY, 5>(L, S, sz, sy, rwz, zn, kload); break;
+    case 6: fv_ring_loop<D, BX, BY, 6>(L, S, sz, sy, rwz, zn, kload); break;
+    case 7: fv_ring_loop<D, BX, BY, 7>(L, S, sz, sy, rwz, zn, kload); break;
+    default: fv_ring_loop<D, BX, BY, 8>(L, S, sz, sy, rwz, zn, kload); break;
+  }
+  cp_async_wait<0>();
+  if (active && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = L.dt;
+  for (int o = 16; o > 0; o >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, o));
+  __shared__ double part[BX*BY/32];
+  const int tid = ty*BX + tx;
   if ((tid & 31) == 0) part[tid >> 5] = sum_max;
   __syncthreads();
   if (tid == 0) {
@@ -596,6 +847,35 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
         case 16: DGB_SEP(2, 128, 4, 4) break;
         case 17: DGB_SEP(2, 128, 2, 8) break;
         case 99: DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4) break;          // the general kernel, for comparison
+#define DGB_RING(D_, BX_, BY_, MINB_)                                                                                \
+    { dim3 mblock(BX_, BY_, 1);                                                                                      \
+      dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
+      const size_t smem = size_t(D_+2)*(BX_+2)*(BY_+2)*sizeof(double);                                               \
+      if (pb) { auto kf = k_fv_ring<1, D_, BX_, BY_, MINB_>;                                                         \
+                DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));          \
+                kf<<<mgrid, mblock, smem, stream>>>(v, a, zc); }                                                     \
+      else { auto kf = k_fv_ring<0, D_, BX_, BY_, MINB_>;                                                            \
+             DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));             \
+             kf<<<mgrid, mblock, smem, stream>>>(v, a, zc); } }
+        case 20: DGB_RING(6, 32, 16, 3) break;
+        case 21: DGB_RING(4, 32, 16, 3) break;
+        case 22: DGB_RING(6, 64, 8, 3) break;
+        case 23: DGB_RING(6, 32, 8, 6) break;
+        case 24: DGB_RING(4, 32, 8, 6) break;
+        case 25: DGB_RING(8, 32, 8, 6) break;
+        case 26: DGB_RING(6, 32, 16, 4) break;
+        case 27: DGB_RING(6, 64, 4, 6) break;
+        case 28: DGB_RING(6, 128, 4, 3) break;
+        case 29: DGB_RING(3, 32, 16, 4) break;
+        case 30: DGB_RING(6, 32, 32, 2) break;
+        case 31: DGB_RING(2, 32, 16, 4) break;
+        case 32: DGB_RING(6, 32, 8, 5) break;
+        case 33: DGB_RING(6, 32, 8, 4) break;
+        case 34: DGB_RING(6, 32, 16, 2) break;
+        case 35: DGB_RING(4, 64, 8, 2) break;
+        case 36: DGB_RING(8, 32, 8, 4) break;
+        case 37: DGB_RING(4, 32, 8, 5) break;
+#undef DGB_RING
       }
 #undef DGB_SEP
     }
