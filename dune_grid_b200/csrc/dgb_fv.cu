@@ -526,7 +526,9 @@ struct FvRingLane {
 // slow path extras
 struct FvRingSlow { double alt0, alt1, alt2, alt3, un4; unsigned flags; };
 
-// MODE 0..7: direction triple DX*4+DY*2+DZ of the fast path; 8: per-lane flags
+// MODE 0..7: direction triple DX*4+DY*2+DZ of the fast path; 8: per-lane flags.
+// Threads outside the region (partial tiles) stage nothing and store nothing but run the same arithmetic (on the
+// clamped column of the last valid thread of their row / the last valid row): no divergence around the barriers.
 template<int D, int BX, int BY, int MODE>
 __device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, const long long sz, const int sy, const double* rwz,
                                              const int zn, const int kload) {
@@ -535,68 +537,78 @@ __device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, c
   const double* gl = L.g + (long long)(D+1)*sz;          // next plane to stage
   double c_below = L.c_below, c_here = 0.0;
   const bool self4 = S.un4 >= 0.0, self5 = L.un5 >= 0.0;
+  const bool hL = L.halo & 1u, hR = L.halo & 2u, hB = L.halo & 4u, hT = L.halo & 8u, hAny = L.halo != 0;
   // stage plane k+1+D into the slot that plane k-1 occupied (its readers passed the barrier of iteration k)
-#define DGB_RING_ISSUE(K, SLOTIDX)                                                                             \
+#define DGB_RING_ISSUE(GUARD, K)                                                                               \
   {                                                                                                            \
-    if (L.active && (K)+1+D <= kload) {                                                                        \
-      double* dst = L.own + (SLOTIDX)*SLOT;                                                                    \
+    if (L.active && (!(GUARD) || (K)+1+D <= kload)) {                                                          \
+      double* dst = const_cast<double*>(prev);                                                                 \
       cp_async8(dst, gl);                                                                                      \
-      if (L.halo) {                                                                                            \
-        if (L.halo & 1u) cp_async8(dst - 1, gl - 1);                                                           \
-        if (L.halo & 2u) cp_async8(dst + 1, gl + 1);                                                           \
-        if (L.halo & 4u) cp_async8(dst - PX, gl - sy);                                                         \
-        if (L.halo & 8u) cp_async8(dst + PX, gl + sy);                                                         \
+      if (hAny) {                                                                                              \
+        if (hL) cp_async8(dst - 1, gl - 1);                                                                    \
+        if (hR) cp_async8(dst + 1, gl + 1);                                                                    \
+        if (hB) cp_async8(dst - PX, gl - sy);                                                                  \
+        if (hT) cp_async8(dst + PX, gl + sy);                                                                  \
       }                                                                                                        \
     }                                                                                                          \
     cp_async_commit();                                                                                         \
     gl += sz;                                                                                                  \
   }
-#define DGB_RING_CELL(K, J)                                                                                    \
+#define DGB_RING_CELL(GUARD, K)                                                                                \
   {                                                                                                            \
     cp_async_wait<D-1>();                                                                                      \
     __syncthreads();                                                                                           \
-    DGB_RING_ISSUE(K, ((J)+R-1) % R)                                                                           \
-    if (L.active) {                                                                                            \
-      const double* cur = L.own + (J)*SLOT;                                                                    \
-      const double* nxt = L.own + (((J)+1) % R)*SLOT;                                                          \
-      if ((K) == 0) c_here = *cur;                                                                             \
-      const double c_above = ((K)+1 <= kload) ? *nxt : L.zhigh;                                                \
-      const double rw = __ldg(rwz + (K));                                                                      \
-      double upd;                                                                                              \
-      if (MODE < 8) {                                                                                          \
-        const double f5 = L.un5*rw;                                                                            \
-        const double nx = cur[L.ox], ny = cur[L.oy];                                                           \
-        upd = 0.0 - (DX ? nx : c_here)*L.f0;                                                                   \
-        if (DX) upd -= L.tbx;                                                                                  \
-        upd -= (DX ? c_here : nx)*L.f1;                                                                        \
-        if (!DX) upd -= L.tbx;                                                                                 \
-        upd -= (DY ? ny : c_here)*L.f2;                                                                        \
-        if (DY) upd -= L.tby;                                                                                  \
-        upd -= (DY ? c_here : ny)*L.f3;                                                                        \
-        if (!DY) upd -= L.tby;                                                                                 \
-        upd -= (DZ ? c_below : c_here)*(-f5);                                                                  \
-        upd -= (DZ ? c_here : c_above)*f5;                                                                     \
-      } else {                                                                                                 \
-        double val;                                                                                            \
-        val = S.alt0; if (S.flags & 16u) val = cur[-1];   if (S.flags & 1u) val = c_here; upd = 0.0 - val*L.f0; \
-        val = S.alt1; if (S.flags & 32u) val = cur[1];    if (S.flags & 2u) val = c_here; upd -= val*L.f1;     \
-        val = S.alt2; if (S.flags & 64u) val = cur[-PX];  if (S.flags & 4u) val = c_here; upd -= val*L.f2;     \
-        val = S.alt3; if (S.flags & 128u) val = cur[PX];  if (S.flags & 8u) val = c_here; upd -= val*L.f3;     \
-        upd -= (self4 ? c_here : c_below)*(S.un4*rw);                                                          \
-        upd -= (self5 ? c_here : c_above)*(L.un5*rw);                                                          \
-      }                                                                                                        \
-      __stcs(L.w, c_here + L.dt*upd);                                                                          \
-      c_below = c_here; c_here = c_above;                                                                      \
-      L.w += sz;                                                                                               \
+    DGB_RING_ISSUE(GUARD, K)                                                                                   \
+    const double c_above = (!(GUARD) || (K)+1 <= kload) ? *nxt : L.zhigh;                                      \
+    const double rw = __ldg(rwz + (K));                                                                        \
+    double upd;                                                                                                \
+    if (MODE < 8) {                                                                                            \
+      const double f5 = L.un5*rw;                                                                              \
+      const double nx = cur[L.ox], ny = cur[L.oy];                                                             \
+      upd = 0.0 - (DX ? nx : c_here)*L.f0;                                                                     \
+      if (DX) upd -= L.tbx;                                                                                    \
+      upd -= (DX ? c_here : nx)*L.f1;                                                                          \
+      if (!DX) upd -= L.tbx;                                                                                   \
+      upd -= (DY ? ny : c_here)*L.f2;                                                                          \
+      if (DY) upd -= L.tby;                                                                                    \
+      upd -= (DY ? c_here : ny)*L.f3;                                                                          \
+      if (!DY) upd -= L.tby;                                                                                   \
+      upd -= (DZ ? c_below : c_here)*(-f5);                                                                    \
+      upd -= (DZ ? c_here : c_above)*f5;                                                                       \
+    } else {                                                                                                   \
+      double val;                                                                                              \
+      val = S.alt0; if (S.flags & 16u) val = cur[-1];   if (S.flags & 1u) val = c_here; upd = 0.0 - val*L.f0;  \
+      val = S.alt1; if (S.flags & 32u) val = cur[1];    if (S.flags & 2u) val = c_here; upd -= val*L.f1;       \
+      val = S.alt2; if (S.flags & 64u) val = cur[-PX];  if (S.flags & 4u) val = c_here; upd -= val*L.f2;       \
+      val = S.alt3; if (S.flags & 128u) val = cur[PX];  if (S.flags & 8u) val = c_here; upd -= val*L.f3;       \
+      upd -= (self4 ? c_here : c_below)*(S.un4*rw);                                                            \
+      upd -= (self5 ? c_here : c_above)*(L.un5*rw);                                                            \
     }                                                                                                          \
+    if (L.active) __stcs(L.w, c_here + L.dt*upd);                                                              \
+    c_below = c_here; c_here = c_above;                                                                        \
+    L.w += sz;                                                                                                 \
   }
-  int kb = 0;
-  for (; kb + R <= zn; kb += R) {                        // whole turns of the ring: slot indices are literals
-#pragma unroll
-    for (int j = 0; j < R; ++j) DGB_RING_CELL(kb+j, j)
+  // plane 0 of the own column
+  cp_async_wait<D>();
+  c_here = *L.own;
+  // the loops are deliberately not unrolled: the ring position rotates through three byte offsets (previous,
+  // current, next slot), which keeps the body small enough for the register allocator not to interleave cells
+  const double* prev = L.own + (R-1)*SLOT;               // slot of plane k-1 (free), k, k+1
+  const double* cur = L.own;
+  const double* nxt = L.own + SLOT;
+  const double* const last = L.own + (R-1)*SLOT;
+  const int kmain = max(0, min(zn, kload-D));            // cells whose staging and reads all hit stored planes
+  int k = 0;
+#pragma unroll 1
+  for (; k < kmain; ++k) {
+    DGB_RING_CELL(false, k)
+    prev = cur; cur = nxt; nxt = (nxt == last) ? L.own : nxt + SLOT;
   }
-#pragma unroll
-  for (int j = 0; j < R; ++j) if (kb+j < zn) DGB_RING_CELL(kb+j, j)
+#pragma unroll 1
+  for (; k < zn; ++k) {
+    DGB_RING_CELL(true, k)
+    prev = cur; cur = nxt; nxt = (nxt == last) ? L.own : nxt + SLOT;
+  }
 #undef DGB_RING_CELL
 #undef DGB_RING_ISSUE
 }
@@ -626,8 +638,9 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   const bool perz = v.periodic >> 2 & 1u;
   const int ovz0 = ov.origin[2], ovz1 = ovz0 + ov.size[2]-1;
   const double bval = fv_boundary(a.problem, nullptr);
-  const int cx = a.region.origin[0]+i0, cy = a.region.origin[1]+i1;
-  if (active) {
+  // threads outside the region shadow the last valid column of their row / the last valid row (stores suppressed)
+  const int cx = a.region.origin[0]+min(i0, a.region.size[0]-1), cy = a.region.origin[1]+min(i1, a.region.size[1]-1);
+  {
     const int ttx = cx-a.tab.first[0], tty = cy-a.tab.first[1];
     const double llx = __ldg(a.tab.xv[0]+ttx), urx = __ldg(a.tab.xv[0]+ttx+1), xcx = __ldg(a.tab.xc[0]+ttx), rwx = __ldg(a.tab.rw[0]+ttx);
     const double lly = __ldg(a.tab.xv[1]+tty), ury = __ldg(a.tab.xv[1]+tty+1), xcy = __ldg(a.tab.xc[1]+tty), rwy = __ldg(a.tab.rw[1]+tty);
@@ -660,22 +673,20 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     sum_max = sum;
   }
   int dx = 2, dy = 2, dz = 2;
-  if (active) {
+  {
     const bool o0 = flags & 1u, o1 = flags & 2u, o2 = flags & 4u, o3 = flags & 8u;
     if ((!o0 && o1) || (o0 && o1 && f0 == 0.0 && f1 == 0.0)) dx = 1; else if (o0 && !o1) dx = 0;
     if ((!o2 && o3) || (o2 && o3 && f2 == 0.0 && f3 == 0.0)) dy = 1; else if (o2 && !o3) dy = 0;
     dz = (un5 >= 0.0) ? 1 : 0;
   }
-  // one code path per CTA (the loop contains barriers): fast only if every active thread agrees on the directions
+  // one code path per CTA (the loop contains barriers): fast only if every thread agrees on the directions
   __shared__ int s_pat[2];
-  if (tx == 0 && ty == 0) { s_pat[0] = -1; s_pat[1] = 1; }
-  __syncthreads();
-  if (active && s_pat[0] == -1) s_pat[0] = dx*4 + dy*2 + dz;              // any active thread's triple (races are benign)
+  if (tx == 0 && ty == 0) { s_pat[0] = dx*4 + dy*2 + dz; s_pat[1] = 1; }
   __syncthreads();
   const int cand = s_pat[0];
-  if (active && (dx == 2 || dy == 2 || dx*4 + dy*2 + dz != cand)) s_pat[1] = 0;
+  if (dx == 2 || dy == 2 || dx*4 + dy*2 + dz != cand) s_pat[1] = 0;
   __syncthreads();
-  const int pat = (s_pat[1] && cand >= 0) ? cand : 8;
+  const int pat = s_pat[1] ? cand : 8;
 
   FvRingLane L; FvRingSlow S;
   L.active = active;
@@ -684,7 +695,7 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   const double zlow = (!perz && ovz0 == 0) ? bval : 0.0;
   L.zhigh = (!perz && ovz1+1 == v.N[2]) ? bval : 0.0;
   L.dt = 0.99*(1.0/(*a.slotIn));
-  const long long idx0 = active ? (long long)(cz0-of.origin[2])*sz + (long long)(cy-of.origin[1])*sy + (cx-of.origin[0]) : 0;
+  const long long idx0 = (long long)(cz0-of.origin[2])*sz + (long long)(cy-of.origin[1])*sy + (cx-of.origin[0]);
   L.g = a.c + idx0; L.w = a.cnew + idx0;
   const int kload = min(zn, ovz1-cz0);                   // last plane offset holding stored cells
   L.own = ring + (ty+1)*PX + (tx+1);
@@ -710,8 +721,8 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     }
     cp_async_commit();
   }
-  L.c_below = (active && cz0 > ovz0) ? __ldg(L.g - sz) : zlow;
-  if (active && pat < 8) {
+  L.c_below = (cz0 > ovz0) ? __ldg(L.g - sz) : zlow;
+  if (pat < 8) {
     const int mx = dx ? 0 : 1, my = dy ? 2 : 3;
     L.ox = dx ? -1 : 1; L.oy = dy ? -PX : PX;
     if (!(flags >> (4+mx) & 1u) && !(flags >> mx & 1u)) { L.ox = 0; L.tbx = (flags >> (8+mx) & 1u) ? bval*(dx ? f0 : f1) : 0.0; if (dx) L.f0 = 0.0; else L.f1 = 0.0; }
@@ -875,6 +886,14 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
         case 35: DGB_RING(4, 64, 8, 2) break;
         case 36: DGB_RING(8, 32, 8, 4) break;
         case 37: DGB_RING(4, 32, 8, 5) break;
+        case 38: DGB_RING(6, 64, 8, 2) break;
+        case 39: DGB_RING(6, 64, 4, 4) break;
+        case 40: DGB_RING(8, 64, 4, 4) break;
+        case 41: DGB_RING(10, 32, 8, 4) break;
+        case 42: DGB_RING(6, 128, 2, 4) break;
+        case 43: DGB_RING(6, 128, 4, 2) break;
+        case 44: DGB_RING(12, 32, 8, 4) break;
+        case 45: DGB_RING(6, 32, 4, 8) break;
 #undef DGB_RING
       }
 #undef DGB_SEP
