@@ -10,6 +10,7 @@
 // max_i(sum of outflow factors) for step n+1 (velocities are time independent); one geometry-only bootstrap
 // reduction precedes the first step. min_i fl(1/s_i) == fl(1/max_i s_i) because correctly rounded division is monotone.
 #include <cstdlib>
+#include <cstring>
 #include "dgb_internal.hh"
 #include "dgb_device.cuh"
 #include "dgb_comm.hh"
@@ -519,48 +520,45 @@ struct FvRingLane {
   const double* g;                            // own column in c, plane 0 of the chunk
   double* w;                                  // own column in cnew
   double* own;                                // own cell in slot 0 of the ring
+  const double* hg;                           // halo duty of this thread: its halo cell in c, plane 0 of the chunk ...
+  int hoff;                                   // ... and its shared-memory element offset relative to `own`
   int ox, oy;                                 // shared-memory element offsets of the upwind x / y neighbour (0: none)
-  unsigned halo;                              // bit 0..3: this thread also stages the -x,+x,-y,+y halo cell of its plane
-  bool active;
+  bool active, hasHalo;
 };
 // slow path extras
 struct FvRingSlow { double alt0, alt1, alt2, alt3, un4; unsigned flags; };
+// reciprocal z widths of the whole stored box, passed in the kernel parameter space: indexed uniformly per CTA,
+// they are read through the constant cache (LDC) and cost no load/store-unit wavefront
+#define DGB_RWZ_MAX 1040
+struct FvZTable { double rw[DGB_RWZ_MAX]; };
 
 // MODE 0..7: direction triple DX*4+DY*2+DZ of the fast path; 8: per-lane flags.
 // Threads outside the region (partial tiles) stage nothing and store nothing but run the same arithmetic (on the
 // clamped column of the last valid thread of their row / the last valid row): no divergence around the barriers.
-template<int D, int BX, int BY, int MODE>
-__device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, const long long sz, const int sy, const double* rwz,
-                                             const int zn, const int kload) {
+template<int D, int BX, int BY, int MODE, bool ZPARAM>
+__device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, const long long sz, const double* rwz,
+                                             const FvZTable& zt, const int zbase, const int zn, const int kload) {
   constexpr int R = D+2, PX = BX+2, PY = BY+2, SLOT = PX*PY;
   constexpr bool DX = MODE & 4, DY = MODE & 2, DZ = MODE & 1;
-  const double* gl = L.g + (long long)(D+1)*sz;          // next plane to stage
+  const long long sz8 = sz*8;
+  const char* gl = reinterpret_cast<const char*>(L.g) + (D+1)*sz8;      // own cell of the next plane to stage
+  const char* hl = reinterpret_cast<const char*>(L.hg) + (D+1)*sz8;     // halo cell of the next plane to stage
+  char* w = reinterpret_cast<char*>(L.w);
   double c_below = L.c_below, c_here = 0.0;
   const bool self4 = S.un4 >= 0.0, self5 = L.un5 >= 0.0;
-  const bool hL = L.halo & 1u, hR = L.halo & 2u, hB = L.halo & 4u, hT = L.halo & 8u, hAny = L.halo != 0;
   // stage plane k+1+D into the slot that plane k-1 occupied (its readers passed the barrier of iteration k)
-#define DGB_RING_ISSUE(GUARD, K)                                                                               \
-  {                                                                                                            \
-    if (L.active && (!(GUARD) || (K)+1+D <= kload)) {                                                          \
-      double* dst = const_cast<double*>(prev);                                                                 \
-      cp_async8(dst, gl);                                                                                      \
-      if (hAny) {                                                                                              \
-        if (hL) cp_async8(dst - 1, gl - 1);                                                                    \
-        if (hR) cp_async8(dst + 1, gl + 1);                                                                    \
-        if (hB) cp_async8(dst - PX, gl - sy);                                                                  \
-        if (hT) cp_async8(dst + PX, gl + sy);                                                                  \
-      }                                                                                                        \
-    }                                                                                                          \
-    cp_async_commit();                                                                                         \
-    gl += sz;                                                                                                  \
-  }
 #define DGB_RING_CELL(GUARD, K)                                                                                \
   {                                                                                                            \
     cp_async_wait<D-1>();                                                                                      \
     __syncthreads();                                                                                           \
-    DGB_RING_ISSUE(GUARD, K)                                                                                   \
+    if (!(GUARD) || (K)+1+D <= kload) {                                                                        \
+      if (L.active) cp_async8(const_cast<double*>(prev), gl);                                                  \
+      if (L.hasHalo) cp_async8(const_cast<double*>(prev) + L.hoff, hl);                                        \
+    }                                                                                                          \
+    cp_async_commit();                                                                                         \
+    gl += sz8; hl += sz8;                                                                                      \
     const double c_above = (!(GUARD) || (K)+1 <= kload) ? *nxt : L.zhigh;                                      \
-    const double rw = __ldg(rwz + (K));                                                                        \
+    const double rw = ZPARAM ? zt.rw[zbase + (K)] : __ldg(rwz + (K));                                          \
     double upd;                                                                                                \
     if (MODE < 8) {                                                                                            \
       const double f5 = L.un5*rw;                                                                              \
@@ -584,14 +582,14 @@ __device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, c
       upd -= (self4 ? c_here : c_below)*(S.un4*rw);                                                            \
       upd -= (self5 ? c_here : c_above)*(L.un5*rw);                                                            \
     }                                                                                                          \
-    if (L.active) __stcs(L.w, c_here + L.dt*upd);                                                              \
+    if (L.active) __stcs(reinterpret_cast<double*>(w), c_here + L.dt*upd);                                     \
     c_below = c_here; c_here = c_above;                                                                        \
-    L.w += sz;                                                                                                 \
+    w += sz8;                                                                                                  \
   }
   // plane 0 of the own column
   cp_async_wait<D>();
   c_here = *L.own;
-  // the loops are deliberately not unrolled: the ring position rotates through three byte offsets (previous,
+  // the loops are deliberately not unrolled: the ring position rotates through three pointers (previous,
   // current, next slot), which keeps the body small enough for the register allocator not to interleave cells
   const double* prev = L.own + (R-1)*SLOT;               // slot of plane k-1 (free), k, k+1
   const double* cur = L.own;
@@ -610,12 +608,13 @@ __device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, c
     prev = cur; cur = nxt; nxt = (nxt == last) ? L.own : nxt + SLOT;
   }
 #undef DGB_RING_CELL
-#undef DGB_RING_ISSUE
 }
 
-template<int PROBLEM, int D, int BX, int BY, int MINB>
-__global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a, const int zc) {
+template<int PROBLEM, int D, int BX, int BY, int MINB, bool ZPARAM>
+__global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a,
+                                                         const __grid_constant__ FvZTable zt, const int zc) {
   constexpr int R = D+2, PX = BX+2, PY = BY+2, SLOT = PX*PY;
+  static_assert(2*BX + 2*BY <= BX*BY, "one halo cell per thread");
   extern __shared__ double ring[];                     // [R][PY][PX]
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i0 = blockIdx.x*BX + tx;
@@ -624,7 +623,8 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   const int zn = min(zc, a.region.size[2]-z0);
   const int cz0 = a.region.origin[2]+z0;
   const bool active = i0 < a.region.size[0] && i1 < a.region.size[1];
-  const double* rwz = a.tab.rw[2] + (cz0-a.tab.first[2]);
+  const int zbase = cz0-a.tab.first[2];
+  const double* rwz = a.tab.rw[2] + zbase;
   double rwmax = 0.0;
   for (int k = tx & 31; k < zn; k += 32) rwmax = fmax(rwmax, __ldg(rwz + k));
   for (int o = 16; o > 0; o >>= 1) rwmax = fmax(rwmax, __shfl_xor_sync(0xffffffffu, rwmax, o));
@@ -699,25 +699,33 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   L.g = a.c + idx0; L.w = a.cnew + idx0;
   const int kload = min(zn, ovz1-cz0);                   // last plane offset holding stored cells
   L.own = ring + (ty+1)*PX + (tx+1);
-  // halo duties: the upwind value of a face on the tile edge is a stored neighbour outside the tile
-  L.halo = 0;
-  if (active) {
-    if (tx == 0 && (flags & 16u)) L.halo |= 1u;
-    if ((tx == BX-1 || i0 == a.region.size[0]-1) && (flags & 32u)) L.halo |= 2u;
-    if (ty == 0 && (flags & 64u)) L.halo |= 4u;
-    if ((ty == BY-1 || i1 == a.region.size[1]-1) && (flags & 128u)) L.halo |= 8u;
+  // halo duty: thread t stages halo cell t of the tile (left column, right column, bottom row, top row), if that
+  // cell is a stored neighbour and - on the fast path, where all columns share the flow direction - on an inflow side
+  {
+    const int t = ty*BX + tx;
+    const int nxv = min(BX, a.region.size[0]-blockIdx.x*BX), nyv = min(BY, a.region.size[1]-blockIdx.y*BY);   // valid columns / rows
+    int hx = 0, hy = 0, side = -1;
+    if (t < BY) { side = 0; hx = -1; hy = t; }
+    else if (t < 2*BY) { side = 1; hx = nxv; hy = t-BY; }
+    else if (t < 2*BY+BX) { side = 2; hx = t-2*BY; hy = -1; }
+    else if (t < 2*BY+2*BX) { side = 3; hx = t-2*BY-BX; hy = nyv; }
+    const int gx = a.region.origin[0]+blockIdx.x*BX+hx, gy = a.region.origin[1]+blockIdx.y*BY+hy;
+    bool need = side >= 0 && (side < 2 ? hy < nyv : hx < nxv)
+                && gx >= ov.origin[0] && gx < ov.origin[0]+ov.size[0] && gy >= ov.origin[1] && gy < ov.origin[1]+ov.size[1];
+    if (need && pat < 8) {
+      const bool px = pat & 4, py = pat & 2;
+      need = (side == 0 && px) || (side == 1 && !px) || (side == 2 && py) || (side == 3 && !py);
+    }
+    L.hasHalo = need;
+    L.hg = need ? a.c + ((long long)(cz0-of.origin[2])*sz + (long long)(gy-of.origin[1])*sy + (gx-of.origin[0])) : a.c;
+    L.hoff = ((hy+1)*PX + (hx+1)) - ((ty+1)*PX + (tx+1));
   }
   // prologue: planes 0..D of the chunk
 #pragma unroll
   for (int j = 0; j <= D; ++j) {
-    if (active && j <= kload) {
-      const double* src = L.g + (long long)j*sz;
-      double* dst = L.own + j*SLOT;
-      cp_async8(dst, src);
-      if (L.halo & 1u) cp_async8(dst - 1, src - 1);
-      if (L.halo & 2u) cp_async8(dst + 1, src + 1);
-      if (L.halo & 4u) cp_async8(dst - PX, src - sy);
-      if (L.halo & 8u) cp_async8(dst + PX, src + sy);
+    if (j <= kload) {
+      if (active) cp_async8(L.own + j*SLOT, L.g + (long long)j*sz);
+      if (L.hasHalo) cp_async8(L.own + j*SLOT + L.hoff, L.hg + (long long)j*sz);
     }
     cp_async_commit();
   }
@@ -731,15 +739,15 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     if (flags >> my & 1u) L.oy = 0;
   }
   switch (pat) {
-    case 0: fv_ring_loop<D, BX, BY, 0>(L, S, sz, sy, rwz, zn, kload); break;
-    case 1: fv_ring_loop<D, BX, BY, 1>(L, S, sz, sy, rwz, zn, kload); break;
-    case 2: fv_ring_loop<D, BX, BY, 2>(L, S, sz, sy, rwz, zn, kload); break;
-    case 3: fv_ring_loop<D, BX, BY, 3>(L, S, sz, sy, rwz, zn, kload); break;
-    case 4: fv_ring_loop<D, BX, BY, 4>(L, S, sz, sy, rwz, zn, kload); break;
-    case 5: fv_ring_loop<D, BX, BY, 5>(L, S, sz, sy, rwz, zn, kload); break;
-    case 6: fv_ring_loop<D, BX, BY, 6>(L, S, sz, sy, rwz, zn, kload); break;
-    case 7: fv_ring_loop<D, BX, BY, 7>(L, S, sz, sy, rwz, zn, kload); break;
-    default: fv_ring_loop<D, BX, BY, 8>(L, S, sz, sy, rwz, zn, kload); break;
+    case 0: fv_ring_loop<D, BX, BY, 0, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 1: fv_ring_loop<D, BX, BY, 1, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 2: fv_ring_loop<D, BX, BY, 2, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 3: fv_ring_loop<D, BX, BY, 3, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 4: fv_ring_loop<D, BX, BY, 4, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 5: fv_ring_loop<D, BX, BY, 5, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 6: fv_ring_loop<D, BX, BY, 6, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 7: fv_ring_loop<D, BX, BY, 7, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    default: fv_ring_loop<D, BX, BY, 8, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
   }
   cp_async_wait<0>();
   if (active && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = L.dt;
@@ -797,6 +805,8 @@ struct dgb_fv {
   int level = 0, mode = 0;
   int zchunk = 32;               // planes marched by one CTA of the 3-D kernel (DGB_FV_ZCHUNK overrides)
   int variant = 0;               // tuning variant of the 3-D kernel (DGB_FV_VARIANT overrides), see march_variants
+  std::unique_ptr<dgb::FvZTable> ztab;   // reciprocal z widths for the kernel parameter space (ring kernel)
+  bool zparam = false;
   dgb_view view;
   dgb_mapper mapper;
   FvProblem problem;
@@ -862,12 +872,12 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     { dim3 mblock(BX_, BY_, 1);                                                                                      \
       dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
       const size_t smem = size_t(D_+2)*(BX_+2)*(BY_+2)*sizeof(double);                                               \
-      if (pb) { auto kf = k_fv_ring<1, D_, BX_, BY_, MINB_>;                                                         \
+      if (fv->zparam) { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, true> : k_fv_ring<0, D_, BX_, BY_, MINB_, true>;      \
                 DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));          \
-                kf<<<mgrid, mblock, smem, stream>>>(v, a, zc); }                                                     \
-      else { auto kf = k_fv_ring<0, D_, BX_, BY_, MINB_>;                                                            \
+                kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); }                                          \
+      else { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, false> : k_fv_ring<0, D_, BX_, BY_, MINB_, false>;     \
              DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));             \
-             kf<<<mgrid, mblock, smem, stream>>>(v, a, zc); } }
+             kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); } }
         case 20: DGB_RING(6, 32, 16, 3) break;
         case 21: DGB_RING(4, 32, 16, 3) break;
         case 22: DGB_RING(6, 64, 8, 3) break;
@@ -890,7 +900,6 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
         case 39: DGB_RING(6, 64, 4, 4) break;
         case 40: DGB_RING(8, 64, 4, 4) break;
         case 41: DGB_RING(10, 32, 8, 4) break;
-        case 42: DGB_RING(6, 128, 2, 4) break;
         case 43: DGB_RING(6, 128, 4, 2) break;
         case 44: DGB_RING(12, 32, 8, 4) break;
         case 45: DGB_RING(6, 32, 4, 8) break;
@@ -968,6 +977,11 @@ int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host
     }
     DGB_CUDA(cudaGetLastError());
     DGB_CUDA(cudaDeviceSynchronize());
+    // the device-computed reciprocal z widths also travel in the kernel parameter space (k_fv_ring, FvZTable)
+    fv->ztab.reset(new FvZTable);
+    std::memset(fv->ztab.get(), 0, sizeof(FvZTable));
+    fv->zparam = v.dim == 3 && of.size[2] <= DGB_RWZ_MAX;
+    if (fv->zparam) DGB_CUDA(cudaMemcpy(fv->ztab->rw, fv->tab.rw[2], of.size[2]*sizeof(double), cudaMemcpyDeviceToHost));
     const int32_t items[1] = {1};
     if (int rc = get_plan(g, level, fv->mapper, DGB_InteriorBorder_All_Interface, DGB_ForwardCommunication, items, 1, fv->plan)) return rc;
     *out = fv.release();
