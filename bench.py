@@ -28,6 +28,20 @@ METRIC = "leaf cells/sec (element+intersection FV sweep)"
 BYTES_PER_CELL = 16                                               # read c (8) + write c_new (8), DESIGN.md
 
 
+def ncu_traffic(kernel_prefix):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary (profiles/), or None"""
+    try:
+        import glob
+        best = None
+        for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_fv_ring_ncu_full.json"))):
+            for rec in json.load(open(path)):
+                if kernel_prefix in rec.get("kernel", "") and "traffic_bytes" in rec:
+                    best = (rec["traffic_bytes"], os.path.basename(path))
+        return best
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -229,6 +243,7 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = peaks()
         kernel_ms = ms / args.steps
+        traffic = ncu_traffic("k_fv_ring") if (world == 1 and n == 512 and args.mode == "separable") else None
         achieved = BYTES_PER_CELL * (total_cells / world) / (kernel_ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
@@ -239,7 +254,9 @@ def run_gpu(args):
                            "fv_mode": args.mode, "l2": "inputs (2 x %.2f GB fields per GPU) larger than L2; no flush needed" % (gv.size(0) * 8 / 1e9),
                            "bytes_per_cell": BYTES_PER_CELL},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src,
+                             "traffic": traffic[0] if traffic else None,
+                             "traffic_source": (traffic[1] + " (ncu --set full, 512^3 launch of k_fv_ring)") if traffic else None,
+                             "algorithmic_bytes_per_launch": BYTES_PER_CELL * (total_cells / world), "peak_source": peak_src,
                              "note": "per-GPU algorithmic bytes (16 B x interior cells) / mean step time (one fused kernel per step"
                                      + ("" if world == 1 else " + pack/unpack + NCCL") + ")"},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
@@ -259,13 +276,13 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="separable", choices=["separable", "exact"])
     ap.add_argument("--size", type=int, default=0, help="override the cube edge (default 512 at N=1, 1024 at N>1)")
     ap.add_argument("--ref-size", type=int, default=256, help="cube edge of the bounded CPU sample")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -11,6 +11,7 @@
 // reduction precedes the first step. min_i fl(1/s_i) == fl(1/max_i s_i) because correctly rounded division is monotone.
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include "dgb_internal.hh"
 #include "dgb_device.cuh"
 #include "dgb_comm.hh"
@@ -272,233 +273,6 @@ __global__ void __launch_bounds__(BX*BY) k_fv_march(const __grid_constant__ dgb_
   }
 }
 
-// ---- 3-D separable-mode production kernel -------------------------------------------------------------------
-// Same decomposition as k_fv_march, specialised for DGB_FV_SEPARABLE with a velocity field that does not depend
-// on z (both compiled-in problems): the four x/y face factors (u.n)/w, their upwind decisions, the neighbour /
-// boundary classification of those faces and the partial CFL sum are then properties of the COLUMN and are
-// evaluated once per thread; per cell only  value*factor  products remain. The arithmetic per cell keeps the
-// reference order  upd = ((((((0 - t0) - t1) - t2) - t3) - t4) - t5),  t_k = c_upwind(k) * factor(k)  (faces in
-// intersection order -x,+x,-y,+y,-z,+z), so results equal the general kernel's bit for bit.
-//  * CFL: the sum of a cell is  sxy + [uz != 0] |uz|*rw(z)  with at most one z face flowing out; rounded addition
-//    and multiplication are monotone, so its maximum over the column is taken at the largest rw(z) of the chunk,
-//    which one warp-wide max finds before the loop - the loop body carries no reduction at all.
-//  * Fast path (warps in which every lane has, per axis, one inflow and one outflow face and the direction is the
-//    same for all 32 lanes - every warp of a uniform flow): the loop is instantiated per direction triple, so no
-//    per-face select or predicate remains. The upwind x/y values are read through per-lane pointers that advance
-//    by one plane per cell, or by nothing when they point at the boundary value b (inflow through the physical
-//    boundary) or at 0 (no neighbour and no boundary: overlap 0), so boundary columns need no special code.
-//    A zero velocity component counts as "positive": its two terms are +-0 and change nothing.
-//  * Slow path (mixed, converging or diverging warps): per-lane flags, same arithmetic.
-//  * The PF-deep register queue of planes above is indexed statically (the k loop is unrolled PF times).
-struct FvSepLane {
-  double f0, f1, f2, f3;       // x/y face factors in intersection order (0 for an inflow face without stored neighbour)
-  double tbx, tby;             // constant term b*factor of an x / y inflow face on the physical boundary, else 0
-  double un5, dt;              // +z normal velocity (that of -z is its negative), time step
-  const double* p;             // current cell in c; the cell of cnew is at byte offset dw (uniform)
-  int ox, oy;                  // element offsets of the upwind x / y neighbour (0 when there is none)
-};
-
-template<int PF, bool DX, bool DY, bool DZ>
-__device__ __forceinline__ void fv_sep_fast(FvSepLane L, double c_below, double c_here, double q0, double q1, double q2, double q3,
-                                            double q4, double q5, double q6, double q7, const double zhigh, const long long sz,
-                                            const long long dw, const double* rwz, const int zn, const int kload) {
-  const double* p = L.p;
-#define DGB_FAST_CELL(SLOT, GUARD)                                                                             \
-  {                                                                                                            \
-    const double c_above = SLOT;                                                                               \
-    if (!(GUARD) || k+1+PF <= kload) SLOT = __ldg(p + (1+PF)*sz); else SLOT = zhigh;                           \
-    const double f5 = L.un5*__ldg(rwz + k);                                                                    \
-    const double nx = __ldg(p + L.ox), ny = __ldg(p + L.oy);                                                   \
-    double upd = 0.0 - (DX ? nx : c_here)*L.f0;                                                                \
-    if (DX) upd -= L.tbx;                                                                                      \
-    upd -= (DX ? c_here : nx)*L.f1;                                                                            \
-    if (!DX) upd -= L.tbx;                                                                                     \
-    upd -= (DY ? ny : c_here)*L.f2;                                                                            \
-    if (DY) upd -= L.tby;                                                                                      \
-    upd -= (DY ? c_here : ny)*L.f3;                                                                            \
-    if (!DY) upd -= L.tby;                                                                                     \
-    upd -= (DZ ? c_below : c_here)*(-f5);                                                                      \
-    upd -= (DZ ? c_here : c_above)*f5;                                                                         \
-    __stcs(reinterpret_cast<double*>(reinterpret_cast<char*>(const_cast<double*>(p)) + dw), c_here + L.dt*upd); \
-    c_below = c_here; c_here = c_above;                                                                        \
-    p += sz; ++k;                                                                                              \
-  }
-  int k = 0;
-  const int kmain = max(0, min(zn, kload-PF)/PF*PF);
-  while (k < kmain) {
-    DGB_FAST_CELL(q0, false)
-    if (PF > 1) DGB_FAST_CELL(q1, false)
-    if (PF > 2) DGB_FAST_CELL(q2, false)
-    if (PF > 3) DGB_FAST_CELL(q3, false)
-    if (PF > 4) DGB_FAST_CELL(q4, false)
-    if (PF > 5) DGB_FAST_CELL(q5, false)
-    if (PF > 6) DGB_FAST_CELL(q6, false)
-    if (PF > 7) DGB_FAST_CELL(q7, false)
-  }
-  while (k < zn) {
-    DGB_FAST_CELL(q0, true)
-    if (PF > 1 && k < zn) DGB_FAST_CELL(q1, true)
-    if (PF > 2 && k < zn) DGB_FAST_CELL(q2, true)
-    if (PF > 3 && k < zn) DGB_FAST_CELL(q3, true)
-    if (PF > 4 && k < zn) DGB_FAST_CELL(q4, true)
-    if (PF > 5 && k < zn) DGB_FAST_CELL(q5, true)
-    if (PF > 6 && k < zn) DGB_FAST_CELL(q6, true)
-    if (PF > 7 && k < zn) DGB_FAST_CELL(q7, true)
-  }
-#undef DGB_FAST_CELL
-}
-
-// per-lane upwind flags: bit m (m<4): face m flows out; bit 4+m: the upwind value of face m is a stored neighbour;
-// alt[m]: the boundary value otherwise (0: the face contributes nothing). No prefetch queue: this path is rare.
-__device__ __noinline__ void fv_sep_slow(const double* p, double* w, double f0, double f1, double f2, double f3, double un4, double un5,
-                                         double dt, double c_below, double zhigh, unsigned flags, double alt0, double alt1, double alt2,
-                                         double alt3, int sy, long long sz, const double* rwz, int zn, int kload) {
-  const bool self4 = un4 >= 0.0, self5 = un5 >= 0.0;                     // widths are positive: sign(un*rw) = sign(un)
-  double c_here = __ldg(p);
-  for (int k = 0; k < zn; ++k) {
-    const double c_above = (k+1 <= kload) ? __ldg(p + sz) : zhigh;
-    const double rw = __ldg(rwz + k);
-    double val, upd;
-    val = alt0; if (flags & 16u) val = __ldg(p - 1);   if (flags & 1u) val = c_here; upd = 0.0 - val*f0;
-    val = alt1; if (flags & 32u) val = __ldg(p + 1);   if (flags & 2u) val = c_here; upd -= val*f1;
-    val = alt2; if (flags & 64u) val = __ldg(p - sy);  if (flags & 4u) val = c_here; upd -= val*f2;
-    val = alt3; if (flags & 128u) val = __ldg(p + sy); if (flags & 8u) val = c_here; upd -= val*f3;
-    upd -= (self4 ? c_here : c_below)*(un4*rw);
-    upd -= (self5 ? c_here : c_above)*(un5*rw);
-    __stcs(w, c_here + dt*upd);
-    c_below = c_here; c_here = c_above;
-    p += sz; w += sz;
-  }
-}
-
-template<int PROBLEM, int PF, int BX, int BY, int MINB>
-__global__ void __launch_bounds__(BX*BY, MINB) k_fv_march_sep(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a, const int zc) {
-  static_assert(PF >= 1 && PF <= 8, "prefetch depth");
-  const int i0 = blockIdx.x*BX + threadIdx.x;
-  const int i1 = blockIdx.y*BY + threadIdx.y;
-  const int z0 = blockIdx.z*zc;
-  const int zn = min(zc, a.region.size[2]-z0);
-  const int cz0 = a.region.origin[2]+z0;
-  const bool active = i0 < a.region.size[0] && i1 < a.region.size[1];
-  // largest reciprocal z width of the chunk (one table entry per lane, warp max)
-  const double* rwz = a.tab.rw[2] + (cz0-a.tab.first[2]);
-  double rwmax = 0.0;
-  for (int k = threadIdx.x & 31; k < zn; k += 32) rwmax = fmax(rwmax, __ldg(rwz + k));
-  for (int o = 16; o > 0; o >>= 1) rwmax = fmax(rwmax, __shfl_xor_sync(0xffffffffu, rwmax, o));
-  double sum_max = 0.0;
-  double f0 = 0, f1 = 0, f2 = 0, f3 = 0, un4 = 0, un5 = 0, alt0 = 0, alt1 = 0, alt2 = 0, alt3 = 0;
-  unsigned flags = 0;                 // bit m: face m flows out; 4+m: upwind value is a stored neighbour; 8+m: boundary value
-  const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
-  const dgb_box& ov = v.comp[0].box[DGB_BOX_OVERLAP];
-  const int sy = of.size[0];
-  const long long sz = (long long)sy*of.size[1];
-  const bool perz = v.periodic >> 2 & 1u;
-  const int ovz0 = ov.origin[2], ovz1 = ovz0 + ov.size[2]-1;              // neighbor(): ovz0 < cz+side <= ovz1
-  const double bval = fv_boundary(a.problem, nullptr);
-  const int cx = a.region.origin[0]+i0, cy = a.region.origin[1]+i1;
-  if (active) {
-    const int tx = cx-a.tab.first[0], ty = cy-a.tab.first[1];
-    const double llx = __ldg(a.tab.xv[0]+tx), urx = __ldg(a.tab.xv[0]+tx+1), xcx = __ldg(a.tab.xc[0]+tx), rwx = __ldg(a.tab.rw[0]+tx);
-    const double lly = __ldg(a.tab.xv[1]+ty), ury = __ldg(a.tab.xv[1]+ty+1), xcy = __ldg(a.tab.xc[1]+ty), rwy = __ldg(a.tab.rw[1]+ty);
-    const double xcz = __ldg(a.tab.xc[2]+(cz0-a.tab.first[2]));          // any z: the velocity does not depend on it
-    const bool perx = v.periodic & 1u, pery = v.periodic >> 1 & 1u;
-    double sxy = 0.0;
-#define DGB_COLFACE(K, F, ALT, DIRX, SIDE, FCX, FCY, RW, NB, BD)                                               \
-    {                                                                                                          \
-      const double fc[3] = { FCX, FCY, xcz };                                                                  \
-      double u[3]; fv_velocity3<PROBLEM>(a.problem, fc, u);                                                    \
-      const double un = (SIDE) ? u[DIRX] : -u[DIRX];                                                           \
-      F = un*(RW);                                                                                             \
-      if (F >= 0.0) { sxy += F; flags |= 1u << K; }                                                            \
-      else if (NB) flags |= 16u << K;                                                                          \
-      else if (BD) { ALT = bval; flags |= 256u << K; }                                                         \
-    }
-    DGB_COLFACE(0, f0, alt0, 0, 0, llx, xcy, rwx, cx > ov.origin[0] && cx <= ov.origin[0]+ov.size[0]-1, !perx && cx == 0)
-    DGB_COLFACE(1, f1, alt1, 0, 1, urx, xcy, rwx, cx+1 > ov.origin[0] && cx+1 <= ov.origin[0]+ov.size[0]-1, !perx && cx+1 == v.N[0])
-    DGB_COLFACE(2, f2, alt2, 1, 0, xcx, lly, rwy, cy > ov.origin[1] && cy <= ov.origin[1]+ov.size[1]-1, !pery && cy == 0)
-    DGB_COLFACE(3, f3, alt3, 1, 1, xcx, ury, rwy, cy+1 > ov.origin[1] && cy+1 <= ov.origin[1]+ov.size[1]-1, !pery && cy+1 == v.N[1])
-#undef DGB_COLFACE
-    {
-      const double fc[3] = { xcx, xcy, xcz };
-      double u[3]; fv_velocity3<PROBLEM>(a.problem, fc, u);
-      un4 = -u[2]; un5 = u[2];
-    }
-    // CFL sum of the column: faces in order, the z faces with the largest reciprocal width of the chunk
-    double sum = sxy;
-    if (un4 >= 0.0) sum += un4*rwmax;
-    if (un5 >= 0.0) sum += un5*rwmax;
-    sum_max = sum;
-  }
-  // direction per axis: 1 = positive (inflow through the low face; also zero velocity), 0 = negative, 2 = neither
-  int dx = 2, dy = 2, dz = 2;
-  if (active) {
-    const bool o0 = flags & 1u, o1 = flags & 2u, o2 = flags & 4u, o3 = flags & 8u;
-    if ((!o0 && o1) || (o0 && o1 && f0 == 0.0 && f1 == 0.0)) dx = 1; else if (o0 && !o1) dx = 0;
-    if ((!o2 && o3) || (o2 && o3 && f2 == 0.0 && f3 == 0.0)) dy = 1; else if (o2 && !o3) dy = 0;
-    dz = (un5 >= 0.0) ? 1 : 0;                                            // un4 = -un5
-  }
-  const unsigned amask = __ballot_sync(0xffffffffu, active);
-  const int lead = amask ? __ffs(amask)-1 : 0;
-  const int ldx = __shfl_sync(0xffffffffu, dx, lead), ldy = __shfl_sync(0xffffffffu, dy, lead), ldz = __shfl_sync(0xffffffffu, dz, lead);
-  const bool fast = __all_sync(0xffffffffu, !active || (dx == ldx && dy == ldy && dz == ldz && dx != 2 && dy != 2));
-  if (active) {
-    // value seen through the bottom face of the lowest / the top face of the highest cell of the stored box
-    const double zlow = (!perz && ovz0 == 0) ? bval : 0.0;
-    const double zhigh = (!perz && ovz1+1 == v.N[2]) ? bval : 0.0;
-    const double dt = 0.99*(1.0/(*a.slotIn));
-    const long long idx0 = (long long)(cz0-of.origin[2])*sz + (long long)(cy-of.origin[1])*sy + (cx-of.origin[0]);
-    const double* p = a.c + idx0;
-    const int kload = min(zn, ovz1-cz0);                                  // last plane offset holding a stored cell
-    const double c_below = (cz0 > ovz0) ? __ldg(p - sz) : zlow;
-    if (fast) {
-      FvSepLane L;
-      L.f0 = f0; L.f1 = f1; L.f2 = f2; L.f3 = f3; L.un5 = un5; L.dt = dt; L.p = p;
-      // upwind x / y sources: a stored neighbour; else the own cell with factor 0 plus the constant boundary term
-      const int mx = dx ? 0 : 1, my = dy ? 2 : 3;                         // inflow face of the axis
-      L.ox = dx ? -1 : 1; L.oy = dy ? -sy : sy; L.tbx = 0.0; L.tby = 0.0;
-      if (!(flags >> (4+mx) & 1u) && !(flags >> mx & 1u)) {               // inflow, no stored neighbour
-        L.ox = 0; L.tbx = (flags >> (8+mx) & 1u) ? bval*(dx ? f0 : f1) : 0.0;
-        if (dx) L.f0 = 0.0; else L.f1 = 0.0;
-      }
-      if (!(flags >> (4+my) & 1u) && !(flags >> my & 1u)) {
-        L.oy = 0; L.tby = (flags >> (8+my) & 1u) ? bval*(dy ? f2 : f3) : 0.0;
-        if (dy) L.f2 = 0.0; else L.f3 = 0.0;
-      }
-      if (flags >> mx & 1u) L.ox = 0;                                     // zero velocity: both faces "flow out" with factor +-0
-      if (flags >> my & 1u) L.oy = 0;
-      const double c_here = __ldg(p);
-      double q[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) q[j] = (j < PF && 1+j <= kload) ? __ldg(p + (long long)(1+j)*sz) : zhigh;
-      const long long dw = reinterpret_cast<const char*>(a.cnew) - reinterpret_cast<const char*>(a.c);
-#define DGB_GO(A, B, C) fv_sep_fast<PF, A, B, C>(L, c_below, c_here, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], zhigh, sz, dw, rwz, zn, kload)
-      switch (ldx*4 + ldy*2 + ldz) {
-        case 0: DGB_GO(false, false, false); break;
-        case 1: DGB_GO(false, false, true); break;
-        case 2: DGB_GO(false, true, false); break;
-        case 3: DGB_GO(false, true, true); break;
-        case 4: DGB_GO(true, false, false); break;
-        case 5: DGB_GO(true, false, true); break;
-        case 6: DGB_GO(true, true, false); break;
-        default: DGB_GO(true, true, true); break;
-      }
-#undef DGB_GO
-    } else fv_sep_slow(p, a.cnew + idx0, f0, f1, f2, f3, un4, un5, dt, c_below, zhigh, flags, alt0, alt1, alt2, alt3, sy, sz, rwz, zn, kload);
-    if (a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = dt;
-  }
-  for (int o = 16; o > 0; o >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, o));
-  __shared__ double part[BX*BY/32];
-  const int tid = threadIdx.y*BX + threadIdx.x;
-  if ((tid & 31) == 0) part[tid >> 5] = sum_max;
-  __syncthreads();
-  if (tid == 0) {
-    double m = 0.0;
-    for (int k = 0; k < BX*BY/32; ++k) m = fmax(m, part[k]);
-    if (m > 0.0) atomic_max_nonneg(a.slotOut, m);
-    if (a.slotZero && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *a.slotZero = 0.0;
-  }
-}
-
 // ---- 3-D separable-mode kernel, shared-memory plane ring ------------------------------------------------------
 // Same arithmetic as k_fv_march_sep, different data path: the CTA's (BX x BY) tile of every z-plane, with a
 // one-cell halo in x and y, is staged in a ring of D+2 shared-memory slots by cp.async (LDGSTS, 8-byte
@@ -613,7 +387,7 @@ __device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, c
 template<int PROBLEM, int D, int BX, int BY, int MINB, bool ZPARAM>
 __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a,
                                                          const __grid_constant__ FvZTable zt, const int zc) {
-  constexpr int R = D+2, PX = BX+2, PY = BY+2, SLOT = PX*PY;
+  constexpr int PX = BX+2, PY = BY+2, SLOT = PX*PY;
   static_assert(2*BX + 2*BY <= BX*BY, "one halo cell per thread");
   extern __shared__ double ring[];                     // [R][PY][PX]
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -803,7 +577,7 @@ struct dgb_fv {
   dgb_grid* grid = nullptr;
   dgb_comm* comm = nullptr;
   int level = 0, mode = 0;
-  int zchunk = 32;               // planes marched by one CTA of the 3-D kernel (DGB_FV_ZCHUNK overrides)
+  int zchunk = 0;                // planes marched by one CTA of the 3-D kernel; 0 = auto (DGB_FV_ZCHUNK overrides)
   int variant = 0;               // tuning variant of the 3-D kernel (DGB_FV_VARIANT overrides), see march_variants
   std::unique_ptr<dgb::FvZTable> ztab;   // reciprocal z widths for the kernel parameter space (ring kernel)
   bool zparam = false;
@@ -819,9 +593,20 @@ struct dgb_fv {
   std::shared_ptr<CommPlan> plan;
   double* dStage[2] = {nullptr, nullptr};     // device staging for the host-buffer entry point
   size_t stageBytes = 0;
+  cudaStream_t sIn = nullptr, sOut = nullptr;  // copy streams of the pipelined host-buffer step
+  std::vector<cudaEvent_t> evIn, evK;
+  cudaEvent_t evStart = nullptr, evEnd = nullptr;
 };
 
 namespace dgb {
+
+// planes per CTA: long columns amortise the ring prologue; short ones keep >= ~2 waves of 32x8 tiles on 148 SMs
+static int auto_zchunk(const int* size) {
+  const long long tiles = (long long)((size[0]+31)/32)*((size[1]+7)/8);
+  int zc = 128;
+  while (zc > 16 && tiles*((size[2]+zc-1)/zc) < 2*148*4) zc /= 2;
+  return zc;
+}
 
 template<bool REDUCE_ONLY>
 static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
@@ -830,7 +615,7 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
   dim3 grid((a.region.size[0]+FBX-1)/FBX, (a.region.size[1]+FBY-1)/FBY, v.dim > 2 ? a.region.size[2] : 1);
   if (a.region.size[0] <= 0 || a.region.size[1] <= 0 || (v.dim > 2 && a.region.size[2] <= 0)) return DGB_OK;
   if (v.dim == 3) {
-    const int zc = fv->zchunk;
+    const int zc = fv->zchunk > 0 ? fv->zchunk : auto_zchunk(a.region.size);
     const bool exact = fv->mode == DGB_FV_EXACT;
     const int pb = fv->problem.id == 1 ? 1 : 0;
 #define DGB_MARCH(MODE_, PROB_, PF_, BX_, BY_)                                                                       \
@@ -842,32 +627,6 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     } else if (REDUCE_ONLY || a.update || !a.cnew) {
       if (pb) DGB_MARCH(DGB_FV_SEPARABLE, 1, 4, 128, 4) else DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4)
     } else {
-#define DGB_SEP(PF_, BX_, BY_, MINB_)                                                                                \
-    { dim3 mblock(BX_, BY_, 1);                                                                                      \
-      dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
-      if (pb) k_fv_march_sep<1, PF_, BX_, BY_, MINB_><<<mgrid, mblock, 0, stream>>>(v, a, zc);                       \
-      else k_fv_march_sep<0, PF_, BX_, BY_, MINB_><<<mgrid, mblock, 0, stream>>>(v, a, zc); }
-      switch (fv->variant) {                  // tuning variants (prefetch depth, tile, occupancy target)
-        default:
-        case 0: DGB_SEP(4, 128, 4, 2) break;
-        case 1: DGB_SEP(1, 128, 4, 2) break;
-        case 2: DGB_SEP(2, 128, 4, 2) break;
-        case 3: DGB_SEP(8, 128, 4, 2) break;
-        case 4: DGB_SEP(4, 64, 8, 2) break;
-        case 5: DGB_SEP(4, 32, 16, 2) break;
-        case 6: DGB_SEP(4, 64, 4, 4) break;
-        case 7: DGB_SEP(8, 64, 4, 4) break;
-        case 8: DGB_SEP(4, 128, 2, 4) break;
-        case 9: DGB_SEP(8, 128, 2, 4) break;
-        case 10: DGB_SEP(2, 128, 4, 3) break;
-        case 11: DGB_SEP(4, 128, 4, 3) break;
-        case 12: DGB_SEP(2, 128, 2, 6) break;
-        case 13: DGB_SEP(4, 128, 2, 6) break;
-        case 14: DGB_SEP(4, 256, 2, 2) break;
-        case 15: DGB_SEP(6, 128, 4, 2) break;
-        case 16: DGB_SEP(2, 128, 4, 4) break;
-        case 17: DGB_SEP(2, 128, 2, 8) break;
-        case 99: DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4) break;          // the general kernel, for comparison
 #define DGB_RING(D_, BX_, BY_, MINB_)                                                                                \
     { dim3 mblock(BX_, BY_, 1);                                                                                      \
       dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
@@ -878,34 +637,18 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
       else { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, false> : k_fv_ring<0, D_, BX_, BY_, MINB_, false>;     \
              DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));             \
              kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); } }
-        case 20: DGB_RING(6, 32, 16, 3) break;
-        case 21: DGB_RING(4, 32, 16, 3) break;
-        case 22: DGB_RING(6, 64, 8, 3) break;
-        case 23: DGB_RING(6, 32, 8, 6) break;
-        case 24: DGB_RING(4, 32, 8, 6) break;
-        case 25: DGB_RING(8, 32, 8, 6) break;
-        case 26: DGB_RING(6, 32, 16, 4) break;
-        case 27: DGB_RING(6, 64, 4, 6) break;
-        case 28: DGB_RING(6, 128, 4, 3) break;
-        case 29: DGB_RING(3, 32, 16, 4) break;
-        case 30: DGB_RING(6, 32, 32, 2) break;
-        case 31: DGB_RING(2, 32, 16, 4) break;
-        case 32: DGB_RING(6, 32, 8, 5) break;
-        case 33: DGB_RING(6, 32, 8, 4) break;
-        case 34: DGB_RING(6, 32, 16, 2) break;
-        case 35: DGB_RING(4, 64, 8, 2) break;
-        case 36: DGB_RING(8, 32, 8, 4) break;
-        case 37: DGB_RING(4, 32, 8, 5) break;
-        case 38: DGB_RING(6, 64, 8, 2) break;
-        case 39: DGB_RING(6, 64, 4, 4) break;
-        case 40: DGB_RING(8, 64, 4, 4) break;
-        case 41: DGB_RING(10, 32, 8, 4) break;
-        case 43: DGB_RING(6, 128, 4, 2) break;
-        case 44: DGB_RING(12, 32, 8, 4) break;
-        case 45: DGB_RING(6, 32, 4, 8) break;
-#undef DGB_RING
+      switch (fv->variant) {                  // tuning variants: ring depth, tile, occupancy target (tools/fv_sweep.py)
+        default:
+        case 0: DGB_RING(8, 32, 8, 4) break;                               // production choice
+        case 1: DGB_RING(6, 32, 8, 4) break;
+        case 2: DGB_RING(6, 64, 4, 4) break;
+        case 3: DGB_RING(6, 128, 4, 2) break;
+        case 4: DGB_RING(6, 32, 16, 2) break;
+        case 5: DGB_RING(4, 64, 8, 2) break;
+        case 6: DGB_RING(12, 32, 8, 4) break;
+        case 99: DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4) break;          // the general kernel, for comparison
       }
-#undef DGB_SEP
+#undef DGB_RING
     }
 #undef DGB_MARCH
   } else {
@@ -994,6 +737,12 @@ int dgb_fv_destroy(dgb_fv* fv) {
   if (fv->dSlots) cudaFree(fv->dSlots);
   if (fv->dTables) cudaFree(fv->dTables);
   for (int i = 0; i < 2; ++i) if (fv->dStage[i]) cudaFree(fv->dStage[i]);
+  for (cudaEvent_t e : fv->evIn) cudaEventDestroy(e);
+  for (cudaEvent_t e : fv->evK) cudaEventDestroy(e);
+  if (fv->evStart) cudaEventDestroy(fv->evStart);
+  if (fv->evEnd) cudaEventDestroy(fv->evEnd);
+  if (fv->sIn) cudaStreamDestroy(fv->sIn);
+  if (fv->sOut) cudaStreamDestroy(fv->sOut);
   delete fv;
   return DGB_OK;
 }
@@ -1086,11 +835,66 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
     DGB_CUDA(cudaMalloc(&fv->dStage[1], bytes));
     fv->stageBytes = bytes;
   }
-  DGB_CUDA(cudaMemcpyAsync(fv->dStage[0], h_c_in, bytes, cudaMemcpyHostToDevice, stream));
-  // every stored cell of the result is written: interior cells by the kernel, overlap cells by the exchange
-  if (int rc = dgb_fv_step(fv, fv->dStage[0], fv->dStage[1], stream)) return rc;
-  DGB_CUDA(cudaMemcpyAsync(h_c_out, fv->dStage[1], bytes, cudaMemcpyDeviceToHost, stream));
+  const dgb_view& v = fv->view;
+  const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+  const dgb_box& in = v.comp[0].box[DGB_BOX_INTERIOR];
+  // Pipelined form (one rank, no overlap cells to refresh, 3-D): the field crosses PCIe in z-slabs; slab i is updated
+  // as soon as slab i+1 (whose first plane it reads) has arrived, and its result leaves while later slabs are still
+  // coming in - the two copy directions run concurrently on their own streams around the compute stream.
+  const int nslab = 16;
+  const bool pipelined = v.dim == 3 && v.nranks == 1 && !fv->plan->nSendBoxes && !fv->plan->nRecvBoxes
+                         && of.size[2] == in.size[2] && of.size[2] >= 4*nslab && !getenv("DGB_FV_HOST_SERIAL");
+  if (!pipelined) {
+    DGB_CUDA(cudaMemcpyAsync(fv->dStage[0], h_c_in, bytes, cudaMemcpyHostToDevice, stream));
+    // every stored cell of the result is written: interior cells by the kernel, overlap cells by the exchange
+    if (int rc = dgb_fv_step(fv, fv->dStage[0], fv->dStage[1], stream)) return rc;
+    DGB_CUDA(cudaMemcpyAsync(h_c_out, fv->dStage[1], bytes, cudaMemcpyDeviceToHost, stream));
+    if (dt_host) DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 3, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    DGB_CUDA(cudaStreamSynchronize(stream));
+    return DGB_OK;
+  }
+  if (!fv->sIn) {
+    DGB_CUDA(cudaStreamCreateWithFlags(&fv->sIn, cudaStreamNonBlocking));
+    DGB_CUDA(cudaStreamCreateWithFlags(&fv->sOut, cudaStreamNonBlocking));
+    fv->evIn.resize(nslab); fv->evK.resize(nslab);
+    for (int i = 0; i < nslab; ++i) {
+      DGB_CUDA(cudaEventCreateWithFlags(&fv->evIn[i], cudaEventDisableTiming));
+      DGB_CUDA(cudaEventCreateWithFlags(&fv->evK[i], cudaEventDisableTiming));
+    }
+    DGB_CUDA(cudaEventCreateWithFlags(&fv->evStart, cudaEventDisableTiming));
+    DGB_CUDA(cudaEventCreateWithFlags(&fv->evEnd, cudaEventDisableTiming));
+  }
+  if (!fv->bootstrapped) if (int rc = bootstrap(fv, stream)) return rc;
+  DGB_CUDA(cudaEventRecord(fv->evStart, stream));
+  DGB_CUDA(cudaStreamWaitEvent(fv->sIn, fv->evStart, 0));
+  DGB_CUDA(cudaStreamWaitEvent(fv->sOut, fv->evStart, 0));
+  const size_t plane = size_t(of.size[0])*of.size[1];
+  const int nz = of.size[2];
+  auto zbegin = [&](int i) { return int((long long)nz*i/nslab); };
+  for (int i = 0; i < nslab; ++i) {
+    const size_t o = plane*zbegin(i), cnt = plane*(zbegin(i+1)-zbegin(i));
+    DGB_CUDA(cudaMemcpyAsync(fv->dStage[0] + o, h_c_in + o, cnt*sizeof(double), cudaMemcpyHostToDevice, fv->sIn));
+    DGB_CUDA(cudaEventRecord(fv->evIn[i], fv->sIn));
+  }
+  const long long sn = fv->step;
+  for (int i = 0; i < nslab; ++i) {
+    DGB_CUDA(cudaStreamWaitEvent(stream, fv->evIn[std::min(i+1, nslab-1)], 0));
+    FvArgs a = base_args(fv);
+    a.region.origin[2] = in.origin[2] + zbegin(i); a.region.size[2] = zbegin(i+1)-zbegin(i);
+    a.c = fv->dStage[0]; a.cnew = fv->dStage[1];
+    a.slotIn = fv->dSlots + (sn % 3); a.slotOut = fv->dSlots + ((sn+1) % 3); a.slotZero = fv->dSlots + ((sn+2) % 3);
+    a.dtOut = fv->dSlots + 3;
+    if (int rc = launch_step<false>(fv, a, stream)) return rc;
+    DGB_CUDA(cudaEventRecord(fv->evK[i], stream));
+    DGB_CUDA(cudaStreamWaitEvent(fv->sOut, fv->evK[i], 0));
+    const size_t o = plane*zbegin(i), cnt = plane*(zbegin(i+1)-zbegin(i));
+    DGB_CUDA(cudaMemcpyAsync(h_c_out + o, fv->dStage[1] + o, cnt*sizeof(double), cudaMemcpyDeviceToHost, fv->sOut));
+  }
+  if (int rc = nccl_allreduce(fv->dSlots + ((sn+1) % 3), 1, fv->comm, stream)) return rc;
+  fv->step = sn+1;
   if (dt_host) DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 3, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  DGB_CUDA(cudaEventRecord(fv->evEnd, fv->sOut));
+  DGB_CUDA(cudaStreamWaitEvent(stream, fv->evEnd, 0));
   DGB_CUDA(cudaStreamSynchronize(stream));
   return DGB_OK;
 }
