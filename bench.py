@@ -194,6 +194,7 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    barrier()                                   # the other ranks must not enter the timed region while rank 0 starts nvidia-smi
     l0 = fv.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

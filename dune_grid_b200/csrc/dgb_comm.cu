@@ -9,6 +9,7 @@
 // inside a single group over NVLink, and ONE kernel scatters (set or add) every received segment. Messages
 // to the own rank (periodic wrap on a 1-wide torus direction, torus.hh:395-403) are copied device-to-device.
 #include <dlfcn.h>
+#include <cstdlib>
 #include <nccl.h>
 #include <algorithm>
 #include <sstream>
@@ -195,9 +196,12 @@ CommPlan::~CommPlan() {
   if (dRecvBuf) cudaFree(dRecvBuf);
 }
 
+// blocks per box: enough to cover the box, capped so that pack/unpack, which run concurrently with the bulk FV kernel on
+// a high-priority stream, take SM slots away from it only briefly (DGB_HALO_MAXBLOCKS overrides the cap)
 static dim3 halo_grid(long long maxBox, int nBoxes) {
+  static const long long cap = [] { const char* e = getenv("DGB_HALO_MAXBLOCKS"); long long v = e ? atoll(e) : 2048; return v > 0 ? v : 2048; }();
   long long bx = (maxBox + PACK_THREADS - 1)/PACK_THREADS;
-  if (bx > 2048) bx = 2048;
+  if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   return dim3((unsigned)bx, (unsigned)nBoxes, 1);
 }
@@ -254,6 +258,7 @@ int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_a
   for (auto& s : plan.recvSeg) if (s.peer != myrank) remote = true;
   if (remote && !comm) return fail(DGB_EARG, "this exchange has remote partners: a dgb_comm is required");
   if (int rc = plan_pack(plan, d_arrays, item_sizes, narrays, stream)) return rc;
+  if (plan.trace[0]) cudaEventRecord(plan.trace[0], stream);
   int64_t bytes = 0;
   if (remote) {
     DGB_NCCL(g_nccl.GroupStart());
@@ -268,7 +273,10 @@ int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_a
     }
   }
   g->lastBytesSent = bytes;
-  return plan_unpack(plan, op, d_arrays, item_sizes, narrays, stream);
+  if (plan.trace[1]) cudaEventRecord(plan.trace[1], stream);
+  const int rcu = plan_unpack(plan, op, d_arrays, item_sizes, narrays, stream);
+  if (plan.trace[2]) cudaEventRecord(plan.trace[2], stream);
+  return rcu;
 }
 
 int get_plan(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir, const int32_t* item_sizes, int narrays,

@@ -30,6 +30,7 @@ struct CommPlan {
   double* dSendBuf = nullptr; double* dRecvBuf = nullptr;
   bool uploaded = false;
   long long launches = 0;
+  cudaEvent_t trace[3] = {nullptr, nullptr, nullptr};     // optional timing events: after pack, after transfer, after unpack (DGB_FV_TRACE)
   int upload();
   ~CommPlan();
 };

@@ -9,6 +9,7 @@
 // L1/L2. The CFL bound depends only on geometry and velocity (not on c), so the kernel of step n also reduces
 // max_i(sum of outflow factors) for step n+1 (velocities are time independent); one geometry-only bootstrap
 // reduction precedes the first step. min_i fl(1/s_i) == fl(1/max_i s_i) because correctly rounded division is monotone.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
@@ -65,12 +66,12 @@ struct FvArgs {
 
 // EXACT: the arithmetic of the per-entity CPU loop, operation by operation (bit-identical results).
 // SEPARABLE: face factor (u.n)|F|/|V| = (u.n)/w_dir taken from per-axis reciprocal tables (<= 2 ulp difference).
-template<int DIM, int MODE, bool REDUCE_ONLY>
+// PERM = 1 (thin-x slabs of the exchange shell): the fast thread index runs along y, blockIdx.z along x.
+template<int DIM, int MODE, bool REDUCE_ONLY, int PERM = 0>
 __global__ void __launch_bounds__(FBX*FBY) k_fv_step(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a) {
-  const int i0 = blockIdx.x*FBX + threadIdx.x;
-  const int i1 = blockIdx.y*FBY + threadIdx.y;
-  const int i2 = blockIdx.z;
-  const bool active = i0 < a.region.size[0] && i1 < a.region.size[1];
+  const int t0 = blockIdx.x*FBX + threadIdx.x, t1 = blockIdx.y*FBY + threadIdx.y, t2 = blockIdx.z;
+  const int i0 = PERM ? t2 : t0, i1 = PERM ? t0 : t1, i2 = PERM ? t1 : t2;
+  const bool active = i0 < a.region.size[0] && i1 < a.region.size[1] && (DIM < 3 || i2 < a.region.size[2]);
   double sum = 0.0;
   if (active) {
     const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
@@ -586,14 +587,23 @@ struct dgb_fv {
   FvProblem problem;
   FvTables tab;
   double* dTables = nullptr;
-  double* dSlots = nullptr;        // 3 rotating max-sum slots + dt + the constants {0, boundary value}
+  double* dSlots = nullptr;        // 4 rotating max-sum slots + dt + the constants {0, boundary value}: see slot_args
   long long step = 0;
   bool bootstrapped = false;
+  bool seedPending = false;      // dgb_fv_bootstrap_local: the reduced seed still has to be copied to the second slot
   int64_t launches = 0;
   std::shared_ptr<CommPlan> plan;
   double* dStage[2] = {nullptr, nullptr};     // device staging for the host-buffer entry point
   size_t stageBytes = 0;
   cudaStream_t sIn = nullptr, sOut = nullptr;  // copy streams of the pipelined host-buffer step
+  // exchange shell / bulk split of the interior box (3-D, ranks with overlap cells): the shell slabs are the interior
+  // cells some neighbour receives; they are updated first so that the exchange runs concurrently with the bulk
+  bool split = false;
+  dgb::FvRegion bulk; dgb::FvRegion shell[6]; int shellPerm[6]; int nShell = 0;
+  cudaStream_t sComm = nullptr;
+  cudaEvent_t evShell = nullptr, evBulk = nullptr, evDone = nullptr, evRed[2] = {nullptr, nullptr};
+  cudaEvent_t tr[4] = {nullptr, nullptr, nullptr, nullptr};   // DGB_FV_TRACE: step start, shell end, bulk end, step end (timed)
+  int traceLeft = 0;
   std::vector<cudaEvent_t> evIn, evK;
   cudaEvent_t evStart = nullptr, evEnd = nullptr;
 };
@@ -660,21 +670,75 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
   return DGB_OK;
 }
 
+// the per-cell kernel on an arbitrary 3-D region (exchange shell slabs); perm 1 = thin in x
+static int launch_cells(dgb_fv* fv, const FvArgs& a, int perm, cudaStream_t stream) {
+  const dgb_view& v = fv->view;
+  if (a.region.size[0] <= 0 || a.region.size[1] <= 0 || a.region.size[2] <= 0) return DGB_OK;
+  dim3 block(FBX, FBY, 1);
+  const bool exact = fv->mode == DGB_FV_EXACT;
+  if (perm) {
+    dim3 grid((a.region.size[1]+FBX-1)/FBX, (a.region.size[2]+FBY-1)/FBY, a.region.size[0]);
+    if (exact) k_fv_step<3, DGB_FV_EXACT, false, 1><<<grid, block, 0, stream>>>(v, a);
+    else k_fv_step<3, DGB_FV_SEPARABLE, false, 1><<<grid, block, 0, stream>>>(v, a);
+  } else {
+    dim3 grid((a.region.size[0]+FBX-1)/FBX, (a.region.size[1]+FBY-1)/FBY, a.region.size[2]);
+    if (exact) k_fv_step<3, DGB_FV_EXACT, false, 0><<<grid, block, 0, stream>>>(v, a);
+    else k_fv_step<3, DGB_FV_SEPARABLE, false, 0><<<grid, block, 0, stream>>>(v, a);
+  }
+  ++fv->launches;
+  DGB_CUDA(cudaGetLastError());
+  return DGB_OK;
+}
+
+// interior box = bulk + up to six disjoint shell slabs (z slabs over the full x-y extent, then y, then x)
+static void compute_split(dgb_fv* fv) {
+  const dgb_view& v = fv->view;
+  fv->split = false; fv->nShell = 0;
+  if (v.dim != 3) return;
+  const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+  const dgb_box& in = v.comp[0].box[DGB_BOX_INTERIOR];
+  const int t = v.overlap;
+  if (t <= 0) return;
+  FvRegion cur;
+  for (int i = 0; i < 3; ++i) { cur.origin[i] = in.origin[i]; cur.size[i] = in.size[i]; }
+  bool any = false;
+  for (int axis = 2; axis >= 0; --axis) {
+    const bool lo = of.origin[axis] < in.origin[axis], hi = of.origin[axis]+of.size[axis] > in.origin[axis]+in.size[axis];
+    if (cur.size[axis] < (lo ? t : 0) + (hi ? t : 0) + 1) { fv->nShell = 0; return; }        // no bulk left: keep one launch
+    if (lo) { FvRegion r = cur; r.size[axis] = t; fv->shellPerm[fv->nShell] = axis == 0; fv->shell[fv->nShell++] = r;
+              cur.origin[axis] += t; cur.size[axis] -= t; any = true; }
+    if (hi) { FvRegion r = cur; r.origin[axis] = cur.origin[axis]+cur.size[axis]-t; r.size[axis] = t;
+              fv->shellPerm[fv->nShell] = axis == 0; fv->shell[fv->nShell++] = r; cur.size[axis] -= t; any = true; }
+  }
+  fv->bulk = cur;
+  fv->split = any;
+}
+
 static FvArgs base_args(dgb_fv* fv) {
   FvArgs a{};
   const dgb_box& in = fv->view.comp[0].box[DGB_BOX_INTERIOR];
   for (int i = 0; i < 3; ++i) { a.region.origin[i] = in.origin[i]; a.region.size[i] = i < fv->view.dim ? in.size[i] : 1; }
-  a.problem = fv->problem; a.tab = fv->tab; a.consts = fv->dSlots + 4;
+  a.problem = fv->problem; a.tab = fv->tab; a.consts = fv->dSlots + 5;
   return a;
 }
 
-// geometry-only reduction that seeds the first step's dt
+// CFL slots. The outflow sums depend on geometry and velocity only, and the velocity fields are time independent, so the
+// value reduced while step n runs is used by step n+2: its all-reduce over the ranks then has a whole step to complete
+// off the critical path. Step n reads slot n%4 (reduced), accumulates its own maximum into slot (n+2)%4 and clears
+// slot (n+3)%4 for step n+1. [4] = dt of the last step, [5..6] = {0, boundary value}.
+static void slot_args(dgb_fv* fv, long long n, FvArgs& a) {
+  a.slotIn = fv->dSlots + (n % 4); a.slotOut = fv->dSlots + ((n+2) % 4); a.slotZero = fv->dSlots + ((n+3) % 4);
+  a.dtOut = fv->dSlots + 4;
+}
+
+// geometry-only reduction that seeds the first two steps' dt
 static int bootstrap(dgb_fv* fv, cudaStream_t stream) {
-  DGB_CUDA(cudaMemsetAsync(fv->dSlots, 0, 4*sizeof(double), stream));
+  DGB_CUDA(cudaMemsetAsync(fv->dSlots, 0, 5*sizeof(double), stream));
   FvArgs a = base_args(fv);
   a.slotOut = fv->dSlots + 0;
   if (int rc = launch_step<true>(fv, a, stream)) return rc;
   if (int rc = nccl_allreduce(fv->dSlots + 0, 1, fv->comm, stream)) return rc;
+  DGB_CUDA(cudaMemcpyAsync(fv->dSlots + 1, fv->dSlots + 0, sizeof(double), cudaMemcpyDeviceToDevice, stream));   // steps 0 and 1
   fv->bootstrapped = true; fv->step = 0;
   return DGB_OK;
 }
@@ -699,9 +763,9 @@ int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host
     dgb_mapper_init(&fv->view, block, &fv->mapper);
     fv->problem.id = problem;
     for (int i = 0; i < 12; ++i) fv->problem.p[i] = i < nparams ? params_host[i] : 0.0;
-    DGB_CUDA(cudaMalloc(&fv->dSlots, 6*sizeof(double)));
-    DGB_CUDA(cudaMemset(fv->dSlots, 0, 6*sizeof(double)));
-    DGB_CUDA(cudaMemcpy(fv->dSlots + 5, &fv->problem.p[3], sizeof(double), cudaMemcpyHostToDevice));   // {0, b}: FvArgs::consts
+    DGB_CUDA(cudaMalloc(&fv->dSlots, 7*sizeof(double)));
+    DGB_CUDA(cudaMemset(fv->dSlots, 0, 7*sizeof(double)));
+    DGB_CUDA(cudaMemcpy(fv->dSlots + 6, &fv->problem.p[3], sizeof(double), cudaMemcpyHostToDevice));   // {0, b}: FvArgs::consts
     // per-axis tables over the stored cell range
     const dgb_view& v = fv->view;
     const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
@@ -727,6 +791,19 @@ int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host
     if (fv->zparam) DGB_CUDA(cudaMemcpy(fv->ztab->rw, fv->tab.rw[2], of.size[2]*sizeof(double), cudaMemcpyDeviceToHost));
     const int32_t items[1] = {1};
     if (int rc = get_plan(g, level, fv->mapper, DGB_InteriorBorder_All_Interface, DGB_ForwardCommunication, items, 1, fv->plan)) return rc;
+    compute_split(fv.get());
+    if (getenv("DGB_FV_NO_SPLIT")) fv->split = false;
+    if (const char* e = getenv("DGB_FV_TRACE")) fv->traceLeft = atoi(e);
+    if (fv->split) {
+      int prLow = 0, prHigh = 0;
+      DGB_CUDA(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+      DGB_CUDA(cudaStreamCreateWithPriority(&fv->sComm, cudaStreamNonBlocking, prHigh));   // its small kernels must not queue behind the bulk's CTAs
+      DGB_CUDA(cudaEventCreateWithFlags(&fv->evShell, cudaEventDisableTiming));
+      DGB_CUDA(cudaEventCreateWithFlags(&fv->evBulk, cudaEventDisableTiming));
+      DGB_CUDA(cudaEventCreateWithFlags(&fv->evDone, cudaEventDisableTiming));
+      DGB_CUDA(cudaEventCreateWithFlags(&fv->evRed[0], cudaEventDisableTiming));
+      DGB_CUDA(cudaEventCreateWithFlags(&fv->evRed[1], cudaEventDisableTiming));
+    }
     *out = fv.release();
     return DGB_OK;
   });
@@ -742,6 +819,11 @@ int dgb_fv_destroy(dgb_fv* fv) {
   if (fv->evStart) cudaEventDestroy(fv->evStart);
   if (fv->evEnd) cudaEventDestroy(fv->evEnd);
   if (fv->sIn) cudaStreamDestroy(fv->sIn);
+  if (fv->sComm) cudaStreamDestroy(fv->sComm);
+  if (fv->evShell) cudaEventDestroy(fv->evShell);
+  if (fv->evBulk) cudaEventDestroy(fv->evBulk);
+  if (fv->evDone) cudaEventDestroy(fv->evDone);
+  for (int k = 0; k < 2; ++k) if (fv->evRed[k]) cudaEventDestroy(fv->evRed[k]);
   if (fv->sOut) cudaStreamDestroy(fv->sOut);
   delete fv;
   return DGB_OK;
@@ -765,10 +847,56 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
   const long long n = fv->step;
   FvArgs a = base_args(fv);
   a.c = d_c_in; a.cnew = d_c_out;
-  a.slotIn = fv->dSlots + (n % 3); a.slotOut = fv->dSlots + ((n+1) % 3); a.slotZero = fv->dSlots + ((n+2) % 3);
-  a.dtOut = fv->dSlots + 3;
+  slot_args(fv, n, a);
+  if (fv->split && (fv->plan->nSendBoxes || fv->plan->nRecvBoxes)) {
+    // overlapped form. Caller's stream: shell slabs, bulk. Exchange stream (high priority; every NCCL call of the
+    // step): [after the shell] pack, NCCL send/recv, unpack; [after the bulk] all-reduce of the CFL slot, which
+    // step n+2 reads - the caller's stream waits for it two steps later, and for the exchange at the end of this step.
+    const bool trace = fv->traceLeft > 0;
+    if (trace && !fv->tr[0]) { for (int k = 0; k < 4; ++k) cudaEventCreate(&fv->tr[k]); for (int k = 0; k < 3; ++k) cudaEventCreate(&fv->plan->trace[k]); }
+    if (n >= 2) DGB_CUDA(cudaStreamWaitEvent(stream, fv->evRed[n % 2], 0));           // slot n%4 was reduced during step n-1
+    if (trace) cudaEventRecord(fv->tr[0], stream);
+    for (int k = 0; k < fv->nShell; ++k) {
+      FvArgs s = a; s.region = fv->shell[k];
+      if (int rc = launch_cells(fv, s, fv->shellPerm[k], stream)) return rc;
+    }
+    DGB_CUDA(cudaEventRecord(fv->evShell, stream));
+    if (trace) cudaEventRecord(fv->tr[1], stream);
+    // the bulk is enqueued before the exchange: the host-side cost of the NCCL calls must not delay its start
+    FvArgs b = a; b.region = fv->bulk;
+    if (int rc = launch_step<false>(fv, b, stream)) return rc;
+    DGB_CUDA(cudaEventRecord(fv->evBulk, stream));
+    if (trace) cudaEventRecord(fv->tr[2], stream);
+    DGB_CUDA(cudaStreamWaitEvent(fv->sComm, fv->evShell, 0));
+    {
+      const int32_t items[1] = {1};
+      double* arrays[1] = { d_c_out };
+      const long long before = fv->plan->launches;
+      static const bool skipx = getenv("DGB_FV_DEBUG_SKIP_EXCHANGE") != nullptr;     // developer timing experiment only
+      if (!skipx) if (int rc = run_plan(fv->grid, *fv->plan, fv->view.rank, DGB_OP_SET, arrays, items, 1, fv->comm, fv->sComm)) return rc;
+      fv->launches += fv->plan->launches - before;
+    }
+    DGB_CUDA(cudaEventRecord(fv->evDone, fv->sComm));
+    DGB_CUDA(cudaStreamWaitEvent(stream, fv->evDone, 0));                              // overlap cells of c_out are in place
+    DGB_CUDA(cudaStreamWaitEvent(fv->sComm, fv->evBulk, 0));
+    if (int rc = nccl_allreduce(fv->dSlots + ((n+2) % 4), 1, fv->comm, fv->sComm)) return rc;
+    DGB_CUDA(cudaEventRecord(fv->evRed[n % 2], fv->sComm));
+    fv->step = n+1;
+    if (trace) {                                       // developer timeline (synchronises): ms since the start of the step
+      cudaEventRecord(fv->tr[3], stream);
+      cudaStreamSynchronize(stream);
+      float t[6] = {0, 0, 0, 0, 0, 0};
+      cudaEventElapsedTime(&t[0], fv->tr[0], fv->tr[1]); cudaEventElapsedTime(&t[1], fv->tr[0], fv->plan->trace[0]);
+      cudaEventElapsedTime(&t[2], fv->tr[0], fv->plan->trace[1]); cudaEventElapsedTime(&t[3], fv->tr[0], fv->plan->trace[2]);
+      cudaEventElapsedTime(&t[4], fv->tr[0], fv->tr[2]); cudaEventElapsedTime(&t[5], fv->tr[0], fv->tr[3]);
+      fprintf(stderr, "[dgb_fv trace rank %d] shell_end %.3f pack_end %.3f xfer_end %.3f unpack_end %.3f bulk_end %.3f step_end %.3f ms\n",
+              fv->view.rank, t[0], t[1], t[2], t[3], t[4], t[5]);
+      if (--fv->traceLeft == 0) for (int k = 0; k < 3; ++k) { cudaEventDestroy(fv->plan->trace[k]); fv->plan->trace[k] = nullptr; }
+    }
+    return DGB_OK;
+  }
   if (int rc = launch_step<false>(fv, a, stream)) return rc;
-  if (int rc = nccl_allreduce(fv->dSlots + ((n+1) % 3), 1, fv->comm, stream)) return rc;
+  if (int rc = nccl_allreduce(fv->dSlots + ((n+2) % 4), 1, fv->comm, stream)) return rc;
   // refresh the overlap cells of c_out: communicate(InteriorBorder_All_Interface, ForwardCommunication), set
   if (fv->plan->nSendBoxes || fv->plan->nRecvBoxes) {
     const int32_t items[1] = {1};
@@ -783,11 +911,11 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
 
 int dgb_fv_bootstrap_local(dgb_fv* fv, double** d_pending_max, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DGB_CUDA(cudaMemsetAsync(fv->dSlots, 0, 4*sizeof(double), stream));
+  DGB_CUDA(cudaMemsetAsync(fv->dSlots, 0, 5*sizeof(double), stream));
   FvArgs a = base_args(fv);
   a.slotOut = fv->dSlots + 0;
   if (int rc = launch_step<true>(fv, a, stream)) return rc;
-  fv->bootstrapped = true; fv->step = 0;
+  fv->bootstrapped = true; fv->step = 0; fv->seedPending = true;      // slot 1 = slot 0 once the caller has reduced slot 0
   if (d_pending_max) *d_pending_max = fv->dSlots + 0;
   return DGB_OK;
 }
@@ -796,12 +924,22 @@ int dgb_fv_step_local(dgb_fv* fv, const double* d_c_in, double* d_c_out, double*
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!fv->bootstrapped) return fail(DGB_EARG, "dgb_fv_step_local: call dgb_fv_bootstrap_local (and reduce its result over ranks) first");
   const long long n = fv->step;
+  if (fv->seedPending) {                                      // the caller has reduced slot 0 by now
+    DGB_CUDA(cudaMemcpyAsync(fv->dSlots + 1, fv->dSlots + 0, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    fv->seedPending = false;
+  }
   FvArgs a = base_args(fv);
   a.c = d_c_in; a.cnew = d_c_out;
-  a.slotIn = fv->dSlots + (n % 3); a.slotOut = fv->dSlots + ((n+1) % 3); a.slotZero = fv->dSlots + ((n+2) % 3);
-  a.dtOut = fv->dSlots + 3;
-  if (int rc = launch_step<false>(fv, a, stream)) return rc;
-  if (d_pending_max) *d_pending_max = fv->dSlots + ((n+1) % 3);
+  slot_args(fv, n, a);
+  if (fv->split && getenv("DGB_FV_SPLIT_LOCAL")) {            // the shell / bulk decomposition of dgb_fv_step, without exchange
+    for (int k = 0; k < fv->nShell; ++k) {
+      FvArgs s = a; s.region = fv->shell[k];
+      if (int rc = launch_cells(fv, s, fv->shellPerm[k], stream)) return rc;
+    }
+    FvArgs b = a; b.region = fv->bulk;
+    if (int rc = launch_step<false>(fv, b, stream)) return rc;
+  } else if (int rc = launch_step<false>(fv, a, stream)) return rc;
+  if (d_pending_max) *d_pending_max = fv->dSlots + ((n+2) % 4);
   fv->step = n+1;
   return DGB_OK;
 }
@@ -813,14 +951,14 @@ int dgb_fv_update(dgb_fv* fv, const double* d_c_in, double* d_update, void* stre
   const long long n = fv->step;
   FvArgs a = base_args(fv);
   a.c = d_c_in; a.update = d_update;
-  a.slotIn = fv->dSlots + (n % 3); a.slotOut = fv->dSlots + ((n+2) % 3); a.dtOut = fv->dSlots + 3;
+  a.slotIn = fv->dSlots + (n % 4); a.slotOut = fv->dSlots + ((n+3) % 4); a.dtOut = fv->dSlots + 4;
   if (int rc = launch_step<false>(fv, a, stream)) return rc;
-  DGB_CUDA(cudaMemsetAsync(fv->dSlots + ((n+2) % 3), 0, sizeof(double), stream));
+  DGB_CUDA(cudaMemsetAsync(fv->dSlots + ((n+3) % 4), 0, sizeof(double), stream));
   return DGB_OK;
 }
 
 int dgb_fv_last_dt(dgb_fv* fv, double* dt_host, void* stream) {
-  DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 3, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 4, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   DGB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return DGB_OK;
 }
@@ -849,7 +987,7 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
     // every stored cell of the result is written: interior cells by the kernel, overlap cells by the exchange
     if (int rc = dgb_fv_step(fv, fv->dStage[0], fv->dStage[1], stream)) return rc;
     DGB_CUDA(cudaMemcpyAsync(h_c_out, fv->dStage[1], bytes, cudaMemcpyDeviceToHost, stream));
-    if (dt_host) DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 3, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (dt_host) DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 4, sizeof(double), cudaMemcpyDeviceToHost, stream));
     DGB_CUDA(cudaStreamSynchronize(stream));
     return DGB_OK;
   }
@@ -882,17 +1020,16 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
     FvArgs a = base_args(fv);
     a.region.origin[2] = in.origin[2] + zbegin(i); a.region.size[2] = zbegin(i+1)-zbegin(i);
     a.c = fv->dStage[0]; a.cnew = fv->dStage[1];
-    a.slotIn = fv->dSlots + (sn % 3); a.slotOut = fv->dSlots + ((sn+1) % 3); a.slotZero = fv->dSlots + ((sn+2) % 3);
-    a.dtOut = fv->dSlots + 3;
+    slot_args(fv, sn, a);
     if (int rc = launch_step<false>(fv, a, stream)) return rc;
     DGB_CUDA(cudaEventRecord(fv->evK[i], stream));
     DGB_CUDA(cudaStreamWaitEvent(fv->sOut, fv->evK[i], 0));
     const size_t o = plane*zbegin(i), cnt = plane*(zbegin(i+1)-zbegin(i));
     DGB_CUDA(cudaMemcpyAsync(h_c_out + o, fv->dStage[1] + o, cnt*sizeof(double), cudaMemcpyDeviceToHost, fv->sOut));
   }
-  if (int rc = nccl_allreduce(fv->dSlots + ((sn+1) % 3), 1, fv->comm, stream)) return rc;
+  if (int rc = nccl_allreduce(fv->dSlots + ((sn+2) % 4), 1, fv->comm, stream)) return rc;
   fv->step = sn+1;
-  if (dt_host) DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 3, sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (dt_host) DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 4, sizeof(double), cudaMemcpyDeviceToHost, stream));
   DGB_CUDA(cudaEventRecord(fv->evEnd, fv->sOut));
   DGB_CUDA(cudaStreamWaitEvent(stream, fv->evEnd, 0));
   DGB_CUDA(cudaStreamSynchronize(stream));

@@ -1,0 +1,87 @@
+"""Multi-GPU parity of the public FV step (dgb_fv_step: shell/bulk split, NCCL exchange overlapped with the bulk kernel,
+all-reduce of the CFL value) and of dgb_communicate against the CPU oracle. Run under torchrun, one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/multigpu_check.py
+
+Each rank builds its own grid, rank 0's oracle world simulates all N ranks; every rank compares its own arrays."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import dune_grid_b200 as dg  # noqa: E402
+from tests.common import best_oracle, make_cfg, oracle_world, product_grid  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = dg.Communicator.from_torch_distributed()
+    o = best_oracle()
+    cases = [
+        (make_cfg(dim=3, N=(24, 20, 16)), 0, [1.0, 1.0, 1.0, 0.0, 0.25, 0.25, 0.25, 0.125, 0.2]),
+        (make_cfg(dim=3, N=(20, 24, 18), periodic=5, upper=(1.0, 2.0, 1.5)), 0, [-1.0, 0.7, 0.3, 0.0, 0.5, 1.0, 0.7, 0.1, 0.45]),
+        (make_cfg(dim=3, N=(16, 16, 24), mode=2), 1, [1.5, 0, 0, 0.25, 0.5, 0.5, 0.5, 0.1, 0.6]),
+        (make_cfg(dim=2, N=(32, 24), periodic=1), 1, [1.0, 0, 0, 0.0, 0.5, 0.5, 0.0, 0.1, 0.3]),
+    ]
+    failures = 0
+    for cfg, problem, params in cases:
+        w = oracle_world(o, cfg, world)
+        g = product_grid(cfg, rank, world, comm=comm)
+        gv = g.leafGridView()
+        for mode in ("exact", "separable"):
+            ref = [w.fv_init(r, 0, problem, params) for r in range(world)]
+            fv = dg.FiniteVolume(g, 0, problem, params, mode)
+            c = fv.initial()
+            cn = torch.empty_like(c)
+            ok = np.array_equal(c.cpu().numpy(), ref[rank])
+            for _ in range(4):
+                dt_ref = w.fv_step(0, problem, params, ref)
+                fv.step(c, cn)
+                c, cn = cn, c
+                dt = fv.last_dt()
+                ok = ok and (dt == dt_ref if mode == "exact" else abs(dt - dt_ref) <= 1e-13 * dt_ref)
+            got = c.cpu().numpy()
+            scale = max(np.abs(x).max() for x in ref)
+            if mode == "exact":
+                ok = ok and np.array_equal(got, ref[rank])
+            else:
+                ok = ok and np.abs(got - ref[rank]).max() <= 1e-13 * scale           # tolerance: 1e-13 relative
+            if not ok:
+                failures += 1
+                print(f"rank {rank}: FV mismatch cfg={cfg['N']} mode={mode} maxdiff={np.abs(got - ref[rank]).max()}", flush=True)
+        # communicate through the public call (NCCL transport), all interfaces, set and add
+        layout = [1] + [0] * (cfg["dim"] - 1) + [1]
+        m = dg.MultipleCodimMultipleGeomTypeMapper(gv, layout)
+        rng = np.random.default_rng(99)
+        for iftype in range(5):
+            for direction in (0, 1):
+                for op in ("set", "add"):
+                    sizes = [w.mapper_size(r, 0, layout) for r in range(world)]
+                    host = [[rng.standard_normal(sizes[r]), rng.standard_normal(sizes[r] * 2)] for r in range(world)]
+                    dev = [torch.from_numpy(a.copy()).cuda() for a in host[rank]]
+                    w.communicate(0, layout, iftype, direction, 0 if op == "set" else 1, host, [1, 2])
+                    gv.communicate(m, dev, iftype, direction, op)
+                    torch.cuda.synchronize()
+                    for a in range(2):
+                        if not np.array_equal(dev[a].cpu().numpy(), host[rank][a]):
+                            failures += 1
+                            print(f"rank {rank}: communicate mismatch cfg={cfg['N']} if={iftype} dir={direction} op={op}", flush=True)
+        w.close()
+    t = torch.tensor([failures], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print(f"multigpu_check world={world}: {'OK' if t.item() == 0 else 'FAILED'} ({int(t.item())} mismatches)", flush=True)
+    dist.barrier()
+    comm.close()
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
