@@ -1,0 +1,299 @@
+// bulkgrid.hh — header-only C++17 "bulk GridView" layer over the C ABI of libdgb.so (include/dgb.h).
+//
+// It keeps the operator surface of the reference for the YaspGrid leaf-sweep path, with per-entity calls turned into
+// per-view bulk calls that return device arrays in the reference's iteration order:
+//
+//   Dune::YaspGrid<dim,Coordinates>(L, s, periodic, overlap, comm)   dune/grid/yaspgrid.hh:904-909,974-980,1043-1047
+//     -> DuneB200::BulkYaspGrid<dim>(L, s, periodic, overlap, rank, nranks, comm)
+//   grid.leafGridView() / levelGridView(l), globalRefine, refineOptions   dune/grid/common/grid.hh:878-891, yaspgrid.hh:1216,1270
+//   gv.size(codim), gv.overlapSize(codim), gv.ghostSize(codim)            dune/grid/common/gridview.hh:186-198,343-355
+//   for (e : elements(gv, ps)) { is.index(e); e.partitionType(); e.geometry().center()/volume() }
+//     -> gv.elements<codim>(pit)  (index, partitionType, lower, upper, center, volume arrays)     rangegenerators.hh:881
+//   for (is : intersections(gv,e)) { is.neighbor(); is.boundary(); is.outside(); is.boundarySegmentIndex();
+//                                    is.centerUnitOuterNormal(); is.geometry().center()/volume() }
+//     -> gv.intersections(pit)                                                                     rangegenerators.hh:845
+//   geo.global(x) / jacobianInverseTransposed(x) / integrationElement(x) at quadrature points
+//     -> gv.geometry(qp, pit)                                                                      common/geometry.hh:194-371
+//   MultipleCodimMultipleGeomTypeMapper<GV>(gv, layout).index(e)/subIndex(e,i,cc)/size()           common/mcmgmapper.hh:129-343
+//     -> BulkMapper(gv, layout).index(codim,pit) / subIndex(cc,pit) / size()
+//   gv.communicate(dataHandle, InteriorBorder_All_Interface, ForwardCommunication)                 common/gridview.hh:334-341
+//     -> gv.communicate(BulkDataHandle{mapper, arrays...}, iftype, dir)   (the shape of NumPyCommDataHandle,
+//        dune/python/grid/numpycommdatahandle.hh:41-142)
+//
+// Exceptions mirror the reference's: GridError (yaspgrid.hh:788,1053,1219), RangeError (:1745,1817), Exception.
+// Only the CUDA runtime API header is needed (no nvcc): g++ -std=c++17 -I include -I $CUDA/include x.cc -L... -ldgb -lcudart
+#ifndef DUNE_GRID_B200_BULKGRID_HH
+#define DUNE_GRID_B200_BULKGRID_HH
+#include <array>
+#include <bitset>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include <cuda_runtime_api.h>
+
+#include "../dgb.h"
+
+namespace DuneB200 {
+
+// dune/grid/common/gridenums.hh — identical names and values
+enum PartitionType { InteriorEntity = 0, BorderEntity = 1, OverlapEntity = 2, FrontEntity = 3, GhostEntity = 4 };
+enum InterfaceType { InteriorBorder_InteriorBorder_Interface = 0, InteriorBorder_All_Interface = 1,
+                     Overlap_OverlapFront_Interface = 2, Overlap_All_Interface = 3, All_All_Interface = 4 };
+enum PartitionIteratorType { Interior_Partition = 0, InteriorBorder_Partition = 1, Overlap_Partition = 2,
+                             OverlapFront_Partition = 3, All_Partition = 4, Ghost_Partition = 5 };
+enum CommunicationDirection { ForwardCommunication = 0, BackwardCommunication = 1 };
+enum class CommOp { set = 0, add = 1 };                      // dune/python/grid/mapper.hh:117-137
+
+struct Exception : std::runtime_error { using std::runtime_error::runtime_error; };
+struct GridError : Exception { using Exception::Exception; };
+struct RangeError : Exception { using Exception::Exception; };
+struct CudaError : Exception { using Exception::Exception; };
+
+inline void check(int rc) {
+  if (rc == DGB_OK) return;
+  const std::string msg = dgb_last_error();
+  switch (rc) {
+    case DGB_EGRID: throw GridError(msg);
+    case DGB_ERANGE: throw RangeError(msg);
+    case DGB_ECUDA: case DGB_ENCCL: throw CudaError(msg);
+    default: throw Exception(msg);
+  }
+}
+
+// caller-owned device memory (RAII); the library never allocates user data
+template<class T>
+class DeviceArray {
+  T* p_ = nullptr; std::size_t n_ = 0;
+public:
+  DeviceArray() = default;
+  explicit DeviceArray(std::size_t n) : n_(n) {
+    if (n && cudaMalloc(reinterpret_cast<void**>(&p_), n*sizeof(T)) != cudaSuccess) throw CudaError("cudaMalloc failed");
+  }
+  DeviceArray(DeviceArray&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  DeviceArray& operator=(DeviceArray&& o) noexcept { std::swap(p_, o.p_); std::swap(n_, o.n_); return *this; }
+  DeviceArray(const DeviceArray&) = delete;
+  DeviceArray& operator=(const DeviceArray&) = delete;
+  ~DeviceArray() { if (p_) cudaFree(p_); }
+  T* data() { return p_; }
+  const T* data() const { return p_; }
+  std::size_t size() const { return n_; }
+  std::vector<T> toHost(cudaStream_t s = nullptr) const {
+    std::vector<T> h(n_);
+    if (n_) { cudaMemcpyAsync(h.data(), p_, n_*sizeof(T), cudaMemcpyDeviceToHost, s); cudaStreamSynchronize(s); }
+    return h;
+  }
+  void fromHost(const std::vector<T>& h, cudaStream_t s = nullptr) {
+    if (h.size() != n_) throw Exception("DeviceArray::fromHost: size mismatch");
+    if (n_) { cudaMemcpyAsync(p_, h.data(), n_*sizeof(T), cudaMemcpyHostToDevice, s); cudaStreamSynchronize(s); }
+  }
+};
+
+// the NCCL communicator of the torus exchange (replaces the MPI communicator handed to YaspGrid)
+class Communicator {
+  dgb_comm* c_ = nullptr;
+public:
+  Communicator() = default;
+  Communicator(const void* ncclUniqueId128, int rank, int nranks) { check(dgb_comm_init(ncclUniqueId128, rank, nranks, &c_)); }
+  Communicator(Communicator&& o) noexcept : c_(o.c_) { o.c_ = nullptr; }
+  Communicator(const Communicator&) = delete;
+  ~Communicator() { if (c_) dgb_comm_destroy(c_); }
+  static std::array<char,128> uniqueId() { std::array<char,128> id{}; check(dgb_comm_unique_id(id.data())); return id; }
+  dgb_comm* handle() const { return c_; }
+};
+
+template<int dim> class BulkYaspGrid;
+template<int dim> class BulkGridView;
+template<int dim> class BulkMapper;
+
+// result of elements<codim>(): arrays in iteration order of the partition; vectors are component-major [d*n + e]
+struct ElementRange {
+  std::int64_t n = 0;
+  DeviceArray<std::uint32_t> index;            // indexSet().index(e)
+  DeviceArray<std::uint8_t> partitionType;     // e.partitionType()
+  DeviceArray<double> lower, upper, center;    // geometry().corner(0), corner(last), center()
+  DeviceArray<double> volume;                  // geometry().volume()
+};
+// result of intersections(): per cell and face k in reference order (dir = k/2, side = k%2): [k*n + cell]
+struct IntersectionRange {
+  std::int64_t n = 0;
+  DeviceArray<std::uint8_t> neighbor, boundary;
+  DeviceArray<std::int32_t> outside;               // indexSet().index(is.outside()) or -1
+  DeviceArray<std::int32_t> boundarySegmentIndex;  // or -1
+  DeviceArray<double> center;                      // [(k*dim+d)*n + cell]
+  DeviceArray<double> volume;
+};
+struct GeometryRange {
+  std::int64_t n = 0; int nqp = 0;
+  DeviceArray<double> global;                      // [(q*dim+d)*n + e]
+  DeviceArray<double> jacobianInverseTransposed;   // [((q*dim+r)*dim+c)*n + e]
+  DeviceArray<double> integrationElement;          // [q*n + e]
+};
+
+// MCMGLayout for Yasp: block size per codimension (mcmgmapper.hh:64-110; one geometry type per codim)
+template<int dim> std::array<std::uint32_t,4> mcmgElementLayout() { std::array<std::uint32_t,4> l{}; l[0] = 1; return l; }
+template<int dim> std::array<std::uint32_t,4> mcmgVertexLayout() { std::array<std::uint32_t,4> l{}; l[dim] = 1; return l; }
+
+template<int dim>
+class BulkGridView {
+  const BulkYaspGrid<dim>* grid_; dgb_view v_;
+  friend class BulkYaspGrid<dim>; friend class BulkMapper<dim>;
+  BulkGridView(const BulkYaspGrid<dim>* g, const dgb_view& v) : grid_(g), v_(v) {}
+public:
+  enum { dimension = dim };
+  const dgb_view& descriptor() const { return v_; }
+  const BulkYaspGrid<dim>& grid() const { return *grid_; }
+  int level() const { return v_.level; }
+  std::int64_t size(int codim) const { std::int64_t n; check(dgb_view_size(&v_, codim, &n)); return n; }
+  std::int64_t size(int codim, PartitionIteratorType pit) const { std::int64_t n; check(dgb_view_partition_size(&v_, codim, pit, &n)); return n; }
+  int overlapSize(int codim) const { int n; check(dgb_view_overlap_size(&v_, codim, &n)); return n; }
+  int ghostSize(int codim) const { int n; check(dgb_view_ghost_size(&v_, codim, &n)); return n; }
+
+  template<int codim = 0>
+  ElementRange elements(PartitionIteratorType pit = All_Partition, bool geometry = true, cudaStream_t s = nullptr) const {
+    ElementRange r; r.n = size(codim, pit);
+    r.index = DeviceArray<std::uint32_t>(r.n); r.partitionType = DeviceArray<std::uint8_t>(r.n);
+    if (geometry) { r.lower = DeviceArray<double>(dim*r.n); r.upper = DeviceArray<double>(dim*r.n);
+                    r.center = DeviceArray<double>(dim*r.n); r.volume = DeviceArray<double>(r.n); }
+    check(dgb_elements_materialize(&v_, codim, pit, r.index.data(), r.partitionType.data(), nullptr, r.lower.data(), r.upper.data(),
+                                   r.center.data(), r.volume.data(), s));
+    return r;
+  }
+  IntersectionRange intersections(PartitionIteratorType pit = All_Partition, bool geometry = true, cudaStream_t s = nullptr) const {
+    IntersectionRange r; r.n = size(0, pit);
+    const std::size_t m = 2*dim*r.n;
+    r.neighbor = DeviceArray<std::uint8_t>(m); r.boundary = DeviceArray<std::uint8_t>(m);
+    r.outside = DeviceArray<std::int32_t>(m); r.boundarySegmentIndex = DeviceArray<std::int32_t>(m);
+    if (geometry) { r.center = DeviceArray<double>(dim*m); r.volume = DeviceArray<double>(m); }
+    check(dgb_intersections_materialize(&v_, pit, r.neighbor.data(), r.boundary.data(), r.outside.data(), r.boundarySegmentIndex.data(),
+                                        r.center.data(), r.volume.data(), s));
+    return r;
+  }
+  // YaspIntersection::centerUnitOuterNormal (yaspgridintersection.hh:177-182): +-e_dir for face k, the same for all cells
+  std::array<double,dim> centerUnitOuterNormal(int k) const { std::array<double,dim> n{}; n[k/2] = (k%2) ? 1.0 : -1.0; return n; }
+  GeometryRange geometry(const std::vector<std::array<double,dim>>& qp, PartitionIteratorType pit = All_Partition, cudaStream_t s = nullptr) const {
+    GeometryRange r; r.n = size(0, pit); r.nqp = int(qp.size());
+    r.global = DeviceArray<double>(std::size_t(r.nqp)*dim*r.n);
+    r.jacobianInverseTransposed = DeviceArray<double>(std::size_t(r.nqp)*dim*dim*r.n);
+    r.integrationElement = DeviceArray<double>(std::size_t(r.nqp)*r.n);
+    check(dgb_geometry_eval(&v_, pit, r.nqp, qp.empty() ? nullptr : qp[0].data(), r.global.data(), r.jacobianInverseTransposed.data(),
+                            r.integrationElement.data(), s));
+    return r;
+  }
+  // communicate: the data handle is "arrays indexed by a mapper" with a combine operation
+  template<class DataHandle>
+  void communicate(DataHandle& dh, InterfaceType iftype, CommunicationDirection dir, cudaStream_t s = nullptr) const;
+};
+
+template<int dim>
+class BulkMapper {
+  const BulkGridView<dim>* gv_; dgb_mapper m_;
+public:
+  BulkMapper(const BulkGridView<dim>& gv, const std::array<std::uint32_t,4>& layout) : gv_(&gv) { check(dgb_mapper_init(&gv.v_, layout.data(), &m_)); }
+  const dgb_mapper& descriptor() const { return m_; }
+  std::int64_t size() const { std::int64_t n; check(dgb_mapper_size(&m_, &n)); return n; }
+  DeviceArray<std::uint32_t> index(int codim, PartitionIteratorType pit = All_Partition, cudaStream_t s = nullptr) const {
+    DeviceArray<std::uint32_t> out(gv_->size(codim, pit));
+    check(dgb_mapper_index(&gv_->v_, &m_, codim, pit, out.data(), s));
+    return out;
+  }
+  // [i*n + cell]: subIndex(e, i, cc) for all cells of the partition
+  DeviceArray<std::uint32_t> subIndex(int cc, PartitionIteratorType pit = All_Partition, cudaStream_t s = nullptr) const {
+    std::size_t nsub = 1; for (int k = 0; k < cc; ++k) nsub = nsub*(dim-k)/(k+1);
+    nsub <<= cc;
+    DeviceArray<std::uint32_t> out(nsub*gv_->size(0, pit));
+    check(dgb_mapper_subindex(&gv_->v_, &m_, cc, pit, out.data(), s));
+    return out;
+  }
+};
+
+// NumPyCommDataHandle-shaped data handle: arrays[a] holds itemSize[a] doubles per mapper entry
+template<int dim>
+struct BulkDataHandle {
+  const BulkMapper<dim>& mapper;
+  std::vector<double*> arrays;
+  std::vector<std::int32_t> itemSizes;
+  CommOp op = CommOp::set;
+};
+
+template<int dim>
+class BulkYaspGrid {
+  dgb_grid* g_ = nullptr; dgb_comm* comm_ = nullptr;
+  std::vector<std::vector<double>> keep_;
+  void create(dgb_grid_spec& s, int rank, int nranks) { check(dgb_grid_create(&s, rank, nranks, &g_)); }
+  static dgb_grid_spec base(const std::array<int,dim>& s, std::bitset<dim> periodic, int overlap) {
+    dgb_grid_spec sp{}; sp.dim = dim; sp.overlap = overlap; sp.periodic = unsigned(periodic.to_ulong()); sp.partitioner = DGB_PART_DEFAULT;
+    for (int i = 0; i < 3; ++i) { sp.N[i] = i < dim ? s[i] : 1; sp.upper[i] = 1.0; sp.fixed_dims[i] = 1; }
+    return sp;
+  }
+public:
+  enum { dimension = dim, dimensionworld = dim };
+  // EquidistantCoordinates (yaspgrid.hh:904-909)
+  BulkYaspGrid(const std::array<double,dim>& L, const std::array<int,dim>& s, std::bitset<dim> periodic = {}, int overlap = 1,
+               int rank = 0, int nranks = 1, const Communicator* comm = nullptr) : comm_(comm ? comm->handle() : nullptr) {
+    dgb_grid_spec sp = base(s, periodic, overlap); sp.coord_mode = DGB_COORD_EQUIDISTANT;
+    for (int i = 0; i < dim; ++i) sp.upper[i] = L[i];
+    create(sp, rank, nranks);
+  }
+  // EquidistantOffsetCoordinates (yaspgrid.hh:974-980)
+  BulkYaspGrid(const std::array<double,dim>& lowerleft, const std::array<double,dim>& upperright, const std::array<int,dim>& s,
+               std::bitset<dim> periodic = {}, int overlap = 1, int rank = 0, int nranks = 1, const Communicator* comm = nullptr)
+      : comm_(comm ? comm->handle() : nullptr) {
+    dgb_grid_spec sp = base(s, periodic, overlap); sp.coord_mode = DGB_COORD_EQUIDISTANT_OFFSET;
+    for (int i = 0; i < dim; ++i) { sp.lower[i] = lowerleft[i]; sp.upper[i] = upperright[i]; }
+    create(sp, rank, nranks);
+  }
+  // TensorProductCoordinates (yaspgrid.hh:1043-1047)
+  BulkYaspGrid(const std::array<std::vector<double>,dim>& coords, std::bitset<dim> periodic = {}, int overlap = 1,
+               int rank = 0, int nranks = 1, const Communicator* comm = nullptr) : comm_(comm ? comm->handle() : nullptr) {
+    std::array<int,dim> s{};
+    for (int i = 0; i < dim; ++i) s[i] = int(coords[i].size())-1;
+    dgb_grid_spec sp = base(s, periodic, overlap); sp.coord_mode = DGB_COORD_TENSORPRODUCT;
+    keep_.assign(coords.begin(), coords.end());
+    for (int i = 0; i < dim; ++i) sp.tensor[i] = keep_[i].data();
+    create(sp, rank, nranks);
+  }
+  BulkYaspGrid(const BulkYaspGrid&) = delete;
+  ~BulkYaspGrid() { if (g_) dgb_grid_destroy(g_); }
+
+  dgb_grid* handle() const { return g_; }
+  dgb_comm* comm() const { return comm_; }
+  void refineOptions(bool keepPhysicalOverlap) { check(dgb_grid_refine_options(g_, keepPhysicalOverlap)); }
+  void globalRefine(int refCount) { check(dgb_grid_global_refine(g_, refCount)); }
+  int maxLevel() const { int m; check(dgb_grid_max_level(g_, &m)); return m; }
+  std::int64_t numBoundarySegments() const { std::int64_t n; check(dgb_grid_num_boundary_segments(g_, &n)); return n; }
+  std::array<double,dim> domainSize() const { double L[3]; check(dgb_grid_domain_size(g_, L)); std::array<double,dim> r{}; for (int i = 0; i < dim; ++i) r[i] = L[i]; return r; }
+  std::array<int,dim> torusDims() const { std::int32_t d[3]; check(dgb_grid_torus_dims(g_, d)); std::array<int,dim> r{}; for (int i = 0; i < dim; ++i) r[i] = d[i]; return r; }
+  BulkGridView<dim> leafGridView() const { dgb_view v; check(dgb_view_leaf(g_, &v)); return BulkGridView<dim>(this, v); }
+  BulkGridView<dim> levelGridView(int level) const { dgb_view v; check(dgb_view_level(g_, level, &v)); return BulkGridView<dim>(this, v); }
+};
+
+template<int dim>
+template<class DataHandle>
+void BulkGridView<dim>::communicate(DataHandle& dh, InterfaceType iftype, CommunicationDirection dir, cudaStream_t s) const {
+  check(dgb_communicate(grid_->handle(), v_.level, &dh.mapper.descriptor(), iftype, dir, int(dh.op), dh.arrays.data(), dh.itemSizes.data(),
+                        int(dh.arrays.size()), grid_->comm(), s));
+}
+
+// the explicit upwind finite-volume transport functor (include/dgb.h)
+template<int dim>
+class FiniteVolume {
+  dgb_fv* fv_ = nullptr;
+public:
+  enum Mode { exact = DGB_FV_EXACT, separable = DGB_FV_SEPARABLE };
+  FiniteVolume(BulkYaspGrid<dim>& grid, int level, int problem, const std::vector<double>& params, Mode mode = separable) {
+    check(dgb_fv_create(grid.handle(), level, problem, params.data(), int(params.size()), mode, grid.comm(), &fv_));
+  }
+  FiniteVolume(const FiniteVolume&) = delete;
+  ~FiniteVolume() { if (fv_) dgb_fv_destroy(fv_); }
+  void initial(double* d_c, cudaStream_t s = nullptr) { check(dgb_fv_init_field(fv_, d_c, s)); }
+  void step(const double* d_c_in, double* d_c_out, cudaStream_t s = nullptr) { check(dgb_fv_step(fv_, d_c_in, d_c_out, s)); }
+  double stepHost(const double* h_c_in, double* h_c_out, cudaStream_t s = nullptr) { double dt; check(dgb_fv_step_host(fv_, h_c_in, h_c_out, &dt, s)); return dt; }
+  double lastDt(cudaStream_t s = nullptr) { double dt; check(dgb_fv_last_dt(fv_, &dt, s)); return dt; }
+};
+
+} // namespace DuneB200
+#endif

@@ -1,0 +1,136 @@
+// bulk_gridview_test.cc — the C++ bulk GridView (include/dune_grid_b200/bulkgrid.hh) exercised the way the reference's
+// tests exercise a grid view: sizes (test/gridcheck.hh), index-set consecutiveness and sub-index consistency
+// (test/checkindexset.hh:76-282), boundary-segment bijection (test/gridcheck.hh:844-925), intersection / neighbour symmetry
+// (test/checkintersectionit.hh:275-400), geometry volume sums, and mass conservation of the FV functor.
+// Usage: bulk_gridview_test [--device]   (without --device only the host-side descriptor queries run)
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <set>
+
+#include <dune_grid_b200/bulkgrid.hh>
+
+using namespace DuneB200;
+
+static int failures = 0;
+#define CHECK(cond) do { if (!(cond)) { std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); ++failures; } } while (0)
+
+template<int dim>
+void hostChecks() {
+  std::array<double,dim> L; std::array<int,dim> s;
+  for (int i = 0; i < dim; ++i) { L[i] = 1.0 + i; s[i] = 8 >> (i > 0); }          // 8x4(x4): test/yasp/test-yaspgrid.hh:48-54
+  BulkYaspGrid<dim> grid(L, s, std::bitset<dim>(), 1);
+  auto gv = grid.leafGridView();
+  std::int64_t cells = 1, verts = 1;
+  for (int i = 0; i < dim; ++i) { cells *= s[i]; verts *= s[i]+1; }
+  CHECK(gv.size(0) == cells);
+  CHECK(gv.size(dim) == verts);
+  CHECK(gv.size(0, Interior_Partition) == cells);
+  CHECK(gv.size(0, Ghost_Partition) == 0);
+  CHECK(gv.overlapSize(0) == 1 && gv.ghostSize(0) == 0);
+  CHECK(grid.maxLevel() == 0);
+  std::int64_t nbs = 0;
+  for (int k = 0; k < dim; ++k) { std::int64_t f = 2; for (int l = 0; l < dim; ++l) if (l != k) f *= s[l]; nbs += f; }
+  CHECK(grid.numBoundarySegments() == nbs);
+  grid.globalRefine(1);
+  CHECK(grid.maxLevel() == 1);
+  CHECK(grid.leafGridView().size(0) == cells << dim);
+  CHECK(grid.levelGridView(0).size(0) == cells);
+  bool threw = false;
+  try { grid.levelGridView(5); } catch (const RangeError&) { threw = true; }       // yaspgrid.hh:1745
+  CHECK(threw);
+  BulkMapper<dim> all(gv, [] { std::array<std::uint32_t,4> l{}; for (int c = 0; c <= dim; ++c) l[c] = 1; return l; }());
+  std::int64_t total = 0;
+  for (int c = 0; c <= dim; ++c) total += gv.size(c);
+  CHECK(all.size() == total);
+  // two ranks: the default partitioner splits the longest direction (partitioning.hh:56-117)
+  BulkYaspGrid<dim> r0(L, s, std::bitset<dim>(), 1, 0, 2), r1(L, s, std::bitset<dim>(), 1, 1, 2);
+  CHECK(r0.torusDims()[0] == 2);
+  CHECK(r0.leafGridView().size(0, Interior_Partition) + r1.leafGridView().size(0, Interior_Partition) == cells);
+  CHECK(r0.leafGridView().size(0) == cells/2 + cells/s[0]);
+  threw = false;
+  try { BulkYaspGrid<dim> bad(L, s, std::bitset<dim>(), 3, 0, 4); } catch (const GridError&) { threw = true; }   // yaspgrid.hh:925-937
+  CHECK(threw);
+}
+
+template<int dim>
+void deviceChecks() {
+  std::array<double,dim> L; std::array<int,dim> s;
+  for (int i = 0; i < dim; ++i) { L[i] = 1.0 + 0.5*i; s[i] = 12 - 2*i; }
+  std::bitset<dim> periodic; periodic[0] = true;
+  BulkYaspGrid<dim> grid(L, s, periodic, 1);
+  auto gv = grid.leafGridView();
+  // index set: All_Partition visits indices 0,1,2,... (checkindexset.hh), interior cells are Interior, the periodic layer Overlap
+  auto el = gv.template elements<0>(All_Partition);
+  auto idx = el.index.toHost(); auto pt = el.partitionType.toHost(); auto vol = el.volume.toHost();
+  bool consecutive = true; std::int64_t nint = 0; double vsum = 0.0;
+  for (std::size_t i = 0; i < idx.size(); ++i) { consecutive = consecutive && idx[i] == i; if (pt[i] == InteriorEntity) { ++nint; vsum += vol[i]; } }
+  CHECK(consecutive);
+  CHECK(nint == gv.size(0, Interior_Partition));
+  double domain = 1.0; for (int i = 0; i < dim; ++i) domain *= L[i];
+  CHECK(std::abs(vsum - domain) <= 1e-13*domain);
+  // sub-indices: every vertex index of the view is hit by some cell (checkindexset.hh:140-200)
+  BulkMapper<dim> vm(gv, mcmgVertexLayout<dim>());
+  auto sub = vm.subIndex(dim).toHost();
+  std::set<std::uint32_t> seen(sub.begin(), sub.end());
+  CHECK(std::int64_t(seen.size()) == gv.size(dim) && *seen.rbegin() == std::uint32_t(gv.size(dim)-1));
+  // intersections: outside(outside(e)) == e across every interior face; boundary segments form a bijection
+  auto is = gv.intersections(All_Partition);
+  auto nb = is.neighbor.toHost(); auto bd = is.boundary.toHost(); auto out = is.outside.toHost(); auto bsi = is.boundarySegmentIndex.toHost();
+  const std::int64_t n = is.n;
+  bool symmetric = true; std::set<int> segments; std::int64_t nbnd = 0;
+  for (int k = 0; k < 2*dim; ++k)
+    for (std::int64_t e = 0; e < n; ++e) {
+      if (nb[k*n+e]) { const int o = out[k*n+e]; symmetric = symmetric && nb[(k^1)*n+o] && out[(k^1)*n+o] == e; }
+      if (bd[k*n+e]) { ++nbnd; segments.insert(bsi[k*n+e]); } else symmetric = symmetric && bsi[k*n+e] == -1;
+    }
+  CHECK(symmetric);
+  CHECK(std::int64_t(segments.size()) == grid.numBoundarySegments() && nbnd == grid.numBoundarySegments());
+  CHECK(segments.empty() || (*segments.begin() == 0 && *segments.rbegin() == int(grid.numBoundarySegments())-1));
+  // geometry at the cell centre: integrationElement == volume, J^-T diagonal = 1/h
+  std::vector<std::array<double,dim>> qp(1); qp[0].fill(0.5);
+  auto geo = gv.geometry(qp, All_Partition);
+  auto detJ = geo.integrationElement.toHost(); auto glob = geo.global.toHost(); auto cen = el.center.toHost();
+  bool same = true;
+  for (std::int64_t e = 0; e < n; ++e) { same = same && detJ[e] == vol[e]; for (int d = 0; d < dim; ++d) same = same && glob[d*n+e] == cen[d*n+e]; }
+  CHECK(same);
+  // communicate: the periodic overlap cells receive the values of their interior images (InteriorBorder_All, forward, set)
+  BulkMapper<dim> em(gv, mcmgElementLayout<dim>());
+  std::vector<double> h(n);
+  for (std::int64_t e = 0; e < n; ++e) h[e] = (pt[e] == InteriorEntity) ? cen[e] : -1.0;     // x coordinate of the centre
+  DeviceArray<double> c(n); c.fromHost(h);
+  BulkDataHandle<dim> dh{em, {c.data()}, {1}, CommOp::set};
+  gv.communicate(dh, InteriorBorder_All_Interface, ForwardCommunication);
+  auto after = c.toHost();
+  bool filled = true;
+  for (std::int64_t e = 0; e < n; ++e) filled = filled && std::abs(after[e] - cen[e]) <= 1e-14;   // wrapped centres equal the images' (up to rounding of i*h + L)
+  CHECK(filled);
+  // FV functor: three steps conserve mass while the shell is away from the boundary (b = 0), 0 <= c <= 1
+  if (dim == 3) {
+    std::array<double,dim> L1; L1.fill(1.0); std::array<int,dim> s1; s1.fill(48);
+    BulkYaspGrid<dim> g(L1, s1, std::bitset<dim>(), 1);
+    FiniteVolume<dim> fv(g, 0, 0, {1.0, 1.0, 1.0, 0.0, 0.5, 0.5, 0.5, 0.1, 0.25});
+    const std::int64_t m = g.leafGridView().size(0);
+    DeviceArray<double> a(m), b(m);
+    fv.initial(a.data());
+    auto h0 = a.toHost();
+    for (int k = 0; k < 3; ++k) { fv.step(a.data(), b.data()); std::swap(a, b); }
+    auto h1 = a.toHost();
+    const double m0 = std::accumulate(h0.begin(), h0.end(), 0.0), m1 = std::accumulate(h1.begin(), h1.end(), 0.0);
+    CHECK(m0 > 0 && std::abs(m1 - m0) <= 1e-12*m0);
+    bool bounded = true; for (double x : h1) bounded = bounded && x >= 0.0 && x <= 1.0;
+    CHECK(bounded);
+    CHECK(fv.lastDt() == 0.99*(1.0/(3.0*48)));
+  }
+}
+
+int main(int argc, char** argv) {
+  const bool device = argc > 1 && !std::strcmp(argv[1], "--device");
+  try {
+    hostChecks<2>(); hostChecks<3>();
+    if (device) { deviceChecks<2>(); deviceChecks<3>(); }
+  } catch (const std::exception& e) { std::printf("exception: %s\n", e.what()); return 2; }
+  std::printf("bulk_gridview_test (%s): %s\n", device ? "host+device" : "host", failures ? "FAILED" : "OK");
+  return failures ? 1 : 0;
+}
