@@ -5,7 +5,7 @@
  * libraries, and only as the checker or the timed CPU baseline.
  *
  * Two libraries export exactly these symbols:
- *   oracle/_ref/liboracle_ref.so   the reference's own dune/grid/yaspgrid.hh, dune/grid/yaspgrid/*.hh and
+ *   oracle/_ref/liboracle_ref.so   the reference's own dune/grid/yaspgrid.hh, dune/grid/yaspgrid/ headers and
  *                                  dune/grid/common/mcmgmapper.hh compiled UNMODIFIED from /root/reference against
  *                                  the stand-in headers in oracle/ref/shim (dune-common / dune-geometry / MPI are not
  *                                  available here); ranks are threads (oracle/ref/shim/mpi.h).

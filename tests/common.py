@@ -11,8 +11,14 @@ def oracle_kinds():
 
 
 def best_oracle():
+    """the reference's own headers when built (oracle/_ref), else the self-contained restatement; ORACLE_KIND=ref|port forces one"""
+    import os
     kinds = oracle_kinds()
     assert kinds, "no CPU oracle built: run `make -C oracle` (python -c 'import __graft_entry__ as g; g.build()')"
+    want = os.environ.get("ORACLE_KIND")
+    if want:
+        assert want in kinds, f"oracle '{want}' is not built"
+        return orc.load(want)
     return orc.load(kinds[0])
 
 
