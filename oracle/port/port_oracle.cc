@@ -181,13 +181,13 @@ struct Box {
   Box intersection(int d, const Box& r) const {                                                   // :271-289
     Box e;
     if (empty(d) || r.empty(d)) return e;
-    for (int i = 0; i < d; ++i) { e.origin[i] = std::max(origin[i], r.origin[i]); e.size[i] = std::min(max(i), r.max(i)) - e.origin[i] + 1; if (e.size[i] < 0) e.size[i] = 0; }
+    for (int i = 0; i < d; ++i) { e.origin[i] = std::max(origin[i], r.origin[i]); e.size[i] = std::min(max(i), r.max(i)) - e.origin[i] + 1; }   // may be negative: not "empty" upstream either (overlap 0)
     return e;
   }
 };
 // lexicographic walk over a box, axis 0 fastest (YGridComponent::Iterator, :317-400)
 template<class F> void forEachCoord(int d, const Box& b, F&& f) {
-  if (b.empty(d)) return;
+  for (int i = 0; i < d; ++i) if (b.size[i] <= 0) return;          // negative sizes (overlap-0 partitions) are undefined upstream: walk nothing
   I3 c = b.origin;
   for (;;) {
     f(c);
