@@ -252,12 +252,13 @@ int plan_unpack(CommPlan& plan, int op, double* const* d_arrays, const int32_t* 
 
 // the exchange itself; `arrays` are device pointers
 int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays,
-             dgb_comm* comm, cudaStream_t stream) {
+             dgb_comm* comm, cudaStream_t stream, bool packed) {
   bool remote = false;
   for (auto& s : plan.sendSeg) if (s.peer != myrank) remote = true;
   for (auto& s : plan.recvSeg) if (s.peer != myrank) remote = true;
   if (remote && !comm) return fail(DGB_EARG, "this exchange has remote partners: a dgb_comm is required");
-  if (int rc = plan_pack(plan, d_arrays, item_sizes, narrays, stream)) return rc;
+  if (packed) { if (int rc = plan.upload()) return rc; }
+  else if (int rc = plan_pack(plan, d_arrays, item_sizes, narrays, stream)) return rc;
   if (plan.trace[0]) cudaEventRecord(plan.trace[0], stream);
   int64_t bytes = 0;
   if (remote) {

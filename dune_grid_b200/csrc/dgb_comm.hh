@@ -36,8 +36,9 @@ struct CommPlan {
 };
 int get_plan(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir, const int32_t* item_sizes, int narrays,
              std::shared_ptr<CommPlan>& out);
+// packed = true: the send buffer has already been filled (in-kernel pack of the FV shell kernel)
 int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays,
-             dgb_comm* comm, cudaStream_t stream);
+             dgb_comm* comm, cudaStream_t stream, bool packed = false);
 int nccl_allreduce(double* d, int op /*0 min, 1 max*/, dgb_comm* comm, cudaStream_t stream);
 }
 #endif

@@ -146,6 +146,85 @@ __global__ void __launch_bounds__(FBX*FBY) k_fv_step(const __grid_constant__ dgb
   }
 }
 
+// ---- exchange shell: all slabs in one launch, with the pack of communicate() fused in -------------------------
+// The shell slabs (<= 6 thin boxes of interior cells that some neighbour receives) are updated by one launch:
+// blockIdx.y selects the slab, threads run along the slab's longest contiguous axis (y for the thin-x slabs, whose
+// cells are one per row anyway). Each new value is stored to c_new AND to every send box of the exchange plan that
+// contains the cell ("in-kernel pack": the separate gather kernel, its strided re-read of c_new and one stream
+// dependency disappear). Same per-cell arithmetic as k_fv_step.
+struct FvShell { FvRegion slab[6]; int perm[6]; int n; const PlanBox* boxes; int nBoxes; double* sendBuf; };
+
+template<int MODE>
+__global__ void __launch_bounds__(256) k_fv_shell(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a, const __grid_constant__ FvShell sh) {
+  const FvRegion& r = sh.slab[blockIdx.y];
+  const int perm = sh.perm[blockIdx.y];
+  const long long cells = (long long)r.size[0]*r.size[1]*r.size[2];
+  const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+  const long long stride[3] = { 1, of.size[0], (long long)of.size[0]*of.size[1] };
+  const double dt = 0.99*(1.0/(*a.slotIn));
+  double sum_max = 0.0;
+  for (long long t = (long long)blockIdx.x*256 + threadIdx.x; t < cells; t += (long long)gridDim.x*256) {
+    int i[3];
+    if (perm) { i[1] = int(t % r.size[1]); const long long q = t / r.size[1]; i[2] = int(q % r.size[2]); i[0] = int(q / r.size[2]); }
+    else { i[0] = int(t % r.size[0]); const long long q = t / r.size[0]; i[1] = int(q % r.size[1]); i[2] = int(q / r.size[1]); }
+    int coord[3]; long long idx = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { coord[k] = r.origin[k] + i[k]; idx += (coord[k]-of.origin[k])*stride[k]; }
+    double ll[3], ur[3], w[3], xc[3], rw[3], vol = 1.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (MODE == DGB_FV_SEPARABLE) {
+        const int tt = coord[k]-a.tab.first[k];
+        ll[k] = __ldg(a.tab.xv[k]+tt); ur[k] = __ldg(a.tab.xv[k]+tt+1); xc[k] = __ldg(a.tab.xc[k]+tt); rw[k] = __ldg(a.tab.rw[k]+tt);
+      } else {
+        ll[k] = vertex_coord(v, k, coord[k]); ur[k] = vertex_coord(v, k, coord[k]+1);
+        w[k] = ur[k]-ll[k]; vol *= w[k]; xc[k] = 0.5*(ll[k]+ur[k]);
+      }
+    }
+    const double ci = __ldg(a.c + idx);
+    double upd = 0.0, sum = 0.0;
+#pragma unroll
+    for (int dir = 0; dir < 3; ++dir) {
+      double area = 1.0;
+      if (MODE == DGB_FV_EXACT) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) if (k != dir) area *= w[k];
+      }
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        double fc[3], u[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) fc[k] = (k == dir) ? (side ? ur[k] : ll[k]) : xc[k];
+        fv_velocity<3>(a.problem, fc, u);
+        const double un = side ? u[dir] : -u[dir];
+        const double factor = (MODE == DGB_FV_EXACT) ? (un*area)/vol : un*rw[dir];
+        if (factor >= 0.0) { sum += factor; upd -= ci*factor; }
+        else if (face_neighbor(v, coord, dir, side)) upd -= __ldg(a.c + idx + (side ? stride[dir] : -stride[dir]))*factor;
+        else if (face_boundary(v, coord, dir, side)) upd -= fv_boundary(a.problem, fc)*factor;
+      }
+    }
+    sum_max = fmax(sum_max, sum);
+    const double cn = ci + dt*upd;
+    a.cnew[idx] = cn;
+    for (int b = 0; b < sh.nBoxes; ++b) {                            // in-kernel pack (codim 0, one double per cell)
+      const PlanBox& pb = sh.boxes[b];
+      const int j0 = coord[0]-pb.origin[0], j1 = coord[1]-pb.origin[1], j2 = coord[2]-pb.origin[2];
+      if (j0 >= 0 && j0 < pb.size[0] && j1 >= 0 && j1 < pb.size[1] && j2 >= 0 && j2 < pb.size[2])
+        sh.sendBuf[pb.buf_offset + ((long long)j2*pb.size[1] + j1)*pb.size[0] + j0] = cn;
+    }
+  }
+  if (a.dtOut && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.dtOut = dt;
+  for (int off = 16; off > 0; off >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, off));
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sum_max;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0;
+    for (int k = 0; k < 8; ++k) m = fmax(m, part[k]);
+    if (m > 0.0) atomic_max_nonneg(a.slotOut, m);
+  }
+}
+
 // ---- 3-D production kernel: z-marching with a register prefetch queue ---------------------------------------
 // A CTA owns a (BX x BY) column tile of the region and marches over ZC consecutive z-planes. Everything that
 // does not depend on z (x/y coordinates, reciprocal widths, x/y neighbour and boundary flags, velocity terms that
@@ -670,21 +749,23 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
   return DGB_OK;
 }
 
-// the per-cell kernel on an arbitrary 3-D region (exchange shell slabs); perm 1 = thin in x
-static int launch_cells(dgb_fv* fv, const FvArgs& a, int perm, cudaStream_t stream) {
-  const dgb_view& v = fv->view;
-  if (a.region.size[0] <= 0 || a.region.size[1] <= 0 || a.region.size[2] <= 0) return DGB_OK;
-  dim3 block(FBX, FBY, 1);
-  const bool exact = fv->mode == DGB_FV_EXACT;
-  if (perm) {
-    dim3 grid((a.region.size[1]+FBX-1)/FBX, (a.region.size[2]+FBY-1)/FBY, a.region.size[0]);
-    if (exact) k_fv_step<3, DGB_FV_EXACT, false, 1><<<grid, block, 0, stream>>>(v, a);
-    else k_fv_step<3, DGB_FV_SEPARABLE, false, 1><<<grid, block, 0, stream>>>(v, a);
-  } else {
-    dim3 grid((a.region.size[0]+FBX-1)/FBX, (a.region.size[1]+FBY-1)/FBY, a.region.size[2]);
-    if (exact) k_fv_step<3, DGB_FV_EXACT, false, 0><<<grid, block, 0, stream>>>(v, a);
-    else k_fv_step<3, DGB_FV_SEPARABLE, false, 0><<<grid, block, 0, stream>>>(v, a);
+// all exchange-shell slabs in one launch; pack = true also fills the send buffer of the FV exchange plan
+static int launch_shell(dgb_fv* fv, const FvArgs& a, bool pack, cudaStream_t stream) {
+  if (!fv->nShell) return DGB_OK;
+  FvShell sh{};
+  long long most = 0;
+  for (int k = 0; k < fv->nShell; ++k) {
+    sh.slab[k] = fv->shell[k]; sh.perm[k] = fv->shellPerm[k];
+    most = std::max(most, (long long)fv->shell[k].size[0]*fv->shell[k].size[1]*fv->shell[k].size[2]);
   }
+  sh.n = fv->nShell;
+  if (pack) {
+    if (int rc = fv->plan->upload()) return rc;
+    sh.boxes = fv->plan->dSendBoxes; sh.nBoxes = fv->plan->nSendBoxes; sh.sendBuf = fv->plan->dSendBuf;
+  }
+  dim3 grid((unsigned)std::min<long long>((most+255)/256, 4096), (unsigned)fv->nShell, 1);
+  if (fv->mode == DGB_FV_EXACT) k_fv_shell<DGB_FV_EXACT><<<grid, 256, 0, stream>>>(fv->view, a, sh);
+  else k_fv_shell<DGB_FV_SEPARABLE><<<grid, 256, 0, stream>>>(fv->view, a, sh);
   ++fv->launches;
   DGB_CUDA(cudaGetLastError());
   return DGB_OK;
@@ -856,10 +937,7 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
     if (trace && !fv->tr[0]) { for (int k = 0; k < 4; ++k) cudaEventCreate(&fv->tr[k]); for (int k = 0; k < 3; ++k) cudaEventCreate(&fv->plan->trace[k]); }
     if (n >= 2) DGB_CUDA(cudaStreamWaitEvent(stream, fv->evRed[n % 2], 0));           // slot n%4 was reduced during step n-1
     if (trace) cudaEventRecord(fv->tr[0], stream);
-    for (int k = 0; k < fv->nShell; ++k) {
-      FvArgs s = a; s.region = fv->shell[k];
-      if (int rc = launch_cells(fv, s, fv->shellPerm[k], stream)) return rc;
-    }
+    if (int rc = launch_shell(fv, a, true, stream)) return rc;
     DGB_CUDA(cudaEventRecord(fv->evShell, stream));
     if (trace) cudaEventRecord(fv->tr[1], stream);
     // the bulk is enqueued before the exchange: the host-side cost of the NCCL calls must not delay its start
@@ -873,7 +951,7 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
       double* arrays[1] = { d_c_out };
       const long long before = fv->plan->launches;
       static const bool skipx = getenv("DGB_FV_DEBUG_SKIP_EXCHANGE") != nullptr;     // developer timing experiment only
-      if (!skipx) if (int rc = run_plan(fv->grid, *fv->plan, fv->view.rank, DGB_OP_SET, arrays, items, 1, fv->comm, fv->sComm)) return rc;
+      if (!skipx) if (int rc = run_plan(fv->grid, *fv->plan, fv->view.rank, DGB_OP_SET, arrays, items, 1, fv->comm, fv->sComm, true)) return rc;
       fv->launches += fv->plan->launches - before;
     }
     DGB_CUDA(cudaEventRecord(fv->evDone, fv->sComm));
@@ -932,10 +1010,7 @@ int dgb_fv_step_local(dgb_fv* fv, const double* d_c_in, double* d_c_out, double*
   a.c = d_c_in; a.cnew = d_c_out;
   slot_args(fv, n, a);
   if (fv->split && getenv("DGB_FV_SPLIT_LOCAL")) {            // the shell / bulk decomposition of dgb_fv_step, without exchange
-    for (int k = 0; k < fv->nShell; ++k) {
-      FvArgs s = a; s.region = fv->shell[k];
-      if (int rc = launch_cells(fv, s, fv->shellPerm[k], stream)) return rc;
-    }
+    if (int rc = launch_shell(fv, a, false, stream)) return rc;
     FvArgs b = a; b.region = fv->bulk;
     if (int rc = launch_step<false>(fv, b, stream)) return rc;
   } else if (int rc = launch_step<false>(fv, a, stream)) return rc;
