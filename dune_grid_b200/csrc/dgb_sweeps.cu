@@ -17,11 +17,15 @@ struct SweepGeom {                   // where this launch walks and where it wri
   long long n;                       // total entities of the sweep (array stride of component-major outputs)
 };
 
-__device__ __forceinline__ bool sweep_entity(const dgb_view& v, const SweepGeom& s, int* coord, long long& pos) {
+// a thread walks SW_ROWS consecutive rows (i1) of its column: 8x fewer, 8x longer-lived blocks than one entity per
+// thread, which matters for the 4-byte-per-entity outputs (mapper indices), where block scheduling was the cost
+// (ROWS = 8); kernels that write hundreds of bytes per entity keep one entity per thread (ROWS = 1)
+template<int SW_ROWS>
+__device__ __forceinline__ bool sweep_entity(const dgb_view& v, const SweepGeom& s, int row, int* coord, long long& pos) {
   const dgb_box& b = v.comp[s.comp].box[s.kind];
   const int i0 = blockIdx.x*blockDim.x + threadIdx.x;
-  const int i1 = blockIdx.y, i2 = blockIdx.z;
-  if (i0 >= b.size[0]) return false;
+  const int i1 = blockIdx.y*SW_ROWS + row, i2 = blockIdx.z;
+  if (i0 >= b.size[0] || i1 >= b.size[1]) return false;
   coord[0] = b.origin[0] + i0;
   coord[1] = b.origin[1] + i1;
   coord[2] = (v.dim > 2) ? b.origin[2] + i2 : 0;
@@ -29,9 +33,9 @@ __device__ __forceinline__ bool sweep_entity(const dgb_view& v, const SweepGeom&
   return true;
 }
 
-static dim3 sweep_grid(const dgb_view& v, int comp, int kind) {
+static dim3 sweep_grid(const dgb_view& v, int comp, int kind, int SW_ROWS) {
   const dgb_box& b = v.comp[comp].box[kind];
-  return dim3((b.size[0]+BX-1)/BX, b.size[1], v.dim > 2 ? b.size[2] : 1);
+  return dim3((b.size[0]+BX-1)/BX, (b.size[1]+SW_ROWS-1)/SW_ROWS, v.dim > 2 ? b.size[2] : 1);
 }
 static bool sweep_empty(const dgb_view& v, int comp, int kind) {
   const dgb_box& b = v.comp[comp].box[kind];
@@ -43,8 +47,9 @@ static bool sweep_empty(const dgb_view& v, int comp, int kind) {
 struct EntityOut { uint32_t* index; uint8_t* ptype; int32_t* coord; double *lower, *upper, *center, *volume; uint32_t block, offset; };
 
 __global__ void __launch_bounds__(BX) k_entities(const __grid_constant__ dgb_view v, const SweepGeom s, const EntityOut o) {
+  for (int row = 0; row < 8; ++row) {
   int coord[3]; long long pos;
-  if (!sweep_entity(v, s, coord, pos)) return;
+  if (!sweep_entity<8>(v, s, row, coord, pos)) continue;
   const dgb_component& c = v.comp[s.comp];
   if (o.index) o.index[pos] = entity_index(v, c, s.kind, coord)*o.block + o.offset;
   if (o.ptype) o.ptype[pos] = partition_type(v, c, coord);
@@ -64,13 +69,15 @@ __global__ void __launch_bounds__(BX) k_entities(const __grid_constant__ dgb_vie
     }
     if (o.volume) o.volume[pos] = vol;
   }
+  }
 }
 
 // ---- K2: sub-entity indices of cells -------------------------------------------------------------------
 __global__ void __launch_bounds__(BX) k_subindex(const __grid_constant__ dgb_view v, const SweepGeom s, const SubTable t,
                                                  int cc, uint32_t block, uint32_t offset, uint32_t* out) {
+  for (int row = 0; row < 8; ++row) {
   int coord[3]; long long pos;
-  if (!sweep_entity(v, s, coord, pos)) return;
+  if (!sweep_entity<8>(v, s, row, coord, pos)) continue;
   for (int i = 0; i < t.n; ++i) {
     // yaspgridentity.hh:764-776: coord += move, component = shiftmapping[shift], index in the overlapfront numbering
     int sc[3];
@@ -78,14 +85,16 @@ __global__ void __launch_bounds__(BX) k_subindex(const __grid_constant__ dgb_vie
     const dgb_component& c = v.comp[v.comp_begin[cc] + v.shiftmap[t.shift[i]]];
     out[(long long)i*s.n + pos] = entity_index(v, c, DGB_BOX_OVERLAPFRONT, sc)*block + offset;
   }
+  }
 }
 
 // ---- K3: intersections -------------------------------------------------------------------------------
 struct FaceOut { uint8_t *neighbor, *boundary; int32_t *outside, *bsi; double *center, *volume; };
 
 __global__ void __launch_bounds__(BX) k_intersections(const __grid_constant__ dgb_view v, const SweepGeom s, const FaceOut o) {
+  for (int row = 0; row < 1; ++row) {
   int coord[3]; long long pos;
-  if (!sweep_entity(v, s, coord, pos)) return;
+  if (!sweep_entity<1>(v, s, row, coord, pos)) continue;
   const dgb_component& c = v.comp[0];
   const dgb_box& of = c.box[DGB_BOX_OVERLAPFRONT];
   const int inside = int(entity_index(v, c, s.kind, coord));
@@ -122,6 +131,7 @@ __global__ void __launch_bounds__(BX) k_intersections(const __grid_constant__ dg
     }
     stride *= of.size[dir];
   }
+  }
 }
 
 // ---- K4: axis-aligned geometry at quadrature points ---------------------------------------------------
@@ -129,8 +139,9 @@ struct QuadPoints { int n; double x[27*3]; };
 struct GeoOut { double *global, *jit, *detJ; };
 
 __global__ void __launch_bounds__(BX) k_geometry(const __grid_constant__ dgb_view v, const SweepGeom s, const QuadPoints q, const GeoOut o) {
+  for (int row = 0; row < 1; ++row) {
   int coord[3]; long long pos;
-  if (!sweep_entity(v, s, coord, pos)) return;
+  if (!sweep_entity<1>(v, s, row, coord, pos)) continue;
   const int dim = v.dim;
   double ll[3], w[3], vol = 1.0;
   for (int i = 0; i < dim; ++i) {
@@ -146,6 +157,7 @@ __global__ void __launch_bounds__(BX) k_geometry(const __grid_constant__ dgb_vie
     }
     if (o.detJ) o.detJ[(long long)p*s.n + pos] = vol;
   }
+  }
 }
 
 // ---- K8: GeometryGrid (multilinear geometry over deformed corners) ------------------------------------
@@ -154,8 +166,9 @@ struct GeoGridOut { double *corners, *global, *jt, *jit, *detJ; };
 template<int DIM>
 __global__ void __launch_bounds__(BX) k_geogrid(const __grid_constant__ dgb_view v, const SweepGeom s, const QuadPoints q,
                                                 const Deformation def, const GeoGridOut o) {
+  for (int row = 0; row < 1; ++row) {
   int coord[3]; long long pos;
-  if (!sweep_entity(v, s, coord, pos)) return;
+  if (!sweep_entity<1>(v, s, row, coord, pos)) continue;
   constexpr int NC = 1 << DIM;
   double ll[DIM], ur[DIM];
   for (int i = 0; i < DIM; ++i) {
@@ -199,15 +212,17 @@ __global__ void __launch_bounds__(BX) k_geogrid(const __grid_constant__ dgb_view
     }
     if (o.detJ) o.detJ[(long long)p*s.n + pos] = fabs(det);
   }
+  }
 }
 
 // reduction variant: sum_q w_q |det J(x_q)| over all cells; block partial via warp shuffles, one atomicAdd per block
 template<int DIM>
 __global__ void __launch_bounds__(BX) k_geogrid_volume(const __grid_constant__ dgb_view v, const SweepGeom s, const QuadPoints q,
                                                        const QuadPoints wts, const Deformation def, double* sum) {
-  int coord[3]; long long pos;
   double acc = 0.0;
-  if (sweep_entity(v, s, coord, pos)) {
+  for (int row = 0; row < 8; ++row) {
+  int coord[3]; long long pos;
+  if (sweep_entity<8>(v, s, row, coord, pos)) {
     constexpr int NC = 1 << DIM;
     double ll[DIM], ur[DIM], c[NC][DIM];
     for (int i = 0; i < DIM; ++i) {
@@ -230,6 +245,7 @@ __global__ void __launch_bounds__(BX) k_geogrid_volume(const __grid_constant__ d
       acc += wts.x[p]*fabs(ml_det<DIM>(J));
     }
   }
+  }
   for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
   __shared__ double part[BX/32];
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
@@ -243,7 +259,7 @@ __global__ void __launch_bounds__(BX) k_geogrid_volume(const __grid_constant__ d
 
 // ---- host drivers ------------------------------------------------------------------------------------
 template<class Launch>
-static int for_each_component(const dgb_view& v, int codim, int pitype, Launch&& launch) {
+static int for_each_component(const dgb_view& v, int codim, int pitype, int rows, Launch&& launch) {
   if (codim < 0 || codim > v.dim) return fail(DGB_EARG, "bad codim");
   const int kind = box_kind_of(pitype);
   if (kind == -2) return fail(DGB_EGRID, "YaspLevelIterator with this codim or partition type not implemented");
@@ -252,7 +268,7 @@ static int for_each_component(const dgb_view& v, int codim, int pitype, Launch&&
   SweepGeom s; s.kind = kind; s.base = 0; s.n = partition_size(v, codim, pitype);
   for (int j = v.comp_begin[codim]; j < v.comp_begin[codim+1]; ++j) {
     s.comp = j;
-    if (!sweep_empty(v, j, kind)) launch(s, sweep_grid(v, j, kind));
+    if (!sweep_empty(v, j, kind)) launch(s, sweep_grid(v, j, kind, rows));
     long long t = 1; for (int i = 0; i < v.dim; ++i) t *= v.comp[j].box[kind].size[i];
     s.base += t;
   }
@@ -283,7 +299,7 @@ int dgb_mapper_index(const dgb_view* v, const dgb_mapper* m, int codim, int pity
   if (codim < 0 || codim > v->dim) return fail(DGB_EARG, "bad codim");
   if (m->offset[codim] == DGB_INVALID_OFFSET) return fail(DGB_EARG, "codim not contained in the mapper layout");
   EntityOut o{}; o.index = d_out; o.block = m->block[codim]; o.offset = m->offset[codim];
-  return for_each_component(*v, codim, pitype, [&](const SweepGeom& s, dim3 grid) {
+  return for_each_component(*v, codim, pitype, 8, [&](const SweepGeom& s, dim3 grid) {
     k_entities<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o);
   });
 }
@@ -294,7 +310,7 @@ int dgb_mapper_subindex(const dgb_view* v, const dgb_mapper* m, int cc, int pity
   SubTable t; t.n = sub_entities(v->dim, cc);
   for (int i = 0; i < t.n; ++i) { t.shift[i] = (unsigned char)sub_shift(v->dim, i, cc); t.move[i] = (unsigned char)sub_move(v->dim, i, cc); }
   const uint32_t block = m->block[cc], offset = m->offset[cc];
-  return for_each_component(*v, 0, pitype, [&](const SweepGeom& s, dim3 grid) {
+  return for_each_component(*v, 0, pitype, 8, [&](const SweepGeom& s, dim3 grid) {
     k_subindex<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, t, cc, block, offset, d_out);
   });
 }
@@ -303,7 +319,7 @@ int dgb_elements_materialize(const dgb_view* v, int codim, int pitype, uint32_t*
                              double* d_lower, double* d_upper, double* d_center, double* d_volume, void* stream) {
   if ((d_lower || d_upper || d_center || d_volume)) if (int rc = check_tensor(*v)) return rc;
   EntityOut o{d_index, d_ptype, d_coord, d_lower, d_upper, d_center, d_volume, 1u, 0u};
-  return for_each_component(*v, codim, pitype, [&](const SweepGeom& s, dim3 grid) {
+  return for_each_component(*v, codim, pitype, 8, [&](const SweepGeom& s, dim3 grid) {
     k_entities<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o);
   });
 }
@@ -312,7 +328,7 @@ int dgb_intersections_materialize(const dgb_view* v, int pitype, uint8_t* d_neig
                                   int32_t* d_bsi, double* d_center, double* d_volume, void* stream) {
   if (d_center || d_volume) if (int rc = check_tensor(*v)) return rc;
   FaceOut o{d_neighbor, d_boundary, d_outside, d_bsi, d_center, d_volume};
-  return for_each_component(*v, 0, pitype, [&](const SweepGeom& s, dim3 grid) {
+  return for_each_component(*v, 0, pitype, 1, [&](const SweepGeom& s, dim3 grid) {
     k_intersections<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o);
   });
 }
@@ -322,7 +338,7 @@ int dgb_geometry_eval(const dgb_view* v, int pitype, int nqp, const double* qp_h
   if (int rc = check_tensor(*v)) return rc;
   QuadPoints q; if (int rc = fill_qp(*v, nqp, qp_host, q)) return rc;
   GeoOut o{d_global, d_jit, d_detJ};
-  return for_each_component(*v, 0, pitype, [&](const SweepGeom& s, dim3 grid) {
+  return for_each_component(*v, 0, pitype, 1, [&](const SweepGeom& s, dim3 grid) {
     k_geometry<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, q, o);
   });
 }
@@ -335,7 +351,7 @@ int dgb_geogrid_eval(const dgb_view* v, int pitype, int deformation, const doubl
   for (int i = 0; i < 4; ++i) def.p[i] = (params_host && i < nparams) ? params_host[i] : 0.0;
   if (deformation < 0 || deformation > 1) return fail(DGB_EARG, "unknown deformation id");
   GeoGridOut o{d_corners, d_global, d_jt, d_jit, d_detJ};
-  return for_each_component(*v, 0, pitype, [&](const SweepGeom& s, dim3 grid) {
+  return for_each_component(*v, 0, pitype, 1, [&](const SweepGeom& s, dim3 grid) {
     if (v->dim == 3) k_geogrid<3><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, q, def, o);
     else k_geogrid<2><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, q, def, o);
   });
@@ -351,7 +367,7 @@ int dgb_geogrid_volume(const dgb_view* v, int pitype, int deformation, const dou
   if (deformation < 0 || deformation > 1) return fail(DGB_EARG, "unknown deformation id");
   if (int rc = require_device()) return rc;
   DGB_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), (cudaStream_t)stream));
-  return for_each_component(*v, 0, pitype, [&](const SweepGeom& s, dim3 grid) {
+  return for_each_component(*v, 0, pitype, 8, [&](const SweepGeom& s, dim3 grid) {
     if (v->dim == 3) k_geogrid_volume<3><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, q, w, def, d_sum);
     else k_geogrid_volume<2><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, q, w, def, d_sum);
   });
