@@ -658,7 +658,7 @@ struct dgb_fv {
   dgb_comm* comm = nullptr;
   int level = 0, mode = 0;
   int zchunk = 0;                // planes marched by one CTA of the 3-D kernel; 0 = auto (DGB_FV_ZCHUNK overrides)
-  int variant = 0;               // tuning variant of the 3-D kernel (DGB_FV_VARIANT overrides), see march_variants
+  int variant = -1;              // tuning variant of the 3-D kernel; -1 = automatic (DGB_FV_VARIANT overrides)
   std::unique_ptr<dgb::FvZTable> ztab;   // reciprocal z widths for the kernel parameter space (ring kernel)
   bool zparam = false;
   dgb_view view;
@@ -690,10 +690,11 @@ struct dgb_fv {
 namespace dgb {
 
 // planes per CTA: long columns amortise the ring prologue; short ones keep >= ~2 waves of 32x8 tiles on 148 SMs
-static int auto_zchunk(const int* size) {
-  const long long tiles = (long long)((size[0]+31)/32)*((size[1]+7)/8);
-  int zc = 128;
-  while (zc > 16 && tiles*((size[2]+zc-1)/zc) < 2*148*4) zc /= 2;
+static int auto_zchunk(const int* size, int bx, int by) {
+  const long long tiles = (long long)((size[0]+bx-1)/bx)*((size[1]+by-1)/by);
+  const int resident = 148*1024/(bx*by);                       // CTAs the ring kernel keeps on the chip
+  int zc = bx >= 128 ? 256 : 128;
+  while (zc > 16 && tiles*((size[2]+zc-1)/zc) < 2*resident) zc /= 2;
   return zc;
 }
 
@@ -704,7 +705,10 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
   dim3 grid((a.region.size[0]+FBX-1)/FBX, (a.region.size[1]+FBY-1)/FBY, v.dim > 2 ? a.region.size[2] : 1);
   if (a.region.size[0] <= 0 || a.region.size[1] <= 0 || (v.dim > 2 && a.region.size[2] <= 0)) return DGB_OK;
   if (v.dim == 3) {
-    const int zc = fv->zchunk > 0 ? fv->zchunk : auto_zchunk(a.region.size);
+    // tile choice (measured, tools/fv_sweep.py): 128x4 columns for wide regions, 32x8 otherwise
+    const int variant = fv->variant >= 0 ? fv->variant : (a.region.size[0] >= 256 ? 3 : 0);
+    const bool wide = variant == 3;
+    const int zc = fv->zchunk > 0 ? fv->zchunk : auto_zchunk(a.region.size, wide ? 128 : 32, wide ? 4 : 8);
     const bool exact = fv->mode == DGB_FV_EXACT;
     const int pb = fv->problem.id == 1 ? 1 : 0;
 #define DGB_MARCH(MODE_, PROB_, PF_, BX_, BY_)                                                                       \
@@ -726,16 +730,16 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
       else { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, false> : k_fv_ring<0, D_, BX_, BY_, MINB_, false>;     \
              DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));             \
              kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); } }
-      switch (fv->variant) {                  // tuning variants: ring depth, tile, occupancy target (tools/fv_sweep.py)
+      switch (variant) {                      // tuning variants: ring depth, tile, occupancy target (tools/fv_sweep.py)
         default:
-        case 0: DGB_RING(8, 32, 8, 4) break;                               // production choice
+        case 0: DGB_RING(8, 32, 8, 4) break;                               // production choice, narrow regions
         case 1: DGB_RING(6, 32, 8, 4) break;
         case 2: DGB_RING(6, 64, 4, 4) break;
-        case 3: DGB_RING(6, 128, 4, 2) break;
+        case 3: DGB_RING(6, 128, 4, 2) break;                              // production choice, wide regions
         case 4: DGB_RING(6, 32, 16, 2) break;
         case 5: DGB_RING(4, 64, 8, 2) break;
         case 6: DGB_RING(12, 32, 8, 4) break;
-        case 99: DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4) break;          // the general kernel, for comparison
+        case 99: if (pb) DGB_MARCH(DGB_FV_SEPARABLE, 1, 4, 128, 4) else DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4) break;   // the general kernel, for comparison
       }
 #undef DGB_RING
     }
@@ -930,22 +934,23 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
   a.c = d_c_in; a.cnew = d_c_out;
   slot_args(fv, n, a);
   if (fv->split && (fv->plan->nSendBoxes || fv->plan->nRecvBoxes)) {
-    // overlapped form. Caller's stream: shell slabs, bulk. Exchange stream (high priority; every NCCL call of the
-    // step): [after the shell] pack, NCCL send/recv, unpack; [after the bulk] all-reduce of the CFL slot, which
+    // overlapped form. Caller's stream: bulk. Exchange stream (high priority; every NCCL call of the step): shell
+    // slabs with in-kernel pack, NCCL send/recv, unpack; [after the bulk] all-reduce of the CFL slot, which
     // step n+2 reads - the caller's stream waits for it two steps later, and for the exchange at the end of this step.
     const bool trace = fv->traceLeft > 0;
     if (trace && !fv->tr[0]) { for (int k = 0; k < 4; ++k) cudaEventCreate(&fv->tr[k]); for (int k = 0; k < 3; ++k) cudaEventCreate(&fv->plan->trace[k]); }
     if (n >= 2) DGB_CUDA(cudaStreamWaitEvent(stream, fv->evRed[n % 2], 0));           // slot n%4 was reduced during step n-1
     if (trace) cudaEventRecord(fv->tr[0], stream);
-    if (int rc = launch_shell(fv, a, true, stream)) return rc;
-    DGB_CUDA(cudaEventRecord(fv->evShell, stream));
-    if (trace) cudaEventRecord(fv->tr[1], stream);
-    // the bulk is enqueued before the exchange: the host-side cost of the NCCL calls must not delay its start
+    // the shell runs on the exchange stream, concurrently with the bulk: its strided, latency-bound accesses hide behind
+    // the streaming bulk kernel, and the stream's priority schedules its CTAs ahead of the bulk's
+    DGB_CUDA(cudaEventRecord(fv->evShell, stream));                                    // c_in is ready, slot n%4 is reduced
+    DGB_CUDA(cudaStreamWaitEvent(fv->sComm, fv->evShell, 0));
+    if (int rc = launch_shell(fv, a, true, fv->sComm)) return rc;
+    if (trace) cudaEventRecord(fv->tr[1], fv->sComm);
     FvArgs b = a; b.region = fv->bulk;
     if (int rc = launch_step<false>(fv, b, stream)) return rc;
     DGB_CUDA(cudaEventRecord(fv->evBulk, stream));
     if (trace) cudaEventRecord(fv->tr[2], stream);
-    DGB_CUDA(cudaStreamWaitEvent(fv->sComm, fv->evShell, 0));
     {
       const int32_t items[1] = {1};
       double* arrays[1] = { d_c_out };
@@ -1054,7 +1059,7 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
   // Pipelined form (one rank, no overlap cells to refresh, 3-D): the field crosses PCIe in z-slabs; slab i is updated
   // as soon as slab i+1 (whose first plane it reads) has arrived, and its result leaves while later slabs are still
   // coming in - the two copy directions run concurrently on their own streams around the compute stream.
-  const int nslab = 16;
+  static const int nslab = [] { const char* e = getenv("DGB_FV_HOST_SLABS"); const int v = e ? atoi(e) : 32; return v >= 2 && v <= 256 ? v : 32; }();
   const bool pipelined = v.dim == 3 && v.nranks == 1 && !fv->plan->nSendBoxes && !fv->plan->nRecvBoxes
                          && of.size[2] == in.size[2] && of.size[2] >= 4*nslab && !getenv("DGB_FV_HOST_SERIAL");
   if (!pipelined) {
