@@ -10,6 +10,7 @@
 // to the own rank (periodic wrap on a 1-wide torus direction, torus.hh:395-403) are copied device-to-device.
 #include <dlfcn.h>
 #include <cstdlib>
+#include <cstring>
 #include <nccl.h>
 #include <algorithm>
 #include <sstream>
@@ -28,6 +29,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -39,7 +41,7 @@ struct NcclApi {
     if (!lib) { error = std::string("cannot load libnccl: ") + dlerror(); return false; }
 #define DGB_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(lib, name)); if (!field) { error = std::string("libnccl lacks ") + name; lib = nullptr; return false; }
     DGB_SYM(GetUniqueId, "ncclGetUniqueId") DGB_SYM(CommInitRank, "ncclCommInitRank") DGB_SYM(CommDestroy, "ncclCommDestroy")
-    DGB_SYM(Send, "ncclSend") DGB_SYM(Recv, "ncclRecv") DGB_SYM(AllReduce, "ncclAllReduce")
+    DGB_SYM(Send, "ncclSend") DGB_SYM(Recv, "ncclRecv") DGB_SYM(AllReduce, "ncclAllReduce") DGB_SYM(AllGather, "ncclAllGather")
     DGB_SYM(GroupStart, "ncclGroupStart") DGB_SYM(GroupEnd, "ncclGroupEnd") DGB_SYM(GetErrorString, "ncclGetErrorString")
 #undef DGB_SYM
     return true;
@@ -190,6 +192,10 @@ int CommPlan::upload() {
   return DGB_OK;
 }
 CommPlan::~CommPlan() {
+  for (void* p : ipcOpened) cudaIpcCloseMemHandle(p);
+  for (int k = 0; k < 2; ++k) if (dRecvBuf2[k]) cudaFree(dRecvBuf2[k]);
+  for (int k = 0; k < 2; ++k) if (dDst[k]) cudaFree(dDst[k]);
+  if (dBarrier) cudaFree(dBarrier);
   if (dSendBoxes) cudaFree(dSendBoxes);
   if (dRecvBoxes) cudaFree(dRecvBoxes);
   if (dSendBuf) cudaFree(dSendBuf);
@@ -278,6 +284,99 @@ int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_a
   const int rcu = plan_unpack(plan, op, d_arrays, item_sizes, narrays, stream);
   if (plan.trace[2]) cudaEventRecord(plan.trace[2], stream);
   return rcu;
+}
+
+// ---- direct exchange over peer-mapped memory ------------------------------------------------------------------------
+// what every rank publishes: the IPC handles of its two receive buffers and, per sender rank, the offset (in doubles) of
+// that sender's segment in the buffers (-1: no message from that rank)
+struct DirectInfo { cudaIpcMemHandle_t handle[2]; long long segOffset[64]; long long segCount[64]; int ok; int pad; };
+
+int plan_enable_direct(dgb_grid* g, CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream) {
+  if (plan.direct) return DGB_OK;                         // a cached plan shared by several FV objects: set up once
+  if (nranks > 64) return DGB_OK;
+  if (int rc = plan.upload()) return rc;
+  const bool multi = nranks > 1;
+  if (multi && !comm) return DGB_OK;
+  // own buffers, not the plan's dRecvBuf: a peer may already store step n+1 while this rank's dgb_communicate of the same
+  // (cached) plan is still using dRecvBuf
+  for (int k = 0; k < 2; ++k)
+    if (!plan.dRecvBuf2[k] && plan.recvTotal) DGB_CUDA(cudaMalloc(&plan.dRecvBuf2[k], plan.recvTotal*sizeof(double)));
+  if (!plan.dBarrier) { DGB_CUDA(cudaMalloc(&plan.dBarrier, sizeof(double))); DGB_CUDA(cudaMemset(plan.dBarrier, 0, sizeof(double))); }
+  std::vector<DirectInfo> all(nranks);
+  DirectInfo mine; std::memset(&mine, 0, sizeof(mine));
+  mine.ok = 1;
+  for (int r = 0; r < 64; ++r) { mine.segOffset[r] = -1; mine.segCount[r] = 0; }
+  for (auto& s : plan.recvSeg) { mine.segOffset[s.peer] = s.offset; mine.segCount[s.peer] = s.count; }
+  if (multi && plan.recvTotal)
+    for (int k = 0; k < 2; ++k)
+      if (cudaIpcGetMemHandle(&mine.handle[k], plan.dRecvBuf2[k]) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+  if (multi) {
+    DirectInfo* dAll = nullptr;
+    DGB_CUDA(cudaMalloc(&dAll, sizeof(DirectInfo)*nranks));
+    DGB_CUDA(cudaMemcpyAsync(dAll + myrank, &mine, sizeof(DirectInfo), cudaMemcpyHostToDevice, stream));
+    DGB_NCCL(g_nccl.AllGather(dAll + myrank, dAll, sizeof(DirectInfo), ncclChar, comm->comm, stream));
+    DGB_CUDA(cudaMemcpyAsync(all.data(), dAll, sizeof(DirectInfo)*nranks, cudaMemcpyDeviceToHost, stream));
+    DGB_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(dAll);
+  } else all[0] = mine;
+  bool ok = true;
+  for (int r = 0; r < nranks; ++r) ok = ok && all[r].ok;
+  // map the buffers of the ranks this rank sends to; every rank must reach the same verdict, so a failure is all-reduced
+  std::vector<double*> peerBuf[2]; peerBuf[0].assign(nranks, nullptr); peerBuf[1].assign(nranks, nullptr);
+  if (ok)
+    for (auto& s : plan.sendSeg) {
+      if (peerBuf[0][s.peer]) continue;
+      if (s.peer == myrank) { peerBuf[0][s.peer] = plan.dRecvBuf2[0]; peerBuf[1][s.peer] = plan.dRecvBuf2[1]; continue; }
+      for (int k = 0; k < 2 && ok; ++k) {
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[s.peer].handle[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        plan.ipcOpened.push_back(p);
+        peerBuf[k][s.peer] = static_cast<double*>(p);
+      }
+      if (ok && (all[s.peer].segOffset[myrank] < 0 || all[s.peer].segCount[myrank] != s.count)) ok = false;
+    }
+  if (multi) {                                           // agree on the verdict (min over ranks of 1/0)
+    double v = ok ? 1.0 : 0.0;
+    DGB_CUDA(cudaMemcpyAsync(plan.dBarrier, &v, sizeof(double), cudaMemcpyHostToDevice, stream));
+    DGB_NCCL(g_nccl.AllReduce(plan.dBarrier, plan.dBarrier, 1, ncclDouble, ncclMin, comm->comm, stream));
+    DGB_CUDA(cudaMemcpyAsync(&v, plan.dBarrier, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    DGB_CUDA(cudaStreamSynchronize(stream));
+    ok = v > 0.5;
+  }
+  if (!ok) return DGB_OK;
+  // destination of every send box: receiver's buffer + offset of my segment there + offset of the box inside my segment
+  std::vector<double*> dst[2]; dst[0].resize(plan.nSendBoxes); dst[1].resize(plan.nSendBoxes);
+  for (int b = 0; b < plan.nSendBoxes; ++b) {
+    const PlanBox& pb = plan.hostSend[b];
+    const CommPlan::Segment* seg = nullptr;
+    for (auto& s : plan.sendSeg) if (pb.buf_offset >= s.offset && pb.buf_offset < s.offset + s.count) seg = &s;
+    if (!seg) return fail(DGB_EGRID, "send box outside every segment");
+    for (int k = 0; k < 2; ++k) dst[k][b] = peerBuf[k][seg->peer] + all[seg->peer].segOffset[myrank] + (pb.buf_offset - seg->offset);
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (!plan.dDst[k] && plan.nSendBoxes) DGB_CUDA(cudaMalloc(&plan.dDst[k], plan.nSendBoxes*sizeof(double*)));
+    if (plan.nSendBoxes) DGB_CUDA(cudaMemcpy(plan.dDst[k], dst[k].data(), plan.nSendBoxes*sizeof(double*), cudaMemcpyHostToDevice));
+  }
+  (void)g;
+  plan.direct = true;
+  return DGB_OK;
+}
+
+int run_plan_direct(dgb_grid* g, CommPlan& plan, int parity, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays,
+                    dgb_comm* comm, cudaStream_t stream) {
+  if (plan.trace[0]) cudaEventRecord(plan.trace[0], stream);
+  // every rank's packing kernel precedes this all-reduce in its stream: when it completes here, all peers' stores into
+  // this rank's buffer have been performed
+  if (comm && comm->nranks > 1) DGB_NCCL(g_nccl.AllReduce(plan.dBarrier, plan.dBarrier, 1, ncclDouble, ncclMax, comm->comm, stream));
+  if (plan.trace[1]) cudaEventRecord(plan.trace[1], stream);
+  ArrayTable at; if (int rc = make_table(plan, d_arrays, item_sizes, narrays, at)) return rc;
+  if (plan.nRecvBoxes) launch_boxes(plan, at, op == DGB_OP_ADD ? 2 : 1, plan.hostRecv, plan.dRecvBoxes, plan.dRecvBuf2[parity], &plan.recvWaveEnd, stream);
+  DGB_CUDA(cudaGetLastError());
+  if (plan.trace[2]) cudaEventRecord(plan.trace[2], stream);
+  int64_t bytes = 0;
+  for (auto& s : plan.sendSeg) bytes += s.count*8;
+  g->lastBytesSent = bytes;
+  return DGB_OK;
 }
 
 int get_plan(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir, const int32_t* item_sizes, int narrays,

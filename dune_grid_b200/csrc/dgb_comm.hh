@@ -31,6 +31,14 @@ struct CommPlan {
   bool uploaded = false;
   long long launches = 0;
   cudaEvent_t trace[3] = {nullptr, nullptr, nullptr};     // optional timing events: after pack, after transfer, after unpack (DGB_FV_TRACE)
+  // direct mode (plan_enable_direct): the packing kernel stores straight into the RECEIVER's exchange buffer through
+  // peer-mapped memory (NVLink), double buffered by step parity; one small all-reduce orders "all senders have written"
+  // before the unpack. dDst[parity][box] = where send box `box` starts in its receiver's buffer.
+  bool direct = false;
+  double* dRecvBuf2[2] = {nullptr, nullptr};              // receive buffers of the direct mode, by step parity
+  double** dDst[2] = {nullptr, nullptr};                  // device arrays of nSendBoxes pointers
+  std::vector<void*> ipcOpened;
+  double* dBarrier = nullptr;
   int upload();
   ~CommPlan();
 };
@@ -40,5 +48,11 @@ int get_plan(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir, c
 int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays,
              dgb_comm* comm, cudaStream_t stream, bool packed = false);
 int nccl_allreduce(double* d, int op /*0 min, 1 max*/, dgb_comm* comm, cudaStream_t stream);
+// collective over all ranks: exchange IPC handles of the plans' receive buffers and the segment offsets, map the peers'
+// buffers. Returns DGB_OK with plan.direct = false when peer mapping is not available (the NCCL path stays in use).
+int plan_enable_direct(dgb_grid* g, CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream);
+// the part of a direct exchange after the packing kernel: barrier over the ranks, unpack from buffer `parity`
+int run_plan_direct(dgb_grid* g, CommPlan& plan, int parity, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays,
+                    dgb_comm* comm, cudaStream_t stream);
 }
 #endif

@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(FBX*FBY) k_fv_step(const __grid_constant__ dgb
 // cells are one per row anyway). Each new value is stored to c_new AND to every send box of the exchange plan that
 // contains the cell ("in-kernel pack": the separate gather kernel, its strided re-read of c_new and one stream
 // dependency disappear). Same per-cell arithmetic as k_fv_step.
-struct FvShell { FvRegion slab[6]; int perm[6]; int n; const PlanBox* boxes; int nBoxes; double* sendBuf; };
+struct FvShell { FvRegion slab[6]; int perm[6]; int n; const PlanBox* boxes; int nBoxes; double* sendBuf;
+                 double* const* dst; };   // dst != NULL: box b starts at dst[b] (the receiver's buffer, peer-mapped)
 
 template<int MODE>
 __global__ void __launch_bounds__(256) k_fv_shell(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a, const __grid_constant__ FvShell sh) {
@@ -210,9 +211,10 @@ __global__ void __launch_bounds__(256) k_fv_shell(const __grid_constant__ dgb_vi
       const PlanBox& pb = sh.boxes[b];
       const int j0 = coord[0]-pb.origin[0], j1 = coord[1]-pb.origin[1], j2 = coord[2]-pb.origin[2];
       if (j0 >= 0 && j0 < pb.size[0] && j1 >= 0 && j1 < pb.size[1] && j2 >= 0 && j2 < pb.size[2])
-        sh.sendBuf[pb.buf_offset + ((long long)j2*pb.size[1] + j1)*pb.size[0] + j0] = cn;
+        (sh.dst ? sh.dst[b] : sh.sendBuf + pb.buf_offset)[((long long)j2*pb.size[1] + j1)*pb.size[0] + j0] = cn;
     }
   }
+  if (sh.dst) __threadfence_system();          // peer stores are performed before the kernel is seen as complete
   if (a.dtOut && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.dtOut = dt;
   for (int off = 16; off > 0; off >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, off));
   __shared__ double part[8];
@@ -669,6 +671,7 @@ struct dgb_fv {
   double* dSlots = nullptr;        // 4 rotating max-sum slots + dt + the constants {0, boundary value}: see slot_args
   long long step = 0;
   bool bootstrapped = false;
+  bool directTried = false;      // plan_enable_direct has been attempted
   bool seedPending = false;      // dgb_fv_bootstrap_local: the reduced seed still has to be copied to the second slot
   int64_t launches = 0;
   std::shared_ptr<CommPlan> plan;
@@ -754,7 +757,7 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
 }
 
 // all exchange-shell slabs in one launch; pack = true also fills the send buffer of the FV exchange plan
-static int launch_shell(dgb_fv* fv, const FvArgs& a, bool pack, cudaStream_t stream) {
+static int launch_shell(dgb_fv* fv, const FvArgs& a, bool pack, cudaStream_t stream, int parity = -1) {
   if (!fv->nShell) return DGB_OK;
   FvShell sh{};
   long long most = 0;
@@ -766,6 +769,7 @@ static int launch_shell(dgb_fv* fv, const FvArgs& a, bool pack, cudaStream_t str
   if (pack) {
     if (int rc = fv->plan->upload()) return rc;
     sh.boxes = fv->plan->dSendBoxes; sh.nBoxes = fv->plan->nSendBoxes; sh.sendBuf = fv->plan->dSendBuf;
+    if (parity >= 0) sh.dst = fv->plan->dDst[parity];
   }
   dim3 grid((unsigned)std::min<long long>((most+255)/256, 4096), (unsigned)fv->nShell, 1);
   if (fv->mode == DGB_FV_EXACT) k_fv_shell<DGB_FV_EXACT><<<grid, 256, 0, stream>>>(fv->view, a, sh);
@@ -945,7 +949,16 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
     // the streaming bulk kernel, and the stream's priority schedules its CTAs ahead of the bulk's
     DGB_CUDA(cudaEventRecord(fv->evShell, stream));                                    // c_in is ready, slot n%4 is reduced
     DGB_CUDA(cudaStreamWaitEvent(fv->sComm, fv->evShell, 0));
-    if (int rc = launch_shell(fv, a, true, fv->sComm)) return rc;
+    // direct peer-store exchange: collective set-up on the first public step (DGB_FV_DIRECT=0 keeps NCCL send/recv)
+    if (!fv->directTried) {
+      fv->directTried = true;
+      const char* e = getenv("DGB_FV_DIRECT");
+      if (!(e && atoi(e) == 0) && (fv->view.nranks == 1 || fv->comm))
+        if (int rc = plan_enable_direct(fv->grid, *fv->plan, fv->view.rank, fv->view.nranks, fv->comm, fv->sComm)) return rc;
+    }
+    const bool direct = fv->plan->direct;
+    const int parity = int(n & 1);
+    if (int rc = launch_shell(fv, a, true, fv->sComm, direct ? parity : -1)) return rc;
     if (trace) cudaEventRecord(fv->tr[1], fv->sComm);
     FvArgs b = a; b.region = fv->bulk;
     if (int rc = launch_step<false>(fv, b, stream)) return rc;
@@ -956,7 +969,8 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
       double* arrays[1] = { d_c_out };
       const long long before = fv->plan->launches;
       static const bool skipx = getenv("DGB_FV_DEBUG_SKIP_EXCHANGE") != nullptr;     // developer timing experiment only
-      if (!skipx) if (int rc = run_plan(fv->grid, *fv->plan, fv->view.rank, DGB_OP_SET, arrays, items, 1, fv->comm, fv->sComm, true)) return rc;
+      if (direct) { if (int rc = run_plan_direct(fv->grid, *fv->plan, parity, DGB_OP_SET, arrays, items, 1, fv->comm, fv->sComm)) return rc; }
+      else if (!skipx) if (int rc = run_plan(fv->grid, *fv->plan, fv->view.rank, DGB_OP_SET, arrays, items, 1, fv->comm, fv->sComm, true)) return rc;
       fv->launches += fv->plan->launches - before;
     }
     DGB_CUDA(cudaEventRecord(fv->evDone, fv->sComm));
