@@ -92,6 +92,7 @@ _SIG = {
     "dgb_fv_bootstrap_local": (_i, [_vp, C.POINTER(_vp), _vp]),
     "dgb_fv_step_host": (_i, [_vp, _vp, _vp, C.POINTER(C.c_double), _vp]),
     "dgb_fv_launch_count": (_i, [_vp, _i64p]),
+    "dgb_fv_exchange_mode": (_i, [_vp, C.POINTER(_i)]),
 }
 EXPORTS = sorted(_SIG)
 for _name, (_res, _args) in _SIG.items():

@@ -63,18 +63,22 @@ struct ArrayTable { int n; int per_entity; double* ptr[8]; int item[8]; };
 
 static constexpr int PACK_THREADS = 256;
 
-// grid.y = box, grid.x strides over the box's doubles. Thread t of a box handles buffer double t:
-// entity e = t / per_entity (x fastest inside the box), then (array, block entry, item) in reference order.
-template<int MODE>   // 0 pack (gather), 1 unpack set, 2 unpack add
-__global__ void __launch_bounds__(PACK_THREADS) k_halo(const PlanBox* __restrict__ boxes, const ArrayTable arrays, double* __restrict__ buffer) {
-  const PlanBox b = boxes[blockIdx.y];
-  const long long total = b.count*arrays.per_entity;
-  for (long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x*blockDim.x) {
-    const long long e = t / arrays.per_entity;
-    int r = int(t - e*arrays.per_entity);
-    const int i0 = int(e % b.size[0]); const long long q = e / b.size[0];
-    const int i1 = int(q % b.size[1]); const int i2 = int(q / b.size[1]);
-    const long long local = ((long long)(b.origin[2]+i2-b.of_origin[2])*b.of_size[1] + (b.origin[1]+i1-b.of_origin[1]))*b.of_size[0]
+// One launch serves a group of boxes: the 1-D grid is the concatenation of the boxes' CTA ranges (start[b]..start[b+1]),
+// so a one-cell corner box costs one CTA and a face its ceil(count/256) (capped, grid-stride beyond). Thread t of a box
+// handles buffer double t: entity e = t / per_entity (x fastest inside the box), then (array, block entry, item) in
+// reference order. Index arithmetic is 32-bit whenever the box's doubles fit (they do for every BASELINE config).
+static constexpr int HALO_MAX_GROUP = 128;
+struct HaloGroup { int nboxes; int start[HALO_MAX_GROUP+1]; };
+
+template<int MODE, typename IT>
+__device__ __forceinline__ void halo_box(const PlanBox& b, const ArrayTable& arrays, double* __restrict__ buffer, IT first, IT step, IT total) {
+  const IT per = IT(arrays.per_entity), s0 = IT(b.size[0]), s1 = IT(b.size[1]);
+  for (IT t = first; t < total; t += step) {
+    const IT e = per == 1 ? t : t / per;
+    int r = per == 1 ? 0 : int(t - e*per);
+    const IT q = e / s0; const int i0 = int(e - q*s0);
+    const IT i2 = q / s1; const int i1 = int(q - i2*s1);
+    const long long local = ((long long)(b.origin[2]+int(i2)-b.of_origin[2])*b.of_size[1] + (b.origin[1]+i1-b.of_origin[1]))*b.of_size[0]
                             + (b.origin[0]+i0-b.of_origin[0]);
     const unsigned idx = (b.index_base + unsigned(local))*b.block + b.map_offset;
     // (array a, entry r inside the array's block*item run)
@@ -86,6 +90,20 @@ __global__ void __launch_bounds__(PACK_THREADS) k_halo(const PlanBox* __restrict
     else if (MODE == 1) *p = *w;
     else *p = *w + *p;
   }
+}
+
+template<int MODE>   // 0 pack (gather), 1 unpack set, 2 unpack add
+__global__ void __launch_bounds__(PACK_THREADS) k_halo(const PlanBox* __restrict__ boxes, const ArrayTable arrays, double* __restrict__ buffer,
+                                                       const __grid_constant__ HaloGroup grp) {
+  int bi = 0;
+  while (bi+1 < grp.nboxes && int(blockIdx.x) >= grp.start[bi+1]) ++bi;          // CTA-uniform
+  const PlanBox& b = boxes[bi];
+  const long long total = b.count*arrays.per_entity;
+  const unsigned cta = blockIdx.x - unsigned(grp.start[bi]), nctas = unsigned(grp.start[bi+1]-grp.start[bi]);
+  if (total < (1ll << 31) - (long long)nctas*PACK_THREADS)
+    halo_box<MODE, unsigned>(b, arrays, buffer, cta*PACK_THREADS + threadIdx.x, nctas*PACK_THREADS, unsigned(total));
+  else
+    halo_box<MODE, long long>(b, arrays, buffer, (long long)cta*PACK_THREADS + threadIdx.x, (long long)nctas*PACK_THREADS, total);
 }
 
 // ---- plan construction (host) -------------------------------------------------------------------------
@@ -192,24 +210,17 @@ int CommPlan::upload() {
   return DGB_OK;
 }
 CommPlan::~CommPlan() {
-  for (void* p : ipcOpened) cudaIpcCloseMemHandle(p);
-  for (int k = 0; k < 2; ++k) if (dRecvBuf2[k]) cudaFree(dRecvBuf2[k]);
-  for (int k = 0; k < 2; ++k) if (dDst[k]) cudaFree(dDst[k]);
-  if (dBarrier) cudaFree(dBarrier);
   if (dSendBoxes) cudaFree(dSendBoxes);
   if (dRecvBoxes) cudaFree(dRecvBoxes);
   if (dSendBuf) cudaFree(dSendBuf);
   if (dRecvBuf) cudaFree(dRecvBuf);
 }
 
-// blocks per box: enough to cover the box, capped so that pack/unpack, which run concurrently with the bulk FV kernel on
-// a high-priority stream, take SM slots away from it only briefly (DGB_HALO_MAXBLOCKS overrides the cap)
-static dim3 halo_grid(long long maxBox, int nBoxes) {
+// CTAs of one box: enough to cover it, capped (grid-stride beyond; DGB_HALO_MAXBLOCKS overrides the cap)
+static int halo_ctas(long long doubles) {
   static const long long cap = [] { const char* e = getenv("DGB_HALO_MAXBLOCKS"); long long v = e ? atoll(e) : 2048; return v > 0 ? v : 2048; }();
-  long long bx = (maxBox + PACK_THREADS - 1)/PACK_THREADS;
-  if (bx > cap) bx = cap;
-  if (bx < 1) bx = 1;
-  return dim3((unsigned)bx, (unsigned)nBoxes, 1);
+  long long bx = (doubles + PACK_THREADS - 1)/PACK_THREADS;
+  return int(std::max(1ll, std::min(bx, cap)));
 }
 
 static int make_table(const CommPlan& plan, double* const* d_arrays, const int32_t* item_sizes, int narrays, ArrayTable& at) {
@@ -228,13 +239,17 @@ static void launch_boxes(CommPlan& plan, const ArrayTable& at, int mode, const s
   while (k < host.size()) {
     std::size_t limit = host.size();
     if (waveEnd) { while (wv < waveEnd->size() && std::size_t((*waveEnd)[wv]) <= k) ++wv; limit = std::size_t((*waveEnd)[wv]); }
-    std::size_t e = k; long long mx = 0;
-    while (e < limit && host[e].block == host[k].block) { mx = std::max(mx, host[e].count*(long long)host[e].block*plan.items); ++e; }
+    HaloGroup grp; grp.nboxes = 0; grp.start[0] = 0;
+    std::size_t e = k;
+    while (e < limit && host[e].block == host[k].block && grp.nboxes < HALO_MAX_GROUP) {
+      grp.start[grp.nboxes+1] = grp.start[grp.nboxes] + halo_ctas(host[e].count*(long long)host[e].block*plan.items);
+      ++grp.nboxes; ++e;
+    }
     ArrayTable t = at; t.per_entity = int(host[k].block)*plan.items;
-    dim3 grid = halo_grid(mx, int(e-k));
-    if (mode == 0) k_halo<0><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf);
-    else if (mode == 1) k_halo<1><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf);
-    else k_halo<2><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf);
+    const unsigned grid = unsigned(grp.start[grp.nboxes]);
+    if (mode == 0) k_halo<0><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
+    else if (mode == 1) k_halo<1><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
+    else k_halo<2><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
     ++plan.launches;
     k = e;
   }
@@ -286,96 +301,112 @@ int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_a
   return rcu;
 }
 
-// ---- direct exchange over peer-mapped memory ------------------------------------------------------------------------
-// what every rank publishes: the IPC handles of its two receive buffers and, per sender rank, the offset (in doubles) of
-// that sender's segment in the buffers (-1: no message from that rank)
-struct DirectInfo { cudaIpcMemHandle_t handle[2]; long long segOffset[64]; long long segCount[64]; int ok; int pad; };
-
-int plan_enable_direct(dgb_grid* g, CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream) {
-  if (plan.direct) return DGB_OK;                         // a cached plan shared by several FV objects: set up once
-  if (nranks > 64) return DGB_OK;
+int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream) {
   if (int rc = plan.upload()) return rc;
+  ArrayTable at; if (int rc = make_table(plan, d_arrays, item_sizes, narrays, at)) return rc;
+  if (plan.nRecvBoxes) launch_boxes(plan, at, op == DGB_OP_ADD ? 2 : 1, plan.hostRecv, plan.dRecvBoxes, const_cast<double*>(buf), &plan.recvWaveEnd, stream);
+  DGB_CUDA(cudaGetLastError());
+  return DGB_OK;
+}
+
+// ---- fused exchange over peer-mapped memory: set-up ------------------------------------------------------------------
+// what every rank publishes: the IPC handle of its block and, per sender rank, the offset (in doubles) of that sender's
+// segment in the receive buffers (-1: no message from that rank)
+struct FusedInfo { cudaIpcMemHandle_t handle; long long segOffset[64]; long long segCount[64]; long long recvTotal; int ok; int pad; };
+
+void FusedState::release() {
+  for (void* p : opened) cudaIpcCloseMemHandle(p);
+  opened.clear();
+  for (int k = 0; k < 2; ++k) { if (dDst[k]) cudaFree(dDst[k]); dDst[k] = nullptr; }
+  if (dPack) cudaFree(dPack);
+  if (block) cudaFree(block);
+  dPack = nullptr; block = nullptr; ctl = nullptr; recv[0] = recv[1] = nullptr; on = false;
+}
+
+int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs) {
+  fs.on = false;
+  if (nranks > 64) return DGB_OK;                              // FusedCtl capacity (same verdict on every rank)
   const bool multi = nranks > 1;
   if (multi && !comm) return DGB_OK;
-  // own buffers, not the plan's dRecvBuf: a peer may already store step n+1 while this rank's dgb_communicate of the same
-  // (cached) plan is still using dRecvBuf
-  for (int k = 0; k < 2; ++k)
-    if (!plan.dRecvBuf2[k] && plan.recvTotal) DGB_CUDA(cudaMalloc(&plan.dRecvBuf2[k], plan.recvTotal*sizeof(double)));
-  if (!plan.dBarrier) { DGB_CUDA(cudaMalloc(&plan.dBarrier, sizeof(double))); DGB_CUDA(cudaMemset(plan.dBarrier, 0, sizeof(double))); }
-  std::vector<DirectInfo> all(nranks);
-  DirectInfo mine; std::memset(&mine, 0, sizeof(mine));
-  mine.ok = 1;
+  if (int rc = plan.upload()) return rc;
+  auto round256 = [](size_t b) { return (b + 255)/256*256; };
+  const size_t ctlBytes = round256(sizeof(FusedCtl));
+  auto buf_bytes = [&](long long doubles) { return round256(size_t(doubles)*sizeof(double)); };
+  DGB_CUDA(cudaMalloc(&fs.block, ctlBytes + 2*buf_bytes(plan.recvTotal)));
+  DGB_CUDA(cudaMemset(fs.block, 0, ctlBytes + 2*buf_bytes(plan.recvTotal)));
+  fs.ctl = static_cast<FusedCtl*>(fs.block);
+  for (int k = 0; k < 2; ++k) fs.recv[k] = reinterpret_cast<double*>(static_cast<char*>(fs.block) + ctlBytes + k*buf_bytes(plan.recvTotal));
+  std::vector<FusedInfo> all(nranks);
+  FusedInfo mine; std::memset(&mine, 0, sizeof(mine));
+  mine.ok = plan.nSendBoxes <= 32 ? 1 : 0;               // FUSED_MAX_BOXES of the step kernels
+  mine.recvTotal = plan.recvTotal;
   for (int r = 0; r < 64; ++r) { mine.segOffset[r] = -1; mine.segCount[r] = 0; }
   for (auto& s : plan.recvSeg) { mine.segOffset[s.peer] = s.offset; mine.segCount[s.peer] = s.count; }
-  if (multi && plan.recvTotal)
-    for (int k = 0; k < 2; ++k)
-      if (cudaIpcGetMemHandle(&mine.handle[k], plan.dRecvBuf2[k]) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+  if (multi && cudaIpcGetMemHandle(&mine.handle, fs.block) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+  double* dScratch = nullptr;
   if (multi) {
-    DirectInfo* dAll = nullptr;
-    DGB_CUDA(cudaMalloc(&dAll, sizeof(DirectInfo)*nranks));
-    DGB_CUDA(cudaMemcpyAsync(dAll + myrank, &mine, sizeof(DirectInfo), cudaMemcpyHostToDevice, stream));
-    DGB_NCCL(g_nccl.AllGather(dAll + myrank, dAll, sizeof(DirectInfo), ncclChar, comm->comm, stream));
-    DGB_CUDA(cudaMemcpyAsync(all.data(), dAll, sizeof(DirectInfo)*nranks, cudaMemcpyDeviceToHost, stream));
+    FusedInfo* dAll = nullptr;
+    DGB_CUDA(cudaMalloc(&dAll, sizeof(FusedInfo)*nranks));
+    DGB_CUDA(cudaMalloc(&dScratch, sizeof(double)));
+    DGB_CUDA(cudaMemcpyAsync(dAll + myrank, &mine, sizeof(FusedInfo), cudaMemcpyHostToDevice, stream));
+    DGB_NCCL(g_nccl.AllGather(dAll + myrank, dAll, sizeof(FusedInfo), ncclChar, comm->comm, stream));
+    DGB_CUDA(cudaMemcpyAsync(all.data(), dAll, sizeof(FusedInfo)*nranks, cudaMemcpyDeviceToHost, stream));
     DGB_CUDA(cudaStreamSynchronize(stream));
     cudaFree(dAll);
   } else all[0] = mine;
   bool ok = true;
   for (int r = 0; r < nranks; ++r) ok = ok && all[r].ok;
-  // map the buffers of the ranks this rank sends to; every rank must reach the same verdict, so a failure is all-reduced
-  std::vector<double*> peerBuf[2]; peerBuf[0].assign(nranks, nullptr); peerBuf[1].assign(nranks, nullptr);
+  // map every rank's block: flags and CFL values go to all ranks, field data to the ranks this rank sends to
+  std::vector<char*> base(nranks, nullptr);
+  for (int r = 0; r < nranks && ok; ++r) {
+    if (r == myrank) { base[r] = static_cast<char*>(fs.block); continue; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    fs.opened.push_back(p);
+    base[r] = static_cast<char*>(p);
+  }
   if (ok)
-    for (auto& s : plan.sendSeg) {
-      if (peerBuf[0][s.peer]) continue;
-      if (s.peer == myrank) { peerBuf[0][s.peer] = plan.dRecvBuf2[0]; peerBuf[1][s.peer] = plan.dRecvBuf2[1]; continue; }
-      for (int k = 0; k < 2 && ok; ++k) {
-        void* p = nullptr;
-        if (cudaIpcOpenMemHandle(&p, all[s.peer].handle[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
-        plan.ipcOpened.push_back(p);
-        peerBuf[k][s.peer] = static_cast<double*>(p);
-      }
-      if (ok && (all[s.peer].segOffset[myrank] < 0 || all[s.peer].segCount[myrank] != s.count)) ok = false;
-    }
-  if (multi) {                                           // agree on the verdict (min over ranks of 1/0)
+    for (auto& s : plan.sendSeg)
+      if (all[s.peer].segOffset[myrank] < 0 || all[s.peer].segCount[myrank] != s.count) ok = false;
+  if (multi) {                                           // every rank must reach the same verdict: min over ranks of 1/0
     double v = ok ? 1.0 : 0.0;
-    DGB_CUDA(cudaMemcpyAsync(plan.dBarrier, &v, sizeof(double), cudaMemcpyHostToDevice, stream));
-    DGB_NCCL(g_nccl.AllReduce(plan.dBarrier, plan.dBarrier, 1, ncclDouble, ncclMin, comm->comm, stream));
-    DGB_CUDA(cudaMemcpyAsync(&v, plan.dBarrier, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    DGB_CUDA(cudaMemcpyAsync(dScratch, &v, sizeof(double), cudaMemcpyHostToDevice, stream));
+    DGB_NCCL(g_nccl.AllReduce(dScratch, dScratch, 1, ncclDouble, ncclMin, comm->comm, stream));
+    DGB_CUDA(cudaMemcpyAsync(&v, dScratch, sizeof(double), cudaMemcpyDeviceToHost, stream));
     DGB_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(dScratch);
     ok = v > 0.5;
   }
-  if (!ok) return DGB_OK;
+  if (!ok) { fs.release(); return DGB_OK; }
   // destination of every send box: receiver's buffer + offset of my segment there + offset of the box inside my segment
-  std::vector<double*> dst[2]; dst[0].resize(plan.nSendBoxes); dst[1].resize(plan.nSendBoxes);
-  for (int b = 0; b < plan.nSendBoxes; ++b) {
-    const PlanBox& pb = plan.hostSend[b];
-    const CommPlan::Segment* seg = nullptr;
-    for (auto& s : plan.sendSeg) if (pb.buf_offset >= s.offset && pb.buf_offset < s.offset + s.count) seg = &s;
-    if (!seg) return fail(DGB_EGRID, "send box outside every segment");
-    for (int k = 0; k < 2; ++k) dst[k][b] = peerBuf[k][seg->peer] + all[seg->peer].segOffset[myrank] + (pb.buf_offset - seg->offset);
-  }
+  FusedPack pk[2];
   for (int k = 0; k < 2; ++k) {
-    if (!plan.dDst[k] && plan.nSendBoxes) DGB_CUDA(cudaMalloc(&plan.dDst[k], plan.nSendBoxes*sizeof(double*)));
-    if (plan.nSendBoxes) DGB_CUDA(cudaMemcpy(plan.dDst[k], dst[k].data(), plan.nSendBoxes*sizeof(double*), cudaMemcpyHostToDevice));
+    std::vector<double*> dst(plan.nSendBoxes);
+    for (int b = 0; b < plan.nSendBoxes; ++b) {
+      const PlanBox& pb = plan.hostSend[b];
+      const CommPlan::Segment* seg = nullptr;
+      for (auto& s : plan.sendSeg) if (pb.buf_offset >= s.offset && pb.buf_offset < s.offset + s.count) seg = &s;
+      if (!seg) return fail(DGB_EGRID, "send box outside every segment");
+      char* peerBuf = base[seg->peer] + ctlBytes + k*buf_bytes(all[seg->peer].recvTotal);
+      dst[b] = reinterpret_cast<double*>(peerBuf) + all[seg->peer].segOffset[myrank] + (pb.buf_offset - seg->offset);
+    }
+    if (plan.nSendBoxes) {
+      DGB_CUDA(cudaMalloc(&fs.dDst[k], plan.nSendBoxes*sizeof(double*)));
+      DGB_CUDA(cudaMemcpy(fs.dDst[k], dst.data(), plan.nSendBoxes*sizeof(double*), cudaMemcpyHostToDevice));
+    }
+    std::memset(&pk[k], 0, sizeof(FusedPack));
+    pk[k].boxes = plan.dSendBoxes; pk[k].dst = fs.dDst[k]; pk[k].counter = &fs.ctl->counter;
+    pk[k].nBoxes = plan.nSendBoxes; pk[k].nranks = nranks;
+    for (int r = 0; r < nranks; ++r) {
+      FusedCtl* c = reinterpret_cast<FusedCtl*>(base[r]);
+      pk[k].peerFlag[r] = &c->flags[myrank];
+      pk[k].peerCfl[r] = &c->cfl[k][myrank];
+    }
   }
-  (void)g;
-  plan.direct = true;
-  return DGB_OK;
-}
-
-int run_plan_direct(dgb_grid* g, CommPlan& plan, int parity, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays,
-                    dgb_comm* comm, cudaStream_t stream) {
-  if (plan.trace[0]) cudaEventRecord(plan.trace[0], stream);
-  // every rank's packing kernel precedes this all-reduce in its stream: when it completes here, all peers' stores into
-  // this rank's buffer have been performed
-  if (comm && comm->nranks > 1) DGB_NCCL(g_nccl.AllReduce(plan.dBarrier, plan.dBarrier, 1, ncclDouble, ncclMax, comm->comm, stream));
-  if (plan.trace[1]) cudaEventRecord(plan.trace[1], stream);
-  ArrayTable at; if (int rc = make_table(plan, d_arrays, item_sizes, narrays, at)) return rc;
-  if (plan.nRecvBoxes) launch_boxes(plan, at, op == DGB_OP_ADD ? 2 : 1, plan.hostRecv, plan.dRecvBoxes, plan.dRecvBuf2[parity], &plan.recvWaveEnd, stream);
-  DGB_CUDA(cudaGetLastError());
-  if (plan.trace[2]) cudaEventRecord(plan.trace[2], stream);
-  int64_t bytes = 0;
-  for (auto& s : plan.sendSeg) bytes += s.count*8;
-  g->lastBytesSent = bytes;
+  DGB_CUDA(cudaMalloc(&fs.dPack, 2*sizeof(FusedPack)));
+  DGB_CUDA(cudaMemcpy(fs.dPack, pk, 2*sizeof(FusedPack), cudaMemcpyHostToDevice));
+  fs.epoch = 0;
+  fs.on = true;
   return DGB_OK;
 }
 

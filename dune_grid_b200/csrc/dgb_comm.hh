@@ -31,14 +31,6 @@ struct CommPlan {
   bool uploaded = false;
   long long launches = 0;
   cudaEvent_t trace[3] = {nullptr, nullptr, nullptr};     // optional timing events: after pack, after transfer, after unpack (DGB_FV_TRACE)
-  // direct mode (plan_enable_direct): the packing kernel stores straight into the RECEIVER's exchange buffer through
-  // peer-mapped memory (NVLink), double buffered by step parity; one small all-reduce orders "all senders have written"
-  // before the unpack. dDst[parity][box] = where send box `box` starts in its receiver's buffer.
-  bool direct = false;
-  double* dRecvBuf2[2] = {nullptr, nullptr};              // receive buffers of the direct mode, by step parity
-  double** dDst[2] = {nullptr, nullptr};                  // device arrays of nSendBoxes pointers
-  std::vector<void*> ipcOpened;
-  double* dBarrier = nullptr;
   int upload();
   ~CommPlan();
 };
@@ -48,11 +40,42 @@ int get_plan(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir, c
 int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays,
              dgb_comm* comm, cudaStream_t stream, bool packed = false);
 int nccl_allreduce(double* d, int op /*0 min, 1 max*/, dgb_comm* comm, cudaStream_t stream);
-// collective over all ranks: exchange IPC handles of the plans' receive buffers and the segment offsets, map the peers'
-// buffers. Returns DGB_OK with plan.direct = false when peer mapping is not available (the NCCL path stays in use).
-int plan_enable_direct(dgb_grid* g, CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream);
-// the part of a direct exchange after the packing kernel: barrier over the ranks, unpack from buffer `parity`
-int run_plan_direct(dgb_grid* g, CommPlan& plan, int parity, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays,
-                    dgb_comm* comm, cudaStream_t stream);
+// recv boxes scattered from `buf` (laid out like the plan's receive buffer) instead of plan.dRecvBuf
+int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream);
+
+// ---- fused exchange: the FV step kernel itself packs into the RECEIVERS' buffers through peer-mapped memory (NVLink) and
+// signals completion with a flag; no NCCL call and no second stream in the steady state (dgb_fv.cu) -------------------
+// One block per rank, shared with every other rank by CUDA IPC: control words + two receive buffers (by step parity).
+struct FusedCtl {
+  unsigned flags[64];        // flags[s] = number of steps whose data (and CFL value) rank s has delivered here
+  unsigned counter;          // CTAs of the running step kernel that have finished (local)
+  unsigned timeout;          // set by the wait kernel if a peer did not deliver in time
+  unsigned pad[62];
+  double cfl[2][64];         // cfl[parity][s] = local outflow maximum of rank s
+};
+// what the step kernel needs (device memory, one per parity)
+struct FusedPack {
+  const PlanBox* boxes;      // send boxes of the plan
+  double* const* dst;        // dst[b] = first double of box b in its receiver's buffer of this parity
+  unsigned* counter;
+  int nBoxes, nranks;
+  unsigned* peerFlag[64];    // &ctl(r).flags[myrank]
+  double* peerCfl[64];       // &ctl(r).cfl[parity][myrank]
+};
+struct FusedState {
+  bool on = false;
+  void* block = nullptr;
+  FusedCtl* ctl = nullptr;
+  double* recv[2] = {nullptr, nullptr};
+  FusedPack* dPack = nullptr;            // [2]
+  double** dDst[2] = {nullptr, nullptr};
+  std::vector<void*> opened;
+  unsigned epoch = 0;                    // fused steps done
+  void release();
+  ~FusedState() { release(); }
+};
+// collective over all ranks: allocate and publish this rank's block, map the peers'. Leaves fs.on = false (and DGB_OK) when
+// peer mapping is not available on every rank - the caller then keeps the NCCL path.
+int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs);
 }
 #endif

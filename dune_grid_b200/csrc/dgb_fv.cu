@@ -62,7 +62,109 @@ struct FvArgs {
   double* slotZero;      // slot to clear for the step after next
   double* dtOut;         // dt actually used
   const double* consts;  // device constants {0, boundary value} (upwind sources of faces without a stored neighbour)
+  const FusedPack* pack; // fused exchange (3-D step kernels): pack into the receivers' buffers and signal; NULL = off
+  unsigned packEpoch;    // value published in the receivers' flags when this launch has delivered everything
 };
+
+// ---- fused exchange, device side (dgb_comm.hh: FusedCtl / FusedPack) -------------------------------------------------
+// Called by every CTA of a 3-D step kernel after its last store to c_new: the cells of the CTA's tile x chunk that lie in
+// a send box of communicate(InteriorBorder_All, Forward) are copied to that box's place in the RECEIVER's buffer (peer-
+// mapped memory: the stores travel over NVLink while the other CTAs are still computing). All threads of the CTA share
+// the copy, whatever the shape of the intersection (an x-face is one cell per row: 1 x BY x ZC cells here).
+// fv_fused_prepare (kernel start, one thread per send box): the intersection of the box with the CTA's tile x chunk.
+// fv_fused_pack (after the CTA's last store): all threads share the copy of every non-empty intersection.
+struct FusedItem { double* dst0; long long src0; int ex, ey, n, dsy, dsz; };
+static constexpr int FUSED_MAX_BOXES = 32;
+__device__ __forceinline__ void fv_fused_prepare(const FvArgs& a, const dgb_box& of, FusedItem* items, int x0, int nx, int y0, int ny,
+                                                 int z0, int nz, int tid) {
+  const FusedPack& P = *a.pack;
+  if (tid < P.nBoxes) {
+    const PlanBox& pb = P.boxes[tid];
+    const int lx = max(x0, pb.origin[0]), hx = min(x0+nx, pb.origin[0]+pb.size[0]);
+    const int ly = max(y0, pb.origin[1]), hy = min(y0+ny, pb.origin[1]+pb.size[1]);
+    const int lz = max(z0, pb.origin[2]), hz = min(z0+nz, pb.origin[2]+pb.size[2]);
+    FusedItem it;
+    it.n = 0;
+    if (lx < hx && ly < hy && lz < hz) {
+      it.ex = hx-lx; it.ey = hy-ly; it.n = it.ex*it.ey*(hz-lz);
+      it.dsy = pb.size[0]; it.dsz = pb.size[0]*pb.size[1];
+      it.dst0 = P.dst[tid] + ((long long)(lz-pb.origin[2])*pb.size[1] + (ly-pb.origin[1]))*pb.size[0] + (lx-pb.origin[0]);
+      it.src0 = ((long long)(lz-of.origin[2])*of.size[1] + (ly-of.origin[1]))*of.size[0] + (lx-of.origin[0]);
+      items[tid] = it;
+    } else items[tid].n = 0;
+  }
+}
+template<int NT>
+__device__ __forceinline__ void fv_fused_pack(const FvArgs& a, const dgb_box& of, const FusedItem* items, int tid) {
+  const int nBoxes = a.pack->nBoxes;
+  const int sy = of.size[0]; const long long sz = (long long)of.size[0]*of.size[1];
+  __syncthreads();                                   // the CTA's stores to c_new are visible to all its threads
+  for (int b = 0; b < nBoxes; ++b) {
+    const int n = items[b].n;
+    if (n == 0) continue;
+    const FusedItem it = items[b];
+    // U independent loads in flight per thread before the first store: a y-face tile is BX x 1 x ZC cells, i.e. 64 cells
+    // per thread, and one load-store round trip per cell would keep the CTA (and the kernel's tail) alive for ~60 us
+    constexpr int U = 8;
+    for (int t0 = tid; t0 < n; t0 += NT*U) {
+      double val[U]; long long d[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t0 + u*NT;
+        if (t < n) {
+          const int i0 = t % it.ex, q = t / it.ex, i1 = q % it.ey, i2 = q / it.ey;
+          val[u] = __ldcg(a.cnew + it.src0 + i2*sz + i1*sy + i0);
+          d[u] = (long long)i2*it.dsz + i1*it.dsy + i0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) if (t0 + u*NT < n) it.dst0[d[u]] = val[u];
+    }
+  }
+}
+// Tile row of a CTA of the 3-D step kernels. With the fused exchange the LAST tile row is scheduled first: a y-face is
+// BX x 1 x ZC cells of one CTA, the heaviest pack, and must not sit in the kernel's tail.
+__device__ __forceinline__ int fv_tile_row(const FvArgs& a) {
+  if (!a.pack) return int(blockIdx.y);
+  return blockIdx.y == 0 ? int(gridDim.y)-1 : int(blockIdx.y)-1;
+}
+// Called by ONE thread per CTA after a __syncthreads that follows fv_fused_pack and the CTA's CFL atomic: the last CTA of
+// the grid publishes the rank's outflow maximum and then the epoch in every rank's control block.
+__device__ __forceinline__ void fv_fused_signal(const FvArgs& a) {
+  const FusedPack& P = *a.pack;
+  __threadfence_system();                            // the CTA's peer stores and its CFL atomic are performed
+  const unsigned total = gridDim.x*gridDim.y*gridDim.z;
+  if (atomicAdd(P.counter, 1u) == total-1) {
+    atomicExch(P.counter, 0u);
+    __threadfence();
+    const double m = __longlong_as_double((long long)atomicAdd(reinterpret_cast<unsigned long long*>(a.slotOut), 0ull));
+    for (int r = 0; r < P.nranks; ++r) *reinterpret_cast<volatile double*>(P.peerCfl[r]) = m;
+    __threadfence_system();
+    for (int r = 0; r < P.nranks; ++r) *reinterpret_cast<volatile unsigned*>(P.peerFlag[r]) = a.packEpoch;
+  }
+}
+// the receiving side: thread s waits until rank s has delivered epoch `target`, then the reduced CFL value is stored
+__global__ void k_fv_wait(FusedCtl* ctl, int nranks, unsigned target, int parity, double* slot) {
+  const int s = threadIdx.x;
+  if (s < nranks) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      unsigned f;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&ctl->flags[s]) : "memory");
+      if (int(f - target) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) { ctl->timeout = 1u; break; }        // 20 s: a peer is gone; do not hang the device
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (s == 0) {
+    double m = 0.0;
+    for (int r = 0; r < nranks; ++r) m = fmax(m, *reinterpret_cast<volatile double*>(&ctl->cfl[parity][r]));
+    *slot = m;
+  }
+}
 
 // EXACT: the arithmetic of the per-entity CPU loop, operation by operation (bit-identical results).
 // SEPARABLE: face factor (u.n)|F|/|V| = (u.n)/w_dir taken from per-axis reciprocal tables (<= 2 ulp difference).
@@ -152,8 +254,7 @@ __global__ void __launch_bounds__(FBX*FBY) k_fv_step(const __grid_constant__ dgb
 // cells are one per row anyway). Each new value is stored to c_new AND to every send box of the exchange plan that
 // contains the cell ("in-kernel pack": the separate gather kernel, its strided re-read of c_new and one stream
 // dependency disappear). Same per-cell arithmetic as k_fv_step.
-struct FvShell { FvRegion slab[6]; int perm[6]; int n; const PlanBox* boxes; int nBoxes; double* sendBuf;
-                 double* const* dst; };   // dst != NULL: box b starts at dst[b] (the receiver's buffer, peer-mapped)
+struct FvShell { FvRegion slab[6]; int perm[6]; int n; const PlanBox* boxes; int nBoxes; double* sendBuf; };
 
 template<int MODE>
 __global__ void __launch_bounds__(256) k_fv_shell(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a, const __grid_constant__ FvShell sh) {
@@ -211,10 +312,9 @@ __global__ void __launch_bounds__(256) k_fv_shell(const __grid_constant__ dgb_vi
       const PlanBox& pb = sh.boxes[b];
       const int j0 = coord[0]-pb.origin[0], j1 = coord[1]-pb.origin[1], j2 = coord[2]-pb.origin[2];
       if (j0 >= 0 && j0 < pb.size[0] && j1 >= 0 && j1 < pb.size[1] && j2 >= 0 && j2 < pb.size[2])
-        (sh.dst ? sh.dst[b] : sh.sendBuf + pb.buf_offset)[((long long)j2*pb.size[1] + j1)*pb.size[0] + j0] = cn;
+        sh.sendBuf[pb.buf_offset + ((long long)j2*pb.size[1] + j1)*pb.size[0] + j0] = cn;
     }
   }
-  if (sh.dst) __threadfence_system();          // peer stores are performed before the kernel is seen as complete
   if (a.dtOut && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.dtOut = dt;
   for (int off = 16; off > 0; off >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, off));
   __shared__ double part[8];
@@ -246,7 +346,8 @@ __device__ __forceinline__ void fv_velocity3(const FvProblem& q, const double* x
 template<int MODE, int PROBLEM, bool REDUCE_ONLY, int PF, int BX, int BY>
 __global__ void __launch_bounds__(BX*BY) k_fv_march(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a, const int zc) {
   const int i0 = blockIdx.x*BX + threadIdx.x;
-  const int i1 = blockIdx.y*BY + threadIdx.y;
+  const int by = fv_tile_row(a);
+  const int i1 = by*BY + threadIdx.y;
   const int z0 = blockIdx.z*zc;
   const int zn = min(zc, a.region.size[2]-z0);
   double sum_max = 0.0;
@@ -342,9 +443,16 @@ __global__ void __launch_bounds__(BX*BY) k_fv_march(const __grid_constant__ dgb_
     }
     if (!REDUCE_ONLY && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = dt;
   }
+  const int tid = threadIdx.y*BX + threadIdx.x;
+  if (!REDUCE_ONLY && a.pack) {
+    __shared__ FusedItem items[FUSED_MAX_BOXES];
+    const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+    fv_fused_prepare(a, of, items, a.region.origin[0]+blockIdx.x*BX, min(BX, a.region.size[0]-(int)blockIdx.x*BX),
+                     a.region.origin[1]+by*BY, min(BY, a.region.size[1]-by*BY), a.region.origin[2]+z0, zn, tid);
+    fv_fused_pack<BX*BY>(a, of, items, tid);
+  }
   for (int off = 16; off > 0; off >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, off));
   __shared__ double part[BX*BY/32];
-  const int tid = threadIdx.y*BX + threadIdx.x;
   if ((tid & 31) == 0) part[tid >> 5] = sum_max;
   __syncthreads();
   if (tid == 0) {
@@ -352,6 +460,7 @@ __global__ void __launch_bounds__(BX*BY) k_fv_march(const __grid_constant__ dgb_
     for (int k = 0; k < BX*BY/32; ++k) m = fmax(m, part[k]);
     if (m > 0.0) atomic_max_nonneg(a.slotOut, m);
     if (a.slotZero && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *a.slotZero = 0.0;
+    if (!REDUCE_ONLY && a.pack) fv_fused_signal(a);
   }
 }
 
@@ -474,7 +583,8 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   extern __shared__ double ring[];                     // [R][PY][PX]
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i0 = blockIdx.x*BX + tx;
-  const int i1 = blockIdx.y*BY + ty;
+  const int by = fv_tile_row(a);
+  const int i1 = by*BY + ty;
   const int z0 = blockIdx.z*zc;
   const int zn = min(zc, a.region.size[2]-z0);
   const int cz0 = a.region.origin[2]+z0;
@@ -535,6 +645,11 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     if ((!o2 && o3) || (o2 && o3 && f2 == 0.0 && f3 == 0.0)) dy = 1; else if (o2 && !o3) dy = 0;
     dz = (un5 >= 0.0) ? 1 : 0;
   }
+  // fused exchange: which send boxes this CTA's tile x chunk meets (read at the very end; the barriers below publish it)
+  __shared__ FusedItem s_items[FUSED_MAX_BOXES];
+  if (a.pack)
+    fv_fused_prepare(a, of, s_items, a.region.origin[0]+blockIdx.x*BX, min(BX, a.region.size[0]-(int)blockIdx.x*BX),
+                     a.region.origin[1]+by*BY, min(BY, a.region.size[1]-by*BY), cz0, zn, ty*BX + tx);
   // one code path per CTA (the loop contains barriers): fast only if every thread agrees on the directions
   __shared__ int s_pat[2];
   if (tx == 0 && ty == 0) { s_pat[0] = dx*4 + dy*2 + dz; s_pat[1] = 1; }
@@ -559,13 +674,13 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   // cell is a stored neighbour and - on the fast path, where all columns share the flow direction - on an inflow side
   {
     const int t = ty*BX + tx;
-    const int nxv = min(BX, a.region.size[0]-blockIdx.x*BX), nyv = min(BY, a.region.size[1]-blockIdx.y*BY);   // valid columns / rows
+    const int nxv = min(BX, a.region.size[0]-blockIdx.x*BX), nyv = min(BY, a.region.size[1]-by*BY);   // valid columns / rows
     int hx = 0, hy = 0, side = -1;
     if (t < BY) { side = 0; hx = -1; hy = t; }
     else if (t < 2*BY) { side = 1; hx = nxv; hy = t-BY; }
     else if (t < 2*BY+BX) { side = 2; hx = t-2*BY; hy = -1; }
     else if (t < 2*BY+2*BX) { side = 3; hx = t-2*BY-BX; hy = nyv; }
-    const int gx = a.region.origin[0]+blockIdx.x*BX+hx, gy = a.region.origin[1]+blockIdx.y*BY+hy;
+    const int gx = a.region.origin[0]+blockIdx.x*BX+hx, gy = a.region.origin[1]+by*BY+hy;
     bool need = side >= 0 && (side < 2 ? hy < nyv : hx < nxv)
                 && gx >= ov.origin[0] && gx < ov.origin[0]+ov.size[0] && gy >= ov.origin[1] && gy < ov.origin[1]+ov.size[1];
     if (need && pat < 8) {
@@ -607,9 +722,10 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   }
   cp_async_wait<0>();
   if (active && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = L.dt;
+  const int tid = ty*BX + tx;
+  if (a.pack) fv_fused_pack<BX*BY>(a, of, s_items, tid);
   for (int o = 16; o > 0; o >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, o));
   __shared__ double part[BX*BY/32];
-  const int tid = ty*BX + tx;
   if ((tid & 31) == 0) part[tid >> 5] = sum_max;
   __syncthreads();
   if (tid == 0) {
@@ -617,6 +733,7 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     for (int k = 0; k < BX*BY/32; ++k) m = fmax(m, part[k]);
     if (m > 0.0) atomic_max_nonneg(a.slotOut, m);
     if (a.slotZero && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *a.slotZero = 0.0;
+    if (a.pack) fv_fused_signal(a);
   }
 }
 
@@ -671,7 +788,9 @@ struct dgb_fv {
   double* dSlots = nullptr;        // 4 rotating max-sum slots + dt + the constants {0, boundary value}: see slot_args
   long long step = 0;
   bool bootstrapped = false;
-  bool directTried = false;      // plan_enable_direct has been attempted
+  bool fusedTried = false;       // fused_setup has been attempted
+  int exchangeMode = DGB_FV_EXCHANGE_NONE;
+  dgb::FusedState fused;         // fused exchange (pack + peer stores + signal inside the step kernel)
   bool seedPending = false;      // dgb_fv_bootstrap_local: the reduced seed still has to be copied to the second slot
   int64_t launches = 0;
   std::shared_ptr<CommPlan> plan;
@@ -757,7 +876,7 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
 }
 
 // all exchange-shell slabs in one launch; pack = true also fills the send buffer of the FV exchange plan
-static int launch_shell(dgb_fv* fv, const FvArgs& a, bool pack, cudaStream_t stream, int parity = -1) {
+static int launch_shell(dgb_fv* fv, const FvArgs& a, bool pack, cudaStream_t stream) {
   if (!fv->nShell) return DGB_OK;
   FvShell sh{};
   long long most = 0;
@@ -769,7 +888,6 @@ static int launch_shell(dgb_fv* fv, const FvArgs& a, bool pack, cudaStream_t str
   if (pack) {
     if (int rc = fv->plan->upload()) return rc;
     sh.boxes = fv->plan->dSendBoxes; sh.nBoxes = fv->plan->nSendBoxes; sh.sendBuf = fv->plan->dSendBuf;
-    if (parity >= 0) sh.dst = fv->plan->dDst[parity];
   }
   dim3 grid((unsigned)std::min<long long>((most+255)/256, 4096), (unsigned)fv->nShell, 1);
   if (fv->mode == DGB_FV_EXACT) k_fv_shell<DGB_FV_EXACT><<<grid, 256, 0, stream>>>(fv->view, a, sh);
@@ -937,7 +1055,39 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
   FvArgs a = base_args(fv);
   a.c = d_c_in; a.cnew = d_c_out;
   slot_args(fv, n, a);
-  if (fv->split && (fv->plan->nSendBoxes || fv->plan->nRecvBoxes)) {
+  const bool exchanges = fv->plan->nSendBoxes || fv->plan->nRecvBoxes;
+  // Fused form (3-D, default): ONE step kernel over the whole interior packs the send boxes straight into the receivers'
+  // buffers (peer-mapped memory, NVLink) while it computes and raises a flag when the rank has delivered; a one-CTA kernel
+  // waits for all ranks' flags (which also carry the CFL maxima: no all-reduce), then the overlap cells are scattered.
+  // One stream, no NCCL call in the steady state. Collective set-up on the first step; DGB_FV_FUSED=0 or ranks without
+  // peer mapping keep the NCCL forms below.
+  if (!fv->fusedTried) {
+    fv->fusedTried = true;
+    const char* e = getenv("DGB_FV_FUSED");
+    if (!(e && atoi(e) == 0) && fv->view.dim == 3 && (exchanges || fv->view.nranks > 1) && (fv->view.nranks == 1 || fv->comm))
+      if (int rc = fused_setup(*fv->plan, fv->view.rank, fv->view.nranks, fv->comm, stream, fv->fused)) return rc;
+  }
+  if (fv->fused.on) {
+    FusedState& fs = fv->fused;
+    const int parity = int(fs.epoch & 1u);
+    a.pack = fs.dPack + parity; a.packEpoch = fs.epoch + 1u;
+    if (int rc = launch_step<false>(fv, a, stream)) return rc;
+    k_fv_wait<<<1, 64, 0, stream>>>(fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4));
+    ++fv->launches;
+    const int32_t items[1] = {1};
+    double* arrays[1] = { d_c_out };
+    const long long before = fv->plan->launches;
+    if (int rc = plan_unpack_from(*fv->plan, fs.recv[parity], DGB_OP_SET, arrays, items, 1, stream)) return rc;
+    fv->launches += fv->plan->launches - before;
+    int64_t bytes = 0;
+    for (auto& sg : fv->plan->sendSeg) if (sg.peer != fv->view.rank) bytes += sg.count*8;
+    fv->grid->lastBytesSent = bytes;
+    ++fs.epoch;
+    fv->step = n+1;
+    fv->exchangeMode = DGB_FV_EXCHANGE_FUSED;
+    return DGB_OK;
+  }
+  if (fv->split && exchanges) {
     // overlapped form. Caller's stream: bulk. Exchange stream (high priority; every NCCL call of the step): shell
     // slabs with in-kernel pack, NCCL send/recv, unpack; [after the bulk] all-reduce of the CFL slot, which
     // step n+2 reads - the caller's stream waits for it two steps later, and for the exchange at the end of this step.
@@ -949,16 +1099,7 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
     // the streaming bulk kernel, and the stream's priority schedules its CTAs ahead of the bulk's
     DGB_CUDA(cudaEventRecord(fv->evShell, stream));                                    // c_in is ready, slot n%4 is reduced
     DGB_CUDA(cudaStreamWaitEvent(fv->sComm, fv->evShell, 0));
-    // direct peer-store exchange: collective set-up on the first public step (DGB_FV_DIRECT=0 keeps NCCL send/recv)
-    if (!fv->directTried) {
-      fv->directTried = true;
-      const char* e = getenv("DGB_FV_DIRECT");
-      if (!(e && atoi(e) == 0) && (fv->view.nranks == 1 || fv->comm))
-        if (int rc = plan_enable_direct(fv->grid, *fv->plan, fv->view.rank, fv->view.nranks, fv->comm, fv->sComm)) return rc;
-    }
-    const bool direct = fv->plan->direct;
-    const int parity = int(n & 1);
-    if (int rc = launch_shell(fv, a, true, fv->sComm, direct ? parity : -1)) return rc;
+    if (int rc = launch_shell(fv, a, true, fv->sComm)) return rc;
     if (trace) cudaEventRecord(fv->tr[1], fv->sComm);
     FvArgs b = a; b.region = fv->bulk;
     if (int rc = launch_step<false>(fv, b, stream)) return rc;
@@ -969,8 +1110,7 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
       double* arrays[1] = { d_c_out };
       const long long before = fv->plan->launches;
       static const bool skipx = getenv("DGB_FV_DEBUG_SKIP_EXCHANGE") != nullptr;     // developer timing experiment only
-      if (direct) { if (int rc = run_plan_direct(fv->grid, *fv->plan, parity, DGB_OP_SET, arrays, items, 1, fv->comm, fv->sComm)) return rc; }
-      else if (!skipx) if (int rc = run_plan(fv->grid, *fv->plan, fv->view.rank, DGB_OP_SET, arrays, items, 1, fv->comm, fv->sComm, true)) return rc;
+      if (!skipx) if (int rc = run_plan(fv->grid, *fv->plan, fv->view.rank, DGB_OP_SET, arrays, items, 1, fv->comm, fv->sComm, true)) return rc;
       fv->launches += fv->plan->launches - before;
     }
     DGB_CUDA(cudaEventRecord(fv->evDone, fv->sComm));
@@ -979,6 +1119,7 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
     if (int rc = nccl_allreduce(fv->dSlots + ((n+2) % 4), 1, fv->comm, fv->sComm)) return rc;
     DGB_CUDA(cudaEventRecord(fv->evRed[n % 2], fv->sComm));
     fv->step = n+1;
+    fv->exchangeMode = DGB_FV_EXCHANGE_OVERLAPPED;
     if (trace) {                                       // developer timeline (synchronises): ms since the start of the step
       cudaEventRecord(fv->tr[3], stream);
       cudaStreamSynchronize(stream);
@@ -1001,6 +1142,7 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
     const long long before = fv->plan->launches;
     if (int rc = run_plan(fv->grid, *fv->plan, fv->view.rank, DGB_OP_SET, arrays, items, 1, fv->comm, stream)) return rc;
     fv->launches += fv->plan->launches - before;
+    fv->exchangeMode = DGB_FV_EXCHANGE_SERIAL;
   }
   fv->step = n+1;
   return DGB_OK;
@@ -1053,7 +1195,10 @@ int dgb_fv_update(dgb_fv* fv, const double* d_c_in, double* d_update, void* stre
 
 int dgb_fv_last_dt(dgb_fv* fv, double* dt_host, void* stream) {
   DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 4, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  unsigned timedOut = 0;
+  if (fv->fused.on) DGB_CUDA(cudaMemcpyAsync(&timedOut, &fv->fused.ctl->timeout, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   DGB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (timedOut) return fail(DGB_ENCCL, "fused exchange: a rank did not deliver its step within 20 s (ranks out of step?)");
   return DGB_OK;
 }
 
@@ -1131,5 +1276,6 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
 }
 
 int dgb_fv_launch_count(const dgb_fv* fv, int64_t* kernels) { *kernels = fv->launches; return DGB_OK; }
+int dgb_fv_exchange_mode(const dgb_fv* fv, int* mode) { *mode = fv->exchangeMode; return DGB_OK; }
 
 } // extern "C"

@@ -445,3 +445,9 @@ class FiniteVolume:
         n = C.c_int64(0)
         check(lib.dgb_fv_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def exchange_mode(self):
+        """how the last step refreshed the overlap cells: 'none', 'serial', 'overlapped' (NCCL) or 'fused' (peer stores)"""
+        m = C.c_int(0)
+        check(lib.dgb_fv_exchange_mode(self.h, C.byref(m)))
+        return ("none", "serial", "overlapped", "fused")[m.value]

@@ -201,6 +201,12 @@ int dgb_fv_update(dgb_fv* fv, const double* d_c_in, double* d_update, void* stre
 /* the same step on HOST buffers (pinned or pageable): H2D copy of c, step, D2H copy of the result */
 int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* dt_host, void* stream);
 int dgb_fv_launch_count(const dgb_fv* fv, int64_t* kernels);           /* kernels launched by this object so far */
+/* how the last dgb_fv_step refreshed the overlap cells: */
+#define DGB_FV_EXCHANGE_NONE 0      /* no step yet, or nothing to exchange */
+#define DGB_FV_EXCHANGE_SERIAL 1    /* step kernel, then communicate() (2-D, or no room for a shell/bulk split) */
+#define DGB_FV_EXCHANGE_OVERLAPPED 2 /* shell kernel + NCCL send/recv on a second stream, concurrent with the bulk kernel */
+#define DGB_FV_EXCHANGE_FUSED 3     /* one step kernel stores into the receivers' buffers over peer-mapped memory and signals */
+int dgb_fv_exchange_mode(const dgb_fv* fv, int* mode);
 
 #ifdef __cplusplus
 }

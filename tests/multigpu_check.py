@@ -30,6 +30,7 @@ def main():
         (make_cfg(dim=2, N=(32, 24), periodic=1), 1, [1.0, 0, 0, 0.0, 0.5, 0.5, 0.0, 0.1, 0.3]),
     ]
     failures = 0
+    modes = set()
     for cfg, problem, params in cases:
         w = oracle_world(o, cfg, world)
         g = product_grid(cfg, rank, world, comm=comm)
@@ -52,6 +53,7 @@ def main():
                 ok = ok and np.array_equal(got, ref[rank])
             else:
                 ok = ok and np.abs(got - ref[rank]).max() <= 1e-13 * scale           # tolerance: 1e-13 relative
+            modes.add(fv.exchange_mode())
             if not ok:
                 failures += 1
                 print(f"rank {rank}: FV mismatch cfg={cfg['N']} mode={mode} maxdiff={np.abs(got - ref[rank]).max()}", flush=True)
@@ -76,7 +78,8 @@ def main():
     t = torch.tensor([failures], dtype=torch.int64, device="cuda")
     dist.all_reduce(t)
     if rank == 0:
-        print(f"multigpu_check world={world}: {'OK' if t.item() == 0 else 'FAILED'} ({int(t.item())} mismatches)", flush=True)
+        print(f"multigpu_check world={world}: {'OK' if t.item() == 0 else 'FAILED'} ({int(t.item())} mismatches), "
+              f"FV exchange modes on rank 0: {sorted(modes)}", flush=True)
     dist.barrier()
     comm.close()
     dist.destroy_process_group()

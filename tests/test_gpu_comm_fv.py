@@ -304,3 +304,44 @@ def test_fv_ring_kernels_equal_general_kernel_bitwise(problem, params, monkeypat
         for variant in ("0", "3"):
             assert res[variant][1] == res["99"][1]
             assert torch.equal(res[variant][0], res["99"][0]), (cfg["N"], variant)
+
+
+@pytest.mark.parametrize("mode", ["exact", "separable"])
+@pytest.mark.parametrize("cfg,problem,params", [
+    (make_cfg(dim=3, N=(40, 23, 37), periodic=7, upper=(1.0, 0.7, 1.3)), 0, [1.0, -0.5, 0.25, 0.1, 0.5, 0.35, 0.6, 0.1, 0.45]),
+    (make_cfg(dim=3, N=(150, 9, 40), periodic=5, mode=2), 1, [2.0, 0, 0, 0.5, 0.15, 0.35, 0.9, 0.05, 0.4]),
+    (make_cfg(dim=3, N=(12, 300, 5), periodic=2, overlap=2), 0, [-0.3, 0.6, 1.0, 0.7, 0.5, 0.5, 0.5, 0.1, 0.45]),
+])
+def test_fv_fused_exchange_single_rank(cfg, problem, params, mode, monkeypatch):
+    """the fused step (pack + stores into the receiver's buffer + flag inside the step kernel; here the receiver is the
+    rank itself through the periodic wrap) against the CPU oracle and, bit for bit, against the serial form
+    (step kernel, then communicate)"""
+    import torch
+    import dune_grid_b200 as dg
+    o = best_oracle()
+    w = oracle_world(o, cfg, 1)
+    ref = [w.fv_init(0, 0, problem, params)]
+    res = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("DGB_FV_FUSED", fused)
+        monkeypatch.setenv("DGB_FV_NO_SPLIT", "1")
+        g = product_grid(cfg, 0, 1)
+        fv = dg.FiniteVolume(g, 0, problem, params, mode)
+        c = fv.initial()
+        cn = torch.empty_like(c)
+        dts = []
+        for _ in range(5):
+            fv.step(c, cn)
+            c, cn = cn, c
+            dts.append(fv.last_dt())
+        assert fv.exchange_mode() == ("fused" if fused == "1" else "serial")
+        res[fused] = (np_(c), dts)
+    assert np.array_equal(res["1"][0], res["0"][0]) and res["1"][1] == res["0"][1]
+    for k in range(5):
+        dt_ref = w.fv_step(0, problem, params, ref)
+        assert res["1"][1][k] == dt_ref if mode == "exact" else abs(res["1"][1][k] - dt_ref) <= 1e-13 * dt_ref
+    if mode == "exact":
+        assert np.array_equal(res["1"][0], ref[0])
+    else:
+        assert np.abs(res["1"][0] - ref[0]).max() <= 1e-13 * np.abs(ref[0]).max()       # tolerance: 1e-13 relative
+    w.close()
