@@ -829,7 +829,7 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
   if (v.dim == 3) {
     // tile choice (measured, tools/fv_sweep.py): 128x4 columns for wide regions, 32x8 otherwise
     const int variant = fv->variant >= 0 ? fv->variant : (a.region.size[0] >= 256 ? 3 : 0);
-    const bool wide = variant == 3;
+    const bool wide = variant == 3 || variant == 7 || variant == 8;
     const int zc = fv->zchunk > 0 ? fv->zchunk : auto_zchunk(a.region.size, wide ? 128 : 32, wide ? 4 : 8);
     const bool exact = fv->mode == DGB_FV_EXACT;
     const int pb = fv->problem.id == 1 ? 1 : 0;
@@ -861,6 +861,9 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
         case 4: DGB_RING(6, 32, 16, 2) break;
         case 5: DGB_RING(4, 64, 8, 2) break;
         case 6: DGB_RING(12, 32, 8, 4) break;
+        case 7: DGB_RING(8, 128, 4, 2) break;
+        case 8: DGB_RING(10, 128, 4, 2) break;
+        case 9: DGB_RING(8, 64, 8, 2) break;
         case 99: if (pb) DGB_MARCH(DGB_FV_SEPARABLE, 1, 4, 128, 4) else DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4) break;   // the general kernel, for comparison
       }
 #undef DGB_RING
