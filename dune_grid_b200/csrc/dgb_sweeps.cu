@@ -2,6 +2,7 @@
 // One launch per shift component of the requested codim; a thread owns one entity (i0 fastest, so a warp
 // writes 32 consecutive entries of every output array: fully coalesced stores, no loads except the optional
 // tensor-product coordinate tables). All kernels are store-bandwidth bound: roofline = bytes written / HBM BW.
+#include <cstdlib>
 #include "dgb_internal.hh"
 #include "dgb_device.cuh"
 #include "dgb_geogrid.cuh"
@@ -46,91 +47,165 @@ static bool sweep_empty(const dgb_view& v, int comp, int kind) {
 // ---- K1: entities ------------------------------------------------------------------------------------
 struct EntityOut { uint32_t* index; uint8_t* ptype; int32_t* coord; double *lower, *upper, *center, *volume; uint32_t block, offset; };
 
+// A thread owns one column (i0, i2) and walks ENT_ROWS rows (i1); axes 0 and 2 (coordinates, table loads, periodic
+// shifts) are evaluated once per column, position and consecutive index advance by constant strides.
+static constexpr int ENT_ROWS = 8;
+
 __global__ void __launch_bounds__(BX) k_entities(const __grid_constant__ dgb_view v, const SweepGeom s, const EntityOut o) {
-  for (int row = 0; row < 8; ++row) {
-  int coord[3]; long long pos;
-  if (!sweep_entity<8>(v, s, row, coord, pos)) continue;
   const dgb_component& c = v.comp[s.comp];
-  if (o.index) o.index[pos] = entity_index(v, c, s.kind, coord)*o.block + o.offset;
-  if (o.ptype) o.ptype[pos] = partition_type(v, c, coord);
-  if (o.coord) for (int i = 0; i < v.dim; ++i) o.coord[i*s.n + pos] = coord[i];
-  if (o.lower || o.upper || o.center || o.volume) {
-    // yaspgridentity.hh:270-274 (no wrap for 0 < codim), :491-514 (codim 0 wraps), AxisAlignedCubeGeometry
-    double vol = 1.0;
-    for (int i = 0; i < v.dim; ++i) {
-      const bool ext = c.shift >> i & 1u;
-      double ll = vertex_coord(v, i, coord[i]);
-      double ur = ext ? vertex_coord(v, i, coord[i]+1) : ll;
-      if (c.codim == 0) { const double sh = periodic_shift(v, i, coord[i]); if (sh != 0.0) { ll += sh; ur += sh; } }
-      if (o.lower) o.lower[i*s.n + pos] = ll;
-      if (o.upper) o.upper[i*s.n + pos] = ur;
-      if (o.center) o.center[i*s.n + pos] = 0.5*(ll+ur);
-      if (ext) vol *= ur-ll;
+  const dgb_box& b = c.box[s.kind];
+  const int dim = v.dim;
+  const int i0 = blockIdx.x*BX + threadIdx.x, i1 = blockIdx.y*ENT_ROWS, i2 = blockIdx.z;
+  if (i0 >= b.size[0]) return;
+  int coord[3] = { b.origin[0]+i0, b.origin[1]+i1, dim > 2 ? b.origin[2]+i2 : 0 };
+  long long pos = s.base + ((long long)i2*b.size[1] + i1)*b.size[0] + i0;
+  uint32_t idx = entity_index(v, c, s.kind, coord)*o.block + o.offset;
+  const uint32_t didx = uint32_t(c.box[DGB_BOX_OVERLAPFRONT].size[0])*o.block;
+  const bool geo = o.lower || o.upper || o.center || o.volume;
+  double ll[3] = {0, 0, 0}, ur[3] = {0, 0, 0};
+  // yaspgridentity.hh:270-274 (no wrap for 0 < codim), :491-514 (codim 0 wraps), AxisAlignedCubeGeometry
+  auto axis = [&](int i) {
+    const bool ext = c.shift >> i & 1u;
+    ll[i] = vertex_coord(v, i, coord[i]);
+    ur[i] = ext ? vertex_coord(v, i, coord[i]+1) : ll[i];
+    if (c.codim == 0) { const double sh = periodic_shift(v, i, coord[i]); if (sh != 0.0) { ll[i] += sh; ur[i] += sh; } }
+  };
+  if (geo) { axis(0); if (dim > 2) axis(2); }
+  const int rows = min(ENT_ROWS, b.size[1]-i1);
+  for (int r = 0; r < rows; ++r) {
+    if (o.index) o.index[pos] = idx;
+    if (o.ptype) o.ptype[pos] = partition_type(v, c, coord);
+    if (o.coord) { long long p = pos; for (int i = 0; i < dim; ++i) { o.coord[p] = coord[i]; p += s.n; } }
+    if (geo) {
+      if (dim > 1) axis(1);
+      double vol = 1.0;
+      long long p = pos;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i < dim) {
+          if (o.lower) o.lower[p] = ll[i];
+          if (o.upper) o.upper[p] = ur[i];
+          if (o.center) o.center[p] = 0.5*(ll[i]+ur[i]);
+          if (c.shift >> i & 1u) vol *= ur[i]-ll[i];
+          p += s.n;
+        }
+      }
+      if (o.volume) o.volume[pos] = vol;
     }
-    if (o.volume) o.volume[pos] = vol;
-  }
+    pos += b.size[0]; idx += didx; ++coord[1];
   }
 }
 
-// ---- K2: sub-entity indices of cells -------------------------------------------------------------------
-__global__ void __launch_bounds__(BX) k_subindex(const __grid_constant__ dgb_view v, const SweepGeom s, const SubTable t,
-                                                 int cc, uint32_t block, uint32_t offset, uint32_t* out) {
-  for (int row = 0; row < 8; ++row) {
-  int coord[3]; long long pos;
-  if (!sweep_entity<8>(v, s, row, coord, pos)) continue;
+// ---- K1b / K2b: mapper indices, incremental form ------------------------------------------------------------------
+// The 4-byte-per-entity outputs are integer-issue-bound when every entity recomputes its position and index from its
+// coordinates (64-bit multiplies) - 16-byte stores did not help (measured). Here a thread owns one column (i0) and walks
+// IDX_ROWS consecutive rows (i1): position and consecutive index are computed once, then advance by constant strides
+// (row length of the swept box / of the enclosing overlapfront box), so an entity costs two adds and one coalesced store.
+static constexpr int IDX_ROWS = 32;
+
+__global__ void __launch_bounds__(BX) k_index_rows(const __grid_constant__ dgb_view v, const SweepGeom s, uint32_t block, uint32_t offset,
+                                                   uint32_t* __restrict__ out) {
+  const dgb_component& c = v.comp[s.comp];
+  const dgb_box& b = c.box[s.kind];
+  const int i0 = blockIdx.x*BX + threadIdx.x, i1 = blockIdx.y*IDX_ROWS;
+  if (i0 >= b.size[0]) return;
+  const int coord[3] = { b.origin[0]+i0, b.origin[1]+i1, v.dim > 2 ? b.origin[2]+int(blockIdx.z) : 0 };
+  uint32_t* p = out + (s.base + ((long long)blockIdx.z*b.size[1] + i1)*b.size[0] + i0);
+  uint32_t val = entity_index(v, c, s.kind, coord)*block + offset;
+  const uint32_t dval = uint32_t(c.box[DGB_BOX_OVERLAPFRONT].size[0])*block;     // next row of the overlapfront numbering
+  const int rows = min(IDX_ROWS, b.size[1]-i1), dp = b.size[0];
+  for (int r = 0; r < rows; ++r) { *p = val; p += dp; val += dval; }
+}
+
+__global__ void __launch_bounds__(BX) k_subindex_rows(const __grid_constant__ dgb_view v, const SweepGeom s, const SubTable t, int cc,
+                                                      uint32_t block, uint32_t offset, uint32_t* __restrict__ out) {
+  const dgb_box& b = v.comp[s.comp].box[s.kind];
+  const int i0 = blockIdx.x*BX + threadIdx.x, i1 = blockIdx.y*IDX_ROWS;
+  if (i0 >= b.size[0]) return;
+  const int coord[3] = { b.origin[0]+i0, b.origin[1]+i1, v.dim > 2 ? b.origin[2]+int(blockIdx.z) : 0 };
+  const long long pos = s.base + ((long long)blockIdx.z*b.size[1] + i1)*b.size[0] + i0;
+  const int rows = min(IDX_ROWS, b.size[1]-i1), dp = b.size[0];
   for (int i = 0; i < t.n; ++i) {
     // yaspgridentity.hh:764-776: coord += move, component = shiftmapping[shift], index in the overlapfront numbering
-    int sc[3];
-    for (int j = 0; j < 3; ++j) sc[j] = coord[j] + (t.move[i] >> j & 1);
     const dgb_component& c = v.comp[v.comp_begin[cc] + v.shiftmap[t.shift[i]]];
-    out[(long long)i*s.n + pos] = entity_index(v, c, DGB_BOX_OVERLAPFRONT, sc)*block + offset;
-  }
+    const int sc[3] = { coord[0] + (t.move[i] & 1), coord[1] + (t.move[i] >> 1 & 1), coord[2] + (t.move[i] >> 2 & 1) };
+    uint32_t val = entity_index(v, c, DGB_BOX_OVERLAPFRONT, sc)*block + offset;
+    const uint32_t dval = uint32_t(c.box[DGB_BOX_OVERLAPFRONT].size[0])*block;
+    uint32_t* p = out + ((long long)i*s.n + pos);
+    for (int r = 0; r < rows; ++r) { *p = val; p += dp; val += dval; }
   }
 }
 
 // ---- K3: intersections -------------------------------------------------------------------------------
 struct FaceOut { uint8_t *neighbor, *boundary; int32_t *outside, *bsi; double *center, *volume; };
 
+// A thread owns one column (i0, i2) and walks FACE_ROWS rows (i1): everything that belongs to axes 0 and 2 (vertex
+// coordinates incl. the tensor-product table loads, periodic shifts, neighbour / boundary flags) is computed once per
+// column; per row only axis 1 is refreshed and the output positions advance by the row length.
+static constexpr int FACE_ROWS_DEFAULT = 2;     // measured (256^3, 48 output streams): 1: 0.76 ms, 2: 0.74, 4: 1.06, 8: 1.29, 16: 0.89
+
+template<int FACE_ROWS>
 __global__ void __launch_bounds__(BX) k_intersections(const __grid_constant__ dgb_view v, const SweepGeom s, const FaceOut o) {
-  for (int row = 0; row < 1; ++row) {
-  int coord[3]; long long pos;
-  if (!sweep_entity<1>(v, s, row, coord, pos)) continue;
   const dgb_component& c = v.comp[0];
+  const dgb_box& b = c.box[s.kind];
   const dgb_box& of = c.box[DGB_BOX_OVERLAPFRONT];
-  const int inside = int(entity_index(v, c, s.kind, coord));
+  const int dim = v.dim;
+  const int i0 = blockIdx.x*BX + threadIdx.x, i1 = blockIdx.y*FACE_ROWS, i2 = blockIdx.z;
+  if (i0 >= b.size[0]) return;
+  int coord[3] = { b.origin[0]+i0, b.origin[1]+i1, dim > 2 ? b.origin[2]+i2 : 0 };
+  long long pos = s.base + ((long long)i2*b.size[1] + i1)*b.size[0] + i0;
+  int inside = int(entity_index(v, c, s.kind, coord));
   const bool geo = o.center || o.volume;
-  double ll[3], ur[3];
-  if (geo)
-    for (int i = 0; i < v.dim; ++i) {
+  double ll[3] = {0, 0, 0}, ur[3] = {0, 0, 0};
+  bool nb[6], bd[6];
+  auto axis = [&](int i) {
+    if (geo) {
       const double sh = periodic_shift(v, i, coord[i]);
       ll[i] = vertex_coord(v, i, coord[i]); ur[i] = vertex_coord(v, i, coord[i]+1);
       if (sh != 0.0) { ll[i] += sh; ur[i] += sh; }
     }
-  int stride = 1;
-  for (int dir = 0; dir < v.dim; ++dir) {
-    for (int side = 0; side < 2; ++side) {
-      const int k = 2*dir + side;
-      const bool nb = face_neighbor(v, coord, dir, side);
-      const bool bd = face_boundary(v, coord, dir, side);
-      if (o.neighbor) o.neighbor[k*s.n + pos] = nb;
-      if (o.boundary) o.boundary[k*s.n + pos] = bd;
-      // outside index = inside index -+ superincrement(dir) (yaspgridintersection.hh:40-57, ygrid.hh:362-366)
-      if (o.outside) o.outside[k*s.n + pos] = nb ? inside + (side ? stride : -stride) : -1;
-      if (o.bsi) o.bsi[k*s.n + pos] = bd ? boundary_segment_index(v, coord, dir, side) : -1;
-      if (geo) {
-        // yaspgridintersection.hh:232-269: the face is flat in `dir` at vertex coord+side, wrapped like the cell
-        double vol = 1.0;
-        for (int i = 0; i < v.dim; ++i) {
-          double lo = ll[i], hi = ur[i];
-          if (i == dir) { lo = side ? ur[i] : ll[i]; hi = lo; }
-          else vol *= hi-lo;
-          if (o.center) o.center[((long long)k*v.dim + i)*s.n + pos] = 0.5*(lo+hi);
+    nb[2*i] = face_neighbor(v, coord, i, 0); nb[2*i+1] = face_neighbor(v, coord, i, 1);
+    bd[2*i] = face_boundary(v, coord, i, 0); bd[2*i+1] = face_boundary(v, coord, i, 1);
+  };
+  axis(0);
+  if (dim > 2) axis(2);
+  int stride[3] = { 1, of.size[0], of.size[0]*of.size[1] };
+  const int rows = min(FACE_ROWS, b.size[1]-i1);
+  for (int r = 0; r < rows; ++r) {
+    if (dim > 1) axis(1);
+    long long pf = pos;                       // position in the one-value-per-face arrays (face-major)
+    long long pc = pos;                       // position in the face centre array ((face, axis)-major)
+#pragma unroll
+    for (int dir = 0; dir < 3; ++dir) {
+      if (dir < dim) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const int k = 2*dir + side;
+          if (o.neighbor) o.neighbor[pf] = nb[k];
+          if (o.boundary) o.boundary[pf] = bd[k];
+          // outside index = inside index -+ superincrement(dir) (yaspgridintersection.hh:40-57, ygrid.hh:362-366)
+          if (o.outside) o.outside[pf] = nb[k] ? inside + (side ? stride[dir] : -stride[dir]) : -1;
+          if (o.bsi) o.bsi[pf] = bd[k] ? boundary_segment_index(v, coord, dir, side) : -1;
+          if (geo) {
+            // yaspgridintersection.hh:232-269: the face is flat in `dir` at vertex coord+side, wrapped like the cell
+            double vol = 1.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              if (i < dim) {
+                double lo = ll[i], hi = ur[i];
+                if (i == dir) { lo = side ? ur[i] : ll[i]; hi = lo; }
+                else vol *= hi-lo;
+                if (o.center) o.center[pc] = 0.5*(lo+hi);
+                pc += s.n;
+              }
+            }
+            if (o.volume) o.volume[pf] = vol;
+          }
+          pf += s.n;
         }
-        if (o.volume) o.volume[k*s.n + pos] = vol;
       }
     }
-    stride *= of.size[dir];
-  }
+    pos += b.size[0]; inside += of.size[0]; ++coord[1];
   }
 }
 
@@ -299,8 +374,8 @@ int dgb_mapper_index(const dgb_view* v, const dgb_mapper* m, int codim, int pity
   if (codim < 0 || codim > v->dim) return fail(DGB_EARG, "bad codim");
   if (m->offset[codim] == DGB_INVALID_OFFSET) return fail(DGB_EARG, "codim not contained in the mapper layout");
   EntityOut o{}; o.index = d_out; o.block = m->block[codim]; o.offset = m->offset[codim];
-  return for_each_component(*v, codim, pitype, 8, [&](const SweepGeom& s, dim3 grid) {
-    k_entities<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o);
+  return for_each_component(*v, codim, pitype, IDX_ROWS, [&](const SweepGeom& s, dim3 grid) {
+    k_index_rows<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o.block, o.offset, d_out);
   });
 }
 
@@ -310,8 +385,8 @@ int dgb_mapper_subindex(const dgb_view* v, const dgb_mapper* m, int cc, int pity
   SubTable t; t.n = sub_entities(v->dim, cc);
   for (int i = 0; i < t.n; ++i) { t.shift[i] = (unsigned char)sub_shift(v->dim, i, cc); t.move[i] = (unsigned char)sub_move(v->dim, i, cc); }
   const uint32_t block = m->block[cc], offset = m->offset[cc];
-  return for_each_component(*v, 0, pitype, 8, [&](const SweepGeom& s, dim3 grid) {
-    k_subindex<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, t, cc, block, offset, d_out);
+  return for_each_component(*v, 0, pitype, IDX_ROWS, [&](const SweepGeom& s, dim3 grid) {
+    k_subindex_rows<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, t, cc, block, offset, d_out);
   });
 }
 
@@ -319,7 +394,7 @@ int dgb_elements_materialize(const dgb_view* v, int codim, int pitype, uint32_t*
                              double* d_lower, double* d_upper, double* d_center, double* d_volume, void* stream) {
   if ((d_lower || d_upper || d_center || d_volume)) if (int rc = check_tensor(*v)) return rc;
   EntityOut o{d_index, d_ptype, d_coord, d_lower, d_upper, d_center, d_volume, 1u, 0u};
-  return for_each_component(*v, codim, pitype, 8, [&](const SweepGeom& s, dim3 grid) {
+  return for_each_component(*v, codim, pitype, ENT_ROWS, [&](const SweepGeom& s, dim3 grid) {
     k_entities<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o);
   });
 }
@@ -328,8 +403,15 @@ int dgb_intersections_materialize(const dgb_view* v, int pitype, uint8_t* d_neig
                                   int32_t* d_bsi, double* d_center, double* d_volume, void* stream) {
   if (d_center || d_volume) if (int rc = check_tensor(*v)) return rc;
   FaceOut o{d_neighbor, d_boundary, d_outside, d_bsi, d_center, d_volume};
-  return for_each_component(*v, 0, pitype, 1, [&](const SweepGeom& s, dim3 grid) {
-    k_intersections<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o);
+  static const int rows = [] { const char* e = getenv("DGB_FACE_ROWS"); const int r = e ? atoi(e) : FACE_ROWS_DEFAULT; return r; }();
+  return for_each_component(*v, 0, pitype, rows, [&](const SweepGeom& s, dim3 grid) {
+    switch (rows) {                                   // rows walked per thread (tuning knob DGB_FACE_ROWS)
+      case 1: k_intersections<1><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o); break;
+      case 2: k_intersections<2><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o); break;
+      case 8: k_intersections<8><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o); break;
+      case 16: k_intersections<16><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o); break;
+      default: k_intersections<4><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o); break;
+    }
   });
 }
 
