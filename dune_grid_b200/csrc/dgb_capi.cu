@@ -1,6 +1,9 @@
 // dgb_capi.cu — grid life cycle, views, mapper set-up and host-side queries of the C ABI (include/dgb.h).
 // Host arithmetic only (dgb_host.hh); the device is touched solely to upload tensor-product coordinates.
+#include <cstdio>
 #include <cstring>
+#include <fstream>
+#include <sstream>
 #include "dgb_internal.hh"
 
 namespace dgb {
@@ -145,6 +148,130 @@ int dgb_grid_create(const dgb_grid_spec* spec, int rank, int nranks, dgb_grid** 
   });
 }
 
+// BackupRestoreFacility::backup (yaspgrid/backuprestore.hh:105-128, 222-246). std::ostream formatting = the reference's.
+int dgb_grid_backup(const dgb_grid* g, char* text, int64_t cap, int64_t* needed) {
+  return guarded([&] {
+    if (!g || !needed) throw ArgError("null argument");
+    const RankGrid& me = g->me;
+    const int dim = me.spec.dim;
+    std::ostringstream s;
+    s << "YaspGrid BackupRestore Format Version: " << 2 << std::endl;
+    s << "Torus structure: ";
+    for (int i = 0; i < dim; ++i) s << me.torus.dims[i] << " ";
+    s << std::endl << "Refinement level: " << int(me.levels.size())-1 << std::endl;
+    s << "Periodicity: ";
+    for (int i = 0; i < dim; ++i) s << ((me.spec.periodic >> i & 1u) ? "1 " : "0 ");
+    s << std::endl << "Overlap: " << me.levels[0].b.overlap << std::endl;
+    s << "KeepPhysicalOverlap: ";
+    for (std::size_t l = 1; l < me.levels.size(); ++l) s << (me.levels[l].keep ? "1" : "0") << " ";
+    s << std::endl;
+    s << "Coarse Size: ";
+    for (int i = 0; i < dim; ++i) s << me.N0[i] << " ";
+    s << std::endl;
+    const Coords& cc = me.levels[0].coords;
+    if (cc.mode != DGB_COORD_TENSORPRODUCT) {
+      s << "Meshsize: ";
+      for (int i = 0; i < dim; ++i) s << cc.h[i] << " ";
+      s << std::endl;
+      if (cc.mode == DGB_COORD_EQUIDISTANT_OFFSET) {               // MaybeHaveOrigin::writeOrigin :51-57
+        s << "Origin: ";
+        for (int i = 0; i < dim; ++i) s << cc.origin[i] << " ";
+        s << std::endl;
+      }
+    } else {                                                        // TensorProductCoordinates::print, coordinates.hh:347-356
+      s << "Printing TensorProduct Coordinate information:" << std::endl;
+      for (int i = 0; i < dim; ++i) {
+        s << "Direction " << i << ": " << cc.c[i].size() << " coordinates" << std::endl;
+        for (std::size_t j = 0; j < cc.c[i].size(); ++j) s << cc.c[i][j] << std::endl;
+      }
+    }
+    const std::string out = s.str();
+    *needed = int64_t(out.size()) + 1;
+    if (text && cap >= *needed) std::memcpy(text, out.c_str(), out.size()+1);
+    return DGB_OK;
+  });
+}
+
+// BackupRestoreFacility::restore (yaspgrid/backuprestore.hh:146-218, 268-346): same token-skipping reads
+int dgb_grid_restore(const char* text, int coord_mode, int rank, int nranks, dgb_grid** out) {
+  return guarded([&] {
+    if (!text || !out) throw ArgError("null argument");
+    if (coord_mode < 0 || coord_mode > 2) throw ArgError("unknown coordinate mode");
+    if (nranks < 1 || rank < 0 || rank >= nranks) throw ArgError("bad rank/nranks");
+    std::istringstream stream(text);
+    std::string input;
+    int version = 0;
+    stream >> input >> input >> input >> input;
+    stream >> version;
+    if (!stream || version != 2) throw ArgError("Your YaspGrid backup file is written in an outdated format!");
+    // the reference is a template on dim; here the dimension is the number of integers on the torus line
+    std::string line;
+    std::getline(stream, line);                       // rest of line 1
+    std::getline(stream, line);                       // "Torus structure: d0 d1 [d2] "
+    std::vector<int> torus_dims;
+    { std::istringstream ls(line); ls >> input >> input; int v; while (ls >> v) torus_dims.push_back(v); }
+    const int dim = int(torus_dims.size());
+    if (dim < 2 || dim > 3) throw ArgError("restore: dim must be 2 or 3");
+    int refinement = 0;
+    stream >> input >> input;
+    stream >> refinement;
+    unsigned periodic = 0;
+    bool b = false;
+    stream >> input;
+    for (int i = 0; i < dim; ++i) { stream >> b; if (b) periodic |= 1u << i; }
+    int overlap = 0;
+    stream >> input;
+    stream >> overlap;
+    std::vector<bool> keep(refinement > 0 ? refinement : 0);
+    stream >> input;
+    for (int i = 0; i < refinement; ++i) { stream >> b; keep[i] = b; }
+    dgb_grid_spec spec; std::memset(&spec, 0, sizeof(spec));
+    spec.dim = dim; spec.coord_mode = coord_mode; spec.periodic = periodic; spec.overlap = overlap;
+    spec.partitioner = DGB_PART_FIXED;
+    for (int i = 0; i < 3; ++i) { spec.fixed_dims[i] = i < dim ? torus_dims[i] : 1; spec.N[i] = 1; }
+    stream >> input >> input;
+    for (int i = 0; i < dim; ++i) stream >> spec.N[i];
+    std::vector<double> local[3];
+    if (coord_mode != DGB_COORD_TENSORPRODUCT) {
+      double h[3] = {0,0,0}, origin[3] = {0,0,0};
+      stream >> input;
+      for (int i = 0; i < dim; ++i) stream >> h[i];
+      if (coord_mode == DGB_COORD_EQUIDISTANT_OFFSET) { stream >> input; for (int i = 0; i < dim; ++i) stream >> origin[i]; }
+      if (!stream) throw ArgError("restore: truncated backup text");
+      for (int i = 0; i < dim; ++i) {
+        double length = h[i]; length *= spec.N[i];                   // :193-195
+        if (coord_mode == DGB_COORD_EQUIDISTANT) spec.upper[i] = length;
+        else { spec.lower[i] = origin[i]; double ur = origin[i]; ur += length; spec.upper[i] = ur; }     // :74-76
+      }
+    } else {
+      stream >> input >> input >> input >> input;
+      for (int d = 0; d < dim; ++d) {
+        stream >> input >> input;
+        int size = 0;
+        stream >> size;
+        stream >> input;
+        if (!stream || size < 0) throw ArgError("restore: truncated backup text");
+        local[d].resize(size);
+        for (int i = 0; i < size; ++i) stream >> local[d][i];
+      }
+      if (!stream) throw ArgError("restore: truncated backup text");
+    }
+    std::unique_ptr<dgb_grid> g(new dgb_grid);
+    g->me.construct(spec, rank, nranks, nullptr, false, coord_mode == DGB_COORD_TENSORPRODUCT ? local : nullptr);
+    g->all.resize(nranks);
+    for (int r = 0; r < nranks; ++r) g->all[r].construct(spec, r, nranks, &g->me.torus, true);
+    refresh_boundary_segments(g.get());
+    for (int i = 0; i < refinement; ++i) {                           // :206-210
+      g->keepOverlap = keep[i];
+      g->me.refine_once(g->keepOverlap, false);
+      for (auto& o : g->all) o.refine_once(g->keepOverlap, true);
+    }
+    sync_dev_coords(g.get());
+    *out = g.release();
+    return DGB_OK;
+  });
+}
+
 int dgb_grid_destroy(dgb_grid* g) {
   if (!g) return DGB_OK;
   free_dev_coords(g);
@@ -228,6 +355,69 @@ int dgb_mapper_init(const dgb_view* v, const uint32_t* block, dgb_mapper* m) {
   return DGB_OK;
 }
 int dgb_mapper_size(const dgb_mapper* m, int64_t* n) { *n = m->size; return DGB_OK; }
+
+// ---- field checkpoint ----------------------------------------------------------------------------------------------
+static std::string field_header(const dgb_grid* g, int level, const dgb_mapper* m, int item_size, const std::string& gridText) {
+  std::ostringstream h;
+  h << "dune-grid-b200 field checkpoint v1 rank " << g->me.rank << " nranks " << g->me.nranks << " level " << level
+    << " mapper " << m->block[0] << " " << m->block[1] << " " << m->block[2] << " " << m->block[3] << " size " << m->size
+    << " item " << item_size << " gridtext " << gridText.size() << "\n";
+  return h.str();
+}
+static int grid_text(const dgb_grid* g, std::string& t) {
+  int64_t need = 0;
+  if (int rc = dgb_grid_backup(g, nullptr, 0, &need)) return rc;
+  t.assign(std::size_t(need), '\0');
+  if (int rc = dgb_grid_backup(g, &t[0], need, &need)) return rc;
+  t.resize(std::size_t(need)-1);
+  return DGB_OK;
+}
+
+int dgb_field_backup(const dgb_grid* g, int level, const dgb_mapper* m, const double* d_field, int item_size, const char* filename, void* stream) {
+  return guarded([&]() -> int {
+    if (!g || !m || !d_field || !filename || item_size < 1) throw ArgError("bad argument");
+    if (level < 0 || level >= int(g->me.levels.size())) throw RangeError("level out of range");
+    if (int rc = require_device()) return rc;
+    std::string gt; if (int rc = grid_text(g, gt)) return rc;
+    const std::size_t n = std::size_t(m->size)*item_size;
+    std::vector<double> host(n);
+    DGB_CUDA(cudaMemcpyAsync(host.data(), d_field, n*sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    DGB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    const std::string path = std::string(filename) + "." + std::to_string(g->me.rank);
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw ArgError("field backup: cannot open " + path);
+    const std::string h = field_header(g, level, m, item_size, gt);
+    f.write(h.data(), std::streamsize(h.size()));
+    f.write(gt.data(), std::streamsize(gt.size()));
+    f.write(reinterpret_cast<const char*>(host.data()), std::streamsize(n*sizeof(double)));
+    if (!f) throw ArgError("field backup: write failed on " + path);
+    return DGB_OK;
+  });
+}
+
+int dgb_field_restore(const dgb_grid* g, int level, const dgb_mapper* m, double* d_field, int item_size, const char* filename, void* stream) {
+  return guarded([&]() -> int {
+    if (!g || !m || !d_field || !filename || item_size < 1) throw ArgError("bad argument");
+    if (level < 0 || level >= int(g->me.levels.size())) throw RangeError("level out of range");
+    if (int rc = require_device()) return rc;
+    std::string gt; if (int rc = grid_text(g, gt)) return rc;
+    const std::string path = std::string(filename) + "." + std::to_string(g->me.rank);
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw ArgError("field restore: cannot open " + path);
+    std::string h; std::getline(f, h); h += "\n";
+    if (h != field_header(g, level, m, item_size, gt)) throw ArgError("field restore: " + path + " was written for another rank, level, mapper or item size");
+    std::string stored(gt.size(), '\0');
+    f.read(&stored[0], std::streamsize(stored.size()));
+    if (!f || stored != gt) throw ArgError("field restore: " + path + " belongs to a different grid");
+    const std::size_t n = std::size_t(m->size)*item_size;
+    std::vector<double> host(n);
+    f.read(reinterpret_cast<char*>(host.data()), std::streamsize(n*sizeof(double)));
+    if (!f) throw ArgError("field restore: " + path + " is truncated");
+    DGB_CUDA(cudaMemcpyAsync(d_field, host.data(), n*sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    DGB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return DGB_OK;
+  });
+}
 
 int dgb_comm_last_bytes(const dgb_grid* g, int64_t* bytes) { *bytes = g->lastBytesSent; return DGB_OK; }
 

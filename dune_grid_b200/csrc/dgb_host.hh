@@ -284,14 +284,23 @@ struct RankGrid {
   std::vector<Level> levels;
   std::vector<std::vector<double>> tensor_in;     // host copy of the user's tensor coordinates
 
-  void construct(const dgb_grid_spec& s, int rk, int np, const Torus* shared, bool ints_only) {
+  // `local` (tensor mode, BackupRestoreFacility::restore only): the rank's own level-0 coordinates incl. overlap, as the
+  // private constructor yaspgrid.hh:1156-1197 takes them; the global coordinate arrays are then not known.
+  void construct(const dgb_grid_spec& s, int rk, int np, const Torus* shared, bool ints_only,
+                 const std::vector<double>* local = nullptr) {
     spec = s; rank = rk; nranks = np;
     const int dim = s.dim;
     if (dim < 2 || dim > 3) throw ArgError("dim must be 2 or 3");
     if (s.overlap < 0) throw ArgError("negative overlap");
     for (int i = 0; i < 3; ++i) N0[i] = i < dim ? s.N[i] : 1;
     for (int i = 0; i < dim; ++i) if (N0[i] < 1) throw ArgError("grid size must be positive");
-    if (s.coord_mode == DGB_COORD_TENSORPRODUCT && !ints_only) {
+    if (s.coord_mode == DGB_COORD_TENSORPRODUCT && !ints_only && local) {
+      for (int i = 0; i < dim; ++i) {
+        if (local[i].size() <= 1) throw GridError("Setup of a tensorproduct grid requires monotonous sequences of coordinates.");
+        for (std::size_t j = 1; j < local[i].size(); ++j)
+          if (local[i][j] < local[i][j-1]) throw GridError("Setup of a tensorproduct grid requires monotonous sequences of coordinates.");
+      }
+    } else if (s.coord_mode == DGB_COORD_TENSORPRODUCT && !ints_only) {
       tensor_in.resize(dim);
       for (int i = 0; i < dim; ++i) {
         if (!s.tensor[i]) throw ArgError("tensor coordinates missing");
@@ -360,7 +369,13 @@ struct RankGrid {
         if (addLow) { cnt += ov; off -= ov; }
         b.sStored[i] = cnt-1;
         cc.offset[i] = off;
-        if (!ints_only) {
+        if (!ints_only && local) {
+          // yaspgrid.hh:1172-1190: _L from the LOCAL coordinates, offset = o_interior (- overlap if periodic or o_interior > 0)
+          if (int(local[i].size()) != cnt) throw GridError("restore: the number of coordinates does not match the partition of this rank");
+          L[i] = local[i].back() - local[i].front();
+          cc.offset[i] = oI[i] - ((per || oI[i] > 0) ? ov : 0);
+          cc.c[i] = local[i];
+        } else if (!ints_only) {
           const std::vector<double>& in = tensor_in[i];
           L[i] = in[N0[i]] - in[0];
           std::vector<double> nc(in.begin()+begin, in.begin()+end);

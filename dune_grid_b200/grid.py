@@ -81,6 +81,45 @@ class YaspGrid:
         except Exception:
             pass
 
+    # ---- Dune::BackupRestoreFacility<YaspGrid> (dune/grid/yaspgrid/backuprestore.hh) ----
+    def backup(self, filename=None):
+        """the text BackupRestoreFacility::backup writes; with a filename also written like the reference does: one file
+        from rank 0 (equidistant containers, :91-104) or `filename + rank` from every rank (tensor product, :208-220)"""
+        need = C.c_int64(0)
+        check(lib.dgb_grid_backup(self.h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        check(lib.dgb_grid_backup(self.h, buf, need.value, C.byref(need)))
+        text = buf.value.decode()
+        if filename is not None:
+            if self.spec.coord_mode == 2:
+                with open(f"{filename}{self.rank}", "w") as f:
+                    f.write(text)
+            elif self.rank == 0:
+                with open(filename, "w") as f:
+                    f.write(text)
+        return text
+
+    @classmethod
+    def restore(cls, text_or_filename, coordinates="equidistant", rank=0, nranks=1, comm=None, is_file=False):
+        """BackupRestoreFacility::restore (:131-218, :249-346); tensor-product files are per rank (`filename + rank`)"""
+        mode = {"equidistant": 0, "equidistantoffset": 1, "tensorproduct": 2}[coordinates]
+        text = text_or_filename
+        if is_file:
+            with open(f"{text_or_filename}{rank}" if mode == 2 else text_or_filename) as f:
+                text = f.read()
+        self = cls.__new__(cls)
+        self._keep = []
+        self.h = C.c_void_p()
+        check(lib.dgb_grid_restore(text.encode(), mode, rank, nranks, C.byref(self.h)))
+        self.rank, self.nranks, self.comm = rank, nranks, comm
+        s = capi.GridSpec()
+        s.coord_mode = mode
+        self.spec = s
+        v = capi.View()
+        check(lib.dgb_view_level(self.h, 0, C.byref(v)))
+        self.dim = s.dim = v.dim
+        return self
+
     def refineOptions(self, keepPhysicalOverlap: bool):
         check(lib.dgb_grid_refine_options(self.h, int(keepPhysicalOverlap)))
 
@@ -340,6 +379,18 @@ class MultipleCodimMultipleGeomTypeMapper:
 
     def communicate(self, iftype, direction, op, *arrays):
         self.gv.communicate(self, arrays, iftype, direction, op)
+
+    def backupField(self, array, filename, item_size=1):
+        """restart checkpoint of a device array indexed by this mapper: file `filename.rank` (header, grid backup text, data)"""
+        _require_cuda()
+        check(lib.dgb_field_backup(self.gv.grid.h, self.gv.v.level, C.byref(self.m), _ptr(array), item_size,
+                                   str(filename).encode(), _stream()))
+
+    def restoreField(self, array, filename, item_size=1):
+        """inverse of backupField; refuses files written for another grid, rank, level, mapper or item size"""
+        _require_cuda()
+        check(lib.dgb_field_restore(self.gv.grid.h, self.gv.v.level, C.byref(self.m), _ptr(array), item_size,
+                                    str(filename).encode(), _stream()))
 
 
 def mcmgElementLayout(dim):

@@ -71,6 +71,14 @@ int dgb_grid_max_level(const dgb_grid* g, int* maxLevel);
 int dgb_grid_torus_dims(const dgb_grid* g, int32_t* dims);             /* torus.hh:112 */
 int dgb_grid_num_boundary_segments(const dgb_grid* g, int64_t* n);     /* yaspgrid.hh:1456 */
 int dgb_grid_domain_size(const dgb_grid* g, double* L);                /* yaspgrid.hh:1462 */
+/* BackupRestoreFacility<YaspGrid<dim,Coordinates>> (yaspgrid/backuprestore.hh, format version 2).
+ * dgb_grid_backup: the text backup(grid, std::ostream&) writes (:105-128 equidistant / offset, :222-246 tensor product -
+ * there every rank writes its own file holding its LOCAL coordinates); *needed = length incl. the terminating NUL, the
+ * text is copied when cap >= *needed. Numbers are formatted like the reference's operator<< (6 significant digits).
+ * dgb_grid_restore: restore(std::istream&, comm) (:146-218, :268-346): FixedSizePartitioning with the stored torus,
+ * then one refineOptions(keep_l) + globalRefine(1) per stored level. `text` is this rank's file. */
+int dgb_grid_backup(const dgb_grid* g, char* text, int64_t cap, int64_t* needed);
+int dgb_grid_restore(const char* text, int coord_mode, int rank, int nranks, dgb_grid** out);
 /* standalone processor-grid choice, partitioning.hh:56-117 */
 int dgb_partition(int dim, const int32_t* N, int P, int overlap, int partitioner, const int32_t* fixed, int32_t* dims_out);
 
@@ -127,6 +135,15 @@ int dgb_mapper_size(const dgb_mapper* m, int64_t* n);
 int dgb_mapper_index(const dgb_view* v, const dgb_mapper* m, int codim, int pitype, uint32_t* d_out, void* stream);
 /* mapper.subIndex(e,i,cc) for every cell of the partition -> d_out[i*n + cell] (sub-entity major) */
 int dgb_mapper_subindex(const dgb_view* v, const dgb_mapper* m, int cc, int pitype, uint32_t* d_out, void* stream);
+
+/* Field checkpoint for restarts (not in the reference, which leaves user data to the user; the grid part of a restart is
+ * dgb_grid_backup/restore above): file `filename`.`rank` = one header line, this rank's grid backup text, then the raw
+ * doubles of a DEVICE array indexed by `mapper` (item_size doubles per index). Restore checks that header and grid text
+ * match the grid and mapper it is given (DGB_EARG otherwise) and copies the data back to the device. Both synchronise. */
+int dgb_field_backup(const dgb_grid* g, int level, const dgb_mapper* m, const double* d_field, int item_size,
+                     const char* filename, void* stream);
+int dgb_field_restore(const dgb_grid* g, int level, const dgb_mapper* m, double* d_field, int item_size,
+                      const char* filename, void* stream);
 
 /* ---- element sweep (rangegenerators.hh:881 elements(gv); yaspgridentity.hh:270-305,480-514; AxisAlignedCubeGeometry).
  *      All outputs are optional (NULL = skip), in iteration order of the partition; vector quantities are stored

@@ -27,7 +27,11 @@
 #include <array>
 #include <bitset>
 #include <cstdint>
+#include <fstream>
+#include <iostream>
+#include <iterator>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -258,6 +262,9 @@ public:
   }
   BulkYaspGrid(const BulkYaspGrid&) = delete;
   ~BulkYaspGrid() { if (g_) dgb_grid_destroy(g_); }
+  // adopts a grid built by the C ABI (BackupRestoreFacility::restore)
+  struct Adopt {};
+  BulkYaspGrid(Adopt, dgb_grid* g, const Communicator* comm) : g_(g), comm_(comm ? comm->handle() : nullptr) {}
 
   dgb_grid* handle() const { return g_; }
   dgb_comm* comm() const { return comm_; }
@@ -269,6 +276,40 @@ public:
   std::array<int,dim> torusDims() const { std::int32_t d[3]; check(dgb_grid_torus_dims(g_, d)); std::array<int,dim> r{}; for (int i = 0; i < dim; ++i) r[i] = d[i]; return r; }
   BulkGridView<dim> leafGridView() const { dgb_view v; check(dgb_view_leaf(g_, &v)); return BulkGridView<dim>(this, v); }
   BulkGridView<dim> levelGridView(int level) const { dgb_view v; check(dgb_view_level(g_, level, &v)); return BulkGridView<dim>(this, v); }
+};
+
+// Dune::BackupRestoreFacility<YaspGrid<dim,Coordinates>> (dune/grid/yaspgrid/backuprestore.hh): same static members and the
+// same file format / file naming. The coordinate container is a run-time property here, so restore takes DGB_COORD_*.
+template<class Grid> struct BackupRestoreFacility;
+template<int dim>
+struct BackupRestoreFacility<BulkYaspGrid<dim>> {
+  typedef BulkYaspGrid<dim> Grid;
+  static std::string text(const Grid& grid) {
+    std::int64_t need = 0; check(dgb_grid_backup(grid.handle(), nullptr, 0, &need));
+    std::string t(std::size_t(need), '\0'); check(dgb_grid_backup(grid.handle(), &t[0], need, &need)); t.resize(std::size_t(need)-1);
+    return t;
+  }
+  static void backup(const Grid& grid, std::ostream& stream) { stream << text(grid); }
+  // :91-104 one file written by rank 0; tensor product :208-220 one file per rank, named filename + rank
+  static void backup(const Grid& grid, const std::string& filename) {
+    const dgb_view v = grid.leafGridView().descriptor();
+    const bool tensor = v.coord_mode == DGB_COORD_TENSORPRODUCT;
+    if (!tensor && v.rank != 0) return;
+    std::ofstream file(tensor ? filename + std::to_string(v.rank) : filename);
+    if (file) backup(grid, file);
+    else std::cerr << "ERROR: BackupRestoreFacility::backup: couldn't open file `" << filename << "'" << std::endl;
+  }
+  static Grid* restore(std::istream& stream, int coordMode, int rank = 0, int nranks = 1, const Communicator* comm = nullptr) {
+    const std::string t((std::istreambuf_iterator<char>(stream)), std::istreambuf_iterator<char>());
+    dgb_grid* g = nullptr; check(dgb_grid_restore(t.c_str(), coordMode, rank, nranks, &g));
+    return new Grid(typename Grid::Adopt(), g, comm);
+  }
+  static Grid* restore(const std::string& filename, int coordMode, int rank = 0, int nranks = 1, const Communicator* comm = nullptr) {
+    std::ifstream file(coordMode == DGB_COORD_TENSORPRODUCT ? filename + std::to_string(rank) : filename);
+    if (file) return restore(file, coordMode, rank, nranks, comm);
+    std::cerr << "ERROR: BackupRestoreFacility::restore: couldn't open file `" << filename << "'" << std::endl;
+    return nullptr;
+  }
 };
 
 template<int dim>

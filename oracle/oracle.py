@@ -105,6 +105,8 @@ class OracleLib:
             "orc_geometry_eval": (i64, [vp, i32, i32, i32, i32, pd, pd, pd, pd]),
             "orc_geogrid_eval": (i64, [vp, i32, i32, i32, i32, pd, i32, pd, pd, pd, pd, pd, pd]),
             "orc_communicate": (i64, [vp, i32, pu32, i32, i32, i32, i32, ppd, pi]),
+            "orc_backup": (i32, [vp, i32, C.c_char_p, i32]),
+            "orc_restore": (vp, [i32, i32, i32, C.POINTER(C.c_char_p)]),
             "orc_fv_init": (i32, [vp, i32, i32, i32, pd, pd]),
             "orc_fv_step": (dbl, [vp, i32, i32, pd, ppd, ppd]),
             "orc_fv_run": (dbl, [vp, i32, i32, pd, ppd, i32, pd]),
@@ -139,6 +141,16 @@ class OracleLib:
     def world(self, spec: Spec, nranks: int = 1):
         return World(self, spec, nranks)
 
+    def restore(self, dim, coord_mode, texts):
+        """a world whose rank r is restored by BackupRestoreFacility::restore from texts[r]"""
+        arr = (C.c_char_p * len(texts))(*[t.encode() for t in texts])
+        h = self.lib.orc_restore(dim, coord_mode, len(texts), arr)
+        if not h:
+            raise OracleError(self.err())
+        w = World.__new__(World)
+        w.o, w.spec, w.P, w.dim, w.h, w.L = self, None, len(texts), dim, h, self.lib
+        return w
+
 
 def _block(block):
     b = list(block) + [0] * (4 - len(block))
@@ -164,6 +176,13 @@ class World:
             self.close()
         except Exception:
             pass
+
+    def backup(self, rank):
+        """the text BackupRestoreFacility::backup(grid, stream) writes on `rank`"""
+        n = self._chk(self.L.orc_backup(self.h, rank, None, 0))
+        buf = C.create_string_buffer(n + 1)
+        self._chk(self.L.orc_backup(self.h, rank, buf, n + 1))
+        return buf.value.decode()
 
     def _chk(self, rc):
         if rc < 0:

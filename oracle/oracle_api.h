@@ -103,6 +103,12 @@ double orc_fv_step(void* w, int level, int problem, const double* params, double
 /* the same step repeated `steps` times with rank threads kept alive; returns seconds of wall time for the loop */
 double orc_fv_run(void* w, int level, int problem, const double* params, double** c, int steps, double* dt_last);
 
+/* (f3) BackupRestoreFacility<YaspGrid<dim,CC>> (yaspgrid/backuprestore.hh). orc_backup: the text backup(grid, std::ostream&)
+ * writes for `rank` (:105-128, :222-246); returns its length without the NUL (copied when it fits into cap) or -1.
+ * orc_restore: a world whose rank r is built by restore(std::istream&, comm) (:146-218, :268-346) from texts[r]. */
+int   orc_backup(void* w, int rank, char* out, int cap);
+void* orc_restore(int dim, int coord_mode, int nranks, const char* const* texts);
+
 #ifdef __cplusplus
 }
 #endif

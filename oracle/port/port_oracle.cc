@@ -20,6 +20,7 @@
 #include <deque>
 #include <limits>
 #include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -789,6 +790,81 @@ int64_t orc_geogrid_eval(void* w, int rank, int level, int pitype, int deformati
 int64_t orc_communicate(void* w, int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* item_sizes) {
   return guarded(int64_t(-1), [&]() -> int64_t { return W(w)->communicate(level, block, iftype, dir, op, narrays, arrays, item_sizes); });
 }
+// (f3) BackupRestoreFacility::backup, yaspgrid/backuprestore.hh:105-128 (equidistant, offset), :222-246 (tensor product:
+// TensorProductCoordinates::print of the rank's level-0 container, coordinates.hh:347-356); default ostream formatting
+int orc_backup(void* w, int rank, char* out, int cap) {
+  return guarded(-1, [&] {
+    World& W_ = *W(w); const RankGrid& rg = W_.ranks[rank]; const int dim = W_.dim;
+    std::ostringstream s;
+    s << "YaspGrid BackupRestore Format Version: " << 2 << std::endl;
+    s << "Torus structure: ";
+    for (int i = 0; i < dim; ++i) s << rg.torus.dims[i] << " ";
+    s << std::endl << "Refinement level: " << int(rg.levels.size())-1 << std::endl;
+    s << "Periodicity: ";
+    for (int i = 0; i < dim; ++i) s << (W_.per(i) ? "1 " : "0 ");
+    s << std::endl << "Overlap: " << rg.levels[0].overlap << std::endl;
+    s << "KeepPhysicalOverlap: ";
+    for (std::size_t l = 1; l < rg.levels.size(); ++l) s << (W_.sp.keep ? "1" : "0") << " ";
+    s << std::endl;
+    s << "Coarse Size: ";
+    for (int i = 0; i < dim; ++i) s << W_.sp.N[i] << " ";
+    s << std::endl;
+    const Coordinates& cc = rg.levels[0].coords;
+    if (cc.mode != 2) {
+      s << "Meshsize: ";
+      for (int i = 0; i < dim; ++i) s << cc.h[i] << " ";
+      s << std::endl;
+      if (cc.mode == 1) { s << "Origin: "; for (int i = 0; i < dim; ++i) s << cc.origin[i] << " "; s << std::endl; }
+    } else {
+      s << "Printing TensorProduct Coordinate information:" << std::endl;
+      for (int i = 0; i < dim; ++i) {
+        s << "Direction " << i << ": " << cc.c[i].size() << " coordinates" << std::endl;
+        for (std::size_t j = 0; j < cc.c[i].size(); ++j) s << cc.c[i][j] << std::endl;
+      }
+    }
+    const std::string t = s.str();
+    if (out && cap > int(t.size())) std::memcpy(out, t.c_str(), t.size()+1);
+    return int(t.size());
+  });
+}
+// BackupRestoreFacility::restore, :146-218. The port restores the equidistant containers with one keepOverlap flag for all
+// levels (what orc_spec can express); the tensor-product variant (:268-346, rank-local coordinates through the private
+// constructor yaspgrid.hh:1156) is only available in the reference-built oracle.
+void* orc_restore(int dim, int coord_mode, int nranks, const char* const* texts) {
+  return guarded((void*)nullptr, [&]() -> void* {
+    if (coord_mode == 2) throw std::runtime_error("orc_restore: tensor-product restore is not restated in the port oracle");
+    std::istringstream stream(texts[0]);
+    std::string input; int version = 0;
+    stream >> input >> input >> input >> input; stream >> version;
+    if (version != 2) throw std::runtime_error("Your YaspGrid backup file is written in an outdated format!");
+    orc_spec sp; std::memset(&sp, 0, sizeof(sp));
+    sp.dim = dim; sp.coord_mode = coord_mode; sp.partitioner = 2;
+    stream >> input >> input;
+    for (int i = 0; i < 3; ++i) sp.fixed_dims[i] = 1;
+    for (int i = 0; i < dim; ++i) stream >> sp.fixed_dims[i];
+    stream >> input >> input; stream >> sp.refine;
+    bool b; stream >> input;
+    for (int i = 0; i < dim; ++i) { stream >> b; if (b) sp.periodic |= 1u << i; }
+    stream >> input; stream >> sp.overlap;
+    stream >> input; sp.keep_overlap = 1;
+    for (int i = 0; i < sp.refine; ++i) {
+      stream >> b;
+      if (i == 0) sp.keep_overlap = b; else if (int(b) != sp.keep_overlap) throw std::runtime_error("orc_restore: mixed keepOverlap flags are not restated in the port oracle");
+    }
+    stream >> input >> input;
+    for (int i = 0; i < 3; ++i) sp.N[i] = 1;
+    for (int i = 0; i < dim; ++i) stream >> sp.N[i];
+    double h[3] = {0,0,0}, origin[3] = {0,0,0};
+    stream >> input; for (int i = 0; i < dim; ++i) stream >> h[i];
+    if (coord_mode == 1) { stream >> input; for (int i = 0; i < dim; ++i) stream >> origin[i]; }
+    for (int i = 0; i < dim; ++i) {
+      double length = h[i]; length *= sp.N[i];
+      if (coord_mode == 0) sp.upper[i] = length; else { sp.lower[i] = origin[i]; double ur = origin[i]; ur += length; sp.upper[i] = ur; }
+    }
+    return new World(sp, nranks);
+  });
+}
+
 int orc_fv_init(void* w, int rank, int level, int problem, const double* params, double* c) {
   return guarded(-1, [&] {
     const World& wd = *W(w); const int dim = wd.dim;

@@ -5,6 +5,7 @@
 //   dune/grid/yaspgrid.hh, dune/grid/yaspgrid/{coordinates,torus,partitioning,ygrid,yaspgridgeometry,
 //   yaspgridentity,yaspgridintersection,yaspgridintersectioniterator,yaspgridleveliterator,
 //   yaspgridindexsets,yaspgrididset,yaspgridentityseed,yaspgridhierarchiciterator}.hh,
+//   dune/grid/yaspgrid/backuprestore.hh,
 //   dune/grid/common/{gridenums,exceptions,datahandleif,mapper,mcmgmapper,capabilities,backuprestore}.hh
 // are included unmodified; dune-common, dune-geometry and MPI (absent from this image) are replaced
 // by the stand-ins in oracle/ref/shim (ranks = threads of this process, see shim/mpi.h).
@@ -19,6 +20,7 @@
 #include <functional>
 #include <limits>
 #include <memory>
+#include <sstream>
 #include <string>
 #include <thread>
 
@@ -53,6 +55,7 @@ struct WorldBase {
   virtual int64_t geogridEval(int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
                               double*, double*, double*, double*, double*) = 0;
   virtual int64_t communicate(int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* items) = 0;
+  virtual std::string backup(int rank) = 0;
   virtual int fvInit(int rank, int level, int problem, const double* params, double* c) = 0;
   virtual double fvRun(int level, int problem, const double* params, double** c, double** upd, int steps, double* dt_last) = 0;
 };
@@ -168,6 +171,23 @@ struct World : WorldBase {
       grids[p]->refineOptions(s.keep_overlap != 0);
       if (s.refine > 0) grids[p]->globalRefine(s.refine);
     });
+  }
+
+  // every rank restored by the reference's BackupRestoreFacility from its own text (yaspgrid/backuprestore.hh:146-218, 268-346)
+  World(int nranks, const char* const* texts) {
+    P = nranks; gdim = dim;
+    vw.reset(new vmpi_world(P)); rk.resize(P); grids.resize(P);
+    for (int p = 0; p < P; ++p) rk[p] = vmpi_rank{vw.get(), p};
+    on_all_ranks(P, [&](int p) {
+      typename Grid::Communication comm(&rk[p]);
+      std::istringstream in(texts[p]);
+      grids[p].reset(Dune::BackupRestoreFacility<Grid>::restore(in, comm));
+    });
+  }
+  std::string backup(int rank) override {
+    std::ostringstream s;
+    Dune::BackupRestoreFacility<Grid>::backup(g(rank), s);
+    return s.str();
   }
 
   Grid& g(int rank) { return *grids[rank]; }
@@ -484,6 +504,16 @@ WorldBase* make_world(const orc_spec& s, int nranks) {
   DUNE_THROW(Dune::GridError, "bad coord_mode " << s.coord_mode);
 }
 
+template<int dim>
+WorldBase* restore_world(int coord_mode, int nranks, const char* const* texts) {
+  switch (coord_mode) {
+    case 0: return new World<dim, Dune::EquidistantCoordinates<double,dim>>(nranks, texts);
+    case 1: return new World<dim, Dune::EquidistantOffsetCoordinates<double,dim>>(nranks, texts);
+    case 2: return new World<dim, Dune::TensorProductCoordinates<double,dim>>(nranks, texts);
+  }
+  DUNE_THROW(Dune::GridError, "bad coord_mode " << coord_mode);
+}
+
 template<class F, class R>
 R guarded(R onerr, F&& f) {
   try { g_err.clear(); return f(); }
@@ -580,6 +610,20 @@ int64_t orc_geogrid_eval(void* w, int rank, int level, int pit, int def, const d
 }
 int64_t orc_communicate(void* w, int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* items) {
   return guarded(int64_t(-1), [&]{ return W(w)->communicate(level, block, iftype, dir, op, narrays, arrays, items); });
+}
+int orc_backup(void* w, int rank, char* out, int cap) {
+  return guarded(-1, [&] {
+    const std::string t = W(w)->backup(rank);
+    if (out && cap > int(t.size())) std::memcpy(out, t.c_str(), t.size()+1);
+    return int(t.size());
+  });
+}
+void* orc_restore(int dim, int coord_mode, int nranks, const char* const* texts) {
+  return guarded((void*)nullptr, [&]() -> void* {
+    if (dim == 2) return restore_world<2>(coord_mode, nranks, texts);
+    if (dim == 3) return restore_world<3>(coord_mode, nranks, texts);
+    DUNE_THROW(Dune::GridError, "oracle supports dim 2 and 3");
+  });
 }
 int orc_fv_init(void* w, int rank, int level, int problem, const double* params, double* c) {
   return guarded(-1, [&]{ return W(w)->fvInit(rank, level, problem, params, c); });

@@ -57,3 +57,35 @@ def product_grid(cfg, rank, P, comm=None):
     if cfg["refine"]:
         g.globalRefine(cfg["refine"])
     return g
+
+
+BOXES = ("overlapfront", "overlap", "interiorborder", "interior")
+
+
+def compare_world(w, grid_of_rank, d, P, nlevels):
+    """host descriptors of the product grids (grid_of_rank(r)) against an oracle world: torus, boundary segments, levels,
+    nested boxes, index offsets, sizes, all eight send/recv lists and the coordinates, bit for bit"""
+    for r in range(P):
+        g = grid_of_rank(r)
+        assert g.torusDims() == w.torus_dims()
+        assert g.numBoundarySegments() == w.num_boundary_segments(r)
+        assert g.maxLevel == w.max_level
+        assert np.array_equal(g.domainSize(), w.domain_size()) or r > 0      # the oracle reports rank 0's domain size
+        for lvl in range(nlevels):
+            gv = g.levelGridView(lvl)
+            assert gv.overlapSize(0) == w.overlap_size(lvl)
+            for c in range(d + 1):
+                a, b = gv.boxes(c), w.boxes(r, lvl, c)
+                assert len(a) == len(b)
+                for x, y in zip(a, b):
+                    assert x["shift"] == y["shift"] and x["offset"] == y["offset"]
+                    for k in BOXES:
+                        assert x[k][0][:d] == y[k][0][:d] and x[k][1][:d] == y[k][1][:d], (r, lvl, c, k, x, y)
+                assert gv.size(c) == w.size(r, lvl, c)
+                for which in range(8):
+                    la, lb = g.commList(lvl, c, which), w.lists(r, lvl, c, which)
+                    assert la.shape == lb.shape and np.array_equal(la, lb), (r, lvl, c, which, la, lb)
+            for ax in range(d):
+                fa, ca = gv.coordinates(ax)
+                fb, cb = w.coordinates(r, lvl, ax)
+                assert fa == fb and np.array_equal(ca, cb, equal_nan=True), (r, lvl, ax)

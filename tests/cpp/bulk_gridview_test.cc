@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <sstream>
 #include <numeric>
 #include <set>
 
@@ -52,6 +53,16 @@ void hostChecks() {
   threw = false;
   try { BulkYaspGrid<dim> bad(L, s, std::bitset<dim>(), 3, 0, 4); } catch (const GridError&) { threw = true; }   // yaspgrid.hh:925-937
   CHECK(threw);
+  // BackupRestoreFacility (yaspgrid/backuprestore.hh): backup -> restore -> same backup text, same level structure
+  typedef BackupRestoreFacility<BulkYaspGrid<dim>> BRF;
+  std::ostringstream os;
+  BRF::backup(grid, os);
+  CHECK(os.str().rfind("YaspGrid BackupRestore Format Version: 2", 0) == 0);
+  std::istringstream is(os.str());
+  std::unique_ptr<BulkYaspGrid<dim>> back(BRF::restore(is, DGB_COORD_EQUIDISTANT));
+  CHECK(back && back->maxLevel() == grid.maxLevel());
+  CHECK(back->leafGridView().size(0) == grid.leafGridView().size(0));
+  CHECK(BRF::text(*back) == os.str());
 }
 
 template<int dim>

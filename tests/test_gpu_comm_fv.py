@@ -345,3 +345,40 @@ def test_fv_fused_exchange_single_rank(cfg, problem, params, mode, monkeypatch):
     else:
         assert np.abs(res["1"][0] - ref[0]).max() <= 1e-13 * np.abs(ref[0]).max()       # tolerance: 1e-13 relative
     w.close()
+
+
+def test_fv_restart_from_backup(tmp_path):
+    """restart of an FV run (SURVEY §8f row 3): grid through BackupRestoreFacility text, field through the checkpoint file;
+    the restarted run must continue bit-identically, and the checkpoint must refuse a different grid"""
+    import torch
+    import dune_grid_b200 as dg
+    cfg = make_cfg(dim=3, N=(20, 12, 16), periodic=1, mode=1, lower=(0.0, -1.0, 0.5), upper=(1.0, 0.0, 1.5), refine=1)
+    params = [1.0, -0.5, 0.25, 0.1, 0.5, -0.5, 1.0, 0.1, 0.45]
+    g = product_grid(cfg, 0, 1)
+    fv = dg.FiniteVolume(g, None, 0, params, "exact")
+    c = fv.initial()
+    cn = torch.empty_like(c)
+    for _ in range(3):
+        fv.step(c, cn)
+        c, cn = cn, c
+    m = dg.MultipleCodimMultipleGeomTypeMapper(g.leafGridView(), dg.mcmgElementLayout(3))
+    m.backupField(c, tmp_path / "c")
+    text = g.backup()
+    for _ in range(2):
+        fv.step(c, cn)
+        c, cn = cn, c
+    # restart
+    g2 = dg.YaspGrid.restore(text, "equidistantoffset")
+    m2 = dg.MultipleCodimMultipleGeomTypeMapper(g2.leafGridView(), dg.mcmgElementLayout(3))
+    c2 = torch.zeros(m2.size, dtype=torch.float64, device="cuda")
+    m2.restoreField(c2, tmp_path / "c")
+    fv2 = dg.FiniteVolume(g2, None, 0, params, "exact")
+    c2n = torch.empty_like(c2)
+    for _ in range(2):
+        fv2.step(c2, c2n)
+        c2, c2n = c2n, c2
+    assert torch.equal(c, c2)
+    other = product_grid(make_cfg(dim=3, N=(20, 12, 16), refine=1), 0, 1)
+    mo = dg.MultipleCodimMultipleGeomTypeMapper(other.leafGridView(), dg.mcmgElementLayout(3))
+    with pytest.raises(Exception):
+        mo.restoreField(torch.zeros(mo.size, dtype=torch.float64, device="cuda"), tmp_path / "c")

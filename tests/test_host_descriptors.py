@@ -8,37 +8,13 @@ import pytest
 
 from tests.common import best_oracle, make_cfg, oracle_world, product_grid
 
-BOXES = ("overlapfront", "overlap", "interiorborder", "interior")
+from tests.common import compare_world  # noqa: E402
 
 
 def compare(cfg, P):
     o = best_oracle()
     w = oracle_world(o, cfg, P)
-    d = cfg["dim"]
-    for r in range(P):
-        g = product_grid(cfg, r, P)
-        assert g.torusDims() == w.torus_dims()
-        assert g.numBoundarySegments() == w.num_boundary_segments(r)
-        assert g.maxLevel == w.max_level
-        assert np.array_equal(g.domainSize(), w.domain_size())
-        for lvl in range(cfg["refine"] + 1):
-            gv = g.levelGridView(lvl)
-            assert gv.overlapSize(0) == w.overlap_size(lvl)
-            for c in range(d + 1):
-                a, b = gv.boxes(c), w.boxes(r, lvl, c)
-                assert len(a) == len(b)
-                for x, y in zip(a, b):
-                    assert x["shift"] == y["shift"] and x["offset"] == y["offset"]
-                    for k in BOXES:
-                        assert x[k][0][:d] == y[k][0][:d] and x[k][1][:d] == y[k][1][:d], (r, lvl, c, k, x, y)
-                assert gv.size(c) == w.size(r, lvl, c)
-                for which in range(8):
-                    la, lb = g.commList(lvl, c, which), w.lists(r, lvl, c, which)
-                    assert la.shape == lb.shape and np.array_equal(la, lb), (r, lvl, c, which, la, lb)
-            for ax in range(d):
-                fa, ca = gv.coordinates(ax)
-                fb, cb = w.coordinates(r, lvl, ax)
-                assert fa == fb and np.array_equal(ca, cb, equal_nan=True), (r, lvl, ax)
+    compare_world(w, lambda r: product_grid(cfg, r, P), cfg["dim"], P, cfg["refine"] + 1)
     w.close()
 
 
