@@ -88,11 +88,13 @@ __device__ __forceinline__ void halo_box(const PlanBox& b, const ArrayTable& arr
     double* w = buffer + b.buf_offset + t;
     if (MODE == 0) *w = *p;
     else if (MODE == 1) *p = *w;
-    else *p = *w + *p;
+    else if (MODE == 2) *p = *w + *p;
+    else if (MODE == 3) { const double x = *w; if (x >= 0.0) *p = fmin(x, *p); }      // MinimumExchange (globalindexset.hh:153-160)
+    else { const double x = *w; if (x >= 0.0) *p = x; }                               // IndexExchange (globalindexset.hh:262-289)
   }
 }
 
-template<int MODE>   // 0 pack (gather), 1 unpack set, 2 unpack add
+template<int MODE>   // 0 pack (gather), unpack: 1 set, 2 add, 3 min of non-negative, 4 set if non-negative
 __global__ void __launch_bounds__(PACK_THREADS) k_halo(const PlanBox* __restrict__ boxes, const ArrayTable arrays, double* __restrict__ buffer,
                                                        const __grid_constant__ HaloGroup grp) {
   int bi = 0;
@@ -249,7 +251,9 @@ static void launch_boxes(CommPlan& plan, const ArrayTable& at, int mode, const s
     const unsigned grid = unsigned(grp.start[grp.nboxes]);
     if (mode == 0) k_halo<0><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
     else if (mode == 1) k_halo<1><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
-    else k_halo<2><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
+    else if (mode == 2) k_halo<2><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
+    else if (mode == 3) k_halo<3><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
+    else k_halo<4><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
     ++plan.launches;
     k = e;
   }
@@ -266,7 +270,7 @@ int plan_pack(CommPlan& plan, double* const* d_arrays, const int32_t* item_sizes
 int plan_unpack(CommPlan& plan, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream) {
   if (int rc = plan.upload()) return rc;
   ArrayTable at; if (int rc = make_table(plan, d_arrays, item_sizes, narrays, at)) return rc;
-  if (plan.nRecvBoxes) launch_boxes(plan, at, op == DGB_OP_ADD ? 2 : 1, plan.hostRecv, plan.dRecvBoxes, plan.dRecvBuf, &plan.recvWaveEnd, stream);
+  if (plan.nRecvBoxes) launch_boxes(plan, at, op + 1, plan.hostRecv, plan.dRecvBoxes, plan.dRecvBuf, &plan.recvWaveEnd, stream);
   DGB_CUDA(cudaGetLastError());
   return DGB_OK;
 }
@@ -304,7 +308,7 @@ int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_a
 int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream) {
   if (int rc = plan.upload()) return rc;
   ArrayTable at; if (int rc = make_table(plan, d_arrays, item_sizes, narrays, at)) return rc;
-  if (plan.nRecvBoxes) launch_boxes(plan, at, op == DGB_OP_ADD ? 2 : 1, plan.hostRecv, plan.dRecvBoxes, const_cast<double*>(buf), &plan.recvWaveEnd, stream);
+  if (plan.nRecvBoxes) launch_boxes(plan, at, op + 1, plan.hostRecv, plan.dRecvBoxes, const_cast<double*>(buf), &plan.recvWaveEnd, stream);
   DGB_CUDA(cudaGetLastError());
   return DGB_OK;
 }
@@ -423,6 +427,13 @@ int get_plan(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir, c
   return DGB_OK;
 }
 
+int comm_rank_count(const dgb_comm* comm, int* rank, int* nranks) { *rank = comm ? comm->rank : 0; *nranks = comm ? comm->nranks : 1; return DGB_OK; }
+int nccl_allgather_bytes(const void* d_in, void* d_out, size_t bytes, dgb_comm* comm, cudaStream_t stream) {
+  if (!comm || comm->nranks == 1) { DGB_CUDA(cudaMemcpyAsync(d_out, d_in, bytes, cudaMemcpyDeviceToDevice, stream)); return DGB_OK; }
+  DGB_NCCL(g_nccl.AllGather(d_in, d_out, bytes, ncclChar, comm->comm, stream));
+  return DGB_OK;
+}
+
 int nccl_allreduce(double* d, int op, dgb_comm* comm, cudaStream_t stream) {
   if (!comm || comm->nranks == 1) return DGB_OK;
   DGB_NCCL(g_nccl.AllReduce(d, d, 1, ncclDouble, op == 0 ? ncclMin : ncclMax, comm->comm, stream));
@@ -464,7 +475,7 @@ int dgb_communicate(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int
   return guarded([&]() -> int {
     if (level < 0 || level >= int(g->me.levels.size())) throw RangeError("level out of range");
     if (narrays < 1) throw ArgError("no arrays");
-    if (op != DGB_OP_SET && op != DGB_OP_ADD) throw ArgError("unknown combine op");
+    if (op < DGB_OP_SET || op > DGB_OP_SET_NONNEG) throw ArgError("unknown combine op");
     std::shared_ptr<CommPlan> plan;
     if (int rc = get_plan(g, level, *m, iftype, dir, item_sizes, narrays, plan)) return rc;
     return run_plan(g, *plan, g->me.rank, op, d_arrays, item_sizes, narrays, comm, (cudaStream_t)stream);
@@ -504,7 +515,7 @@ int dgb_comm_unpack(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int
                     const int32_t* item_sizes, int narrays, void* stream) {
   return guarded([&]() -> int {
     if (level < 0 || level >= int(g->me.levels.size())) throw RangeError("level out of range");
-    if (op != DGB_OP_SET && op != DGB_OP_ADD) throw ArgError("unknown combine op");
+    if (op < DGB_OP_SET || op > DGB_OP_SET_NONNEG) throw ArgError("unknown combine op");
     std::shared_ptr<CommPlan> plan;
     if (int rc = get_plan(g, level, *m, iftype, dir, item_sizes, narrays, plan)) return rc;
     return plan_unpack(*plan, op, d_arrays, item_sizes, narrays, (cudaStream_t)stream);

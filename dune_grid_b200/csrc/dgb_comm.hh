@@ -40,6 +40,9 @@ int get_plan(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir, c
 int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays,
              dgb_comm* comm, cudaStream_t stream, bool packed = false);
 int nccl_allreduce(double* d, int op /*0 min, 1 max*/, dgb_comm* comm, cudaStream_t stream);
+// rank-ordered concatenation of `bytes` bytes per rank (d_out holds nranks*bytes); one rank: a copy
+int nccl_allgather_bytes(const void* d_in, void* d_out, size_t bytes, dgb_comm* comm, cudaStream_t stream);
+int comm_rank_count(const dgb_comm* comm, int* rank, int* nranks);
 // recv boxes scattered from `buf` (laid out like the plan's receive buffer) instead of plan.dRecvBuf
 int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream);
 

@@ -300,6 +300,17 @@ class GridView:
                                      _ptr(out), _stream()))
         return out
 
+    def globalIndexSet(self, codim):
+        """Dune::GlobalIndexSet(gridView, codim) (dune/grid/utility/globalindexset.hh): (int32 tensor with index(e) for every
+        entity of `codim` in local index order, size(codim) over all ranks). Collective."""
+        _require_cuda()
+        torch = _torch()
+        out = torch.empty(self.size(codim), dtype=torch.int32, device="cuda")
+        n = C.c_int64(0)
+        comm = self.grid.comm.h if self.grid.comm is not None else None
+        check(lib.dgb_global_index(self.grid.h, self.level, codim, _ptr(out), C.byref(n), comm, _stream()))
+        return out, n.value
+
     def communicate(self, mapper, arrays, iftype, direction, op="set", item_sizes=None):
         """gv.communicate(dataHandle, iftype, dir) with the data handle 'arrays indexed by mapper' and the
         combine operation op in {'set','add'} (dune/python/grid/mapper.hh:117-137)"""
@@ -310,7 +321,7 @@ class GridView:
         ptrs = (C.c_void_p * len(arrays))(*[a.data_ptr() for a in arrays])
         items = (C.c_int32 * len(arrays))(*item_sizes)
         comm = self.grid.comm.h if self.grid.comm is not None else None
-        check(lib.dgb_communicate(self.grid.h, self.level, C.byref(mapper.m), iftype, direction, {"set": 0, "add": 1}[op],
+        check(lib.dgb_communicate(self.grid.h, self.level, C.byref(mapper.m), iftype, direction, {"set": 0, "add": 1, "min_nonneg": 2, "set_nonneg": 3}[op],
                                   ptrs, items, len(arrays), comm, _stream()))
 
 
@@ -343,7 +354,7 @@ class GridView:
     def commUnpack(self, mapper, arrays, iftype, direction, op="set", item_sizes=None):
         _require_cuda()
         arrays, ptrs, items = self._items(mapper, arrays, item_sizes)
-        check(lib.dgb_comm_unpack(self.grid.h, self.level, C.byref(mapper.m), iftype, direction, {"set": 0, "add": 1}[op],
+        check(lib.dgb_comm_unpack(self.grid.h, self.level, C.byref(mapper.m), iftype, direction, {"set": 0, "add": 1, "min_nonneg": 2, "set_nonneg": 3}[op],
                                   ptrs, items, len(arrays), _stream()))
 
 

@@ -39,7 +39,9 @@ enum { DGB_InteriorBorder_InteriorBorder_Interface = 0, DGB_InteriorBorder_All_I
 enum { DGB_Interior_Partition = 0, DGB_InteriorBorder_Partition = 1, DGB_Overlap_Partition = 2,
        DGB_OverlapFront_Partition = 3, DGB_All_Partition = 4, DGB_Ghost_Partition = 5 };
 enum { DGB_ForwardCommunication = 0, DGB_BackwardCommunication = 1 };
-enum { DGB_OP_SET = 0, DGB_OP_ADD = 1 };       /* dune/python/grid/mapper.hh:117-137 commOp */
+enum { DGB_OP_SET = 0, DGB_OP_ADD = 1,         /* dune/python/grid/mapper.hh:117-137 commOp */
+       DGB_OP_MIN_NONNEG = 2,                  /* if (remote >= 0) local = min(remote, local): MinimumExchange, utility/globalindexset.hh:153-160 */
+       DGB_OP_SET_NONNEG = 3 };                /* if (remote >= 0) local = remote: IndexExchange, utility/globalindexset.hh:262-289 */
 /* index of the four nested partition boxes of a component (yaspgrid.hh:199-206) */
 enum { DGB_BOX_OVERLAPFRONT = 0, DGB_BOX_OVERLAP = 1, DGB_BOX_INTERIORBORDER = 2, DGB_BOX_INTERIOR = 3 };
 
@@ -79,6 +81,14 @@ int dgb_grid_domain_size(const dgb_grid* g, double* L);                /* yaspgr
  * then one refineOptions(keep_l) + globalRefine(1) per stored level. `text` is this rank's file. */
 int dgb_grid_backup(const dgb_grid* g, char* text, int64_t cap, int64_t* needed);
 int dgb_grid_restore(const char* text, int coord_mode, int rank, int nranks, dgb_grid** out);
+/* Dune::GlobalIndexSet<GridView>(gridview, codim) (dune/grid/utility/globalindexset.hh:318-440): globally unique consecutive
+ * indices of the entities of one codimension. d_out[e] = index(entity with local index e) for all size(codim) entities of
+ * the level (int32, like the reference's Index); *global_size = size(codim). Same algorithm, as device kernels: owner =
+ * smallest rank that holds the entity as interior or border (communicate All_All with DGB_OP_MIN_NONNEG), owned entities
+ * numbered in the order the reference meets them (cells in index order, sub-entities in reference-element order) by a
+ * device-wide prefix sum, rank offsets from an all-gather of the counts, non-owners served by communicate All_All with
+ * DGB_OP_SET_NONNEG. Collective over the ranks of `comm` (NULL on one rank); synchronises the stream. */
+int dgb_global_index(dgb_grid* g, int level, int codim, int32_t* d_out, int64_t* global_size, struct dgb_comm* comm, void* stream);
 /* standalone processor-grid choice, partitioning.hh:56-117 */
 int dgb_partition(int dim, const int32_t* N, int P, int overlap, int partitioner, const int32_t* fixed, int32_t* dims_out);
 

@@ -105,6 +105,7 @@ class OracleLib:
             "orc_geometry_eval": (i64, [vp, i32, i32, i32, i32, pd, pd, pd, pd]),
             "orc_geogrid_eval": (i64, [vp, i32, i32, i32, i32, pd, i32, pd, pd, pd, pd, pd, pd]),
             "orc_communicate": (i64, [vp, i32, pu32, i32, i32, i32, i32, ppd, pi]),
+            "orc_global_index": (i64, [vp, i32, i32, C.POINTER(pi32)]),
             "orc_backup": (i32, [vp, i32, C.c_char_p, i32]),
             "orc_restore": (vp, [i32, i32, i32, C.POINTER(C.c_char_p)]),
             "orc_fv_init": (i32, [vp, i32, i32, i32, pd, pd]),
@@ -176,6 +177,13 @@ class World:
             self.close()
         except Exception:
             pass
+
+    def global_index(self, level, codim):
+        """Dune::GlobalIndexSet(levelGridView(level), codim) on all ranks: ([per-rank int32 array in local index order], size)"""
+        outs = [np.full(self.size(r, level, codim), -7, dtype=np.int32) for r in range(self.P)]
+        ptrs = (C.POINTER(C.c_int32) * self.P)(*[_p(a, C.c_int32) for a in outs])
+        n = self._chk(self.L.orc_global_index(self.h, level, codim, ptrs))
+        return outs, n
 
     def backup(self, rank):
         """the text BackupRestoreFacility::backup(grid, stream) writes on `rank`"""

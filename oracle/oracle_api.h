@@ -103,6 +103,13 @@ double orc_fv_step(void* w, int level, int problem, const double* params, double
 /* the same step repeated `steps` times with rank threads kept alive; returns seconds of wall time for the loop */
 double orc_fv_run(void* w, int level, int problem, const double* params, double** c, int steps, double* dt_last);
 
+/* (f2) Dune::GlobalIndexSet<LevelGridView>(gridview, codim) (dune/grid/utility/globalindexset.hh:318-440) built on all ranks
+ * at once. out[rank] receives size(level, codim) ints: the global index of the entity with local index e, read back
+ * through subIndex(cell, i, codim) / index(cell). Returns size(codim), the number of global entities, or -1.
+ * orc_communicate additionally understands op 2 (if remote >= 0: local = min(remote, local), MinimumExchange :153-160)
+ * and op 3 (if remote >= 0: local = remote, IndexExchange :262-289). */
+int64_t orc_global_index(void* w, int level, int codim, int32_t** out);
+
 /* (f3) BackupRestoreFacility<YaspGrid<dim,CC>> (yaspgrid/backuprestore.hh). orc_backup: the text backup(grid, std::ostream&)
  * writes for `rank` (:105-128, :222-246); returns its length without the NUL (copied when it fits into cap) or -1.
  * orc_restore: a world whose rank r is built by restore(std::istream&, comm) (:146-218, :268-346) from texts[r]. */

@@ -544,13 +544,71 @@ struct World {
                 for (int i = 0; i < items[a]; ++i) {
                   double& local = arrays[p*narrays+a][std::size_t(base+b)*items[a]+i];
                   const double remote = (*buf)[pos++];
-                  local = op == 1 ? remote+local : remote;
+                  if (op == 2) { if (remote >= 0) local = std::min(remote, local); }     // MinimumExchange, utility/globalindexset.hh:153-160
+                  else if (op == 3) { if (remote >= 0) local = remote; }                   // IndexExchange, :262-289
+                  else local = op == 1 ? remote+local : remote;
                 }
           });
         }
       }
     }
     return sent;
+  }
+
+  // ---- (f2) GlobalIndexSet (dune/grid/utility/globalindexset.hh:318-440), all ranks at once ---------------------------
+  int64_t globalIndex(int level, int codim, int32_t** out) {
+    if (codim < 0 || codim > dim) throw std::range_error("codim out of range");
+    uint32_t block[4] = {0, 0, 0, 0}; block[codim] = 1;
+    const int items[1] = {1};
+    const std::vector<SubEntity> tab = subEntityTable(dim, codim);
+    std::vector<std::vector<double>> assignment(P), gidx(P);
+    std::vector<double*> ptr(P);
+    // UniqueEntityPartition (:176-203): own rank where the sub-entity is interior or border, else -1; minimum exchange
+    for (int p = 0; p < P; ++p) {
+      const Level& g = lev(p, level);
+      std::size_t n = 0; for (const Component& c : g.comp[codim]) n += std::size_t(c.box[OF].total(dim));
+      assignment[p].assign(n, -1.0); gidx[p].assign(n, -1.0);
+      if (codim != 0)
+        forEachEntity(p, level, 0, 4, [&](const Level&, int, const I3& cell, int, int64_t) {
+          for (int i = 0; i < int(tab.size()); ++i) {
+            I3 c = cell; for (int j = 0; j < dim; ++j) c[j] += int(tab[i].move >> j & 1u);
+            const int pt = partitionType(g, codim, g.shiftmap[codim][tab[i].shift], c);
+            assignment[p][subIndex(g, cell, i, codim)] = (pt == 0 || pt == 1) ? double(p) : -1.0;
+          }
+        });
+      ptr[p] = assignment[p].data();
+    }
+    if (codim != 0) communicate(level, block, 4, 0, 2, 1, ptr.data(), items);
+    // counts and offsets (:338-362)
+    std::vector<int64_t> nLocal(P, 0);
+    for (int p = 0; p < P; ++p) {
+      if (codim == 0) nLocal[p] = forEachEntity(p, level, 0, 0, [](const Level&, int, const I3&, int, int64_t) {});
+      else for (double a : assignment[p]) if (a == double(p)) ++nLocal[p];
+    }
+    int64_t total = 0; for (int64_t v : nLocal) total += v;
+    // numbering in the order of the first visit (:384-428)
+    for (int p = 0; p < P; ++p) {
+      const Level& g = lev(p, level);
+      int64_t myoffset = 0; for (int q = 0; q < p; ++q) myoffset += nLocal[q];
+      int64_t contrib = 0;
+      std::vector<bool> firstTime(gidx[p].size(), true);
+      forEachEntity(p, level, 0, 4, [&](const Level&, int, const I3& cell, int cellIndex, int64_t) {
+        if (codim == 0) {
+          if (partitionType(g, 0, 0, cell) == 0) gidx[p][cellIndex] = double(myoffset + contrib++);
+          return;
+        }
+        for (int i = 0; i < int(tab.size()); ++i) {
+          const int idx = subIndex(g, cell, i, codim);
+          if (!firstTime[idx]) continue;
+          firstTime[idx] = false;
+          if (assignment[p][idx] == double(p)) gidx[p][idx] = double(myoffset + contrib++);
+        }
+      });
+      ptr[p] = gidx[p].data();
+    }
+    communicate(level, block, 4, 0, 3, 1, ptr.data(), items);             // IndexExchange (:430-431)
+    for (int p = 0; p < P; ++p) for (std::size_t e = 0; e < gidx[p].size(); ++e) out[p][e] = int32_t(gidx[p][e]);
+    return total;
   }
 
   // ---- a11: FV transport step on every rank, then communicate(InteriorBorder_All, Forward) ----------
@@ -792,6 +850,9 @@ int64_t orc_communicate(void* w, int level, const uint32_t* block, int iftype, i
 }
 // (f3) BackupRestoreFacility::backup, yaspgrid/backuprestore.hh:105-128 (equidistant, offset), :222-246 (tensor product:
 // TensorProductCoordinates::print of the rank's level-0 container, coordinates.hh:347-356); default ostream formatting
+int64_t orc_global_index(void* w, int level, int codim, int32_t** out) {
+  return guarded(int64_t(-1), [&] { return W(w)->globalIndex(level, codim, out); });
+}
 int orc_backup(void* w, int rank, char* out, int cap) {
   return guarded(-1, [&] {
     World& W_ = *W(w); const RankGrid& rg = W_.ranks[rank]; const int dim = W_.dim;

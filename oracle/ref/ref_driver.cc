@@ -14,6 +14,7 @@
 #define HAVE_MPI 1
 #include <dune/grid/yaspgrid.hh>
 #include <dune/grid/common/mcmgmapper.hh>
+#include <dune/grid/utility/globalindexset.hh>
 
 #include <chrono>
 #include <cstring>
@@ -56,6 +57,7 @@ struct WorldBase {
                               double*, double*, double*, double*, double*) = 0;
   virtual int64_t communicate(int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* items) = 0;
   virtual std::string backup(int rank) = 0;
+  virtual int64_t globalIndex(int level, int codim, int32_t** out) = 0;
   virtual int fvInit(int rank, int level, int problem, const double* params, double* c) = 0;
   virtual double fvRun(int level, int problem, const double* params, double** c, double** upd, int steps, double* dt_last) = 0;
 };
@@ -123,7 +125,9 @@ public:
         for (int i = 0; i < items_[a]; ++i) {
           double& local = arrays_[a][std::size_t(index)*items_[a]+i];
           double remote; buf.read(remote);
-          local = (op_ == 1) ? remote+local : remote;
+          if (op_ == 2) { if (remote >= 0) local = std::min(remote, local); }       // MinimumExchange, utility/globalindexset.hh:153-160
+          else if (op_ == 3) { if (remote >= 0) local = remote; }                     // IndexExchange, :262-289
+          else local = (op_ == 1) ? remote+local : remote;
         }
   }
   mutable int64_t written;
@@ -427,6 +431,24 @@ struct World : WorldBase {
     return s;
   }
 
+  // the reference's own GlobalIndexSet, constructed collectively on all rank threads
+  int64_t globalIndex(int level, int codim, int32_t** out) override {
+    std::vector<int64_t> sizes(P, 0);
+    on_all_ranks(P, [&](int p) {
+      Grid& gr = g(p);
+      GV gv = gr.levelGridView(level);
+      Dune::GlobalIndexSet<GV> gis(gv, codim);
+      const auto& is = gr.levelIndexSet(level);
+      for (auto it = gv.template begin<0>(); it != gv.template end<0>(); ++it) {
+        const auto& e = *it;
+        if (codim == 0) out[p][is.index(e)] = gis.index(e);
+        else for (unsigned int i = 0; i < e.subEntities(codim); ++i) out[p][is.subIndex(e, i, codim)] = gis.subIndex(e, i, codim);
+      }
+      sizes[p] = gis.size(codim);
+    });
+    return sizes[0];
+  }
+
   int fvInit(int rank, int level, int problem, const double* params, double* c) override {
     Grid& gr = g(rank);
     GV gv = gr.levelGridView(level);
@@ -610,6 +632,9 @@ int64_t orc_geogrid_eval(void* w, int rank, int level, int pit, int def, const d
 }
 int64_t orc_communicate(void* w, int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* items) {
   return guarded(int64_t(-1), [&]{ return W(w)->communicate(level, block, iftype, dir, op, narrays, arrays, items); });
+}
+int64_t orc_global_index(void* w, int level, int codim, int32_t** out) {
+  return guarded(int64_t(-1), [&] { return W(w)->globalIndex(level, codim, out); });
 }
 int orc_backup(void* w, int rank, char* out, int cap) {
   return guarded(-1, [&] {

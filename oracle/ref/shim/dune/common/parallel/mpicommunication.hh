@@ -16,6 +16,14 @@ namespace Dune {
     template<class T> T min(const T& x) const { T r = x; if (c_) vmpi_reduce<T>(c_, &x, &r, 1, [](T a, T b){ return a<b?a:b; }); return r; }
     template<class T> T sum(const T& x) const { T r = x; if (c_) vmpi_reduce<T>(c_, &x, &r, 1, [](T a, T b){ return a+b; }); return r; }
     int barrier() const { return c_ ? MPI_Barrier(c_) : 0; }
+    // reference dune/common/parallel/mpicommunication.hh allgather(sbuf, count, rbuf): rank-ordered concatenation
+    template<class T> int allgather(const T* sbuf, int count, T* rbuf) const {
+      if (!c_) { for (int i = 0; i < count; ++i) rbuf[i] = sbuf[i]; return 0; }
+      std::vector<std::vector<char>> all;
+      vmpi_allgather(c_, sbuf, int(sizeof(T))*count, all);
+      for (std::size_t r = 0; r < all.size(); ++r) std::memcpy(rbuf + r*count, all[r].data(), sizeof(T)*count);
+      return 0;
+    }
     template<class Op, class T> int allreduce(const T* in, T* out, int n) const {
       if (!c_) { for (int i=0;i<n;++i) out[i]=in[i]; return 0; }
       vmpi_reduce<T>(c_, in, out, n, [](T a, T b){ return Op()(a,b); }); return 0;

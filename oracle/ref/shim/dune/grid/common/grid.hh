@@ -6,6 +6,8 @@
 // /root/reference for oracle/_ref. Test infrastructure only; no arithmetic lives here.
 #ifndef SHIM_DUNE_GRID_COMMON_GRID_HH
 #define SHIM_DUNE_GRID_COMMON_GRID_HH
+#include <iterator>
+#include <cstddef>
 #include <array>
 #include <cstddef>
 #include <type_traits>
@@ -117,6 +119,12 @@ namespace Dune {
   public:
     typedef IteratorImp Implementation;
     typedef typename IteratorImp::Entity Entity;
+    // std::iterator_traits members (reference common/entityiterator.hh:26-47); std::distance in utility/globalindexset.hh:340
+    typedef std::forward_iterator_tag iterator_category;
+    typedef Entity value_type;
+    typedef std::ptrdiff_t difference_type;
+    typedef const Entity* pointer;
+    typedef const Entity& reference;
     EntityIterator() {}
     EntityIterator(const IteratorImp& imp) : imp_(imp) {}
     EntityIterator& operator++() { imp_.increment(); return *this; }
@@ -185,6 +193,7 @@ namespace Dune {
   class GridView {
   public:
     typedef typename std::remove_const<typename ViewTraits::Grid>::type Grid;
+    typedef GridView Traits;          // GridView::Traits::Codim<cd>::Iterator (used by utility/globalindexset.hh:102)
     typedef typename Grid::Traits GTraits;
     typedef typename std::conditional<ViewTraits::leaf, typename GTraits::LeafIndexSet, typename GTraits::LevelIndexSet>::type IndexSet;
     typedef typename GTraits::LeafIntersectionIterator IntersectionIterator;

@@ -63,17 +63,24 @@ def main():
         rng = np.random.default_rng(99)
         for iftype in range(5):
             for direction in (0, 1):
-                for op in ("set", "add"):
+                for op in ("set", "add", "min_nonneg", "set_nonneg"):
                     sizes = [w.mapper_size(r, 0, layout) for r in range(world)]
                     host = [[rng.standard_normal(sizes[r]), rng.standard_normal(sizes[r] * 2)] for r in range(world)]
                     dev = [torch.from_numpy(a.copy()).cuda() for a in host[rank]]
-                    w.communicate(0, layout, iftype, direction, 0 if op == "set" else 1, host, [1, 2])
+                    w.communicate(0, layout, iftype, direction, ("set", "add", "min_nonneg", "set_nonneg").index(op), host, [1, 2])
                     gv.communicate(m, dev, iftype, direction, op)
                     torch.cuda.synchronize()
                     for a in range(2):
                         if not np.array_equal(dev[a].cpu().numpy(), host[rank][a]):
                             failures += 1
                             print(f"rank {rank}: communicate mismatch cfg={cfg['N']} if={iftype} dir={direction} op={op}", flush=True)
+        # Dune::GlobalIndexSet of every codim (collective: all-gather of the counts, two exchanges)
+        for codim in range(cfg["dim"] + 1):
+            ref, n = w.global_index(0, codim)
+            got, m = gv.globalIndexSet(codim)
+            if m != n or not np.array_equal(got.cpu().numpy(), ref[rank]):
+                failures += 1
+                print(f"rank {rank}: global index mismatch cfg={cfg['N']} codim={codim} size {m} vs {n}", flush=True)
         w.close()
     t = torch.tensor([failures], dtype=torch.int64, device="cuda")
     dist.all_reduce(t)
