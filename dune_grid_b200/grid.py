@@ -300,6 +300,29 @@ class GridView:
                                      _ptr(out), _stream()))
         return out
 
+    def writeVTK(self, name, celldata=None, pointdata=None, path="", float64=False):
+        """VTKWriter(gridView).addCellData/addVertexData + write(name) (dune/grid/io/file/vtk/vtkwriter.hh; dune-python:
+        gridView.writeVTK(name, celldata={...}, pointdata={...})). Values: CUDA tensors indexed by the element / vertex index,
+        shape (n,) scalar, (n, k) with k <= 3 vector. Returns the file to open (.vtu, or the .pvtu header on several ranks)."""
+        def pack(d):
+            arr = (capi.VtkField * max(1, len(d or {})))()
+            keep = []
+            for k, (nm, t) in enumerate((d or {}).items()):
+                t = t.contiguous()
+                keep.append(t)
+                arr[k].name = nm.encode()
+                arr[k].d_data = t.data_ptr()
+                arr[k].ncomp = 1 if t.dim() == 1 else int(t.shape[1])
+                arr[k].is_vector = 0 if t.dim() == 1 else 1
+                arr[k].precision = 1 if float64 else 0
+            return arr, len(d or {}), keep
+        ca, nc, k1 = pack(celldata)
+        va, nv, k2 = pack(pointdata)
+        out = C.create_string_buffer(4096)
+        check(lib.dgb_vtk_write(self.grid.h, self.level, str(name).encode(), str(path).encode(), ca, nc, va, nv, 1 if float64 else 0,
+                                out, 4096, _stream() if (nc or nv) else None))
+        return out.value.decode()
+
     def globalIndexSet(self, codim):
         """Dune::GlobalIndexSet(gridView, codim) (dune/grid/utility/globalindexset.hh): (int32 tensor with index(e) for every
         entity of `codim` in local index order, size(codim) over all ranks). Collective."""

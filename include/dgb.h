@@ -89,6 +89,23 @@ int dgb_grid_restore(const char* text, int coord_mode, int rank, int nranks, dgb
  * device-wide prefix sum, rank offsets from an all-gather of the counts, non-owners served by communicate All_All with
  * DGB_OP_SET_NONNEG. Collective over the ranks of `comm` (NULL on one rank); synchronises the stream. */
 int dgb_global_index(dgb_grid* g, int level, int codim, int32_t* d_out, int64_t* global_size, struct dgb_comm* comm, void* stream);
+/* VTKWriter<GridView>(gridView, VTK::conforming) with addCellData / addVertexData and write(name, VTK::ascii)
+ * (dune/grid/io/file/vtk/vtkwriter.hh:638-642, 698, 764, 985-1030): cells of the InteriorBorder partition, vertices numbered at
+ * their first visit, sections PointData / CellData / Points / Cells, vectors padded to 3 components. Fields are DEVICE arrays
+ * indexed by the element index (cell fields) or the vertex index (vertex fields) of the level, ncomp doubles per entity, like the
+ * containers of P0VTKFunction / P1VTKFunction. One rank: <path>/<name>.vtu; several ranks: every rank writes
+ * s####-p####-<name>.vtu and rank 0 the header s####-<name>.pvtu (:858-909). `written` receives the file to open (piece or
+ * header). Parity of this component is unpinned (the upstream writer cannot be built without dune-common). */
+typedef struct dgb_vtk_field {
+  const char* name;
+  const double* d_data;
+  int32_t ncomp;                    /* FieldInfo::size() */
+  int32_t is_vector;                /* FieldInfo::Type::vector (written with 3 components) or scalar */
+  int32_t precision;                /* 0 VTK::Precision::float32 (the reference's default), 1 float64 */
+} dgb_vtk_field;
+int dgb_vtk_write(const dgb_grid* g, int level, const char* name, const char* path, const dgb_vtk_field* cell_fields,
+                  int ncell_fields, const dgb_vtk_field* vertex_fields, int nvertex_fields, int coord_precision,
+                  char* written, int cap, void* stream);
 /* standalone processor-grid choice, partitioning.hh:56-117 */
 int dgb_partition(int dim, const int32_t* N, int P, int overlap, int partitioner, const int32_t* fixed, int32_t* dims_out);
 
