@@ -178,6 +178,11 @@ class GridView:
     def globalIndexSet(self, codim):
         return self._gv.globalIndexSet(codim)
 
+    def writeVTK(self, name, celldata=None, pointdata=None, **kw):
+        """gridView.writeVTK(name, celldata={...}, pointdata={...}) of dune-python (python/dune/grid/grid_generator.py): arrays
+        indexed by the element / vertex index"""
+        return self._gv.writeVTK(name, celldata=celldata, pointdata=pointdata, **kw)
+
     interiorPartition = property(lambda self: Partition(self, _g.Interior_Partition))
     interiorBorderPartition = property(lambda self: Partition(self, _g.InteriorBorder_Partition))
     overlapPartition = property(lambda self: Partition(self, _g.Overlap_Partition))
