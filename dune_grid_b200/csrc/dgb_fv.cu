@@ -575,7 +575,143 @@ __device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, c
 #undef DGB_RING_CELL
 }
 
-template<int PROBLEM, int D, int BX, int BY, int MINB, bool ZPARAM>
+// ---- bulk-copy (TMA engine) staging of the same ring ----------------------------------------------------------------
+// Instead of one 8-byte LDGSTS per thread and cell (which costs as many load/store-unit wavefronts as all shared-memory
+// reads of the loop together), warp 0 issues one cp.async.bulk per tile ROW and plane: the copy engine moves the row
+// (tile width + x halo, ~1 KB) from L2 to shared memory and signals an mbarrier; no LSU wavefronts, no per-thread address
+// arithmetic, full 128-byte line requests whatever the alignment of the row. Bulk copies need 16-byte aligned source
+// addresses and sizes, while rows of a stored box with odd width start at odd element offsets every other row: the copy
+// starts at the even element below the row start, so a row lands with a phase of 0 or 1 elements; a thread's own cell moves
+// by that phase from plane to plane (dz) and from row to row (dyadj), two integer updates per plane.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}"
+               :: "r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               :: "r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+
+// one staged row of a tile: first needed element (plane 0 of the chunk) and number of elements; len = 0: row not staged
+struct FvBulkRow { long long e0; int len; int pad; };
+
+// Warp 0 stages plane p (planeOff = p*sz) into `slot`: lane r issues the copy of row r, lane 0 arms the mbarrier with the
+// plane's byte count (tot[p & 1], precomputed: the phases depend on the plane only through its parity). The arrive may
+// follow or precede the copies' complete_tx - the phase cannot complete before both have happened - so the lanes do not
+// synchronise: staging sits on warp 0's critical path between two CTA barriers and must stay a dozen instructions.
+// ORDERED (only CTAs whose rows reach the very end of an array with an odd element count): the engine must not read past
+// the end, so the last element of that row comes by a plain load, published before the arrive.
+template<int BY, int RP, bool ORDERED>
+__device__ __forceinline__ void fv_bulk_stage(const double* __restrict__ c, double* slot, unsigned long long* bar, const FvBulkRow* rows,
+                                              const unsigned* tot, long long planeOff, int parity, long long total, int lane) {
+  unsigned bytes = 0; long long a0 = 0;
+  if (lane < BY+2 && rows[lane].len > 0) {
+    const long long e = rows[lane].e0 + planeOff;
+    a0 = e & ~1ll;
+    int cnt = (int(e & 1) + rows[lane].len + 1) & ~1;
+    if (ORDERED && a0 + cnt > total) {
+      cnt -= 2;
+      for (long long q = a0 + cnt; q < e + rows[lane].len; ++q) slot[lane*RP + (q - a0)] = __ldg(c + q);
+    }
+    bytes = unsigned(cnt)*8u;
+  }
+  if (ORDERED) {
+    unsigned sum = bytes;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_expect_tx(bar, sum);
+    __syncwarp();
+  } else if (lane == 0) mbar_arrive_expect_tx(bar, tot[parity]);
+  if (bytes) bulk_g2s(slot + lane*RP, c + a0, bytes, bar);
+}
+
+struct FvBulkLane {
+  double f0, f1, f2, f3, tbx, tby, un5, dt, c_below, zhigh;
+  double* w;                      // own column in cnew
+  const double* cur;              // own cell of plane 0 in slot 0
+  int ox, oy, dz, dyadj, sgn;     // neighbour offsets; phase steps (see above); sgn = -1 if the phase alternates from plane to plane
+  bool active;
+};
+
+template<int D, int BX, int BY, int MODE, bool ZPARAM>
+__device__ __forceinline__ void fv_bulk_loop(FvBulkLane L, const FvRingSlow S, const double* __restrict__ c, double* ring,
+                                             unsigned long long* bars, const FvBulkRow* rows, const unsigned* tot, const bool ordered,
+                                             const long long sz, const long long total,
+                                             const double* rwz, const FvZTable& zt, const int zbase, const int zn, const int kload) {
+  constexpr int R = D+2, RP = BX+4, SLOT = (BY+2)*RP;
+  constexpr bool DX = MODE & 4, DY = MODE & 2, DZ = MODE & 1;
+  const int lane = threadIdx.x & 31;
+  const bool stager = (threadIdx.y*BX + threadIdx.x) < 32;          // warp 0
+  char* w = reinterpret_cast<char*>(L.w);
+  const long long sz8 = sz*8;
+  double c_below = L.c_below, c_here = 0.0;
+  const bool self4 = S.un4 >= 0.0, self5 = L.un5 >= 0.0;
+  int dz = L.dz, dyadj = L.dyadj;
+  const double* cur = L.cur;
+  int slotNext = 1 % R; unsigned parNext = 0;                       // slot / phase parity of plane k+1
+  int slotPrev = R-1;                                               // slot of plane k-1 = where plane k+1+D goes
+  mbar_wait(bars + 0, 0);
+  c_here = *cur;
+  const double* nxt = cur + SLOT + dz;
+#define DGB_BULK_CELL(GUARD, K)                                                                                \
+  {                                                                                                            \
+    if (!(GUARD) || (K)+1 <= kload) mbar_wait(bars + slotNext, parNext);                                       \
+    __syncthreads();                                                                                           \
+    if (stager && (!(GUARD) || (K)+1+D <= kload)) {                                                            \
+      if (!ordered) fv_bulk_stage<BY, RP, false>(c, ring + slotPrev*SLOT, bars + slotPrev, rows, tot, ((K)+1+D)*sz, ((K)+1+D) & 1, total, lane);  \
+      else fv_bulk_stage<BY, RP, true>(c, ring + slotPrev*SLOT, bars + slotPrev, rows, tot, ((K)+1+D)*sz, ((K)+1+D) & 1, total, lane);           \
+    }                                                                                                          \
+    const double c_above = (!(GUARD) || (K)+1 <= kload) ? *nxt : L.zhigh;                                      \
+    const double rw = ZPARAM ? zt.rw[zbase + (K)] : __ldg(rwz + (K));                                          \
+    double upd;                                                                                                \
+    if (MODE < 8) {                                                                                            \
+      const double f5 = L.un5*rw;                                                                              \
+      const double nx = cur[L.ox], ny = cur[L.oy + dyadj];                                                     \
+      upd = 0.0 - (DX ? nx : c_here)*L.f0;                                                                     \
+      if (DX) upd -= L.tbx;                                                                                    \
+      upd -= (DX ? c_here : nx)*L.f1;                                                                          \
+      if (!DX) upd -= L.tbx;                                                                                   \
+      upd -= (DY ? ny : c_here)*L.f2;                                                                          \
+      if (DY) upd -= L.tby;                                                                                    \
+      upd -= (DY ? c_here : ny)*L.f3;                                                                          \
+      if (!DY) upd -= L.tby;                                                                                   \
+      upd -= (DZ ? c_below : c_here)*(-f5);                                                                    \
+      upd -= (DZ ? c_here : c_above)*f5;                                                                       \
+    } else {                                                                                                   \
+      double val;                                                                                              \
+      val = S.alt0; if (S.flags & 16u) val = cur[-1];          if (S.flags & 1u) val = c_here; upd = 0.0 - val*L.f0;  \
+      val = S.alt1; if (S.flags & 32u) val = cur[1];           if (S.flags & 2u) val = c_here; upd -= val*L.f1;       \
+      val = S.alt2; if (S.flags & 64u) val = cur[dyadj - RP];  if (S.flags & 4u) val = c_here; upd -= val*L.f2;       \
+      val = S.alt3; if (S.flags & 128u) val = cur[dyadj + RP]; if (S.flags & 8u) val = c_here; upd -= val*L.f3;       \
+      upd -= (self4 ? c_here : c_below)*(S.un4*rw);                                                            \
+      upd -= (self5 ? c_here : c_above)*(L.un5*rw);                                                            \
+    }                                                                                                          \
+    if (L.active) __stcs(reinterpret_cast<double*>(w), c_here + L.dt*upd);                                     \
+    c_below = c_here; c_here = c_above;                                                                        \
+    w += sz8;                                                                                                  \
+    /* advance: plane k+1 becomes current; phases flip where the plane stride is odd */                        \
+    cur = nxt; dz *= L.sgn; dyadj *= L.sgn;                                                                    \
+    slotPrev = (slotPrev + 1 == R) ? 0 : slotPrev + 1;                                                         \
+    if (++slotNext == R) { slotNext = 0; parNext ^= 1u; nxt = cur - (R-1)*SLOT + dz; }                         \
+    else nxt = cur + ((slotNext == 0) ? -(R-1)*SLOT : SLOT) + dz;                                              \
+  }
+  const int kmain = max(0, min(zn, kload-D));
+  int k = 0;
+#pragma unroll 1
+  for (; k < kmain; ++k) DGB_BULK_CELL(false, k)
+#pragma unroll 1
+  for (; k < zn; ++k) DGB_BULK_CELL(true, k)
+#undef DGB_BULK_CELL
+}
+
+template<int PROBLEM, int D, int BX, int BY, int MINB, bool ZPARAM, bool BULK = false>
 __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a,
                                                          const __grid_constant__ FvZTable zt, const int zc) {
   constexpr int PX = BX+2, PY = BY+2, SLOT = PX*PY;
@@ -659,16 +795,98 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   __syncthreads();
   const int pat = s_pat[1] ? cand : 8;
 
+  const double zlow = (!perz && ovz0 == 0) ? bval : 0.0;
+  const long long idx0 = (long long)(cz0-of.origin[2])*sz + (long long)(cy-of.origin[1])*sy + (cx-of.origin[0]);
+  const int kload = min(zn, ovz1-cz0);                   // last plane offset holding stored cells
+  if constexpr (BULK) {
+    constexpr int R = D+2, RP = BX+4, SLOT = (BY+2)*RP;
+    __shared__ __align__(8) unsigned long long s_bar[R];
+    __shared__ FvBulkRow s_rows[BY+2];
+    const int t = ty*BX + tx;
+    const int tx0 = a.region.origin[0]+blockIdx.x*BX, ty0 = a.region.origin[1]+by*BY;
+    const int nxv = min(BX, a.region.size[0]-(int)blockIdx.x*BX), nyv = min(BY, a.region.size[1]-by*BY);
+    // x range of every staged row: the tile's columns plus the x neighbours that are stored cells
+    const int xs = tx0-1 >= of.origin[0] ? tx0-1 : tx0;
+    const int xe = tx0+nxv < of.origin[0]+of.size[0] ? tx0+nxv+1 : tx0+nxv;
+    if (t < BY+2) {
+      const int gy = ty0-1+t;
+      bool need = t >= 1 && t <= nyv;
+      if (t == 0 || t == nyv+1) {                        // y halo rows: stored neighbours, on the fast path the inflow side only
+        need = gy >= ov.origin[1] && gy < ov.origin[1]+ov.size[1];
+        if (need && pat < 8) need = (t == 0) == bool(pat & 2);
+      }
+      s_rows[t].e0 = (long long)(cz0-of.origin[2])*sz + (long long)(gy-of.origin[1])*sy + (xs-of.origin[0]);
+      s_rows[t].len = need ? xe-xs : 0;
+    }
+    __shared__ unsigned s_tot[2];
+    __shared__ int s_ordered;
+    const long long total = sz*of.size[2];
+    if (t == 0) { for (int j = 0; j < R; ++j) mbar_init(s_bar + j, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+    __syncthreads();
+    if (t == 0) {                                        // bytes of a staged plane by plane parity; does any row end at the array's end?
+      unsigned t0 = 0, t1 = 0; int ord = 0;
+      for (int r = 0; r < BY+2; ++r) if (s_rows[r].len > 0) {
+        const long long e = s_rows[r].e0;
+        t0 += unsigned((int(e & 1) + s_rows[r].len + 1) & ~1)*8u;
+        t1 += unsigned((int((e + sz) & 1) + s_rows[r].len + 1) & ~1)*8u;
+        if (e + (long long)min(zn, kload)*sz + s_rows[r].len + 1 > total) ord = 1;
+      }
+      s_tot[0] = t0; s_tot[1] = t1; s_ordered = ord;
+    }
+    __syncthreads();
+    const bool ordered = s_ordered != 0;
+    if (t < 32)
+#pragma unroll 1
+      for (int j = 0; j <= D; ++j) if (j <= kload) {
+        if (!ordered) fv_bulk_stage<BY, RP, false>(a.c, ring + j*SLOT, s_bar + j, s_rows, s_tot, j*sz, j & 1, total, t);
+        else fv_bulk_stage<BY, RP, true>(a.c, ring + j*SLOT, s_bar + j, s_rows, s_tot, j*sz, j & 1, total, t);
+      }
+    FvBulkLane L; FvRingSlow S;
+    L.active = active;
+    L.f0 = f0; L.f1 = f1; L.f2 = f2; L.f3 = f3; L.un5 = un5; L.tbx = 0.0; L.tby = 0.0; L.ox = 0; L.oy = 0;
+    S.alt0 = alt0; S.alt1 = alt1; S.alt2 = alt2; S.alt3 = alt3; S.un4 = un4; S.flags = flags;
+    L.zhigh = (!perz && ovz1+1 == v.N[2]) ? bval : 0.0;
+    L.dt = 0.99*(1.0/(*a.slotIn));
+    L.w = a.cnew + idx0;
+    // own cell in slot 0: row ty+1, column = position in the staged row + phase of that row in plane 0
+    const int psy = sy & 1, psz = int(sz & 1);
+    const int rowc = min(ty, nyv-1)+1, colc = min(tx, nxv-1) + (tx0-xs);         // clamped like cx, cy
+    const int phi = int((s_rows[0].e0 + (long long)rowc*sy) & 1);
+    L.cur = ring + rowc*RP + colc + phi;
+    const int d = 1 - 2*phi;
+    L.sgn = psz ? -1 : 1;
+    L.dz = psz ? d : 0;
+    L.dyadj = 0;
+    L.c_below = (cz0 > ovz0) ? __ldg(a.c + idx0 - sz) : zlow;
+    if (pat < 8) {
+      const int mx = dx ? 0 : 1, my = dy ? 2 : 3;
+      L.ox = dx ? -1 : 1; L.oy = dy ? -RP : RP;
+      if (!(flags >> (4+mx) & 1u) && !(flags >> mx & 1u)) { L.ox = 0; L.tbx = (flags >> (8+mx) & 1u) ? bval*(dx ? f0 : f1) : 0.0; if (dx) L.f0 = 0.0; else L.f1 = 0.0; }
+      if (!(flags >> (4+my) & 1u) && !(flags >> my & 1u)) { L.oy = 0; L.tby = (flags >> (8+my) & 1u) ? bval*(dy ? f2 : f3) : 0.0; if (dy) L.f2 = 0.0; else L.f3 = 0.0; }
+      if (flags >> mx & 1u) L.ox = 0;
+      if (flags >> my & 1u) L.oy = 0;
+      if (L.oy != 0 && psy) L.dyadj = d;               // the neighbouring row has the other phase
+    } else if (psy) L.dyadj = d;
+    switch (pat) {
+      case 0: fv_bulk_loop<D, BX, BY, 0, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
+      case 1: fv_bulk_loop<D, BX, BY, 1, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
+      case 2: fv_bulk_loop<D, BX, BY, 2, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
+      case 3: fv_bulk_loop<D, BX, BY, 3, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
+      case 4: fv_bulk_loop<D, BX, BY, 4, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
+      case 5: fv_bulk_loop<D, BX, BY, 5, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
+      case 6: fv_bulk_loop<D, BX, BY, 6, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
+      case 7: fv_bulk_loop<D, BX, BY, 7, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
+      default: fv_bulk_loop<D, BX, BY, 8, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
+    }
+    if (active && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = L.dt;
+  } else {
   FvRingLane L; FvRingSlow S;
   L.active = active;
   L.f0 = f0; L.f1 = f1; L.f2 = f2; L.f3 = f3; L.un5 = un5; L.tbx = 0.0; L.tby = 0.0; L.ox = 0; L.oy = 0;
   S.alt0 = alt0; S.alt1 = alt1; S.alt2 = alt2; S.alt3 = alt3; S.un4 = un4; S.flags = flags;
-  const double zlow = (!perz && ovz0 == 0) ? bval : 0.0;
   L.zhigh = (!perz && ovz1+1 == v.N[2]) ? bval : 0.0;
   L.dt = 0.99*(1.0/(*a.slotIn));
-  const long long idx0 = (long long)(cz0-of.origin[2])*sz + (long long)(cy-of.origin[1])*sy + (cx-of.origin[0]);
   L.g = a.c + idx0; L.w = a.cnew + idx0;
-  const int kload = min(zn, ovz1-cz0);                   // last plane offset holding stored cells
   L.own = ring + (ty+1)*PX + (tx+1);
   // halo duty: thread t stages halo cell t of the tile (left column, right column, bottom row, top row), if that
   // cell is a stored neighbour and - on the fast path, where all columns share the flow direction - on an inflow side
@@ -722,6 +940,7 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   }
   cp_async_wait<0>();
   if (active && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = L.dt;
+  }
   const int tid = ty*BX + tx;
   if (a.pack) fv_fused_pack<BX*BY>(a, of, s_items, tid);
   for (int o = 16; o > 0; o >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, o));
@@ -829,7 +1048,8 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
   if (v.dim == 3) {
     // tile choice (measured, tools/fv_sweep.py): 128x4 columns for wide regions, 32x8 otherwise
     const int variant = fv->variant >= 0 ? fv->variant : (a.region.size[0] >= 256 ? 3 : 0);
-    const bool wide = variant == 3 || variant == 7 || variant == 8;
+    const bool wide = variant == 3 || variant == 7 || variant == 8 || variant >= 11;
+    const bool bulk_ok = fv->zparam && (reinterpret_cast<uintptr_t>(a.c) & 15u) == 0;
     const int zc = fv->zchunk > 0 ? fv->zchunk : auto_zchunk(a.region.size, wide ? 128 : 32, wide ? 4 : 8);
     const bool exact = fv->mode == DGB_FV_EXACT;
     const int pb = fv->problem.id == 1 ? 1 : 0;
@@ -842,6 +1062,13 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     } else if (REDUCE_ONLY || a.update || !a.cnew) {
       if (pb) DGB_MARCH(DGB_FV_SEPARABLE, 1, 4, 128, 4) else DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4)
     } else {
+#define DGB_BULK(D_, BX_, BY_, MINB_)                                                                                \
+    { dim3 mblock(BX_, BY_, 1);                                                                                      \
+      dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
+      const size_t smem = size_t(D_+2)*(BX_+4)*(BY_+2)*sizeof(double);                                               \
+      auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, true, true> : k_fv_ring<0, D_, BX_, BY_, MINB_, true, true>;  \
+      DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));                    \
+      kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); }
 #define DGB_RING(D_, BX_, BY_, MINB_)                                                                                \
     { dim3 mblock(BX_, BY_, 1);                                                                                      \
       dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
@@ -864,9 +1091,13 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
         case 7: DGB_RING(8, 128, 4, 2) break;
         case 8: DGB_RING(10, 128, 4, 2) break;
         case 9: DGB_RING(8, 64, 8, 2) break;
+        // bulk-copy (TMA engine) staging: bit-identical, measured SLOWER than LDGSTS staging (0.63-0.66 vs 0.36-0.39 ms at
+        // 512^3): the engine sustains ~8 B/clk/SM on 1 KB row copies whatever the ring depth. Kept as a tested variant.
+        case 11: if (bulk_ok) DGB_BULK(6, 128, 4, 2) else DGB_RING(6, 128, 4, 2) break;
         case 99: if (pb) DGB_MARCH(DGB_FV_SEPARABLE, 1, 4, 128, 4) else DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4) break;   // the general kernel, for comparison
       }
 #undef DGB_RING
+#undef DGB_BULK
     }
 #undef DGB_MARCH
   } else {

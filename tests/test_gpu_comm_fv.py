@@ -284,7 +284,7 @@ def test_fv_full_size_properties():
 @pytest.mark.parametrize("problem,params", [(0, [1.0, -0.5, 0.25, 0.1, 0.5, 0.5, 0.5, 0.1, 0.45]), (0, [-0.3, 0.0, 1.0, 0.7, 0.5, 0.5, 0.5, 0.1, 0.45]),
                                             (1, [2.0, 0, 0, 0.5, 0.15, 0.35, 0.9, 0.05, 0.4])])
 def test_fv_ring_kernels_equal_general_kernel_bitwise(problem, params, monkeypatch):
-    """the production ring kernel (both tile shapes, partial tiles, mixed flow directions, boundary inflow b != 0, graded
+    """the production ring kernel (both tile shapes; variant 11: rows staged by cp.async.bulk + mbarrier) with partial tiles, mixed flow directions, boundary inflow b != 0, graded
     and periodic coordinates) against the general z-march kernel on a random field: same arithmetic, same bits"""
     import torch
     import dune_grid_b200 as dg
@@ -293,7 +293,7 @@ def test_fv_ring_kernels_equal_general_kernel_bitwise(problem, params, monkeypat
         n = g.leafGridView().size(0)
         c0 = torch.from_numpy(np.random.default_rng(3).uniform(0.0, 1.0, n)).cuda()
         res = {}
-        for variant in ("99", "0", "3"):
+        for variant in ("99", "0", "3", "11"):
             monkeypatch.setenv("DGB_FV_VARIANT", variant)
             monkeypatch.setenv("DGB_FV_ZCHUNK", "16")
             fv = dg.FiniteVolume(g, 0, problem, params, "separable")
@@ -302,7 +302,7 @@ def test_fv_ring_kernels_equal_general_kernel_bitwise(problem, params, monkeypat
                 fv.step(c, cn)
                 c, cn = cn, c
             res[variant] = (c.clone(), fv.last_dt())
-        for variant in ("0", "3"):
+        for variant in ("0", "3", "11"):
             assert res[variant][1] == res["99"][1]
             assert torch.equal(res[variant][0], res["99"][0]), (cfg["N"], variant)
 
