@@ -28,6 +28,8 @@ def main():
         (make_cfg(dim=3, N=(20, 24, 18), periodic=5, upper=(1.0, 2.0, 1.5)), 0, [-1.0, 0.7, 0.3, 0.0, 0.5, 1.0, 0.7, 0.1, 0.45]),
         (make_cfg(dim=3, N=(16, 16, 24), mode=2), 1, [1.5, 0, 0, 0.25, 0.5, 0.5, 0.5, 0.1, 0.6]),
         (make_cfg(dim=2, N=(32, 24), periodic=1), 1, [1.0, 0, 0, 0.0, 0.5, 0.5, 0.0, 0.1, 0.3]),
+        # overlap 2, fully periodic, uneven split, partial tiles: send boxes two cells thick, wrap-around partners
+        (make_cfg(dim=3, N=(36, 22, 26), periodic=7, overlap=2), 0, [0.6, -1.0, 0.8, 0.0, 0.5, 0.5, 0.5, 0.1, 0.45]),
     ]
     failures = 0
     modes = set()
