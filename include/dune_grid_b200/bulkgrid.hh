@@ -312,6 +312,45 @@ struct BackupRestoreFacility<BulkYaspGrid<dim>> {
   }
 };
 
+// Dune::GlobalIndexSet<GridView>(gridview, codim) (dune/grid/utility/globalindexset.hh:318-497). The per-entity calls
+// index(e) / subIndex(e,i,codim) become one device array: index()[e] for the entity with local index e of the codim.
+template<int dim>
+class GlobalIndexSet {
+  DeviceArray<std::int32_t> idx_; std::int64_t n_ = 0; int codim_;
+public:
+  typedef int Index;
+  GlobalIndexSet(const BulkGridView<dim>& gv, int codim, cudaStream_t s = nullptr) : idx_(std::size_t(gv.size(codim))), codim_(codim) {
+    check(dgb_global_index(gv.grid().handle(), gv.level(), codim, idx_.data(), &n_, gv.grid().comm(), s));
+  }
+  const DeviceArray<std::int32_t>& index() const { return idx_; }
+  unsigned int size(unsigned int codim) const { return int(codim) == codim_ ? unsigned(n_) : 0u; }   // :487-490
+};
+
+// Dune::VTKWriter<GridView>(gridView) with addCellData / addVertexData / write(name) (dune/grid/io/file/vtk/vtkwriter.hh:638,
+// 698, 764, 985): the data are device arrays indexed by the element / vertex index, ncomp values per entity (P0 / P1 containers)
+template<int dim>
+class VTKWriter {
+  const BulkGridView<dim>& gv_;
+  struct Field { std::string name; const double* data; int ncomp; bool vector; };
+  std::vector<Field> cell_, vertex_;
+  static std::vector<dgb_vtk_field> pack(const std::vector<Field>& f) {
+    std::vector<dgb_vtk_field> o;
+    for (const Field& x : f) o.push_back(dgb_vtk_field{x.name.c_str(), x.data, x.ncomp, x.vector ? 1 : 0, 0});
+    return o;
+  }
+public:
+  explicit VTKWriter(const BulkGridView<dim>& gv) : gv_(gv) {}
+  void addCellData(const double* d_values, const std::string& name, int ncomps = 1) { cell_.push_back({name, d_values, ncomps, ncomps > 1}); }
+  void addVertexData(const double* d_values, const std::string& name, int ncomps = 1) { vertex_.push_back({name, d_values, ncomps, ncomps > 1}); }
+  void clear() { cell_.clear(); vertex_.clear(); }
+  std::string write(const std::string& name, const std::string& path = "", cudaStream_t s = nullptr) const {
+    auto c = pack(cell_), v = pack(vertex_);
+    char out[4096];
+    check(dgb_vtk_write(gv_.grid().handle(), gv_.level(), name.c_str(), path.c_str(), c.data(), int(c.size()), v.data(), int(v.size()), 0, out, 4096, s));
+    return out;
+  }
+};
+
 template<int dim>
 template<class DataHandle>
 void BulkGridView<dim>::communicate(DataHandle& dh, InterfaceType iftype, CommunicationDirection dir, cudaStream_t s) const {

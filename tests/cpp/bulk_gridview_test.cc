@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
+#include <iterator>
 #include <sstream>
 #include <numeric>
 #include <set>
@@ -117,6 +119,27 @@ void deviceChecks() {
   bool filled = true;
   for (std::int64_t e = 0; e < n; ++e) filled = filled && std::abs(after[e] - cen[e]) <= 1e-14;   // wrapped centres equal the images' (up to rounding of i*h + L)
   CHECK(filled);
+  // GlobalIndexSet on one rank without periodic copies: a permutation of 0..size-1 (utility/globalindexset.hh)
+  {
+    BulkYaspGrid<dim> plain(L, s, std::bitset<dim>(), 1);
+    auto pv = plain.leafGridView();
+    for (int codim = 0; codim <= dim; ++codim) {
+      GlobalIndexSet<dim> gis(pv, codim);
+      auto gi = gis.index().toHost();
+      std::set<int> distinct(gi.begin(), gi.end());
+      CHECK(std::int64_t(gis.size(codim)) == pv.size(codim) && gis.size((codim+1)%(dim+1)) == 0);
+      CHECK(std::int64_t(distinct.size()) == pv.size(codim) && *distinct.begin() == 0 && *distinct.rbegin() == int(pv.size(codim))-1);
+    }
+    // VTKWriter: cell data = x coordinate of the centre; the file names the interior cells and the field
+    auto pel = pv.template elements<0>(All_Partition);
+    VTKWriter<dim> vtk(pv);
+    vtk.addCellData(pel.center.data(), "xcenter");
+    const std::string file = vtk.write("bulk_gridview_test_out", "/tmp");
+    std::ifstream in(file);
+    std::string all((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    CHECK(file == "/tmp/bulk_gridview_test_out.vtu" && all.find("<CellData Scalars=\"xcenter\">") != std::string::npos);
+    CHECK(all.find("NumberOfCells=\"" + std::to_string(pv.size(0)) + "\"") != std::string::npos);
+  }
   // FV functor: three steps conserve mass while the shell is away from the boundary (b = 0), 0 <= c <= 1
   if (dim == 3) {
     std::array<double,dim> L1; L1.fill(1.0); std::array<int,dim> s1; s1.fill(48);
