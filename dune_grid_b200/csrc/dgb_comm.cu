@@ -94,9 +94,35 @@ __device__ __forceinline__ void halo_box(const PlanBox& b, const ArrayTable& arr
   }
 }
 
+// the receiving side of the fused FV exchange, folded into the first unpack launch: thread s waits until rank s has
+// delivered epoch `target` (a 20 s timeout marks a peer that never arrives instead of hanging the device), CTA 0 reduces
+// the published CFL maxima
+__device__ __forceinline__ void halo_wait(const HaloWait& hw) {
+  const int s = threadIdx.x;
+  if (s < hw.nranks) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      unsigned f;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&hw.ctl->flags[s]) : "memory");
+      if (int(f - hw.target) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 20000000000ull) { hw.ctl->timeout = 1u; break; }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && s == 0) {
+    double m = 0.0;
+    for (int r = 0; r < hw.nranks; ++r) m = fmax(m, *reinterpret_cast<volatile double*>(&hw.ctl->cfl[hw.parity][r]));
+    *hw.slot = m;
+  }
+}
+
 template<int MODE>   // 0 pack (gather), unpack: 1 set, 2 add, 3 min of non-negative, 4 set if non-negative
 __global__ void __launch_bounds__(PACK_THREADS) k_halo(const PlanBox* __restrict__ boxes, const ArrayTable arrays, double* __restrict__ buffer,
-                                                       const __grid_constant__ HaloGroup grp) {
+                                                       const __grid_constant__ HaloGroup grp, const HaloWait hw) {
+  if (hw.ctl) halo_wait(hw);
   int bi = 0;
   while (bi+1 < grp.nboxes && int(blockIdx.x) >= grp.start[bi+1]) ++bi;          // CTA-uniform
   const PlanBox& b = boxes[bi];
@@ -236,8 +262,10 @@ static int make_table(const CommPlan& plan, double* const* d_arrays, const int32
 
 // boxes of one launch share the mapper block size (per-entity run length) and, for unpack, the wave
 static void launch_boxes(CommPlan& plan, const ArrayTable& at, int mode, const std::vector<PlanBox>& host, PlanBox* dev, double* buf,
-                         const std::vector<int>* waveEnd, cudaStream_t stream) {
+                         const std::vector<int>* waveEnd, cudaStream_t stream, const HaloWait* wait = nullptr) {
   std::size_t k = 0, wv = 0;
+  HaloWait hw{nullptr, 0, 0u, 0, nullptr};
+  if (wait) hw = *wait;                                   // only the first launch waits
   while (k < host.size()) {
     std::size_t limit = host.size();
     if (waveEnd) { while (wv < waveEnd->size() && std::size_t((*waveEnd)[wv]) <= k) ++wv; limit = std::size_t((*waveEnd)[wv]); }
@@ -249,11 +277,12 @@ static void launch_boxes(CommPlan& plan, const ArrayTable& at, int mode, const s
     }
     ArrayTable t = at; t.per_entity = int(host[k].block)*plan.items;
     const unsigned grid = unsigned(grp.start[grp.nboxes]);
-    if (mode == 0) k_halo<0><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
-    else if (mode == 1) k_halo<1><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
-    else if (mode == 2) k_halo<2><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
-    else if (mode == 3) k_halo<3><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
-    else k_halo<4><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp);
+    if (mode == 0) k_halo<0><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp, hw);
+    else if (mode == 1) k_halo<1><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp, hw);
+    else if (mode == 2) k_halo<2><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp, hw);
+    else if (mode == 3) k_halo<3><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp, hw);
+    else k_halo<4><<<grid, PACK_THREADS, 0, stream>>>(dev+k, t, buf, grp, hw);
+    hw.ctl = nullptr;
     ++plan.launches;
     k = e;
   }
@@ -305,10 +334,11 @@ int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_a
   return rcu;
 }
 
-int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream) {
+int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream,
+                     const HaloWait* wait) {
   if (int rc = plan.upload()) return rc;
   ArrayTable at; if (int rc = make_table(plan, d_arrays, item_sizes, narrays, at)) return rc;
-  if (plan.nRecvBoxes) launch_boxes(plan, at, op + 1, plan.hostRecv, plan.dRecvBoxes, const_cast<double*>(buf), &plan.recvWaveEnd, stream);
+  if (plan.nRecvBoxes) launch_boxes(plan, at, op + 1, plan.hostRecv, plan.dRecvBoxes, const_cast<double*>(buf), &plan.recvWaveEnd, stream, wait);
   DGB_CUDA(cudaGetLastError());
   return DGB_OK;
 }

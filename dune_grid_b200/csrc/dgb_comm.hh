@@ -43,8 +43,12 @@ int nccl_allreduce(double* d, int op /*0 min, 1 max*/, dgb_comm* comm, cudaStrea
 // rank-ordered concatenation of `bytes` bytes per rank (d_out holds nranks*bytes); one rank: a copy
 int nccl_allgather_bytes(const void* d_in, void* d_out, size_t bytes, dgb_comm* comm, cudaStream_t stream);
 int comm_rank_count(const dgb_comm* comm, int* rank, int* nranks);
+// what the first unpack launch of a fused step waits for before it touches the receive buffer (dgb_fv.cu): the flags of
+// all ranks reaching `target`; CTA 0 then also stores the maximum of the published CFL values into `slot`
+struct HaloWait { struct FusedCtl* ctl; int nranks; unsigned target; int parity; double* slot; };
 // recv boxes scattered from `buf` (laid out like the plan's receive buffer) instead of plan.dRecvBuf
-int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream);
+int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream,
+                     const HaloWait* wait = nullptr);
 
 // ---- fused exchange: the FV step kernel itself packs into the RECEIVERS' buffers through peer-mapped memory (NVLink) and
 // signals completion with a flag; no NCCL call and no second stream in the steady state (dgb_fv.cu) -------------------

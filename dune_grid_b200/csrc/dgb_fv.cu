@@ -1306,12 +1306,14 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
     const int parity = int(fs.epoch & 1u);
     a.pack = fs.dPack + parity; a.packEpoch = fs.epoch + 1u;
     if (int rc = launch_step<false>(fv, a, stream)) return rc;
-    k_fv_wait<<<1, 64, 0, stream>>>(fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4));
-    ++fv->launches;
     const int32_t items[1] = {1};
     double* arrays[1] = { d_c_out };
     const long long before = fv->plan->launches;
-    if (int rc = plan_unpack_from(*fv->plan, fs.recv[parity], DGB_OP_SET, arrays, items, 1, stream)) return rc;
+    // the wait for all ranks' flags (+ CFL reduction) rides on the first unpack launch; ranks that receive nothing (no
+    // overlap cells) still need it for the CFL value
+    const HaloWait hw{fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4)};
+    if (fv->plan->nRecvBoxes == 0) { k_fv_wait<<<1, 64, 0, stream>>>(fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4)); ++fv->launches; }
+    if (int rc = plan_unpack_from(*fv->plan, fs.recv[parity], DGB_OP_SET, arrays, items, 1, stream, &hw)) return rc;
     fv->launches += fv->plan->launches - before;
     int64_t bytes = 0;
     for (auto& sg : fv->plan->sendSeg) if (sg.peer != fv->view.rank) bytes += sg.count*8;
