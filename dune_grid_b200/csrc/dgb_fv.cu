@@ -1345,8 +1345,7 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
       const int32_t items[1] = {1};
       double* arrays[1] = { d_c_out };
       const long long before = fv->plan->launches;
-      static const bool skipx = getenv("DGB_FV_DEBUG_SKIP_EXCHANGE") != nullptr;     // developer timing experiment only
-      if (!skipx) if (int rc = run_plan(fv->grid, *fv->plan, fv->view.rank, DGB_OP_SET, arrays, items, 1, fv->comm, fv->sComm, true)) return rc;
+      if (int rc = run_plan(fv->grid, *fv->plan, fv->view.rank, DGB_OP_SET, arrays, items, 1, fv->comm, fv->sComm, true)) return rc;
       fv->launches += fv->plan->launches - before;
     }
     DGB_CUDA(cudaEventRecord(fv->evDone, fv->sComm));
