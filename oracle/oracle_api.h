@@ -11,6 +11,12 @@
  *                                  available here); ranks are threads (oracle/ref/shim/mpi.h).
  *   oracle/liboracle_port.so       a self-contained C++ restatement of the same algorithms (oracle/port/), which does
  *                                  not need /root/reference and is what travels in git.
+ * Pinning: everything integer (partitioning, boxes, lists, indices, partition types, intersections' topology, communicate,
+ * GlobalIndexSet, BackupRestore text) is pinned by the reference itself - the _ref library IS its code, the port is checked
+ * against it and against the golden vectors generated from it (tests/golden/). PARITY UNPINNED for the floating-point
+ * geometry (AxisAlignedCubeGeometry, MultiLinearGeometry, FieldMatrix inverse): that arithmetic lives in dune-geometry /
+ * dune-common (Depends: dune-geometry >= 2.12, no commit pinned), which are not vendored in the reference tree and not in this
+ * image; both libraries use the stand-ins of oracle/ref/shim and oracle/common, restated from the published algorithms.
  * Every function simulates ALL ranks of a run inside one process ("world").
  *
  * Conventions: entity arrays are in the reference's iteration order for the requested
