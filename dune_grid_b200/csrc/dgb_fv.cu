@@ -475,6 +475,10 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(s), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 
@@ -488,7 +492,8 @@ struct FvRingLane {
   const double* hg;                           // halo duty of this thread: its halo cell in c, plane 0 of the chunk ...
   int hoff;                                   // ... and its shared-memory element offset relative to `own`
   int ox, oy;                                 // shared-memory element offsets of the upwind x / y neighbour (0: none)
-  bool active, hasHalo;
+  int poff;                                   // A16: shared-memory offset (relative to `own`) of the cell PAIR this thread stages
+  bool active, hasHalo, loader;               // loader (A16): this thread stages a pair; g then points at the pair
 };
 // slow path extras
 struct FvRingSlow { double alt0, alt1, alt2, alt3, un4; unsigned flags; };
@@ -500,10 +505,13 @@ struct FvZTable { double rw[DGB_RWZ_MAX]; };
 // MODE 0..7: direction triple DX*4+DY*2+DZ of the fast path; 8: per-lane flags.
 // Threads outside the region (partial tiles) stage nothing and store nothing but run the same arithmetic (on the
 // clamped column of the last valid thread of their row / the last valid row): no divergence around the barriers.
-template<int D, int BX, int BY, int MODE, bool ZPARAM>
+// A16 (rows 16-byte aligned: even row length, even region offset, aligned field): the own cells are staged as PAIRS by half
+// of the threads with 16-byte cp.async - half the LDGSTS instructions and shared-memory store wavefronts of the 8-byte form;
+// the row pitch grows to BX+4 so that pair destinations are 16-byte aligned (left halo in column 1, cells from column 2).
+template<int D, int BX, int BY, int MODE, bool ZPARAM, bool A16>
 __device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, const long long sz, const double* rwz,
                                              const FvZTable& zt, const int zbase, const int zn, const int kload) {
-  constexpr int R = D+2, PX = BX+2, PY = BY+2, SLOT = PX*PY;
+  constexpr int R = D+2, PX = A16 ? BX+4 : BX+2, PY = BY+2, SLOT = PX*PY;
   constexpr bool DX = MODE & 4, DY = MODE & 2, DZ = MODE & 1;
   const long long sz8 = sz*8;
   const char* gl = reinterpret_cast<const char*>(L.g) + (D+1)*sz8;      // own cell of the next plane to stage
@@ -517,7 +525,8 @@ __device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, c
     cp_async_wait<D-1>();                                                                                      \
     __syncthreads();                                                                                           \
     if (!(GUARD) || (K)+1+D <= kload) {                                                                        \
-      if (L.active) cp_async8(const_cast<double*>(prev), gl);                                                  \
+      if (A16) { if (L.loader) cp_async16(const_cast<double*>(prev) + L.poff, gl); }                           \
+      else if (L.active) cp_async8(const_cast<double*>(prev), gl);                                             \
       if (L.hasHalo) cp_async8(const_cast<double*>(prev) + L.hoff, hl);                                        \
     }                                                                                                          \
     cp_async_commit();                                                                                         \
@@ -551,8 +560,9 @@ __device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, c
     c_below = c_here; c_here = c_above;                                                                        \
     w += sz8;                                                                                                  \
   }
-  // plane 0 of the own column
+  // plane 0 of the own column (A16: staged by another thread, so its arrival has to be published first)
   cp_async_wait<D>();
+  if (A16) __syncthreads();
   c_here = *L.own;
   // the loops are deliberately not unrolled: the ring position rotates through three pointers (previous,
   // current, next slot), which keeps the body small enough for the register allocator not to interleave cells
@@ -711,12 +721,12 @@ __device__ __forceinline__ void fv_bulk_loop(FvBulkLane L, const FvRingSlow S, c
 #undef DGB_BULK_CELL
 }
 
-template<int PROBLEM, int D, int BX, int BY, int MINB, bool ZPARAM, bool BULK = false>
+template<int PROBLEM, int D, int BX, int BY, int MINB, bool ZPARAM, bool BULK = false, bool A16 = false>
 __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a,
                                                          const __grid_constant__ FvZTable zt, const int zc) {
-  constexpr int PX = BX+2, PY = BY+2, SLOT = PX*PY;
+  constexpr int PX = A16 ? BX+4 : BX+2, PY = BY+2, SLOT = PX*PY, XO = A16 ? 2 : 1;      // XO: column of the tile's first cell
   static_assert(2*BX + 2*BY <= BX*BY, "one halo cell per thread");
-  extern __shared__ double ring[];                     // [R][PY][PX]
+  extern __shared__ __align__(16) double ring[];       // [R][PY][PX]
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i0 = blockIdx.x*BX + tx;
   const int by = fv_tile_row(a);
@@ -887,7 +897,16 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   L.zhigh = (!perz && ovz1+1 == v.N[2]) ? bval : 0.0;
   L.dt = 0.99*(1.0/(*a.slotIn));
   L.g = a.c + idx0; L.w = a.cnew + idx0;
-  L.own = ring + (ty+1)*PX + (tx+1);
+  L.own = ring + (ty+1)*PX + (tx+XO);
+  L.poff = 0; L.loader = false;
+  if (A16) {                                           // thread t < BX*BY/2 stages the pair (2j, 2j+1) of row r
+    const int t = ty*BX + tx, r = t/(BX/2), j = t - r*(BX/2);
+    const int nxv = min(BX, a.region.size[0]-(int)blockIdx.x*BX), nyv = min(BY, a.region.size[1]-by*BY);
+    L.loader = r < nyv && 2*j < nxv;
+    const int gx = a.region.origin[0]+blockIdx.x*BX+2*j, gy = a.region.origin[1]+by*BY+min(r, nyv-1);
+    if (L.loader) L.g = a.c + ((long long)(cz0-of.origin[2])*sz + (long long)(gy-of.origin[1])*sy + (gx-of.origin[0]));
+    L.poff = ((r+1)*PX + XO + 2*j) - ((ty+1)*PX + tx + XO);
+  }
   // halo duty: thread t stages halo cell t of the tile (left column, right column, bottom row, top row), if that
   // cell is a stored neighbour and - on the fast path, where all columns share the flow direction - on an inflow side
   {
@@ -907,18 +926,19 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     }
     L.hasHalo = need;
     L.hg = need ? a.c + ((long long)(cz0-of.origin[2])*sz + (long long)(gy-of.origin[1])*sy + (gx-of.origin[0])) : a.c;
-    L.hoff = ((hy+1)*PX + (hx+1)) - ((ty+1)*PX + (tx+1));
+    L.hoff = ((hy+1)*PX + (hx+XO)) - ((ty+1)*PX + (tx+XO));
   }
   // prologue: planes 0..D of the chunk
 #pragma unroll
   for (int j = 0; j <= D; ++j) {
     if (j <= kload) {
-      if (active) cp_async8(L.own + j*SLOT, L.g + (long long)j*sz);
+      if (A16) { if (L.loader) cp_async16(L.own + j*SLOT + L.poff, L.g + (long long)j*sz); }
+      else if (active) cp_async8(L.own + j*SLOT, L.g + (long long)j*sz);
       if (L.hasHalo) cp_async8(L.own + j*SLOT + L.hoff, L.hg + (long long)j*sz);
     }
     cp_async_commit();
   }
-  L.c_below = (cz0 > ovz0) ? __ldg(L.g - sz) : zlow;
+  L.c_below = (cz0 > ovz0) ? __ldg(a.c + idx0 - sz) : zlow;
   if (pat < 8) {
     const int mx = dx ? 0 : 1, my = dy ? 2 : 3;
     L.ox = dx ? -1 : 1; L.oy = dy ? -PX : PX;
@@ -928,15 +948,15 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     if (flags >> my & 1u) L.oy = 0;
   }
   switch (pat) {
-    case 0: fv_ring_loop<D, BX, BY, 0, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
-    case 1: fv_ring_loop<D, BX, BY, 1, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
-    case 2: fv_ring_loop<D, BX, BY, 2, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
-    case 3: fv_ring_loop<D, BX, BY, 3, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
-    case 4: fv_ring_loop<D, BX, BY, 4, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
-    case 5: fv_ring_loop<D, BX, BY, 5, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
-    case 6: fv_ring_loop<D, BX, BY, 6, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
-    case 7: fv_ring_loop<D, BX, BY, 7, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
-    default: fv_ring_loop<D, BX, BY, 8, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 0: fv_ring_loop<D, BX, BY, 0, ZPARAM, A16>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 1: fv_ring_loop<D, BX, BY, 1, ZPARAM, A16>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 2: fv_ring_loop<D, BX, BY, 2, ZPARAM, A16>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 3: fv_ring_loop<D, BX, BY, 3, ZPARAM, A16>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 4: fv_ring_loop<D, BX, BY, 4, ZPARAM, A16>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 5: fv_ring_loop<D, BX, BY, 5, ZPARAM, A16>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 6: fv_ring_loop<D, BX, BY, 6, ZPARAM, A16>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    case 7: fv_ring_loop<D, BX, BY, 7, ZPARAM, A16>(L, S, sz, rwz, zt, zbase, zn, kload); break;
+    default: fv_ring_loop<D, BX, BY, 8, ZPARAM, A16>(L, S, sz, rwz, zt, zbase, zn, kload); break;
   }
   cp_async_wait<0>();
   if (active && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = L.dt;
@@ -1050,6 +1070,11 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     const int variant = fv->variant >= 0 ? fv->variant : (a.region.size[0] >= 256 ? 3 : 0);
     const bool wide = variant == 3 || variant == 7 || variant == 8 || variant >= 11;
     const bool bulk_ok = fv->zparam && (reinterpret_cast<uintptr_t>(a.c) & 15u) == 0;
+    // 16-byte staging of the own cells: every pair source must be 16-byte aligned (DGB_FV_A16=0 keeps the 8-byte form)
+    const dgb_box& ofb = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+    static const bool a16env = [] { const char* e = getenv("DGB_FV_A16"); return !(e && atoi(e) == 0); }();
+    const bool a16 = a16env && wide && fv->zparam && (reinterpret_cast<uintptr_t>(a.c) & 15u) == 0 && ofb.size[0] % 2 == 0
+                     && (a.region.origin[0]-ofb.origin[0]) % 2 == 0 && a.region.size[0] % 2 == 0;
     const int zc = fv->zchunk > 0 ? fv->zchunk : auto_zchunk(a.region.size, wide ? 128 : 32, wide ? 4 : 8);
     const bool exact = fv->mode == DGB_FV_EXACT;
     const int pb = fv->problem.id == 1 ? 1 : 0;
@@ -1072,8 +1097,11 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
 #define DGB_RING(D_, BX_, BY_, MINB_)                                                                                \
     { dim3 mblock(BX_, BY_, 1);                                                                                      \
       dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
-      const size_t smem = size_t(D_+2)*(BX_+2)*(BY_+2)*sizeof(double);                                               \
-      if (fv->zparam) { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, true> : k_fv_ring<0, D_, BX_, BY_, MINB_, true>;      \
+      const size_t smem = size_t(D_+2)*(BX_+(a16 ? 4 : 2))*(BY_+2)*sizeof(double);                                  \
+      if (fv->zparam && a16) { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, true, false, true> : k_fv_ring<0, D_, BX_, BY_, MINB_, true, false, true>;  \
+                DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));          \
+                kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); }                                          \
+      else if (fv->zparam) { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, true> : k_fv_ring<0, D_, BX_, BY_, MINB_, true>;      \
                 DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));          \
                 kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); }                                          \
       else { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, false> : k_fv_ring<0, D_, BX_, BY_, MINB_, false>;     \
