@@ -131,3 +131,64 @@ def test_config3_rank_of_1024_cube_descriptor_and_sweep():
         os.environ.pop("DGB_FV_SPLIT_LOCAL", None)
         assert torch.equal(res[0], res[1])
         del res
+
+
+def test_config1_recipes_256x256_against_the_oracle():
+    """config 1: YaspGrid<2> 256x256, the loops of doc/recipes/recipe-integration.cc:90-126 (midpoint rule, 3x3 Gauss rule
+    of order 5, boundary flux of f(x) = x) and the MCMG mapper sweeps of recipe-iterate-over-grid, as bulk sweeps. The
+    per-entity factors are bit-equal to the oracle's; the sums are compared with tolerance 1e-12 relative (the device sum
+    and the CPU loop add in different orders)."""
+    import torch
+    import dune_grid_b200 as dg
+    from tests.common import best_oracle, make_cfg, oracle_world, product_grid
+    cfg = make_cfg(dim=2, N=(256, 256))
+    o = best_oracle()
+    w = oracle_world(o, cfg, 1)
+    g = product_grid(cfg, 0, 1)
+    gv = g.leafGridView()
+    assert gv.size(0) == 65536 and gv.size(1) == 131584 and gv.size(2) == 66049            # SURVEY 8: sizes of config 1
+    # midpoint rule: sum_e u(center) * volume, u(x) = exp(|x|)
+    e, r = gv.elements(0, dg.All_Partition), w.entities(0, 0, 0)
+    center, vol = e["center"].cpu().numpy().T, e["volume"].cpu().numpy()
+    assert np.array_equal(center, r["center"]) and np.array_equal(vol, r["volume"])
+    ref1 = 0.0
+    for c, v in zip(r["center"], r["volume"]):                                             # the recipe's loop, in its order
+        ref1 += np.exp(np.sqrt(c @ c)) * v
+    got1 = (torch.exp(torch.linalg.vector_norm(e["center"], dim=0)) * e["volume"]).sum().item()
+    assert abs(got1 - ref1) <= 1e-12 * abs(ref1)
+    # Gauss rule of order 5 (3 x 3 points): sum_e sum_q u(global(x_q)) * integrationElement * w_q
+    x1, w1 = np.polynomial.legendre.leggauss(3)
+    x1, w1 = 0.5 * (x1 + 1.0), 0.5 * w1
+    qp = np.array([[a, b] for b in x1 for a in x1])
+    wq = np.array([wa * wb for wb in w1 for wa in w1])
+    geo, rg = gv.geometry(qp, dg.All_Partition), w.geometry_eval(0, 0, qp)
+    glob = geo["global"].cpu().numpy()                                                     # (nq, dim, n)
+    assert np.array_equal(np.transpose(glob, (2, 0, 1)), rg["global"])
+    assert np.array_equal(geo["integrationElement"].cpu().numpy().T, rg["detJ"])
+    ref2 = float(np.sum(np.exp(np.linalg.norm(rg["global"], axis=2)) * rg["detJ"] * wq[None, :]))
+    wt = torch.from_numpy(wq).cuda()
+    got2 = (torch.exp(torch.linalg.vector_norm(geo["global"], dim=1)) * geo["integrationElement"] * wt[:, None]).sum().item()
+    assert abs(got2 - ref2) <= 1e-12 * abs(ref2)
+    assert abs(got1 - got2) <= 1e-4 * abs(got2)                                            # the two rules agree to discretisation error
+    # boundary flux: sum over faces without neighbour of f(center) . n * |F|, f(x) = x  (= dim * |domain| = 2)
+    it, ri = gv.intersections(dg.All_Partition), w.intersections(0, 0)
+    nb = it["neighbor"].cpu().numpy().T
+    assert np.array_equal(nb, ri["neighbor"])
+    fc = it["center"].cpu().numpy()                                                        # (faces, dim, n)
+    assert np.array_equal(np.transpose(fc, (2, 0, 1)), ri["center"]) and np.array_equal(it["volume"].cpu().numpy().T, ri["volume"])
+    ref3 = float(np.sum(np.where(ri["neighbor"] == 0, np.einsum("efd,efd->ef", ri["center"], ri["normal"]) * ri["volume"], 0.0)))
+    got3 = 0.0
+    for k in range(4):
+        nrm = torch.tensor(gv.centerUnitOuterNormal(k), dtype=torch.float64, device="cuda")
+        flux = (it["center"][k] * nrm[:, None]).sum(0) * it["volume"][k]
+        got3 += flux[~it["neighbor"][k].bool()].sum().item()
+    assert abs(got3 - ref3) <= 1e-12 * abs(ref3) and abs(got3 - 2.0) <= 1e-12
+    # mapper sweeps: element / vertex / all-codim layouts, index and subIndex (bit-exact)
+    for layout in ([1, 0, 0], [0, 0, 1], [1, 1, 1]):
+        m = dg.MultipleCodimMultipleGeomTypeMapper(gv, layout)
+        assert m.size == w.mapper_size(0, 0, layout)
+        for codim in range(3):
+            if layout[codim]:
+                assert np.array_equal(m.index(codim).cpu().numpy().view(np.uint32), w.mapper_index(0, 0, layout, codim))
+                assert np.array_equal(m.subIndex(codim).cpu().numpy().view(np.uint32).T, w.mapper_subindex(0, 0, layout, codim))
+    w.close()
