@@ -85,3 +85,41 @@ def test_backup_files_follow_the_reference_naming(tmp_path):
     assert os.path.exists(tmp_path / "tp0") and os.path.exists(tmp_path / "tp1")
     r1 = dg.YaspGrid.restore(str(tmp_path / "tp"), "tensorproduct", 1, 2, is_file=True)
     assert r1.backup() == product_grid(cfg, 1, 2).backup()
+
+
+def test_backup_restore_random_sweep():
+    """seeded random configurations (all coordinate containers, periodicity, overlaps, refinement options, rank counts):
+    backup text byte-equal to the reference's on every rank, restored grid equal to the reference's restored grid"""
+    rng = np.random.default_rng(20261020)
+    o = best_oracle()
+    done = 0
+    for _ in range(50):
+        dim = int(rng.integers(2, 4))
+        N = tuple(int(x) for x in rng.integers(4, 11, size=dim))
+        cfg = make_cfg(dim=dim, N=N, mode=int(rng.integers(0, 3)), periodic=int(rng.integers(0, 1 << dim)),
+                       overlap=int(rng.integers(0, 3)), refine=int(rng.integers(0, 3)), keep=int(rng.integers(0, 2)),
+                       lower=tuple(rng.uniform(-1, 0, dim)), upper=tuple(rng.uniform(0.5, 2, dim)))
+        P = int(rng.choice([1, 2, 3, 4, 6]))
+        try:
+            w0 = oracle_world(o, cfg, P)
+        except Exception:
+            continue                                      # the reference rejects the combination (covered in test_host_descriptors)
+        texts = [w0.backup(r) for r in range(P)]
+        w0.close()
+        for r in range(P):
+            assert product_grid(cfg, r, P).backup() == texts[r], (cfg, P, r)
+        if o.kind == "port" and cfg["mode"] == 2:
+            done += 1
+            continue
+        try:
+            w = o.restore(cfg["dim"], cfg["mode"], texts)
+        except Exception:
+            # six significant digits can make the restored tensor coordinates non-monotone or the torus too fine for
+            # the coarse size: the product must reject the text too
+            with pytest.raises(Exception):
+                dg.YaspGrid.restore(texts[0], MODES[cfg["mode"]], 0, P)
+            continue
+        compare_world(w, lambda r: dg.YaspGrid.restore(texts[r], MODES[cfg["mode"]], r, P), cfg["dim"], P, cfg["refine"] + 1)
+        w.close()
+        done += 1
+    assert done >= 20
