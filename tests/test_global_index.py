@@ -49,3 +49,33 @@ def test_global_index_single_rank(cfg):
             assert m == n
             assert np.array_equal(got.cpu().numpy(), ref[0]), (lvl, codim)
     w.close()
+
+
+@pytest.mark.skipif(not (orc.available("ref") and orc.available("port")), reason="needs both oracles")
+def test_port_restatement_random_sweep():
+    """seeded random non-periodic configurations: the restatement equals the reference's class on every rank, level and codim"""
+    rng = np.random.default_rng(20261021)
+    ref, port = orc.load("ref"), orc.load("port")
+    done = 0
+    for _ in range(40):
+        dim = int(rng.integers(2, 4))
+        N = tuple(int(x) for x in rng.integers(4, 11, size=dim))
+        cfg = make_cfg(dim=dim, N=N, mode=int(rng.integers(0, 3)), overlap=int(rng.integers(0, 3)), refine=int(rng.integers(0, 2)),
+                       keep=int(rng.integers(0, 2)))
+        P = int(rng.choice([1, 2, 3, 4, 6, 8]))
+        try:
+            wr = oracle_world(ref, cfg, P)
+        except Exception:
+            continue
+        if any(n < t for n, t in zip(N, wr.torus_dims())):
+            wr.close()                                    # a rank without cells (overlap 0 lets the reference build such grids): its
+            continue                                      # entities are never visited and the reference's result is whatever std::vector<int>(n) holds
+        wp = oracle_world(port, cfg, P)
+        for lvl in range(cfg["refine"] + 1):
+            for codim in range(dim + 1):
+                a, na = wr.global_index(lvl, codim)
+                b, nb = wp.global_index(lvl, codim)
+                assert na == nb and all(np.array_equal(x, y) for x, y in zip(a, b)), (cfg, P, lvl, codim)
+        wr.close(); wp.close()
+        done += 1
+    assert done >= 15
