@@ -357,7 +357,7 @@ void FusedState::release() {
   dPack = nullptr; block = nullptr; ctl = nullptr; recv[0] = recv[1] = nullptr; on = false;
 }
 
-int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs) {
+int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs, bool local_ok) {
   fs.on = false;
   if (nranks > 64) return DGB_OK;                              // FusedCtl capacity (same verdict on every rank)
   const bool multi = nranks > 1;
@@ -372,7 +372,7 @@ int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStre
   for (int k = 0; k < 2; ++k) fs.recv[k] = reinterpret_cast<double*>(static_cast<char*>(fs.block) + ctlBytes + k*buf_bytes(plan.recvTotal));
   std::vector<FusedInfo> all(nranks);
   FusedInfo mine; std::memset(&mine, 0, sizeof(mine));
-  mine.ok = plan.nSendBoxes <= 32 ? 1 : 0;               // FUSED_MAX_BOXES of the step kernels
+  mine.ok = (local_ok && plan.nSendBoxes <= 32) ? 1 : 0;  // FUSED_MAX_BOXES of the step kernels
   mine.recvTotal = plan.recvTotal;
   for (int r = 0; r < 64; ++r) { mine.segOffset[r] = -1; mine.segCount[r] = 0; }
   for (auto& s : plan.recvSeg) { mine.segOffset[s.peer] = s.offset; mine.segCount[s.peer] = s.count; }

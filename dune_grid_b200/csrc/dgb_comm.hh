@@ -83,6 +83,8 @@ struct FusedState {
 };
 // collective over all ranks: allocate and publish this rank's block, map the peers'. Leaves fs.on = false (and DGB_OK) when
 // peer mapping is not available on every rank - the caller then keeps the NCCL path.
-int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs);
+// `local_ok` = false vetoes the fused form for ALL ranks (e.g. a rank without interior cells launches no step kernel and
+// could never signal)
+int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs, bool local_ok = true);
 }
 #endif

@@ -1327,7 +1327,10 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
     fv->fusedTried = true;
     const char* e = getenv("DGB_FV_FUSED");
     if (!(e && atoi(e) == 0) && fv->view.dim == 3 && (exchanges || fv->view.nranks > 1) && (fv->view.nranks == 1 || fv->comm))
-      if (int rc = fused_setup(*fv->plan, fv->view.rank, fv->view.nranks, fv->comm, stream, fv->fused)) return rc;
+    {
+      const bool nonEmpty = a.region.size[0] > 0 && a.region.size[1] > 0 && a.region.size[2] > 0;    // every rank must launch a step kernel
+      if (int rc = fused_setup(*fv->plan, fv->view.rank, fv->view.nranks, fv->comm, stream, fv->fused, nonEmpty)) return rc;
+    }
   }
   if (fv->fused.on) {
     FusedState& fs = fv->fused;
