@@ -326,13 +326,21 @@ struct World {
     }
   }
 
-  World(const orc_spec& s, int nranks) {
+  // `local` (tensor-product restore, yaspgrid.hh:1156-1197): local[p][i] = rank p's own level-0 coordinates incl. overlap
+  typedef std::vector<std::array<std::vector<double>,3>> LocalCoords;
+  World(const orc_spec& s, int nranks, const LocalCoords* local = nullptr) {
     P = nranks; dim = s.dim;
     if (dim != 2 && dim != 3) throw GridError("oracle supports dim 2 and 3");
     sp.dim = dim; sp.mode = s.coord_mode; sp.periodic = s.periodic; sp.overlap = s.overlap; sp.partitioner = s.partitioner;
     sp.refine = s.refine; sp.keep = s.keep_overlap != 0;
     for (int i = 0; i < 3; ++i) { sp.lower[i] = s.lower[i]; sp.upper[i] = s.upper[i]; sp.N[i] = i < dim ? s.N[i] : 1; sp.fixed[i] = s.fixed_dims[i]; }
-    if (sp.mode == 2)
+    if (sp.mode == 2 && local) {
+      for (const auto& rk : *local) for (int i = 0; i < dim; ++i) {
+        if (rk[i].size() <= 1) throw GridError("Setup of a tensorproduct grid requires monotonous sequences of coordinates.");
+        for (std::size_t j = 1; j < rk[i].size(); ++j)
+          if (rk[i][j] < rk[i][j-1]) throw GridError("Setup of a tensorproduct grid requires monotonous sequences of coordinates.");
+      }
+    } else if (sp.mode == 2)
       for (int i = 0; i < dim; ++i) {
         sp.tensor[i].assign(s.tensor[i], s.tensor[i]+sp.N[i]+1);
         if (sp.tensor[i].size() <= 1) throw GridError("Setup of a tensorproduct grid requires monotonous sequences of coordinates.");
@@ -352,7 +360,10 @@ struct World {
         if (rg.sInterior[i] < 2*sp.overlap && (per(i) || rg.sInterior[i] != sp.N[i])) tooSmall = true;
     }
     if (tooSmall) throw GridError("YaspGrid does not support degrees of freedom shared by more than immediately neighboring subdomains.");
-    for (int i = 0; i < dim; ++i) L[i] = sp.mode == 0 ? sp.upper[i] : sp.mode == 1 ? sp.upper[i]-sp.lower[i] : sp.tensor[i][sp.N[i]] - sp.tensor[i][0];
+    for (int i = 0; i < dim; ++i)
+      L[i] = sp.mode == 0 ? sp.upper[i] : sp.mode == 1 ? sp.upper[i]-sp.lower[i]
+           : local ? (*local)[0][i].back() - (*local)[0][i].front()            // _L from the LOCAL coordinates (:1172-1173)
+           : sp.tensor[i][sp.N[i]] - sp.tensor[i][0];
     // level 0: constructors yaspgrid.hh:904-961 (equidistant), :974-1032 (offset), :1043-1138 (tensor product)
     for (int p = 0; p < P; ++p) {
       RankGrid& rg = ranks[p];
@@ -366,6 +377,9 @@ struct World {
           if (oI + sI + ov <= sp.N[i] || per(i)) sOv += ov;
           if (sp.mode == 0) g.coords.setEquidistant(i, (sp.upper[i]/sp.N[i])*sOv, sOv);
           else g.coords.setOffset(i, sp.lower[i], sp.lower[i] + sOv*(sp.upper[i]-sp.lower[i])/sp.N[i], sOv);
+        } else if (local) {                                                   // :1183-1190
+          g.coords.c[i] = (*local)[p][i];
+          g.coords.offset[i] = oI - ((per(i) || oI > 0) ? ov : 0);
         } else {
           const std::vector<double>& in = sp.tensor[i];
           int begin = oI, end = oI + sI + 1, offset = oI;
@@ -888,12 +902,10 @@ int orc_backup(void* w, int rank, char* out, int cap) {
     return int(t.size());
   });
 }
-// BackupRestoreFacility::restore, :146-218. The port restores the equidistant containers with one keepOverlap flag for all
-// levels (what orc_spec can express); the tensor-product variant (:268-346, rank-local coordinates through the private
-// constructor yaspgrid.hh:1156) is only available in the reference-built oracle.
+// BackupRestoreFacility::restore, :146-218 and :268-346 (tensor product: rank-local coordinates through the private
+// constructor yaspgrid.hh:1156-1197). One keepOverlap flag for all levels (what orc_spec can express).
 void* orc_restore(int dim, int coord_mode, int nranks, const char* const* texts) {
   return guarded((void*)nullptr, [&]() -> void* {
-    if (coord_mode == 2) throw std::runtime_error("orc_restore: tensor-product restore is not restated in the port oracle");
     std::istringstream stream(texts[0]);
     std::string input; int version = 0;
     stream >> input >> input >> input >> input; stream >> version;
@@ -915,6 +927,21 @@ void* orc_restore(int dim, int coord_mode, int nranks, const char* const* texts)
     stream >> input >> input;
     for (int i = 0; i < 3; ++i) sp.N[i] = 1;
     for (int i = 0; i < dim; ++i) stream >> sp.N[i];
+    if (coord_mode == 2) {                                                     // :318-334, one text per rank
+      World::LocalCoords local(nranks);
+      for (int p = 0; p < nranks; ++p) {
+        std::istringstream rs(texts[p]);
+        std::string tok;
+        while (rs >> tok && tok != "information:") {}                            // "... Printing TensorProduct Coordinate information:"
+        for (int d = 0; d < dim; ++d) {
+          int size = 0;
+          rs >> tok >> tok; rs >> size; rs >> tok;
+          local[p][d].resize(size);
+          for (int i = 0; i < size; ++i) rs >> local[p][d][i];
+        }
+      }
+      return new World(sp, nranks, &local);
+    }
     double h[3] = {0,0,0}, origin[3] = {0,0,0};
     stream >> input; for (int i = 0; i < dim; ++i) stream >> h[i];
     if (coord_mode == 1) { stream >> input; for (int i = 0; i < dim; ++i) stream >> origin[i]; }

@@ -57,8 +57,6 @@ def test_restored_grid_equals_the_reference(cfg, P):
     w0 = oracle_world(o, cfg, P)
     texts = [w0.backup(r) for r in range(P)]
     w0.close()
-    if o.kind == "port" and cfg["mode"] == 2:
-        pytest.skip("tensor-product restore is only in the reference-built oracle")
     w = o.restore(cfg["dim"], cfg["mode"], texts)
     compare_world(w, lambda r: dg.YaspGrid.restore(texts[r], MODES[cfg["mode"]], r, P), cfg["dim"], P, cfg["refine"] + 1)
     w.close()
@@ -108,9 +106,6 @@ def test_backup_restore_random_sweep():
         w0.close()
         for r in range(P):
             assert product_grid(cfg, r, P).backup() == texts[r], (cfg, P, r)
-        if o.kind == "port" and cfg["mode"] == 2:
-            done += 1
-            continue
         try:
             w = o.restore(cfg["dim"], cfg["mode"], texts)
         except Exception:
