@@ -123,18 +123,18 @@ extern "C" int dgb_global_index(dgb_grid* g, int level, int codim, int32_t* d_ou
     if (int rc = scan.alloc(m*sizeof(int))) return rc;
     if (int rc = counts.alloc((v.nranks+1)*sizeof(long long))) return rc;
     const int32_t items[1] = {1};
-    k_gis_assign<<<unsigned((n+GT-1)/GT), GT, 0, stream>>>(v, codim, n, own.as<double>(), gidx.as<double>());
+    if (n > 0) k_gis_assign<<<unsigned((n+GT-1)/GT), GT, 0, stream>>>(v, codim, n, own.as<double>(), gidx.as<double>());   // a rank may hold no entity at all
     DGB_CUDA(cudaGetLastError());
     if (codim != 0) {                                                  // UniqueEntityPartition, :176-203
       double* arrays[1] = { own.as<double>() };
       if (int rc = dgb_communicate(g, level, &mapper, DGB_All_All_Interface, DGB_ForwardCommunication, DGB_OP_MIN_NONNEG, arrays, items, 1, comm, stream)) return rc;
     }
-    k_gis_flags<<<unsigned((ncells+GT-1)/GT), GT, 0, stream>>>(v, codim, t, ncells, own.as<double>(), flags.as<int>());
+    if (ncells > 0) k_gis_flags<<<unsigned((ncells+GT-1)/GT), GT, 0, stream>>>(v, codim, t, ncells, own.as<double>(), flags.as<int>());
     DGB_CUDA(cudaGetLastError());
     size_t tmpBytes = 0;
     DGB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, flags.as<int>(), scan.as<int>(), int(m), stream));
     if (int rc = tmp.alloc(tmpBytes)) return rc;
-    DGB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, flags.as<int>(), scan.as<int>(), int(m), stream));
+    if (m > 0) DGB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, flags.as<int>(), scan.as<int>(), int(m), stream));
     // counts of all ranks -> my offset and the global size (:338-362)
     long long* dCounts = counts.as<long long>();
     k_gis_total<<<1, GT, 0, stream>>>(flags.as<int>(), scan.as<int>(), m, dCounts + v.nranks);
@@ -146,13 +146,13 @@ extern "C" int dgb_global_index(dgb_grid* g, int level, int codim, int32_t* d_ou
     for (int r = 0; r < v.nranks; ++r) { if (r < v.rank) myoffset += hc[r]; total += hc[r]; }
     if (total >= (1ll << 31)) throw ArgError("global index: more than 2^31 entities (the reference's Index is int)");
     *global_size = total;
-    k_gis_number<<<unsigned((ncells+GT-1)/GT), GT, 0, stream>>>(v, codim, t, ncells, flags.as<int>(), scan.as<int>(), myoffset, gidx.as<double>());
+    if (ncells > 0) k_gis_number<<<unsigned((ncells+GT-1)/GT), GT, 0, stream>>>(v, codim, t, ncells, flags.as<int>(), scan.as<int>(), myoffset, gidx.as<double>());
     DGB_CUDA(cudaGetLastError());
     {                                                                  // IndexExchange, :430-431
       double* arrays[1] = { gidx.as<double>() };
       if (int rc = dgb_communicate(g, level, &mapper, DGB_All_All_Interface, DGB_ForwardCommunication, DGB_OP_SET_NONNEG, arrays, items, 1, comm, stream)) return rc;
     }
-    k_gis_final<<<unsigned((n+GT-1)/GT), GT, 0, stream>>>(gidx.as<double>(), n, d_out);
+    if (n > 0) k_gis_final<<<unsigned((n+GT-1)/GT), GT, 0, stream>>>(gidx.as<double>(), n, d_out);
     DGB_CUDA(cudaGetLastError());
     DGB_CUDA(cudaStreamSynchronize(stream));
     return DGB_OK;
