@@ -9,7 +9,8 @@ configs[2] — 1024^3, overlap 1, DefaultPartitioning over N ranks, communicate(
 over NVLink each step. A "step" is one full FV time step over the whole grid.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref: the unmodified dune-grid YaspGrid
-headers, one thread per rank like its MPI model) on a bounded sample of the same workload.
+headers, one thread per rank like its MPI model, all host cores) on THE SAME grid and step (`config` is identical in
+both arms); --size overrides the cube edge of both arms for local experiments only.
 """
 import argparse
 import json
@@ -17,7 +18,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -26,14 +26,30 @@ sys.path.insert(0, ROOT)
 PARAMS = [1.0, 1.0, 1.0, 0.0, 0.25, 0.25, 0.25, 0.125, 0.2]     # u=(1,1,1), b=0, shell centre/radii
 METRIC = "leaf cells/sec (element+intersection FV sweep)"
 BYTES_PER_CELL = 16                                               # read c (8) + write c_new (8), DESIGN.md
+NVLINK_GBS = 900.0                                                # nominal per direction per GPU (B200_PROFILING.md)
 
 
-def ncu_traffic(kernel_prefix):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary (profiles/), or None"""
+def workload_config(n, n_gpus):
+    """the `config` object of the JSON line: a function of the workload only, so that both arms print the same one"""
+    per_gpu = n ** 3 * 8 / max(1, n_gpus) / 1e9
+    if n_gpus == 1:
+        w = (f"YaspGrid<3> {n}^3 equidistant, overlap 1: explicit first-order finite-volume transport sweep "
+             "(elements+intersections, MCMG mapper, geometry, CFL min-reduction)")
+    else:
+        w = (f"YaspGrid<3> {n}^3 equidistant, overlap 1, DefaultPartitioning over the ranks of the arm: explicit first-order "
+             "finite-volume transport sweep (elements+intersections, MCMG mapper, geometry, CFL min-reduction) + "
+             "communicate(InteriorBorder_All_Interface, ForwardCommunication) halo exchange each step")
+    return {"workload": w, "grid": [n, n, n], "cells": n ** 3, "problem": "u=(1,1,1), b=0, c0 = spherical shell (SURVEY §8d)",
+            "bytes_per_cell": BYTES_PER_CELL,
+            "l2": "inputs larger than L2 (two %.2f GB fields per GPU, ping-pong): no flush needed" % per_gpu}
+
+
+def ncu_traffic(pattern, kernel_prefix):
+    """DRAM bytes per launch of the dominant kernel from the newest committed `ncu --set full` summary (profiles/), or None"""
     try:
         import glob
         best = None
-        for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_fv_ring_ncu_full.json"))):
+        for path in sorted(glob.glob(os.path.join(ROOT, "profiles", pattern))):
             for rec in json.load(open(path)):
                 if kernel_prefix in rec.get("kernel", "") and "traffic_bytes" in rec:
                     best = (rec["traffic_bytes"], os.path.basename(path))
@@ -117,13 +133,42 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa(local):
+    """pin this process to the CPUs next to its GPU BEFORE any pinned host buffer is allocated, so that the buffers of the
+    end-to-end path are NUMA-local to the GPU (first touch); best effort, reports what it did"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        index = local
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x for x in vis.split(",") if x.strip() != ""]
+            if local < len(ids) and ids[local].strip().isdigit():
+                index = int(ids[local])
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        near = {i * 64 + b for i, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(near & allowed)
+        if not cpus:
+            return {"bound": False, "why": "no allowed CPU next to the GPU", "allowed": len(allowed)}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "cpus": f"{cpus[0]}-{cpus[-1]}", "count": len(cpus)}
+    except Exception as e:                                      # noqa: BLE001
+        return {"bound": False, "why": str(e)[:80]}
+
+
 def cpu_reference_run(n, P, steps, warmup):
-    """the reference's CPU path (oracle/_ref, else the port) on an n^3 grid with P thread-ranks; returns cells/s"""
+    """the reference's CPU path (oracle/_ref, else the port) on an n^3 grid with P thread-ranks; returns cells/s.
+    This function and run_reference are the ONLY places of bench.py that execute anything under oracle/."""
+    from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle as orc
     kind = "ref" if orc.available("ref") else "port"
     o = orc.load(kind)
     w = o.world(orc.Spec(dim=3, N=(n, n, n)), P)
-    c = [w.fv_init(r, 0, 0, PARAMS) for r in range(P)]
+    with ThreadPoolExecutor(max_workers=P) as ex:                # the per-rank initialisation runs concurrently (world is only read)
+        c = list(ex.map(lambda r: w.fv_init(r, 0, 0, PARAMS), range(P)))
     if warmup:
         w.fv_run(0, 0, PARAMS, c, warmup)
     secs, _ = w.fv_run(0, 0, PARAMS, c, steps)
@@ -132,40 +177,89 @@ def cpu_reference_run(n, P, steps, warmup):
 
 
 def feasible_ranks(n, maxp):
-    """largest rank count <= maxp that DefaultPartitioning accepts for an n^3 grid and that is a power of two"""
+    """largest power of two <= maxp (DefaultPartitioning accepts every power of two for a power-of-two cube)"""
     p = 1
     while p * 2 <= maxp:
         p *= 2
     return p
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    P = feasible_ranks(args.ref_size, min(cores, 64))
-    n = args.ref_size
+    cores = host_cores()
+    n = args.size or (512 if args.gpus == 1 else 1024)
+    P = feasible_ranks(n, min(cores, 64))
     t0 = time.time()
-    val, kind, secs = cpu_reference_run(n, P, max(1, args.steps), min(args.warmup, 1))
-    workload = ("YaspGrid<3> 512^3 equidistant FV sweep" if args.gpus == 1 else "YaspGrid<3> 1024^3 overlap=1 FV sweep + halo exchange")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
+    steps = max(1, args.steps)
+    val, kind, secs = cpu_reference_run(n, P, steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "cells/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True,
             "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "sample": f"{n}^3 cells per step on {P} thread-ranks"},
+            "config": workload_config(n, args.gpus),
             "cpu_baseline": {"value": val, "unit": "cells/s", "cores": P, "kind": kind,
-                             "sample": f"{max(1, args.steps)} FV steps on a {n}^3 YaspGrid, {P} ranks (threads) of {cores} host cores"},
+                             "sample": f"{steps} FV steps (after {min(args.warmup, 1)} warm-up) on the full {n}^3 YaspGrid, "
+                                       f"{P} ranks (threads) of {cores} host cores, {secs:.1f} s"},
             "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "wall_s": time.time() - t0}
+            "ranks": P, "wall_s": time.time() - t0}
     print(json.dumps(line), flush=True)
 
 
+def parity_check(dg, torch, dist, rank, world, comm, dims, mode):
+    """multi-GPU parity inside the scaling run: 3 steps of the SAME public step (fused peer-memory exchange) on a smaller grid
+    with the partition of the timed grid (FixedSizePartitioning with its torus; 256 x 64 x 64 cells per rank, so the wide
+    128x4 tile and the odd row strides of the timed run are what is exercised), every rank compares ALL its stored cells
+    (interior + refreshed overlap) with the CPU oracle's rank of the same number. Oracle = checker only."""
+    import numpy as np
+    from oracle import oracle as orc
+    kind = "ref" if orc.available("ref") else "port"
+    o = orc.load(kind)
+    N = (256 * dims[0], 64 * dims[1], 64 * dims[2])
+    upper = (1.0, 0.25 * dims[1] / dims[0], 0.25 * dims[2] / dims[0])        # cubic cells
+    params = [1.0, 0.6, -0.8, 0.0, 0.3, upper[1] / 2, upper[2] / 2, 0.05, 0.2]
+    w = o.world(orc.Spec(dim=3, N=N, upper=upper, partitioner=2, fixed_dims=dims), world)
+    ref = [w.fv_init(r, 0, 0, params) for r in range(world)]
+    g = dg.YaspGrid(dim=3, N=N, upper=upper, overlap=1, rank=rank, nranks=world, comm=comm, partitioner="fixed", fixed_dims=dims)
+    fv = dg.FiniteVolume(g, 0, 0, params, mode)
+    c = fv.initial()
+    ok = bool(np.array_equal(c.cpu().numpy(), ref[rank]))
+    cn = torch.empty_like(c)
+    steps, dt_rel = 3, 0.0
+    for _ in range(steps):
+        dt_ref = w.fv_step(0, 0, params, ref)
+        fv.step(c, cn)
+        c, cn = cn, c
+        dt_rel = max(dt_rel, abs(fv.last_dt() - dt_ref) / dt_ref)
+    scale = max(float(np.abs(x).max()) for x in ref)
+    err = float(np.abs(c.cpu().numpy() - ref[rank]).max()) / scale
+    moved = bool(np.abs(ref[rank]).max() > 0)
+    tol = 0.0 if mode == "exact" else 1e-13
+    ok = ok and err <= tol and dt_rel <= tol and moved
+    info, xmode = fv.kernel_info(), fv.exchange_mode()
+    fv.close()
+    w.close()
+    t = torch.tensor([err, dt_rel, 0.0 if ok else 1.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"grid": list(N), "partition": list(dims), "steps": steps, "max_rel": t[0].item(), "dt_rel": t[1].item(), "tol": tol,
+            "ok": t[2].item() == 0.0, "oracle": "reference" if kind == "ref" else "port", "exchange": xmode,
+            "kernel": f"{info['kind']} {info['tile'][0]}x{info['tile'][1]} staging {info['staging_bytes']} B"}
+
+
 def run_gpu(args):
-    import torch
-    import dune_grid_b200 as dg
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa(local) if world > 1 else {"bound": False, "why": "single GPU: all cores stay available to the CPU baseline"}
+    import torch
+    import dune_grid_b200 as dg
     torch.cuda.set_device(local)
     dist = None
     comm = None
@@ -180,6 +274,8 @@ def run_gpu(args):
     interior = gv.size(0, dg.Interior_Partition)
     c = fv.initial()
     cn = torch.empty_like(c)
+    if world > 1 and not args.no_register:
+        fv.register_fields(c, cn)               # collective: peers may then store halo cells straight into these two arrays
 
     def barrier():
         torch.cuda.synchronize()
@@ -206,6 +302,8 @@ def run_gpu(args):
     ms = ev0.elapsed_time(ev1)
     launches = fv.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
+    kinfo, xmode = fv.kernel_info(), fv.exchange_mode()
+    fv.last_dt()                                # raises if the fused exchange timed out anywhere in the run
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -218,6 +316,46 @@ def run_gpu(args):
     assert abs(total_cells - n ** 3) < 0.5
     value = total_cells * args.steps / (ms * 1e-3)
 
+    # the halo exchange on its own (N>1): (i) exposed cost inside the step = step time - time of the same kernel without
+    # exchange; (ii) the same halo through the stand-alone dgb_communicate (pack, NCCL send/recv over NVLink, unpack)
+    halo = None
+    if dist is not None and not args.no_halo:
+        hs = max(5, min(args.steps, 50))
+        sent = g.lastBytesSent()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        barrier()
+        ev[0].record()
+        for _ in range(hs):
+            fv.step_local(c, cn)
+            c, cn = cn, c
+        ev[1].record()
+        barrier()
+        m = dg.MultipleCodimMultipleGeomTypeMapper(gv, dg.mcmgElementLayout(3))
+        for _ in range(3):
+            gv.communicate(m, [c], dg.InteriorBorder_All_Interface, dg.ForwardCommunication, "set")
+        barrier()
+        ev[2].record()
+        for _ in range(hs):
+            gv.communicate(m, [c], dg.InteriorBorder_All_Interface, dg.ForwardCommunication, "set")
+        ev[3].record()
+        barrier()
+        t = torch.tensor([ev[0].elapsed_time(ev[1]) / hs, ev[2].elapsed_time(ev[3]) / hs, float(sent)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        local_ms, comm_ms, max_sent = t[0].item(), t[1].item(), t[2].item()
+        exposed = max(ms / args.steps - local_ms, 1e-6)
+        halo = {"bytes_per_rank": int(max_sent), "note": "max over ranks of the bytes one rank sends per step (= receives)",
+                "step_ms": ms / args.steps, "kernel_only_ms": local_ms, "exchange_ms": exposed,
+                "nvlink_gbs": max_sent / (exposed * 1e-3) / 1e9, "frac_of_900": max_sent / (exposed * 1e-3) / 1e9 / NVLINK_GBS,
+                "how": "exchange_ms = step time minus the time of the same step kernel without exchange (the fused kernel stores into "
+                       "the peers' memory while it computes, so only this exposed part costs time); nvlink_gbs = bytes_per_rank / exchange_ms",
+                "standalone": {"ms": comm_ms, "nvlink_gbs": max_sent / (comm_ms * 1e-3) / 1e9,
+                               "frac_of_900": max_sent / (comm_ms * 1e-3) / 1e9 / NVLINK_GBS,
+                               "how": "dgb_communicate(InteriorBorder_All, Forward) of the same field alone: pack kernel + grouped "
+                                      "ncclSend/ncclRecv + unpack kernel, nothing overlapped"}}
+        # the local steps left the overlap cells stale: refresh them before anything else uses the field
+        gv.communicate(m, [c], dg.InteriorBorder_All_Interface, dg.ForwardCommunication, "set")
+        barrier()
+
     # end to end through the reference-facing C-ABI call with HOST buffers (copies inside the timed region)
     e2e = None
     if not args.no_e2e:
@@ -227,6 +365,7 @@ def run_gpu(args):
         h_in.copy_(c)
         ksteps = max(1, min(args.steps, args.e2e_steps))
         fv.step_host(h_in, h_out)                 # warm-up (allocates the staging buffers)
+        h_in, h_out = h_out, h_in
         barrier()
         t0 = time.perf_counter()
         for _ in range(ksteps):
@@ -239,37 +378,64 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             secs = t.item()
         e2e = {"value": total_cells * ksteps / secs, "unit": "cells/s", "h2d_bytes_per_step": ncell * 8 * world,
-               "d2h_bytes_per_step": ncell * 8 * world + 8 * world, "steps": ksteps}
+               "d2h_bytes_per_step": ncell * 8 * world + 8 * world, "steps": ksteps,
+               "pcie_gbs_per_gpu_per_direction": ncell * 8 * ksteps / secs / 1e9, "host_path": fv.host_path()}
+        del h_in, h_out
+
+    parity = None
+    if dist is not None and not args.no_parity:
+        parity = parity_check(dg, torch, dist, rank, world, comm, g.torusDims(), args.mode)
 
     if rank == 0:
         peak, peak_src = peaks()
         kernel_ms = ms / args.steps
-        traffic = ncu_traffic("k_fv_ring") if (world == 1 and n == 512 and args.mode == "separable") else None
+        if world == 1 and n == 512 and args.mode == "separable":
+            traffic = ncu_traffic("r*_fv_ring_ncu_full.json", "k_fv_ring")
+        elif world > 1 and n == 1024 and args.mode == "separable":
+            traffic = ncu_traffic("r*_fv_ring_stride513_ncu_full.json", "k_fv_ring")
+        else:
+            traffic = None
         achieved = BYTES_PER_CELL * (total_cells / world) / (kernel_ms * 1e-3) / 1e9
+        cfg = workload_config(n, world)
         line = {"metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": (f"YaspGrid<3> {n}^3 equidistant: explicit first-order FV transport sweep "
-                                        "(elements+intersections, CFL min-reduction)" + ("" if world == 1 else
-                                        f", overlap=1, DefaultPartitioning {g.torusDims()}, communicate(InteriorBorder_All) each step")),
-                           "fv_mode": args.mode, "l2": "inputs (2 x %.2f GB fields per GPU) larger than L2; no flush needed" % (gv.size(0) * 8 / 1e9),
-                           "bytes_per_cell": BYTES_PER_CELL},
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "fv_mode": args.mode, "partition": list(g.torusDims()),
+                "kernel": {"kind": kinfo["kind"], "tile": list(kinfo["tile"]), "staging_bytes": kinfo["staging_bytes"],
+                           "zchunk": kinfo["zchunk"], "exchange": xmode, "registered_fields": bool(world > 1 and not args.no_register)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic[0] if traffic else None,
-                             "traffic_source": (traffic[1] + " (ncu --set full, 512^3 launch of k_fv_ring)") if traffic else None,
+                             "traffic_source": (traffic[1] + " (ncu --set full capture of one k_fv_ring launch on a box of this shape, "
+                                                "committed under profiles/; not re-measured in this run)") if traffic else None,
                              "algorithmic_bytes_per_launch": BYTES_PER_CELL * (total_cells / world), "peak_source": peak_src,
-                             "note": "per-GPU algorithmic bytes (16 B x interior cells) / mean step time (one fused kernel per step"
-                                     + ("" if world == 1 else " + pack/unpack + NCCL") + ")"},
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
-        if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
-            P = feasible_ranks(args.ref_size, min(cores, 64))
-            val, kind, secs = cpu_reference_run(args.ref_size, P, 24, 1)
+                             "note": "per-GPU algorithmic bytes (16 B x interior cells) / mean step time; one fused kernel per step"
+                                     + ("" if world == 1 else " that also stores the halo into the peers' memory over NVLink (no NCCL call in the "
+                                        "steady state) + a one-CTA flag wait (+ an unpack kernel when the fields are not registered)")},
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "numa": numa}
+        if halo:
+            line["halo"] = halo
+        if parity:
+            line["parity_check"] = parity
+        if not args.no_cpu:
+            cores = host_cores()
+            P = feasible_ranks(n, min(cores, 64))
+            csteps = args.cpu_steps or (8 if n <= 512 else 2)
+            val, kind, secs = cpu_reference_run(n, P, csteps, 1 if n <= 512 else 0)
             line["cpu_baseline"] = {"value": val, "unit": "cells/s", "cores": P, "kind": kind,
-                                    "sample": f"24 FV steps on a {args.ref_size}^3 YaspGrid, {P} ranks (threads) of {cores} host cores, {secs:.1f} s"}
+                                    "sample": f"{csteps} FV steps on the full {n}^3 YaspGrid, {P} ranks (threads) of {cores} host cores, {secs:.1f} s"}
         print(json.dumps(line), flush=True)
     if dist is not None:
+        # the other ranks wait for rank 0's CPU baseline in a socket wait (no spinning next to the CPU threads being timed)
+        try:
+            store = dist.distributed_c10d._get_default_store()
+            if rank == 0:
+                store.set("dgb_bench_done", "1")
+            else:
+                store.wait(["dgb_bench_done"])
+        except Exception:                        # noqa: BLE001
+            pass
         dist.barrier()
+        fv.close()                               # collective teardown of the fused exchange: before the communicator goes away
         comm.close()
         dist.destroy_process_group()
 
@@ -281,13 +447,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="separable", choices=["separable", "exact"])
-    ap.add_argument("--size", type=int, default=0, help="override the cube edge (default 512 at N=1, 1024 at N>1)")
-    ap.add_argument("--ref-size", type=int, default=256, help="cube edge of the bounded CPU sample")
+    ap.add_argument("--size", type=int, default=0, help="override the cube edge (default 512 at N=1, 1024 at N>1) - local experiments only")
+    ap.add_argument("--cpu-steps", type=int, default=0, help="steps of the cpu_baseline sample (default 8 at 512^3, 2 at 1024^3)")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-halo", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-register", action="store_true", help="N>1: keep the receive-buffer + unpack form of the fused exchange")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.steps == 1000 and args.warmup == 20:      # no flags: a CPU-sized default
+            args.steps, args.warmup = 10, 1
         run_reference(args)
     else:
         run_gpu(args)

@@ -288,8 +288,15 @@ int dgb_grid_global_refine(dgb_grid* g, int refCount) {
     std::lock_guard<std::mutex> lk(g->mtx);
     g->plans.clear();
     if (refCount < 0) {
-      free_dev_coords(g);
-      for (int k = refCount; k < 0; ++k) { g->me.levels.pop_back(); for (auto& o : g->all) o.levels.pop_back(); }
+      // only the device coordinate arrays of the popped levels are freed: views of the surviving levels (dgb_view::tensor)
+      // held by callers keep pointing at live memory
+      for (int k = refCount; k < 0; ++k) {
+        g->me.levels.pop_back(); for (auto& o : g->all) o.levels.pop_back();
+        if (g->devCoords.size() > g->me.levels.size()) {
+          for (int i = 0; i < 3; ++i) if (g->devCoords.back().d[i]) cudaFree(g->devCoords.back().d[i]);
+          g->devCoords.pop_back();
+        }
+      }
     }
     for (int k = 0; k < refCount; ++k) {
       if (g->me.levels.size() >= 32) throw GridError("at most 32 levels (ReservedVector<YGridLevel,32>)");

@@ -32,6 +32,7 @@ struct NcclApi {
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   std::string error;
   bool load() {
@@ -43,6 +44,7 @@ struct NcclApi {
     DGB_SYM(GetUniqueId, "ncclGetUniqueId") DGB_SYM(CommInitRank, "ncclCommInitRank") DGB_SYM(CommDestroy, "ncclCommDestroy")
     DGB_SYM(Send, "ncclSend") DGB_SYM(Recv, "ncclRecv") DGB_SYM(AllReduce, "ncclAllReduce") DGB_SYM(AllGather, "ncclAllGather")
     DGB_SYM(GroupStart, "ncclGroupStart") DGB_SYM(GroupEnd, "ncclGroupEnd") DGB_SYM(GetErrorString, "ncclGetErrorString")
+    DGB_SYM(CommGetAsyncError, "ncclCommGetAsyncError")
 #undef DGB_SYM
     return true;
   }
@@ -97,8 +99,11 @@ __device__ __forceinline__ void halo_box(const PlanBox& b, const ArrayTable& arr
 // the receiving side of the fused FV exchange, folded into the first unpack launch: thread s waits until rank s has
 // delivered epoch `target` (a 20 s timeout marks a peer that never arrives instead of hanging the device), CTA 0 reduces
 // the published CFL maxima
-__device__ __forceinline__ void halo_wait(const HaloWait& hw) {
+__device__ __forceinline__ bool halo_wait(const HaloWait& hw) {
+  __shared__ int s_timed_out;
   const int s = threadIdx.x;
+  if (s == 0) s_timed_out = 0;
+  __syncthreads();
   if (s < hw.nranks) {
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -107,22 +112,28 @@ __device__ __forceinline__ void halo_wait(const HaloWait& hw) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&hw.ctl->flags[s]) : "memory");
       if (int(f - hw.target) >= 0) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 20000000000ull) { hw.ctl->timeout = 1u; break; }
+      if (hw.ctl->timeout || t1 - t0 > 20000000000ull) {              // sticky: also seen by the host before the next step
+        hw.ctl->timeout = 1u; s_timed_out = 1;
+        if (hw.hostTimeout) { *reinterpret_cast<volatile unsigned*>(hw.hostTimeout) = 1u; __threadfence_system(); }
+        break;
+      }
       __nanosleep(64);
     }
   }
   __syncthreads();
+  if (s_timed_out) return false;                                      // never scatter a buffer a peer has not completed
   if (blockIdx.x == 0 && s == 0) {
     double m = 0.0;
     for (int r = 0; r < hw.nranks; ++r) m = fmax(m, *reinterpret_cast<volatile double*>(&hw.ctl->cfl[hw.parity][r]));
     *hw.slot = m;
   }
+  return true;
 }
 
 template<int MODE>   // 0 pack (gather), unpack: 1 set, 2 add, 3 min of non-negative, 4 set if non-negative
 __global__ void __launch_bounds__(PACK_THREADS) k_halo(const PlanBox* __restrict__ boxes, const ArrayTable arrays, double* __restrict__ buffer,
                                                        const __grid_constant__ HaloGroup grp, const HaloWait hw) {
-  if (hw.ctl) halo_wait(hw);
+  if (hw.ctl && !halo_wait(hw)) return;
   int bi = 0;
   while (bi+1 < grp.nboxes && int(blockIdx.x) >= grp.start[bi+1]) ++bi;          // CTA-uniform
   const PlanBox& b = boxes[bi];
@@ -238,6 +249,7 @@ int CommPlan::upload() {
   return DGB_OK;
 }
 CommPlan::~CommPlan() {
+  if (busy) cudaEventDestroy(busy);
   if (dSendBoxes) cudaFree(dSendBoxes);
   if (dRecvBoxes) cudaFree(dRecvBoxes);
   if (dSendBuf) cudaFree(dSendBuf);
@@ -264,7 +276,7 @@ static int make_table(const CommPlan& plan, double* const* d_arrays, const int32
 static void launch_boxes(CommPlan& plan, const ArrayTable& at, int mode, const std::vector<PlanBox>& host, PlanBox* dev, double* buf,
                          const std::vector<int>* waveEnd, cudaStream_t stream, const HaloWait* wait = nullptr) {
   std::size_t k = 0, wv = 0;
-  HaloWait hw{nullptr, 0, 0u, 0, nullptr};
+  HaloWait hw{nullptr, 0, 0u, 0, nullptr, nullptr};
   if (wait) hw = *wait;                                   // only the first launch waits
   while (k < host.size()) {
     std::size_t limit = host.size();
@@ -311,6 +323,8 @@ int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_a
   for (auto& s : plan.sendSeg) if (s.peer != myrank) remote = true;
   for (auto& s : plan.recvSeg) if (s.peer != myrank) remote = true;
   if (remote && !comm) return fail(DGB_EARG, "this exchange has remote partners: a dgb_comm is required");
+  if (remote) if (int rc = nccl_check_async(comm)) return rc;
+  if (int rc = plan.enter(stream)) return rc;
   if (packed) { if (int rc = plan.upload()) return rc; }
   else if (int rc = plan_pack(plan, d_arrays, item_sizes, narrays, stream)) return rc;
   if (plan.trace[0]) cudaEventRecord(plan.trace[0], stream);
@@ -331,6 +345,7 @@ int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_a
   if (plan.trace[1]) cudaEventRecord(plan.trace[1], stream);
   const int rcu = plan_unpack(plan, op, d_arrays, item_sizes, narrays, stream);
   if (plan.trace[2]) cudaEventRecord(plan.trace[2], stream);
+  if (int rc = plan.leave(stream)) return rc;
   return rcu;
 }
 
@@ -348,13 +363,34 @@ int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d
 // segment in the receive buffers (-1: no message from that rank)
 struct FusedInfo { cudaIpcMemHandle_t handle; long long segOffset[64]; long long segCount[64]; long long recvTotal; int ok; int pad; };
 
-void FusedState::release() {
+void FusedState::release(bool free_block) {
   for (void* p : opened) cudaIpcCloseMemHandle(p);
   opened.clear();
   for (int k = 0; k < 2; ++k) { if (dDst[k]) cudaFree(dDst[k]); dDst[k] = nullptr; }
   if (dPack) cudaFree(dPack);
-  if (block) cudaFree(block);
-  dPack = nullptr; block = nullptr; ctl = nullptr; recv[0] = recv[1] = nullptr; on = false;
+  if (block && free_block) cudaFree(block);
+  if (hTimeout) cudaFreeHost(hTimeout);
+  dPack = nullptr; block = nullptr; ctl = nullptr; recv[0] = recv[1] = nullptr; hTimeout = dTimeout = nullptr; on = false; multi = false;
+}
+
+int fused_teardown(FusedState& fs, dgb_comm* comm, cudaStream_t stream) {
+  const bool collective = fs.multi && comm && comm->nranks > 1;
+  if (!fs.block && !collective) { fs.release(); return DGB_OK; }
+  cudaStreamSynchronize(stream);
+  for (void* p : fs.opened) cudaIpcCloseMemHandle(p);              // 1. nobody keeps a mapping of a peer's block ...
+  fs.opened.clear();
+  int rc = DGB_OK;
+  if (collective) {                                                // 2. ... and every rank knows that ...
+    double* d = nullptr;
+    if (cudaMalloc(&d, sizeof(double)) == cudaSuccess) {
+      cudaMemsetAsync(d, 0, sizeof(double), stream);
+      if (g_nccl.AllReduce(d, d, 1, ncclDouble, ncclMax, comm->comm, stream) != ncclSuccess) rc = DGB_ENCCL;
+      cudaStreamSynchronize(stream);
+      cudaFree(d);
+    } else rc = DGB_ECUDA;
+  }
+  fs.release(rc == DGB_OK);                                         // 3. ... before any exported block is freed
+  return rc;
 }
 
 int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs, bool local_ok) {
@@ -362,85 +398,125 @@ int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStre
   if (nranks > 64) return DGB_OK;                              // FusedCtl capacity (same verdict on every rank)
   const bool multi = nranks > 1;
   if (multi && !comm) return DGB_OK;
-  if (int rc = plan.upload()) return rc;
+  // Every rank takes part in BOTH collectives below (all-gather of the handles, all-reduce of the verdict) whatever fails
+  // locally: a local failure only turns this rank's vote into "no", it never leaves the peers blocked in a collective.
+  bool ok = local_ok && plan.nSendBoxes <= 32;                 // FUSED_MAX_BOXES of the step kernels
+  std::string why;
+  auto soft = [&](cudaError_t e, const char* what) { if (e != cudaSuccess) { cudaGetLastError(); if (ok) why = std::string(what) + ": " + cudaGetErrorString(e); ok = false; } return e == cudaSuccess; };
+  if (plan.upload() != DGB_OK) ok = false;
   auto round256 = [](size_t b) { return (b + 255)/256*256; };
   const size_t ctlBytes = round256(sizeof(FusedCtl));
   auto buf_bytes = [&](long long doubles) { return round256(size_t(doubles)*sizeof(double)); };
-  DGB_CUDA(cudaMalloc(&fs.block, ctlBytes + 2*buf_bytes(plan.recvTotal)));
-  DGB_CUDA(cudaMemset(fs.block, 0, ctlBytes + 2*buf_bytes(plan.recvTotal)));
+  const size_t blockBytes = ctlBytes + 2*buf_bytes(plan.recvTotal);
+  if (soft(cudaMalloc(&fs.block, blockBytes), "cudaMalloc(fused block)")) soft(cudaMemset(fs.block, 0, blockBytes), "cudaMemset(fused block)");
+  else fs.block = nullptr;
+  if (soft(cudaHostAlloc(reinterpret_cast<void**>(&fs.hTimeout), sizeof(unsigned), cudaHostAllocMapped), "cudaHostAlloc(timeout word)")) {
+    *fs.hTimeout = 0u;
+    soft(cudaHostGetDevicePointer(reinterpret_cast<void**>(&fs.dTimeout), fs.hTimeout, 0), "cudaHostGetDevicePointer");
+  } else fs.hTimeout = nullptr;
+  fs.multi = multi;
   fs.ctl = static_cast<FusedCtl*>(fs.block);
-  for (int k = 0; k < 2; ++k) fs.recv[k] = reinterpret_cast<double*>(static_cast<char*>(fs.block) + ctlBytes + k*buf_bytes(plan.recvTotal));
+  if (fs.block)
+    for (int k = 0; k < 2; ++k) fs.recv[k] = reinterpret_cast<double*>(static_cast<char*>(fs.block) + ctlBytes + k*buf_bytes(plan.recvTotal));
   std::vector<FusedInfo> all(nranks);
   FusedInfo mine; std::memset(&mine, 0, sizeof(mine));
-  mine.ok = (local_ok && plan.nSendBoxes <= 32) ? 1 : 0;  // FUSED_MAX_BOXES of the step kernels
   mine.recvTotal = plan.recvTotal;
   for (int r = 0; r < 64; ++r) { mine.segOffset[r] = -1; mine.segCount[r] = 0; }
   for (auto& s : plan.recvSeg) { mine.segOffset[s.peer] = s.offset; mine.segCount[s.peer] = s.count; }
-  if (multi && cudaIpcGetMemHandle(&mine.handle, fs.block) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
-  double* dScratch = nullptr;
+  if (multi && fs.block) soft(cudaIpcGetMemHandle(&mine.handle, fs.block), "cudaIpcGetMemHandle");
+  mine.ok = ok ? 1 : 0;
+  int hard = DGB_OK;                                           // failures of the collectives themselves: nothing left to agree on
   if (multi) {
     FusedInfo* dAll = nullptr;
-    DGB_CUDA(cudaMalloc(&dAll, sizeof(FusedInfo)*nranks));
-    DGB_CUDA(cudaMalloc(&dScratch, sizeof(double)));
-    DGB_CUDA(cudaMemcpyAsync(dAll + myrank, &mine, sizeof(FusedInfo), cudaMemcpyHostToDevice, stream));
-    DGB_NCCL(g_nccl.AllGather(dAll + myrank, dAll, sizeof(FusedInfo), ncclChar, comm->comm, stream));
-    DGB_CUDA(cudaMemcpyAsync(all.data(), dAll, sizeof(FusedInfo)*nranks, cudaMemcpyDeviceToHost, stream));
-    DGB_CUDA(cudaStreamSynchronize(stream));
-    cudaFree(dAll);
+    if (cudaMalloc(&dAll, sizeof(FusedInfo)*nranks) != cudaSuccess) { cudaGetLastError(); hard = fail(DGB_ECUDA, "fused_setup: cudaMalloc of the handle table"); }
+    else {
+      cudaMemcpyAsync(dAll + myrank, &mine, sizeof(FusedInfo), cudaMemcpyHostToDevice, stream);
+      if (g_nccl.AllGather(dAll + myrank, dAll, sizeof(FusedInfo), ncclChar, comm->comm, stream) != ncclSuccess) hard = fail(DGB_ENCCL, "fused_setup: ncclAllGather");
+      cudaMemcpyAsync(all.data(), dAll, sizeof(FusedInfo)*nranks, cudaMemcpyDeviceToHost, stream);
+      if (cudaStreamSynchronize(stream) != cudaSuccess && hard == DGB_OK) hard = fail(DGB_ECUDA, "fused_setup: exchange of the IPC handles");
+      cudaFree(dAll);
+    }
+    if (hard != DGB_OK) { fs.release(false); return hard; }
   } else all[0] = mine;
-  bool ok = true;
   for (int r = 0; r < nranks; ++r) ok = ok && all[r].ok;
   // map every rank's block: flags and CFL values go to all ranks, field data to the ranks this rank sends to
   std::vector<char*> base(nranks, nullptr);
   for (int r = 0; r < nranks && ok; ++r) {
     if (r == myrank) { base[r] = static_cast<char*>(fs.block); continue; }
     void* p = nullptr;
-    if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+    if (!soft(cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) break;
     fs.opened.push_back(p);
     base[r] = static_cast<char*>(p);
   }
   if (ok)
     for (auto& s : plan.sendSeg)
       if (all[s.peer].segOffset[myrank] < 0 || all[s.peer].segCount[myrank] != s.count) ok = false;
-  if (multi) {                                           // every rank must reach the same verdict: min over ranks of 1/0
-    double v = ok ? 1.0 : 0.0;
-    DGB_CUDA(cudaMemcpyAsync(dScratch, &v, sizeof(double), cudaMemcpyHostToDevice, stream));
-    DGB_NCCL(g_nccl.AllReduce(dScratch, dScratch, 1, ncclDouble, ncclMin, comm->comm, stream));
-    DGB_CUDA(cudaMemcpyAsync(&v, dScratch, sizeof(double), cudaMemcpyDeviceToHost, stream));
-    DGB_CUDA(cudaStreamSynchronize(stream));
-    cudaFree(dScratch);
-    ok = v > 0.5;
-  }
-  if (!ok) { fs.release(); return DGB_OK; }
   // destination of every send box: receiver's buffer + offset of my segment there + offset of the box inside my segment
   FusedPack pk[2];
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 2 && ok; ++k) {
     std::vector<double*> dst(plan.nSendBoxes);
-    for (int b = 0; b < plan.nSendBoxes; ++b) {
+    for (int b = 0; b < plan.nSendBoxes && ok; ++b) {
       const PlanBox& pb = plan.hostSend[b];
       const CommPlan::Segment* seg = nullptr;
       for (auto& s : plan.sendSeg) if (pb.buf_offset >= s.offset && pb.buf_offset < s.offset + s.count) seg = &s;
-      if (!seg) return fail(DGB_EGRID, "send box outside every segment");
+      if (!seg) { ok = false; why = "send box outside every segment"; break; }
       char* peerBuf = base[seg->peer] + ctlBytes + k*buf_bytes(all[seg->peer].recvTotal);
       dst[b] = reinterpret_cast<double*>(peerBuf) + all[seg->peer].segOffset[myrank] + (pb.buf_offset - seg->offset);
     }
-    if (plan.nSendBoxes) {
-      DGB_CUDA(cudaMalloc(&fs.dDst[k], plan.nSendBoxes*sizeof(double*)));
-      DGB_CUDA(cudaMemcpy(fs.dDst[k], dst.data(), plan.nSendBoxes*sizeof(double*), cudaMemcpyHostToDevice));
+    if (ok && plan.nSendBoxes) {
+      if (soft(cudaMalloc(&fs.dDst[k], plan.nSendBoxes*sizeof(double*)), "cudaMalloc(box destinations)"))
+        soft(cudaMemcpy(fs.dDst[k], dst.data(), plan.nSendBoxes*sizeof(double*), cudaMemcpyHostToDevice), "cudaMemcpy(box destinations)");
     }
     std::memset(&pk[k], 0, sizeof(FusedPack));
-    pk[k].boxes = plan.dSendBoxes; pk[k].dst = fs.dDst[k]; pk[k].counter = &fs.ctl->counter;
+    pk[k].boxes = plan.dSendBoxes; pk[k].dst = fs.dDst[k]; pk[k].counter = fs.ctl ? &fs.ctl->counter : nullptr;
     pk[k].nBoxes = plan.nSendBoxes; pk[k].nranks = nranks;
-    for (int r = 0; r < nranks; ++r) {
+    for (int r = 0; r < nranks && ok; ++r) {
       FusedCtl* c = reinterpret_cast<FusedCtl*>(base[r]);
       pk[k].peerFlag[r] = &c->flags[myrank];
       pk[k].peerCfl[r] = &c->cfl[k][myrank];
     }
   }
-  DGB_CUDA(cudaMalloc(&fs.dPack, 2*sizeof(FusedPack)));
-  DGB_CUDA(cudaMemcpy(fs.dPack, pk, 2*sizeof(FusedPack), cudaMemcpyHostToDevice));
+  if (ok && soft(cudaMalloc(&fs.dPack, 2*sizeof(FusedPack)), "cudaMalloc(FusedPack)"))
+    soft(cudaMemcpy(fs.dPack, pk, 2*sizeof(FusedPack), cudaMemcpyHostToDevice), "cudaMemcpy(FusedPack)");
+  if (multi) {                                           // every rank must reach the same verdict: min over ranks of 1/0
+    double v = ok ? 1.0 : 0.0;
+    double* dScratch = nullptr;
+    if (cudaMalloc(&dScratch, sizeof(double)) != cudaSuccess) { cudaGetLastError(); fs.release(false); return fail(DGB_ECUDA, "fused_setup: cudaMalloc of the verdict word"); }
+    cudaMemcpyAsync(dScratch, &v, sizeof(double), cudaMemcpyHostToDevice, stream);
+    const bool sent = g_nccl.AllReduce(dScratch, dScratch, 1, ncclDouble, ncclMin, comm->comm, stream) == ncclSuccess;
+    cudaMemcpyAsync(&v, dScratch, sizeof(double), cudaMemcpyDeviceToHost, stream);
+    const bool synced = cudaStreamSynchronize(stream) == cudaSuccess;
+    cudaFree(dScratch);
+    if (!sent || !synced) { fs.release(false); return fail(DGB_ENCCL, "fused_setup: verdict all-reduce failed"); }
+    ok = v > 0.5;
+  }
+  if (!ok) {
+    // all ranks are here with the same verdict; peers may still hold mappings of this rank's block: collective teardown
+    if (int rc = fused_teardown(fs, comm, stream)) return rc;
+    return DGB_OK;
+  }
   fs.epoch = 0;
   fs.on = true;
+  return DGB_OK;
+}
+
+int CommPlan::enter(cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(mtx);
+  if (!busy) DGB_CUDA(cudaEventCreateWithFlags(&busy, cudaEventDisableTiming));
+  else DGB_CUDA(cudaStreamWaitEvent(stream, busy, 0));
+  return DGB_OK;
+}
+int CommPlan::leave(cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(mtx);
+  if (busy) DGB_CUDA(cudaEventRecord(busy, stream));
+  return DGB_OK;
+}
+
+int nccl_check_async(dgb_comm* comm) {
+  if (!comm || !g_nccl.CommGetAsyncError) return DGB_OK;
+  ncclResult_t st = ncclSuccess;
+  if (g_nccl.CommGetAsyncError(comm->comm, &st) != ncclSuccess) return fail(DGB_ENCCL, "ncclCommGetAsyncError failed");
+  if (st != ncclSuccess && st != ncclInProgress) return fail(DGB_ENCCL, std::string("NCCL communicator reports an asynchronous error: ") + g_nccl.GetErrorString(st));
   return DGB_OK;
 }
 
@@ -534,7 +610,9 @@ int dgb_comm_pack(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int d
     if (level < 0 || level >= int(g->me.levels.size())) throw RangeError("level out of range");
     std::shared_ptr<CommPlan> plan;
     if (int rc = get_plan(g, level, *m, iftype, dir, item_sizes, narrays, plan)) return rc;
+    if (int rc = plan->enter((cudaStream_t)stream)) return rc;
     if (int rc = plan_pack(*plan, d_arrays, item_sizes, narrays, (cudaStream_t)stream)) return rc;
+    if (int rc = plan->leave((cudaStream_t)stream)) return rc;
     if (d_sendbuf) *d_sendbuf = plan->dSendBuf;
     if (d_recvbuf) *d_recvbuf = plan->dRecvBuf;
     return DGB_OK;
@@ -548,7 +626,9 @@ int dgb_comm_unpack(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int
     if (op < DGB_OP_SET || op > DGB_OP_SET_NONNEG) throw ArgError("unknown combine op");
     std::shared_ptr<CommPlan> plan;
     if (int rc = get_plan(g, level, *m, iftype, dir, item_sizes, narrays, plan)) return rc;
-    return plan_unpack(*plan, op, d_arrays, item_sizes, narrays, (cudaStream_t)stream);
+    if (int rc = plan->enter((cudaStream_t)stream)) return rc;
+    if (int rc = plan_unpack(*plan, op, d_arrays, item_sizes, narrays, (cudaStream_t)stream)) return rc;
+    return plan->leave((cudaStream_t)stream);
   });
 }
 

@@ -2,6 +2,7 @@
 #ifndef DGB_COMM_HH
 #define DGB_COMM_HH
 #include <memory>
+#include <mutex>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../include/dgb.h"
@@ -31,6 +32,12 @@ struct CommPlan {
   bool uploaded = false;
   long long launches = 0;
   cudaEvent_t trace[3] = {nullptr, nullptr, nullptr};     // optional timing events: after pack, after transfer, after unpack (DGB_FV_TRACE)
+  // A cached plan owns ONE send / receive buffer pair: users on different streams are serialised through this event (every
+  // use waits for the previous one and records its own end); host-side bookkeeping is guarded by `mtx`.
+  cudaEvent_t busy = nullptr;
+  std::mutex mtx;
+  int enter(cudaStream_t stream);                         // stream waits for the previous user of the buffers
+  int leave(cudaStream_t stream);                         // marks the end of this use
   int upload();
   ~CommPlan();
 };
@@ -45,7 +52,7 @@ int nccl_allgather_bytes(const void* d_in, void* d_out, size_t bytes, dgb_comm* 
 int comm_rank_count(const dgb_comm* comm, int* rank, int* nranks);
 // what the first unpack launch of a fused step waits for before it touches the receive buffer (dgb_fv.cu): the flags of
 // all ranks reaching `target`; CTA 0 then also stores the maximum of the published CFL values into `slot`
-struct HaloWait { struct FusedCtl* ctl; int nranks; unsigned target; int parity; double* slot; };
+struct HaloWait { struct FusedCtl* ctl; int nranks; unsigned target; int parity; double* slot; unsigned* hostTimeout; };
 // recv boxes scattered from `buf` (laid out like the plan's receive buffer) instead of plan.dRecvBuf
 int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream,
                      const HaloWait* wait = nullptr);
@@ -78,13 +85,28 @@ struct FusedState {
   double** dDst[2] = {nullptr, nullptr};
   std::vector<void*> opened;
   unsigned epoch = 0;                    // fused steps done
-  void release();
-  ~FusedState() { release(); }
+  // sticky time-out word in mapped pinned host memory: the waiting kernels store 1 there when a peer did not deliver within
+  // 20 s; the host reads it (no synchronisation needed) at the start of every later step and refuses to launch
+  unsigned* hTimeout = nullptr;          // host address
+  unsigned* dTimeout = nullptr;          // device alias of the same word
+  bool multi = false;                    // the block is exported to other processes (teardown must be collective)
+  bool timed_out() const { return hTimeout && *const_cast<volatile unsigned*>(hTimeout) != 0u; }
+  // closes the peers' mappings; `free_block` = false leaves the exported block allocated (non-collective teardown: freeing a
+  // block other processes may still have mapped is undefined behaviour, so it is deliberately leaked until process exit)
+  void release(bool free_block = true);
+  ~FusedState() { release(!multi); }
 };
 // collective over all ranks: allocate and publish this rank's block, map the peers'. Leaves fs.on = false (and DGB_OK) when
 // peer mapping is not available on every rank - the caller then keeps the NCCL path.
 // `local_ok` = false vetoes the fused form for ALL ranks (e.g. a rank without interior cells launches no step kernel and
 // could never signal)
 int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs, bool local_ok = true);
+// collective teardown of a fused state shared between processes: every rank closes its imported mappings, all ranks meet in
+// a barrier (all-reduce on the communicator), only then the exported blocks are freed
+int fused_teardown(FusedState& fs, dgb_comm* comm, cudaStream_t stream);
+// a plan of its own for one user (not the per-grid cache): its buffers are then private to that user's stream
+std::shared_ptr<CommPlan> build_plan(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir, const int32_t* item_sizes, int narrays);
+// ncclCommGetAsyncError of the communicator (DGB_OK without a communicator): DGB_ENCCL once a peer has failed
+int nccl_check_async(dgb_comm* comm);
 }
 #endif

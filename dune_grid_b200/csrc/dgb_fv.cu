@@ -144,8 +144,11 @@ __device__ __forceinline__ void fv_fused_signal(const FvArgs& a) {
   }
 }
 // the receiving side: thread s waits until rank s has delivered epoch `target`, then the reduced CFL value is stored
-__global__ void k_fv_wait(FusedCtl* ctl, int nranks, unsigned target, int parity, double* slot) {
+__global__ void k_fv_wait(FusedCtl* ctl, int nranks, unsigned target, int parity, double* slot, unsigned* hostTimeout) {
+  __shared__ int s_timed_out;
   const int s = threadIdx.x;
+  if (s == 0) s_timed_out = 0;
+  __syncthreads();
   if (s < nranks) {
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -154,12 +157,16 @@ __global__ void k_fv_wait(FusedCtl* ctl, int nranks, unsigned target, int parity
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&ctl->flags[s]) : "memory");
       if (int(f - target) >= 0) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 20000000000ull) { ctl->timeout = 1u; break; }        // 20 s: a peer is gone; do not hang the device
+      if (ctl->timeout || t1 - t0 > 20000000000ull) {                    // 20 s: a peer is gone; do not hang the device
+        ctl->timeout = 1u; s_timed_out = 1;                               // sticky: dgb_fv_step refuses every later step
+        if (hostTimeout) { *reinterpret_cast<volatile unsigned*>(hostTimeout) = 1u; __threadfence_system(); }
+        break;
+      }
       __nanosleep(64);
     }
   }
   __syncthreads();
-  if (s == 0) {
+  if (s == 0 && !s_timed_out) {
     double m = 0.0;
     for (int r = 0; r < nranks; ++r) m = fmax(m, *reinterpret_cast<volatile double*>(&ctl->cfl[parity][r]));
     *slot = m;
@@ -585,105 +592,77 @@ __device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, c
 #undef DGB_RING_CELL
 }
 
-// ---- bulk-copy (TMA engine) staging of the same ring ----------------------------------------------------------------
-// Instead of one 8-byte LDGSTS per thread and cell (which costs as many load/store-unit wavefronts as all shared-memory
-// reads of the loop together), warp 0 issues one cp.async.bulk per tile ROW and plane: the copy engine moves the row
-// (tile width + x halo, ~1 KB) from L2 to shared memory and signals an mbarrier; no LSU wavefronts, no per-thread address
-// arithmetic, full 128-byte line requests whatever the alignment of the row. Bulk copies need 16-byte aligned source
-// addresses and sizes, while rows of a stored box with odd width start at odd element offsets every other row: the copy
-// starts at the even element below the row start, so a row lands with a phase of 0 or 1 elements; a thread's own cell moves
-// by that phase from plane to plane (dz) and from row to row (dyadj), two integer updates per plane.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(b)), "r"(count) : "memory");
+// ---- paired, phase-aware staging (STG = 2) --------------------------------------------------------------------------
+// The rows of a rank-local box of a partitioned grid are only 8-byte aligned: its row length is odd (513 for the 2x2x2 split of
+// 1024^3) or the interior starts at an odd offset, and with an odd plane stride the alignment of a row alternates from
+// plane to plane as well. 8-byte LDGSTS staging costs twice the instructions and shared-memory store wavefronts of 16-byte
+// staging, which is why those boxes ran 11 % slower than the aligned single-GPU box. Here EVERY staged row
+// is copied as 16-byte aligned PAIRS whatever its alignment: a cell is placed in shared memory at column
+//     2 + (x - x0) + phi(row, plane),     phi = parity of the element address of the tile's first cell of that row,
+// so that even element addresses land on even columns. The aligned pairs of a row then sit at fixed columns (2p, 2p+1) and
+// cover the tile's cells, both x neighbours and at most three surplus cells; thread t < (BY+2)*(BX+4)/2 stages pair
+// t % ((BX+4)/2) of row t / ((BX+4)/2) (tile rows and the y neighbour rows alike), so no separate halo duty exists.
+// A thread's own cell moves by the phase of its row: its column alternates from plane to plane when the plane stride is
+// odd, and the y neighbour's row has the other phase when the row stride is odd. The ring has an even number of slots and
+// the loop is unrolled by two, so "even" and "odd" planes of the chunk always use the same slots and every phase-dependent
+// offset is a per-thread constant (one for even, one for odd planes): the hot loop has no phase arithmetic at all. Slot
+// positions are CTA-uniform byte offsets (uPrev/uCur/uNxt), per-thread positions are byte offsets inside a slot.
+__device__ __forceinline__ void cp_async16_b(unsigned smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(smem), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* b, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(b)), "r"(bytes) : "memory");
+__device__ __forceinline__ void cp_async8_b(unsigned smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(smem), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
-  asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}"
-               :: "r"(smem_u32(b)), "r"(parity) : "memory");
+__device__ __forceinline__ double lds_f64(unsigned smem) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];\n" : "=d"(v) : "r"(smem) : "memory");
+  return v;
 }
-__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* b) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-               :: "r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(b)) : "memory");
-}
-
-// one staged row of a tile: first needed element (plane 0 of the chunk) and number of elements; len = 0: row not staged
-struct FvBulkRow { long long e0; int len; int pad; };
-
-// Warp 0 stages plane p (planeOff = p*sz) into `slot`: lane r issues the copy of row r, lane 0 arms the mbarrier with the
-// plane's byte count (tot[p & 1], precomputed: the phases depend on the plane only through its parity). The arrive may
-// follow or precede the copies' complete_tx - the phase cannot complete before both have happened - so the lanes do not
-// synchronise: staging sits on warp 0's critical path between two CTA barriers and must stay a dozen instructions.
-// ORDERED (only CTAs whose rows reach the very end of an array with an odd element count): the engine must not read past
-// the end, so the last element of that row comes by a plain load, published before the arrive.
-template<int BY, int RP, bool ORDERED>
-__device__ __forceinline__ void fv_bulk_stage(const double* __restrict__ c, double* slot, unsigned long long* bar, const FvBulkRow* rows,
-                                              const unsigned* tot, long long planeOff, int parity, long long total, int lane) {
-  unsigned bytes = 0; long long a0 = 0;
-  if (lane < BY+2 && rows[lane].len > 0) {
-    const long long e = rows[lane].e0 + planeOff;
-    a0 = e & ~1ll;
-    int cnt = (int(e & 1) + rows[lane].len + 1) & ~1;
-    if (ORDERED && a0 + cnt > total) {
-      cnt -= 2;
-      for (long long q = a0 + cnt; q < e + rows[lane].len; ++q) slot[lane*RP + (q - a0)] = __ldg(c + q);
-    }
-    bytes = unsigned(cnt)*8u;
+// a pair that may stick out of the array by one element at either end (first / last element of the field)
+__device__ __forceinline__ void stage_pair_checked(unsigned dst, const char* src, const char* lo, const char* hi) {
+  if (src >= lo && src + 16 <= hi) cp_async16_b(dst, src);
+  else {
+    if (src >= lo && src + 8 <= hi) cp_async8_b(dst, src);
+    if (src + 8 >= lo && src + 16 <= hi) cp_async8_b(dst + 8, src + 8);
   }
-  if (ORDERED) {
-    unsigned sum = bytes;
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    __syncwarp();
-    if (lane == 0) mbar_arrive_expect_tx(bar, sum);
-    __syncwarp();
-  } else if (lane == 0) mbar_arrive_expect_tx(bar, tot[parity]);
-  if (bytes) bulk_g2s(slot + lane*RP, c + a0, bytes, bar);
 }
-
-struct FvBulkLane {
-  double f0, f1, f2, f3, tbx, tby, un5, dt, c_below, zhigh;
-  double* w;                      // own column in cnew
-  const double* cur;              // own cell of plane 0 in slot 0
-  int ox, oy, dz, dyadj, sgn;     // neighbour offsets; phase steps (see above); sgn = -1 if the phase alternates from plane to plane
-  bool active;
+struct FvPairLane {
+  double f0, f1, f2, f3, tbx, tby, un5, dt;   // as FvRingLane
+  double c_below, zhigh;
+  char* w;                                    // own column in cnew
+  const char* glE; const char* glO;           // loader: source of this thread's pair in the next even / odd plane to stage
+  unsigned aE, aO;                            // shared address of the own cell in slot 0 for an even / odd plane of the chunk
+  unsigned xE, xO, yE, yO;                    // ... of the upwind x / y neighbour (= own cell if none); slow path: yE/yO = phase step
+  unsigned ld;                                // loader: shared address of the pair in slot 0
+  bool active, loader;
 };
 
 template<int D, int BX, int BY, int MODE, bool ZPARAM>
-__device__ __forceinline__ void fv_bulk_loop(FvBulkLane L, const FvRingSlow S, const double* __restrict__ c, double* ring,
-                                             unsigned long long* bars, const FvBulkRow* rows, const unsigned* tot, const bool ordered,
-                                             const long long sz, const long long total,
-                                             const double* rwz, const FvZTable& zt, const int zbase, const int zn, const int kload) {
-  constexpr int R = D+2, RP = BX+4, SLOT = (BY+2)*RP;
+__device__ __forceinline__ void fv_pair_loop(FvPairLane L, const FvRingSlow S, const long long sz, const double* rwz, const FvZTable& zt,
+                                             const int zbase, const int zn, const int kload, const int kmain,
+                                             const char* lo, const char* hi) {
+  constexpr int R = D+2, PX = BX+4, PY = BY+2;
+  constexpr unsigned SLOTB = PX*PY*8u, LASTB = (R-1)*SLOTB, ROWB = PX*8u;
+  static_assert(R % 2 == 0, "even and odd planes must keep their slots");
   constexpr bool DX = MODE & 4, DY = MODE & 2, DZ = MODE & 1;
-  const int lane = threadIdx.x & 31;
-  const bool stager = (threadIdx.y*BX + threadIdx.x) < 32;          // warp 0
-  char* w = reinterpret_cast<char*>(L.w);
-  const long long sz8 = sz*8;
+  const long long sz8 = sz*8, step2 = 2*sz8;
   double c_below = L.c_below, c_here = 0.0;
   const bool self4 = S.un4 >= 0.0, self5 = L.un5 >= 0.0;
-  int dz = L.dz, dyadj = L.dyadj;
-  const double* cur = L.cur;
-  int slotNext = 1 % R; unsigned parNext = 0;                       // slot / phase parity of plane k+1
-  int slotPrev = R-1;                                               // slot of plane k-1 = where plane k+1+D goes
-  mbar_wait(bars + 0, 0);
-  c_here = *cur;
-  const double* nxt = cur + SLOT + dz;
-#define DGB_BULK_CELL(GUARD, K)                                                                                \
+  unsigned uPrev = LASTB, uCur = 0u, uNxt = SLOTB;       // CTA-uniform: slot of plane k-1 (free), k, k+1
+#define DGB_PAIR_CELL(GUARD, K, AOWN, AX, AY, ANXT, GL)                                                       \
   {                                                                                                            \
-    if (!(GUARD) || (K)+1 <= kload) mbar_wait(bars + slotNext, parNext);                                       \
+    cp_async_wait<D-1>();                                                                                      \
     __syncthreads();                                                                                           \
-    if (stager && (!(GUARD) || (K)+1+D <= kload)) {                                                            \
-      if (!ordered) fv_bulk_stage<BY, RP, false>(c, ring + slotPrev*SLOT, bars + slotPrev, rows, tot, ((K)+1+D)*sz, ((K)+1+D) & 1, total, lane);  \
-      else fv_bulk_stage<BY, RP, true>(c, ring + slotPrev*SLOT, bars + slotPrev, rows, tot, ((K)+1+D)*sz, ((K)+1+D) & 1, total, lane);           \
-    }                                                                                                          \
-    const double c_above = (!(GUARD) || (K)+1 <= kload) ? *nxt : L.zhigh;                                      \
+    if (!(GUARD)) { if (L.loader) cp_async16_b(uPrev + L.ld, GL); }                                            \
+    else if ((K)+1+D <= kload && L.loader) stage_pair_checked(uPrev + L.ld, GL, lo, hi);                       \
+    cp_async_commit();                                                                                         \
+    GL += step2;                                                                                               \
+    const double c_above = (!(GUARD) || (K)+1 <= kload) ? lds_f64(uNxt + (ANXT)) : L.zhigh;                    \
     const double rw = ZPARAM ? zt.rw[zbase + (K)] : __ldg(rwz + (K));                                          \
     double upd;                                                                                                \
     if (MODE < 8) {                                                                                            \
       const double f5 = L.un5*rw;                                                                              \
-      const double nx = cur[L.ox], ny = cur[L.oy + dyadj];                                                     \
+      const double nx = lds_f64(uCur + (AX)), ny = lds_f64(uCur + (AY));                                       \
       upd = 0.0 - (DX ? nx : c_here)*L.f0;                                                                     \
       if (DX) upd -= L.tbx;                                                                                    \
       upd -= (DX ? c_here : nx)*L.f1;                                                                          \
@@ -695,37 +674,47 @@ __device__ __forceinline__ void fv_bulk_loop(FvBulkLane L, const FvRingSlow S, c
       upd -= (DZ ? c_below : c_here)*(-f5);                                                                    \
       upd -= (DZ ? c_here : c_above)*f5;                                                                       \
     } else {                                                                                                   \
+      /* slow path: AY is the phase step (in bytes) towards the rows above and below */                       \
+      const unsigned own = uCur + (AOWN);                                                                      \
       double val;                                                                                              \
-      val = S.alt0; if (S.flags & 16u) val = cur[-1];          if (S.flags & 1u) val = c_here; upd = 0.0 - val*L.f0;  \
-      val = S.alt1; if (S.flags & 32u) val = cur[1];           if (S.flags & 2u) val = c_here; upd -= val*L.f1;       \
-      val = S.alt2; if (S.flags & 64u) val = cur[dyadj - RP];  if (S.flags & 4u) val = c_here; upd -= val*L.f2;       \
-      val = S.alt3; if (S.flags & 128u) val = cur[dyadj + RP]; if (S.flags & 8u) val = c_here; upd -= val*L.f3;       \
+      val = S.alt0; if (S.flags & 16u) val = lds_f64(own - 8u);             if (S.flags & 1u) val = c_here; upd = 0.0 - val*L.f0;  \
+      val = S.alt1; if (S.flags & 32u) val = lds_f64(own + 8u);             if (S.flags & 2u) val = c_here; upd -= val*L.f1;       \
+      val = S.alt2; if (S.flags & 64u) val = lds_f64(own - ROWB + (AY));    if (S.flags & 4u) val = c_here; upd -= val*L.f2;       \
+      val = S.alt3; if (S.flags & 128u) val = lds_f64(own + ROWB + (AY));   if (S.flags & 8u) val = c_here; upd -= val*L.f3;       \
       upd -= (self4 ? c_here : c_below)*(S.un4*rw);                                                            \
       upd -= (self5 ? c_here : c_above)*(L.un5*rw);                                                            \
     }                                                                                                          \
-    if (L.active) __stcs(reinterpret_cast<double*>(w), c_here + L.dt*upd);                                     \
+    if (L.active) __stcs(reinterpret_cast<double*>(L.w), c_here + L.dt*upd);                                   \
     c_below = c_here; c_here = c_above;                                                                        \
-    w += sz8;                                                                                                  \
-    /* advance: plane k+1 becomes current; phases flip where the plane stride is odd */                        \
-    cur = nxt; dz *= L.sgn; dyadj *= L.sgn;                                                                    \
-    slotPrev = (slotPrev + 1 == R) ? 0 : slotPrev + 1;                                                         \
-    if (++slotNext == R) { slotNext = 0; parNext ^= 1u; nxt = cur - (R-1)*SLOT + dz; }                         \
-    else nxt = cur + ((slotNext == 0) ? -(R-1)*SLOT : SLOT) + dz;                                              \
+    L.w += sz8;                                                                                                \
+    uPrev = uCur; uCur = uNxt; uNxt = (uNxt == LASTB) ? 0u : uNxt + SLOTB;                                     \
   }
-  const int kmain = max(0, min(zn, kload-D));
+  // plane 0 of the own column was staged by another thread: publish its arrival first
+  cp_async_wait<D>();
+  __syncthreads();
+  c_here = lds_f64(L.aE);
   int k = 0;
+  // an even plane of the chunk stages plane k+1+D, which is odd (D is even), and vice versa
 #pragma unroll 1
-  for (; k < kmain; ++k) DGB_BULK_CELL(false, k)
+  for (; k+1 < kmain; k += 2) {
+    DGB_PAIR_CELL(false, k, L.aE, L.xE, L.yE, L.aO, L.glO)
+    DGB_PAIR_CELL(false, k+1, L.aO, L.xO, L.yO, L.aE, L.glE)
+  }
 #pragma unroll 1
-  for (; k < zn; ++k) DGB_BULK_CELL(true, k)
-#undef DGB_BULK_CELL
+  for (; k < zn; k += 2) {
+    DGB_PAIR_CELL(true, k, L.aE, L.xE, L.yE, L.aO, L.glO)
+    if (k+1 < zn) DGB_PAIR_CELL(true, k+1, L.aO, L.xO, L.yO, L.aE, L.glE)
+  }
+#undef DGB_PAIR_CELL
 }
 
-template<int PROBLEM, int D, int BX, int BY, int MINB, bool ZPARAM, bool BULK = false, bool A16 = false>
+template<int PROBLEM, int D, int BX, int BY, int MINB, bool ZPARAM, int STG = 0>      // STG: 0 8-byte staging, 1 aligned pairs, 2 phase-aware pairs
 __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a,
                                                          const __grid_constant__ FvZTable zt, const int zc) {
-  constexpr int PX = A16 ? BX+4 : BX+2, PY = BY+2, SLOT = PX*PY, XO = A16 ? 2 : 1;      // XO: column of the tile's first cell
+  constexpr bool A16 = STG == 1;
+  constexpr int PX = STG ? BX+4 : BX+2, PY = BY+2, SLOT = PX*PY, XO = STG ? 2 : 1;      // XO: column of the tile's first cell
   static_assert(2*BX + 2*BY <= BX*BY, "one halo cell per thread");
+  static_assert(PY*(PX/2) <= BX*BY, "one pair per thread");
   extern __shared__ __align__(16) double ring[];       // [R][PY][PX]
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i0 = blockIdx.x*BX + tx;
@@ -808,86 +797,83 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   const double zlow = (!perz && ovz0 == 0) ? bval : 0.0;
   const long long idx0 = (long long)(cz0-of.origin[2])*sz + (long long)(cy-of.origin[1])*sy + (cx-of.origin[0]);
   const int kload = min(zn, ovz1-cz0);                   // last plane offset holding stored cells
-  if constexpr (BULK) {
-    constexpr int R = D+2, RP = BX+4, SLOT = (BY+2)*RP;
-    __shared__ __align__(8) unsigned long long s_bar[R];
-    __shared__ FvBulkRow s_rows[BY+2];
-    const int t = ty*BX + tx;
-    const int tx0 = a.region.origin[0]+blockIdx.x*BX, ty0 = a.region.origin[1]+by*BY;
-    const int nxv = min(BX, a.region.size[0]-(int)blockIdx.x*BX), nyv = min(BY, a.region.size[1]-by*BY);
-    // x range of every staged row: the tile's columns plus the x neighbours that are stored cells
-    const int xs = tx0-1 >= of.origin[0] ? tx0-1 : tx0;
-    const int xe = tx0+nxv < of.origin[0]+of.size[0] ? tx0+nxv+1 : tx0+nxv;
-    if (t < BY+2) {
-      const int gy = ty0-1+t;
-      bool need = t >= 1 && t <= nyv;
-      if (t == 0 || t == nyv+1) {                        // y halo rows: stored neighbours, on the fast path the inflow side only
-        need = gy >= ov.origin[1] && gy < ov.origin[1]+ov.size[1];
-        if (need && pat < 8) need = (t == 0) == bool(pat & 2);
-      }
-      s_rows[t].e0 = (long long)(cz0-of.origin[2])*sz + (long long)(gy-of.origin[1])*sy + (xs-of.origin[0]);
-      s_rows[t].len = need ? xe-xs : 0;
-    }
-    __shared__ unsigned s_tot[2];
-    __shared__ int s_ordered;
-    const long long total = sz*of.size[2];
-    if (t == 0) { for (int j = 0; j < R; ++j) mbar_init(s_bar + j, 1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-    __syncthreads();
-    if (t == 0) {                                        // bytes of a staged plane by plane parity; does any row end at the array's end?
-      unsigned t0 = 0, t1 = 0; int ord = 0;
-      for (int r = 0; r < BY+2; ++r) if (s_rows[r].len > 0) {
-        const long long e = s_rows[r].e0;
-        t0 += unsigned((int(e & 1) + s_rows[r].len + 1) & ~1)*8u;
-        t1 += unsigned((int((e + sz) & 1) + s_rows[r].len + 1) & ~1)*8u;
-        if (e + (long long)min(zn, kload)*sz + s_rows[r].len + 1 > total) ord = 1;
-      }
-      s_tot[0] = t0; s_tot[1] = t1; s_ordered = ord;
-    }
-    __syncthreads();
-    const bool ordered = s_ordered != 0;
-    if (t < 32)
-#pragma unroll 1
-      for (int j = 0; j <= D; ++j) if (j <= kload) {
-        if (!ordered) fv_bulk_stage<BY, RP, false>(a.c, ring + j*SLOT, s_bar + j, s_rows, s_tot, j*sz, j & 1, total, t);
-        else fv_bulk_stage<BY, RP, true>(a.c, ring + j*SLOT, s_bar + j, s_rows, s_tot, j*sz, j & 1, total, t);
-      }
-    FvBulkLane L; FvRingSlow S;
+  if constexpr (STG == 2) {
+    FvPairLane L; FvRingSlow S;
     L.active = active;
-    L.f0 = f0; L.f1 = f1; L.f2 = f2; L.f3 = f3; L.un5 = un5; L.tbx = 0.0; L.tby = 0.0; L.ox = 0; L.oy = 0;
+    L.f0 = f0; L.f1 = f1; L.f2 = f2; L.f3 = f3; L.un5 = un5; L.tbx = 0.0; L.tby = 0.0;
     S.alt0 = alt0; S.alt1 = alt1; S.alt2 = alt2; S.alt3 = alt3; S.un4 = un4; S.flags = flags;
     L.zhigh = (!perz && ovz1+1 == v.N[2]) ? bval : 0.0;
     L.dt = 0.99*(1.0/(*a.slotIn));
-    L.w = a.cnew + idx0;
-    // own cell in slot 0: row ty+1, column = position in the staged row + phase of that row in plane 0
-    const int psy = sy & 1, psz = int(sz & 1);
-    const int rowc = min(ty, nyv-1)+1, colc = min(tx, nxv-1) + (tx0-xs);         // clamped like cx, cy
-    const int phi = int((s_rows[0].e0 + (long long)rowc*sy) & 1);
-    L.cur = ring + rowc*RP + colc + phi;
-    const int d = 1 - 2*phi;
-    L.sgn = psz ? -1 : 1;
-    L.dz = psz ? d : 0;
-    L.dyadj = 0;
-    L.c_below = (cz0 > ovz0) ? __ldg(a.c + idx0 - sz) : zlow;
+    L.w = reinterpret_cast<char*>(a.cnew + idx0);
+    const int t = ty*BX + tx;
+    const int tx0 = a.region.origin[0]+blockIdx.x*BX, ty0 = a.region.origin[1]+by*BY;
+    const int nxv = min(BX, a.region.size[0]-(int)blockIdx.x*BX), nyv = min(BY, a.region.size[1]-by*BY);
+    const unsigned ring0 = (unsigned)__cvta_generic_to_shared(ring);
+    // element offset of (tx0, ty0-1, cz0) = first tile cell of staged row 0; `par` folds in the alignment of the field itself
+    const long long e00 = (long long)(cz0-of.origin[2])*sz + (long long)(ty0-1-of.origin[1])*sy + (tx0-of.origin[0]);
+    const unsigned par = unsigned(reinterpret_cast<uintptr_t>(a.c) >> 3) + unsigned(e00);
+    const unsigned psy = unsigned(sy) & 1u, psz = unsigned(sz) & 1u;
+    auto phase = [&](int rr, int kk) -> unsigned { return (par + unsigned(rr)*psy + unsigned(kk)*psz) & 1u; };
+    // own cell (threads outside the region shadow the last valid column / row, like cx and cy)
+    const int rrO = min(ty, nyv-1)+1, ctx = min(tx, nxv-1);
+    const unsigned ph0 = phase(rrO, 0), ph1 = phase(rrO, 1);
+    L.aE = ring0 + unsigned(rrO*PX + 2 + ctx + int(ph0))*8u;
+    L.aO = ring0 + unsigned(rrO*PX + 2 + ctx + int(ph1))*8u;
+    // phase step towards the neighbouring rows (they have the other phase when the row stride is odd), in bytes
+    const int dE = psy ? (ph0 ? -8 : 8) : 0, dO = psy ? (ph1 ? -8 : 8) : 0;
+    L.xE = L.aE; L.xO = L.aO; L.yE = L.aE; L.yO = L.aO;
     if (pat < 8) {
       const int mx = dx ? 0 : 1, my = dy ? 2 : 3;
-      L.ox = dx ? -1 : 1; L.oy = dy ? -RP : RP;
-      if (!(flags >> (4+mx) & 1u) && !(flags >> mx & 1u)) { L.ox = 0; L.tbx = (flags >> (8+mx) & 1u) ? bval*(dx ? f0 : f1) : 0.0; if (dx) L.f0 = 0.0; else L.f1 = 0.0; }
-      if (!(flags >> (4+my) & 1u) && !(flags >> my & 1u)) { L.oy = 0; L.tby = (flags >> (8+my) & 1u) ? bval*(dy ? f2 : f3) : 0.0; if (dy) L.f2 = 0.0; else L.f3 = 0.0; }
-      if (flags >> mx & 1u) L.ox = 0;
-      if (flags >> my & 1u) L.oy = 0;
-      if (L.oy != 0 && psy) L.dyadj = d;               // the neighbouring row has the other phase
-    } else if (psy) L.dyadj = d;
-    switch (pat) {
-      case 0: fv_bulk_loop<D, BX, BY, 0, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
-      case 1: fv_bulk_loop<D, BX, BY, 1, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
-      case 2: fv_bulk_loop<D, BX, BY, 2, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
-      case 3: fv_bulk_loop<D, BX, BY, 3, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
-      case 4: fv_bulk_loop<D, BX, BY, 4, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
-      case 5: fv_bulk_loop<D, BX, BY, 5, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
-      case 6: fv_bulk_loop<D, BX, BY, 6, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
-      case 7: fv_bulk_loop<D, BX, BY, 7, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
-      default: fv_bulk_loop<D, BX, BY, 8, ZPARAM>(L, S, a.c, ring, s_bar, s_rows, s_tot, ordered, sz, total, rwz, zt, zbase, zn, kload); break;
+      int ox = dx ? -8 : 8, oy = dy ? -PX*8 : PX*8;
+      if (!(flags >> (4+mx) & 1u) && !(flags >> mx & 1u)) { ox = 0; L.tbx = (flags >> (8+mx) & 1u) ? bval*(dx ? f0 : f1) : 0.0; if (dx) L.f0 = 0.0; else L.f1 = 0.0; }
+      if (!(flags >> (4+my) & 1u) && !(flags >> my & 1u)) { oy = 0; L.tby = (flags >> (8+my) & 1u) ? bval*(dy ? f2 : f3) : 0.0; if (dy) L.f2 = 0.0; else L.f3 = 0.0; }
+      if (flags >> mx & 1u) ox = 0;
+      if (flags >> my & 1u) oy = 0;
+      L.xE = unsigned(int(L.aE) + ox); L.xO = unsigned(int(L.aO) + ox);
+      if (oy) { L.yE = unsigned(int(L.aE) + oy + dE); L.yO = unsigned(int(L.aO) + oy + dO); }
+    } else { L.yE = unsigned(dE); L.yO = unsigned(dO); }
+    // loader duty: pair p of staged row rr (row 0 / nyv+1: the y neighbour rows, if stored and - fast path - on the inflow side)
+    constexpr int NP = PX/2;
+    const int rr = t / NP, p = t - rr*NP;
+    bool need = rr >= 1 && rr <= nyv;
+    if (rr == 0 || rr == nyv+1) {
+      const int gy = ty0-1+rr;
+      need = gy >= ov.origin[1] && gy < ov.origin[1]+ov.size[1];
+      if (need && pat < 8) need = (rr == 0) == bool(pat & 2);
     }
+    L.loader = need && rr < PY;
+    L.ld = ring0 + unsigned(rr*PX + 2*p)*8u;
+    const char* lo = reinterpret_cast<const char*>(a.c);
+    const char* hi = lo + sz*of.size[2]*8;
+    const long long sz8 = sz*8;
+    // source of the pair in plane 0 / plane 1 of the chunk; plane j: same parity class, (j or j-1) planes further
+    const char* srcE = lo + (e00 + (long long)rr*sy - 2 - (long long)phase(rr, 0) + 2*p)*8;
+    const char* srcO = lo + (e00 + (long long)rr*sy + sz - 2 - (long long)phase(rr, 1) + 2*p)*8;
+    constexpr unsigned SLOTB = SLOT*8u;
+#pragma unroll
+    for (int j = 0; j <= D; ++j) {
+      if (j <= kload && L.loader) stage_pair_checked(L.ld + j*SLOTB, (j & 1) ? srcO + (long long)(j-1)*sz8 : srcE + (long long)j*sz8, lo, hi);
+      cp_async_commit();
+    }
+    L.glO = srcO + (long long)D*sz8;                     // plane D+1 (odd), staged by the first (even) iteration
+    L.glE = srcE + (long long)(D+2)*sz8;                 // plane D+2
+    L.c_below = (cz0 > ovz0) ? __ldg(a.c + idx0 - sz) : zlow;
+    // cells whose staging and reads all hit stored planes; the last plane of the ARRAY is staged with bounds checks (its last
+    // pair may stick out of the field by one element)
+    int kmain = max(0, min(zn, kload-D));
+    if (cz0 + kload >= of.origin[2]+of.size[2]-1) kmain = max(0, min(kmain, kload-D-1));
+    switch (pat) {
+      case 0: fv_pair_loop<D, BX, BY, 0, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
+      case 1: fv_pair_loop<D, BX, BY, 1, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
+      case 2: fv_pair_loop<D, BX, BY, 2, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
+      case 3: fv_pair_loop<D, BX, BY, 3, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
+      case 4: fv_pair_loop<D, BX, BY, 4, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
+      case 5: fv_pair_loop<D, BX, BY, 5, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
+      case 6: fv_pair_loop<D, BX, BY, 6, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
+      case 7: fv_pair_loop<D, BX, BY, 7, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
+      default: fv_pair_loop<D, BX, BY, 8, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
+    }
+    cp_async_wait<0>();
     if (active && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = L.dt;
   } else {
   FvRingLane L; FvRingSlow S;
@@ -1017,6 +1003,7 @@ struct dgb_fv {
   int level = 0, mode = 0;
   int zchunk = 0;                // planes marched by one CTA of the 3-D kernel; 0 = auto (DGB_FV_ZCHUNK overrides)
   int variant = -1;              // tuning variant of the 3-D kernel; -1 = automatic (DGB_FV_VARIANT overrides)
+  int staging = 2;               // staging of the ring kernel: 2 phase-aware pairs (default), 1 aligned pairs, 0 8 bytes per cell (DGB_FV_STAGING=pair|a16|8)
   std::unique_ptr<dgb::FvZTable> ztab;   // reciprocal z widths for the kernel parameter space (ring kernel)
   bool zparam = false;
   dgb_view view;
@@ -1032,6 +1019,8 @@ struct dgb_fv {
   dgb::FusedState fused;         // fused exchange (pack + peer stores + signal inside the step kernel)
   bool seedPending = false;      // dgb_fv_bootstrap_local: the reduced seed still has to be copied to the second slot
   int64_t launches = 0;
+  int kinfo[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // last step kernel: see dgb_fv_kernel_info
+  int hostPath = 0;              // last dgb_fv_step_host: DGB_FV_HOST_*
   std::shared_ptr<CommPlan> plan;
   double* dStage[2] = {nullptr, nullptr};     // device staging for the host-buffer entry point
   size_t stageBytes = 0;
@@ -1067,17 +1056,26 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
   if (a.region.size[0] <= 0 || a.region.size[1] <= 0 || (v.dim > 2 && a.region.size[2] <= 0)) return DGB_OK;
   if (v.dim == 3) {
     // tile choice (measured, tools/fv_sweep.py): 128x4 columns for wide regions, 32x8 otherwise
-    const int variant = fv->variant >= 0 ? fv->variant : (a.region.size[0] >= 256 ? 3 : 0);
-    const bool wide = variant == 3 || variant == 7 || variant == 8 || variant >= 11;
-    const bool bulk_ok = fv->zparam && (reinterpret_cast<uintptr_t>(a.c) & 15u) == 0;
-    // 16-byte staging of the own cells: every pair source must be 16-byte aligned (DGB_FV_A16=0 keeps the 8-byte form)
+    int variant = fv->variant >= 0 ? fv->variant : (a.region.size[0] >= 256 ? 3 : 0);
+    if (variant != 99 && variant != 0 && variant != 2 && variant != 3 && variant != 7 && variant != 9) variant = a.region.size[0] >= 256 ? 3 : 0;
+    const bool wide = variant == 3 || variant == 7;
+    // staging of the ring kernel: 2 = 16-byte pairs with per-row phases (default: works for every alignment, row length and
+    // region offset), 1 = 16-byte pairs of rows that are all 16-byte aligned (round-1 form, 128x4 tile only), 0 = 8 bytes per cell
     const dgb_box& ofb = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
-    static const bool a16env = [] { const char* e = getenv("DGB_FV_A16"); return !(e && atoi(e) == 0); }();
-    const bool a16 = a16env && wide && fv->zparam && (reinterpret_cast<uintptr_t>(a.c) & 15u) == 0 && ofb.size[0] % 2 == 0
-                     && (a.region.origin[0]-ofb.origin[0]) % 2 == 0 && a.region.size[0] % 2 == 0;
+    int stg = fv->staging;
+    if (stg == 1 && !(variant == 3 && fv->zparam && (reinterpret_cast<uintptr_t>(a.c) & 15u) == 0 && ofb.size[0] % 2 == 0
+                      && (a.region.origin[0]-ofb.origin[0]) % 2 == 0 && a.region.size[0] % 2 == 0)) stg = 0;
+    if (stg == 0 && !(variant == 0 || variant == 3)) stg = 2;
     const int zc = fv->zchunk > 0 ? fv->zchunk : auto_zchunk(a.region.size, wide ? 128 : 32, wide ? 4 : 8);
     const bool exact = fv->mode == DGB_FV_EXACT;
     const int pb = fv->problem.id == 1 ? 1 : 0;
+    const bool ring = !exact && !(REDUCE_ONLY || a.update || !a.cnew) && variant != 99;
+    if (!REDUCE_ONLY) {
+      int bx = 128, by = 4;                                                   // the z-march kernels
+      if (ring) switch (variant) { case 2: bx = 64; by = 4; break; case 3: case 7: bx = 128; by = 4; break; case 9: bx = 64; by = 8; break; default: bx = 32; by = 8; }
+      const int info[8] = { ring ? DGB_FV_KERNEL_RING : DGB_FV_KERNEL_MARCH, ring ? variant : 99, bx, by, ring ? (stg ? 16 : 8) : 0, zc, a.pack ? 1 : 0, ring ? stg : 0 };
+      for (int k = 0; k < 8; ++k) fv->kinfo[k] = info[k];
+    }
 #define DGB_MARCH(MODE_, PROB_, PF_, BX_, BY_)                                                                       \
     { dim3 mblock(BX_, BY_, 1);                                                                                      \
       dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
@@ -1087,48 +1085,34 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     } else if (REDUCE_ONLY || a.update || !a.cnew) {
       if (pb) DGB_MARCH(DGB_FV_SEPARABLE, 1, 4, 128, 4) else DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4)
     } else {
-#define DGB_BULK(D_, BX_, BY_, MINB_)                                                                                \
-    { dim3 mblock(BX_, BY_, 1);                                                                                      \
-      dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
-      const size_t smem = size_t(D_+2)*(BX_+4)*(BY_+2)*sizeof(double);                                               \
-      auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, true, true> : k_fv_ring<0, D_, BX_, BY_, MINB_, true, true>;  \
+#define DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, ZP_, STG_)                                                              \
+    { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, ZP_, STG_> : k_fv_ring<0, D_, BX_, BY_, MINB_, ZP_, STG_>;        \
       DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));                    \
       kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); }
-#define DGB_RING(D_, BX_, BY_, MINB_)                                                                                \
+#define DGB_RING(D_, BX_, BY_, MINB_, WITH8_, WITHA16_)                                                             \
     { dim3 mblock(BX_, BY_, 1);                                                                                      \
       dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
-      const size_t smem = size_t(D_+2)*(BX_+(a16 ? 4 : 2))*(BY_+2)*sizeof(double);                                  \
-      if (fv->zparam && a16) { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, true, false, true> : k_fv_ring<0, D_, BX_, BY_, MINB_, true, false, true>;  \
-                DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));          \
-                kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); }                                          \
-      else if (fv->zparam) { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, true> : k_fv_ring<0, D_, BX_, BY_, MINB_, true>;      \
-                DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));          \
-                kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); }                                          \
-      else { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, false> : k_fv_ring<0, D_, BX_, BY_, MINB_, false>;     \
-             DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));             \
-             kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); } }
+      const size_t smem = size_t(D_+2)*(BX_+(stg ? 4 : 2))*(BY_+2)*sizeof(double);                                  \
+      if (WITHA16_ && stg == 1) DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, true, (WITHA16_ ? 1 : 2))                       \
+      else if (WITH8_ && stg == 0) { if (fv->zparam) DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, true, (WITH8_ ? 0 : 2))    \
+                                     else DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, false, (WITH8_ ? 0 : 2)) }            \
+      else if (fv->zparam) DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, true, 2)                                             \
+      else DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, false, 2) }
       switch (variant) {                      // tuning variants: ring depth, tile, occupancy target (tools/fv_sweep.py)
         default:
-        case 0: DGB_RING(8, 32, 8, 4) break;                               // production choice, narrow regions
-        case 1: DGB_RING(6, 32, 8, 4) break;
-        case 2: DGB_RING(6, 64, 4, 4) break;
-        case 3: DGB_RING(6, 128, 4, 2) break;                              // production choice, wide regions
-        case 4: DGB_RING(6, 32, 16, 2) break;
-        case 5: DGB_RING(4, 64, 8, 2) break;
-        case 6: DGB_RING(12, 32, 8, 4) break;
-        case 7: DGB_RING(8, 128, 4, 2) break;
-        case 8: DGB_RING(10, 128, 4, 2) break;
-        case 9: DGB_RING(8, 64, 8, 2) break;
-        // bulk-copy (TMA engine) staging: bit-identical, measured SLOWER than LDGSTS staging (0.63-0.66 vs 0.36-0.39 ms at
-        // 512^3): the engine sustains ~8 B/clk/SM on 1 KB row copies whatever the ring depth. Kept as a tested variant.
-        case 11: if (bulk_ok) DGB_BULK(6, 128, 4, 2) else DGB_RING(6, 128, 4, 2) break;
+        case 0: DGB_RING(8, 32, 8, 4, true, false) break;                  // production choice, narrow regions
+        case 2: DGB_RING(6, 64, 4, 4, false, false) break;
+        case 3: DGB_RING(6, 128, 4, 2, true, true) break;                  // production choice, wide regions
+        case 7: DGB_RING(8, 128, 4, 2, false, false) break;
+        case 9: DGB_RING(8, 64, 8, 2, false, false) break;
         case 99: if (pb) DGB_MARCH(DGB_FV_SEPARABLE, 1, 4, 128, 4) else DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4) break;   // the general kernel, for comparison
       }
 #undef DGB_RING
-#undef DGB_BULK
+#undef DGB_RING_LAUNCH
     }
 #undef DGB_MARCH
   } else {
+    if (!REDUCE_ONLY) { const int info[8] = { DGB_FV_KERNEL_STEP2D, -1, FBX, FBY, 0, 1, 0, 0 }; for (int k = 0; k < 8; ++k) fv->kinfo[k] = info[k]; }
     if (fv->mode == DGB_FV_EXACT) k_fv_step<2, DGB_FV_EXACT, REDUCE_ONLY><<<grid, block, 0, stream>>>(v, a);
     else k_fv_step<2, DGB_FV_SEPARABLE, REDUCE_ONLY><<<grid, block, 0, stream>>>(v, a);
   }
@@ -1226,6 +1210,7 @@ int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host
     fv->grid = g; fv->comm = comm; fv->level = level; fv->mode = mode;
     if (const char* e = getenv("DGB_FV_ZCHUNK")) { int z = atoi(e); if (z > 0) fv->zchunk = z; }
     if (const char* e = getenv("DGB_FV_VARIANT")) fv->variant = atoi(e);
+    if (const char* e = getenv("DGB_FV_STAGING")) fv->staging = !strcmp(e, "8") ? 0 : !strcmp(e, "a16") ? 1 : 2;
     if (int rc = make_view(g, level, &fv->view)) return rc;
     if (g->me.nranks > 1 && !comm) throw ArgError("a dgb_comm is required on a multi-rank grid");
     const uint32_t block[4] = {1,0,0,0};
@@ -1259,7 +1244,9 @@ int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host
     fv->zparam = v.dim == 3 && of.size[2] <= DGB_RWZ_MAX;
     if (fv->zparam) DGB_CUDA(cudaMemcpy(fv->ztab->rw, fv->tab.rw[2], of.size[2]*sizeof(double), cudaMemcpyDeviceToHost));
     const int32_t items[1] = {1};
-    if (int rc = get_plan(g, level, fv->mapper, DGB_InteriorBorder_All_Interface, DGB_ForwardCommunication, items, 1, fv->plan)) return rc;
+    // a plan of its own (not the grid's cache): the FV exchange may run while the user calls dgb_communicate with the same
+    // layout on another stream, and the two must not share send / receive buffers
+    fv->plan = build_plan(g, level, fv->mapper, DGB_InteriorBorder_All_Interface, DGB_ForwardCommunication, items, 1);
     compute_split(fv.get());
     if (getenv("DGB_FV_NO_SPLIT")) fv->split = false;
     if (const char* e = getenv("DGB_FV_TRACE")) fv->traceLeft = atoi(e);
@@ -1278,8 +1265,13 @@ int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host
   });
 }
 
-int dgb_fv_destroy(dgb_fv* fv) {
+static int fv_free(dgb_fv* fv, bool collective) {
   if (!fv) return DGB_OK;
+  int rc = DGB_OK;
+  // the fused exchange block is mapped by the other ranks: collective teardown (close, barrier, free) - or, when the caller
+  // cannot promise that all ranks are here (dgb_fv_abandon), close the imports and leak the exported block
+  if (collective) rc = fused_teardown(fv->fused, fv->comm, nullptr);
+  else { cudaDeviceSynchronize(); fv->fused.release(!fv->fused.multi); }
   if (fv->dSlots) cudaFree(fv->dSlots);
   if (fv->dTables) cudaFree(fv->dTables);
   for (int i = 0; i < 2; ++i) if (fv->dStage[i]) cudaFree(fv->dStage[i]);
@@ -1295,8 +1287,11 @@ int dgb_fv_destroy(dgb_fv* fv) {
   for (int k = 0; k < 2; ++k) if (fv->evRed[k]) cudaEventDestroy(fv->evRed[k]);
   if (fv->sOut) cudaStreamDestroy(fv->sOut);
   delete fv;
-  return DGB_OK;
+  return rc;
 }
+
+int dgb_fv_destroy(dgb_fv* fv) { return fv_free(fv, true); }
+int dgb_fv_abandon(dgb_fv* fv) { return fv_free(fv, false); }
 
 int dgb_fv_init_field(dgb_fv* fv, double* d_c, void* stream) {
   const dgb_view& v = fv->view;
@@ -1310,8 +1305,13 @@ int dgb_fv_init_field(dgb_fv* fv, double* d_c, void* stream) {
   return DGB_OK;
 }
 
+static const char* const kTimeoutMsg = "fused exchange: a rank did not deliver its step within 20 s (ranks out of step, or a peer has died); "
+                                       "this dgb_fv object accepts no further steps";
+
 int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (fv->fused.timed_out()) return fail(DGB_ENCCL, kTimeoutMsg);           // sticky: nothing is launched after a time-out
+  if (fv->comm) if (int rc = nccl_check_async(fv->comm)) return rc;
   if (!fv->bootstrapped) if (int rc = bootstrap(fv, stream)) return rc;
   const long long n = fv->step;
   FvArgs a = base_args(fv);
@@ -1342,8 +1342,8 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
     const long long before = fv->plan->launches;
     // the wait for all ranks' flags (+ CFL reduction) rides on the first unpack launch; ranks that receive nothing (no
     // overlap cells) still need it for the CFL value
-    const HaloWait hw{fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4)};
-    if (fv->plan->nRecvBoxes == 0) { k_fv_wait<<<1, 64, 0, stream>>>(fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4)); ++fv->launches; }
+    const HaloWait hw{fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4), fs.dTimeout};
+    if (fv->plan->nRecvBoxes == 0) { k_fv_wait<<<1, 64, 0, stream>>>(fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4), fs.dTimeout); ++fv->launches; }
     if (int rc = plan_unpack_from(*fv->plan, fs.recv[parity], DGB_OP_SET, arrays, items, 1, stream, &hw)) return rc;
     fv->launches += fv->plan->launches - before;
     int64_t bytes = 0;
@@ -1464,7 +1464,7 @@ int dgb_fv_last_dt(dgb_fv* fv, double* dt_host, void* stream) {
   unsigned timedOut = 0;
   if (fv->fused.on) DGB_CUDA(cudaMemcpyAsync(&timedOut, &fv->fused.ctl->timeout, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   DGB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  if (timedOut) return fail(DGB_ENCCL, "fused exchange: a rank did not deliver its step within 20 s (ranks out of step?)");
+  if (timedOut || fv->fused.timed_out()) return fail(DGB_ENCCL, kTimeoutMsg);
   return DGB_OK;
 }
 
@@ -1487,6 +1487,7 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
   static const int nslab = [] { const char* e = getenv("DGB_FV_HOST_SLABS"); const int v = e ? atoi(e) : 32; return v >= 2 && v <= 256 ? v : 32; }();
   const bool pipelined = v.dim == 3 && v.nranks == 1 && !fv->plan->nSendBoxes && !fv->plan->nRecvBoxes
                          && of.size[2] == in.size[2] && of.size[2] >= 4*nslab && !getenv("DGB_FV_HOST_SERIAL");
+  fv->hostPath = pipelined ? DGB_FV_HOST_PIPELINED : DGB_FV_HOST_SERIAL;
   if (!pipelined) {
     DGB_CUDA(cudaMemcpyAsync(fv->dStage[0], h_c_in, bytes, cudaMemcpyHostToDevice, stream));
     // every stored cell of the result is written: interior cells by the kernel, overlap cells by the exchange
@@ -1541,6 +1542,8 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
   return DGB_OK;
 }
 
+int dgb_fv_host_path(const dgb_fv* fv, int* path) { *path = fv->hostPath; return DGB_OK; }
+int dgb_fv_kernel_info(const dgb_fv* fv, int32_t* info8) { for (int k = 0; k < 8; ++k) info8[k] = fv->kinfo[k]; return DGB_OK; }
 int dgb_fv_launch_count(const dgb_fv* fv, int64_t* kernels) { *kernels = fv->launches; return DGB_OK; }
 int dgb_fv_exchange_mode(const dgb_fv* fv, int* mode) { *mode = fv->exchangeMode; return DGB_OK; }
 

@@ -140,10 +140,11 @@ extern "C" int dgb_vtk_write(const dgb_grid* g, int level, const char* name, con
     const std::string dir = path ? path : "";
     const std::string piece = with_path(dir, size > 1 ? parallel_name(name, rank, size) : std::string(name) + ".vtu");
     {
-      std::ofstream file(piece.c_str(), std::ios::binary);
-      if (!file.is_open()) throw ArgError("Could not write to piece file " + piece);
-      std::vector<char> buffer(1 << 22);
+      std::vector<char> buffer(1 << 22);                 // declared before the stream: it must outlive the filebuf that uses it
+      std::ofstream file;
       file.rdbuf()->pubsetbuf(buffer.data(), std::streamsize(buffer.size()));
+      file.open(piece.c_str(), std::ios::binary);
+      if (!file.is_open()) throw ArgError("Could not write to piece file " + piece);
       VtkIndent indent;
       file << indent << "<?xml version=\"1.0\"?>\n";
       file << indent << "<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n";

@@ -153,6 +153,12 @@ class YaspGrid:
     def levelGridView(self, level):
         return GridView(self, level)
 
+    def lastBytesSent(self):
+        """bytes this rank sent to OTHER ranks in its most recent exchange (dgb_communicate or the FV step)"""
+        n = C.c_int64(0)
+        check(lib.dgb_comm_last_bytes(self.h, C.byref(n)))
+        return n.value
+
     def commList(self, level, codim, which):
         cap = 4096
         out = (C.c_int32 * (cap * 10))()
@@ -304,11 +310,19 @@ class GridView:
         """VTKWriter(gridView).addCellData/addVertexData + write(name) (dune/grid/io/file/vtk/vtkwriter.hh; dune-python:
         gridView.writeVTK(name, celldata={...}, pointdata={...})). Values: CUDA tensors indexed by the element / vertex index,
         shape (n,) scalar, (n, k) with k <= 3 vector. Returns the file to open (.vtu, or the .pvtu header on several ranks)."""
-        def pack(d):
+        def pack(d, nent, kind):
             arr = (capi.VtkField * max(1, len(d or {})))()
             keep = []
             for k, (nm, t) in enumerate((d or {}).items()):
-                t = t.contiguous()
+                # dgb_vtk_write reads ncomp*entities DOUBLES from DEVICE memory: convert / validate instead of passing garbage
+                torch = _torch()
+                if not isinstance(t, torch.Tensor):
+                    t = torch.as_tensor(np.asarray(t))
+                t = t.to(device="cuda", dtype=torch.float64).contiguous()
+                if t.dim() not in (1, 2) or (t.dim() == 2 and not 1 <= t.shape[1] <= 3):
+                    raise ValueError(f"writeVTK: field '{nm}' must have shape (n,) or (n, k) with k <= 3, got {tuple(t.shape)}")
+                if t.shape[0] != nent:
+                    raise ValueError(f"writeVTK: field '{nm}' has {t.shape[0]} entries, the view has {nent} {kind}")
                 keep.append(t)
                 arr[k].name = nm.encode()
                 arr[k].d_data = t.data_ptr()
@@ -316,8 +330,10 @@ class GridView:
                 arr[k].is_vector = 0 if t.dim() == 1 else 1
                 arr[k].precision = 1 if float64 else 0
             return arr, len(d or {}), keep
-        ca, nc, k1 = pack(celldata)
-        va, nv, k2 = pack(pointdata)
+        if celldata or pointdata:
+            _require_cuda()
+        ca, nc, k1 = pack(celldata, self.size(0), "cells")
+        va, nv, k2 = pack(pointdata, self.size(self.dim), "vertices")
         out = C.create_string_buffer(4096)
         check(lib.dgb_vtk_write(self.grid.h, self.level, str(name).encode(), str(path).encode(), ca, nc, va, nv, 1 if float64 else 0,
                                 out, 4096, _stream() if (nc or nv) else None))
@@ -481,13 +497,28 @@ class FiniteVolume:
         self.gv = grid.levelGridView(level)
         self.ncells = self.gv.size(0)
 
+    def close(self):
+        """dgb_fv_destroy: COLLECTIVE on a multi-rank grid (all ranks close their mappings of the peers' exchange blocks, meet in
+        a barrier on the communicator, then free) - call it on every rank before Communicator.close()"""
+        if getattr(self, "h", None):
+            h, self.h = self.h, None
+            check(lib.dgb_fv_destroy(h))
+
     def __del__(self):
+        # garbage collection is not collective: free what is local, leave the exported exchange block to process exit
         try:
             if getattr(self, "h", None):
-                lib.dgb_fv_destroy(self.h)
+                (lib.dgb_fv_abandon if self.grid.nranks > 1 else lib.dgb_fv_destroy)(self.h)
                 self.h = None
         except Exception:
             pass
+
+    def kernel_info(self):
+        """which kernel the last step ran: dict(kind='ring'|'ring_bulk'|'march'|'step2d', variant, tile, staging_bytes, zchunk, packs)"""
+        a = (C.c_int32 * 8)()
+        check(lib.dgb_fv_kernel_info(self.h, a))
+        return {"kind": ("none", "step2d", "march", "ring", "ring_bulk")[a[0]], "variant": a[1], "tile": (a[2], a[3]),
+                "staging_bytes": a[4], "zchunk": a[5], "packs": bool(a[6])}
 
     def initial(self):
         torch = _torch()
@@ -525,6 +556,12 @@ class FiniteVolume:
         dt = C.c_double(0)
         check(lib.dgb_fv_step_host(self.h, C.c_void_p(h_in.data_ptr()), C.c_void_p(h_out.data_ptr()), C.byref(dt), _stream()))
         return dt.value
+
+    def host_path(self):
+        """how the last step_host moved the field: 'none', 'serial' or 'pipelined' (z-slabs on three streams)"""
+        m = C.c_int(0)
+        check(lib.dgb_fv_host_path(self.h, C.byref(m)))
+        return ("none", "serial", "pipelined")[m.value]
 
     def launch_count(self):
         n = C.c_int64(0)

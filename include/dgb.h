@@ -230,7 +230,12 @@ enum { DGB_FV_EXACT = 0,           /* per-cell arithmetic in the reference order
        DGB_FV_SEPARABLE = 1 };     /* tensor-product factorised face factors: <= 1e-13 relative */
 int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host, int nparams, int mode,
                   dgb_comm* comm, dgb_fv** out);
+/* dgb_fv_destroy is COLLECTIVE on a multi-rank grid whose steps used the fused exchange (like MPI_Win_free): every rank closes
+ * its mappings of the peers' exchange blocks, all ranks meet in a barrier on `comm` (which must still be alive), then the blocks
+ * are freed. dgb_fv_abandon is the non-collective form (e.g. from a garbage collector): it frees everything local and
+ * deliberately leaks the exported exchange block, because freeing memory another process may still have mapped is undefined. */
 int dgb_fv_destroy(dgb_fv* fv);
+int dgb_fv_abandon(dgb_fv* fv);
 int dgb_fv_init_field(dgb_fv* fv, double* d_c, void* stream);          /* c0 at the cell centres, all stored cells */
 /* one step: c_out = c_in + dt*update(c_in) on interior cells, halo of c_out refreshed, dt = 0.99*min(1/sum_out) */
 int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream);
@@ -244,12 +249,27 @@ int dgb_fv_last_dt(dgb_fv* fv, double* dt_host, void* stream);         /* synchr
 int dgb_fv_update(dgb_fv* fv, const double* d_c_in, double* d_update, void* stream);
 /* the same step on HOST buffers (pinned or pageable): H2D copy of c, step, D2H copy of the result */
 int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* dt_host, void* stream);
+/* how the last dgb_fv_step_host moved the field: */
+#define DGB_FV_HOST_NONE 0
+#define DGB_FV_HOST_SERIAL 1        /* H2D of the whole field, step, D2H of the whole field */
+#define DGB_FV_HOST_PIPELINED 2     /* z-slabs: upload, step kernel and download of different slabs run concurrently on three streams */
+int dgb_fv_host_path(const dgb_fv* fv, int* path);
 int dgb_fv_launch_count(const dgb_fv* fv, int64_t* kernels);           /* kernels launched by this object so far */
+/* which kernel the last step launched for the (bulk of the) interior cells: info8 = { kind, tuning variant, tile width, tile
+ * height, bytes per staging copy (16 = paired cp.async, 8 = per cell, 0 = not a ring kernel), z planes per CTA, 1 if the
+ * launch packed the send boxes into the peers' memory (fused exchange), 0 } */
+enum { DGB_FV_KERNEL_NONE = 0, DGB_FV_KERNEL_STEP2D = 1, DGB_FV_KERNEL_MARCH = 2, DGB_FV_KERNEL_RING = 3, DGB_FV_KERNEL_RING_BULK = 4 };
+int dgb_fv_kernel_info(const dgb_fv* fv, int32_t* info8);
 /* how the last dgb_fv_step refreshed the overlap cells: */
 #define DGB_FV_EXCHANGE_NONE 0      /* no step yet, or nothing to exchange */
 #define DGB_FV_EXCHANGE_SERIAL 1    /* step kernel, then communicate() (2-D, or no room for a shell/bulk split) */
 #define DGB_FV_EXCHANGE_OVERLAPPED 2 /* shell kernel + NCCL send/recv on a second stream, concurrent with the bulk kernel */
 #define DGB_FV_EXCHANGE_FUSED 3     /* one step kernel stores into the receivers' buffers over peer-mapped memory and signals */
+/* Limits of the fused form (beyond them dgb_fv_step keeps the NCCL forms, same results): at most 64 ranks (control block),
+ * at most 32 send boxes per rank (26 in 3-D with overlap; more only with several codims, which the FV exchange does not
+ * have). dgb_communicate takes at most 8 arrays per call. A peer that does not deliver its step within 20 s makes the
+ * waiting kernel give up WITHOUT unpacking; the time-out is sticky: every later dgb_fv_step / dgb_fv_step_host / dgb_fv_last_dt
+ * of the object returns DGB_ENCCL and launches nothing. */
 int dgb_fv_exchange_mode(const dgb_fv* fv, int* mode);
 
 #ifdef __cplusplus

@@ -89,3 +89,30 @@ def compare_world(w, grid_of_rank, d, P, nlevels):
                 fa, ca = gv.coordinates(ax)
                 fb, cb = w.coordinates(r, lvl, ax)
                 assert fa == fb and np.array_equal(ca, cb, equal_nan=True), (r, lvl, ax)
+
+
+def fv_init_all(w, P, level, problem, params):
+    """initial fields of all ranks; the per-rank oracle calls run concurrently (ctypes releases the GIL, the world is only read)"""
+    from concurrent.futures import ThreadPoolExecutor
+    if P == 1:
+        return [w.fv_init(0, level, problem, params)]
+    with ThreadPoolExecutor(max_workers=min(P, 32)) as ex:
+        return list(ex.map(lambda r: w.fv_init(r, level, problem, params), range(P)))
+
+
+def assemble_global(w, cfg, P, level, per_rank):
+    """one array over all cells of the level (x fastest) from the per-rank arrays of an oracle world: every rank contributes
+    its INTERIOR cells (the FV result does not depend on the partition: same cells, same arithmetic, global dt)"""
+    d = cfg["dim"]
+    N = [n << level for n in cfg["N"]]
+    shape = tuple(reversed(N))
+    out = np.full(shape, np.nan)
+    for r in range(P):
+        b = w.boxes(r, level, 0)[0]
+        (oo, os_), (io, is_) = b["overlapfront"], b["interior"]
+        a = per_rank[r].reshape(tuple(reversed(os_[:d])))
+        src = tuple(slice(io[i] - oo[i], io[i] - oo[i] + is_[i]) for i in reversed(range(d)))
+        dst = tuple(slice(io[i], io[i] + is_[i]) for i in reversed(range(d)))
+        out[dst] = a[src]
+    assert not np.isnan(out).any()
+    return out.reshape(-1)

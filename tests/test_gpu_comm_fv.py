@@ -135,8 +135,9 @@ FV_CASES = [
 ]
 
 
-def run_fv(cfg, P, problem, params, mode, steps):
-    """product FV over `steps` steps with emulated ranks; returns per-rank fields (numpy), dts and first update"""
+def run_fv(cfg, P, problem, params, mode, steps, want_info=False):
+    """product FV over `steps` steps with emulated ranks; returns per-rank fields (numpy), dts and first update
+    (+ the kernel_info of every rank's last step with want_info)"""
     import torch
     import dune_grid_b200 as dg
     lvl = cfg["refine"]
@@ -169,6 +170,8 @@ def run_fv(cfg, P, problem, params, mode, steps):
                           dg.ForwardCommunication, "set")
         dts.append(fvs[0].last_dt())
         c, cn = cn, c
+    if want_info:
+        return [np_(x) for x in c], dts, upd0, [fv.kernel_info() for fv in fvs]
     return [np_(x) for x in c], dts, upd0
 
 
@@ -252,59 +255,168 @@ def test_fv_public_step_and_host_entry_single_rank():
     w.close()
 
 
-def test_fv_full_size_properties():
-    """BASELINE config 2 at full size (512^3, 1 GPU): the oracle cannot run this in seconds, so check
-    size-independent properties: (i) discrete mass balance sum(c_new)-sum(c) = -dt*outflow through the boundary
-    (zero while the shell is away from the boundary, b = 0), (ii) maximum principle 0 <= c <= 1 for CFL 0.99,
-    (iii) dt = 0.99*h/3 exactly for u=(1,1,1) on the 2^-9 grid, (iv) exact and separable modes agree bit for bit
-    there (every operation is exact in binary floating point on this grid)."""
+def test_fv_production_kernel_against_oracle_at_baseline_size():
+    """BASELINE config 2 at full size (512^3 on one GPU; 256^3 if the device lacks memory): the kernels `bench.py` times
+    - k_fv_ring, 128x4 tile, 16-byte staging, selected because the region is >= 256 cells wide - compared DIRECTLY with the
+    reference oracle on the whole field after 3 steps: exact mode bit for bit, separable mode (production) within
+    1e-13 relative (tolerance of north_star), dt likewise. The oracle runs the same grid on 8 thread-ranks (the FV result
+    does not depend on the partition); plus the size-independent properties: dt = 0.99*h/3 exactly for u=(1,1,1) on the
+    2^-k grid, maximum principle, discrete mass balance."""
     import torch
     import dune_grid_b200 as dg
+    from tests.common import assemble_global, fv_init_all
     free, _ = torch.cuda.mem_get_info()
     n = 512 if free > 8 * 512 ** 3 * 8 else 256
     cfg = make_cfg(dim=3, N=(n, n, n))
+    P, steps = 8, 3
+    o = best_oracle()
+    w = oracle_world(o, cfg, P)
+    ref = fv_init_all(w, P, 0, 0, PARAMS0)
+    c0_ref = assemble_global(w, cfg, P, 0, ref)
+    _, dt_ref = w.fv_run(0, 0, PARAMS0, ref, steps)
+    c_ref = assemble_global(w, cfg, P, 0, ref)
+    w.close()
+    del ref
     g = product_grid(cfg, 0, 1)
-    res = {}
-    for mode in ("exact", "separable"):
+    for mode in ("separable", "exact"):
         fv = dg.FiniteVolume(g, 0, 0, PARAMS0, mode)
         c = fv.initial()
+        assert np.array_equal(np_(c), c0_ref)
         cn = torch.empty_like(c)
         m0 = c.sum().item()
-        for _ in range(3):
+        for _ in range(steps):
             fv.step(c, cn)
             c, cn = cn, c
-        assert fv.last_dt() == 0.99 * (1.0 / (3.0 * n))
+        info = fv.kernel_info()
+        if mode == "separable":       # the production selection, not a small-grid variant
+            assert info["kind"] == "ring" and info["tile"] == (128, 4) and info["staging_bytes"] == 16, info
+        else:
+            assert info["kind"] == "march", info
+        dt = fv.last_dt()
+        assert dt == 0.99 * (1.0 / (3.0 * n))
+        assert dt == dt_ref if mode == "exact" else abs(dt - dt_ref) <= 1e-13 * dt_ref
         assert c.min().item() >= 0.0 and c.max().item() <= 1.0
         assert abs(c.sum().item() - m0) <= 1e-9 * m0
-        res[mode] = c.clone()
-        del fv, cn
-    assert torch.equal(res["exact"], res["separable"])
+        got = np_(c)
+        if mode == "exact":
+            assert np.array_equal(got, c_ref)
+        else:
+            assert np.abs(got - c_ref).max() <= 1e-13 * np.abs(c_ref).max()          # tolerance: 1e-13 relative
+        del fv, c, cn, got
+
+
+ODD_STRIDE_PARAMS = [1.0, -0.5, 0.25, 0.1, 0.5, 0.5, 0.5, 0.1, 0.45]
+
+
+@pytest.mark.parametrize("mode", ["exact", "separable"])
+def test_fv_wide_rank_boxes_with_odd_row_stride_against_oracle(mode):
+    """the rank-local boxes of a partitioned grid (BASELINE config 3: 513 cells per row) have odd row strides and interior
+    regions that start at an odd offset: rows are only 8-byte aligned. Here 512 x 48 x 40 on 2 emulated ranks (257-wide
+    stored boxes, 256-wide regions -> the wide 128x4 tile is selected) against the oracle, mixed flow directions, b != 0"""
+    cfg = make_cfg(dim=3, N=(512, 48, 40))
+    o = best_oracle()
+    w = oracle_world(o, cfg, 2)
+    steps = 4
+    ref = [w.fv_init(r, 0, 0, ODD_STRIDE_PARAMS) for r in range(2)]
+    ref_dts = [w.fv_step(0, 0, ODD_STRIDE_PARAMS, ref) for _ in range(steps)]
+    got, dts, _, infos = run_fv(cfg, 2, 0, ODD_STRIDE_PARAMS, mode, steps, want_info=True)
+    if mode == "separable":
+        for info in infos:
+            assert info["kind"] == "ring" and info["tile"] == (128, 4), info
+    scale = max(np.abs(x).max() for x in ref)
+    for a, b in zip(dts, ref_dts):
+        assert a == b if mode == "exact" else abs(a - b) <= 1e-13 * abs(b)
+    for r in range(2):
+        if mode == "exact":
+            assert np.array_equal(got[r], ref[r])
+        else:
+            assert np.abs(got[r] - ref[r]).max() <= 1e-13 * scale                       # tolerance: 1e-13 relative
+    w.close()
+
+
+@pytest.mark.parametrize("N,periodic", [((511, 24, 40), 7), ((510, 21, 37), 5), ((255, 40, 33), 3)])
+def test_fv_fused_exchange_on_wide_odd_boxes_against_oracle(N, periodic):
+    """the fused step (in-kernel pack + peer stores + flags) on single-rank periodic grids whose stored boxes are 513 / 512
+    / 257 cells wide with the interior starting at offset 1 - the shapes of the 2x2x2, 4x1x1 and 2x1x1 rank boxes of
+    config 3 - in production (separable) mode against the oracle within 1e-13, and in exact mode bit for bit"""
+    import torch
+    import dune_grid_b200 as dg
+    cfg = make_cfg(dim=3, N=N, periodic=periodic, upper=(1.0, 0.1, 0.1))
+    o = best_oracle()
+    w = oracle_world(o, cfg, 1)
+    params = [1.0, -0.07, 0.03, 0.2, 0.5, 0.05, 0.05, 0.02, 0.3]
+    for mode in ("separable", "exact"):
+        ref = [w.fv_init(0, 0, 0, params)]
+        g = product_grid(cfg, 0, 1)
+        fv = dg.FiniteVolume(g, 0, 0, params, mode)
+        c = fv.initial()
+        cn = torch.empty_like(c)
+        for _ in range(4):
+            dt_ref = w.fv_step(0, 0, params, ref)
+            fv.step(c, cn)
+            c, cn = cn, c
+            dt = fv.last_dt()
+            assert dt == dt_ref if mode == "exact" else abs(dt - dt_ref) <= 1e-13 * dt_ref
+        assert fv.exchange_mode() == "fused"
+        info = fv.kernel_info()
+        assert info["packs"]
+        if mode == "separable" and N[0] >= 256:
+            assert info["kind"] == "ring" and info["tile"] == (128, 4), info
+        if mode == "exact":
+            assert np.array_equal(np_(c), ref[0])
+        else:
+            assert np.abs(np_(c) - ref[0]).max() <= 1e-13 * np.abs(ref[0]).max()         # tolerance: 1e-13 relative
+        fv.close()
+    w.close()
 
 
 @pytest.mark.parametrize("problem,params", [(0, [1.0, -0.5, 0.25, 0.1, 0.5, 0.5, 0.5, 0.1, 0.45]), (0, [-0.3, 0.0, 1.0, 0.7, 0.5, 0.5, 0.5, 0.1, 0.45]),
                                             (1, [2.0, 0, 0, 0.5, 0.15, 0.35, 0.9, 0.05, 0.4])])
 def test_fv_ring_kernels_equal_general_kernel_bitwise(problem, params, monkeypatch):
-    """the production ring kernel (both tile shapes; variant 11: rows staged by cp.async.bulk + mbarrier) with partial tiles, mixed flow directions, boundary inflow b != 0, graded
-    and periodic coordinates) against the general z-march kernel on a random field: same arithmetic, same bits"""
+    """the production ring kernel - every tile shape, and all three staging forms: phase-aware 16-byte pairs (default),
+    aligned pairs, 8 bytes per cell - with partial tiles, mixed flow directions, boundary inflow b != 0, graded and periodic
+    coordinates, odd and even row / plane strides, fields that are only 8-byte aligned, chunks that end at the array's last
+    element, against the general z-march kernel on a random field: same arithmetic, same bits"""
     import torch
     import dune_grid_b200 as dg
-    for cfg in (make_cfg(dim=3, N=(150, 37, 70), mode=2), make_cfg(dim=3, N=(70, 45, 33), periodic=3, upper=(1.0, 0.7, 1.3))):
+    cfgs = (make_cfg(dim=3, N=(150, 37, 70), mode=2),                                        # even rows, odd offsets nowhere
+            make_cfg(dim=3, N=(70, 45, 33), periodic=3, upper=(1.0, 0.7, 1.3)),              # 72 x 47: even row, odd plane stride... (72*47 even)
+            make_cfg(dim=3, N=(131, 21, 19), periodic=7, upper=(1.0, 0.2, 0.2)),             # 133 x 23 x 21: odd rows, odd planes, interior at offset 1
+            make_cfg(dim=3, N=(259, 10, 18), periodic=1, upper=(1.0, 0.05, 0.1)))            # 261 wide: the 128x4 tile with a partial last tile
+    for ci, cfg in enumerate(cfgs):
         g = product_grid(cfg, 0, 1)
         n = g.leafGridView().size(0)
-        c0 = torch.from_numpy(np.random.default_rng(3).uniform(0.0, 1.0, n)).cuda()
-        res = {}
-        for variant in ("99", "0", "3", "11"):
-            monkeypatch.setenv("DGB_FV_VARIANT", variant)
-            monkeypatch.setenv("DGB_FV_ZCHUNK", "16")
-            fv = dg.FiniteVolume(g, 0, problem, params, "separable")
-            c, cn = c0.clone(), torch.empty_like(c0)
-            for _ in range(2):
-                fv.step(c, cn)
-                c, cn = cn, c
-            res[variant] = (c.clone(), fv.last_dt())
-        for variant in ("0", "3", "11"):
-            assert res[variant][1] == res["99"][1]
-            assert torch.equal(res[variant][0], res["99"][0]), (cfg["N"], variant)
+        for misalign in (0, 1):                                  # field (and result) start at an odd multiple of 8 bytes
+            buf0 = torch.zeros(n + 2, dtype=torch.float64, device="cuda")
+            buf1 = torch.zeros(n + 2, dtype=torch.float64, device="cuda")
+            c0 = torch.from_numpy(np.random.default_rng(3).uniform(0.0, 1.0, n)).cuda()
+            res = {}
+            for variant, staging in (("99", "pair"), ("0", "pair"), ("3", "pair"), ("0", "8"), ("3", "8"), ("3", "a16"), ("7", "pair"),
+                                     ("2", "pair"), ("9", "pair")):
+                if misalign and (variant, staging) not in (("99", "pair"), ("0", "pair"), ("3", "pair"), ("3", "a16")):
+                    continue
+                monkeypatch.setenv("DGB_FV_VARIANT", variant)
+                monkeypatch.setenv("DGB_FV_STAGING", staging)
+                monkeypatch.setenv("DGB_FV_ZCHUNK", "16")
+                monkeypatch.setenv("DGB_FV_FUSED", "0")         # the serial exchange: the step kernel alone is compared here
+                monkeypatch.setenv("DGB_FV_NO_SPLIT", "1")
+                fv = dg.FiniteVolume(g, 0, problem, params, "separable")
+                c, cn = buf0[misalign:misalign + n], buf1[misalign:misalign + n]
+                c.copy_(c0)
+                for _ in range(2):
+                    fv.step(c, cn)
+                    c, cn = cn, c
+                info = fv.kernel_info()
+                if variant != "99":
+                    assert info["kind"] == "ring" and info["variant"] == int(variant), info
+                    if staging == "pair":
+                        assert info["staging_bytes"] == 16
+                    if staging == "8":
+                        assert info["staging_bytes"] == 8
+                res[(variant, staging)] = (c.clone(), fv.last_dt())
+            for key, val in res.items():
+                assert val[1] == res[("99", "pair")][1]
+                assert torch.equal(val[0], res[("99", "pair")][0]), (cfg["N"], misalign, key)
 
 
 @pytest.mark.parametrize("mode", ["exact", "separable"])
