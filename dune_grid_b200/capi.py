@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdgb.so")
+LIB_PATH = os.environ.get("DGB_LIBRARY") or os.path.join(HERE, "libdgb.so")      # DGB_LIBRARY: an alternative build (developer A/B runs)
 
 DGB_MAX_DIM, DGB_MAX_COMP = 3, 8
 OK, EGRID, ERANGE, EARG, ECUDA, ENCCL, ENOTIMPL = 0, -1, -2, -3, -4, -5, -6
@@ -96,6 +96,7 @@ _SIG = {
     "dgb_comm_last_bytes": (_i, [_vp, _i64p]),
     "dgb_fv_create": (_i, [_vp, _i, _i, C.POINTER(C.c_double), _i, _i, _vp, C.POINTER(_vp)]),
     "dgb_fv_destroy": (_i, [_vp]), "dgb_fv_abandon": (_i, [_vp]), "dgb_fv_init_field": (_i, [_vp, _vp, _vp]),
+    "dgb_fv_register_fields": (_i, [_vp, C.POINTER(_vp), _i, _vp]), "dgb_fv_registered_fields": (_i, [_vp, C.POINTER(_i)]),
     "dgb_fv_kernel_info": (_i, [_vp, C.POINTER(C.c_int32)]), "dgb_fv_host_path": (_i, [_vp, C.POINTER(_i)]),
     "dgb_fv_step": (_i, [_vp, _vp, _vp, _vp]), "dgb_fv_last_dt": (_i, [_vp, C.POINTER(C.c_double), _vp]),
     "dgb_fv_update": (_i, [_vp, _vp, _vp, _vp]),

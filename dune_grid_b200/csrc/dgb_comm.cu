@@ -160,6 +160,15 @@ static void add_boxes(const dgb_grid* g, int level, int codim, int which, const 
     for (int i = lb.dim; i < 3; ++i) { b.size[i] = 1; b.of_size[i] = 1; b.origin[i] = 0; b.of_origin[i] = 0; }
     b.index_base = unsigned(e.index_offset);
     b.block = m.block[codim]; b.map_offset = m.offset[codim];
+    {
+      const LevelBoxes& pl = g->all[e.rank].levels[level].b;
+      const dgb_box& pof = pl.comp[pl.comp_begin[codim] + pl.shiftmap[e.shift]].box[DGB_BOX_OVERLAPFRONT];
+      for (int i = 0; i < 3; ++i) {
+        b.peer_origin[i] = i < lb.dim ? e.box.origin[i] - e.move[i] : 0;
+        b.peer_of_origin[i] = i < lb.dim ? pof.origin[i] : 0; b.peer_of_size[i] = i < lb.dim ? pof.size[i] : 1;
+      }
+      b.peer = e.rank;
+    }
     b.buf_offset = 0;
     (void)per_entity_codim;
     boxes.push_back(b);
@@ -363,7 +372,13 @@ int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d
 // segment in the receive buffers (-1: no message from that rank)
 struct FusedInfo { cudaIpcMemHandle_t handle; long long segOffset[64]; long long segCount[64]; long long recvTotal; int ok; int pad; };
 
+void FusedState::release_direct() {
+  for (auto& d : direct) { if (d.dPack) cudaFree(d.dPack); if (d.dDst) cudaFree(d.dDst); if (d.dRow) cudaFree(d.dRow); if (d.dPlane) cudaFree(d.dPlane); }
+  direct.clear();
+}
+
 void FusedState::release(bool free_block) {
+  release_direct();
   for (void* p : opened) cudaIpcCloseMemHandle(p);
   opened.clear();
   for (int k = 0; k < 2; ++k) { if (dDst[k]) cudaFree(dDst[k]); dDst[k] = nullptr; }
@@ -478,6 +493,7 @@ int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStre
   }
   if (ok && soft(cudaMalloc(&fs.dPack, 2*sizeof(FusedPack)), "cudaMalloc(FusedPack)"))
     soft(cudaMemcpy(fs.dPack, pk, 2*sizeof(FusedPack), cudaMemcpyHostToDevice), "cudaMemcpy(FusedPack)");
+  fs.hostPack[0] = pk[0]; fs.hostPack[1] = pk[1];
   if (multi) {                                           // every rank must reach the same verdict: min over ranks of 1/0
     double v = ok ? 1.0 : 0.0;
     double* dScratch = nullptr;
@@ -497,6 +513,114 @@ int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStre
   }
   fs.epoch = 0;
   fs.on = true;
+  return DGB_OK;
+}
+
+// base address of the allocation that holds `p` (cuMemGetAddressRange through the driver library, which - like NCCL - is
+// loaded at run time so that libdgb.so still loads on a box without a GPU driver)
+static bool allocation_base(const void* p, char** base) {
+  typedef int (*fn_t)(unsigned long long*, size_t*, unsigned long long);
+  static fn_t fn = [] { void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL); return h ? reinterpret_cast<fn_t>(dlsym(h, "cuMemGetAddressRange_v2")) : nullptr; }();
+  if (!fn) return false;
+  unsigned long long b = 0; size_t n = 0;
+  if (fn(&b, &n, reinterpret_cast<unsigned long long>(p)) != 0) return false;
+  *base = reinterpret_cast<char*>(b);
+  return true;
+}
+
+static constexpr int MAX_REG_FIELDS = 4;
+struct RegInfo { cudaIpcMemHandle_t handle[MAX_REG_FIELDS]; unsigned long long offset[MAX_REG_FIELDS]; int ok; int pad; };
+
+int fused_register(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs,
+                   double* const* fields, int nfields) {
+  fs.release_direct();
+  if (!fs.on) return DGB_OK;
+  if (nfields < 1 || nfields > MAX_REG_FIELDS) return fail(DGB_EARG, "dgb_fv_register_fields: 1 to 4 fields");
+  const bool multi = nranks > 1;
+  // local vote: the plan must be a plain codim-0, one-double-per-cell exchange without overlapping receive boxes
+  bool ok = plan.items == 1 && plan.recvWaveEnd.size() <= 1;
+  for (auto& b : plan.hostSend) if (b.block != 1 || b.map_offset != 0 || b.index_base != 0) ok = false;
+  for (auto& b : plan.hostRecv) if (b.block != 1 || b.map_offset != 0 || b.index_base != 0) ok = false;
+  RegInfo mine; std::memset(&mine, 0, sizeof(mine));
+  if (multi) {
+    for (int f = 0; f < nfields && ok; ++f) {
+      char* base = nullptr;
+      if (!allocation_base(fields[f], &base)) { ok = false; break; }
+      if (cudaIpcGetMemHandle(&mine.handle[f], base) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      mine.offset[f] = (unsigned long long)(reinterpret_cast<const char*>(fields[f]) - base);
+    }
+  }
+  mine.ok = ok ? 1 : 0;
+  std::vector<RegInfo> all(nranks);
+  if (multi) {
+    RegInfo* dAll = nullptr;
+    if (cudaMalloc(&dAll, sizeof(RegInfo)*nranks) != cudaSuccess) { cudaGetLastError(); return fail(DGB_ECUDA, "fused_register: cudaMalloc"); }
+    cudaMemcpyAsync(dAll + myrank, &mine, sizeof(RegInfo), cudaMemcpyHostToDevice, stream);
+    const bool sent = g_nccl.AllGather(dAll + myrank, dAll, sizeof(RegInfo), ncclChar, comm->comm, stream) == ncclSuccess;
+    cudaMemcpyAsync(all.data(), dAll, sizeof(RegInfo)*nranks, cudaMemcpyDeviceToHost, stream);
+    const bool synced = cudaStreamSynchronize(stream) == cudaSuccess;
+    cudaFree(dAll);
+    if (!sent || !synced) return fail(DGB_ENCCL, "fused_register: exchange of the field handles failed");
+  } else all[0] = mine;
+  for (int r = 0; r < nranks; ++r) ok = ok && all[r].ok;
+  // map the arrays of the ranks this rank sends to (one mapping per distinct allocation)
+  std::vector<std::vector<char*>> fieldOf(nranks, std::vector<char*>(nfields, nullptr));
+  std::vector<std::pair<cudaIpcMemHandle_t, char*>> mapped;
+  for (int f = 0; f < nfields; ++f) fieldOf[myrank][f] = reinterpret_cast<char*>(fields[f]);
+  if (ok)
+    for (auto& sg : plan.sendSeg) {
+      if (sg.peer == myrank) continue;
+      for (int f = 0; f < nfields && ok; ++f) {
+        char* base = nullptr;
+        for (auto& m : mapped) if (!std::memcmp(&m.first, &all[sg.peer].handle[f], sizeof(cudaIpcMemHandle_t))) base = m.second;
+        if (!base) {
+          void* p = nullptr;
+          if (cudaIpcOpenMemHandle(&p, all[sg.peer].handle[f], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+          fs.opened.push_back(p);
+          base = static_cast<char*>(p);
+          mapped.emplace_back(all[sg.peer].handle[f], base);
+        }
+        fieldOf[sg.peer][f] = base + all[sg.peer].offset[f];
+      }
+    }
+  std::vector<FusedState::Direct> dir(ok ? nfields : 0);
+  for (int f = 0; f < nfields && ok; ++f) {
+    const int nb = plan.nSendBoxes;
+    std::vector<double*> dst(nb); std::vector<int> row(nb), plane(nb);
+    for (int b = 0; b < nb; ++b) {
+      const PlanBox& pb = plan.hostSend[b];
+      const long long idx = ((long long)(pb.peer_origin[2]-pb.peer_of_origin[2])*pb.peer_of_size[1] + (pb.peer_origin[1]-pb.peer_of_origin[1]))*pb.peer_of_size[0]
+                            + (pb.peer_origin[0]-pb.peer_of_origin[0]);
+      dst[b] = reinterpret_cast<double*>(fieldOf[pb.peer][f]) + idx;
+      row[b] = pb.peer_of_size[0]; plane[b] = pb.peer_of_size[0]*pb.peer_of_size[1];
+    }
+    FusedState::Direct& d = dir[f];
+    d.field = fields[f];
+    auto up = [&](void** dev, const void* host, size_t bytes) {
+      if (bytes == 0) return true;
+      if (cudaMalloc(dev, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+      return cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    ok = ok && up(reinterpret_cast<void**>(&d.dDst), dst.data(), nb*sizeof(double*)) && up(reinterpret_cast<void**>(&d.dRow), row.data(), nb*sizeof(int))
+            && up(reinterpret_cast<void**>(&d.dPlane), plane.data(), nb*sizeof(int));
+    FusedPack pk[2] = { fs.hostPack[0], fs.hostPack[1] };
+    for (int k = 0; k < 2; ++k) { pk[k].dst = d.dDst; pk[k].dstRow = d.dRow; pk[k].dstPlane = d.dPlane; }
+    ok = ok && up(reinterpret_cast<void**>(&d.dPack), pk, 2*sizeof(FusedPack));
+  }
+  if (multi) {                                           // same verdict everywhere
+    double v = ok ? 1.0 : 0.0;
+    double* dScratch = nullptr;
+    if (cudaMalloc(&dScratch, sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(DGB_ECUDA, "fused_register: cudaMalloc"); }
+    cudaMemcpyAsync(dScratch, &v, sizeof(double), cudaMemcpyHostToDevice, stream);
+    const bool sent = g_nccl.AllReduce(dScratch, dScratch, 1, ncclDouble, ncclMin, comm->comm, stream) == ncclSuccess;
+    cudaMemcpyAsync(&v, dScratch, sizeof(double), cudaMemcpyDeviceToHost, stream);
+    const bool synced = cudaStreamSynchronize(stream) == cudaSuccess;
+    cudaFree(dScratch);
+    if (!sent || !synced) return fail(DGB_ENCCL, "fused_register: verdict all-reduce failed");
+    ok = v > 0.5;
+  }
+  if (ok) fs.direct = dir;
+  else for (auto& d : dir) { if (d.dPack) cudaFree(d.dPack); if (d.dDst) cudaFree(d.dDst); if (d.dRow) cudaFree(d.dRow); if (d.dPlane) cudaFree(d.dPlane); }
   return DGB_OK;
 }
 

@@ -19,6 +19,10 @@ struct PlanBox {
   long long count;                  // entities
   unsigned index_base;              // mapper: index = (component offset + local superindex)*block + offset
   unsigned block, map_offset;
+  // the same entities in the partner's own frame, and the partner's enclosing overlapfront box of the component: where a
+  // sender finds the receiver's copy of a cell (registered fields: stores go straight into the partner's array)
+  int peer_origin[3], peer_of_origin[3], peer_of_size[3];
+  int peer;
 };
 struct CommPlan {
   struct Segment { int peer; long long offset, count; };     // doubles
@@ -70,7 +74,9 @@ struct FusedCtl {
 // what the step kernel needs (device memory, one per parity)
 struct FusedPack {
   const PlanBox* boxes;      // send boxes of the plan
-  double* const* dst;        // dst[b] = first double of box b in its receiver's buffer of this parity
+  double* const* dst;        // dst[b] = first double of box b in its receiver's buffer of this parity (or in the receiver's field)
+  const int* dstRow;         // registered fields: row / plane stride (doubles) of the receiver's stored box per send box;
+  const int* dstPlane;       //   NULL: box-linear layout of the exchange buffer
   unsigned* counter;
   int nBoxes, nranks;
   unsigned* peerFlag[64];    // &ctl(r).flags[myrank]
@@ -84,6 +90,12 @@ struct FusedState {
   FusedPack* dPack = nullptr;            // [2]
   double** dDst[2] = {nullptr, nullptr};
   std::vector<void*> opened;
+  FusedPack hostPack[2];                 // host copies of dPack[0..1]
+  // registered fields (dgb_fv_register_fields): peers store halo cells straight into these arrays, no receive buffer, no unpack
+  struct Direct { double* field = nullptr; FusedPack* dPack = nullptr; double** dDst = nullptr; int* dRow = nullptr; int* dPlane = nullptr; };
+  std::vector<Direct> direct;
+  int direct_slot(const double* p) const { for (std::size_t k = 0; k < direct.size(); ++k) if (direct[k].field == p) return int(k); return -1; }
+  void release_direct();
   unsigned epoch = 0;                    // fused steps done
   // sticky time-out word in mapped pinned host memory: the waiting kernels store 1 there when a peer did not deliver within
   // 20 s; the host reads it (no synchronisation needed) at the start of every later step and refuses to launch
@@ -104,6 +116,11 @@ int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStre
 // collective teardown of a fused state shared between processes: every rank closes its imported mappings, all ranks meet in
 // a barrier (all-reduce on the communicator), only then the exported blocks are freed
 int fused_teardown(FusedState& fs, dgb_comm* comm, cudaStream_t stream);
+// collective: every rank publishes IPC handles of its `nfields` arrays (all indexed like the plan's mapper, one double per
+// cell), maps the arrays of the ranks it sends to and prepares, per array, the destinations of its send boxes INSIDE the
+// receivers' arrays. Leaves fs.direct empty (DGB_OK) if any rank cannot (all ranks agree).
+int fused_register(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs,
+                   double* const* fields, int nfields);
 // a plan of its own for one user (not the per-grid cache): its buffers are then private to that user's stream
 std::shared_ptr<CommPlan> build_plan(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir, const int32_t* item_sizes, int narrays);
 // ncclCommGetAsyncError of the communicator (DGB_OK without a communicator): DGB_ENCCL once a peer has failed

@@ -64,6 +64,7 @@ struct FvArgs {
   const double* consts;  // device constants {0, boundary value} (upwind sources of faces without a stored neighbour)
   const FusedPack* pack; // fused exchange (3-D step kernels): pack into the receivers' buffers and signal; NULL = off
   unsigned packEpoch;    // value published in the receivers' flags when this launch has delivered everything
+  int packSignal;        // 1: the last CTA of this launch publishes the epoch (the last slab launch of a step); 0: pack and fence only
 };
 
 // ---- fused exchange, device side (dgb_comm.hh: FusedCtl / FusedPack) -------------------------------------------------
@@ -87,8 +88,10 @@ __device__ __forceinline__ void fv_fused_prepare(const FvArgs& a, const dgb_box&
     it.n = 0;
     if (lx < hx && ly < hy && lz < hz) {
       it.ex = hx-lx; it.ey = hy-ly; it.n = it.ex*it.ey*(hz-lz);
-      it.dsy = pb.size[0]; it.dsz = pb.size[0]*pb.size[1];
-      it.dst0 = P.dst[tid] + ((long long)(lz-pb.origin[2])*pb.size[1] + (ly-pb.origin[1]))*pb.size[0] + (lx-pb.origin[0]);
+      // destination layout: the box's place in the receiver's exchange buffer (box-linear), or - registered fields - the
+      // receiver's FIELD itself (row and plane strides of the receiver's stored box)
+      it.dsy = P.dstRow ? P.dstRow[tid] : pb.size[0]; it.dsz = P.dstPlane ? P.dstPlane[tid] : pb.size[0]*pb.size[1];
+      it.dst0 = P.dst[tid] + ((long long)(lz-pb.origin[2])*it.dsz + (long long)(ly-pb.origin[1])*it.dsy) + (lx-pb.origin[0]);
       it.src0 = ((long long)(lz-of.origin[2])*of.size[1] + (ly-of.origin[1]))*of.size[0] + (lx-of.origin[0]);
       items[tid] = it;
     } else items[tid].n = 0;
@@ -133,6 +136,7 @@ __device__ __forceinline__ int fv_tile_row(const FvArgs& a) {
 __device__ __forceinline__ void fv_fused_signal(const FvArgs& a) {
   const FusedPack& P = *a.pack;
   __threadfence_system();                            // the CTA's peer stores and its CFL atomic are performed
+  if (!a.packSignal) return;                         // an earlier slab launch of the step: the last launch signals for all
   const unsigned total = gridDim.x*gridDim.y*gridDim.z;
   if (atomicAdd(P.counter, 1u) == total-1) {
     atomicExch(P.counter, 0u);
@@ -607,8 +611,15 @@ __device__ __forceinline__ void fv_ring_loop(FvRingLane L, const FvRingSlow S, c
 // the loop is unrolled by two, so "even" and "odd" planes of the chunk always use the same slots and every phase-dependent
 // offset is a per-thread constant (one for even, one for odd planes): the hot loop has no phase arithmetic at all. Slot
 // positions are CTA-uniform byte offsets (uPrev/uCur/uNxt), per-thread positions are byte offsets inside a slot.
+// .ca, not .cg: measured with ncu (profiles/r02_fv_staging_notes.md) - 16-byte copies that bypass L1 are merged into 32-byte
+// sector requests per aligned LANE PAIR only, so rows whose pairs start at an odd multiple of 16 bytes fetched every
+// sector twice (L2 -> SM traffic 2.16 GB instead of 1.39 GB per 513^3 launch); through L1 the second request hits
 __device__ __forceinline__ void cp_async16_b(unsigned smem, const void* gmem) {
+#ifdef DGB_PAIR_CG
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(smem), "l"(gmem) : "memory");
+#else
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" :: "r"(smem), "l"(gmem) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async8_b(unsigned smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(smem), "l"(gmem) : "memory");
@@ -1023,6 +1034,7 @@ struct dgb_fv {
   int hostPath = 0;              // last dgb_fv_step_host: DGB_FV_HOST_*
   std::shared_ptr<CommPlan> plan;
   double* dStage[2] = {nullptr, nullptr};     // device staging for the host-buffer entry point
+  double* dHostVote = nullptr;                // one device word: do all ranks take the pipelined host path?
   size_t stageBytes = 0;
   cudaStream_t sIn = nullptr, sOut = nullptr;  // copy streams of the pipelined host-buffer step
   // exchange shell / bulk split of the interior box (3-D, ranks with overlap cells): the shell slabs are the interior
@@ -1275,6 +1287,7 @@ static int fv_free(dgb_fv* fv, bool collective) {
   if (fv->dSlots) cudaFree(fv->dSlots);
   if (fv->dTables) cudaFree(fv->dTables);
   for (int i = 0; i < 2; ++i) if (fv->dStage[i]) cudaFree(fv->dStage[i]);
+  if (fv->dHostVote) cudaFree(fv->dHostVote);
   for (cudaEvent_t e : fv->evIn) cudaEventDestroy(e);
   for (cudaEvent_t e : fv->evK) cudaEventDestroy(e);
   if (fv->evStart) cudaEventDestroy(fv->evStart);
@@ -1305,6 +1318,20 @@ int dgb_fv_init_field(dgb_fv* fv, double* d_c, void* stream) {
   return DGB_OK;
 }
 
+// collective, once per object: try to set up the fused peer-memory exchange (see dgb_fv_step)
+static int ensure_fused(dgb_fv* fv, cudaStream_t stream) {
+  if (fv->fusedTried) return DGB_OK;
+  fv->fusedTried = true;
+  const bool exchanges = fv->plan->nSendBoxes || fv->plan->nRecvBoxes;
+  const char* e = getenv("DGB_FV_FUSED");
+  if (!(e && atoi(e) == 0) && fv->view.dim == 3 && (exchanges || fv->view.nranks > 1) && (fv->view.nranks == 1 || fv->comm)) {
+    const dgb_box& in = fv->view.comp[0].box[DGB_BOX_INTERIOR];
+    const bool nonEmpty = in.size[0] > 0 && in.size[1] > 0 && in.size[2] > 0;    // every rank must launch a step kernel
+    if (int rc = fused_setup(*fv->plan, fv->view.rank, fv->view.nranks, fv->comm, stream, fv->fused, nonEmpty)) return rc;
+  }
+  return DGB_OK;
+}
+
 static const char* const kTimeoutMsg = "fused exchange: a rank did not deliver its step within 20 s (ranks out of step, or a peer has died); "
                                        "this dgb_fv object accepts no further steps";
 
@@ -1323,35 +1350,34 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
   // waits for all ranks' flags (which also carry the CFL maxima: no all-reduce), then the overlap cells are scattered.
   // One stream, no NCCL call in the steady state. Collective set-up on the first step; DGB_FV_FUSED=0 or ranks without
   // peer mapping keep the NCCL forms below.
-  if (!fv->fusedTried) {
-    fv->fusedTried = true;
-    const char* e = getenv("DGB_FV_FUSED");
-    if (!(e && atoi(e) == 0) && fv->view.dim == 3 && (exchanges || fv->view.nranks > 1) && (fv->view.nranks == 1 || fv->comm))
-    {
-      const bool nonEmpty = a.region.size[0] > 0 && a.region.size[1] > 0 && a.region.size[2] > 0;    // every rank must launch a step kernel
-      if (int rc = fused_setup(*fv->plan, fv->view.rank, fv->view.nranks, fv->comm, stream, fv->fused, nonEmpty)) return rc;
-    }
-  }
+  if (int rc = ensure_fused(fv, stream)) return rc;
   if (fv->fused.on) {
     FusedState& fs = fv->fused;
     const int parity = int(fs.epoch & 1u);
-    a.pack = fs.dPack + parity; a.packEpoch = fs.epoch + 1u;
+    // registered output array (dgb_fv_register_fields): the kernel stores the halo cells straight into the receivers' arrays;
+    // nothing to unpack, only the one-CTA wait for all ranks' flags (+ CFL reduction) remains
+    const int slot = fs.direct_slot(d_c_out);
+    a.pack = (slot >= 0 ? fs.direct[slot].dPack : fs.dPack) + parity; a.packEpoch = fs.epoch + 1u; a.packSignal = 1;
     if (int rc = launch_step<false>(fv, a, stream)) return rc;
-    const int32_t items[1] = {1};
-    double* arrays[1] = { d_c_out };
-    const long long before = fv->plan->launches;
-    // the wait for all ranks' flags (+ CFL reduction) rides on the first unpack launch; ranks that receive nothing (no
-    // overlap cells) still need it for the CFL value
-    const HaloWait hw{fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4), fs.dTimeout};
-    if (fv->plan->nRecvBoxes == 0) { k_fv_wait<<<1, 64, 0, stream>>>(fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4), fs.dTimeout); ++fv->launches; }
-    if (int rc = plan_unpack_from(*fv->plan, fs.recv[parity], DGB_OP_SET, arrays, items, 1, stream, &hw)) return rc;
-    fv->launches += fv->plan->launches - before;
+    if (slot >= 0 || fv->plan->nRecvBoxes == 0) {
+      k_fv_wait<<<1, 64, 0, stream>>>(fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4), fs.dTimeout); ++fv->launches;
+    }
+    if (slot < 0) {
+      const int32_t items[1] = {1};
+      double* arrays[1] = { d_c_out };
+      const long long before = fv->plan->launches;
+      // the wait for all ranks' flags (+ CFL reduction) rides on the first unpack launch
+      const HaloWait hw{fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4), fs.dTimeout};
+      if (int rc = plan_unpack_from(*fv->plan, fs.recv[parity], DGB_OP_SET, arrays, items, 1, stream, &hw)) return rc;
+      fv->launches += fv->plan->launches - before;
+    }
+    DGB_CUDA(cudaGetLastError());
     int64_t bytes = 0;
     for (auto& sg : fv->plan->sendSeg) if (sg.peer != fv->view.rank) bytes += sg.count*8;
     fv->grid->lastBytesSent = bytes;
     ++fs.epoch;
     fv->step = n+1;
-    fv->exchangeMode = DGB_FV_EXCHANGE_FUSED;
+    fv->exchangeMode = slot >= 0 ? DGB_FV_EXCHANGE_DIRECT : DGB_FV_EXCHANGE_FUSED;
     return DGB_OK;
   }
   if (fv->split && exchanges) {
@@ -1414,6 +1440,16 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
   return DGB_OK;
 }
 
+int dgb_fv_register_fields(dgb_fv* fv, double* const* d_fields, int nfields, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (fv->fused.timed_out()) return fail(DGB_ENCCL, kTimeoutMsg);
+  if (int rc = ensure_fused(fv, stream)) return rc;
+  if (!fv->fused.on) return DGB_OK;                            // NCCL forms: nothing to register, the steps work as before
+  DGB_CUDA(cudaStreamSynchronize(stream));
+  return fused_register(*fv->plan, fv->view.rank, fv->view.nranks, fv->comm, stream, fv->fused, d_fields, nfields);
+}
+int dgb_fv_registered_fields(const dgb_fv* fv, int* n) { *n = int(fv->fused.direct.size()); return DGB_OK; }
+
 int dgb_fv_bootstrap_local(dgb_fv* fv, double** d_pending_max, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DGB_CUDA(cudaMemsetAsync(fv->dSlots, 0, 5*sizeof(double), stream));
@@ -1470,6 +1506,8 @@ int dgb_fv_last_dt(dgb_fv* fv, double* dt_host, void* stream) {
 
 int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* dt_host, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (fv->fused.timed_out()) return fail(DGB_ENCCL, kTimeoutMsg);
+  if (fv->comm) if (int rc = nccl_check_async(fv->comm)) return rc;
   int64_t n = 0; dgb_view_size(&fv->view, 0, &n);
   const size_t bytes = size_t(n)*sizeof(double);
   if (fv->stageBytes < bytes) {
@@ -1481,12 +1519,34 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
   const dgb_view& v = fv->view;
   const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
   const dgb_box& in = v.comp[0].box[DGB_BOX_INTERIOR];
-  // Pipelined form (one rank, no overlap cells to refresh, 3-D): the field crosses PCIe in z-slabs; slab i is updated
-  // as soon as slab i+1 (whose first plane it reads) has arrived, and its result leaves while later slabs are still
-  // coming in - the two copy directions run concurrently on their own streams around the compute stream.
+  // Pipelined form (3-D): the field crosses PCIe in z-slabs of the STORED box; the interior cells of slab i are updated as soon
+  // as slab i+1 (whose first plane they read) has arrived, and slab i of the result leaves while later slabs are still coming
+  // in - the two copy directions run concurrently on their own streams around the compute stream. Ranks that exchange
+  // overlap cells (several ranks, or periodic directions) use the fused exchange: every slab launch stores its share of
+  // the send boxes into the receivers' buffers (peer memory) as it goes, the LAST launch raises the flag, and after the
+  // last download the unpack kernel waits for all ranks' flags and scatters the received cells STRAIGHT INTO THE HOST
+  // RESULT (mapped pinned memory) - the stale overlap cells the slab downloads carried are overwritten in place.
   static const int nslab = [] { const char* e = getenv("DGB_FV_HOST_SLABS"); const int v = e ? atoi(e) : 32; return v >= 2 && v <= 256 ? v : 32; }();
-  const bool pipelined = v.dim == 3 && v.nranks == 1 && !fv->plan->nSendBoxes && !fv->plan->nRecvBoxes
-                         && of.size[2] == in.size[2] && of.size[2] >= 4*nslab && !getenv("DGB_FV_HOST_SERIAL");
+  const bool exchanges = fv->plan->nSendBoxes || fv->plan->nRecvBoxes;
+  bool pipelined = v.dim == 3 && of.size[2] >= 4*nslab && in.size[0] > 0 && in.size[1] > 0 && in.size[2] > 0 && !getenv("DGB_FV_HOST_SERIAL");
+  double* d_host_out = nullptr;                        // device alias of h_c_out (exchanging ranks unpack into it)
+  if (pipelined && (exchanges || v.nranks > 1)) {
+    if (int rc = ensure_fused(fv, stream)) return rc;
+    cudaPointerAttributes attr;
+    const bool mapped = cudaPointerGetAttributes(&attr, h_c_out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer;
+    if (!mapped) cudaGetLastError();
+    // every rank must take the same path (the fused exchange is collective): a rank with pageable buffers vetoes it for all
+    double ok = (fv->fused.on && mapped) ? 1.0 : 0.0;
+    if (v.nranks > 1) {
+      if (!fv->dHostVote) DGB_CUDA(cudaMalloc(&fv->dHostVote, sizeof(double)));
+      DGB_CUDA(cudaMemcpyAsync(fv->dHostVote, &ok, sizeof(double), cudaMemcpyHostToDevice, stream));
+      if (int rc = nccl_allreduce(fv->dHostVote, 0, fv->comm, stream)) return rc;
+      DGB_CUDA(cudaMemcpyAsync(&ok, fv->dHostVote, sizeof(double), cudaMemcpyDeviceToHost, stream));
+      DGB_CUDA(cudaStreamSynchronize(stream));
+    }
+    pipelined = ok > 0.5;
+    if (pipelined) d_host_out = static_cast<double*>(attr.devicePointer);
+  }
   fv->hostPath = pipelined ? DGB_FV_HOST_PIPELINED : DGB_FV_HOST_SERIAL;
   if (!pipelined) {
     DGB_CUDA(cudaMemcpyAsync(fv->dStage[0], h_c_in, bytes, cudaMemcpyHostToDevice, stream));
@@ -1514,31 +1574,58 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
   DGB_CUDA(cudaStreamWaitEvent(fv->sOut, fv->evStart, 0));
   const size_t plane = size_t(of.size[0])*of.size[1];
   const int nz = of.size[2];
-  auto zbegin = [&](int i) { return int((long long)nz*i/nslab); };
+  auto zbegin = [&](int i) { return int((long long)nz*i/nslab); };            // first stored plane of slab i
   for (int i = 0; i < nslab; ++i) {
     const size_t o = plane*zbegin(i), cnt = plane*(zbegin(i+1)-zbegin(i));
     DGB_CUDA(cudaMemcpyAsync(fv->dStage[0] + o, h_c_in + o, cnt*sizeof(double), cudaMemcpyHostToDevice, fv->sIn));
     DGB_CUDA(cudaEventRecord(fv->evIn[i], fv->sIn));
   }
   const long long sn = fv->step;
+  const bool fused = fv->fused.on;
+  FusedState& fs = fv->fused;
+  const int parity = int(fs.epoch & 1u);
+  // interior planes of slab i (stored plane p holds the cells with z = of.origin[2] + p)
+  auto zlo = [&](int i) { return std::max(of.origin[2] + zbegin(i), in.origin[2]); };
+  auto zhi = [&](int i) { return std::min(of.origin[2] + zbegin(i+1), in.origin[2] + in.size[2]); };
+  int lastLaunch = -1;
+  for (int i = 0; i < nslab; ++i) if (zhi(i) > zlo(i)) lastLaunch = i;
   for (int i = 0; i < nslab; ++i) {
-    DGB_CUDA(cudaStreamWaitEvent(stream, fv->evIn[std::min(i+1, nslab-1)], 0));
-    FvArgs a = base_args(fv);
-    a.region.origin[2] = in.origin[2] + zbegin(i); a.region.size[2] = zbegin(i+1)-zbegin(i);
-    a.c = fv->dStage[0]; a.cnew = fv->dStage[1];
-    slot_args(fv, sn, a);
-    if (int rc = launch_step<false>(fv, a, stream)) return rc;
+    if (zhi(i) > zlo(i)) {
+      DGB_CUDA(cudaStreamWaitEvent(stream, fv->evIn[std::min(i+1, nslab-1)], 0));
+      FvArgs a = base_args(fv);
+      a.region.origin[2] = zlo(i); a.region.size[2] = zhi(i)-zlo(i);
+      a.c = fv->dStage[0]; a.cnew = fv->dStage[1];
+      slot_args(fv, sn, a);
+      if (fused) { a.pack = fs.dPack + parity; a.packEpoch = fs.epoch + 1u; a.packSignal = (i == lastLaunch) ? 1 : 0; }
+      if (int rc = launch_step<false>(fv, a, stream)) return rc;
+    }
     DGB_CUDA(cudaEventRecord(fv->evK[i], stream));
     DGB_CUDA(cudaStreamWaitEvent(fv->sOut, fv->evK[i], 0));
     const size_t o = plane*zbegin(i), cnt = plane*(zbegin(i+1)-zbegin(i));
     DGB_CUDA(cudaMemcpyAsync(h_c_out + o, fv->dStage[1] + o, cnt*sizeof(double), cudaMemcpyDeviceToHost, fv->sOut));
   }
-  if (int rc = nccl_allreduce(fv->dSlots + ((sn+2) % 4), 1, fv->comm, stream)) return rc;
+  if (fused) {
+    // after the last download: wait for every rank's flag (CTA 0 also reduces the CFL maxima into the slot of step n+2), then
+    // scatter the received overlap cells into the host result
+    const int32_t items[1] = {1};
+    double* arrays[1] = { d_host_out };
+    const long long before = fv->plan->launches;
+    const HaloWait hw{fs.ctl, v.nranks, fs.epoch + 1u, parity, fv->dSlots + ((sn+2) % 4), fs.dTimeout};
+    if (fv->plan->nRecvBoxes == 0) { k_fv_wait<<<1, 64, 0, fv->sOut>>>(fs.ctl, v.nranks, fs.epoch + 1u, parity, fv->dSlots + ((sn+2) % 4), fs.dTimeout); ++fv->launches; }
+    if (int rc = plan_unpack_from(*fv->plan, fs.recv[parity], DGB_OP_SET, arrays, items, 1, fv->sOut, &hw)) return rc;
+    fv->launches += fv->plan->launches - before;
+    int64_t sent = 0;
+    for (auto& sg : fv->plan->sendSeg) if (sg.peer != v.rank) sent += sg.count*8;
+    fv->grid->lastBytesSent = sent;
+    ++fs.epoch;
+    fv->exchangeMode = DGB_FV_EXCHANGE_FUSED;
+  } else if (int rc = nccl_allreduce(fv->dSlots + ((sn+2) % 4), 1, fv->comm, stream)) return rc;
   fv->step = sn+1;
-  if (dt_host) DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 4, sizeof(double), cudaMemcpyDeviceToHost, stream));
   DGB_CUDA(cudaEventRecord(fv->evEnd, fv->sOut));
   DGB_CUDA(cudaStreamWaitEvent(stream, fv->evEnd, 0));
+  if (dt_host) DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 4, sizeof(double), cudaMemcpyDeviceToHost, stream));
   DGB_CUDA(cudaStreamSynchronize(stream));
+  if (fv->fused.timed_out()) return fail(DGB_ENCCL, kTimeoutMsg);
   return DGB_OK;
 }
 

@@ -529,6 +529,17 @@ class FiniteVolume:
     def step(self, c_in, c_out):
         check(lib.dgb_fv_step(self.h, _ptr(c_in), _ptr(c_out), _stream()))
 
+    def register_fields(self, *fields):
+        """dgb_fv_register_fields (collective): the arrays the time loop alternates between; steps that write one of them let
+        the peers store halo cells straight into it (no receive buffer, no unpack). Returns the number of registered arrays
+        (0: declined on some rank - the steps then keep the buffered form)."""
+        self._registered = list(fields)                 # keep them alive
+        ptrs = (C.c_void_p * len(fields))(*[f.data_ptr() for f in fields])
+        check(lib.dgb_fv_register_fields(self.h, ptrs, len(fields), _stream()))
+        n = C.c_int(0)
+        check(lib.dgb_fv_registered_fields(self.h, C.byref(n)))
+        return n.value
+
     def bootstrap_local(self):
         p = C.c_void_p()
         check(lib.dgb_fv_bootstrap_local(self.h, C.byref(p), _stream()))
@@ -569,7 +580,8 @@ class FiniteVolume:
         return n.value
 
     def exchange_mode(self):
-        """how the last step refreshed the overlap cells: 'none', 'serial', 'overlapped' (NCCL) or 'fused' (peer stores)"""
+        """how the last step refreshed the overlap cells: 'none', 'serial', 'overlapped' (NCCL), 'fused' (peer stores into the
+        receivers' buffers) or 'direct' (peer stores into the receivers' registered arrays)"""
         m = C.c_int(0)
         check(lib.dgb_fv_exchange_mode(self.h, C.byref(m)))
-        return ("none", "serial", "overlapped", "fused")[m.value]
+        return ("none", "serial", "overlapped", "fused", "direct")[m.value]

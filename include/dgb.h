@@ -239,6 +239,16 @@ int dgb_fv_abandon(dgb_fv* fv);
 int dgb_fv_init_field(dgb_fv* fv, double* d_c, void* stream);          /* c0 at the cell centres, all stored cells */
 /* one step: c_out = c_in + dt*update(c_in) on interior cells, halo of c_out refreshed, dt = 0.99*min(1/sum_out) */
 int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream);
+/* Registration of the arrays a time loop alternates between (collective over the ranks of the grid; the analogue of
+ * MPI_Win_create / ncclCommRegister): every rank passes its `nfields` (<= 4) device arrays, indexed by the element mapper,
+ * in the same order. Afterwards a dgb_fv_step whose d_c_out is one of them lets the peers' step kernels store the halo
+ * cells STRAIGHT INTO that array over NVLink (CUDA IPC mapping): no receive buffer, no unpack launch. Contract: all ranks
+ * pass the array of the same registration slot to the same step; d_c_in != d_c_out; while an array is registered, its
+ * overlap cells may be overwritten by the peers as soon as this rank has entered the step that writes it. If the arrays
+ * cannot be mapped on every rank (not cudaMalloc memory, no peer access) nothing is registered on any rank and the steps
+ * keep the receive-buffer form - same results. The arrays must stay allocated until dgb_fv_destroy. */
+int dgb_fv_register_fields(dgb_fv* fv, double* const* d_fields, int nfields, void* stream);
+int dgb_fv_registered_fields(const dgb_fv* fv, int* n);                /* 0 = the registration was declined */
 /* the kernel of dgb_fv_step alone: no halo exchange, no reduction across ranks. *d_pending_max then points at the
  * device double holding this rank's max outflow sum, which the caller must max-reduce over ranks before the next
  * step (dgb_fv_step does both itself). For transports other than NCCL and single-device rank emulation. */
@@ -247,7 +257,10 @@ int dgb_fv_bootstrap_local(dgb_fv* fv, double** d_pending_max, void* stream);
 int dgb_fv_last_dt(dgb_fv* fv, double* dt_host, void* stream);         /* synchronises the stream */
 /* optional: also materialise the update array (tests) */
 int dgb_fv_update(dgb_fv* fv, const double* d_c_in, double* d_update, void* stream);
-/* the same step on HOST buffers (pinned or pageable): H2D copy of c, step, D2H copy of the result */
+/* the same step on HOST buffers: H2D copy of c, step, D2H copy of the result (incl. refreshed overlap cells). 3-D grids
+ * with pinned buffers are pipelined in z-slabs (upload / kernel / download of different slabs run concurrently, the halo
+ * exchange rides on the slab kernels and is unpacked straight into h_c_out); pageable buffers take the serial form.
+ * Collective on a multi-rank grid, synchronises the stream. */
 int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* dt_host, void* stream);
 /* how the last dgb_fv_step_host moved the field: */
 #define DGB_FV_HOST_NONE 0
@@ -265,6 +278,7 @@ int dgb_fv_kernel_info(const dgb_fv* fv, int32_t* info8);
 #define DGB_FV_EXCHANGE_SERIAL 1    /* step kernel, then communicate() (2-D, or no room for a shell/bulk split) */
 #define DGB_FV_EXCHANGE_OVERLAPPED 2 /* shell kernel + NCCL send/recv on a second stream, concurrent with the bulk kernel */
 #define DGB_FV_EXCHANGE_FUSED 3     /* one step kernel stores into the receivers' buffers over peer-mapped memory and signals */
+#define DGB_FV_EXCHANGE_DIRECT 4    /* as FUSED, and the stores go straight into the receivers' registered arrays: no unpack */
 /* Limits of the fused form (beyond them dgb_fv_step keeps the NCCL forms, same results): at most 64 ranks (control block),
  * at most 32 send boxes per rank (26 in 3-D with overlap; more only with several codims, which the FV exchange does not
  * have). dgb_communicate takes at most 8 arrays per call. A peer that does not deliver its step within 20 s makes the

@@ -460,6 +460,91 @@ def test_fv_fused_exchange_single_rank(cfg, problem, params, mode, monkeypatch):
     w.close()
 
 
+@pytest.mark.parametrize("mode", ["exact", "separable"])
+@pytest.mark.parametrize("N,periodic,overlap", [((40, 23, 37), 7, 1), ((131, 9, 20), 5, 1), ((12, 30, 16), 2, 2), ((257, 12, 18), 1, 1)])
+def test_fv_registered_fields_peers_store_into_the_arrays(N, periodic, overlap, mode):
+    """dgb_fv_register_fields: the step kernel stores the halo cells straight into the receiver's registered ARRAY (here the rank
+    itself through the periodic wrap) - no receive buffer, no unpack launch - and must give the same bits as the buffered
+    fused form, and the oracle's result"""
+    import torch
+    import dune_grid_b200 as dg
+    cfg = make_cfg(dim=3, N=N, periodic=periodic, overlap=overlap, upper=(1.0, 0.6, 0.9))
+    params = [0.8, -0.5, 0.25, 0.1, 0.5, 0.3, 0.45, 0.1, 0.45]
+    o = best_oracle()
+    w = oracle_world(o, cfg, 1)
+    ref = [w.fv_init(0, 0, 0, params)]
+    res = {}
+    for registered in (True, False):
+        g = product_grid(cfg, 0, 1)
+        fv = dg.FiniteVolume(g, 0, 0, params, mode)
+        c = fv.initial()
+        cn = torch.empty_like(c)
+        third = torch.empty_like(c)
+        if registered:
+            assert fv.register_fields(c, cn) == 2
+        l0 = fv.launch_count()
+        for _ in range(4):
+            fv.step(c, cn)
+            c, cn = cn, c
+        assert fv.exchange_mode() == ("direct" if registered else "fused")
+        launches = fv.launch_count() - l0
+        if registered:
+            assert launches <= 4 * 2 + 1                         # step kernel + one-CTA wait (+ bootstrap), no unpack launches
+            fv.step(c, third)                                    # an unregistered output array: the buffered form, same object
+            assert fv.exchange_mode() == "fused"
+            res["mixed"] = np_(third)
+        else:
+            fv.step(c, cn)
+            res["buffered5"] = np_(cn)
+        res[registered] = np_(c)
+        fv.close()
+    assert np.array_equal(res[True], res[False])
+    assert np.array_equal(res["mixed"], res["buffered5"])
+    for _ in range(4):
+        w.fv_step(0, 0, params, ref)
+    if mode == "exact":
+        assert np.array_equal(res[True], ref[0])
+    else:
+        assert np.abs(res[True] - ref[0]).max() <= 1e-13 * np.abs(ref[0]).max()            # tolerance: 1e-13 relative
+    w.close()
+
+
+@pytest.mark.parametrize("N,periodic", [((20, 12, 126), 7), ((36, 10, 128), 4), ((24, 16, 140), 0)])
+def test_fv_step_host_pipelined(N, periodic):
+    """dgb_fv_step_host on pinned buffers: z-slab pipeline (upload / kernel / download on three streams); with periodic
+    directions the fused exchange rides on the slab launches and the received overlap cells are unpacked straight into the
+    host result. Bit-equal to the oracle (exact mode), all stored cells including the refreshed overlap; pageable buffers
+    take the serial path and give the same bits."""
+    import torch
+    import dune_grid_b200 as dg
+    cfg = make_cfg(dim=3, N=N, periodic=periodic, upper=(1.0, 0.6, 4.0))
+    params = [0.8, -0.5, 1.25, 0.1, 0.5, 0.3, 2.0, 0.3, 1.45]
+    o = best_oracle()
+    w = oracle_world(o, cfg, 1)
+    ref = [w.fv_init(0, 0, 0, params)]
+    g = product_grid(cfg, 0, 1)
+    fv = dg.FiniteVolume(g, 0, 0, params, "exact")
+    h_in = torch.from_numpy(ref[0].copy()).pin_memory()
+    h_out = torch.full_like(h_in, float("nan")).pin_memory()
+    for _ in range(3):
+        dt = fv.step_host(h_in, h_out)
+        dt_ref = w.fv_step(0, 0, params, ref)
+        assert fv.host_path() == "pipelined"
+        assert dt == dt_ref
+        assert np.array_equal(h_out.numpy(), ref[0])
+        h_in, h_out = h_out, h_in
+    if periodic:
+        assert fv.exchange_mode() == "fused"
+    p_in = torch.from_numpy(ref[0].copy())                       # pageable
+    p_out = torch.empty_like(p_in)
+    fv.step_host(p_in, p_out)
+    w.fv_step(0, 0, params, ref)
+    assert fv.host_path() == ("serial" if periodic else "pipelined")
+    assert np.array_equal(p_out.numpy(), ref[0])
+    fv.close()
+    w.close()
+
+
 def test_fv_restart_from_backup(tmp_path):
     """restart of an FV run (SURVEY §8f row 3): grid through BackupRestoreFacility text, field through the checkpoint file;
     the restarted run must continue bit-identically, and the checkpoint must refuse a different grid"""
