@@ -1014,7 +1014,7 @@ struct dgb_fv {
   int level = 0, mode = 0;
   int zchunk = 0;                // planes marched by one CTA of the 3-D kernel; 0 = auto (DGB_FV_ZCHUNK overrides)
   int variant = -1;              // tuning variant of the 3-D kernel; -1 = automatic (DGB_FV_VARIANT overrides)
-  int staging = 2;               // staging of the ring kernel: 2 phase-aware pairs (default), 1 aligned pairs, 0 8 bytes per cell (DGB_FV_STAGING=pair|a16|8)
+  int staging = 3;               // staging of the ring kernel: 3 automatic (default), 2 phase-aware pairs, 1 aligned pairs, 0 8 bytes per cell (DGB_FV_STAGING=auto|pair|a16|8)
   std::unique_ptr<dgb::FvZTable> ztab;   // reciprocal z widths for the kernel parameter space (ring kernel)
   bool zparam = false;
   dgb_view view;
@@ -1074,9 +1074,13 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     // staging of the ring kernel: 2 = 16-byte pairs with per-row phases (default: works for every alignment, row length and
     // region offset), 1 = 16-byte pairs of rows that are all 16-byte aligned (round-1 form, 128x4 tile only), 0 = 8 bytes per cell
     const dgb_box& ofb = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+    // measured (profiles/r02_fv_staging.jsonl): aligned pairs win where every row is 16-byte aligned (512^3 single rank: 0.350 ms vs
+    // 0.360 phase-aware pairs vs 0.360 8-byte), phase-aware pairs win on the odd rank boxes of a partitioned grid (513^3: 0.382 vs 0.391)
+    const bool a16ok = variant == 3 && fv->zparam && (reinterpret_cast<uintptr_t>(a.c) & 15u) == 0 && ofb.size[0] % 2 == 0
+                       && (a.region.origin[0]-ofb.origin[0]) % 2 == 0 && a.region.size[0] % 2 == 0;
     int stg = fv->staging;
-    if (stg == 1 && !(variant == 3 && fv->zparam && (reinterpret_cast<uintptr_t>(a.c) & 15u) == 0 && ofb.size[0] % 2 == 0
-                      && (a.region.origin[0]-ofb.origin[0]) % 2 == 0 && a.region.size[0] % 2 == 0)) stg = 0;
+    if (stg == 3) stg = a16ok ? 1 : 2;                  // automatic
+    if (stg == 1 && !a16ok) stg = 0;
     if (stg == 0 && !(variant == 0 || variant == 3)) stg = 2;
     const int zc = fv->zchunk > 0 ? fv->zchunk : auto_zchunk(a.region.size, wide ? 128 : 32, wide ? 4 : 8);
     const bool exact = fv->mode == DGB_FV_EXACT;
@@ -1222,7 +1226,7 @@ int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host
     fv->grid = g; fv->comm = comm; fv->level = level; fv->mode = mode;
     if (const char* e = getenv("DGB_FV_ZCHUNK")) { int z = atoi(e); if (z > 0) fv->zchunk = z; }
     if (const char* e = getenv("DGB_FV_VARIANT")) fv->variant = atoi(e);
-    if (const char* e = getenv("DGB_FV_STAGING")) fv->staging = !strcmp(e, "8") ? 0 : !strcmp(e, "a16") ? 1 : 2;
+    if (const char* e = getenv("DGB_FV_STAGING")) fv->staging = !strcmp(e, "8") ? 0 : !strcmp(e, "a16") ? 1 : !strcmp(e, "pair") ? 2 : 3;
     if (int rc = make_view(g, level, &fv->view)) return rc;
     if (g->me.nranks > 1 && !comm) throw ArgError("a dgb_comm is required on a multi-rank grid");
     const uint32_t block[4] = {1,0,0,0};

@@ -62,6 +62,24 @@ namespace orc {
     return std::abs(v0*A[2][0] + v1*A[2][1] + v2*A[2][2]);
   }
 
+  // FieldMatrixHelper::sqrtDetAAT<m,n> for the Jacobians of sub-entities (m < n): explicit 2x3 formula; 1xn through the general
+  // path (A A^T is 1x1, its Cholesky factor is the square root); 0xn (vertices): 1; square: as above
+  template<int m, int n> inline double sqrt_det_aat_rect(const double (*A)[n]) {
+    if constexpr (m == n) return sqrt_det_aat<n>(A);
+    else if constexpr (m == 0) return 1.0;
+    else if constexpr (m == 2 && n == 3) {
+      const double v0 = A[0][0]*A[1][1] - A[0][1]*A[1][0];
+      const double v1 = A[0][0]*A[1][2] - A[1][0]*A[0][2];
+      const double v2 = A[0][1]*A[1][2] - A[0][2]*A[1][1];
+      return std::sqrt(v0*v0 + v1*v1 + v2*v2);
+    } else {
+      static_assert(m == 1, "only faces of 2-D / 3-D cubes");
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s += A[0][k]*A[0][k];
+      return std::sqrt(s);
+    }
+  }
+
   // FieldMatrixHelper::rightInvA: ret (n x m) with A*ret = I; returns |det|.
   // 2x2: closed form. Otherwise: L L^T = A A^T (AAT_L + cholesky_L), (A A^T)^-1 = L^-T L^-1 (invL + LTL),
   // ret = A^T (A A^T)^-1.

@@ -95,6 +95,16 @@ int64_t orc_geometry_eval(void* w, int rank, int level, int pitype, int nqp, con
 /* a9: GeometryGrid over the Yasp host level: corners n×2^dim×dim, then as above with jt too */
 int64_t orc_geogrid_eval(void* w, int rank, int level, int pitype, int deformation, const double* params,
                          int nqp, const double* qp, double* corners, double* global, double* jt, double* jit, double* detJ);
+/* a9, second half: GeoGrid::Intersection (geometrygrid/intersection.hh:103-172, cornerstorage.hh:122-165) for all cells of the
+ * partition and their 2*dim faces in reference order. corners: n x 2dim x 2^(dim-1) x dim = insideGeo.global(hostLocalGeo.corner(i));
+ * center, volume: n x 2dim (x dim) of the face geometry (MultiLinearGeometry<dim-1,dim> over those corners); at the nqp face-local
+ * points qp (nqp x (dim-1)): integrationOuterNormal = J^-T(x) n_ref |det J(x)|, outerNormal = J^-T(x) n_ref, unitOuterNormal:
+ * n x 2dim x nqp x dim; centerUnitOuterNormal: n x 2dim x dim. The reference headers for these rules are compiled into the
+ * reference library; the multilinear arithmetic under them is the restatement of oracle/common/multilinear.hh (unpinned). */
+int64_t orc_geogrid_intersections(void* w, int rank, int level, int pitype, int deformation, const double* params,
+                                  int nqp, const double* qp_face, double* corners, double* center, double* volume,
+                                  double* integrationOuterNormal, double* outerNormal, double* unitOuterNormal,
+                                  double* centerUnitOuterNormal);
 /* a10: communicate on all ranks at once. arrays[rank*narrays + a] is indexed by the mapper (block) with item_sizes[a]
  * doubles per mapper entry. op 0 = set (local = remote), 1 = add (local = local + remote). Returns doubles sent in total. */
 int64_t orc_communicate(void* w, int level, const uint32_t* block, int iftype, int dir, int op,

@@ -15,6 +15,10 @@
 #include <dune/grid/yaspgrid.hh>
 #include <dune/grid/common/mcmgmapper.hh>
 #include <dune/grid/utility/globalindexset.hh>
+// GeometryGrid: the reference's own corner and intersection rules (compiled unmodified; they pull in
+// geometrygrid/{declaration,coordfunction,coordfunctioncaller,hostcorners}.hh)
+#include <dune/grid/geometrygrid/cornerstorage.hh>
+#include <dune/grid/geometrygrid/intersection.hh>
 
 #include <chrono>
 #include <cstring>
@@ -28,6 +32,98 @@
 #include "../oracle_api.h"
 #include "../common/fv_problem.hh"
 #include "../common/multilinear.hh"
+
+
+// ---- GeometryGrid<YaspGrid<dim>, AnalyticalCoordFunction> as far as the path needs it ----------------------------------
+// The reference's GeoGrid::CoordVector (corners = F(hostGeometry.corner(i)) through HostCorners + CoordFunctionCaller,
+// geometrygrid/cornerstorage.hh:54-60), GeoGrid::IntersectionCoordVector (face corners = insideGeo.global(hostLocalGeo.corner(i)),
+// :148-154) and GeoGrid::Intersection (normals, geometrygrid/intersection.hh:103-172) are instantiated UNMODIFIED on a
+// small traits class; only the geometry implementation they are given is ours: the multilinear map restated in
+// oracle/common/multilinear.hh (dune-geometry's MultiLinearGeometry is not vendored - unpinned arithmetic, pinned rules).
+namespace orcgeo {
+  template<int dim>
+  struct CoordFunction : public Dune::AnalyticalCoordFunction<double, dim, dim, CoordFunction<dim>> {
+    int def = 0; const double* params = nullptr;
+    CoordFunction(int d, const double* p) : def(d), params(p) {}
+    void evaluate(const Dune::FieldVector<double,dim>& x, Dune::FieldVector<double,dim>& y) const { orc::deformation(def, params, dim, x.data(), y.data()); }
+  };
+
+  template<int mydim, int cdim> struct JacInvT {          // MultiLinearGeometry::JacobianInverseTransposed: cdim x mydim + detInv()
+    double m[cdim][mydim]; double detInv_;
+    template<class X, class Y> void mv(const X& x, Y& y) const { for (int i = 0; i < cdim; ++i) { y[i] = 0; for (int j = 0; j < mydim; ++j) y[i] += m[i][j]*x[j]; } }
+    double detInv() const { return detInv_; }
+    double det() const { return 1.0/detInv_; }
+    const double* operator[](int i) const { return m[i]; }
+  };
+
+  template<int mydim, int cdim, class Grid>
+  class MLGeometry {
+  public:
+    typedef Dune::FieldVector<double,mydim> LocalCoordinate;
+    typedef Dune::FieldVector<double,cdim> GlobalCoordinate;
+    typedef JacInvT<mydim,cdim> JacobianInverseTransposed;
+    static const int ncorners = 1 << mydim;
+    MLGeometry() : grid_(nullptr), valid_(false) {}
+    explicit MLGeometry(const Grid& g) : grid_(&g), valid_(false) {}
+    template<class CoordVector>
+    MLGeometry(const Grid& g, const Dune::GeometryType&, const CoordVector& coords) : grid_(&g), valid_(true) {
+      std::array<GlobalCoordinate, ncorners> c;
+      coords.calculate(c);                               // the reference's corner rule fills the corners
+      for (int k = 0; k < ncorners; ++k) for (int i = 0; i < cdim; ++i) c_[k][i] = c[k][i];
+    }
+    explicit operator bool() const { return valid_; }
+    const Grid& grid() const { return *grid_; }
+    Dune::GeometryType type() const { return Dune::GeometryTypes::cube(mydim); }
+    int corners() const { return ncorners; }
+    GlobalCoordinate corner(int k) const { GlobalCoordinate y; for (int i = 0; i < cdim; ++i) y[i] = c_[k][i]; return y; }
+    GlobalCoordinate global(const LocalCoordinate& x) const {
+      GlobalCoordinate y; const double (*cit)[cdim] = c_;
+      orc::ml_global<cdim>(mydim, cit, x.data(), 1.0, false, y.data());
+      return y;
+    }
+    void jacobianTransposed(const LocalCoordinate& x, double (*jt)[cdim]) const {
+      const double (*cit)[cdim] = c_;
+      orc::ml_jt<cdim>(mydim, cit, x.data(), 1.0, false, jt);
+    }
+    JacobianInverseTransposed jacobianInverseTransposed(const LocalCoordinate& x) const {
+      static_assert(mydim == cdim, "inverse only for elements");
+      double jt[mydim][cdim], inv[cdim][cdim];
+      jacobianTransposed(x, jt);
+      JacobianInverseTransposed r;
+      r.detInv_ = orc::right_inv<cdim>(jt, inv);          // MatrixHelper::rightInvA returns sqrt(det(A A^T))
+      for (int i = 0; i < cdim; ++i) for (int j = 0; j < mydim; ++j) r.m[i][j] = inv[i][j];
+      return r;
+    }
+    double integrationElement(const LocalCoordinate& x) const {
+      double jt[mydim > 0 ? mydim : 1][cdim];
+      jacobianTransposed(x, jt);
+      return orc::sqrt_det_aat_rect<mydim,cdim>(jt);
+    }
+    GlobalCoordinate center() const { return global(Dune::referenceElement<double,mydim>(type()).position(0, 0)); }
+    double volume() const { return integrationElement(Dune::referenceElement<double,mydim>(type()).position(0, 0))*1.0; }
+    const double (*raw() const)[cdim] { return c_; }
+  private:
+    const Grid* grid_; bool valid_;
+    double c_[ncorners][cdim];
+  };
+
+  template<int dim, class HostGridType>
+  struct Grid {
+    typedef Grid<dim, HostGridType> This;
+    struct Traits {
+      typedef double ctype;
+      static const int dimension = dim, dimensionworld = dim;
+      typedef HostGridType HostGrid;
+      typedef orcgeo::CoordFunction<dim> CoordFunction;
+      template<int cd> struct Codim {
+        typedef MLGeometry<dim-cd, dim, const This> GeometryImpl;
+        typedef GeometryImpl Geometry;
+        typedef typename HostGrid::template Codim<1>::LocalGeometry LocalGeometry;
+        typedef int Entity; typedef int EntityImpl;          // inside() / outside() are never instantiated
+      };
+    };
+  };
+}
 
 namespace {
 
@@ -55,6 +151,8 @@ struct WorldBase {
   virtual int64_t geometryEval(int rank, int level, int pit, int nqp, const double* qp, double*, double*, double*) = 0;
   virtual int64_t geogridEval(int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
                               double*, double*, double*, double*, double*) = 0;
+  virtual int64_t geogridIntersections(int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
+                                       double*, double*, double*, double*, double*, double*, double*) = 0;
   virtual int64_t communicate(int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* items) = 0;
   virtual std::string backup(int rank) = 0;
   virtual int64_t globalIndex(int level, int codim, int32_t** out) = 0;
@@ -392,16 +490,19 @@ struct World : WorldBase {
     Grid& gr = g(rank);
     int64_t n = 0;
     constexpr int nc = 1 << dim;
+    const orcgeo::CoordFunction<dim> cf(def, params);
     dispatch<dim>(0, pit, [&](auto, auto pitc) {
       constexpr Dune::PartitionIteratorType pt = decltype(pitc)::value;
       auto end = gr.template lend<0,pt>(level);
       for (auto it = gr.template lbegin<0,pt>(level); it != end; ++it, ++n) {
-        auto hostGeo = it->geometry();
+        // corners through the reference's own GeoGrid::CoordVector (HostCorners + CoordFunctionCaller)
+        typedef orcgeo::Grid<dim, Grid> GG;
+        typedef typename std::decay_t<decltype(*it)> HostElement;
+        std::array<Dune::FieldVector<double,dim>, nc> cc;
+        Dune::GeoGrid::CoordVector<dim, const GG, false>(*it, cf).calculate(cc);
         double c[nc][dim];
         for (int k = 0; k < nc; ++k) {
-          auto hc = hostGeo.corner(k);
-          double x[dim]; for (int i = 0; i < dim; ++i) x[i] = hc[i];
-          orc::deformation(def, params, dim, x, c[k]);
+          for (int i = 0; i < dim; ++i) c[k][i] = cc[k][i];
           if (corners) for (int i = 0; i < dim; ++i) corners[(n*nc+k)*dim+i] = c[k][i];
         }
         for (int q = 0; q < nqp; ++q) {
@@ -413,6 +514,47 @@ struct World : WorldBase {
           if (jt) for (int i = 0; i < dim; ++i) for (int j = 0; j < dim; ++j) jt[(k*dim+i)*dim+j] = J[i][j];
           if (jit) { orc::right_inv<dim>(J, Ji); for (int i = 0; i < dim; ++i) for (int j = 0; j < dim; ++j) jit[(k*dim+i)*dim+j] = Ji[i][j]; }
           if (detJ) detJ[k] = orc::sqrt_det_aat<dim>(J);
+        }
+      }
+    });
+    return n;
+  }
+
+
+  // GeoGrid::Intersection (geometrygrid/intersection.hh, compiled unmodified) over the Yasp host intersections
+  int64_t geogridIntersections(int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
+                               double* corners, double* center, double* volume, double* ion, double* on, double* uon, double* cuon) override {
+    typedef orcgeo::Grid<dim, Grid> GG;
+    typedef typename GG::Traits::template Codim<0>::GeometryImpl ElementGeo;
+    Grid& gr = g(rank);
+    GV gv = gr.levelGridView(level);
+    const GG gg;
+    const orcgeo::CoordFunction<dim> cf(def, params);
+    constexpr int nfc = 1 << (dim-1);
+    int64_t n = 0;
+    dispatch<dim>(0, pit, [&](auto, auto pitc) {
+      constexpr Dune::PartitionIteratorType pt = decltype(pitc)::value;
+      auto end = gr.template lend<0,pt>(level);
+      for (auto it = gr.template lbegin<0,pt>(level); it != end; ++it, ++n) {
+        const auto& e = *it;
+        Dune::GeoGrid::CoordVector<dim, const GG, false> coords(e, cf);
+        const ElementGeo insideGeo(gg, e.type(), coords);                                  // geometrygrid/geometry.hh:138-145
+        auto iend = gv.iend(e);
+        for (auto iit = gv.ibegin(e); iit != iend; ++iit) {
+          typedef typename std::decay_t<decltype(*iit)>::Implementation HostIntersectionImpl;
+          Dune::GeoGrid::Intersection<const GG, HostIntersectionImpl> is(iit->impl(), insideGeo);
+          const int64_t k = n*2*dim + is.indexInInside();
+          auto geo = is.geometry();
+          if (corners) for (int c = 0; c < nfc; ++c) { auto x = geo.corner(c); for (int i = 0; i < dim; ++i) corners[(k*nfc+c)*dim+i] = x[i]; }
+          if (center) { auto x = geo.center(); for (int i = 0; i < dim; ++i) center[k*dim+i] = x[i]; }
+          if (volume) volume[k] = geo.volume();
+          for (int q = 0; q < nqp; ++q) {
+            Dune::FieldVector<double,dim-1> x; for (int i = 0; i < dim-1; ++i) x[i] = qp[q*(dim-1)+i];
+            if (ion) { auto v = is.integrationOuterNormal(x); for (int i = 0; i < dim; ++i) ion[((k*nqp)+q)*dim+i] = v[i]; }
+            if (on) { auto v = is.outerNormal(x); for (int i = 0; i < dim; ++i) on[((k*nqp)+q)*dim+i] = v[i]; }
+            if (uon) { auto v = is.unitOuterNormal(x); for (int i = 0; i < dim; ++i) uon[((k*nqp)+q)*dim+i] = v[i]; }
+          }
+          if (cuon) { auto v = is.centerUnitOuterNormal(); for (int i = 0; i < dim; ++i) cuon[k*dim+i] = v[i]; }
         }
       }
     });
@@ -629,6 +771,10 @@ int64_t orc_geometry_eval(void* w, int rank, int level, int pit, int nqp, const 
 int64_t orc_geogrid_eval(void* w, int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
                          double* corners, double* global, double* jt, double* jit, double* detJ) {
   return guarded(int64_t(-1), [&]{ return W(w)->geogridEval(rank, level, pit, def, params, nqp, qp, corners, global, jt, jit, detJ); });
+}
+int64_t orc_geogrid_intersections(void* w, int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
+                                  double* corners, double* center, double* volume, double* ion, double* on, double* uon, double* cuon) {
+  return guarded(int64_t(-1), [&]{ return W(w)->geogridIntersections(rank, level, pit, def, params, nqp, qp, corners, center, volume, ion, on, uon, cuon); });
 }
 int64_t orc_communicate(void* w, int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* items) {
   return guarded(int64_t(-1), [&]{ return W(w)->communicate(level, block, iftype, dir, op, narrays, arrays, items); });

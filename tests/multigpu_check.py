@@ -30,18 +30,27 @@ def main():
         (make_cfg(dim=2, N=(32, 24), periodic=1), 1, [1.0, 0, 0, 0.0, 0.5, 0.5, 0.0, 0.1, 0.3]),
         # overlap 2, fully periodic, uneven split, partial tiles: send boxes two cells thick, wrap-around partners
         (make_cfg(dim=3, N=(36, 22, 26), periodic=7, overlap=2), 0, [0.6, -1.0, 0.8, 0.0, 0.5, 0.5, 0.5, 0.1, 0.45]),
+        # wide and tall rank boxes: the 128x4 tile with odd row strides, and z extents that take the pipelined host path
+        (make_cfg(dim=3, N=(520, 12, 300), upper=(1.0, 0.05, 0.6)), 0, [1.0, -0.05, 0.4, 0.2, 0.5, 0.02, 0.3, 0.01, 0.2]),
     ]
     failures = 0
     modes = set()
+    host_paths = set()
     for cfg, problem, params in cases:
         w = oracle_world(o, cfg, world)
         g = product_grid(cfg, rank, world, comm=comm)
         gv = g.leafGridView()
-        for mode in ("exact", "separable"):
+        for mode, registered in (("exact", False), ("separable", False), ("exact", True), ("separable", True)):
+            if registered and cfg["dim"] != 3:
+                continue
             ref = [w.fv_init(r, 0, problem, params) for r in range(world)]
             fv = dg.FiniteVolume(g, 0, problem, params, mode)
             c = fv.initial()
             cn = torch.empty_like(c)
+            if registered:                    # peers store the halo cells straight into these two arrays (CUDA IPC)
+                nreg = fv.register_fields(c, cn)
+                if nreg != 2:
+                    print(f"rank {rank}: register_fields declined ({nreg}) cfg={cfg['N']}", flush=True)
             ok = np.array_equal(c.cpu().numpy(), ref[rank])
             for _ in range(4):
                 dt_ref = w.fv_step(0, problem, params, ref)
@@ -58,7 +67,24 @@ def main():
             modes.add(fv.exchange_mode())
             if not ok:
                 failures += 1
-                print(f"rank {rank}: FV mismatch cfg={cfg['N']} mode={mode} maxdiff={np.abs(got - ref[rank]).max()}", flush=True)
+                print(f"rank {rank}: FV mismatch cfg={cfg['N']} mode={mode} registered={registered} exchange={fv.exchange_mode()} "
+                      f"maxdiff={np.abs(got - ref[rank]).max()}", flush=True)
+            if cfg["dim"] == 3 and not registered:
+                # the host-buffer entry point (pipelined over z-slabs where the rank box is tall enough; unpack into the host result)
+                h_in = torch.from_numpy(ref[rank].copy()).pin_memory()
+                h_out = torch.full_like(h_in, float("nan")).pin_memory()
+                for _ in range(2):
+                    dt_ref = w.fv_step(0, problem, params, ref)
+                    dt = fv.step_host(h_in, h_out)
+                    h_in, h_out = h_out, h_in
+                hgot = h_in.numpy()
+                hok = (np.array_equal(hgot, ref[rank]) and dt == dt_ref) if mode == "exact" else \
+                      (np.abs(hgot - ref[rank]).max() <= 1e-13 * scale and abs(dt - dt_ref) <= 1e-13 * dt_ref)
+                host_paths.add(fv.host_path())
+                if not hok:
+                    failures += 1
+                    print(f"rank {rank}: step_host mismatch cfg={cfg['N']} mode={mode} path={fv.host_path()} maxdiff={np.abs(hgot - ref[rank]).max()}", flush=True)
+            fv.close()
         # communicate through the public call (NCCL transport), all interfaces, set and add
         layout = [1] + [0] * (cfg["dim"] - 1) + [1]
         m = dg.MultipleCodimMultipleGeomTypeMapper(gv, layout)
@@ -88,7 +114,7 @@ def main():
     dist.all_reduce(t)
     if rank == 0:
         print(f"multigpu_check world={world}: {'OK' if t.item() == 0 else 'FAILED'} ({int(t.item())} mismatches), "
-              f"FV exchange modes on rank 0: {sorted(modes)}", flush=True)
+              f"FV exchange modes on rank 0: {sorted(modes)}, host paths: {sorted(host_paths)}", flush=True)
     dist.barrier()
     comm.close()
     dist.destroy_process_group()

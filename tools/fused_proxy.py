@@ -34,7 +34,7 @@ def main():
     gv = g.leafGridView()
     interior = gv.size(0, dg.Interior_Partition)
     out = {}
-    for label, env in (("fused", {"DGB_FV_FUSED": "1"}), ("overlapped", {"DGB_FV_FUSED": "0"}),
+    for label, env in (("direct", {"DGB_FV_FUSED": "1"}), ("fused", {"DGB_FV_FUSED": "1"}), ("overlapped", {"DGB_FV_FUSED": "0"}),
                        ("serial", {"DGB_FV_FUSED": "0", "DGB_FV_NO_SPLIT": "1"})):
         for k in ("DGB_FV_FUSED", "DGB_FV_NO_SPLIT"):
             os.environ.pop(k, None)
@@ -43,6 +43,8 @@ def main():
         c = fv.initial()
         cn = torch.empty_like(c)
         state = [c, cn]
+        if label == "direct":
+            assert fv.register_fields(c, cn) == 2
 
         def step():
             fv.step(state[0], state[1])

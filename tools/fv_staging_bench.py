@@ -64,11 +64,12 @@ def run(label, grid, staging, reps, local):
 
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    quick = len(sys.argv) > 2 and sys.argv[2] == "quick"
     g1 = dg.YaspGrid(dim=3, N=(512, 512, 512), upper=(1.0, 1.0, 1.0), overlap=1)
     for st in ("pair", "a16", "8"):
         run("512^3 single rank (config 2)", g1, st, reps, False)
     del g1
-    for P, ranks in ((8, (0, 7)), (2, (0, 1)), (4, (0, 1))):
+    for P, ranks in (((8, (7,)), (2, (1,)), (4, (1,))) if quick else ((8, (0, 7)), (2, (0, 1)), (4, (0, 1)))):
         for r in ranks:
             g = dg.YaspGrid(dim=3, N=(1024, 1024, 1024), upper=(1.0, 1.0, 1.0), overlap=1, rank=r, nranks=P)
             g.comm = _FakeComm()
