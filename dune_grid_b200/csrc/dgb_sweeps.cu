@@ -290,6 +290,131 @@ __global__ void __launch_bounds__(BX) k_geogrid(const __grid_constant__ dgb_view
   }
 }
 
+
+// ---- K8b: GeometryGrid intersections ---------------------------------------------------------------------------------
+// GeoGrid::Intersection over the Yasp host intersection (geometrygrid/intersection.hh:103-172): per cell the deformed corners
+// are evaluated once (8 coordinate-function calls in 3-D); per face k (dir = k/2, side = k%2) the face corners are
+// insideGeo.global(hostLocalGeometry.corner(i)) (cornerstorage.hh:148-154; the host's local face geometry is the unit face of
+// yaspgridintersection.hh:195-209), the face geometry is the multilinear map over them (centre, volume), and the normals at a
+// face-local point come from the ELEMENT's Jacobian at x = geometryInInside().global(local): outerNormal = J^-T n_ref,
+// integrationOuterNormal = J^-T n_ref |det J|, unitOuterNormal = outerNormal / |outerNormal|.
+struct FacePoints { int n; double x[16*2]; };
+struct GeoFaceOut { double *corners, *center, *volume, *ion, *on, *uon, *cuon; };
+
+template<int DIM>
+__device__ __forceinline__ void geoface_normals(const double (*c)[DIM], int dir, int side, const double* xl, double* vI, double* vO, double* vU) {
+  double x[DIM], J[DIM][DIM], Ji[DIM][DIM], nrm[DIM];
+  int b = 0;
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) x[i] = (i == dir) ? double(side) : 0.0 + xl[b++]*(1.0 - 0.0);     // AxisAlignedCubeGeometry::global of the unit face
+  ml_jt<DIM>(c, x, J);
+  const double det = ml_det<DIM>(J);
+  ml_inverse_transposed<DIM>(J, det, Ji);
+  const double sgn = side ? 1.0 : -1.0;
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) nrm[i] = Ji[i][dir]*sgn;                                        // jit.mv(refNormal), refNormal = +-e_dir
+  if (vO) {
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) vO[i] = nrm[i];
+  }
+  if (vI) {
+    const double a = fabs(det);                                                               // jit.detInv()
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) vI[i] = nrm[i]*a;
+  }
+  if (vU) {
+    double s2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) s2 += nrm[i]*nrm[i];
+    const double f = 1.0/sqrt(s2);
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) vU[i] = nrm[i]*f;
+  }
+}
+
+template<int DIM>
+__global__ void __launch_bounds__(BX) k_geogrid_faces(const __grid_constant__ dgb_view v, const SweepGeom s, const FacePoints q,
+                                                      const Deformation def, const GeoFaceOut o) {
+  int coord[3]; long long pos;
+  if (!sweep_entity<1>(v, s, 0, coord, pos)) return;
+  constexpr int NC = 1 << DIM, NFC = 1 << (DIM-1);
+  double ll[DIM], ur[DIM];
+  for (int i = 0; i < DIM; ++i) {
+    const double sh = periodic_shift(v, i, coord[i]);
+    ll[i] = vertex_coord(v, i, coord[i]); ur[i] = vertex_coord(v, i, coord[i]+1);
+    if (sh != 0.0) { ll[i] += sh; ur[i] += sh; }
+  }
+  double c[NC][DIM];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    double x[DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) x[i] = (k >> i & 1) ? ur[i] : ll[i];
+    deform<DIM>(def, x, c[k]);
+  }
+  double half[DIM];
+#pragma unroll
+  for (int i = 0; i < DIM; ++i) half[i] = 0.5;
+#pragma unroll
+  for (int f = 0; f < 2*DIM; ++f) {
+    const int dir = f/2, side = f % 2;
+    if (o.corners || o.center || o.volume) {
+      double fc[NFC][DIM];
+#pragma unroll
+      for (int i = 0; i < NFC; ++i) {
+        double xl[DIM];
+        int b = 0;
+#pragma unroll
+        for (int ax = 0; ax < DIM; ++ax) xl[ax] = (ax == dir) ? double(side) : double((i >> b++) & 1);
+        ml_global<DIM>(c, xl, fc[i]);
+        if (o.corners)
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) o.corners[((long long)(f*NFC + i)*DIM + d)*s.n + pos] = fc[i][d];
+      }
+      if (o.center) {
+        double y[DIM];
+        MLGlobal<DIM, DIM-1, 0, false>::run(fc, half, 1.0, y);
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) o.center[((long long)f*DIM + d)*s.n + pos] = y[d];
+      }
+      if (o.volume) {
+        double jt[DIM > 1 ? DIM-1 : 1][DIM];
+        MLJt<DIM, DIM-1, 0, false>::run(fc, half, 1.0, jt);
+        double vol;
+        if (DIM == 3) {                                   // FieldMatrixHelper::sqrtDetAAT<2,3>
+          const double v0 = jt[0][0]*jt[1][1] - jt[0][1]*jt[1][0];
+          const double v1 = jt[0][0]*jt[1][2 % DIM] - jt[1][0]*jt[0][2 % DIM];
+          const double v2 = jt[0][1]*jt[1][2 % DIM] - jt[0][2 % DIM]*jt[1][1];
+          vol = sqrt(v0*v0 + v1*v1 + v2*v2);
+        } else {                                          // <1,2>: Cholesky factor of the 1x1 matrix A A^T
+          double a = 0.0;
+#pragma unroll
+          for (int d = 0; d < DIM; ++d) a += jt[0][d]*jt[0][d];
+          vol = sqrt(a);
+        }
+        o.volume[(long long)f*s.n + pos] = vol;
+      }
+    }
+    for (int p = 0; p < q.n; ++p) {
+      double vI[DIM], vO[DIM], vU[DIM];
+      geoface_normals<DIM>(c, dir, side, q.x + p*(DIM-1), o.ion ? vI : nullptr, o.on ? vO : nullptr, o.uon ? vU : nullptr);
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) {
+        const long long at = ((long long)(f*q.n + p)*DIM + d)*s.n + pos;
+        if (o.ion) o.ion[at] = vI[d];
+        if (o.on) o.on[at] = vO[d];
+        if (o.uon) o.uon[at] = vU[d];
+      }
+    }
+    if (o.cuon) {
+      double vU[DIM];
+      geoface_normals<DIM>(c, dir, side, half, nullptr, nullptr, vU);
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) o.cuon[((long long)f*DIM + d)*s.n + pos] = vU[d];
+    }
+  }
+}
+
 // reduction variant: sum_q w_q |det J(x_q)| over all cells; block partial via warp shuffles, one atomicAdd per block
 template<int DIM>
 __global__ void __launch_bounds__(BX) k_geogrid_volume(const __grid_constant__ dgb_view v, const SweepGeom s, const QuadPoints q,
@@ -436,6 +561,24 @@ int dgb_geogrid_eval(const dgb_view* v, int pitype, int deformation, const doubl
   return for_each_component(*v, 0, pitype, 1, [&](const SweepGeom& s, dim3 grid) {
     if (v->dim == 3) k_geogrid<3><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, q, def, o);
     else k_geogrid<2><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, q, def, o);
+  });
+}
+
+int dgb_geogrid_intersections(const dgb_view* v, int pitype, int deformation, const double* params_host, int nparams, int nqp,
+                              const double* qp_face_host, double* d_corners, double* d_center, double* d_volume,
+                              double* d_integrationOuterNormal, double* d_outerNormal, double* d_unitOuterNormal,
+                              double* d_centerUnitOuterNormal, void* stream) {
+  if (int rc = check_tensor(*v)) return rc;
+  if (nqp < 0 || nqp > 16) return fail(DGB_EARG, "at most 16 face points per call");
+  if (deformation < 0 || deformation > 1) return fail(DGB_EARG, "unknown deformation id");
+  FacePoints q; q.n = nqp;
+  for (int i = 0; i < nqp*(v->dim-1); ++i) q.x[i] = qp_face_host[i];
+  Deformation def; def.id = deformation;
+  for (int i = 0; i < 4; ++i) def.p[i] = (params_host && i < nparams) ? params_host[i] : 0.0;
+  GeoFaceOut o{d_corners, d_center, d_volume, d_integrationOuterNormal, d_outerNormal, d_unitOuterNormal, d_centerUnitOuterNormal};
+  return for_each_component(*v, 0, pitype, 1, [&](const SweepGeom& s, dim3 grid) {
+    if (v->dim == 3) k_geogrid_faces<3><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, q, def, o);
+    else k_geogrid_faces<2><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, q, def, o);
   });
 }
 

@@ -294,6 +294,27 @@ class GridView:
                                    _ptr(r["integrationElement"]), _stream()))
         return r
 
+    def geometryGridIntersections(self, deformation, params, qp_face, partition=All_Partition, corners=True):
+        """GeometryGrid<YaspGrid, F> intersections of every cell (GeoGrid::Intersection): corners (2dim, 2^(dim-1), dim, n), center
+        (2dim, dim, n), volume (2dim, n); at the face-local points qp_face (nqp x (dim-1)): integrationOuterNormal, outerNormal,
+        unitOuterNormal (2dim, nqp, dim, n); centerUnitOuterNormal (2dim, dim, n)"""
+        _require_cuda()
+        torch = _torch()
+        d = self.dim
+        qp = np.ascontiguousarray(qp_face, dtype=np.float64).reshape(-1, max(1, d - 1))
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        n, nq = self.size(0, partition), qp.shape[0]
+        z = lambda *shape: torch.empty(shape, dtype=torch.float64, device="cuda")       # noqa: E731
+        r = {"center": z(2 * d, d, n), "volume": z(2 * d, n), "integrationOuterNormal": z(2 * d, nq, d, n), "outerNormal": z(2 * d, nq, d, n),
+             "unitOuterNormal": z(2 * d, nq, d, n), "centerUnitOuterNormal": z(2 * d, d, n)}
+        if corners:
+            r["corners"] = z(2 * d, 1 << (d - 1), d, n)
+        check(lib.dgb_geogrid_intersections(C.byref(self.v), partition, deformation, params.ctypes.data_as(C.POINTER(C.c_double)), params.size,
+                                            nq, qp.ctypes.data_as(C.POINTER(C.c_double)), _ptr(r.get("corners")), _ptr(r["center"]), _ptr(r["volume"]),
+                                            _ptr(r["integrationOuterNormal"]), _ptr(r["outerNormal"]), _ptr(r["unitOuterNormal"]),
+                                            _ptr(r["centerUnitOuterNormal"]), _stream()))
+        return r
+
     def geometryGridVolume(self, deformation, params, qp, weights, partition=All_Partition):
         _require_cuda()
         torch = _torch()

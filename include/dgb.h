@@ -194,6 +194,17 @@ int dgb_geometry_eval(const dgb_view* v, int pitype, int nqp, const double* qp_h
 int dgb_geogrid_eval(const dgb_view* v, int pitype, int deformation, const double* params_host, int nparams,
                      int nqp, const double* qp_host, double* d_corners, double* d_global, double* d_jt, double* d_jit,
                      double* d_detJ, void* stream);
+/* GeoGrid::Intersection of GeometryGrid over the Yasp host view (geometrygrid/intersection.hh:103-172, cornerstorage.hh:122-165)
+ * for every cell of the partition and its 2*dim faces in reference order (k: dir = k/2, side = k%2), NULL = skip:
+ *   corners[((k*2^(dim-1)+i)*dim+d)*n+e]  geometry().corner(i) = insideGeo.global(hostLocalGeometry.corner(i))
+ *   center[(k*dim+d)*n+e], volume[k*n+e]  geometry().center() / .volume() of the multilinear face geometry
+ *   at the nqp (<= 16) face-local points qp_face_host (nqp x (dim-1)), out[((k*nqp+q)*dim+d)*n+e]:
+ *     integrationOuterNormal = J^-T(x) n_ref |det J(x)|, outerNormal = J^-T(x) n_ref, unitOuterNormal, x = geometryInInside().global(local)
+ *   centerUnitOuterNormal[(k*dim+d)*n+e]  = unitOuterNormal(face centre) */
+int dgb_geogrid_intersections(const dgb_view* v, int pitype, int deformation, const double* params_host, int nparams,
+                              int nqp, const double* qp_face_host, double* d_corners, double* d_center, double* d_volume,
+                              double* d_integrationOuterNormal, double* d_outerNormal, double* d_unitOuterNormal,
+                              double* d_centerUnitOuterNormal, void* stream);
 /* reduction variant: sum over cells and points of weight_q * detJ -> *d_sum (one double, device) */
 int dgb_geogrid_volume(const dgb_view* v, int pitype, int deformation, const double* params_host, int nparams,
                        int nqp, const double* qp_host, const double* weights_host, double* d_sum, void* stream);

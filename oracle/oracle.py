@@ -104,6 +104,7 @@ class OracleLib:
             "orc_intersections": (i64, [vp, i32, i32, i32, pu8, pu8, pi32, pi32, pd, pd, pd]),
             "orc_geometry_eval": (i64, [vp, i32, i32, i32, i32, pd, pd, pd, pd]),
             "orc_geogrid_eval": (i64, [vp, i32, i32, i32, i32, pd, i32, pd, pd, pd, pd, pd, pd]),
+            "orc_geogrid_intersections": (i64, [vp, i32, i32, i32, i32, pd, i32, pd, pd, pd, pd, pd, pd, pd, pd]),
             "orc_communicate": (i64, [vp, i32, pu32, i32, i32, i32, i32, ppd, pi]),
             "orc_global_index": (i64, [vp, i32, i32, C.POINTER(pi32)]),
             "orc_backup": (i32, [vp, i32, C.c_char_p, i32]),
@@ -309,6 +310,22 @@ class World:
         self._chk(self.L.orc_geogrid_eval(self.h, rank, level, pitype, deformation, _p(params, C.c_double), nq, _p(qp, C.c_double),
                                           _p(r["corners"], C.c_double), _p(r["global"], C.c_double), _p(r["jt"], C.c_double),
                                           _p(r["jit"], C.c_double), _p(r["detJ"], C.c_double)))
+        return r
+
+    def geogrid_intersections(self, rank, level, deformation, params, qp_face, pitype=All_Partition):
+        """GeoGrid::Intersection of every face of every cell: corners (n, 2d, 2^(d-1), d), center (n, 2d, d), volume (n, 2d),
+        integrationOuterNormal / outerNormal / unitOuterNormal (n, 2d, nqp, d) at the face-local points, centerUnitOuterNormal (n, 2d, d)"""
+        d = self.dim
+        qp = np.ascontiguousarray(qp_face, dtype=np.float64).reshape(-1, max(1, d - 1))
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        n, nq = self.ncells(rank, level, pitype), qp.shape[0]
+        r = {"corners": np.zeros((n, 2 * d, 1 << (d - 1), d)), "center": np.zeros((n, 2 * d, d)), "volume": np.zeros((n, 2 * d)),
+             "integrationOuterNormal": np.zeros((n, 2 * d, nq, d)), "outerNormal": np.zeros((n, 2 * d, nq, d)),
+             "unitOuterNormal": np.zeros((n, 2 * d, nq, d)), "centerUnitOuterNormal": np.zeros((n, 2 * d, d))}
+        self._chk(self.L.orc_geogrid_intersections(self.h, rank, level, pitype, deformation, _p(params, C.c_double), nq, _p(qp, C.c_double),
+                                                   _p(r["corners"], C.c_double), _p(r["center"], C.c_double), _p(r["volume"], C.c_double),
+                                                   _p(r["integrationOuterNormal"], C.c_double), _p(r["outerNormal"], C.c_double),
+                                                   _p(r["unitOuterNormal"], C.c_double), _p(r["centerUnitOuterNormal"], C.c_double)))
         return r
 
     def _pp(self, per_rank_arrays):

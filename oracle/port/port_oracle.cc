@@ -850,7 +850,60 @@ int64_t geogridEval(const World& wd, int rank, int level, int pitype, int def, c
     }
   });
 }
+// GeoGrid::Intersection over the Yasp host (geometrygrid/intersection.hh:103-172): face corners = insideGeo.global(
+// hostLocalGeometry.corner(i)) (cornerstorage.hh:148-154, local geometry of yaspgridintersection.hh:195-209), face geometry =
+// multilinear map over them, normals = J^-T(x) n_ref (|det J(x)|) at x = geometryInInside().global(local)
+template<int dim>
+int64_t geogridIntersections(const World& wd, int rank, int level, int pitype, int def, const double* params, int nqp, const double* qp,
+                             double* corners, double* center, double* volume, double* ion, double* on, double* uon, double* cuon) {
+  constexpr int nc = 1 << dim, nfc = 1 << (dim-1);
+  return wd.forEachEntity(rank, level, 0, pitype, [&](const Level& g, int, const I3& cell, int, int64_t n) {
+    double ll[3], ur[3]; wd.bounds(g, cell, (1u << dim)-1, true, ll, ur);
+    double c[nc][dim];
+    for (int k = 0; k < nc; ++k) {
+      double x[dim]; for (int i = 0; i < dim; ++i) x[i] = (k >> i & 1) ? ur[i] : ll[i];
+      orc::deformation(def, params, dim, x, c[k]);
+    }
+    auto normals = [&](int dir, int side, const double* xl, double* vI, double* vO, double* vU) {
+      double x[dim]; int b = 0;
+      for (int i = 0; i < dim; ++i) x[i] = (i == dir) ? double(side) : 0.0 + xl[b++]*(1.0 - 0.0);      // AxisAlignedCubeGeometry::global
+      double J[dim][dim], Ji[dim][dim], refn[dim], nrm[dim];
+      orc::multilinear_jt<dim>(c, x, J);
+      const double detInv = orc::right_inv<dim>(J, Ji);
+      for (int i = 0; i < dim; ++i) refn[i] = 0.0;
+      refn[dir] = side ? 1.0 : -1.0;
+      for (int i = 0; i < dim; ++i) { nrm[i] = 0; for (int j = 0; j < dim; ++j) nrm[i] += Ji[i][j]*refn[j]; }      // jit.mv
+      if (vO) for (int i = 0; i < dim; ++i) vO[i] = nrm[i];
+      if (vI) for (int i = 0; i < dim; ++i) vI[i] = nrm[i]*detInv;
+      if (vU) { double s = 0; for (int i = 0; i < dim; ++i) s += nrm[i]*nrm[i]; const double f = 1.0/std::sqrt(s); for (int i = 0; i < dim; ++i) vU[i] = nrm[i]*f; }
+    };
+    for (int f = 0; f < 2*dim; ++f) {
+      const int dir = f/2, side = f % 2; const int64_t k = n*2*dim + f;
+      double fc[nfc][dim];
+      for (int i = 0; i < nfc; ++i) {
+        double xl[dim]; int b = 0;
+        for (int ax = 0; ax < dim; ++ax) xl[ax] = (ax == dir) ? double(side) : double((i >> b++) & 1);
+        orc::multilinear_global<dim>(c, xl, fc[i]);
+        if (corners) for (int d = 0; d < dim; ++d) corners[(k*nfc+i)*dim+d] = fc[i][d];
+      }
+      double half[dim > 1 ? dim-1 : 1]; for (int i = 0; i < dim-1; ++i) half[i] = 0.5;
+      if (center) { double y[dim]; const double (*cit)[dim] = fc; orc::ml_global<dim>(dim-1, cit, half, 1.0, false, y); for (int d = 0; d < dim; ++d) center[k*dim+d] = y[d]; }
+      if (volume) { double jt[dim > 1 ? dim-1 : 1][dim]; const double (*cit)[dim] = fc; orc::ml_jt<dim>(dim-1, cit, half, 1.0, false, jt); volume[k] = orc::sqrt_det_aat_rect<dim-1,dim>(jt); }
+      for (int q = 0; q < nqp; ++q)
+        normals(dir, side, qp + q*(dim-1), ion ? ion + (k*nqp+q)*dim : nullptr, on ? on + (k*nqp+q)*dim : nullptr, uon ? uon + (k*nqp+q)*dim : nullptr);
+      if (cuon) normals(dir, side, half, nullptr, nullptr, cuon + k*dim);
+    }
+  });
+}
 extern "C" {
+int64_t orc_geogrid_intersections(void* w, int rank, int level, int pitype, int deformation, const double* params, int nqp, const double* qp,
+                                  double* corners, double* center, double* volume, double* ion, double* on, double* uon, double* cuon) {
+  return guarded(int64_t(-1), [&]() -> int64_t {
+    const World& wd = *W(w);
+    return wd.dim == 2 ? geogridIntersections<2>(wd, rank, level, pitype, deformation, params, nqp, qp, corners, center, volume, ion, on, uon, cuon)
+                       : geogridIntersections<3>(wd, rank, level, pitype, deformation, params, nqp, qp, corners, center, volume, ion, on, uon, cuon);
+  });
+}
 int64_t orc_geogrid_eval(void* w, int rank, int level, int pitype, int deformation, const double* params, int nqp, const double* qp,
                          double* corners, double* global, double* jt, double* jit, double* detJ) {
   return guarded(int64_t(-1), [&]() -> int64_t {
