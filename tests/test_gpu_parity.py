@@ -187,7 +187,8 @@ GEOFACE_CASES = [
 def test_geometrygrid_intersections(cfg):
     """GeoGrid::Intersection (geometrygrid/intersection.hh:103-172, cornerstorage.hh:122-165) as a bulk sweep against the oracle
     - the reference's own intersection / corner-vector headers compiled over the restated multilinear map: face corners,
-    face centre and volume bit for bit (same expressions), normals within 1e-13 relative (the product inverts J by the
+    face centre and volume bit for bit for the identity deformation (same expressions), within 1e-13 relative with the sine
+    deformation (device sin() differs from glibc's by <= 2 ulp), normals within 1e-13 relative (the product inverts J by the
     adjugate, dune-geometry by a Cholesky right inverse) - plus the reference's own invariants: unit normals have norm 1 and
     are parallel to J^-T n_ref (checkintersectionit.hh:329-400), centerUnitOuterNormal == unitOuterNormal(face centre), and the
     integration outer normals of a cell, integrated with the face's Gauss rule, sum to zero (checkintersectionit.hh:643-654)."""
@@ -205,10 +206,12 @@ def test_geometrygrid_intersections(cfg):
         got = gv.geometryGridIntersections(deformation, params, qp, dg.All_Partition)
         ref = w.geogrid_intersections(0, lvl, deformation, params, qp)
         t = lambda a, axes: np.transpose(a.cpu().numpy(), axes)                                  # noqa: E731
-        assert np.array_equal(t(got["corners"], (3, 0, 1, 2)), ref["corners"])
-        assert np.array_equal(t(got["center"], (2, 0, 1)), ref["center"])
-        assert np.array_equal(t(got["volume"], (1, 0)), ref["volume"])
-        scale = np.abs(ref["outerNormal"]).max()
+        for name, axes in (("corners", (3, 0, 1, 2)), ("center", (2, 0, 1)), ("volume", (1, 0))):
+            a, b = t(got[name], axes), ref[name]
+            if deformation == 0:
+                assert np.array_equal(a, b), name
+            else:
+                assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max(), name                      # tolerance: 1e-13 relative
         for name in ("integrationOuterNormal", "outerNormal", "unitOuterNormal"):
             a, b = t(got[name], (3, 0, 1, 2)), ref[name]
             assert np.abs(a - b).max() <= 1e-13 * max(1.0, np.abs(b).max()), name                # tolerance: 1e-13 relative

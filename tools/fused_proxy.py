@@ -28,14 +28,23 @@ def timeit(f, reps):
 
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-    g = dg.YaspGrid(dim=3, N=(n, n, n), upper=(1.0, 1.0, 1.0), overlap=1, periodic=7)
+    if len(sys.argv) > 4:                    # nx ny nz periodic-mask [reps [labels]]
+        N = tuple(int(x) for x in sys.argv[1:4]); per = int(sys.argv[4])
+        reps = int(sys.argv[5]) if len(sys.argv) > 5 else 200
+        only = sys.argv[6].split(",") if len(sys.argv) > 6 else None
+    else:
+        n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+        reps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+        N, per, only = (n, n, n), 7, None
+    n = N
+    g = dg.YaspGrid(dim=3, N=N, upper=(1.0, 1.0, 1.0), overlap=1, periodic=per)
     gv = g.leafGridView()
     interior = gv.size(0, dg.Interior_Partition)
     out = {}
     for label, env in (("direct", {"DGB_FV_FUSED": "1"}), ("fused", {"DGB_FV_FUSED": "1"}), ("overlapped", {"DGB_FV_FUSED": "0"}),
                        ("serial", {"DGB_FV_FUSED": "0", "DGB_FV_NO_SPLIT": "1"})):
+        if only and label not in only:
+            continue
         for k in ("DGB_FV_FUSED", "DGB_FV_NO_SPLIT"):
             os.environ.pop(k, None)
         os.environ.update(env)
@@ -51,7 +60,7 @@ def main():
             state.reverse()
         ms = timeit(step, reps)
         out[label] = (ms, fv.exchange_mode())
-        if label == "fused":
+        if label in ("fused", "direct") and "kernel only" not in out:
             ms_local = timeit(lambda: fv.step_local(c, cn), reps)
             out["kernel only"] = (ms_local, "-")
         del fv
