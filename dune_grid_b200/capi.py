@@ -88,6 +88,10 @@ _SIG = {
     "dgb_geogrid_eval": (_i, [_pv, _i, _i, C.POINTER(C.c_double), _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp, _vp]),
     "dgb_geogrid_intersections": (_i, [_pv, _i, _i, C.POINTER(C.c_double), _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dgb_geogrid_volume": (_i, [_pv, _i, _i, C.POINTER(C.c_double), _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp]),
+    "dgb_functor_count": (_i, [C.POINTER(_i)]),
+    "dgb_functor_info": (_i, [_i, C.POINTER(C.c_char_p), C.POINTER(_i), C.POINTER(_i)]),
+    "dgb_for_each_element": (_i, [_pv, _i, _i, C.POINTER(C.c_double), _i, _vp, _vp, _vp]),
+    "dgb_for_each_intersection": (_i, [_pv, _i, _i, C.POINTER(C.c_double), _i, _vp, _vp, _vp]),
     "dgb_comm_unique_id": (_i, [_vp]), "dgb_comm_init": (_i, [_vp, _i, _i, C.POINTER(_vp)]), "dgb_comm_destroy": (_i, [_vp]),
     "dgb_communicate": (_i, [_vp, _i, _pm, _i, _i, _i, C.POINTER(_vp), C.POINTER(C.c_int32), _i, _vp, _vp]),
     "dgb_comm_plan_info": (_i, [_vp, _i, _pm, _i, _i, C.POINTER(C.c_int32), _i, _i64p, _i]),

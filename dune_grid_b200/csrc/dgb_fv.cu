@@ -15,32 +15,49 @@
 #include <algorithm>
 #include "dgb_internal.hh"
 #include "dgb_device.cuh"
+#include "dgb_functors.cuh"
 #include "dgb_comm.hh"
 
 namespace dgb {
 
 struct FvProblem { int id; double p[12]; };
 
-// velocity, inflow value and initial value: device restatement of oracle/common/fv_problem.hh
+// velocity, inflow value and initial value come from the compiled-in problem registry (dgb_functors.cuh; the CPU statement of the
+// same functions is oracle/common/fv_problem.hh). Runtime dispatch by id for the general kernels, by template for the fast ones.
+template<int ID> struct FvProblemById;
+#define DGB_BY_ID(T_) template<> struct FvProblemById<T_::id> { using type = T_; };
+DGB_FOR_EACH_FV_PROBLEM(DGB_BY_ID)
+#undef DGB_BY_ID
+
 template<int DIM>
 __device__ __forceinline__ void fv_velocity(const FvProblem& q, const double* x, double* u) {
-  if (q.id == 1) {
-    u[0] = -q.p[0]*(x[1]-0.5);
-    u[1] =  q.p[0]*(x[0]-0.5);
-    if (DIM > 2) u[2] = 0.0;
-  } else {
+  double xx[3] = { x[0], x[1], DIM > 2 ? x[2] : 0.0 }, uu[3] = { 0.0, 0.0, 0.0 };
+#define DGB_VEL(T_) if (q.id == T_::id) T_::velocity(q.p, xx, uu);
+  DGB_FOR_EACH_FV_PROBLEM(DGB_VEL)
+#undef DGB_VEL
 #pragma unroll
-    for (int i = 0; i < DIM; ++i) u[i] = q.p[i];
-  }
+  for (int i = 0; i < DIM; ++i) u[i] = uu[i];
 }
-__device__ __forceinline__ double fv_boundary(const FvProblem& q, const double*) { return q.p[3]; }
+__device__ __forceinline__ double fv_boundary(const FvProblem& q, const double* x) {
+  double b = 0.0;
+#define DGB_BND(T_) if (q.id == T_::id) b = T_::boundary(q.p, x);
+  DGB_FOR_EACH_FV_PROBLEM(DGB_BND)
+#undef DGB_BND
+  return b;
+}
 template<int DIM>
 __device__ __forceinline__ double fv_initial(const FvProblem& q, const double* x) {
-  double s = 0.0;
-#pragma unroll
-  for (int i = 0; i < DIM; ++i) { const double d = x[i]-q.p[4+i]; s += d*d; }
-  const double r = sqrt(s);
-  return (r > q.p[7] && r < q.p[8]) ? 1.0 : 0.0;
+  double c = 0.0;
+#define DGB_INI(T_) if (q.id == T_::id) c = T_::initial(q.p, DIM, x);
+  DGB_FOR_EACH_FV_PROBLEM(DGB_INI)
+#undef DGB_INI
+  return c;
+}
+static bool fv_problem_column_invariant(int id) {
+#define DGB_CI(T_) if (id == T_::id) return T_::column_invariant;
+  DGB_FOR_EACH_FV_PROBLEM(DGB_CI)
+#undef DGB_CI
+  return false;
 }
 
 static constexpr int FBX = 128, FBY = 4;
@@ -349,10 +366,7 @@ __global__ void __launch_bounds__(256) k_fv_shell(const __grid_constant__ dgb_vi
 // earlier, so they hit L1 (tile interior) or L2 (tile edge). HBM traffic stays at 8 B read + 8 B write per cell;
 // the CFL max is reduced per thread over its column, then by warp shuffles, then once per CTA.
 template<int PROBLEM>
-__device__ __forceinline__ void fv_velocity3(const FvProblem& q, const double* x, double* u) {
-  if (PROBLEM == 1) { u[0] = -q.p[0]*(x[1]-0.5); u[1] = q.p[0]*(x[0]-0.5); u[2] = 0.0; }
-  else { u[0] = q.p[0]; u[1] = q.p[1]; u[2] = q.p[2]; }
-}
+__device__ __forceinline__ void fv_velocity3(const FvProblem& q, const double* x, double* u) { FvProblemById<PROBLEM>::type::velocity(q.p, x, u); }
 
 template<int MODE, int PROBLEM, bool REDUCE_ONLY, int PF, int BX, int BY>
 __global__ void __launch_bounds__(BX*BY) k_fv_march(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a, const int zc) {
@@ -1084,8 +1098,10 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     if (stg == 0 && !(variant == 0 || variant == 3)) stg = 2;
     const int zc = fv->zchunk > 0 ? fv->zchunk : auto_zchunk(a.region.size, wide ? 128 : 32, wide ? 4 : 8);
     const bool exact = fv->mode == DGB_FV_EXACT;
-    const int pb = fv->problem.id == 1 ? 1 : 0;
-    const bool ring = !exact && !(REDUCE_ONLY || a.update || !a.cnew) && variant != 99;
+    const int pb = fv->problem.id;
+    // the ring kernel evaluates the x/y face factors once per COLUMN: only for problems that declare a z-independent velocity and a
+    // constant inflow value (column_invariant); every other registered problem runs on the general z-march kernel
+    const bool ring = !exact && !(REDUCE_ONLY || a.update || !a.cnew) && variant != 99 && fv_problem_column_invariant(pb);
     if (!REDUCE_ONLY) {
       int bx = 128, by = 4;                                                   // the z-march kernels
       if (ring) switch (variant) { case 2: bx = 64; by = 4; break; case 3: case 7: bx = 128; by = 4; break; case 9: bx = 64; by = 8; break; default: bx = 32; by = 8; }
@@ -1096,11 +1112,12 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     { dim3 mblock(BX_, BY_, 1);                                                                                      \
       dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
       k_fv_march<MODE_, PROB_, REDUCE_ONLY, PF_, BX_, BY_><<<mgrid, mblock, 0, stream>>>(v, a, zc); }
-    if (exact) {
-      if (pb) DGB_MARCH(DGB_FV_EXACT, 1, 4, 128, 4) else DGB_MARCH(DGB_FV_EXACT, 0, 4, 128, 4)
-    } else if (REDUCE_ONLY || a.update || !a.cnew) {
-      if (pb) DGB_MARCH(DGB_FV_SEPARABLE, 1, 4, 128, 4) else DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4)
-    } else {
+#define DGB_MARCH_ANY(MODE_)                                                                                         \
+    { if (pb == 0) DGB_MARCH(MODE_, 0, 4, 128, 4) else if (pb == 1) DGB_MARCH(MODE_, 1, 4, 128, 4) else DGB_MARCH(MODE_, 2, 4, 128, 4) }
+    static_assert(DGB_FV_PROBLEMS == 3, "add the new problem to DGB_MARCH_ANY");
+    if (exact) DGB_MARCH_ANY(DGB_FV_EXACT)
+    else if (!ring) DGB_MARCH_ANY(DGB_FV_SEPARABLE)
+    else {
 #define DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, ZP_, STG_)                                                              \
     { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, ZP_, STG_> : k_fv_ring<0, D_, BX_, BY_, MINB_, ZP_, STG_>;        \
       DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));                    \
@@ -1121,11 +1138,11 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
         case 3: DGB_RING(6, 128, 4, 2, true, true) break;                  // production choice, wide regions
         case 7: DGB_RING(8, 128, 4, 2, false, false) break;
         case 9: DGB_RING(8, 64, 8, 2, false, false) break;
-        case 99: if (pb) DGB_MARCH(DGB_FV_SEPARABLE, 1, 4, 128, 4) else DGB_MARCH(DGB_FV_SEPARABLE, 0, 4, 128, 4) break;   // the general kernel, for comparison
       }
 #undef DGB_RING
 #undef DGB_RING_LAUNCH
     }
+#undef DGB_MARCH_ANY
 #undef DGB_MARCH
   } else {
     if (!REDUCE_ONLY) { const int info[8] = { DGB_FV_KERNEL_STEP2D, -1, FBX, FBY, 0, 1, 0, 0 }; for (int k = 0; k < 8; ++k) fv->kinfo[k] = info[k]; }
@@ -1219,7 +1236,7 @@ extern "C" {
 int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host, int nparams, int mode, dgb_comm* comm, dgb_fv** out) {
   return guarded([&]() -> int {
     if (int rc = require_device()) return rc;
-    if (problem < 0 || problem > 1) throw ArgError("unknown problem id");
+    if (problem < 0 || problem >= DGB_FV_PROBLEMS) throw ArgError("unknown problem id (the compiled-in FV problems are listed in dgb_functors.cuh)");
     if (mode != DGB_FV_EXACT && mode != DGB_FV_SEPARABLE) throw ArgError("unknown fv mode");
     if (nparams > 12) throw ArgError("at most 12 problem parameters");
     std::unique_ptr<dgb_fv> fv(new dgb_fv);

@@ -62,8 +62,16 @@ __global__ void __launch_bounds__(BX) k_entities(const __grid_constant__ dgb_vie
   uint32_t idx = entity_index(v, c, s.kind, coord)*o.block + o.offset;
   const uint32_t didx = uint32_t(c.box[DGB_BOX_OVERLAPFRONT].size[0])*o.block;
   const bool geo = o.lower || o.upper || o.center || o.volume;
+  const int rows = min(ENT_ROWS, b.size[1]-i1);
   double ll[3] = {0, 0, 0}, ur[3] = {0, 0, 0};
-  // yaspgridentity.hh:270-274 (no wrap for 0 < codim), :491-514 (codim 0 wraps), AxisAlignedCubeGeometry
+  // yaspgridentity.hh:270-274 (no wrap for 0 < codim), :491-514 (codim 0 wraps), AxisAlignedCubeGeometry.
+  // ALL coordinate loads of the thread (tensor-product tables) are issued up front, before the first store: ncu showed the
+  // graded 384^3 case stalled on the per-row table loads (long scoreboard), not on DRAM (profiles/r02_sweeps_ncu.json)
+  double y1[ENT_ROWS+1];
+  if (geo) {
+#pragma unroll
+    for (int r = 0; r <= ENT_ROWS; ++r) y1[r] = (dim > 1 && r <= rows) ? vertex_coord(v, 1, coord[1]+r) : 0.0;
+  }
   auto axis = [&](int i) {
     const bool ext = c.shift >> i & 1u;
     ll[i] = vertex_coord(v, i, coord[i]);
@@ -71,28 +79,34 @@ __global__ void __launch_bounds__(BX) k_entities(const __grid_constant__ dgb_vie
     if (c.codim == 0) { const double sh = periodic_shift(v, i, coord[i]); if (sh != 0.0) { ll[i] += sh; ur[i] += sh; } }
   };
   if (geo) { axis(0); if (dim > 2) axis(2); }
-  const int rows = min(ENT_ROWS, b.size[1]-i1);
-  for (int r = 0; r < rows; ++r) {
-    if (o.index) o.index[pos] = idx;
-    if (o.ptype) o.ptype[pos] = partition_type(v, c, coord);
-    if (o.coord) { long long p = pos; for (int i = 0; i < dim; ++i) { o.coord[p] = coord[i]; p += s.n; } }
-    if (geo) {
-      if (dim > 1) axis(1);
-      double vol = 1.0;
-      long long p = pos;
+  const bool ext1 = c.shift >> 1 & 1u;
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if (i < dim) {
-          if (o.lower) o.lower[p] = ll[i];
-          if (o.upper) o.upper[p] = ur[i];
-          if (o.center) o.center[p] = 0.5*(ll[i]+ur[i]);
-          if (c.shift >> i & 1u) vol *= ur[i]-ll[i];
-          p += s.n;
+  for (int r = 0; r < ENT_ROWS; ++r) {
+    if (r < rows) {
+      if (o.index) o.index[pos] = idx;
+      if (o.ptype) o.ptype[pos] = partition_type(v, c, coord);
+      if (o.coord) { long long p = pos; for (int i = 0; i < dim; ++i) { o.coord[p] = coord[i]; p += s.n; } }
+      if (geo) {
+        if (dim > 1) {
+          ll[1] = y1[r]; ur[1] = ext1 ? y1[r+1] : y1[r];
+          if (c.codim == 0) { const double sh = periodic_shift(v, 1, coord[1]); if (sh != 0.0) { ll[1] += sh; ur[1] += sh; } }
         }
+        double vol = 1.0;
+        long long p = pos;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (i < dim) {
+            if (o.lower) o.lower[p] = ll[i];
+            if (o.upper) o.upper[p] = ur[i];
+            if (o.center) o.center[p] = 0.5*(ll[i]+ur[i]);
+            if (c.shift >> i & 1u) vol *= ur[i]-ll[i];
+            p += s.n;
+          }
+        }
+        if (o.volume) o.volume[pos] = vol;
       }
-      if (o.volume) o.volume[pos] = vol;
+      pos += b.size[0]; idx += didx; ++coord[1];
     }
-    pos += b.size[0]; idx += didx; ++coord[1];
   }
 }
 
@@ -103,6 +117,7 @@ __global__ void __launch_bounds__(BX) k_entities(const __grid_constant__ dgb_vie
 // (row length of the swept box / of the enclosing overlapfront box), so an entity costs two adds and one coalesced store.
 static constexpr int IDX_ROWS = 32;
 
+template<int IDX_ROWS>
 __global__ void __launch_bounds__(BX) k_index_rows(const __grid_constant__ dgb_view v, const SweepGeom s, uint32_t block, uint32_t offset,
                                                    uint32_t* __restrict__ out) {
   const dgb_component& c = v.comp[s.comp];
@@ -142,7 +157,7 @@ struct FaceOut { uint8_t *neighbor, *boundary; int32_t *outside, *bsi; double *c
 // A thread owns one column (i0, i2) and walks FACE_ROWS rows (i1): everything that belongs to axes 0 and 2 (vertex
 // coordinates incl. the tensor-product table loads, periodic shifts, neighbour / boundary flags) is computed once per
 // column; per row only axis 1 is refreshed and the output positions advance by the row length.
-static constexpr int FACE_ROWS_DEFAULT = 2;     // measured (256^3, 48 output streams): 1: 0.76 ms, 2: 0.74, 4: 1.06, 8: 1.29, 16: 0.89
+static constexpr int FACE_ROWS_DEFAULT = 2;     // round 1, per-row loads (256^3, 48 output streams): 1: 0.76 ms, 2: 0.74, 4: 1.06, 8: 1.29, 16: 0.89
 
 template<int FACE_ROWS>
 __global__ void __launch_bounds__(BX) k_intersections(const __grid_constant__ dgb_view v, const SweepGeom s, const FaceOut o) {
@@ -156,8 +171,16 @@ __global__ void __launch_bounds__(BX) k_intersections(const __grid_constant__ dg
   long long pos = s.base + ((long long)i2*b.size[1] + i1)*b.size[0] + i0;
   int inside = int(entity_index(v, c, s.kind, coord));
   const bool geo = o.center || o.volume;
+  const int rows = min(FACE_ROWS, b.size[1]-i1);
   double ll[3] = {0, 0, 0}, ur[3] = {0, 0, 0};
   bool nb[6], bd[6];
+  // every coordinate load of the thread (tensor-product tables: x, z and the rows+1 y vertices it walks) is issued before the
+  // first store; ncu had the graded 384^3 sweep waiting on the per-row loads (long scoreboard 10.6 cycles per issue, DRAM 55 %)
+  double y1[FACE_ROWS+1];
+  if (geo) {
+#pragma unroll
+    for (int r = 0; r <= FACE_ROWS; ++r) y1[r] = (dim > 1 && r <= rows) ? vertex_coord(v, 1, coord[1]+r) : 0.0;
+  }
   auto axis = [&](int i) {
     if (geo) {
       const double sh = periodic_shift(v, i, coord[i]);
@@ -170,42 +193,52 @@ __global__ void __launch_bounds__(BX) k_intersections(const __grid_constant__ dg
   axis(0);
   if (dim > 2) axis(2);
   int stride[3] = { 1, of.size[0], of.size[0]*of.size[1] };
-  const int rows = min(FACE_ROWS, b.size[1]-i1);
-  for (int r = 0; r < rows; ++r) {
-    if (dim > 1) axis(1);
-    long long pf = pos;                       // position in the one-value-per-face arrays (face-major)
-    long long pc = pos;                       // position in the face centre array ((face, axis)-major)
 #pragma unroll
-    for (int dir = 0; dir < 3; ++dir) {
-      if (dir < dim) {
+  for (int r = 0; r < FACE_ROWS; ++r) {
+    if (r < rows) {
+      if (dim > 1) {
+        if (geo) {
+          const double sh = periodic_shift(v, 1, coord[1]);
+          ll[1] = y1[r]; ur[1] = y1[r+1];
+          if (sh != 0.0) { ll[1] += sh; ur[1] += sh; }
+        }
+        nb[2] = face_neighbor(v, coord, 1, 0); nb[3] = face_neighbor(v, coord, 1, 1);
+        bd[2] = face_boundary(v, coord, 1, 0); bd[3] = face_boundary(v, coord, 1, 1);
+      }
+      long long pf = pos;                       // position in the one-value-per-face arrays (face-major)
+      long long pc = pos;                       // position in the face centre array ((face, axis)-major)
 #pragma unroll
-        for (int side = 0; side < 2; ++side) {
-          const int k = 2*dir + side;
-          if (o.neighbor) o.neighbor[pf] = nb[k];
-          if (o.boundary) o.boundary[pf] = bd[k];
-          // outside index = inside index -+ superincrement(dir) (yaspgridintersection.hh:40-57, ygrid.hh:362-366)
-          if (o.outside) o.outside[pf] = nb[k] ? inside + (side ? stride[dir] : -stride[dir]) : -1;
-          if (o.bsi) o.bsi[pf] = bd[k] ? boundary_segment_index(v, coord, dir, side) : -1;
-          if (geo) {
-            // yaspgridintersection.hh:232-269: the face is flat in `dir` at vertex coord+side, wrapped like the cell
-            double vol = 1.0;
+      for (int dir = 0; dir < 3; ++dir) {
+        if (dir < dim) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-              if (i < dim) {
-                double lo = ll[i], hi = ur[i];
-                if (i == dir) { lo = side ? ur[i] : ll[i]; hi = lo; }
-                else vol *= hi-lo;
-                if (o.center) o.center[pc] = 0.5*(lo+hi);
-                pc += s.n;
+          for (int side = 0; side < 2; ++side) {
+            const int k = 2*dir + side;
+            if (o.neighbor) o.neighbor[pf] = nb[k];
+            if (o.boundary) o.boundary[pf] = bd[k];
+            // outside index = inside index -+ superincrement(dir) (yaspgridintersection.hh:40-57, ygrid.hh:362-366)
+            if (o.outside) o.outside[pf] = nb[k] ? inside + (side ? stride[dir] : -stride[dir]) : -1;
+            if (o.bsi) o.bsi[pf] = bd[k] ? boundary_segment_index(v, coord, dir, side) : -1;
+            if (geo) {
+              // yaspgridintersection.hh:232-269: the face is flat in `dir` at vertex coord+side, wrapped like the cell
+              double vol = 1.0;
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                if (i < dim) {
+                  double lo = ll[i], hi = ur[i];
+                  if (i == dir) { lo = side ? ur[i] : ll[i]; hi = lo; }
+                  else vol *= hi-lo;
+                  if (o.center) o.center[pc] = 0.5*(lo+hi);
+                  pc += s.n;
+                }
               }
+              if (o.volume) o.volume[pf] = vol;
             }
-            if (o.volume) o.volume[pf] = vol;
+            pf += s.n;
           }
-          pf += s.n;
         }
       }
+      pos += b.size[0]; inside += of.size[0]; ++coord[1];
     }
-    pos += b.size[0]; inside += of.size[0]; ++coord[1];
   }
 }
 
@@ -499,8 +532,11 @@ int dgb_mapper_index(const dgb_view* v, const dgb_mapper* m, int codim, int pity
   if (codim < 0 || codim > v->dim) return fail(DGB_EARG, "bad codim");
   if (m->offset[codim] == DGB_INVALID_OFFSET) return fail(DGB_EARG, "codim not contained in the mapper layout");
   EntityOut o{}; o.index = d_out; o.block = m->block[codim]; o.offset = m->offset[codim];
-  return for_each_component(*v, codim, pitype, IDX_ROWS, [&](const SweepGeom& s, dim3 grid) {
-    k_index_rows<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o.block, o.offset, d_out);
+  static const int rows = [] { const char* e = getenv("DGB_IDX_ROWS"); const int r = e ? atoi(e) : 64; return r == 32 || r == 128 ? r : 64; }();
+  return for_each_component(*v, codim, pitype, rows, [&](const SweepGeom& s, dim3 grid) {
+    if (rows == 32) k_index_rows<32><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o.block, o.offset, d_out);
+    else if (rows == 128) k_index_rows<128><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o.block, o.offset, d_out);
+    else k_index_rows<64><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o.block, o.offset, d_out);
   });
 }
 

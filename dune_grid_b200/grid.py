@@ -22,6 +22,24 @@ InteriorEntity, BorderEntity, OverlapEntity, FrontEntity, GhostEntity = range(5)
 ForwardCommunication, BackwardCommunication = 0, 1
 
 
+# compiled-in sweep functors (include/dgb.h DGB_FUNCTOR_*)
+FUNCTORS = {"midpoint_exp_norm": 0, "gauss5_exp_norm": 1, "boundary_flux_x": 2, "measure": 3}
+
+
+def functors():
+    """the registry as the library reports it: {id: (name, has_element_body, has_intersection_body)}"""
+    n = C.c_int(0)
+    check(lib.dgb_functor_count(C.byref(n)))
+    out = {}
+    for i in range(64):
+        name, e, f = C.c_char_p(), C.c_int(0), C.c_int(0)
+        if lib.dgb_functor_info(i, C.byref(name), C.byref(e), C.byref(f)) == 0:
+            out[i] = (name.value.decode(), bool(e.value), bool(f.value))
+        if len(out) == n.value:
+            break
+    return out
+
+
 def _torch():
     import torch
     return torch
@@ -254,6 +272,28 @@ class GridView:
                                                 _ptr(r["outside"]), _ptr(r["boundarySegmentIndex"]),
                                                 _ptr(r.get("center")), _ptr(r.get("volume")), _stream()))
         return r
+
+    # ---- functor sweeps (compiled-in device functors, csrc/dgb_functors.cuh) --------------------------------------
+    def _for_each(self, faces, functor, args, partition, values):
+        _require_cuda()
+        torch = _torch()
+        fid = FUNCTORS[functor] if isinstance(functor, str) else int(functor)
+        a = np.ascontiguousarray(args if args is not None else [], dtype=np.float64)
+        n = self.size(0, partition)
+        per = torch.empty((2 * self.dim, n) if faces else (n,), dtype=torch.float64, device="cuda") if values else None
+        total = torch.zeros(1, dtype=torch.float64, device="cuda")
+        f = lib.dgb_for_each_intersection if faces else lib.dgb_for_each_element
+        check(f(C.byref(self.v), partition, fid, a.ctypes.data_as(C.POINTER(C.c_double)), a.size, _ptr(per), _ptr(total), _stream()))
+        return (total, per) if values else total
+
+    def forEachElement(self, functor, args=None, partition=All_Partition, values=False):
+        """sum over `for e in elements(gv, partition)` of the compiled-in functor's element body, as ONE fused kernel; returns a
+        1-element CUDA tensor (and the per-element values with values=True). functor: id or a name of FUNCTORS"""
+        return self._for_each(False, functor, args, partition, values)
+
+    def forEachIntersection(self, functor, args=None, partition=All_Partition, values=False):
+        """sum over `for e in elements(gv): for is in intersections(gv, e)` of the functor's intersection body (values: (2dim, n))"""
+        return self._for_each(True, functor, args, partition, values)
 
     def centerUnitOuterNormal(self, k):
         """YaspIntersection::centerUnitOuterNormal (yaspgridintersection.hh:177-182): +-e_dir, independent of the cell"""

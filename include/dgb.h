@@ -209,6 +209,24 @@ int dgb_geogrid_intersections(const dgb_view* v, int pitype, int deformation, co
 int dgb_geogrid_volume(const dgb_view* v, int pitype, int deformation, const double* params_host, int nparams,
                        int nqp, const double* qp_host, const double* weights_host, double* d_sum, void* stream);
 
+/* ---- functor sweeps: `for (e : elements(gv, pitype)) sum += body(e)` and `for (e : ...) for (is : intersections(gv, e)) sum +=
+ *      body(is)` (rangegenerators.hh:845,881) as ONE fused device kernel each (sweep + functor + reduction). The loop bodies are
+ *      compiled-in device functors selected by id - structs in csrc/dgb_functors.cuh with element(ctx) / face(ctx) methods that see
+ *      what the reference's entity / geometry / intersection facades offer; adding one = adding a struct there and listing it in
+ *      the registry macro. No host callbacks, no CPU fallback. Shipped: the three loops of doc/recipes/recipe-integration.cc.
+ *      d_per_element[e] / d_per_face[k*n + e] (iteration order of the partition; NULL = not stored) receive the bodies' values,
+ *      *d_sum (device double; NULL = no reduction) their sum in a fixed, reproducible order. args_host: <= 16 doubles. ---------- */
+enum { DGB_FUNCTOR_MIDPOINT_EXP_NORM = 0,      /* recipe-integration.cc:90-98   u(center)*volume, u(x) = exp(|x|) */
+       DGB_FUNCTOR_GAUSS5_EXP_NORM = 1,        /* recipe-integration.cc:100-111 order-5 Gauss rule of the same u */
+       DGB_FUNCTOR_BOUNDARY_FLUX_X = 2,        /* recipe-integration.cc:113-124 faces without neighbour: center . normal * volume */
+       DGB_FUNCTOR_MEASURE = 3 };              /* args[0] * volume of the element / of the face */
+int dgb_functor_count(int* n);
+int dgb_functor_info(int functor_id, const char** name, int* has_element_body, int* has_intersection_body);
+int dgb_for_each_element(const dgb_view* v, int pitype, int functor_id, const double* args_host, int nargs,
+                         double* d_per_element, double* d_sum, void* stream);
+int dgb_for_each_intersection(const dgb_view* v, int pitype, int functor_id, const double* args_host, int nargs,
+                              double* d_per_face, double* d_sum, void* stream);
+
 /* ---- communication: GridView::communicate(DataHandle, InterfaceType, CommunicationDirection) (gridview.hh:334,
  *      yaspgrid.hh:1470-1730) for flat arrays indexed by a mapper, the shape of the reference's own
  *      NumPyCommDataHandle (dune/python/grid/numpycommdatahandle.hh:41-142). Collective over all ranks. ---------- */
@@ -239,6 +257,12 @@ int dgb_comm_last_bytes(const dgb_grid* g, int64_t* bytes);
 typedef struct dgb_fv dgb_fv;
 enum { DGB_FV_EXACT = 0,           /* per-cell arithmetic in the reference order: bit-identical to the CPU oracle */
        DGB_FV_SEPARABLE = 1 };     /* tensor-product factorised face factors: <= 1e-13 relative */
+/* `problem` selects a compiled-in transport problem (velocity, inflow value, initial value: the FV registry of
+ * csrc/dgb_functors.cuh): 0 constant velocity, 1 rotation in the x-y plane, 2 shear flow with a z-dependent velocity. The
+ * production kernel k_fv_ring evaluates the x/y face factors once per COLUMN of cells, so it REQUIRES a velocity that does not
+ * depend on z and a constant inflow value (`column_invariant` in the registry; problems 0 and 1); any other problem is routed to
+ * the general kernel k_fv_march, which evaluates the functor per face. All problems must be time independent: the CFL bound
+ * reduced while step n runs is the one step n+2 uses. */
 int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host, int nparams, int mode,
                   dgb_comm* comm, dgb_fv** out);
 /* dgb_fv_destroy is COLLECTIVE on a multi-rank grid whose steps used the fused exchange (like MPI_Win_free): every rank closes

@@ -132,6 +132,10 @@ FV_CASES = [
     (make_cfg(dim=3, N=(12, 12, 12), periodic=3, mode=1, lower=(-1.0, 0.0, 0.5), upper=(1.0, 1.0, 2.0)), 8, 1,
      [1.5, 0, 0, 0.25, 0.0, 0.5, 1.2, 0.1, 0.6]),
     (make_cfg(dim=2, N=(16, 16), refine=1), 4, 1, [1.0, 0, 0, 0.0, 0.5, 0.5, 0.0, 0.1, 0.3]),
+    # problem 2 of the FV registry: shear flow whose velocity depends on z - not column invariant, runs on the general kernel
+    (make_cfg(dim=3, N=(14, 12, 16), periodic=2), 1, 2, [0.9, -0.4, 0.7, 0.3, 0.5, 0.5, 0.5, 0.1, 0.45]),
+    (make_cfg(dim=3, N=(16, 8, 12)), 2, 2, [-1.1, 0.5, 0.8, 0.2, 0.4, 0.5, 0.6, 0.1, 0.4]),
+    (make_cfg(dim=2, N=(24, 18)), 1, 2, [0.9, -0.4, 0.7, 0.3, 0.5, 0.5, 0.0, 0.1, 0.45]),
 ]
 
 
@@ -218,7 +222,9 @@ def test_fv_separable_mode_within_1e13(cfg, P, problem, params):
     steps = 4
     ref = [w.fv_init(r, lvl, problem, params) for r in range(P)]
     ref_dts = [w.fv_step(lvl, problem, params, ref) for _ in range(steps)]
-    got, dts, _ = run_fv(cfg, P, problem, params, "separable", steps)
+    got, dts, _, infos = run_fv(cfg, P, problem, params, "separable", steps, want_info=True)
+    if cfg["dim"] == 3:         # registry routing: column-invariant problems on the ring kernel, the others on the general one
+        assert all(i["kind"] == ("march" if problem == 2 else "ring") for i in infos), infos
     for a, b in zip(dts, ref_dts):
         assert abs(a - b) <= 1e-13 * abs(b)
     scale = max(np.abs(x).max() for x in ref)
