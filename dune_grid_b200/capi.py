@@ -102,6 +102,7 @@ _SIG = {
     "dgb_fv_create": (_i, [_vp, _i, _i, C.POINTER(C.c_double), _i, _i, _vp, C.POINTER(_vp)]),
     "dgb_fv_destroy": (_i, [_vp]), "dgb_fv_abandon": (_i, [_vp]), "dgb_fv_init_field": (_i, [_vp, _vp, _vp]),
     "dgb_fv_register_fields": (_i, [_vp, C.POINTER(_vp), _i, _vp]), "dgb_fv_registered_fields": (_i, [_vp, C.POINTER(_i)]),
+    "dgb_fv_fence": (_i, [_vp, _vp]),
     "dgb_fv_kernel_info": (_i, [_vp, C.POINTER(C.c_int32)]), "dgb_fv_host_path": (_i, [_vp, C.POINTER(_i)]),
     "dgb_fv_step": (_i, [_vp, _vp, _vp, _vp]), "dgb_fv_last_dt": (_i, [_vp, C.POINTER(C.c_double), _vp]),
     "dgb_fv_update": (_i, [_vp, _vp, _vp, _vp]),

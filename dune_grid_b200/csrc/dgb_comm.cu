@@ -168,6 +168,9 @@ static void add_boxes(const dgb_grid* g, int level, int codim, int which, const 
         b.peer_of_origin[i] = i < lb.dim ? pof.origin[i] : 0; b.peer_of_size[i] = i < lb.dim ? pof.size[i] : 1;
       }
       b.peer = e.rank;
+      int nz = 0, ax = -1;
+      for (int i = 0; i < lb.dim; ++i) if (e.delta[i] != 0) { ++nz; ax = i; }
+      b.face = (nz == 1) ? 2*ax + (e.delta[ax] > 0 ? 1 : 0) : -1;
     }
     b.buf_offset = 0;
     (void)per_entity_codim;
@@ -367,14 +370,30 @@ int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d
   return DGB_OK;
 }
 
+int plan_unpack_boxes(CommPlan& plan, const std::vector<PlanBox>& host, PlanBox* dev, const double* buf, double* d_array, cudaStream_t stream) {
+  if (host.empty()) return DGB_OK;
+  const int32_t items[1] = {1};
+  double* arrays[1] = { d_array };
+  ArrayTable at; if (int rc = make_table(plan, arrays, items, 1, at)) return rc;
+  launch_boxes(plan, at, DGB_OP_SET + 1, host, dev, const_cast<double*>(buf), nullptr, stream);
+  DGB_CUDA(cudaGetLastError());
+  return DGB_OK;
+}
+
 // ---- fused exchange over peer-mapped memory: set-up ------------------------------------------------------------------
 // what every rank publishes: the IPC handle of its block and, per sender rank, the offset (in doubles) of that sender's
 // segment in the receive buffers (-1: no message from that rank)
 struct FusedInfo { cudaIpcMemHandle_t handle; long long segOffset[64]; long long segCount[64]; long long recvTotal; int ok; int pad; };
 
 void FusedState::release_direct() {
-  for (auto& d : direct) { if (d.dPack) cudaFree(d.dPack); if (d.dDst) cudaFree(d.dDst); if (d.dRow) cudaFree(d.dRow); if (d.dPlane) cudaFree(d.dPlane); }
+  for (auto& d : direct) {
+    if (d.dPack) cudaFree(d.dPack); if (d.dDst) cudaFree(d.dDst); if (d.dRow) cudaFree(d.dRow); if (d.dPlane) cudaFree(d.dPlane);
+    if (d.dHybrid) cudaFree(d.dHybrid); if (d.dRowH) cudaFree(d.dRowH); if (d.dPlaneH) cudaFree(d.dPlaneH);
+    for (int k = 0; k < 2; ++k) if (d.dDstH[k]) cudaFree(d.dDstH[k]);
+  }
   direct.clear();
+  if (dXRecv) cudaFree(dXRecv);
+  dXRecv = nullptr; nXRecv = 0; hostXRecv.clear(); hybridOk = false; xface[0] = XFace(); xface[1] = XFace();
 }
 
 void FusedState::release(bool free_block) {
@@ -494,6 +513,10 @@ int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStre
   if (ok && soft(cudaMalloc(&fs.dPack, 2*sizeof(FusedPack)), "cudaMalloc(FusedPack)"))
     soft(cudaMemcpy(fs.dPack, pk, 2*sizeof(FusedPack), cudaMemcpyHostToDevice), "cudaMemcpy(FusedPack)");
   fs.hostPack[0] = pk[0]; fs.hostPack[1] = pk[1];
+  for (int k = 0; k < 2; ++k) {                       // host copy of the buffered destinations (hybrid form of registered fields)
+    fs.hostDst[k].assign(plan.nSendBoxes, nullptr);
+    if (ok && plan.nSendBoxes) cudaMemcpy(fs.hostDst[k].data(), fs.dDst[k], plan.nSendBoxes*sizeof(double*), cudaMemcpyDeviceToHost);
+  }
   if (multi) {                                           // every rank must reach the same verdict: min over ranks of 1/0
     double v = ok ? 1.0 : 0.0;
     double* dScratch = nullptr;
@@ -606,21 +629,56 @@ int fused_register(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaS
     FusedPack pk[2] = { fs.hostPack[0], fs.hostPack[1] };
     for (int k = 0; k < 2; ++k) { pk[k].dst = d.dDst; pk[k].dstRow = d.dRow; pk[k].dstPlane = d.dPlane; }
     ok = ok && up(reinterpret_cast<void**>(&d.dPack), pk, 2*sizeof(FusedPack));
+    // hybrid: x-face boxes keep their place in the receiver's exchange buffer (box-linear), everything else goes to the field
+    std::vector<int> rowH(row), planeH(plane);
+    for (int b = 0; b < nb; ++b) if (plan.hostSend[b].face == 0 || plan.hostSend[b].face == 1) { rowH[b] = plan.hostSend[b].size[0]; planeH[b] = plan.hostSend[b].size[0]*plan.hostSend[b].size[1]; }
+    ok = ok && up(reinterpret_cast<void**>(&d.dRowH), rowH.data(), nb*sizeof(int)) && up(reinterpret_cast<void**>(&d.dPlaneH), planeH.data(), nb*sizeof(int));
+    FusedPack ph[2] = { fs.hostPack[0], fs.hostPack[1] };
+    for (int k = 0; k < 2; ++k) {
+      std::vector<double*> dstH(dst);
+      for (int b = 0; b < nb; ++b) if (plan.hostSend[b].face == 0 || plan.hostSend[b].face == 1) dstH[b] = fs.hostDst[k][b];
+      ok = ok && up(reinterpret_cast<void**>(&d.dDstH[k]), dstH.data(), nb*sizeof(double*));
+      ph[k].dst = d.dDstH[k]; ph[k].dstRow = d.dRowH; ph[k].dstPlane = d.dPlaneH;
+    }
+    ok = ok && up(reinterpret_cast<void**>(&d.dHybrid), ph, 2*sizeof(FusedPack));
   }
-  if (multi) {                                           // same verdict everywhere
-    double v = ok ? 1.0 : 0.0;
+  // hybrid form: this rank's x-face receive boxes must be whole faces, one cell thick (overlap 1), at most one per side
+  bool hyb = ok;
+  std::vector<PlanBox> xrecv;
+  FusedState::XFace xf[2];
+  for (auto& b : plan.hostRecv) if (b.face == 0 || b.face == 1) {
+    if (b.size[0] != 1 || xf[b.face].on) hyb = false;
+    xf[b.face].on = true; xf[b.face].buf_offset = b.buf_offset; xf[b.face].y0 = b.origin[1]; xf[b.face].z0 = b.origin[2]; xf[b.face].ny = b.size[1];
+    xrecv.push_back(b);
+  }
+  for (auto& b : plan.hostSend) if ((b.face == 0 || b.face == 1) && b.size[0] != 1) hyb = false;
+  bool hyb_all = hyb && ok;
+  if (multi) {                                           // same verdicts everywhere: (registered, hybrid) = min over ranks
+    double v[2] = { ok ? 1.0 : 0.0, hyb_all ? 1.0 : 0.0 };
     double* dScratch = nullptr;
-    if (cudaMalloc(&dScratch, sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(DGB_ECUDA, "fused_register: cudaMalloc"); }
-    cudaMemcpyAsync(dScratch, &v, sizeof(double), cudaMemcpyHostToDevice, stream);
-    const bool sent = g_nccl.AllReduce(dScratch, dScratch, 1, ncclDouble, ncclMin, comm->comm, stream) == ncclSuccess;
-    cudaMemcpyAsync(&v, dScratch, sizeof(double), cudaMemcpyDeviceToHost, stream);
+    if (cudaMalloc(&dScratch, 2*sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(DGB_ECUDA, "fused_register: cudaMalloc"); }
+    cudaMemcpyAsync(dScratch, v, 2*sizeof(double), cudaMemcpyHostToDevice, stream);
+    const bool sent = g_nccl.AllReduce(dScratch, dScratch, 2, ncclDouble, ncclMin, comm->comm, stream) == ncclSuccess;
+    cudaMemcpyAsync(v, dScratch, 2*sizeof(double), cudaMemcpyDeviceToHost, stream);
     const bool synced = cudaStreamSynchronize(stream) == cudaSuccess;
     cudaFree(dScratch);
     if (!sent || !synced) return fail(DGB_ENCCL, "fused_register: verdict all-reduce failed");
-    ok = v > 0.5;
+    ok = v[0] > 0.5; hyb_all = v[1] > 0.5;
   }
-  if (ok) fs.direct = dir;
-  else for (auto& d : dir) { if (d.dPack) cudaFree(d.dPack); if (d.dDst) cudaFree(d.dDst); if (d.dRow) cudaFree(d.dRow); if (d.dPlane) cudaFree(d.dPlane); }
+  if (ok) {
+    fs.direct = dir;
+    fs.hybridOk = hyb_all;
+    if (hyb_all) {
+      fs.xface[0] = xf[0]; fs.xface[1] = xf[1];
+      fs.hostXRecv = xrecv; fs.nXRecv = int(xrecv.size());
+      if (fs.nXRecv) {
+        if (cudaMalloc(&fs.dXRecv, fs.nXRecv*sizeof(PlanBox)) != cudaSuccess || cudaMemcpy(fs.dXRecv, xrecv.data(), fs.nXRecv*sizeof(PlanBox), cudaMemcpyHostToDevice) != cudaSuccess)
+          return fail(DGB_ECUDA, "fused_register: x-face receive boxes");
+      }
+    }
+  } else {
+    fs.direct = dir; fs.release_direct();               // frees the partly built tables
+  }
   return DGB_OK;
 }
 

@@ -23,6 +23,7 @@ struct PlanBox {
   // sender finds the receiver's copy of a cell (registered fields: stores go straight into the partner's array)
   int peer_origin[3], peer_of_origin[3], peer_of_size[3];
   int peer;
+  int face;                         // 2*axis + (partner on the high side) if the partner is a FACE neighbour (one non-zero torus offset), else -1
 };
 struct CommPlan {
   struct Segment { int peer; long long offset, count; };     // doubles
@@ -61,6 +62,9 @@ struct HaloWait { struct FusedCtl* ctl; int nranks; unsigned target; int parity;
 int plan_unpack_from(CommPlan& plan, const double* buf, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream,
                      const HaloWait* wait = nullptr);
 
+// scatter (set) a sub-list of the plan's receive boxes - `host` / `dev` hold the same boxes, disjoint - from `buf` into one array
+int plan_unpack_boxes(CommPlan& plan, const std::vector<PlanBox>& host, PlanBox* dev, const double* buf, double* d_array, cudaStream_t stream);
+
 // ---- fused exchange: the FV step kernel itself packs into the RECEIVERS' buffers through peer-mapped memory (NVLink) and
 // signals completion with a flag; no NCCL call and no second stream in the steady state (dgb_fv.cu) -------------------
 // One block per rank, shared with every other rank by CUDA IPC: control words + two receive buffers (by step parity).
@@ -91,8 +95,18 @@ struct FusedState {
   double** dDst[2] = {nullptr, nullptr};
   std::vector<void*> opened;
   FusedPack hostPack[2];                 // host copies of dPack[0..1]
+  std::vector<double*> hostDst[2];       // host copies of dDst[0..1]
   // registered fields (dgb_fv_register_fields): peers store halo cells straight into these arrays, no receive buffer, no unpack
-  struct Direct { double* field = nullptr; FusedPack* dPack = nullptr; double** dDst = nullptr; int* dRow = nullptr; int* dPlane = nullptr; };
+  // `hybrid`: like dPack, but the x-face boxes (one cell per row of the receiver: 8-byte stores into 32-byte sectors, a DRAM
+  // read-modify-write each) keep going to the receiver's contiguous exchange buffer; the receiver's NEXT step kernel reads
+  // its x neighbours from that buffer (dgb_fv.cu, FvArgs::xh) and its overlap column is refreshed only on demand
+  struct Direct { double* field = nullptr; FusedPack* dPack = nullptr; double** dDst = nullptr; int* dRow = nullptr; int* dPlane = nullptr;
+                  FusedPack* dHybrid = nullptr; double** dDstH[2] = {nullptr, nullptr}; int* dRowH = nullptr; int* dPlaneH = nullptr; };
+  // this rank's x-face receive boxes (low side, high side): where the step kernel finds the x halo in the exchange buffer
+  struct XFace { bool on = false; long long buf_offset = 0; int y0 = 0, z0 = 0, ny = 0; };
+  XFace xface[2];
+  bool hybridOk = false;                 // every rank can use the hybrid form (same verdict everywhere)
+  PlanBox* dXRecv = nullptr; int nXRecv = 0; std::vector<PlanBox> hostXRecv;      // the x-face receive boxes, for the on-demand unpack
   std::vector<Direct> direct;
   int direct_slot(const double* p) const { for (std::size_t k = 0; k < direct.size(); ++k) if (direct[k].field == p) return int(k); return -1; }
   void release_direct();

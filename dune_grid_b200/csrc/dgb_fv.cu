@@ -82,6 +82,11 @@ struct FvArgs {
   const FusedPack* pack; // fused exchange (3-D step kernels): pack into the receivers' buffers and signal; NULL = off
   unsigned packEpoch;    // value published in the receivers' flags when this launch has delivered everything
   int packSignal;        // 1: the last CTA of this launch publishes the epoch (the last slab launch of a step); 0: pack and fence only
+  // hybrid exchange of registered fields (phase-aware ring kernel only): the x neighbours beyond the low / high end of the region
+  // are NOT read from the field's overlap column (stale) but from the exchange buffer the peer's previous step filled:
+  // xh[side][(z - xhZ0)*xhNy + (y - xhY0)]; NULL = read the field
+  const double* xh[2];
+  int xhY0[2], xhZ0[2], xhNy[2];
 };
 
 // ---- fused exchange, device side (dgb_comm.hh: FusedCtl / FusedPack) -------------------------------------------------
@@ -521,7 +526,7 @@ struct FvRingLane {
   bool active, hasHalo, loader;               // loader (A16): this thread stages a pair; g then points at the pair
 };
 // slow path extras
-struct FvRingSlow { double alt0, alt1, alt2, alt3, un4; unsigned flags; };
+struct FvRingSlow { double alt0, alt1, alt2, alt3, un4; unsigned flags; unsigned xlE, xlO, xrE, xrO; };    // x*: shared addresses of the x neighbours (pair staging)
 // reciprocal z widths of the whole stored box, passed in the kernel parameter space: indexed uniformly per CTA,
 // they are read through the constant cache (LDC) and cost no load/store-unit wavefront
 #define DGB_RWZ_MAX 1040
@@ -658,8 +663,9 @@ struct FvPairLane {
   const char* glE; const char* glO;           // loader: source of this thread's pair in the next even / odd plane to stage
   unsigned aE, aO;                            // shared address of the own cell in slot 0 for an even / odd plane of the chunk
   unsigned xE, xO, yE, yO;                    // ... of the upwind x / y neighbour (= own cell if none); slow path: yE/yO = phase step
-  unsigned ld;                                // loader: shared address of the pair in slot 0
-  bool active, loader;
+  unsigned ld;                                // loader: shared address of the pair in slot 0 (side duty: of the side cell)
+  unsigned step2;                             // loader: bytes from a plane to the next plane of the same parity in the source
+  bool active, loader, side;                  // side duty (hybrid exchange): one 8-byte x halo cell per plane from the exchange buffer
 };
 
 template<int D, int BX, int BY, int MODE, bool ZPARAM>
@@ -667,21 +673,22 @@ __device__ __forceinline__ void fv_pair_loop(FvPairLane L, const FvRingSlow S, c
                                              const int zbase, const int zn, const int kload, const int kmain,
                                              const char* lo, const char* hi) {
   constexpr int R = D+2, PX = BX+4, PY = BY+2;
-  constexpr unsigned SLOTB = PX*PY*8u, LASTB = (R-1)*SLOTB, ROWB = PX*8u;
+  constexpr unsigned SLOTB = (PX*PY + 2*PY)*8u, LASTB = (R-1)*SLOTB, ROWB = PX*8u;       // + 2*PY side cells (x halo from the exchange buffer)
   static_assert(R % 2 == 0, "even and odd planes must keep their slots");
   constexpr bool DX = MODE & 4, DY = MODE & 2, DZ = MODE & 1;
-  const long long sz8 = sz*8, step2 = 2*sz8;
+  const long long sz8 = sz*8;
   double c_below = L.c_below, c_here = 0.0;
   const bool self4 = S.un4 >= 0.0, self5 = L.un5 >= 0.0;
   unsigned uPrev = LASTB, uCur = 0u, uNxt = SLOTB;       // CTA-uniform: slot of plane k-1 (free), k, k+1
-#define DGB_PAIR_CELL(GUARD, K, AOWN, AX, AY, ANXT, GL)                                                       \
+#define DGB_PAIR_CELL(GUARD, K, AOWN, AX, AY, ANXT, GL, XL, XR)                                               \
   {                                                                                                            \
     cp_async_wait<D-1>();                                                                                      \
     __syncthreads();                                                                                           \
-    if (!(GUARD)) { if (L.loader) cp_async16_b(uPrev + L.ld, GL); }                                            \
+    if (!(GUARD)) { if (L.loader) cp_async16_b(uPrev + L.ld, GL); else if (L.side) cp_async8_b(uPrev + L.ld, GL); }   \
     else if ((K)+1+D <= kload && L.loader) stage_pair_checked(uPrev + L.ld, GL, lo, hi);                       \
+    else if ((K)+1+D < zn && L.side) cp_async8_b(uPrev + L.ld, GL);                                            \
     cp_async_commit();                                                                                         \
-    GL += step2;                                                                                               \
+    GL += L.step2;                                                                                             \
     const double c_above = (!(GUARD) || (K)+1 <= kload) ? lds_f64(uNxt + (ANXT)) : L.zhigh;                    \
     const double rw = ZPARAM ? zt.rw[zbase + (K)] : __ldg(rwz + (K));                                          \
     double upd;                                                                                                \
@@ -702,8 +709,8 @@ __device__ __forceinline__ void fv_pair_loop(FvPairLane L, const FvRingSlow S, c
       /* slow path: AY is the phase step (in bytes) towards the rows above and below */                       \
       const unsigned own = uCur + (AOWN);                                                                      \
       double val;                                                                                              \
-      val = S.alt0; if (S.flags & 16u) val = lds_f64(own - 8u);             if (S.flags & 1u) val = c_here; upd = 0.0 - val*L.f0;  \
-      val = S.alt1; if (S.flags & 32u) val = lds_f64(own + 8u);             if (S.flags & 2u) val = c_here; upd -= val*L.f1;       \
+      val = S.alt0; if (S.flags & 16u) val = lds_f64(uCur + (XL));          if (S.flags & 1u) val = c_here; upd = 0.0 - val*L.f0;  \
+      val = S.alt1; if (S.flags & 32u) val = lds_f64(uCur + (XR));          if (S.flags & 2u) val = c_here; upd -= val*L.f1;       \
       val = S.alt2; if (S.flags & 64u) val = lds_f64(own - ROWB + (AY));    if (S.flags & 4u) val = c_here; upd -= val*L.f2;       \
       val = S.alt3; if (S.flags & 128u) val = lds_f64(own + ROWB + (AY));   if (S.flags & 8u) val = c_here; upd -= val*L.f3;       \
       upd -= (self4 ? c_here : c_below)*(S.un4*rw);                                                            \
@@ -722,13 +729,13 @@ __device__ __forceinline__ void fv_pair_loop(FvPairLane L, const FvRingSlow S, c
   // an even plane of the chunk stages plane k+1+D, which is odd (D is even), and vice versa
 #pragma unroll 1
   for (; k+1 < kmain; k += 2) {
-    DGB_PAIR_CELL(false, k, L.aE, L.xE, L.yE, L.aO, L.glO)
-    DGB_PAIR_CELL(false, k+1, L.aO, L.xO, L.yO, L.aE, L.glE)
+    DGB_PAIR_CELL(false, k, L.aE, L.xE, L.yE, L.aO, L.glO, S.xlE, S.xrE)
+    DGB_PAIR_CELL(false, k+1, L.aO, L.xO, L.yO, L.aE, L.glE, S.xlO, S.xrO)
   }
 #pragma unroll 1
   for (; k < zn; k += 2) {
-    DGB_PAIR_CELL(true, k, L.aE, L.xE, L.yE, L.aO, L.glO)
-    if (k+1 < zn) DGB_PAIR_CELL(true, k+1, L.aO, L.xO, L.yO, L.aE, L.glE)
+    DGB_PAIR_CELL(true, k, L.aE, L.xE, L.yE, L.aO, L.glO, S.xlE, S.xrE)
+    if (k+1 < zn) DGB_PAIR_CELL(true, k+1, L.aO, L.xO, L.yO, L.aE, L.glE, S.xlO, S.xrO)
   }
 #undef DGB_PAIR_CELL
 }
@@ -834,6 +841,7 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     const int tx0 = a.region.origin[0]+blockIdx.x*BX, ty0 = a.region.origin[1]+by*BY;
     const int nxv = min(BX, a.region.size[0]-(int)blockIdx.x*BX), nyv = min(BY, a.region.size[1]-by*BY);
     const unsigned ring0 = (unsigned)__cvta_generic_to_shared(ring);
+    constexpr unsigned SLOTB = (SLOT + 2*PY)*8u;           // a slot = PY rows of PX cells + 2*PY side cells (x halo of the low / high side)
     // element offset of (tx0, ty0-1, cz0) = first tile cell of staged row 0; `par` folds in the alignment of the field itself
     const long long e00 = (long long)(cz0-of.origin[2])*sz + (long long)(ty0-1-of.origin[1])*sy + (tx0-of.origin[0]);
     const unsigned par = unsigned(reinterpret_cast<uintptr_t>(a.c) >> 3) + unsigned(e00);
@@ -844,9 +852,16 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     const unsigned ph0 = phase(rrO, 0), ph1 = phase(rrO, 1);
     L.aE = ring0 + unsigned(rrO*PX + 2 + ctx + int(ph0))*8u;
     L.aO = ring0 + unsigned(rrO*PX + 2 + ctx + int(ph1))*8u;
+    // hybrid exchange: does this tile touch the low / high end of the region, beyond which the x neighbour comes from the exchange
+    // buffer (a side cell of the slot) instead of the field's overlap column?
+    const bool sideLo = a.xh[0] && blockIdx.x == 0, sideHi = a.xh[1] && int(blockIdx.x) == int(gridDim.x)-1;
+    const unsigned sideCellLo = ring0 + unsigned(SLOT + rrO)*8u, sideCellHi = ring0 + unsigned(SLOT + PY + rrO)*8u;
+    const bool edgeLo = sideLo && ctx == 0, edgeHi = sideHi && ctx == nxv-1;
     // phase step towards the neighbouring rows (they have the other phase when the row stride is odd), in bytes
     const int dE = psy ? (ph0 ? -8 : 8) : 0, dO = psy ? (ph1 ? -8 : 8) : 0;
     L.xE = L.aE; L.xO = L.aO; L.yE = L.aE; L.yO = L.aO;
+    S.xlE = edgeLo ? sideCellLo : L.aE - 8u; S.xlO = edgeLo ? sideCellLo : L.aO - 8u;
+    S.xrE = edgeHi ? sideCellHi : L.aE + 8u; S.xrO = edgeHi ? sideCellHi : L.aO + 8u;
     if (pat < 8) {
       const int mx = dx ? 0 : 1, my = dy ? 2 : 3;
       int ox = dx ? -8 : 8, oy = dy ? -PX*8 : PX*8;
@@ -855,10 +870,13 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
       if (flags >> mx & 1u) ox = 0;
       if (flags >> my & 1u) oy = 0;
       L.xE = unsigned(int(L.aE) + ox); L.xO = unsigned(int(L.aO) + ox);
+      if (ox < 0 && edgeLo) L.xE = L.xO = sideCellLo;
+      if (ox > 0 && edgeHi) L.xE = L.xO = sideCellHi;
       if (oy) { L.yE = unsigned(int(L.aE) + oy + dE); L.yO = unsigned(int(L.aO) + oy + dO); }
     } else { L.yE = unsigned(dE); L.yO = unsigned(dO); }
     // loader duty: pair p of staged row rr (row 0 / nyv+1: the y neighbour rows, if stored and - fast path - on the inflow side)
-    constexpr int NP = PX/2;
+    constexpr int NP = PX/2, NLD = PY*NP;
+    static_assert(NLD + 2*PY <= BX*BY, "pair loaders and side loaders are different threads");
     const int rr = t / NP, p = t - rr*NP;
     bool need = rr >= 1 && rr <= nyv;
     if (rr == 0 || rr == nyv+1) {
@@ -871,22 +889,42 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     const char* lo = reinterpret_cast<const char*>(a.c);
     const char* hi = lo + sz*of.size[2]*8;
     const long long sz8 = sz*8;
+    L.step2 = unsigned(2*sz8);
     // source of the pair in plane 0 / plane 1 of the chunk; plane j: same parity class, (j or j-1) planes further
     const char* srcE = lo + (e00 + (long long)rr*sy - 2 - (long long)phase(rr, 0) + 2*p)*8;
     const char* srcO = lo + (e00 + (long long)rr*sy + sz - 2 - (long long)phase(rr, 1) + 2*p)*8;
-    constexpr unsigned SLOTB = SLOT*8u;
+    long long srcStep = sz8;
+    // side duty (hybrid exchange): thread NLD + side*PY + row copies the x halo cell of that tile row from the exchange buffer
+    L.side = false;
+    if (t >= NLD && t < NLD + 2*PY) {
+      const int sd = (t - NLD)/PY, srow = (t - NLD) - sd*PY;
+      bool on = (sd ? sideHi : sideLo) && srow >= 1 && srow <= nyv;
+      if (on && pat < 8) on = (sd == 0) == bool(pat & 4);            // fast path: only the inflow side is read
+      if (on) {
+        L.side = true;
+        L.ld = ring0 + unsigned(SLOT + sd*PY + srow)*8u;
+        srcStep = (long long)a.xhNy[sd]*8;
+        srcE = reinterpret_cast<const char*>(a.xh[sd] + ((long long)(cz0-a.xhZ0[sd])*a.xhNy[sd] + (ty0+srow-1-a.xhY0[sd])));
+        srcO = srcE + srcStep;
+        L.step2 = unsigned(2*srcStep);
+      }
+    }
 #pragma unroll
     for (int j = 0; j <= D; ++j) {
-      if (j <= kload && L.loader) stage_pair_checked(L.ld + j*SLOTB, (j & 1) ? srcO + (long long)(j-1)*sz8 : srcE + (long long)j*sz8, lo, hi);
+      const char* src = (j & 1) ? srcO + (long long)(j-1)*srcStep : srcE + (long long)j*srcStep;
+      if (j <= kload && L.loader) stage_pair_checked(L.ld + j*SLOTB, src, lo, hi);
+      else if (j < zn && L.side) cp_async8_b(L.ld + j*SLOTB, src);
       cp_async_commit();
     }
-    L.glO = srcO + (long long)D*sz8;                     // plane D+1 (odd), staged by the first (even) iteration
-    L.glE = srcE + (long long)(D+2)*sz8;                 // plane D+2
+    L.glO = srcO + (long long)D*srcStep;                 // plane D+1 (odd), staged by the first (even) iteration
+    L.glE = srcE + (long long)(D+2)*srcStep;             // plane D+2
     L.c_below = (cz0 > ovz0) ? __ldg(a.c + idx0 - sz) : zlow;
     // cells whose staging and reads all hit stored planes; the last plane of the ARRAY is staged with bounds checks (its last
-    // pair may stick out of the field by one element)
+    // pair may stick out of the field by one element), and so is the plane above the chunk where side cells are in use (the
+    // exchange buffer holds interior planes only)
     int kmain = max(0, min(zn, kload-D));
     if (cz0 + kload >= of.origin[2]+of.size[2]-1) kmain = max(0, min(kmain, kload-D-1));
+    if (sideLo || sideHi) kmain = max(0, min(kmain, zn-D-1));
     switch (pat) {
       case 0: fv_pair_loop<D, BX, BY, 0, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
       case 1: fv_pair_loop<D, BX, BY, 1, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
@@ -1046,6 +1084,10 @@ struct dgb_fv {
   int64_t launches = 0;
   int kinfo[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // last step kernel: see dgb_fv_kernel_info
   int hostPath = 0;              // last dgb_fv_step_host: DGB_FV_HOST_*
+  // hybrid exchange of registered fields: the x-overlap column of `xhArray` is stale, its values are in the exchange buffer of
+  // parity `xhParity` (read there by the next step, or unpacked on demand: fv_flush_xhalo)
+  bool xhPending = false; double* xhArray = nullptr; int xhParity = 0;
+  bool wantPair = false;         // the next launch_step must use the phase-aware pair staging (the only reader of FvArgs::xh)
   std::shared_ptr<CommPlan> plan;
   double* dStage[2] = {nullptr, nullptr};     // device staging for the host-buffer entry point
   double* dHostVote = nullptr;                // one device word: do all ranks take the pipelined host path?
@@ -1094,6 +1136,7 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
                        && (a.region.origin[0]-ofb.origin[0]) % 2 == 0 && a.region.size[0] % 2 == 0;
     int stg = fv->staging;
     if (stg == 3) stg = a16ok ? 1 : 2;                  // automatic
+    if (fv->wantPair) stg = 2;
     if (stg == 1 && !a16ok) stg = 0;
     if (stg == 0 && !(variant == 0 || variant == 3)) stg = 2;
     const int zc = fv->zchunk > 0 ? fv->zchunk : auto_zchunk(a.region.size, wide ? 128 : 32, wide ? 4 : 8);
@@ -1125,7 +1168,7 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
 #define DGB_RING(D_, BX_, BY_, MINB_, WITH8_, WITHA16_)                                                             \
     { dim3 mblock(BX_, BY_, 1);                                                                                      \
       dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
-      const size_t smem = size_t(D_+2)*(BX_+(stg ? 4 : 2))*(BY_+2)*sizeof(double);                                  \
+      const size_t smem = size_t(D_+2)*((BX_+(stg ? 4 : 2))*(BY_+2) + (stg == 2 ? 2*(BY_+2) : 0))*sizeof(double);  \
       if (WITHA16_ && stg == 1) DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, true, (WITHA16_ ? 1 : 2))                       \
       else if (WITH8_ && stg == 0) { if (fv->zparam) DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, true, (WITH8_ ? 0 : 2))    \
                                      else DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, false, (WITH8_ ? 0 : 2)) }            \
@@ -1339,6 +1382,21 @@ int dgb_fv_init_field(dgb_fv* fv, double* d_c, void* stream) {
   return DGB_OK;
 }
 
+// the step would run on the ring kernel (the only one that can read its x halo from the exchange buffer)
+static bool fv_ring_eligible(const dgb_fv* fv) {
+  return fv->view.dim == 3 && fv->mode == DGB_FV_SEPARABLE && fv->variant != 99 && fv_problem_column_invariant(fv->problem.id);
+}
+// on-demand unpack of the x-face receive boxes into the array whose overlap column the hybrid exchange left stale
+static int fv_flush_xhalo(dgb_fv* fv, cudaStream_t stream) {
+  if (!fv->xhPending) return DGB_OK;
+  fv->xhPending = false;
+  FusedState& fs = fv->fused;
+  const long long before = fv->plan->launches;
+  if (int rc = plan_unpack_boxes(*fv->plan, fs.hostXRecv, fs.dXRecv, fs.recv[fv->xhParity], fv->xhArray, stream)) return rc;
+  fv->launches += fv->plan->launches - before;
+  return DGB_OK;
+}
+
 // collective, once per object: try to set up the fused peer-memory exchange (see dgb_fv_step)
 static int ensure_fused(dgb_fv* fv, cudaStream_t stream) {
   if (fv->fusedTried) return DGB_OK;
@@ -1378,8 +1436,28 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
     // registered output array (dgb_fv_register_fields): the kernel stores the halo cells straight into the receivers' arrays;
     // nothing to unpack, only the one-CTA wait for all ranks' flags (+ CFL reduction) remains
     const int slot = fs.direct_slot(d_c_out);
-    a.pack = (slot >= 0 ? fs.direct[slot].dPack : fs.dPack) + parity; a.packEpoch = fs.epoch + 1u; a.packSignal = 1;
-    if (int rc = launch_step<false>(fv, a, stream)) return rc;
+    // hybrid form (registered output, ring kernel, overlap 1): the x-face boxes - one cell per row of the receiver, every store a
+    // DRAM read-modify-write of a 32-byte sector - keep going to the receiver's contiguous exchange buffer; the receiver's next
+    // step reads its x neighbours from there and its overlap column is refreshed on demand only (dgb_fv_fence)
+    static const bool hybridEnv = [] { const char* e = getenv("DGB_FV_HYBRID"); return !(e && atoi(e) == 0); }();
+    const bool ringOk = fv_ring_eligible(fv);
+    const bool hybrid = slot >= 0 && hybridEnv && fs.hybridOk && ringOk && (fs.xface[0].on || fs.xface[1].on);
+    // input side: x halos of c_in still in the exchange buffer?
+    if (fv->xhPending) {
+      if (ringOk && d_c_in == fv->xhArray) {
+        for (int sd = 0; sd < 2; ++sd) if (fs.xface[sd].on) {
+          a.xh[sd] = fs.recv[fv->xhParity] + fs.xface[sd].buf_offset; a.xhY0[sd] = fs.xface[sd].y0; a.xhZ0[sd] = fs.xface[sd].z0; a.xhNy[sd] = fs.xface[sd].ny;
+        }
+        fv->wantPair = true;
+      } else if (int rc = fv_flush_xhalo(fv, stream)) return rc;
+    }
+    a.pack = (slot >= 0 ? (hybrid ? fs.direct[slot].dHybrid : fs.direct[slot].dPack) : fs.dPack) + parity; a.packEpoch = fs.epoch + 1u; a.packSignal = 1;
+    const int rcl = launch_step<false>(fv, a, stream);
+    const bool readBuffer = fv->wantPair;
+    fv->wantPair = false;
+    if (rcl) return rcl;
+    if (readBuffer) fv->xhPending = false;               // consumed (the array itself was never refreshed; it is an input only)
+    if (hybrid) { fv->xhPending = true; fv->xhArray = d_c_out; fv->xhParity = parity; }
     if (slot >= 0 || fv->plan->nRecvBoxes == 0) {
       k_fv_wait<<<1, 64, 0, stream>>>(fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4), fs.dTimeout); ++fv->launches;
     }
@@ -1398,7 +1476,7 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
     fv->grid->lastBytesSent = bytes;
     ++fs.epoch;
     fv->step = n+1;
-    fv->exchangeMode = slot >= 0 ? DGB_FV_EXCHANGE_DIRECT : DGB_FV_EXCHANGE_FUSED;
+    fv->exchangeMode = slot >= 0 ? (hybrid ? DGB_FV_EXCHANGE_HYBRID : DGB_FV_EXCHANGE_DIRECT) : DGB_FV_EXCHANGE_FUSED;
     return DGB_OK;
   }
   if (fv->split && exchanges) {
@@ -1469,6 +1547,10 @@ int dgb_fv_register_fields(dgb_fv* fv, double* const* d_fields, int nfields, voi
   DGB_CUDA(cudaStreamSynchronize(stream));
   return fused_register(*fv->plan, fv->view.rank, fv->view.nranks, fv->comm, stream, fv->fused, d_fields, nfields);
 }
+int dgb_fv_fence(dgb_fv* fv, void* stream_) {
+  if (fv->fused.timed_out()) return fail(DGB_ENCCL, kTimeoutMsg);
+  return fv_flush_xhalo(fv, (cudaStream_t)stream_);
+}
 int dgb_fv_registered_fields(const dgb_fv* fv, int* n) { *n = int(fv->fused.direct.size()); return DGB_OK; }
 
 int dgb_fv_bootstrap_local(dgb_fv* fv, double** d_pending_max, void* stream_) {
@@ -1485,6 +1567,7 @@ int dgb_fv_bootstrap_local(dgb_fv* fv, double** d_pending_max, void* stream_) {
 int dgb_fv_step_local(dgb_fv* fv, const double* d_c_in, double* d_c_out, double** d_pending_max, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!fv->bootstrapped) return fail(DGB_EARG, "dgb_fv_step_local: call dgb_fv_bootstrap_local (and reduce its result over ranks) first");
+  if (int rc = fv_flush_xhalo(fv, stream)) return rc;
   const long long n = fv->step;
   if (fv->seedPending) {                                      // the caller has reduced slot 0 by now
     DGB_CUDA(cudaMemcpyAsync(fv->dSlots + 1, fv->dSlots + 0, sizeof(double), cudaMemcpyDeviceToDevice, stream));
@@ -1505,6 +1588,7 @@ int dgb_fv_step_local(dgb_fv* fv, const double* d_c_in, double* d_c_out, double*
 
 int dgb_fv_update(dgb_fv* fv, const double* d_c_in, double* d_update, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (int rc = fv_flush_xhalo(fv, stream)) return rc;
   if (!fv->bootstrapped) if (int rc = bootstrap(fv, stream)) return rc;
   // same kernel, update array materialised, nothing advanced: the reduction goes to a scratch slot that is re-zeroed
   const long long n = fv->step;
@@ -1517,6 +1601,7 @@ int dgb_fv_update(dgb_fv* fv, const double* d_c_in, double* d_update, void* stre
 }
 
 int dgb_fv_last_dt(dgb_fv* fv, double* dt_host, void* stream) {
+  if (int rc = fv_flush_xhalo(fv, (cudaStream_t)stream)) return rc;     // this call synchronises: a natural point to complete the halo
   DGB_CUDA(cudaMemcpyAsync(dt_host, fv->dSlots + 4, sizeof(double), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   unsigned timedOut = 0;
   if (fv->fused.on) DGB_CUDA(cudaMemcpyAsync(&timedOut, &fv->fused.ctl->timeout, sizeof(unsigned), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -1529,6 +1614,7 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
   cudaStream_t stream = (cudaStream_t)stream_;
   if (fv->fused.timed_out()) return fail(DGB_ENCCL, kTimeoutMsg);
   if (fv->comm) if (int rc = nccl_check_async(fv->comm)) return rc;
+  if (int rc = fv_flush_xhalo(fv, stream)) return rc;
   int64_t n = 0; dgb_view_size(&fv->view, 0, &n);
   const size_t bytes = size_t(n)*sizeof(double);
   if (fv->stageBytes < bytes) {

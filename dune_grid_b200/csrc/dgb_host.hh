@@ -268,7 +268,7 @@ inline void build_boxes(LevelBoxes& g, unsigned periodic) {
 // one entry of a send/recv list (YGridList::Intersection, ygrid.hh:828-838 + finalize :962-1012)
 // `move`: the partner's box was shifted by this vector into this rank's frame (periodic wrap: +-N, else 0), i.e. a cell at
 // coordinate x here is the cell x - move in the partner's own frame
-struct ListEntry { int rank, distance; unsigned shift; int index_offset; dgb_box box; int move[3]; };
+struct ListEntry { int rank, distance; unsigned shift; int index_offset; dgb_box box; int move[3]; int delta[3]; };   // delta: torus offset of the partner
 
 struct Level {
   LevelBoxes b;
@@ -477,7 +477,7 @@ inline void comm_list(const RankGrid& me, const std::vector<RankGrid>& others, i
       dgb_box is = box_intersect(local, other, dim, empty);
       if (empty) continue;
       int dist = 0; for (int i = 0; i < dim; ++i) dist += std::abs(dl[i]);
-      ListEntry e{nbrank, dist, mine.shift, running, is, {v[0], v[1], v[2]}};
+      ListEntry e{nbrank, dist, mine.shift, running, is, {v[0], v[1], v[2]}, {dl[0], dl[1], dl[2]}};
       tmp.push_back(e);
     }
     if (wantSend) out.insert(out.end(), tmp.rbegin(), tmp.rend());      // push_front: descending delta

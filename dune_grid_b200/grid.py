@@ -590,6 +590,11 @@ class FiniteVolume:
     def step(self, c_in, c_out):
         check(lib.dgb_fv_step(self.h, _ptr(c_in), _ptr(c_out), _stream()))
 
+    def fence(self):
+        """dgb_fv_fence: completes the halo of the most recent REGISTERED output array (its x-overlap column is refreshed on
+        demand only); call before reading overlap cells of that array with anything but step()"""
+        check(lib.dgb_fv_fence(self.h, _stream()))
+
     def register_fields(self, *fields):
         """dgb_fv_register_fields (collective): the arrays the time loop alternates between; steps that write one of them let
         the peers store halo cells straight into it (no receive buffer, no unpack). Returns the number of registered arrays
@@ -645,4 +650,4 @@ class FiniteVolume:
         receivers' buffers) or 'direct' (peer stores into the receivers' registered arrays)"""
         m = C.c_int(0)
         check(lib.dgb_fv_exchange_mode(self.h, C.byref(m)))
-        return ("none", "serial", "overlapped", "fused", "direct")[m.value]
+        return ("none", "serial", "overlapped", "fused", "direct", "hybrid")[m.value]

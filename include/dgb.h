@@ -284,6 +284,15 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream)
  * keep the receive-buffer form - same results. The arrays must stay allocated until dgb_fv_destroy. */
 int dgb_fv_register_fields(dgb_fv* fv, double* const* d_fields, int nfields, void* stream);
 int dgb_fv_registered_fields(const dgb_fv* fv, int* n);                /* 0 = the registration was declined */
+/* Completion of the halo of a REGISTERED output array. With overlap 1 and the production kernel, a step that writes a registered
+ * array delivers the x faces (one cell per row of the receiver: every 8-byte store would be a read-modify-write of a DRAM
+ * sector) into the receiver's contiguous exchange buffer instead of into the array; the next step reads its x neighbours from
+ * that buffer, so in a time loop the overlap COLUMN of the array is never written. dgb_fv_fence(fv, stream) unpacks it for
+ * the most recent output array - call it before anything but dgb_fv_step reads that array's overlap cells (the analogue of
+ * MPI_Win_fence). dgb_fv_last_dt, dgb_fv_step_host, dgb_fv_update, dgb_fv_step_local and a dgb_fv_step whose input is another
+ * array do it themselves. Arrays that were not registered are always complete when dgb_fv_step returns (stream order).
+ * DGB_FV_HYBRID=0 in the environment keeps the x faces going into the array as well (DIRECT). Not collective. */
+int dgb_fv_fence(dgb_fv* fv, void* stream);
 /* the kernel of dgb_fv_step alone: no halo exchange, no reduction across ranks. *d_pending_max then points at the
  * device double holding this rank's max outflow sum, which the caller must max-reduce over ranks before the next
  * step (dgb_fv_step does both itself). For transports other than NCCL and single-device rank emulation. */
@@ -314,6 +323,8 @@ int dgb_fv_kernel_info(const dgb_fv* fv, int32_t* info8);
 #define DGB_FV_EXCHANGE_OVERLAPPED 2 /* shell kernel + NCCL send/recv on a second stream, concurrent with the bulk kernel */
 #define DGB_FV_EXCHANGE_FUSED 3     /* one step kernel stores into the receivers' buffers over peer-mapped memory and signals */
 #define DGB_FV_EXCHANGE_DIRECT 4    /* as FUSED, and the stores go straight into the receivers' registered arrays: no unpack */
+#define DGB_FV_EXCHANGE_HYBRID 5    /* as DIRECT, except the x-face boxes: they stay in the receiver's contiguous exchange buffer, where
+                                       the receiver's next step kernel reads its x neighbours; see dgb_fv_fence */
 /* Limits of the fused form (beyond them dgb_fv_step keeps the NCCL forms, same results): at most 64 ranks (control block),
  * at most 32 send boxes per rank (26 in 3-D with overlap; more only with several codims, which the FV exchange does not
  * have). dgb_communicate takes at most 8 arrays per call. A peer that does not deliver its step within 20 s makes the

@@ -492,10 +492,16 @@ def test_fv_registered_fields_peers_store_into_the_arrays(N, periodic, overlap, 
         for _ in range(4):
             fv.step(c, cn)
             c, cn = cn, c
-        assert fv.exchange_mode() == ("direct" if registered else "fused")
+        # x faces one cell thick + production kernel: they stay in the exchange buffer (hybrid); otherwise straight into the array
+        hybrid = mode == "separable" and overlap == 1 and (periodic & 1)
+        assert fv.exchange_mode() == (("hybrid" if hybrid else "direct") if registered else "fused")
         launches = fv.launch_count() - l0
         if registered:
             assert launches <= 4 * 2 + 1                         # step kernel + one-CTA wait (+ bootstrap), no unpack launches
+            if hybrid:
+                stale = np_(c)
+                fv.fence()                                       # on-demand unpack of the x-overlap column
+                assert not np.array_equal(stale, np_(c))
             fv.step(c, third)                                    # an unregistered output array: the buffered form, same object
             assert fv.exchange_mode() == "fused"
             res["mixed"] = np_(third)
@@ -503,9 +509,29 @@ def test_fv_registered_fields_peers_store_into_the_arrays(N, periodic, overlap, 
             fv.step(c, cn)
             res["buffered5"] = np_(cn)
         res[registered] = np_(c)
+        if registered and hybrid:
+            # a longer hybrid run that is only completed at the end: 5 more steps reading the x halo from the exchange buffer
+            a, b = c.clone(), torch.empty_like(c)
+            fv2 = dg.FiniteVolume(g, 0, 0, params, mode)
+            assert fv2.register_fields(a, b) == 2
+            for _ in range(5):
+                fv2.step(a, b)
+                a, b = b, a
+            assert fv2.exchange_mode() == "hybrid"
+            fv2.fence()
+            res["hybrid9"] = np_(a)
+            fv2.close()
+        elif not registered:
+            a, b = c.clone(), torch.empty_like(c)
+            for _ in range(5):
+                fv.step(a, b)
+                a, b = b, a
+            res["buffered9"] = np_(a)
         fv.close()
     assert np.array_equal(res[True], res[False])
     assert np.array_equal(res["mixed"], res["buffered5"])
+    if "hybrid9" in res:
+        assert np.array_equal(res["hybrid9"], res["buffered9"])
     for _ in range(4):
         w.fv_step(0, 0, params, ref)
     if mode == "exact":
