@@ -84,6 +84,8 @@ _SIG = {
     "dgb_mapper_index": (_i, [_pv, _pm, _i, _i, _vp, _vp]), "dgb_mapper_subindex": (_i, [_pv, _pm, _i, _i, _vp, _vp]),
     "dgb_elements_materialize": (_i, [_pv, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dgb_intersections_materialize": (_i, [_pv, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "dgb_intersection_normals": (_i, [_pv, _i, _vp, _vp, _vp]),
+    "dgb_intersection_local_geometry": (_i, [_i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "dgb_geometry_eval": (_i, [_pv, _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp, _vp]),
     "dgb_geogrid_eval": (_i, [_pv, _i, _i, C.POINTER(C.c_double), _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp, _vp]),
     "dgb_geogrid_intersections": (_i, [_pv, _i, _i, C.POINTER(C.c_double), _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

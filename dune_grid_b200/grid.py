@@ -295,6 +295,28 @@ class GridView:
         """sum over `for e in elements(gv): for is in intersections(gv, e)` of the functor's intersection body (values: (2dim, n))"""
         return self._for_each(True, functor, args, partition, values)
 
+    def intersectionNormals(self, partition=All_Partition):
+        """unitOuterNormal (== outerNormal == centerUnitOuterNormal) and integrationOuterNormal of every face of every cell:
+        two CUDA tensors of shape (2dim, dim, n)"""
+        _require_cuda()
+        torch = _torch()
+        n, d = self.size(0, partition), self.dim
+        u = torch.empty((2 * d, d, n), dtype=torch.float64, device="cuda")
+        w = torch.empty((2 * d, d, n), dtype=torch.float64, device="cuda")
+        check(lib.dgb_intersection_normals(C.byref(self.v), partition, _ptr(u), _ptr(w), _stream()))
+        return u, w
+
+    def geometryInInside(self, k):
+        """(lower, upper) of YaspIntersection::geometryInInside() of face k (the same for every cell)"""
+        lo, hi = (C.c_double * 3)(), (C.c_double * 3)()
+        check(lib.dgb_intersection_local_geometry(self.dim, k, 0, lo, hi))
+        return np.array(lo[:self.dim]), np.array(hi[:self.dim])
+
+    def geometryInOutside(self, k):
+        lo, hi = (C.c_double * 3)(), (C.c_double * 3)()
+        check(lib.dgb_intersection_local_geometry(self.dim, k, 1, lo, hi))
+        return np.array(lo[:self.dim]), np.array(hi[:self.dim])
+
     def centerUnitOuterNormal(self, k):
         """YaspIntersection::centerUnitOuterNormal (yaspgridintersection.hh:177-182): +-e_dir, independent of the cell"""
         n = np.zeros(self.dim)

@@ -184,6 +184,12 @@ int dgb_elements_materialize(const dgb_view* v, int codim, int pitype,
 int dgb_intersections_materialize(const dgb_view* v, int pitype,
                                   uint8_t* d_neighbor, uint8_t* d_boundary, int32_t* d_outside, int32_t* d_bsi,
                                   double* d_center, double* d_volume, void* stream);
+/* YaspIntersection::unitOuterNormal / outerNormal / centerUnitOuterNormal (= +-e_dir) and integrationOuterNormal (= face volume
+ * times it) for every cell of the partition and face k: out[(k*dim+d)*n + cell] (yaspgridintersection.hh:163-190); NULL = skip */
+int dgb_intersection_normals(const dgb_view* v, int pitype, double* d_unitOuterNormal, double* d_integrationOuterNormal, void* stream);
+/* geometryInInside() (in_outside = 0) / geometryInOutside() (1) of face k: lower and upper corner of the unit face in the
+ * element's local coordinates - the same for every cell of a YaspGrid (yaspgridintersection.hh:195-228). Host arithmetic. */
+int dgb_intersection_local_geometry(int dim, int k, int in_outside, double* lower, double* upper);
 /* ---- Geometry::global / jacobianInverseTransposed / integrationElement at nqp local points (host array nqp*dim) for all
  *      cells of the partition: global[(q*dim+d)*n+e], jit[((q*dim+r)*dim+c)*n+e], detJ[q*n+e] (common/geometry.hh:194-371) */
 int dgb_geometry_eval(const dgb_view* v, int pitype, int nqp, const double* qp_host,

@@ -235,3 +235,30 @@ def test_geometrygrid_intersections(cfg):
                 e = np.zeros(d); e[k // 2] = 1.0 if k % 2 else -1.0
                 assert np.abs(got["centerUnitOuterNormal"][k].cpu().numpy() - e[:, None]).max() <= 1e-15
     w.close()
+
+
+@pytest.mark.parametrize("cfg", [make_cfg(dim=3, N=(6, 5, 4), mode=2, periodic=1), make_cfg(dim=2, N=(9, 8), periodic=2, upper=(2.0, 0.5))],
+                         ids=["tensor3d", "periodic2d"])
+def test_yasp_intersection_normals_and_local_geometries(cfg):
+    """YaspIntersection::unitOuterNormal / integrationOuterNormal (yaspgridintersection.hh:163-190) for all faces, bit for bit
+    against the oracle's centerUnitOuterNormal() and geometry().volume(); geometryInInside / geometryInOutside (:195-228) are the
+    unit faces of the reference cube"""
+    import dune_grid_b200 as dg
+    d = cfg["dim"]
+    o = best_oracle()
+    w = oracle_world(o, cfg, 1)
+    g = product_grid(cfg, 0, 1)
+    gv = g.leafGridView()
+    u, wn = gv.intersectionNormals(dg.All_Partition)
+    ri = w.intersections(0, 0, dg.All_Partition)
+    assert np.array_equal(np.transpose(np_(u), (2, 0, 1)), ri["normal"])
+    assert np.array_equal(np.transpose(np_(wn), (2, 0, 1)), ri["volume"][:, :, None] * ri["normal"])
+    for k in range(2 * d):
+        lo, hi = gv.geometryInInside(k)
+        e_lo, e_hi = np.zeros(d), np.ones(d)
+        e_lo[k // 2] = e_hi[k // 2] = float(k % 2)
+        assert np.array_equal(lo, e_lo) and np.array_equal(hi, e_hi)
+        lo, hi = gv.geometryInOutside(k)
+        e_lo[k // 2] = e_hi[k // 2] = float(1 - k % 2)
+        assert np.array_equal(lo, e_lo) and np.array_equal(hi, e_hi)
+    w.close()
