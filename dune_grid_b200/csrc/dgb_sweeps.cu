@@ -243,6 +243,130 @@ __global__ void __launch_bounds__(BX) k_intersections(const __grid_constant__ dg
 }
 
 
+
+// ---- linear walk: the form for boxes whose rows are NOT a multiple of 32 entities ---------------------------------------
+// Measured (tools/intersections_probe.py, profiles/r02_intersections_probe.jsonl): the column form above reaches 90-93 % of
+// the copy peak on 384^3 / 512^3 boxes but 64 % on the 386-wide box of an x-periodic grid (BASELINE config 4) - tensor-product
+// coordinates cost nothing, a 382-cell periodic grid (384 stored) runs at 102 %. With 386-entity rows every row of every
+// output stream starts at another offset inside its 32-byte sector / 128-byte line, so every warp store straddles one more
+// line and leaves two partial sectors, and the fourth CTA of a row has 2 live lanes. Here the box is walked in its LINEAR
+// order instead (which is the order of every output stream): a CTA owns LIN_ROWS*128 consecutive entities, thread t the
+// entities chunk + j*128 + t, so every warp store is a whole, aligned run of 32 entities in all 48 streams whatever the row
+// length. Coordinates follow by carry propagation (i0 += 128, wrap into i1, i2); per-axis values are refreshed only when
+// their index changes.
+static constexpr int LIN_ROWS = 8;
+
+struct LinWalk {
+  int i0, i1, i2;            // position inside the box
+  int s0, s1;
+  __device__ __forceinline__ void init(long long e, const dgb_box& b, int dim) {
+    s0 = b.size[0]; s1 = dim > 1 ? b.size[1] : 1;
+    const long long q = e / s0;
+    i0 = int(e - q*s0);
+    i2 = dim > 2 ? int(q / s1) : 0;
+    i1 = int(q - (long long)i2*s1);
+  }
+  // advance by BX entities; returns a mask: bit 1 = i1 changed, bit 2 = i2 changed
+  __device__ __forceinline__ int step() {
+    int changed = 0;
+    i0 += BX;
+    while (i0 >= s0) { i0 -= s0; ++i1; changed |= 1; if (i1 == s1) { i1 = 0; ++i2; changed |= 2; } }
+    return changed;
+  }
+};
+
+__global__ void __launch_bounds__(BX) k_intersections_linear(const __grid_constant__ dgb_view v, const SweepGeom s, const FaceOut o, long long count) {
+  const dgb_component& c = v.comp[0];
+  const dgb_box& b = c.box[s.kind];
+  const dgb_box& of = c.box[DGB_BOX_OVERLAPFRONT];
+  const int dim = v.dim;
+  long long e = (long long)blockIdx.x*(BX*LIN_ROWS) + threadIdx.x;
+  if (e >= count) return;
+  LinWalk w; w.init(e, b, dim);
+  const bool geo = o.center || o.volume;
+  const int stride[3] = { 1, of.size[0], of.size[0]*of.size[1] };
+  double ll[3] = {0, 0, 0}, ur[3] = {0, 0, 0};
+  bool nb[6], bd[6];
+  int coord[3] = { b.origin[0]+w.i0, b.origin[1]+w.i1, dim > 2 ? b.origin[2]+w.i2 : 0 };
+  auto axis = [&](int i) {
+    if (geo) {
+      const double sh = periodic_shift(v, i, coord[i]);
+      ll[i] = vertex_coord(v, i, coord[i]); ur[i] = vertex_coord(v, i, coord[i]+1);
+      if (sh != 0.0) { ll[i] += sh; ur[i] += sh; }
+    }
+    nb[2*i] = face_neighbor(v, coord, i, 0); nb[2*i+1] = face_neighbor(v, coord, i, 1);
+    bd[2*i] = face_boundary(v, coord, i, 0); bd[2*i+1] = face_boundary(v, coord, i, 1);
+  };
+  axis(0); if (dim > 1) axis(1); if (dim > 2) axis(2);
+  for (int j = 0; j < LIN_ROWS; ++j) {
+    const long long pos = s.base + e;
+    const int inside = int(entity_index(v, c, s.kind, coord));
+    long long pf = pos, pc = pos;
+#pragma unroll
+    for (int dir = 0; dir < 3; ++dir) {
+      if (dir < dim) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const int k = 2*dir + side;
+          if (o.neighbor) o.neighbor[pf] = nb[k];
+          if (o.boundary) o.boundary[pf] = bd[k];
+          if (o.outside) o.outside[pf] = nb[k] ? inside + (side ? stride[dir] : -stride[dir]) : -1;
+          if (o.bsi) o.bsi[pf] = bd[k] ? boundary_segment_index(v, coord, dir, side) : -1;
+          if (geo) {
+            double vol = 1.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              if (i < dim) {
+                double lo = ll[i], hi = ur[i];
+                if (i == dir) { lo = side ? ur[i] : ll[i]; hi = lo; }
+                else vol *= hi-lo;
+                if (o.center) o.center[pc] = 0.5*(lo+hi);
+                pc += s.n;
+              }
+            }
+            if (o.volume) o.volume[pf] = vol;
+          }
+          pf += s.n;
+        }
+      }
+    }
+    e += BX;
+    if (e >= count) break;
+    const int ch = w.step();
+    coord[0] = b.origin[0]+w.i0; axis(0);
+    if (ch & 1) { coord[1] = b.origin[1]+w.i1; axis(1); }
+    if (ch & 2) { coord[2] = b.origin[2]+w.i2; axis(2); }
+  }
+}
+
+// mapper indices of one component in linear order (see above): two adds per entity, every warp store aligned
+__global__ void __launch_bounds__(BX) k_index_linear(const __grid_constant__ dgb_view v, const SweepGeom s, uint32_t block, uint32_t offset,
+                                                     uint32_t* __restrict__ out, long long count) {
+  const dgb_component& c = v.comp[s.comp];
+  const dgb_box& b = c.box[s.kind];
+  const dgb_box& of = c.box[DGB_BOX_OVERLAPFRONT];
+  constexpr int ROWS = 32;
+  long long e = (long long)blockIdx.x*(BX*ROWS) + threadIdx.x;
+  if (e >= count) return;
+  LinWalk w; w.init(e, b, v.dim);
+  const int coord[3] = { b.origin[0]+w.i0, b.origin[1]+w.i1, v.dim > 2 ? b.origin[2]+w.i2 : 0 };
+  uint32_t val = entity_index(v, c, s.kind, coord)*block + offset;
+  // moving by BX entities inside a row adds BX to the index; wrapping into the next row adds the gap between the rows of the
+  // enclosing overlapfront numbering, wrapping into the next plane the gap between its planes
+  const uint32_t rowGap = uint32_t(of.size[0]-b.size[0])*block, planeGap = uint32_t(of.size[0])*uint32_t(of.size[1]-b.size[1])*block;
+  uint32_t* p = out + s.base + e;
+  for (int j = 0; j < ROWS; ++j) {
+    *p = val;
+    e += BX; p += BX;
+    if (e >= count) break;
+    const int i1old = w.i1, i2old = w.i2;
+    w.step();
+    val += uint32_t(BX)*block;
+    int rows = (w.i2 - i2old)*w.s1 + (w.i1 - i1old);        // rows advanced (may be > 1 for narrow boxes)
+    val += uint32_t(rows)*rowGap + uint32_t(w.i2 - i2old)*planeGap;
+  }
+}
+
 // ---- K3b: intersection normals -----------------------------------------------------------------------------------------
 // YaspIntersection::{outerNormal,unitOuterNormal,centerUnitOuterNormal} = +-e_dir (yaspgridintersection.hh:163-182),
 // integrationOuterNormal = geometry().volume() * centerUnitOuterNormal() (:184-190): out[(k*dim+d)*n + cell]
@@ -564,7 +688,15 @@ int dgb_mapper_index(const dgb_view* v, const dgb_mapper* m, int codim, int pity
   if (m->offset[codim] == DGB_INVALID_OFFSET) return fail(DGB_EARG, "codim not contained in the mapper layout");
   EntityOut o{}; o.index = d_out; o.block = m->block[codim]; o.offset = m->offset[codim];
   static const int rows = [] { const char* e = getenv("DGB_IDX_ROWS"); const int r = e ? atoi(e) : 32; return r == 64 || r == 128 ? r : 32; }();      // measured (403 M faces): 32: 0.325 ms, 64: 0.365, 128: 0.396
+  static const int linear = [] { const char* e = getenv("DGB_SWEEP_LINEAR"); return e ? atoi(e) : -1; }();
   return for_each_component(*v, codim, pitype, rows, [&](const SweepGeom& s, dim3 grid) {
+    const dgb_box& b = v->comp[s.comp].box[s.kind];
+    if (linear == 1 || (linear == -1 && b.size[0] % 32 != 0)) {
+      long long count = 1; for (int i = 0; i < v->dim; ++i) count *= b.size[i];
+      const unsigned nb = unsigned((count + BX*32 - 1)/(BX*32));
+      k_index_linear<<<nb, BX, 0, (cudaStream_t)stream>>>(*v, s, o.block, o.offset, d_out, count);
+      return;
+    }
     if (rows == 32) k_index_rows<32><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o.block, o.offset, d_out);
     else if (rows == 128) k_index_rows<128><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o.block, o.offset, d_out);
     else k_index_rows<64><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o.block, o.offset, d_out);
@@ -596,7 +728,15 @@ int dgb_intersections_materialize(const dgb_view* v, int pitype, uint8_t* d_neig
   if (d_center || d_volume) if (int rc = check_tensor(*v)) return rc;
   FaceOut o{d_neighbor, d_boundary, d_outside, d_bsi, d_center, d_volume};
   static const int rows = [] { const char* e = getenv("DGB_FACE_ROWS"); const int r = e ? atoi(e) : FACE_ROWS_DEFAULT; return r; }();
+  static const int linear = [] { const char* e = getenv("DGB_SWEEP_LINEAR"); return e ? atoi(e) : -1; }();      // -1 automatic, 0 never, 1 always
   return for_each_component(*v, 0, pitype, rows, [&](const SweepGeom& s, dim3 grid) {
+    const dgb_box& b = v->comp[s.comp].box[s.kind];
+    if (linear == 1 || (linear == -1 && b.size[0] % 32 != 0)) {       // rows that do not keep the warps aligned: linear walk
+      long long count = 1; for (int i = 0; i < v->dim; ++i) count *= b.size[i];
+      const unsigned nb = unsigned((count + BX*LIN_ROWS - 1)/(BX*LIN_ROWS));
+      k_intersections_linear<<<nb, BX, 0, (cudaStream_t)stream>>>(*v, s, o, count);
+      return;
+    }
     switch (rows) {                                   // rows walked per thread (tuning knob DGB_FACE_ROWS)
       case 1: k_intersections<1><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o); break;
       case 2: k_intersections<2><<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o); break;

@@ -56,8 +56,10 @@ def main():
                 dt_ref = w.fv_step(0, problem, params, ref)
                 fv.step(c, cn)
                 c, cn = cn, c
-                dt = fv.last_dt()
-                ok = ok and (dt == dt_ref if mode == "exact" else abs(dt - dt_ref) <= 1e-13 * dt_ref)
+                if not registered:            # registered runs are completed once, at the end (dgb_fv_fence): the hybrid form
+                    dt = fv.last_dt()         # reads its x halo from the exchange buffer for 3 of the 4 steps
+                    ok = ok and (dt == dt_ref if mode == "exact" else abs(dt - dt_ref) <= 1e-13 * dt_ref)
+            fv.fence()
             got = c.cpu().numpy()
             scale = max(np.abs(x).max() for x in ref)
             if mode == "exact":
