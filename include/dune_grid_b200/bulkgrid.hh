@@ -4,7 +4,8 @@
 // per-view bulk calls that return device arrays in the reference's iteration order:
 //
 //   Dune::YaspGrid<dim,Coordinates>(L, s, periodic, overlap, comm)   dune/grid/yaspgrid.hh:904-909,974-980,1043-1047
-//     -> DuneB200::BulkYaspGrid<dim>(L, s, periodic, overlap, rank, nranks, comm)
+//     -> DuneB200::BulkYaspGrid<dim,Coordinates>(L, s, periodic, overlap, rank, nranks, comm)   (Coordinates = one of the tag
+//        types EquidistantCoordinates / EquidistantOffsetCoordinates / TensorProductCoordinates<ct,dim>, coordinates.hh:27,129,243)
 //   grid.leafGridView() / levelGridView(l), globalRefine, refineOptions   dune/grid/common/grid.hh:878-891, yaspgrid.hh:1216,1270
 //   gv.size(codim), gv.overlapSize(codim), gv.ghostSize(codim)            dune/grid/common/gridview.hh:186-198,343-355
 //   for (e : elements(gv, ps)) { is.index(e); e.partitionType(); e.geometry().center()/volume() }
@@ -16,6 +17,10 @@
 //     -> gv.geometry(qp, pit)                                                                      common/geometry.hh:194-371
 //   MultipleCodimMultipleGeomTypeMapper<GV>(gv, layout).index(e)/subIndex(e,i,cc)/size()           common/mcmgmapper.hh:129-343
 //     -> BulkMapper(gv, layout).index(codim,pit) / subIndex(cc,pit) / size()
+//   for (e : elements(gv)) sum += f(e);  for (is : intersections(gv,e)) sum += f(is)   with a compiled-in device functor
+//     -> gv.forEachElement(functorId, args) / gv.forEachIntersection(functorId, args)             (csrc/dgb_functors.cuh)
+//   is.unitOuterNormal / integrationOuterNormal / geometryInInside / geometryInOutside             yaspgridintersection.hh:163-228
+//     -> gv.intersectionNormals(pit), gv.geometryInInside(k), gv.geometryInOutside(k)
 //   gv.communicate(dataHandle, InteriorBorder_All_Interface, ForwardCommunication)                 common/gridview.hh:334-341
 //     -> gv.communicate(BulkDataHandle{mapper, arrays...}, iftype, dir)   (the shape of NumPyCommDataHandle,
 //        dune/python/grid/numpycommdatahandle.hh:41-142)
@@ -34,6 +39,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -109,7 +115,13 @@ public:
   dgb_comm* handle() const { return c_; }
 };
 
-template<int dim> class BulkYaspGrid;
+// coordinate containers of YaspGrid (dune/grid/yaspgrid/coordinates.hh:27,129,243) as tag types: they select the constructor
+template<class ct, int dim> struct EquidistantCoordinates { typedef ct ctype; static constexpr int mode = DGB_COORD_EQUIDISTANT; };
+template<class ct, int dim> struct EquidistantOffsetCoordinates { typedef ct ctype; static constexpr int mode = DGB_COORD_EQUIDISTANT_OFFSET; };
+template<class ct, int dim> struct TensorProductCoordinates { typedef ct ctype; static constexpr int mode = DGB_COORD_TENSORPRODUCT; };
+
+template<int dim> class BulkYaspGridBase;
+template<int dim, class Coordinates> class BulkYaspGrid;
 template<int dim> class BulkGridView;
 template<int dim> class BulkMapper;
 
@@ -143,13 +155,13 @@ template<int dim> std::array<std::uint32_t,4> mcmgVertexLayout() { std::array<st
 
 template<int dim>
 class BulkGridView {
-  const BulkYaspGrid<dim>* grid_; dgb_view v_;
-  friend class BulkYaspGrid<dim>; friend class BulkMapper<dim>;
-  BulkGridView(const BulkYaspGrid<dim>* g, const dgb_view& v) : grid_(g), v_(v) {}
+  const BulkYaspGridBase<dim>* grid_; dgb_view v_;
+  friend class BulkYaspGridBase<dim>; friend class BulkMapper<dim>;
+  BulkGridView(const BulkYaspGridBase<dim>* g, const dgb_view& v) : grid_(g), v_(v) {}
 public:
   enum { dimension = dim };
   const dgb_view& descriptor() const { return v_; }
-  const BulkYaspGrid<dim>& grid() const { return *grid_; }
+  const BulkYaspGridBase<dim>& grid() const { return *grid_; }
   int level() const { return v_.level; }
   std::int64_t size(int codim) const { std::int64_t n; check(dgb_view_size(&v_, codim, &n)); return n; }
   std::int64_t size(int codim, PartitionIteratorType pit) const { std::int64_t n; check(dgb_view_partition_size(&v_, codim, pit, &n)); return n; }
@@ -187,9 +199,36 @@ public:
                             r.integrationElement.data(), s));
     return r;
   }
+  // unitOuterNormal (== outerNormal == centerUnitOuterNormal) and integrationOuterNormal of every face of every cell: [(k*dim+d)*n + cell]
+  std::pair<DeviceArray<double>, DeviceArray<double>> intersectionNormals(PartitionIteratorType pit = All_Partition, cudaStream_t s = nullptr) const {
+    const std::size_t m = std::size_t(2*dim*dim)*size(0, pit);
+    DeviceArray<double> u(m), w(m);
+    check(dgb_intersection_normals(&v_, pit, u.data(), w.data(), s));
+    return {std::move(u), std::move(w)};
+  }
+  // YaspIntersection::geometryInInside / geometryInOutside of face k: (lower, upper) of the unit face in local coordinates
+  std::pair<std::array<double,dim>, std::array<double,dim>> geometryInInside(int k) const { return localFace(k, 0); }
+  std::pair<std::array<double,dim>, std::array<double,dim>> geometryInOutside(int k) const { return localFace(k, 1); }
+  // sum over the element / intersection loop of a compiled-in device functor (csrc/dgb_functors.cuh), one fused kernel;
+  // `values` (optional, caller-owned: n resp. 2*dim*n doubles) receives the loop body's value per element / face
+  double forEachElement(int functorId, const std::vector<double>& args = {}, PartitionIteratorType pit = All_Partition,
+                        double* d_values = nullptr, cudaStream_t s = nullptr) const { return forEach(false, functorId, args, pit, d_values, s); }
+  double forEachIntersection(int functorId, const std::vector<double>& args = {}, PartitionIteratorType pit = All_Partition,
+                             double* d_values = nullptr, cudaStream_t s = nullptr) const { return forEach(true, functorId, args, pit, d_values, s); }
   // communicate: the data handle is "arrays indexed by a mapper" with a combine operation
   template<class DataHandle>
   void communicate(DataHandle& dh, InterfaceType iftype, CommunicationDirection dir, cudaStream_t s = nullptr) const;
+private:
+  std::pair<std::array<double,dim>, std::array<double,dim>> localFace(int k, int outside) const {
+    double lo[3], hi[3]; check(dgb_intersection_local_geometry(dim, k, outside, lo, hi));
+    std::array<double,dim> a{}, b{}; for (int i = 0; i < dim; ++i) { a[i] = lo[i]; b[i] = hi[i]; }
+    return {a, b};
+  }
+  double forEach(bool faces, int id, const std::vector<double>& args, PartitionIteratorType pit, double* d_values, cudaStream_t s) const {
+    DeviceArray<double> sum(1);
+    check((faces ? dgb_for_each_intersection : dgb_for_each_element)(&v_, pit, id, args.empty() ? nullptr : args.data(), int(args.size()), d_values, sum.data(), s));
+    return sum.toHost(s)[0];
+  }
 };
 
 template<int dim>
@@ -223,8 +262,10 @@ struct BulkDataHandle {
   CommOp op = CommOp::set;
 };
 
+// everything that does not depend on the coordinate container; BulkYaspGrid<dim,Coordinates> below adds the constructor of its container
 template<int dim>
-class BulkYaspGrid {
+class BulkYaspGridBase {
+protected:
   dgb_grid* g_ = nullptr; dgb_comm* comm_ = nullptr;
   std::vector<std::vector<double>> keep_;
   void create(dgb_grid_spec& s, int rank, int nranks) { check(dgb_grid_create(&s, rank, nranks, &g_)); }
@@ -235,15 +276,17 @@ class BulkYaspGrid {
   }
 public:
   enum { dimension = dim, dimensionworld = dim };
+  static_assert(dim == 2 || dim == 3, "the bulk layer covers YaspGrid<2> and YaspGrid<3> (dgb_grid_create rejects other dimensions)");
+  BulkYaspGridBase() = default;
   // EquidistantCoordinates (yaspgrid.hh:904-909)
-  BulkYaspGrid(const std::array<double,dim>& L, const std::array<int,dim>& s, std::bitset<dim> periodic = {}, int overlap = 1,
+  BulkYaspGridBase(const std::array<double,dim>& L, const std::array<int,dim>& s, std::bitset<dim> periodic = {}, int overlap = 1,
                int rank = 0, int nranks = 1, const Communicator* comm = nullptr) : comm_(comm ? comm->handle() : nullptr) {
     dgb_grid_spec sp = base(s, periodic, overlap); sp.coord_mode = DGB_COORD_EQUIDISTANT;
     for (int i = 0; i < dim; ++i) sp.upper[i] = L[i];
     create(sp, rank, nranks);
   }
   // EquidistantOffsetCoordinates (yaspgrid.hh:974-980)
-  BulkYaspGrid(const std::array<double,dim>& lowerleft, const std::array<double,dim>& upperright, const std::array<int,dim>& s,
+  BulkYaspGridBase(const std::array<double,dim>& lowerleft, const std::array<double,dim>& upperright, const std::array<int,dim>& s,
                std::bitset<dim> periodic = {}, int overlap = 1, int rank = 0, int nranks = 1, const Communicator* comm = nullptr)
       : comm_(comm ? comm->handle() : nullptr) {
     dgb_grid_spec sp = base(s, periodic, overlap); sp.coord_mode = DGB_COORD_EQUIDISTANT_OFFSET;
@@ -251,7 +294,7 @@ public:
     create(sp, rank, nranks);
   }
   // TensorProductCoordinates (yaspgrid.hh:1043-1047)
-  BulkYaspGrid(const std::array<std::vector<double>,dim>& coords, std::bitset<dim> periodic = {}, int overlap = 1,
+  BulkYaspGridBase(const std::array<std::vector<double>,dim>& coords, std::bitset<dim> periodic = {}, int overlap = 1,
                int rank = 0, int nranks = 1, const Communicator* comm = nullptr) : comm_(comm ? comm->handle() : nullptr) {
     std::array<int,dim> s{};
     for (int i = 0; i < dim; ++i) s[i] = int(coords[i].size())-1;
@@ -260,11 +303,11 @@ public:
     for (int i = 0; i < dim; ++i) sp.tensor[i] = keep_[i].data();
     create(sp, rank, nranks);
   }
-  BulkYaspGrid(const BulkYaspGrid&) = delete;
-  ~BulkYaspGrid() { if (g_) dgb_grid_destroy(g_); }
+  BulkYaspGridBase(const BulkYaspGridBase&) = delete;
+  ~BulkYaspGridBase() { if (g_) dgb_grid_destroy(g_); }
   // adopts a grid built by the C ABI (BackupRestoreFacility::restore)
   struct Adopt {};
-  BulkYaspGrid(Adopt, dgb_grid* g, const Communicator* comm) : g_(g), comm_(comm ? comm->handle() : nullptr) {}
+  BulkYaspGridBase(Adopt, dgb_grid* g, const Communicator* comm) : g_(g), comm_(comm ? comm->handle() : nullptr) {}
 
   dgb_grid* handle() const { return g_; }
   dgb_comm* comm() const { return comm_; }
@@ -278,12 +321,41 @@ public:
   BulkGridView<dim> levelGridView(int level) const { dgb_view v; check(dgb_view_level(g_, level, &v)); return BulkGridView<dim>(this, v); }
 };
 
+// Dune::YaspGrid<dim, Coordinates> (yaspgrid.hh:164): the coordinate container picks the constructor, as in the reference
+template<int dim, class Coordinates = EquidistantCoordinates<double,dim>>
+class BulkYaspGrid : public BulkYaspGridBase<dim> {
+  typedef BulkYaspGridBase<dim> Base;
+public:
+  typedef Coordinates CoordinateContainer;
+  typedef typename Coordinates::ctype ctype;
+  static_assert(std::is_same<ctype, double>::value, "the device kernels compute in double precision");
+  // yaspgrid.hh:904-909 - only for Coordinates = EquidistantCoordinates
+  BulkYaspGrid(const std::array<double,dim>& L, const std::array<int,dim>& s, std::bitset<dim> periodic = {}, int overlap = 1,
+               int rank = 0, int nranks = 1, const Communicator* comm = nullptr) : Base(L, s, periodic, overlap, rank, nranks, comm) {
+    static_assert(Coordinates::mode == DGB_COORD_EQUIDISTANT, "this constructor belongs to YaspGrid<dim, EquidistantCoordinates>");
+  }
+  // yaspgrid.hh:974-980 - only for Coordinates = EquidistantOffsetCoordinates
+  BulkYaspGrid(const std::array<double,dim>& lowerleft, const std::array<double,dim>& upperright, const std::array<int,dim>& s,
+               std::bitset<dim> periodic = {}, int overlap = 1, int rank = 0, int nranks = 1, const Communicator* comm = nullptr)
+      : Base(lowerleft, upperright, s, periodic, overlap, rank, nranks, comm) {
+    static_assert(Coordinates::mode == DGB_COORD_EQUIDISTANT_OFFSET, "this constructor belongs to YaspGrid<dim, EquidistantOffsetCoordinates>");
+  }
+  // yaspgrid.hh:1043-1047 - only for Coordinates = TensorProductCoordinates
+  explicit BulkYaspGrid(const std::array<std::vector<double>,dim>& coords, std::bitset<dim> periodic = {}, int overlap = 1,
+                        int rank = 0, int nranks = 1, const Communicator* comm = nullptr) : Base(coords, periodic, overlap, rank, nranks, comm) {
+    static_assert(Coordinates::mode == DGB_COORD_TENSORPRODUCT, "this constructor belongs to YaspGrid<dim, TensorProductCoordinates>");
+  }
+  BulkYaspGrid(typename Base::Adopt a, dgb_grid* g, const Communicator* comm) : Base(a, g, comm) {}
+};
+
 // Dune::BackupRestoreFacility<YaspGrid<dim,Coordinates>> (dune/grid/yaspgrid/backuprestore.hh): same static members and the
-// same file format / file naming. The coordinate container is a run-time property here, so restore takes DGB_COORD_*.
+// same file format / file naming; the coordinate container of the grid type tells restore how to read the text.
 template<class Grid> struct BackupRestoreFacility;
-template<int dim>
-struct BackupRestoreFacility<BulkYaspGrid<dim>> {
-  typedef BulkYaspGrid<dim> Grid;
+template<int dim, class Coordinates>
+struct BackupRestoreFacility<BulkYaspGrid<dim,Coordinates>> {
+  typedef BulkYaspGrid<dim,Coordinates> Grid;
+  static Grid* restore(std::istream& stream, const Communicator* comm, int rank = 0, int nranks = 1) { return restore(stream, Coordinates::mode, rank, nranks, comm); }
+  static Grid* restore(const std::string& filename, const Communicator* comm, int rank = 0, int nranks = 1) { return restore(filename, Coordinates::mode, rank, nranks, comm); }
   static std::string text(const Grid& grid) {
     std::int64_t need = 0; check(dgb_grid_backup(grid.handle(), nullptr, 0, &need));
     std::string t(std::size_t(need), '\0'); check(dgb_grid_backup(grid.handle(), &t[0], need, &need)); t.resize(std::size_t(need)-1);
@@ -364,9 +436,15 @@ class FiniteVolume {
   dgb_fv* fv_ = nullptr;
 public:
   enum Mode { exact = DGB_FV_EXACT, separable = DGB_FV_SEPARABLE };
-  FiniteVolume(BulkYaspGrid<dim>& grid, int level, int problem, const std::vector<double>& params, Mode mode = separable) {
+  FiniteVolume(BulkYaspGridBase<dim>& grid, int level, int problem, const std::vector<double>& params, Mode mode = separable) {
     check(dgb_fv_create(grid.handle(), level, problem, params.data(), int(params.size()), mode, grid.comm(), &fv_));
   }
+  // collective (like MPI_Win_create): the arrays the time loop alternates between; peers then store halo cells straight into them
+  int registerFields(const std::vector<double*>& d_fields, cudaStream_t s = nullptr) {
+    check(dgb_fv_register_fields(fv_, d_fields.data(), int(d_fields.size()), s));
+    int n = 0; check(dgb_fv_registered_fields(fv_, &n)); return n;
+  }
+  void fence(cudaStream_t s = nullptr) { check(dgb_fv_fence(fv_, s)); }        // completes the halo of the last registered output array
   FiniteVolume(const FiniteVolume&) = delete;
   ~FiniteVolume() { if (fv_) dgb_fv_destroy(fv_); }
   void initial(double* d_c, cudaStream_t s = nullptr) { check(dgb_fv_init_field(fv_, d_c, s)); }

@@ -140,6 +140,31 @@ void deviceChecks() {
     CHECK(file == "/tmp/bulk_gridview_test_out.vtu" && all.find("<CellData Scalars=\"xcenter\">") != std::string::npos);
     CHECK(all.find("NumberOfCells=\"" + std::to_string(pv.size(0)) + "\"") != std::string::npos);
   }
+  // the coordinate container is a template parameter, as in Dune::YaspGrid<dim,Coordinates>; functor sweeps; face normals
+  {
+    std::array<std::vector<double>,dim> tc;
+    for (int i = 0; i < dim; ++i) for (int k = 0; k <= 6+i; ++k) tc[i].push_back(double(k*k)/double((6+i)*(6+i)));
+    BulkYaspGrid<dim, TensorProductCoordinates<double,dim>> tg(tc, std::bitset<dim>(), 1);
+    auto tv = tg.leafGridView();
+    const double vol = tv.forEachElement(DGB_FUNCTOR_MEASURE, {1.0});                    // sum of the cell volumes = |domain| = 1
+    CHECK(std::abs(vol - 1.0) <= 1e-14);
+    const double flux = tv.forEachIntersection(DGB_FUNCTOR_BOUNDARY_FLUX_X);             // recipe-integration.cc:113-124: = dim*|domain|
+    CHECK(std::abs(flux - double(dim)) <= 1e-13);
+    const double mid = tv.forEachElement(DGB_FUNCTOR_MIDPOINT_EXP_NORM), gauss = tv.forEachElement(DGB_FUNCTOR_GAUSS5_EXP_NORM);
+    CHECK(mid > 1.0 && std::abs(mid - gauss) <= 5e-2*gauss);
+    auto nrm = tv.intersectionNormals(All_Partition);
+    auto un = nrm.first.toHost();
+    const std::int64_t nn = tv.size(0);
+    bool okn = true;
+    for (int k = 0; k < 2*dim; ++k) for (int d = 0; d < dim; ++d)
+      okn = okn && un[std::size_t(k*dim+d)*nn] == ((d == k/2) ? ((k%2) ? 1.0 : -1.0) : 0.0);
+    CHECK(okn);
+    auto in1 = tv.geometryInInside(1), out1 = tv.geometryInOutside(1);
+    CHECK(in1.first[0] == 1.0 && in1.second[0] == 1.0 && out1.first[0] == 0.0 && out1.second[0] == 0.0);
+    std::array<double,dim> lowerleft; lowerleft.fill(-1.0);
+    BulkYaspGrid<dim, EquidistantOffsetCoordinates<double,dim>> og(lowerleft, L, s, std::bitset<dim>(), 1);
+    CHECK(std::abs(og.leafGridView().forEachElement(DGB_FUNCTOR_MEASURE, {1.0}) - std::pow(L[0]+1.0, dim)) <= 1e-12);
+  }
   // FV functor: three steps conserve mass while the shell is away from the boundary (b = 0), 0 <= c <= 1
   if (dim == 3) {
     std::array<double,dim> L1; L1.fill(1.0); std::array<int,dim> s1; s1.fill(48);
