@@ -87,6 +87,10 @@ struct FvArgs {
   // xh[side][(z - xhZ0)*xhNy + (y - xhY0)]; NULL = read the field
   const double* xh[2];
   int xhY0[2], xhZ0[2], xhNy[2];
+  // deferred completion of the PREVIOUS step's exchange (registered fields: no wait kernel between two steps). The CTAs that touch
+  // the rank's boundary - they read halo cells and store into peer memory - first wait until every rank has delivered epoch
+  // waitEpoch; the first CTA also reduces the published CFL maxima into *waitSlot (what k_fv_wait does). NULL: nothing pending.
+  FusedCtl* waitCtl; unsigned waitEpoch; int waitParity, waitRanks; double* waitSlot; unsigned* waitTimeout;
 };
 
 // ---- fused exchange, device side (dgb_comm.hh: FusedCtl / FusedPack) -------------------------------------------------
@@ -169,6 +173,48 @@ __device__ __forceinline__ void fv_fused_signal(const FvArgs& a) {
     for (int r = 0; r < P.nranks; ++r) *reinterpret_cast<volatile unsigned*>(P.peerFlag[r]) = a.packEpoch;
   }
 }
+// see FvArgs::waitCtl. Called by all threads of a CTA before the CTA's first read of c; `boundary` is CTA-uniform.
+__device__ __forceinline__ void fv_peer_wait(const FvArgs& a, bool boundary, int tid) {
+  if (!a.waitCtl) return;
+  const bool first = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (!boundary && !first) return;
+  if (tid < a.waitRanks) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      unsigned f;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&a.waitCtl->flags[tid]) : "memory");
+      if (int(f - a.waitEpoch) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (a.waitCtl->timeout || t1 - t0 > 20000000000ull) {              // 20 s: a peer is gone; sticky, reported by the next API call
+        a.waitCtl->timeout = 1u;
+        if (a.waitTimeout) { *reinterpret_cast<volatile unsigned*>(a.waitTimeout) = 1u; __threadfence_system(); }
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  if (first && tid == 0) {
+    double m = 0.0;
+    for (int r = 0; r < a.waitRanks; ++r) m = fmax(m, *reinterpret_cast<volatile double*>(&a.waitCtl->cfl[a.waitParity][r]));
+    *a.waitSlot = m;
+  }
+}
+// does the CTA's tile x chunk lie within `overlap` cells of a side of the rank's interior box that has an overlap layer (a neighbour)?
+__device__ __forceinline__ bool fv_touches_rank_boundary(const dgb_view& v, int x0, int nx, int y0, int ny, int z0, int nz) {
+  const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
+  const dgb_box& in = v.comp[0].box[DGB_BOX_INTERIOR];
+  const int lo[3] = { x0, y0, z0 }, n[3] = { nx, ny, nz };
+  bool t = false;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (of.origin[i] < in.origin[i] && lo[i] < in.origin[i] + v.overlap) t = true;
+    if (of.origin[i]+of.size[i] > in.origin[i]+in.size[i] && lo[i]+n[i] > in.origin[i]+in.size[i] - v.overlap) t = true;
+  }
+  return t;
+}
+
 // the receiving side: thread s waits until rank s has delivered epoch `target`, then the reduced CFL value is stored
 __global__ void k_fv_wait(FusedCtl* ctl, int nranks, unsigned target, int parity, double* slot, unsigned* hostTimeout) {
   __shared__ int s_timed_out;
@@ -381,6 +427,9 @@ __global__ void __launch_bounds__(BX*BY) k_fv_march(const __grid_constant__ dgb_
   const int z0 = blockIdx.z*zc;
   const int zn = min(zc, a.region.size[2]-z0);
   double sum_max = 0.0;
+  if (!REDUCE_ONLY)
+    fv_peer_wait(a, fv_touches_rank_boundary(v, a.region.origin[0]+blockIdx.x*BX, min(BX, a.region.size[0]-(int)blockIdx.x*BX), a.region.origin[1]+by*BY,
+                                             min(BY, a.region.size[1]-by*BY), a.region.origin[2]+z0, zn), threadIdx.y*BX + threadIdx.x);
   if (i0 < a.region.size[0] && i1 < a.region.size[1]) {
     const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
     const dgb_box& ov = v.comp[0].box[DGB_BOX_OVERLAP];
@@ -812,6 +861,9 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     if ((!o2 && o3) || (o2 && o3 && f2 == 0.0 && f3 == 0.0)) dy = 1; else if (o2 && !o3) dy = 0;
     dz = (un5 >= 0.0) ? 1 : 0;
   }
+  // deferred completion of the previous step's exchange: boundary CTAs wait for the peers before their first read of c
+  fv_peer_wait(a, fv_touches_rank_boundary(v, a.region.origin[0]+blockIdx.x*BX, min(BX, a.region.size[0]-(int)blockIdx.x*BX), a.region.origin[1]+by*BY,
+                                           min(BY, a.region.size[1]-by*BY), cz0, zn), ty*BX + tx);
   // fused exchange: which send boxes this CTA's tile x chunk meets (read at the very end; the barriers below publish it)
   __shared__ FusedItem s_items[FUSED_MAX_BOXES];
   if (a.pack)
@@ -1088,6 +1140,9 @@ struct dgb_fv {
   // parity `xhParity` (read there by the next step, or unpacked on demand: fv_flush_xhalo)
   bool xhPending = false; double* xhArray = nullptr; int xhParity = 0;
   bool wantPair = false;         // the next launch_step must use the phase-aware pair staging (the only reader of FvArgs::xh)
+  // registered fields: the wait for the peers' flags of the last step has not been enqueued yet (it rides on the next step kernel, or
+  // on dgb_fv_fence): epoch to wait for, parity of its CFL values, slot that receives their maximum
+  bool waitPending = false; unsigned waitEpoch = 0; int waitParity = 0, waitSlot = 0;
   std::shared_ptr<CommPlan> plan;
   double* dStage[2] = {nullptr, nullptr};     // device staging for the host-buffer entry point
   double* dHostVote = nullptr;                // one device word: do all ranks take the pipelined host path?
@@ -1391,6 +1446,13 @@ static bool fv_ring_eligible(const dgb_fv* fv) {
 }
 // on-demand unpack of the x-face receive boxes into the array whose overlap column the hybrid exchange left stale
 static int fv_flush_xhalo(dgb_fv* fv, cudaStream_t stream) {
+  if (fv->waitPending) {                                  // the deferred flag wait (+ CFL reduction) of the last registered step
+    fv->waitPending = false;
+    FusedState& fs = fv->fused;
+    k_fv_wait<<<1, 64, 0, stream>>>(fs.ctl, fv->view.nranks, fv->waitEpoch, fv->waitParity, fv->dSlots + fv->waitSlot, fs.dTimeout);
+    ++fv->launches;
+    DGB_CUDA(cudaGetLastError());
+  }
   if (!fv->xhPending) return DGB_OK;
   fv->xhPending = false;
   FusedState& fs = fv->fused;
@@ -1455,13 +1517,23 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
       } else if (int rc = fv_flush_xhalo(fv, stream)) return rc;
     }
     a.pack = (slot >= 0 ? (hybrid ? fs.direct[slot].dHybrid : fs.direct[slot].dPack) : fs.dPack) + parity; a.packEpoch = fs.epoch + 1u; a.packSignal = 1;
+    if (fv->waitPending) {                               // the previous registered step left its flag wait to this kernel's boundary CTAs
+      a.waitCtl = fs.ctl; a.waitEpoch = fv->waitEpoch; a.waitParity = fv->waitParity; a.waitRanks = fv->view.nranks;
+      a.waitSlot = fv->dSlots + fv->waitSlot; a.waitTimeout = fs.dTimeout;
+      fv->waitPending = false;
+    }
     const int rcl = launch_step<false>(fv, a, stream);
     const bool readBuffer = fv->wantPair;
     fv->wantPair = false;
     if (rcl) return rcl;
     if (readBuffer) fv->xhPending = false;               // consumed (the array itself was never refreshed; it is an input only)
     if (hybrid) { fv->xhPending = true; fv->xhArray = d_c_out; fv->xhParity = parity; }
-    if (slot >= 0 || fv->plan->nRecvBoxes == 0) {
+    static const bool mergedEnv = [] { const char* e = getenv("DGB_FV_MERGED_WAIT"); return !(e && atoi(e) == 0); }();
+    if (slot >= 0 && mergedEnv) {
+      // registered output: ONE kernel per step. The wait for this step's flags is done by the boundary CTAs of the next step
+      // kernel (interior CTAs start at once and absorb the skew between the ranks), or by dgb_fv_fence
+      fv->waitPending = true; fv->waitEpoch = fs.epoch + 1u; fv->waitParity = parity; fv->waitSlot = int((n+2) % 4);
+    } else if (slot >= 0 || fv->plan->nRecvBoxes == 0) {
       k_fv_wait<<<1, 64, 0, stream>>>(fs.ctl, fv->view.nranks, fs.epoch + 1u, parity, fv->dSlots + ((n+2) % 4), fs.dTimeout); ++fv->launches;
     }
     if (slot < 0) {
