@@ -91,6 +91,7 @@ struct FvArgs {
   // the rank's boundary - they read halo cells and store into peer memory - first wait until every rank has delivered epoch
   // waitEpoch; the first CTA also reduces the published CFL maxima into *waitSlot (what k_fv_wait does). NULL: nothing pending.
   FusedCtl* waitCtl; unsigned waitEpoch; int waitParity, waitRanks; double* waitSlot; unsigned* waitTimeout;
+  unsigned debugSkipFaces;   // developer knob DGB_FV_SKIP_FACES (timing experiments only, wrong results): bit f = do not pack face boxes f
 };
 
 // ---- fused exchange, device side (dgb_comm.hh: FusedCtl / FusedPack) -------------------------------------------------
@@ -112,7 +113,7 @@ __device__ __forceinline__ void fv_fused_prepare(const FvArgs& a, const dgb_box&
     const int lz = max(z0, pb.origin[2]), hz = min(z0+nz, pb.origin[2]+pb.size[2]);
     FusedItem it;
     it.n = 0;
-    if (lx < hx && ly < hy && lz < hz) {
+    if (lx < hx && ly < hy && lz < hz && !(pb.face >= 0 && (a.debugSkipFaces >> pb.face & 1u))) {
       it.ex = hx-lx; it.ey = hy-ly; it.n = it.ex*it.ey*(hz-lz);
       // destination layout: the box's place in the receiver's exchange buffer (box-linear), or - registered fields - the
       // receiver's FIELD itself (row and plane strides of the receiver's stored box)
@@ -159,9 +160,13 @@ __device__ __forceinline__ int fv_tile_row(const FvArgs& a) {
 }
 // Called by ONE thread per CTA after a __syncthreads that follows fv_fused_pack and the CTA's CFL atomic: the last CTA of
 // the grid publishes the rank's outflow maximum and then the epoch in every rank's control block.
-__device__ __forceinline__ void fv_fused_signal(const FvArgs& a) {
+__device__ __forceinline__ void fv_fused_signal(const FvArgs& a, const FusedItem* items) {
   const FusedPack& P = *a.pack;
-  __threadfence_system();                            // the CTA's peer stores and its CFL atomic are performed
+  // the CTA's peer stores (and its CFL atomic) must be performed system-wide before it is counted; a CTA that stored nothing into
+  // peer memory needs no system-scope fence (it would only wait for its own streaming stores to drain: measured ~14 us per step)
+  bool stored = false;
+  for (int b = 0; b < P.nBoxes; ++b) stored = stored || items[b].n > 0;
+  if (stored) __threadfence_system(); else __threadfence();
   if (!a.packSignal) return;                         // an earlier slab launch of the step: the last launch signals for all
   const unsigned total = gridDim.x*gridDim.y*gridDim.z;
   if (atomicAdd(P.counter, 1u) == total-1) {
@@ -523,12 +528,12 @@ __global__ void __launch_bounds__(BX*BY) k_fv_march(const __grid_constant__ dgb_
     if (!REDUCE_ONLY && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = dt;
   }
   const int tid = threadIdx.y*BX + threadIdx.x;
+  __shared__ FusedItem s_march_items[FUSED_MAX_BOXES];
   if (!REDUCE_ONLY && a.pack) {
-    __shared__ FusedItem items[FUSED_MAX_BOXES];
     const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
-    fv_fused_prepare(a, of, items, a.region.origin[0]+blockIdx.x*BX, min(BX, a.region.size[0]-(int)blockIdx.x*BX),
+    fv_fused_prepare(a, of, s_march_items, a.region.origin[0]+blockIdx.x*BX, min(BX, a.region.size[0]-(int)blockIdx.x*BX),
                      a.region.origin[1]+by*BY, min(BY, a.region.size[1]-by*BY), a.region.origin[2]+z0, zn, tid);
-    fv_fused_pack<BX*BY>(a, of, items, tid);
+    fv_fused_pack<BX*BY>(a, of, s_march_items, tid);
   }
   for (int off = 16; off > 0; off >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, off));
   __shared__ double part[BX*BY/32];
@@ -539,7 +544,7 @@ __global__ void __launch_bounds__(BX*BY) k_fv_march(const __grid_constant__ dgb_
     for (int k = 0; k < BX*BY/32; ++k) m = fmax(m, part[k]);
     if (m > 0.0) atomic_max_nonneg(a.slotOut, m);
     if (a.slotZero && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *a.slotZero = 0.0;
-    if (!REDUCE_ONLY && a.pack) fv_fused_signal(a);
+    if (!REDUCE_ONLY && a.pack) fv_fused_signal(a, s_march_items);
   }
 }
 
@@ -1073,7 +1078,7 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     for (int k = 0; k < BX*BY/32; ++k) m = fmax(m, part[k]);
     if (m > 0.0) atomic_max_nonneg(a.slotOut, m);
     if (a.slotZero && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *a.slotZero = 0.0;
-    if (a.pack) fv_fused_signal(a);
+    if (a.pack) fv_fused_signal(a, s_items);
   }
 }
 
@@ -1306,6 +1311,8 @@ static FvArgs base_args(dgb_fv* fv) {
   const dgb_box& in = fv->view.comp[0].box[DGB_BOX_INTERIOR];
   for (int i = 0; i < 3; ++i) { a.region.origin[i] = in.origin[i]; a.region.size[i] = i < fv->view.dim ? in.size[i] : 1; }
   a.problem = fv->problem; a.tab = fv->tab; a.consts = fv->dSlots + 5;
+  static const unsigned skip = [] { const char* e = getenv("DGB_FV_SKIP_FACES"); return e ? unsigned(atoi(e)) : 0u; }();
+  a.debugSkipFaces = skip;
   return a;
 }
 

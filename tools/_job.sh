@@ -1,5 +1,5 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-python tools/fused_proxy.py 511 511 511 7 60 direct,fused 2>&1 | tail -4
-DGB_FV_MERGED_WAIT=0 python tools/fused_proxy.py 511 511 511 7 60 direct 2>&1 | tail -3
-python tools/sweep_bench.py > gpurun_out/r2j_sweeps.jsonl 2>&1
-python tools/intersections_probe.py > gpurun_out/r2j_intersections_probe.jsonl 2>&1; cat gpurun_out/r2j_intersections_probe.jsonl | cut -c1-200
+python -m pytest tests/test_gpu_comm_fv.py -m gpu -x -q 2>&1 | tail -3
+for m in 0 63; do echo "skip mask $m"; DGB_FV_SKIP_FACES=$m python tools/fused_proxy.py 511 511 511 7 60 direct 2>&1 | grep -E "^direct|kernel"; done
+echo "merged wait off"; DGB_FV_MERGED_WAIT=0 DGB_FV_SKIP_FACES=63 python tools/fused_proxy.py 511 511 511 7 60 direct 2>&1 | grep -E "^direct"
+echo "hybrid off"; DGB_FV_HYBRID=0 DGB_FV_SKIP_FACES=63 python tools/fused_proxy.py 511 511 511 7 60 direct 2>&1 | grep -E "^direct"
+echo "zchunk 256"; DGB_FV_ZCHUNK=256 DGB_FV_SKIP_FACES=63 python tools/fused_proxy.py 511 511 511 7 60 direct 2>&1 | grep -E "^direct"
