@@ -619,6 +619,7 @@ int fused_register(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaS
     }
     FusedState::Direct& d = dir[f];
     d.field = fields[f];
+    d.hDst = dst; d.hRow = row; d.hPlane = plane;
     auto up = [&](void** dev, const void* host, size_t bytes) {
       if (bytes == 0) return true;
       if (cudaMalloc(dev, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -633,11 +634,13 @@ int fused_register(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaS
     std::vector<int> rowH(row), planeH(plane);
     for (int b = 0; b < nb; ++b) if (plan.hostSend[b].face == 0 || plan.hostSend[b].face == 1) { rowH[b] = plan.hostSend[b].size[0]; planeH[b] = plan.hostSend[b].size[0]*plan.hostSend[b].size[1]; }
     ok = ok && up(reinterpret_cast<void**>(&d.dRowH), rowH.data(), nb*sizeof(int)) && up(reinterpret_cast<void**>(&d.dPlaneH), planeH.data(), nb*sizeof(int));
+    d.hRowH = rowH; d.hPlaneH = planeH;
     FusedPack ph[2] = { fs.hostPack[0], fs.hostPack[1] };
     for (int k = 0; k < 2; ++k) {
       std::vector<double*> dstH(dst);
       for (int b = 0; b < nb; ++b) if (plan.hostSend[b].face == 0 || plan.hostSend[b].face == 1) dstH[b] = fs.hostDst[k][b];
       ok = ok && up(reinterpret_cast<void**>(&d.dDstH[k]), dstH.data(), nb*sizeof(double*));
+      d.hDstH[k] = dstH;
       ph[k].dst = d.dDstH[k]; ph[k].dstRow = d.dRowH; ph[k].dstPlane = d.dPlaneH;
     }
     ok = ok && up(reinterpret_cast<void**>(&d.dHybrid), ph, 2*sizeof(FusedPack));

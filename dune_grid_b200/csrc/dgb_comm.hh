@@ -101,7 +101,9 @@ struct FusedState {
   // read-modify-write each) keep going to the receiver's contiguous exchange buffer; the receiver's NEXT step kernel reads
   // its x neighbours from that buffer (dgb_fv.cu, FvArgs::xh) and its overlap column is refreshed only on demand
   struct Direct { double* field = nullptr; FusedPack* dPack = nullptr; double** dDst = nullptr; int* dRow = nullptr; int* dPlane = nullptr;
-                  FusedPack* dHybrid = nullptr; double** dDstH[2] = {nullptr, nullptr}; int* dRowH = nullptr; int* dPlaneH = nullptr; };
+                  FusedPack* dHybrid = nullptr; double** dDstH[2] = {nullptr, nullptr}; int* dRowH = nullptr; int* dPlaneH = nullptr;
+                  // host copies (the step kernels take the send boxes in their parameter space)
+                  std::vector<double*> hDst, hDstH[2]; std::vector<int> hRow, hPlane, hRowH, hPlaneH; };
   // this rank's x-face receive boxes (low side, high side): where the step kernel finds the x halo in the exchange buffer
   struct XFace { bool on = false; long long buf_offset = 0; int y0 = 0, z0 = 0, ny = 0; };
   XFace xface[2];

@@ -67,6 +67,13 @@ struct FvRegion { int origin[3], size[3]; };         // cells to update (a sub-b
 // per-axis tables for DGB_FV_SEPARABLE: reciprocal cell widths, cell centres and vertex coordinates
 struct FvTables { const double* rw[3]; const double* xc[3]; const double* xv[3]; int first[3]; };
 
+// the send boxes of the fused exchange travel in the kernel PARAMETER space (constant cache): every CTA intersects them with its
+// tile at its start, and a global-memory read there costs each of the ~2000 CTAs of a step a DRAM/L2 round trip before it streams
+struct FvSendBoxes {
+  int n;
+  struct Box { int origin[3], size[3]; int row, plane; double* dst; } box[32];      // row / plane: strides (doubles) of the destination
+};
+
 struct FvArgs {
   FvRegion region;
   FvProblem problem;
@@ -92,6 +99,7 @@ struct FvArgs {
   // waitEpoch; the first CTA also reduces the published CFL maxima into *waitSlot (what k_fv_wait does). NULL: nothing pending.
   FusedCtl* waitCtl; unsigned waitEpoch; int waitParity, waitRanks; double* waitSlot; unsigned* waitTimeout;
   unsigned debugSkipFaces;   // developer knob DGB_FV_SKIP_FACES (timing experiments only, wrong results): bit f = do not pack face boxes f
+  FvSendBoxes send;          // valid when pack != NULL
 };
 
 // ---- fused exchange, device side (dgb_comm.hh: FusedCtl / FusedPack) -------------------------------------------------
@@ -105,20 +113,19 @@ struct FusedItem { double* dst0; long long src0; int ex, ey, n, dsy, dsz; };
 static constexpr int FUSED_MAX_BOXES = 32;
 __device__ __forceinline__ void fv_fused_prepare(const FvArgs& a, const dgb_box& of, FusedItem* items, int x0, int nx, int y0, int ny,
                                                  int z0, int nz, int tid) {
-  const FusedPack& P = *a.pack;
-  if (tid < P.nBoxes) {
-    const PlanBox& pb = P.boxes[tid];
+  if (tid < a.send.n) {
+    const FvSendBoxes::Box& pb = a.send.box[tid];
     const int lx = max(x0, pb.origin[0]), hx = min(x0+nx, pb.origin[0]+pb.size[0]);
     const int ly = max(y0, pb.origin[1]), hy = min(y0+ny, pb.origin[1]+pb.size[1]);
     const int lz = max(z0, pb.origin[2]), hz = min(z0+nz, pb.origin[2]+pb.size[2]);
     FusedItem it;
     it.n = 0;
-    if (lx < hx && ly < hy && lz < hz && !(pb.face >= 0 && (a.debugSkipFaces >> pb.face & 1u))) {
+    if (lx < hx && ly < hy && lz < hz) {
       it.ex = hx-lx; it.ey = hy-ly; it.n = it.ex*it.ey*(hz-lz);
       // destination layout: the box's place in the receiver's exchange buffer (box-linear), or - registered fields - the
       // receiver's FIELD itself (row and plane strides of the receiver's stored box)
-      it.dsy = P.dstRow ? P.dstRow[tid] : pb.size[0]; it.dsz = P.dstPlane ? P.dstPlane[tid] : pb.size[0]*pb.size[1];
-      it.dst0 = P.dst[tid] + ((long long)(lz-pb.origin[2])*it.dsz + (long long)(ly-pb.origin[1])*it.dsy) + (lx-pb.origin[0]);
+      it.dsy = pb.row; it.dsz = pb.plane;
+      it.dst0 = pb.dst + ((long long)(lz-pb.origin[2])*it.dsz + (long long)(ly-pb.origin[1])*it.dsy) + (lx-pb.origin[0]);
       it.src0 = ((long long)(lz-of.origin[2])*of.size[1] + (ly-of.origin[1]))*of.size[0] + (lx-of.origin[0]);
       items[tid] = it;
     } else items[tid].n = 0;
@@ -126,7 +133,7 @@ __device__ __forceinline__ void fv_fused_prepare(const FvArgs& a, const dgb_box&
 }
 template<int NT>
 __device__ __forceinline__ void fv_fused_pack(const FvArgs& a, const dgb_box& of, const FusedItem* items, int tid) {
-  const int nBoxes = a.pack->nBoxes;
+  const int nBoxes = a.send.n;
   const int sy = of.size[0]; const long long sz = (long long)of.size[0]*of.size[1];
   __syncthreads();                                   // the CTA's stores to c_new are visible to all its threads
   for (int b = 0; b < nBoxes; ++b) {
@@ -165,7 +172,7 @@ __device__ __forceinline__ void fv_fused_signal(const FvArgs& a, const FusedItem
   // the CTA's peer stores (and its CFL atomic) must be performed system-wide before it is counted; a CTA that stored nothing into
   // peer memory needs no system-scope fence (it would only wait for its own streaming stores to drain: measured ~14 us per step)
   bool stored = false;
-  for (int b = 0; b < P.nBoxes; ++b) stored = stored || items[b].n > 0;
+  for (int b = 0; b < a.send.n; ++b) stored = stored || items[b].n > 0;
   if (stored) __threadfence_system(); else __threadfence();
   if (!a.packSignal) return;                         // an earlier slab launch of the step: the last launch signals for all
   const unsigned total = gridDim.x*gridDim.y*gridDim.z;
@@ -178,16 +185,24 @@ __device__ __forceinline__ void fv_fused_signal(const FvArgs& a, const FusedItem
     for (int r = 0; r < P.nranks; ++r) *reinterpret_cast<volatile unsigned*>(P.peerFlag[r]) = a.packEpoch;
   }
 }
-// see FvArgs::waitCtl. Called by all threads of a CTA before the CTA's first read of c; `boundary` is CTA-uniform.
-__device__ __forceinline__ void fv_peer_wait(const FvArgs& a, bool boundary, int tid) {
+// see FvArgs::waitCtl. fv_peer_wait_issue (at the very top of the kernel) only ISSUES the flag load, so that its latency overlaps the
+// table loads of the column set-up; fv_peer_wait_finish - called by all threads of the CTA before the CTA's first read of c, with
+// the CTA-uniform `boundary` - spins if the peer has not delivered yet and publishes the result to the CTA.
+__device__ __forceinline__ unsigned fv_peer_wait_issue(const FvArgs& a, bool boundary, int tid) {
+  unsigned f = a.waitEpoch;
+  const bool first = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (a.waitCtl && (boundary || first) && tid < a.waitRanks)
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&a.waitCtl->flags[tid]) : "memory");
+  return f;
+}
+__device__ __forceinline__ void fv_peer_wait_finish(const FvArgs& a, bool boundary, int tid, unsigned f) {
   if (!a.waitCtl) return;
   const bool first = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   if (!boundary && !first) return;
-  if (tid < a.waitRanks) {
+  if (tid < a.waitRanks && int(f - a.waitEpoch) < 0) {
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
-      unsigned f;
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(&a.waitCtl->flags[tid]) : "memory");
       if (int(f - a.waitEpoch) >= 0) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -432,9 +447,12 @@ __global__ void __launch_bounds__(BX*BY) k_fv_march(const __grid_constant__ dgb_
   const int z0 = blockIdx.z*zc;
   const int zn = min(zc, a.region.size[2]-z0);
   double sum_max = 0.0;
-  if (!REDUCE_ONLY)
-    fv_peer_wait(a, fv_touches_rank_boundary(v, a.region.origin[0]+blockIdx.x*BX, min(BX, a.region.size[0]-(int)blockIdx.x*BX), a.region.origin[1]+by*BY,
-                                             min(BY, a.region.size[1]-by*BY), a.region.origin[2]+z0, zn), threadIdx.y*BX + threadIdx.x);
+  if (!REDUCE_ONLY) {
+    const bool bnd = fv_touches_rank_boundary(v, a.region.origin[0]+blockIdx.x*BX, min(BX, a.region.size[0]-(int)blockIdx.x*BX), a.region.origin[1]+by*BY,
+                                              min(BY, a.region.size[1]-by*BY), a.region.origin[2]+z0, zn);
+    const unsigned f = fv_peer_wait_issue(a, bnd, threadIdx.y*BX + threadIdx.x);
+    fv_peer_wait_finish(a, bnd, threadIdx.y*BX + threadIdx.x, f);
+  }
   if (i0 < a.region.size[0] && i1 < a.region.size[1]) {
     const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
     const dgb_box& ov = v.comp[0].box[DGB_BOX_OVERLAP];
@@ -812,6 +830,11 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   const bool active = i0 < a.region.size[0] && i1 < a.region.size[1];
   const int zbase = cz0-a.tab.first[2];
   const double* rwz = a.tab.rw[2] + zbase;
+  // deferred completion of the previous step's exchange: boundary CTAs wait for the peers before their first read of c; the flag
+  // load is issued here, its latency overlaps the table loads below
+  const bool rankBoundary = fv_touches_rank_boundary(v, a.region.origin[0]+blockIdx.x*BX, min(BX, a.region.size[0]-(int)blockIdx.x*BX), a.region.origin[1]+by*BY,
+                                                     min(BY, a.region.size[1]-by*BY), cz0, zn);
+  const unsigned peerFlag = fv_peer_wait_issue(a, rankBoundary, ty*BX + tx);
   double rwmax = 0.0;
   for (int k = tx & 31; k < zn; k += 32) rwmax = fmax(rwmax, __ldg(rwz + k));
   for (int o = 16; o > 0; o >>= 1) rwmax = fmax(rwmax, __shfl_xor_sync(0xffffffffu, rwmax, o));
@@ -866,9 +889,7 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     if ((!o2 && o3) || (o2 && o3 && f2 == 0.0 && f3 == 0.0)) dy = 1; else if (o2 && !o3) dy = 0;
     dz = (un5 >= 0.0) ? 1 : 0;
   }
-  // deferred completion of the previous step's exchange: boundary CTAs wait for the peers before their first read of c
-  fv_peer_wait(a, fv_touches_rank_boundary(v, a.region.origin[0]+blockIdx.x*BX, min(BX, a.region.size[0]-(int)blockIdx.x*BX), a.region.origin[1]+by*BY,
-                                           min(BY, a.region.size[1]-by*BY), cz0, zn), ty*BX + tx);
+  fv_peer_wait_finish(a, rankBoundary, ty*BX + tx, peerFlag);
   // fused exchange: which send boxes this CTA's tile x chunk meets (read at the very end; the barriers below publish it)
   __shared__ FusedItem s_items[FUSED_MAX_BOXES];
   if (a.pack)
@@ -1447,6 +1468,19 @@ int dgb_fv_init_field(dgb_fv* fv, double* d_c, void* stream) {
   return DGB_OK;
 }
 
+// the send boxes of this step for the kernel's parameter space: origins / sizes from the plan, destinations by exchange form
+static void fill_send_boxes(FvArgs& a, const CommPlan& plan, const std::vector<double*>& dst, const std::vector<int>* row, const std::vector<int>* plane) {
+  a.send.n = plan.nSendBoxes;
+  for (int b = 0; b < plan.nSendBoxes && b < 32; ++b) {
+    const PlanBox& pb = plan.hostSend[b];
+    FvSendBoxes::Box& o = a.send.box[b];
+    for (int i = 0; i < 3; ++i) { o.origin[i] = pb.origin[i]; o.size[i] = pb.size[i]; }
+    o.row = row ? (*row)[b] : pb.size[0]; o.plane = plane ? (*plane)[b] : pb.size[0]*pb.size[1];
+    o.dst = dst[b];
+    if (pb.face >= 0 && (a.debugSkipFaces >> pb.face & 1u)) o.size[0] = 0;          // developer knob: empty box
+  }
+}
+
 // the step would run on the ring kernel (the only one that can read its x halo from the exchange buffer)
 static bool fv_ring_eligible(const dgb_fv* fv) {
   return fv->view.dim == 3 && fv->mode == DGB_FV_SEPARABLE && fv->variant != 99 && fv_problem_column_invariant(fv->problem.id);
@@ -1524,6 +1558,9 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
       } else if (int rc = fv_flush_xhalo(fv, stream)) return rc;
     }
     a.pack = (slot >= 0 ? (hybrid ? fs.direct[slot].dHybrid : fs.direct[slot].dPack) : fs.dPack) + parity; a.packEpoch = fs.epoch + 1u; a.packSignal = 1;
+    if (slot < 0) fill_send_boxes(a, *fv->plan, fs.hostDst[parity], nullptr, nullptr);
+    else if (hybrid) fill_send_boxes(a, *fv->plan, fs.direct[slot].hDstH[parity], &fs.direct[slot].hRowH, &fs.direct[slot].hPlaneH);
+    else fill_send_boxes(a, *fv->plan, fs.direct[slot].hDst, &fs.direct[slot].hRow, &fs.direct[slot].hPlane);
     if (fv->waitPending) {                               // the previous registered step left its flag wait to this kernel's boundary CTAs
       a.waitCtl = fs.ctl; a.waitEpoch = fv->waitEpoch; a.waitParity = fv->waitParity; a.waitRanks = fv->view.nranks;
       a.waitSlot = fv->dSlots + fv->waitSlot; a.waitTimeout = fs.dTimeout;
@@ -1785,7 +1822,8 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
       a.region.origin[2] = zlo(i); a.region.size[2] = zhi(i)-zlo(i);
       a.c = fv->dStage[0]; a.cnew = fv->dStage[1];
       slot_args(fv, sn, a);
-      if (fused) { a.pack = fs.dPack + parity; a.packEpoch = fs.epoch + 1u; a.packSignal = (i == lastLaunch) ? 1 : 0; }
+      if (fused) { a.pack = fs.dPack + parity; a.packEpoch = fs.epoch + 1u; a.packSignal = (i == lastLaunch) ? 1 : 0;
+                   fill_send_boxes(a, *fv->plan, fs.hostDst[parity], nullptr, nullptr); }
       if (int rc = launch_step<false>(fv, a, stream)) return rc;
     }
     DGB_CUDA(cudaEventRecord(fv->evK[i], stream));
