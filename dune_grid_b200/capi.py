@@ -87,6 +87,7 @@ _SIG = {
     "dgb_intersection_normals": (_i, [_pv, _i, _vp, _vp, _vp]),
     "dgb_intersection_local_geometry": (_i, [_i, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "dgb_geometry_eval": (_i, [_pv, _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp, _vp]),
+    "dgb_geometry_eval_codim": (_i, [_pv, _i, _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp]),
     "dgb_geogrid_eval": (_i, [_pv, _i, _i, C.POINTER(C.c_double), _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp, _vp]),
     "dgb_geogrid_intersections": (_i, [_pv, _i, _i, C.POINTER(C.c_double), _i, _i, C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dgb_geogrid_volume": (_i, [_pv, _i, _i, C.POINTER(C.c_double), _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp, _vp]),

@@ -423,6 +423,41 @@ __global__ void __launch_bounds__(BX) k_geometry(const __grid_constant__ dgb_vie
   }
 }
 
+
+// ---- K4b: axis-aligned geometry of the entities of ANY codimension at local points ---------------------------------------
+// AxisAlignedCubeGeometry<mydim, dim> (yaspgrid/yaspgridgeometry.hh:30-77; entity geometries yaspgridentity.hh:270-274, 491-514,
+// 849-851): the axes in the component's shift span the entity, the others are flat at the lower corner; only cells are wrapped
+// periodically. global[(q*dim+d)*n+e], jt[((q*mydim+r)*dim+c)*n+e], jit[((q*dim+r)*mydim+c)*n+e], detJ[q*n+e].
+struct GeoOutCodim { double *global, *jt, *jit, *detJ; };
+
+__global__ void __launch_bounds__(BX) k_geometry_codim(const __grid_constant__ dgb_view v, const SweepGeom s, const QuadPoints q, const GeoOutCodim o) {
+  int coord[3]; long long pos;
+  if (!sweep_entity<1>(v, s, 0, coord, pos)) return;
+  const dgb_component& c = v.comp[s.comp];
+  const int dim = v.dim, mydim = dim - c.codim;
+  double ll[3], w[3], vol = 1.0;
+  int local[3];                                        // local coordinate number of a spanned axis, -1 for a flat one
+  int lc = 0;
+  for (int i = 0; i < dim; ++i) {
+    const bool ext = c.shift >> i & 1u;
+    double lo = vertex_coord(v, i, coord[i]), hi = ext ? vertex_coord(v, i, coord[i]+1) : lo;
+    if (c.codim == 0) { const double sh = periodic_shift(v, i, coord[i]); if (sh != 0.0) { lo += sh; hi += sh; } }
+    ll[i] = lo; w[i] = hi-lo;
+    local[i] = ext ? lc++ : -1;
+    if (ext) vol *= w[i];
+  }
+  for (int p = 0; p < q.n; ++p) {
+    for (int i = 0; i < dim; ++i) {
+      if (o.global) o.global[((long long)p*dim + i)*s.n + pos] = local[i] >= 0 ? ll[i] + q.x[p*mydim + local[i]]*w[i] : ll[i];
+      for (int r = 0; r < mydim; ++r) {
+        if (o.jt) o.jt[(((long long)p*mydim + r)*dim + i)*s.n + pos] = (local[i] == r) ? w[i] : 0.0;
+        if (o.jit) o.jit[(((long long)p*dim + i)*mydim + r)*s.n + pos] = (local[i] == r) ? 1.0/w[i] : 0.0;
+      }
+    }
+    if (o.detJ) o.detJ[(long long)p*s.n + pos] = vol;
+  }
+}
+
 // ---- K8: GeometryGrid (multilinear geometry over deformed corners) ------------------------------------
 struct GeoGridOut { double *corners, *global, *jt, *jit, *detJ; };
 
@@ -772,6 +807,19 @@ int dgb_geometry_eval(const dgb_view* v, int pitype, int nqp, const double* qp_h
   GeoOut o{d_global, d_jit, d_detJ};
   return for_each_component(*v, 0, pitype, 1, [&](const SweepGeom& s, dim3 grid) {
     k_geometry<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, q, o);
+  });
+}
+
+int dgb_geometry_eval_codim(const dgb_view* v, int codim, int pitype, int nqp, const double* qp_host, double* d_global, double* d_jt,
+                            double* d_jit, double* d_detJ, void* stream) {
+  if (codim < 0 || codim > v->dim) return fail(DGB_EARG, "bad codim");
+  if (int rc = check_tensor(*v)) return rc;
+  if (nqp < 0 || nqp > 27) return fail(DGB_EARG, "at most 27 quadrature points per call");
+  QuadPoints q; q.n = nqp;
+  for (int i = 0; i < nqp*(v->dim-codim); ++i) q.x[i] = qp_host[i];
+  GeoOutCodim o{d_global, d_jt, d_jit, d_detJ};
+  return for_each_component(*v, codim, pitype, 1, [&](const SweepGeom& s, dim3 grid) {
+    k_geometry_codim<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, q, o);
   });
 }
 

@@ -336,6 +336,20 @@ class GridView:
                                     _ptr(r["jacobianInverseTransposed"]), _ptr(r["integrationElement"]), _stream()))
         return r
 
+    def geometryCodim(self, codim, qp, partition=All_Partition):
+        """e.geometry() of the entities of `codim` at local points qp (nqp x (dim-codim)): global (nq, d, n), jacobianTransposed
+        (nq, m, d, n), jacobianInverseTransposed (nq, d, m, n), integrationElement (nq, n)"""
+        _require_cuda()
+        torch = _torch()
+        d, m = self.dim, self.dim - codim
+        qp = np.ascontiguousarray(qp, dtype=np.float64).reshape(-1, max(1, m))
+        n, nq = self.size(codim, partition), qp.shape[0]
+        z = lambda *shape: torch.empty(shape, dtype=torch.float64, device="cuda")       # noqa: E731
+        r = {"global": z(nq, d, n), "jacobianTransposed": z(nq, m, d, n), "jacobianInverseTransposed": z(nq, d, m, n), "integrationElement": z(nq, n)}
+        check(lib.dgb_geometry_eval_codim(C.byref(self.v), codim, partition, nq, qp.ctypes.data_as(C.POINTER(C.c_double)), _ptr(r["global"]),
+                                          _ptr(r["jacobianTransposed"]), _ptr(r["jacobianInverseTransposed"]), _ptr(r["integrationElement"]), _stream()))
+        return r
+
     def geometryGrid(self, deformation, params, qp, partition=All_Partition, corners=True):
         """GeometryGrid<YaspGrid, F> geometries: corners (2^dim x dim x n), global, jacobianTransposed,
         jacobianInverseTransposed, integrationElement at local points qp"""

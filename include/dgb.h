@@ -194,6 +194,12 @@ int dgb_intersection_local_geometry(int dim, int k, int in_outside, double* lowe
  *      cells of the partition: global[(q*dim+d)*n+e], jit[((q*dim+r)*dim+c)*n+e], detJ[q*n+e] (common/geometry.hh:194-371) */
 int dgb_geometry_eval(const dgb_view* v, int pitype, int nqp, const double* qp_host,
                       double* d_global, double* d_jit, double* d_detJ, void* stream);
+/* the same for the entities of ANY codimension (faces, edges, vertices at quadrature points): AxisAlignedCubeGeometry<mydim,dim>,
+ * mydim = dim-codim, local points qp_host (nqp*mydim): global[(q*dim+d)*n+e], jacobianTransposed jt[((q*mydim+r)*dim+c)*n+e],
+ * jacobianInverseTransposed jit[((q*dim+r)*mydim+c)*n+e], integrationElement detJ[q*n+e]; entities in the iteration order of the
+ * partition (components of the codim in ascending shift). yaspgridentity.hh:270-274, 849-851; NULL = skip. */
+int dgb_geometry_eval_codim(const dgb_view* v, int codim, int pitype, int nqp, const double* qp_host,
+                            double* d_global, double* d_jt, double* d_jit, double* d_detJ, void* stream);
 /* ---- GeometryGrid over the Yasp host view with a compiled-in analytic coordinate function
  *      (geometrygrid/cornerstorage.hh:54-60, coordfunctioncaller.hh:40-43, geometry.hh:197-204). deformation: 0 identity,
  *      1 the sine field of SURVEY.md §8d config 5 (amplitude params_host[0]). corners[(k*dim+d)*n+e], jt like jit. */

@@ -103,6 +103,7 @@ class OracleLib:
             "orc_mapper_subindex": (i64, [vp, i32, i32, pu32, i32, i32, pu32]),
             "orc_intersections": (i64, [vp, i32, i32, i32, pu8, pu8, pi32, pi32, pd, pd, pd]),
             "orc_geometry_eval": (i64, [vp, i32, i32, i32, i32, pd, pd, pd, pd]),
+            "orc_geometry_eval_codim": (i64, [vp, i32, i32, i32, i32, i32, pd, pd, pd, pd, pd]),
             "orc_geogrid_eval": (i64, [vp, i32, i32, i32, i32, pd, i32, pd, pd, pd, pd, pd, pd]),
             "orc_geogrid_intersections": (i64, [vp, i32, i32, i32, i32, pd, i32, pd, pd, pd, pd, pd, pd, pd, pd]),
             "orc_communicate": (i64, [vp, i32, pu32, i32, i32, i32, i32, ppd, pi]),
@@ -299,6 +300,18 @@ class World:
         r = {"global": np.zeros((n, nq, d)), "jit": np.zeros((n, nq, d, d)), "detJ": np.zeros((n, nq))}
         self._chk(self.L.orc_geometry_eval(self.h, rank, level, pitype, nq, _p(qp, C.c_double), _p(r["global"], C.c_double),
                                            _p(r["jit"], C.c_double), _p(r["detJ"], C.c_double)))
+        return r
+
+    def geometry_eval_codim(self, rank, level, codim, qp, pitype=All_Partition):
+        """e.geometry() of the entities of `codim` at local points qp (nqp x (dim-codim)): global (n, nq, d), jt (n, nq, m, d),
+        jit (n, nq, d, m), detJ (n, nq)"""
+        d, m = self.dim, self.dim - codim
+        qp = np.ascontiguousarray(qp, dtype=np.float64).reshape(-1, max(1, m))
+        nq = qp.shape[0]
+        n = self._chk(self.L.orc_entities(self.h, rank, level, codim, pitype, None, None, None, None, None, None, None))
+        r = {"global": np.zeros((n, nq, d)), "jt": np.zeros((n, nq, m, d)), "jit": np.zeros((n, nq, d, m)), "detJ": np.zeros((n, nq))}
+        self._chk(self.L.orc_geometry_eval_codim(self.h, rank, level, codim, pitype, nq, _p(qp, C.c_double), _p(r["global"], C.c_double),
+                                                 _p(r["jt"], C.c_double), _p(r["jit"], C.c_double), _p(r["detJ"], C.c_double)))
         return r
 
     def geogrid_eval(self, rank, level, deformation, params, qp, pitype=All_Partition):

@@ -92,6 +92,11 @@ int64_t orc_intersections(void* w, int rank, int level, int pitype,
 /* a8: geometry at quadrature points for codim-0 cells: global n×nqp×dim, jit n×nqp×dim×dim (row major), detJ n×nqp */
 int64_t orc_geometry_eval(void* w, int rank, int level, int pitype, int nqp, const double* qp,
                           double* global, double* jit, double* detJ);
+/* a8 for any codimension: e.geometry() of the entities of `codim` (AxisAlignedCubeGeometry<dim-codim, dim>; only cells are wrapped
+ * periodically, yaspgridentity.hh:270-274) at nqp local points qp (nqp x mydim, mydim = dim-codim): global n x nqp x dim,
+ * jt (jacobianTransposed) n x nqp x mydim x dim, jit n x nqp x dim x mydim, detJ n x nqp. Returns the entity count. */
+int64_t orc_geometry_eval_codim(void* w, int rank, int level, int codim, int pitype, int nqp, const double* qp,
+                                double* global, double* jt, double* jit, double* detJ);
 /* a9: GeometryGrid over the Yasp host level: corners n×2^dim×dim, then as above with jt too */
 int64_t orc_geogrid_eval(void* w, int rank, int level, int pitype, int deformation, const double* params,
                          int nqp, const double* qp, double* corners, double* global, double* jt, double* jit, double* detJ);

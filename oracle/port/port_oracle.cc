@@ -811,6 +811,30 @@ int64_t orc_intersections(void* w, int rank, int level, int pitype, uint8_t* nei
     });
   });
 }
+// AxisAlignedCubeGeometry<mydim,dim> of a codim entity: the axes of its shift span it, the others are flat at the lower corner
+int64_t orc_geometry_eval_codim(void* w, int rank, int level, int codim, int pitype, int nqp, const double* qp, double* global, double* jt, double* jit, double* detJ) {
+  return guarded(int64_t(-1), [&]() -> int64_t {
+    const World& wd = *W(w); const int dim = wd.dim, mydim = dim-codim;
+    return wd.forEachEntity(rank, level, codim, pitype, [&](const Level& g, int kcomp, const I3& c, int, int64_t n) {
+      const unsigned shift = g.comp[codim][kcomp].shift;
+      double ll[3] = {0,0,0}, ur[3] = {0,0,0}; wd.bounds(g, c, shift, codim == 0, ll, ur);
+      double vol = 1.0;
+      for (int i = 0; i < dim; ++i) { if (!(shift >> i & 1u)) ur[i] = ll[i]; else vol *= ur[i]-ll[i]; }
+      for (int q = 0; q < nqp; ++q) {
+        const int64_t k = n*nqp + q;
+        int lc = 0;
+        for (int i = 0; i < dim; ++i) {
+          const bool sp = shift >> i & 1u;
+          if (global) global[k*dim+i] = sp ? ll[i] + qp[q*mydim+lc]*(ur[i]-ll[i]) : ll[i];
+          if (jt) for (int r = 0; r < mydim; ++r) jt[(k*mydim+r)*dim+i] = (sp && r == lc) ? ur[i]-ll[i] : 0.0;
+          if (jit) for (int r = 0; r < mydim; ++r) jit[(k*dim+i)*mydim+r] = (sp && r == lc) ? 1.0/(ur[i]-ll[i]) : 0.0;
+          if (sp) ++lc;
+        }
+        if (detJ) detJ[k] = vol;
+      }
+    });
+  });
+}
 int64_t orc_geometry_eval(void* w, int rank, int level, int pitype, int nqp, const double* qp, double* global, double* jit, double* detJ) {
   return guarded(int64_t(-1), [&]() -> int64_t {
     const World& wd = *W(w); const int dim = wd.dim;

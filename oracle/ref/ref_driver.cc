@@ -149,6 +149,7 @@ struct WorldBase {
   virtual int64_t mapperSubIndex(int rank, int level, const uint32_t* block, int pit, int cc, uint32_t*) = 0;
   virtual int64_t intersections(int rank, int level, int pit, uint8_t*, uint8_t*, int32_t*, int32_t*, double*, double*, double*) = 0;
   virtual int64_t geometryEval(int rank, int level, int pit, int nqp, const double* qp, double*, double*, double*) = 0;
+  virtual int64_t geometryEvalCodim(int rank, int level, int codim, int pit, int nqp, const double* qp, double*, double*, double*, double*) = 0;
   virtual int64_t geogridEval(int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
                               double*, double*, double*, double*, double*) = 0;
   virtual int64_t geogridIntersections(int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
@@ -481,6 +482,29 @@ struct World : WorldBase {
     return n;
   }
 
+  int64_t geometryEvalCodim(int rank, int level, int codim, int pit, int nqp, const double* qp, double* global, double* jt, double* jit, double* detJ) override {
+    Grid& gr = g(rank);
+    int64_t n = 0;
+    dispatch<dim>(codim, pit, [&](auto cdc, auto pitc) {
+      constexpr int cd = decltype(cdc)::value;
+      constexpr int mydim = dim-cd;
+      constexpr Dune::PartitionIteratorType pt = decltype(pitc)::value;
+      auto end = gr.template lend<cd,pt>(level);
+      for (auto it = gr.template lbegin<cd,pt>(level); it != end; ++it, ++n) {
+        auto geo = it->geometry();
+        for (int q = 0; q < nqp; ++q) {
+          Dune::FieldVector<double,mydim> x; for (int i = 0; i < mydim; ++i) x[i] = qp[q*mydim+i];
+          const int64_t k = n*nqp + q;
+          if (global) { auto y = geo.global(x); for (int i = 0; i < dim; ++i) global[k*dim+i] = y[i]; }
+          if (jt) { auto J = geo.jacobianTransposed(x); for (int i = 0; i < mydim; ++i) for (int j = 0; j < dim; ++j) jt[(k*mydim+i)*dim+j] = J[i][j]; }
+          if (jit) { auto J = geo.jacobianInverseTransposed(x); for (int i = 0; i < dim; ++i) for (int j = 0; j < mydim; ++j) jit[(k*dim+i)*mydim+j] = J[i][j]; }
+          if (detJ) detJ[k] = geo.integrationElement(x);
+        }
+      }
+    });
+    return n;
+  }
+
   // GeometryGrid<YaspGrid, AnalyticalCoordFunction>: corners = F(hostGeometry.corner(i))
   // (reference geometrygrid/cornerstorage.hh:54-60, hostcorners.hh:40-43, coordfunctioncaller.hh:40-43), geometry =
   // MultiLinearGeometry over those corners (geometrygrid/geometry.hh:66,197-204) — the multilinear part is the
@@ -767,6 +791,9 @@ int64_t orc_intersections(void* w, int rank, int level, int pit, uint8_t* neighb
 }
 int64_t orc_geometry_eval(void* w, int rank, int level, int pit, int nqp, const double* qp, double* global, double* jit, double* detJ) {
   return guarded(int64_t(-1), [&]{ return W(w)->geometryEval(rank, level, pit, nqp, qp, global, jit, detJ); });
+}
+int64_t orc_geometry_eval_codim(void* w, int rank, int level, int codim, int pit, int nqp, const double* qp, double* global, double* jt, double* jit, double* detJ) {
+  return guarded(int64_t(-1), [&]{ return W(w)->geometryEvalCodim(rank, level, codim, pit, nqp, qp, global, jt, jit, detJ); });
 }
 int64_t orc_geogrid_eval(void* w, int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
                          double* corners, double* global, double* jt, double* jit, double* detJ) {

@@ -262,3 +262,27 @@ def test_yasp_intersection_normals_and_local_geometries(cfg):
         e_lo[k // 2] = e_hi[k // 2] = float(1 - k % 2)
         assert np.array_equal(lo, e_lo) and np.array_equal(hi, e_hi)
     w.close()
+
+
+@pytest.mark.parametrize("cfg", [make_cfg(dim=3, N=(6, 5, 4), mode=2, periodic=1), make_cfg(dim=2, N=(9, 8), periodic=2, upper=(2.0, 0.5)),
+                                 make_cfg(dim=3, N=(4, 4, 4), refine=1, mode=1, lower=(-1.0, 0.0, 0.5), upper=(1.0, 1.0, 2.0))],
+                         ids=["tensor3d", "periodic2d", "offset3d_refined"])
+def test_geometry_of_all_codimensions_at_local_points(cfg):
+    """Geometry::global / jacobianTransposed / jacobianInverseTransposed / integrationElement of the entities of EVERY codimension
+    (faces and edges at quadrature points, vertices) bit for bit against the oracle's e.geometry()"""
+    d, lvl = cfg["dim"], cfg["refine"]
+    o = best_oracle()
+    w = oracle_world(o, cfg, 1)
+    g = product_grid(cfg, 0, 1)
+    gv = g.levelGridView(lvl)
+    for codim in range(d + 1):
+        m = d - codim
+        qp = np.array([[0.3, 0.7, 0.1][:max(1, m)], [0.5] * max(1, m), [1.0, 0.0, 0.25][:max(1, m)]])
+        for pit in (4, 0):
+            ref = w.geometry_eval_codim(0, lvl, codim, qp, pit)
+            got = gv.geometryCodim(codim, qp, pit)
+            assert np.array_equal(np.transpose(np_(got["global"]), (2, 0, 1)), ref["global"]), (codim, pit)
+            assert np.array_equal(np.transpose(np_(got["jacobianTransposed"]), (3, 0, 1, 2)), ref["jt"]), (codim, pit)
+            assert np.array_equal(np.transpose(np_(got["jacobianInverseTransposed"]), (3, 0, 1, 2)), ref["jit"]), (codim, pit)
+            assert np.array_equal(np_(got["integrationElement"]).T, ref["detJ"]), (codim, pit)
+    w.close()
