@@ -1195,7 +1195,9 @@ namespace dgb {
 static int auto_zchunk(const int* size, int bx, int by, bool packs) {
   const long long tiles = (long long)((size[0]+bx-1)/bx)*((size[1]+by-1)/by);
   const int resident = 148*1024/(bx*by);                       // CTAs the ring kernel keeps on the chip
-  int zc = (bx >= 128 && !packs) ? 256 : 128;
+  // measured with the exchange (tools/fused_proxy.py): 513^3 rank box (512 tiles): 128 planes 0.423 ms, 256 planes 0.433; 510x1024x1024
+  // (1024 tiles): 128 planes 1.634 ms, 256 planes 1.567 - long columns as soon as they still give >= 2048 CTAs (~7 waves)
+  int zc = (bx >= 128 && (!packs || tiles*((size[2]+255)/256) >= 2048)) ? 256 : 128;
   while (zc > 16 && tiles*((size[2]+zc-1)/zc) < 2*resident) zc /= 2;
   return zc;
 }
