@@ -577,6 +577,47 @@ def test_fv_step_host_pipelined(N, periodic):
     w.close()
 
 
+@pytest.mark.parametrize("registered", [False, True])
+@pytest.mark.parametrize("N,periodic", [((131, 21, 19), 7), ((260, 10, 18), 1), ((70, 45, 33), 6)])
+def test_fv_guard_bands_stay_untouched(N, periodic, registered, monkeypatch):
+    """compute-sanitizer is closed on the GPU pool (profiles/r02_sanitizer_note.md), so the bounds of the step kernels are checked
+    here: both fields live between NaN guard bands inside ONE allocation (a store outside a field changes a guard; a load
+    outside a field that reaches the arithmetic poisons the result with NaN). Every staging form, buffered / direct / hybrid
+    exchange, odd row and plane strides; results must equal the oracle."""
+    import torch
+    import dune_grid_b200 as dg
+    cfg = make_cfg(dim=3, N=N, periodic=periodic, upper=(1.0, 0.3, 0.4))
+    params = [0.8, -0.5, 0.25, 0.1, 0.5, 0.15, 0.2, 0.05, 0.3]
+    o = best_oracle()
+    w = oracle_world(o, cfg, 1)
+    ref = [w.fv_init(0, 0, 0, params)]
+    for _ in range(4):
+        w.fv_step(0, 0, params, ref)
+    g = product_grid(cfg, 0, 1)
+    n = g.leafGridView().size(0)
+    G = 1031                                                     # guard band length (odd: the fields start at odd multiples of 8 bytes)
+    for staging in ("pair", "8", "a16"):
+        monkeypatch.setenv("DGB_FV_STAGING", staging)
+        big = torch.full((3 * G + 2 * n,), float("nan"), dtype=torch.float64, device="cuda")
+        c, cn = big[G:G + n], big[2 * G + n:2 * G + 2 * n]
+        fv = dg.FiniteVolume(g, 0, 0, params, "separable")
+        c.copy_(fv.initial())
+        if registered:
+            assert fv.register_fields(c, cn) == 2
+        for _ in range(4):
+            fv.step(c, cn)
+            c, cn = cn, c
+        fv.fence()
+        assert fv.last_dt() > 0
+        guards = torch.cat([big[:G], big[G + n:2 * G + n], big[2 * G + 2 * n:]])
+        assert bool(torch.isnan(guards).all()), staging                       # no store outside the fields
+        got = np_(c)
+        assert not np.isnan(got).any(), staging                              # no guard value reached the arithmetic
+        assert np.abs(got - ref[0]).max() <= 1e-13 * np.abs(ref[0]).max(), staging
+        fv.close()
+    w.close()
+
+
 def test_fv_restart_from_backup(tmp_path):
     """restart of an FV run (SURVEY §8f row 3): grid through BackupRestoreFacility text, field through the checkpoint file;
     the restarted run must continue bit-identically, and the checkpoint must refuse a different grid"""
