@@ -73,6 +73,7 @@ _SIG = {
     "dgb_field_restore": (_i, [_vp, _i, C.POINTER(Mapper), _vp, _i, C.c_char_p, _vp]),
     "dgb_global_index": (_i, [_vp, _i, _i, _vp, _i64p, _vp, _vp]),
     "dgb_vtk_write": (_i, [_vp, _i, C.c_char_p, C.c_char_p, C.POINTER(VtkField), _i, C.POINTER(VtkField), _i, _i, C.c_char_p, _i, _vp]),
+    "dgb_vtk_write_ex": (_i, [_vp, _i, C.c_char_p, C.c_char_p, C.POINTER(VtkField), _i, C.POINTER(VtkField), _i, _i, _i, C.c_char_p, _i, _vp]),
     "dgb_grid_destroy": (_i, [_vp]), "dgb_grid_refine_options": (_i, [_vp, _i]), "dgb_grid_global_refine": (_i, [_vp, _i]),
     "dgb_grid_max_level": (_i, [_vp, C.POINTER(_i)]), "dgb_grid_torus_dims": (_i, [_vp, C.POINTER(C.c_int32)]),
     "dgb_grid_num_boundary_segments": (_i, [_vp, _i64p]), "dgb_grid_domain_size": (_i, [_vp, C.POINTER(C.c_double)]),

@@ -50,6 +50,35 @@ public:
   }
 };
 
+// ---- binary encodings (dataarraywriter.hh:196-420, streams.hh, b64enc.hh) -------------------------------------------------
+// base64: every DataArray carries base64(uint32 byte count), flushed (8 characters), then base64(data), flushed. appendedraw /
+// appendedbase64: the tag only names an offset into the <AppendedData> section, where the same header + data follow per array.
+static const char kB64[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+struct B64Sink {                                       // Base64Stream: 3 bytes -> 4 characters, '=' padding on flush
+  std::ostream& s; unsigned char t[3]; int n = 0;
+  explicit B64Sink(std::ostream& s_) : s(s_) {}
+  void put(unsigned char c) { t[n++] = c; if (n == 3) emit(); }
+  void write(const void* p, std::size_t bytes) { const unsigned char* q = static_cast<const unsigned char*>(p); for (std::size_t i = 0; i < bytes; ++i) put(q[i]); }
+  void emit() {
+    const unsigned a = t[0], b = n > 1 ? t[1] : 0u, c = n > 2 ? t[2] : 0u;
+    char o[4] = { kB64[a >> 2], kB64[(a & 3u) << 4 | b >> 4], n > 1 ? kB64[(b & 15u) << 2 | c >> 6] : '=', n > 2 ? kB64[c & 63u] : '=' };
+    s.write(o, 4); n = 0;
+  }
+  void flush() { if (n > 0) emit(); }
+};
+static std::size_t vtk_type_size(int prec) { return prec == 0 ? 4 : prec == 1 ? 8 : prec == 2 ? 4 : 1; }
+// one value in its file type (DataArrayWriter::write<T>: the static_cast of the virtual writeFloat32 / writeFloat64 / writeInt32 / writeUInt8)
+template<class Sink> static void vtk_put_value(Sink& sink, int prec, double x) {
+  if (prec == 0) { const float f = float(x); sink.write(&f, 4); }
+  else if (prec == 1) sink.write(&x, 8);
+  else if (prec == 2) { const std::int32_t i = std::int32_t(x); sink.write(&i, 4); }
+  else { const std::uint8_t u = std::uint8_t(x); sink.write(&u, 1); }
+}
+struct RawSink { std::ostream& s; void write(const void* p, std::size_t bytes) { s.write(static_cast<const char*>(p), std::streamsize(bytes)); } };
+
+// one array of the piece file, in file order
+struct VtkArrayData { int section; std::string name; int ncomps; long long nitems; int prec; std::vector<double> v; };
+
 static std::string parallel_name(const std::string& name, int rank, int size) {      // getParallelPieceName, vtkwriter.hh:858-909
   std::ostringstream s;
   s << 's' << std::setw(4) << std::setfill('0') << size << '-';
@@ -70,10 +99,20 @@ static void first_names(const dgb_vtk_field* f, int n, std::string& scalars, std
 
 using namespace dgb;
 
+extern "C" int dgb_vtk_write_ex(const dgb_grid* g, int level, const char* name, const char* path, const dgb_vtk_field* cell_fields,
+                                int ncell_fields, const dgb_vtk_field* vertex_fields, int nvertex_fields, int coord_precision,
+                                int outputtype, char* written, int cap, void* stream_);
 extern "C" int dgb_vtk_write(const dgb_grid* g, int level, const char* name, const char* path, const dgb_vtk_field* cell_fields,
                              int ncell_fields, const dgb_vtk_field* vertex_fields, int nvertex_fields, int coord_precision,
                              char* written, int cap, void* stream_) {
+  return dgb_vtk_write_ex(g, level, name, path, cell_fields, ncell_fields, vertex_fields, nvertex_fields, coord_precision, DGB_VTK_ASCII,
+                          written, cap, stream_);
+}
+extern "C" int dgb_vtk_write_ex(const dgb_grid* g, int level, const char* name, const char* path, const dgb_vtk_field* cell_fields,
+                                int ncell_fields, const dgb_vtk_field* vertex_fields, int nvertex_fields, int coord_precision,
+                                int outputtype, char* written, int cap, void* stream_) {
   return guarded([&]() -> int {
+    if (outputtype < DGB_VTK_ASCII || outputtype > DGB_VTK_APPENDEDBASE64) throw ArgError("unknown VTK output type");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!g || !name) throw ArgError("null argument");
     if (level < 0 || level >= int(g->me.levels.size())) throw RangeError("level out of range");
@@ -145,43 +184,93 @@ extern "C" int dgb_vtk_write(const dgb_grid* g, int level, const char* name, con
       file.rdbuf()->pubsetbuf(buffer.data(), std::streamsize(buffer.size()));
       file.open(piece.c_str(), std::ios::binary);
       if (!file.is_open()) throw ArgError("Could not write to piece file " + piece);
+      // the arrays of the piece in file order (VTKWriter::writeAllData :1205-1217): PointData, CellData, Points, Cells
+      std::vector<VtkArrayData> arrays;
+      auto add_fields = [&](int section, const dgb_vtk_field* f, int n, const std::vector<std::vector<double>>& host,
+                            const std::vector<long long>& order, long long indexBase) {
+        for (int k = 0; k < n; ++k) {
+          const int writecomps = f[k].is_vector ? 3 : f[k].ncomp;
+          VtkArrayData a{section, f[k].name, writecomps, (long long)order.size(), f[k].precision, {}};
+          a.v.reserve(order.size()*writecomps);
+          for (long long e : order) {
+            const double* v = host[k].data() + std::size_t(e - indexBase)*f[k].ncomp;
+            for (int j = 0; j < f[k].ncomp; ++j) a.v.push_back(v[j]);
+            for (int j = f[k].ncomp; j < writecomps; ++j) a.v.push_back(0.0);
+          }
+          arrays.push_back(std::move(a));
+        }
+      };
+      add_fields(0, vertex_fields, nvertex_fields, hvert, visitVertex, 0);
+      add_fields(1, cell_fields, ncell_fields, hcell, cellIndex, cellc.index_offset[DGB_BOX_OVERLAPFRONT]);
+      arrays.push_back(VtkArrayData{2, "Coordinates", 3, nvertices, coord_precision, points});
+      { VtkArrayData a{3, "connectivity", 1, (long long)connectivity.size(), 2, {}}; a.v.assign(connectivity.begin(), connectivity.end()); arrays.push_back(std::move(a)); }
+      { VtkArrayData a{3, "offsets", 1, ncells, 2, {}}; int off = 0; for (long long t = 0; t < ncells; ++t) { off += ncorner; a.v.push_back(off); } arrays.push_back(std::move(a)); }
+      { VtkArrayData a{3, "types", 1, ncells, 3, {}}; a.v.assign(std::size_t(ncells), dim == 2 ? 9.0 : 12.0); arrays.push_back(std::move(a)); }
+
+      static const char* types[4] = { "Float32", "Float64", "Int32", "UInt8" };
       VtkIndent indent;
+      unsigned offset = 0;                                  // running offset of the appended output types
+      // one DataArray tag (+ inline data) of the main section
+      auto main_array = [&](const VtkArrayData& a) {
+        if (outputtype == DGB_VTK_ASCII) { VtkArray w(file, a.name, a.ncomps, indent, a.prec); for (double x : a.v) w.write(x); return; }
+        file << indent << "<DataArray type=\"" << types[a.prec] << "\" Name=\"" << a.name << "\" NumberOfComponents=\"" << a.ncomps << "\" ";
+        const std::size_t bytes = std::size_t(a.ncomps)*std::size_t(a.nitems)*vtk_type_size(a.prec);
+        if (outputtype == DGB_VTK_BASE64) {
+          file << "format=\"binary\">\n";
+          VtkIndent in1 = indent; ++in1.level;
+          file << in1;
+          B64Sink b(file);
+          const std::uint32_t size = std::uint32_t(bytes);
+          b.write(&size, 4); b.flush();
+          for (double x : a.v) vtk_put_value(b, a.prec, x);
+          b.flush();
+          file << "\n" << indent << "</DataArray>\n";
+        } else {
+          file << "format=\"appended\" offset=\"" << offset << "\" />\n";
+          if (outputtype == DGB_VTK_APPENDEDRAW) offset += 4 + unsigned(bytes);
+          else { offset += 8 + unsigned(bytes/3*4); if (bytes % 3 != 0) offset += 4; }
+        }
+      };
+      auto section_of = [&](int sec, const char* tag, const dgb_vtk_field* f, int n) {
+        bool any = false;
+        for (auto& a : arrays) any = any || a.section == sec;
+        if (!any) return;
+        std::string scalars, vectors; first_names(f, n, scalars, vectors);
+        file << indent << "<" << tag;
+        if (scalars != "") file << " Scalars=\"" << scalars << "\"";
+        if (vectors != "") file << " Vectors=\"" << vectors << "\"";
+        file << ">\n"; ++indent.level;
+        for (auto& a : arrays) if (a.section == sec) main_array(a);
+        --indent.level; file << indent << "</" << tag << ">\n";
+      };
       file << indent << "<?xml version=\"1.0\"?>\n";
       file << indent << "<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\">\n";
       ++indent.level;
       file << indent << "<UnstructuredGrid>\n"; ++indent.level;
       file << indent << "<Piece NumberOfCells=\"" << unsigned(ncells) << "\" NumberOfPoints=\"" << unsigned(nvertices) << "\">\n"; ++indent.level;
-      auto write_fields = [&](const char* section, const dgb_vtk_field* f, int n, const std::vector<std::vector<double>>& host,
-                              const std::vector<long long>& order, long long indexBase) {
-        if (n == 0) return;
-        std::string scalars, vectors; first_names(f, n, scalars, vectors);
-        file << indent << "<" << section;
-        if (scalars != "") file << " Scalars=\"" << scalars << "\"";
-        if (vectors != "") file << " Vectors=\"" << vectors << "\"";
-        file << ">\n"; ++indent.level;
-        for (int k = 0; k < n; ++k) {
-          const int writecomps = f[k].is_vector ? 3 : f[k].ncomp;
-          VtkArray a(file, f[k].name, writecomps, indent, f[k].precision);
-          for (long long e : order) {
-            const double* v = host[k].data() + std::size_t(e - indexBase)*f[k].ncomp;
-            for (int j = 0; j < f[k].ncomp; ++j) a.write(v[j]);
-            for (int j = f[k].ncomp; j < writecomps; ++j) a.write(0.0);
-          }
-        }
-        --indent.level; file << indent << "</" << section << ">\n";
-      };
-      write_fields("PointData", vertex_fields, nvertex_fields, hvert, visitVertex, 0);
-      write_fields("CellData", cell_fields, ncell_fields, hcell, cellIndex, cellc.index_offset[DGB_BOX_OVERLAPFRONT]);
+      section_of(0, "PointData", vertex_fields, nvertex_fields);
+      section_of(1, "CellData", cell_fields, ncell_fields);
       file << indent << "<Points>\n"; ++indent.level;
-      { VtkArray a(file, "Coordinates", 3, indent, coord_precision); for (double x : points) a.write(x); }
+      for (auto& a : arrays) if (a.section == 2) main_array(a);
       --indent.level; file << indent << "</Points>\n";
       file << indent << "<Cells>\n"; ++indent.level;
-      { VtkArray a(file, "connectivity", 1, indent, 2); for (int v : connectivity) a.write(v); }
-      { VtkArray a(file, "offsets", 1, indent, 2); int off = 0; for (long long t = 0; t < ncells; ++t) { off += ncorner; a.write(off); } }
-      { VtkArray a(file, "types", 1, indent, 3); for (long long t = 0; t < ncells; ++t) a.write(dim == 2 ? 9 : 12); }
+      for (auto& a : arrays) if (a.section == 3) main_array(a);
       --indent.level; file << indent << "</Cells>\n";
       --indent.level; file << indent << "</Piece>\n";
       --indent.level; file << indent << "</UnstructuredGrid>\n";
+      if (outputtype == DGB_VTK_APPENDEDRAW || outputtype == DGB_VTK_APPENDEDBASE64) {          // vtuwriter.hh:345-365
+        file << indent << "<AppendedData encoding=\"" << (outputtype == DGB_VTK_APPENDEDRAW ? "raw" : "base64") << "\">\n";
+        ++indent.level;
+        file << indent << "_";
+        for (auto& a : arrays) {                                                               // Naked{Raw,Base64}DataArrayWriter
+          const std::uint32_t size = std::uint32_t(std::size_t(a.ncomps)*std::size_t(a.nitems)*vtk_type_size(a.prec));
+          if (outputtype == DGB_VTK_APPENDEDRAW) { RawSink r{file}; r.write(&size, 4); for (double x : a.v) vtk_put_value(r, a.prec, x); }
+          else { B64Sink b(file); b.write(&size, 4); b.flush(); for (double x : a.v) vtk_put_value(b, a.prec, x); b.flush(); }
+        }
+        file << "\n";
+        --indent.level;
+        file << indent << "</AppendedData>\n";
+      }
       --indent.level; file << indent << "</VTKFile>\n" << std::flush;
       if (!file) throw ArgError("write failed on " + piece);
     }

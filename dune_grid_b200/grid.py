@@ -403,7 +403,7 @@ class GridView:
                                      _ptr(out), _stream()))
         return out
 
-    def writeVTK(self, name, celldata=None, pointdata=None, path="", float64=False):
+    def writeVTK(self, name, celldata=None, pointdata=None, path="", float64=False, outputType="ascii"):
         """VTKWriter(gridView).addCellData/addVertexData + write(name) (dune/grid/io/file/vtk/vtkwriter.hh; dune-python:
         gridView.writeVTK(name, celldata={...}, pointdata={...})). Values: CUDA tensors indexed by the element / vertex index,
         shape (n,) scalar, (n, k) with k <= 3 vector. Returns the file to open (.vtu, or the .pvtu header on several ranks)."""
@@ -432,8 +432,9 @@ class GridView:
         ca, nc, k1 = pack(celldata, self.size(0), "cells")
         va, nv, k2 = pack(pointdata, self.size(self.dim), "vertices")
         out = C.create_string_buffer(4096)
-        check(lib.dgb_vtk_write(self.grid.h, self.level, str(name).encode(), str(path).encode(), ca, nc, va, nv, 1 if float64 else 0,
-                                out, 4096, _stream() if (nc or nv) else None))
+        ot = {"ascii": 0, "base64": 1, "appendedraw": 2, "appendedbase64": 3}[outputType]        # VTK::OutputType (io/file/vtk/common.hh:43-51)
+        check(lib.dgb_vtk_write_ex(self.grid.h, self.level, str(name).encode(), str(path).encode(), ca, nc, va, nv, 1 if float64 else 0,
+                                   ot, out, 4096, _stream() if (nc or nv) else None))
         return out.value.decode()
 
     def globalIndexSet(self, codim):

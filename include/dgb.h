@@ -106,6 +106,13 @@ typedef struct dgb_vtk_field {
 int dgb_vtk_write(const dgb_grid* g, int level, const char* name, const char* path, const dgb_vtk_field* cell_fields,
                   int ncell_fields, const dgb_vtk_field* vertex_fields, int nvertex_fields, int coord_precision,
                   char* written, int cap, void* stream);
+/* the same with the output type of VTKWriter::write(name, type): VTK::OutputType, dune/grid/io/file/vtk/common.hh:43-51 (same values) -
+ * inline base64, appended raw binary, appended base64; array syntax of dataarraywriter.hh:196-420. The syntax of all four types is
+ * pinned byte for byte by the reference's own VTUWriter / DataArrayWriter classes (compiled into the test oracle). */
+enum { DGB_VTK_ASCII = 0, DGB_VTK_BASE64 = 1, DGB_VTK_APPENDEDRAW = 2, DGB_VTK_APPENDEDBASE64 = 3 };
+int dgb_vtk_write_ex(const dgb_grid* g, int level, const char* name, const char* path, const dgb_vtk_field* cell_fields,
+                     int ncell_fields, const dgb_vtk_field* vertex_fields, int nvertex_fields, int coord_precision,
+                     int outputtype, char* written, int cap, void* stream);
 /* standalone processor-grid choice, partitioning.hh:56-117 */
 int dgb_partition(int dim, const int32_t* N, int P, int overlap, int partitioner, const int32_t* fixed, int32_t* dims_out);
 

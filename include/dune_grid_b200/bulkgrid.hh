@@ -415,12 +415,16 @@ public:
   void addCellData(const double* d_values, const std::string& name, int ncomps = 1) { cell_.push_back({name, d_values, ncomps, ncomps > 1}); }
   void addVertexData(const double* d_values, const std::string& name, int ncomps = 1) { vertex_.push_back({name, d_values, ncomps, ncomps > 1}); }
   void clear() { cell_.clear(); vertex_.clear(); }
-  std::string write(const std::string& name, const std::string& path = "", cudaStream_t s = nullptr) const {
+  // write(name, VTK::OutputType) (vtkwriter.hh:803-807); the enumerators carry the values of VTK::OutputType (common.hh:43-51)
+  enum OutputType { ascii = DGB_VTK_ASCII, base64 = DGB_VTK_BASE64, appendedraw = DGB_VTK_APPENDEDRAW, appendedbase64 = DGB_VTK_APPENDEDBASE64 };
+  std::string write(const std::string& name, OutputType type = ascii, const std::string& path = "", cudaStream_t s = nullptr) const {
     auto c = pack(cell_), v = pack(vertex_);
     char out[4096];
-    check(dgb_vtk_write(gv_.grid().handle(), gv_.level(), name.c_str(), path.c_str(), c.data(), int(c.size()), v.data(), int(v.size()), 0, out, 4096, s));
+    check(dgb_vtk_write_ex(gv_.grid().handle(), gv_.level(), name.c_str(), path.c_str(), c.data(), int(c.size()), v.data(), int(v.size()), 0,
+                           int(type), out, 4096, s));
     return out;
   }
+  std::string write(const std::string& name, const std::string& path, cudaStream_t s = nullptr) const { return write(name, ascii, path, s); }
 };
 
 template<int dim>

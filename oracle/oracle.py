@@ -110,6 +110,8 @@ class OracleLib:
             "orc_global_index": (i64, [vp, i32, i32, C.POINTER(pi32)]),
             "orc_backup": (i32, [vp, i32, C.c_char_p, i32]),
             "orc_restore": (vp, [i32, i32, i32, C.POINTER(C.c_char_p)]),
+            "orc_vtu_piece": (i64, [i32, C.c_uint, C.c_uint, i32, pi, C.POINTER(C.c_char_p), pi, pi, pi, ppd, C.c_char_p, C.c_char_p,
+                                    C.c_char_p, C.c_char_p, C.c_char_p, i64]),
             "orc_fv_init": (i32, [vp, i32, i32, i32, pd, pd]),
             "orc_fv_step": (dbl, [vp, i32, i32, pd, ppd, ppd]),
             "orc_fv_run": (dbl, [vp, i32, i32, pd, ppd, i32, pd]),
@@ -121,6 +123,26 @@ class OracleLib:
 
     def err(self):
         return self.lib.orc_last_error().decode()
+
+    def vtu_piece(self, outputtype, ncells, npoints, arrays, point_attrs=("", ""), cell_attrs=("", "")):
+        """One .vtu file from the reference's VTUWriter classes (REFERENCE library only). arrays: list of
+        (section, name, ncomps, precision, values) in file order; section 0 PointData, 1 CellData, 2 Points, 3 Cells;
+        precision 0 Float32, 1 Float64, 2 Int32, 3 UInt8. Returns bytes."""
+        n = len(arrays)
+        vals = [np.ascontiguousarray(a[4], dtype=np.float64).reshape(-1) for a in arrays]
+        sec = (C.c_int * n)(*[a[0] for a in arrays])
+        names = (C.c_char_p * n)(*[a[1].encode() for a in arrays])
+        ncomps = (C.c_int * n)(*[a[2] for a in arrays])
+        nitems = (C.c_int * n)(*[v.size // a[2] for a, v in zip(arrays, vals)])
+        prec = (C.c_int * n)(*[a[3] for a in arrays])
+        ptrs = (C.POINTER(C.c_double) * n)(*[v.ctypes.data_as(C.POINTER(C.c_double)) for v in vals])
+        attrs = [x.encode() for x in (*point_attrs, *cell_attrs)]
+        size = self.lib.orc_vtu_piece(outputtype, ncells, npoints, n, sec, names, ncomps, nitems, prec, ptrs, *attrs, None, 0)
+        if size < 0:
+            raise OracleError(self.err())
+        buf = C.create_string_buffer(size)
+        self.lib.orc_vtu_piece(outputtype, ncells, npoints, n, sec, names, ncomps, nitems, prec, ptrs, *attrs, buf, size)
+        return buf.raw[:size]
 
     def partition(self, N, P, overlap=1, partitioner=0, fixed=None):
         d = len(N)

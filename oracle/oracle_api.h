@@ -137,6 +137,19 @@ int64_t orc_global_index(void* w, int level, int codim, int32_t** out);
 int   orc_backup(void* w, int rank, char* out, int cap);
 void* orc_restore(int dim, int coord_mode, int nranks, const char* const* texts);
 
+/* (f1) one .vtu piece written by the reference's own VTK::VTUWriter / DataArrayWriterFactory / Base64Stream / RawStream
+ * (dune/grid/io/file/vtk/{vtuwriter,dataarraywriter,streams,b64enc,common}.hh, compiled unmodified into the REFERENCE library only; -1 from
+ * the port) in the call sequence of VTKWriter::writeDataFile / writeAllData (vtkwriter.hh:1177-1217): PointData, CellData, Points, Cells,
+ * then - appended output types - the same arrays again into the <AppendedData> section. outputtype: 0 ascii, 1 base64, 2 appendedraw,
+ * 3 appendedbase64 (VTK::OutputType). Arrays: `narrays` entries in file order; section[a]: 0 PointData, 1 CellData, 2 Points, 3 Cells;
+ * precision[a]: 0 Float32, 1 Float64, 2 Int32, 3 UInt8; values[a] holds ncomps[a]*nitems[a] doubles (converted like the writer's
+ * write<T>()). scalars / vectors: the attribute strings of the two data sections ("" = none). Returns the byte count of the file;
+ * the bytes are copied when cap is large enough. */
+int64_t orc_vtu_piece(int outputtype, unsigned ncells, unsigned npoints, int narrays, const int* section, const char* const* names,
+                      const int* ncomps, const int* nitems, const int* precision, const double* const* values,
+                      const char* point_scalars, const char* point_vectors, const char* cell_scalars, const char* cell_vectors,
+                      char* out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1030,6 +1030,12 @@ void* orc_restore(int dim, int coord_mode, int nranks, const char* const* texts)
   });
 }
 
+// the VTK file syntax is checked against the reference's own writer classes only (oracle/_ref); the port has no restatement of it
+int64_t orc_vtu_piece(int, unsigned, unsigned, int, const int*, const char* const*, const int*, const int*, const int*, const double* const*,
+                      const char*, const char*, const char*, const char*, char*, int64_t) {
+  g_err = "orc_vtu_piece: reference library only";
+  return -1;
+}
 int orc_fv_init(void* w, int rank, int level, int problem, const double* params, double* c) {
   return guarded(-1, [&] {
     const World& wd = *W(w); const int dim = wd.dim;

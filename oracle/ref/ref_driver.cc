@@ -17,6 +17,8 @@
 #include <dune/grid/utility/globalindexset.hh>
 // GeometryGrid: the reference's own corner and intersection rules (compiled unmodified; they pull in
 // geometrygrid/{declaration,coordfunction,coordfunctioncaller,hostcorners}.hh)
+// the VTK file syntax: VTUWriter + the four DataArrayWriter families, unmodified
+#include <dune/grid/io/file/vtk/vtuwriter.hh>
 #include <dune/grid/geometrygrid/cornerstorage.hh>
 #include <dune/grid/geometrygrid/intersection.hh>
 
@@ -821,6 +823,44 @@ void* orc_restore(int dim, int coord_mode, int nranks, const char* const* texts)
     if (dim == 2) return restore_world<2>(coord_mode, nranks, texts);
     if (dim == 3) return restore_world<3>(coord_mode, nranks, texts);
     DUNE_THROW(Dune::GridError, "oracle supports dim 2 and 3");
+  });
+}
+int64_t orc_vtu_piece(int outputtype, unsigned ncells, unsigned npoints, int narrays, const int* section, const char* const* names,
+                      const int* ncomps, const int* nitems, const int* precision, const double* const* values,
+                      const char* point_scalars, const char* point_vectors, const char* cell_scalars, const char* cell_vectors,
+                      char* out, int64_t cap) {
+  return guarded(int64_t(-1), [&]() -> int64_t {
+    std::ostringstream s;
+    {
+      Dune::VTK::VTUWriter writer(s, Dune::VTK::OutputType(outputtype), Dune::VTK::unstructuredGrid);
+      static const Dune::VTK::Precision precs[4] = { Dune::VTK::Precision::float32, Dune::VTK::Precision::float64,
+                                                     Dune::VTK::Precision::int32, Dune::VTK::Precision::uint8 };
+      auto arrays = [&](int sec) {
+        for (int a = 0; a < narrays; ++a) if (section[a] == sec) {
+          std::unique_ptr<Dune::VTK::DataArrayWriter> p(writer.makeArrayWriter(names[a], ncomps[a], nitems[a], precs[precision[a]]));
+          if (!p->writeIsNoop())
+            for (std::int64_t k = 0; k < std::int64_t(ncomps[a])*nitems[a]; ++k) p->write(values[a][k]);
+        }
+      };
+      auto all = [&] {                                               // VTKWriter::writeAllData, vtkwriter.hh:1205-1217
+        bool any = false;
+        for (int a = 0; a < narrays; ++a) any = any || section[a] == 0;
+        if (any) { writer.beginPointData(point_scalars, point_vectors); arrays(0); writer.endPointData(); }       // :1342-1353
+        any = false;
+        for (int a = 0; a < narrays; ++a) any = any || section[a] == 1;
+        if (any) { writer.beginCellData(cell_scalars, cell_vectors); arrays(1); writer.endCellData(); }           // :1300-1338
+        writer.beginPoints(); arrays(2); writer.endPoints();
+        writer.beginCells(); arrays(3); writer.endCells();
+      };
+      writer.beginMain(ncells, npoints);
+      all();
+      writer.endMain();
+      if (writer.beginAppended()) all();
+      writer.endAppended();
+    }
+    const std::string t = s.str();
+    if (out && cap >= std::int64_t(t.size())) std::memcpy(out, t.data(), t.size());
+    return std::int64_t(t.size());
   });
 }
 int orc_fv_init(void* w, int rank, int level, int problem, const double* params, double* c) {

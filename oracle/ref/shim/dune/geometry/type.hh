@@ -12,6 +12,13 @@ namespace Dune {
     constexpr bool isNone() const { return none_; }
     constexpr bool isVertex() const { return !none_ && dim_==0; }
     constexpr bool isLine() const { return !none_ && dim_==1; }
+    // the queries of dune/grid/io/file/vtk/common.hh (cube types only exist here)
+    constexpr bool isQuadrilateral() const { return !none_ && dim_==2; }
+    constexpr bool isHexahedron() const { return !none_ && dim_==3; }
+    constexpr bool isTriangle() const { return false; }
+    constexpr bool isTetrahedron() const { return false; }
+    constexpr bool isPyramid() const { return false; }
+    constexpr bool isPrism() const { return false; }
     constexpr unsigned int id() const { return none_ ? 0u : ((1u << dim_) - 1u); }
     constexpr bool operator==(const GeometryType& o) const { return dim_==o.dim_ && none_==o.none_; }
     constexpr bool operator!=(const GeometryType& o) const { return !(*this==o); }

@@ -139,6 +139,12 @@ void deviceChecks() {
     std::string all((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
     CHECK(file == "/tmp/bulk_gridview_test_out.vtu" && all.find("<CellData Scalars=\"xcenter\">") != std::string::npos);
     CHECK(all.find("NumberOfCells=\"" + std::to_string(pv.size(0)) + "\"") != std::string::npos);
+    // write(name, VTK::appendedraw): the arrays move into the <AppendedData> section
+    const std::string raw = vtk.write("bulk_gridview_test_raw", VTKWriter<dim>::appendedraw, "/tmp");
+    std::ifstream inr(raw, std::ios::binary);
+    std::string allr((std::istreambuf_iterator<char>(inr)), std::istreambuf_iterator<char>());
+    CHECK(allr.find("Name=\"xcenter\" NumberOfComponents=\"1\" format=\"appended\" offset=\"0\" />") != std::string::npos);
+    CHECK(allr.find("<AppendedData encoding=\"raw\">") != std::string::npos);
   }
   // the coordinate container is a template parameter, as in Dune::YaspGrid<dim,Coordinates>; functor sweeps; face normals
   {

@@ -117,3 +117,69 @@ def test_fields_from_the_device(tmp_path):
     f64 = gv.writeVTK("fields64", celldata={"c": c}, path=str(tmp_path), float64=True)
     a64 = arrays(ET.parse(f64).getroot().find("UnstructuredGrid/Piece"))
     assert a64["c"][1] == "Float64" and np.allclose(a64["c"][0], c.cpu().numpy()[idx], rtol=1e-14)
+
+
+# ---- the four output types against the reference's own writer classes ----------------------------------------------------------------
+# oracle/_ref compiles dune/grid/io/file/vtk/{vtuwriter,dataarraywriter,streams,b64enc}.hh unmodified (orc_vtu_piece): the product's
+# file must be byte-identical to what those classes write for the same arrays. The arrays are read back from the product's ASCII
+# file; all test values are short dyadic numbers, so the text holds them exactly.
+OUTPUT_TYPES = ["ascii", "base64", "appendedraw", "appendedbase64"]
+PREC = {"Float32": 0, "Float64": 1, "Int32": 2, "UInt8": 3}
+SECTION = {"PointData": 0, "CellData": 1, "Points": 2, "Cells": 3}
+
+
+def piece_arrays(path):
+    piece = ET.parse(path).getroot().find("UnstructuredGrid/Piece")
+    out, attrs = [], {"PointData": ("", ""), "CellData": ("", "")}
+    for sec in piece:
+        if sec.tag in attrs:
+            attrs[sec.tag] = (sec.get("Scalars") or "", sec.get("Vectors") or "")
+        for da in sec.iter("DataArray"):
+            out.append((SECTION[sec.tag], da.get("Name"), int(da.get("NumberOfComponents")), PREC[da.get("type")],
+                        np.array(da.text.split(), dtype=np.float64)))
+    return int(piece.get("NumberOfCells")), int(piece.get("NumberOfPoints")), out, attrs
+
+
+def ref_lib():
+    import oracle.oracle as orc
+    if not orc.available("ref"):
+        pytest.skip("oracle/_ref not built (the reference's VTK writer classes)")
+    return orc.load("ref")
+
+
+def check_against_reference_writer(gv, tmp_path, **kw):
+    o = ref_lib()
+    f = gv.writeVTK("t_ascii", path=str(tmp_path), **kw)
+    ncells, npoints, arrs, attrs = piece_arrays(f)
+    for k, ot in enumerate(OUTPUT_TYPES):
+        got = open(gv.writeVTK("t_" + ot, path=str(tmp_path), outputType=ot, **kw), "rb").read()
+        want = o.vtu_piece(k, ncells, npoints, arrs, attrs["PointData"], attrs["CellData"])
+        assert got == want, f"{ot}: file differs from the reference VTUWriter's ({len(got)} vs {len(want)} bytes)"
+    return arrs
+
+
+@pytest.mark.parametrize("cfg", [make_cfg(dim=2, N=(4, 2), upper=(1.0, 0.5)), make_cfg(dim=3, N=(4, 2, 3), upper=(2.0, 0.5, 0.75)),
+                                 make_cfg(dim=3, N=(5, 3, 2), upper=(5.0, 3.0, 2.0))])
+def test_grid_only_files_match_the_reference_writer(cfg, tmp_path):
+    arrs = check_against_reference_writer(product_grid(cfg, 0, 1).leafGridView(), tmp_path)
+    assert [a[1] for a in arrs] == ["Coordinates", "connectivity", "offsets", "types"]
+
+
+def test_unknown_output_type(tmp_path):
+    gv = product_grid(make_cfg(dim=2, N=(2, 2)), 0, 1).leafGridView()
+    with pytest.raises(KeyError):
+        gv.writeVTK("x", path=str(tmp_path), outputType="binary")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("float64", [False, True])
+def test_field_files_match_the_reference_writer(tmp_path, float64):
+    import torch
+    cfg = make_cfg(dim=3, N=(5, 4, 3), upper=(5.0, 2.0, 0.75))
+    gv = product_grid(cfg, 0, 1).leafGridView()
+    rng = np.random.default_rng(5)
+    c = torch.from_numpy(rng.integers(-64, 64, gv.size(0)) / 8.0).cuda()
+    vel = torch.from_numpy(rng.integers(-64, 64, (gv.size(0), 2)) / 4.0).cuda()
+    p = torch.from_numpy(rng.integers(-64, 64, gv.size(3)) / 2.0).cuda()
+    arrs = check_against_reference_writer(gv, tmp_path, celldata={"c": c, "velocity": vel}, pointdata={"p": p}, float64=float64)
+    assert [a[1] for a in arrs] == ["p", "c", "velocity", "Coordinates", "connectivity", "offsets", "types"]
