@@ -101,6 +101,14 @@ _SIG = {
     "dgb_comm_plan_info": (_i, [_vp, _i, _pm, _i, _i, C.POINTER(C.c_int32), _i, _i64p, _i]),
     "dgb_comm_pack": (_i, [_vp, _i, _pm, _i, _i, C.POINTER(_vp), C.POINTER(C.c_int32), _i, C.POINTER(_vp), C.POINTER(_vp), _vp]),
     "dgb_comm_unpack": (_i, [_vp, _i, _pm, _i, _i, _i, C.POINTER(_vp), C.POINTER(C.c_int32), _i, _vp]),
+    "dgb_commvar_create": (_i, [_vp, _i, _pm, _i, _i, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "dgb_commvar_exchange": (_i, [_vp, _vp, _vp]),
+    "dgb_commvar_segments": (_i, [_vp, _i, _i64p, _i]),
+    "dgb_commvar_buffers": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "dgb_commvar_sizes_received": (_i, [_vp, _vp]),
+    "dgb_commvar_finish": (_i, [_vp, _vp, _i64p, _i64p]),
+    "dgb_commvar_result": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "dgb_commvar_destroy": (_i, [_vp]),
     "dgb_allreduce_min": (_i, [_vp, _vp, _vp]), "dgb_allreduce_max": (_i, [_vp, _vp, _vp]),
     "dgb_comm_last_bytes": (_i, [_vp, _i64p]),
     "dgb_fv_create": (_i, [_vp, _i, _i, C.POINTER(C.c_double), _i, _i, _vp, C.POINTER(_vp)]),

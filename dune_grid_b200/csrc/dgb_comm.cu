@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <nccl.h>
+#include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <sstream>
 #include "dgb_internal.hh"
@@ -145,6 +146,58 @@ __global__ void __launch_bounds__(PACK_THREADS) k_halo(const PlanBox* __restrict
     halo_box<MODE, long long>(b, arrays, buffer, (long long)cta*PACK_THREADS + threadIdx.x, (long long)nctas*PACK_THREADS, total);
 }
 
+// ---- data handles of variable size (CommDataHandleIF::fixedSize == false, yaspgrid.hh:1562-1634) ----------------------------------
+// The sender decides how many items an entity carries. Bulk form: the send side is a CSR pair (offsets by mapper index, items);
+// every message is preceded by a message of per-entity sizes (the reference's first exchange round); the receiver gets the
+// sequence of scatter(buff, e, n) calls the reference would make - in its order - as (mapper index of e, offsets, items).
+struct VarBuf {
+  void* p = nullptr;
+  ~VarBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) { if (p) { cudaFree(p); p = nullptr; } DGB_CUDA(cudaMalloc(&p, bytes ? bytes : 8)); return DGB_OK; }
+  template<class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// one thread per entity slot of a box: the mapper index of the entity (block 1), its size on the send side, its place in the
+// reference's scatter order on the receive side
+__global__ void __launch_bounds__(PACK_THREADS) k_var_slots(const PlanBox b, const long long* __restrict__ csr, long long* __restrict__ slotIndex,
+                                                            long long* __restrict__ slotSize, long long* __restrict__ slotOut, long long outBase) {
+  const long long s0 = b.size[0], s1 = b.size[1];
+  for (long long t = (long long)blockIdx.x*PACK_THREADS + threadIdx.x; t < b.count; t += (long long)gridDim.x*PACK_THREADS) {
+    const long long q = t / s0; const int i0 = int(t - q*s0);
+    const long long i2 = q / s1; const int i1 = int(q - i2*s1);
+    const long long local = ((long long)(b.origin[2]+int(i2)-b.of_origin[2])*b.of_size[1] + (b.origin[1]+i1-b.of_origin[1]))*b.of_size[0]
+                            + (b.origin[0]+i0-b.of_origin[0]);
+    const unsigned idx = (b.index_base + unsigned(local))*b.block + b.map_offset;
+    slotIndex[b.buf_offset + t] = idx;
+    if (slotSize) slotSize[b.buf_offset + t] = csr[idx+1] - csr[idx];
+    if (slotOut) slotOut[b.buf_offset + t] = outBase + t;
+  }
+}
+
+// one warp per slot: n[slot] doubles from src[srcTable[srcSel ? srcSel[slot] : slot] ...] to dst[dstTable[dstSel ? dstSel[slot] : slot] ...]
+__global__ void __launch_bounds__(PACK_THREADS) k_var_copy(long long nslots, const long long* __restrict__ n, const double* __restrict__ src,
+                                                           const long long* __restrict__ srcTable, const long long* __restrict__ srcSel,
+                                                           double* __restrict__ dst, const long long* __restrict__ dstTable, const long long* __restrict__ dstSel) {
+  const int lane = threadIdx.x & 31;
+  for (long long w = ((long long)blockIdx.x*PACK_THREADS + threadIdx.x) >> 5; w < nslots; w += ((long long)gridDim.x*PACK_THREADS) >> 5) {
+    const long long cnt = n[w];
+    const double* sp = src + srcTable[srcSel ? srcSel[w] : w];
+    double* dp = dst + dstTable[dstSel ? dstSel[w] : w];
+    for (long long j = lane; j < cnt; j += 32) dp[j] = sp[j];
+  }
+}
+
+__global__ void __launch_bounds__(PACK_THREADS) k_var_permute(long long nslots, const long long* __restrict__ pos, const long long* __restrict__ idx,
+                                                              const long long* __restrict__ size, long long* __restrict__ outIndex, long long* __restrict__ outSize) {
+  for (long long t = (long long)blockIdx.x*PACK_THREADS + threadIdx.x; t < nslots; t += (long long)gridDim.x*PACK_THREADS) {
+    outIndex[pos[t]] = idx[t]; outSize[pos[t]] = size[t];
+  }
+}
+
+__global__ void __launch_bounds__(PACK_THREADS) k_var_index32(long long n, const long long* __restrict__ in, uint32_t* __restrict__ out) {
+  for (long long t = (long long)blockIdx.x*PACK_THREADS + threadIdx.x; t < n; t += (long long)gridDim.x*PACK_THREADS) out[t] = uint32_t(in[t]);
+}
+
 // ---- plan construction (host) -------------------------------------------------------------------------
 static void add_boxes(const dgb_grid* g, int level, int codim, int which, const dgb_mapper& m, int per_entity_codim,
                       std::vector<PlanBox>& boxes, std::vector<int>& peer) {
@@ -173,6 +226,7 @@ static void add_boxes(const dgb_grid* g, int level, int codim, int which, const 
       b.face = (nz == 1) ? 2*ax + (e.delta[ax] > 0 ? 1 : 0) : -1;
     }
     b.buf_offset = 0;
+    b.list_pos = int(boxes.size());
     (void)per_entity_codim;
     boxes.push_back(b);
     peer.push_back(e.rank);
@@ -685,6 +739,163 @@ int fused_register(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaS
   return DGB_OK;
 }
 
+// ---- variable-size exchange (host) ---------------------------------------------------------------------------------------------------
+} // namespace dgb
+
+struct dgb_commvar {
+  dgb_grid* g = nullptr;
+  std::shared_ptr<dgb::CommPlan> plan;
+  int myrank = 0, stage = 0;                 // 0 created (send side packed), 1 sizes received, 2 finished
+  const long long* csr = nullptr; const double* data = nullptr;
+  dgb::VarBuf sendIdx, sendSizes, sendOff, sendItems, recvSizes, recvOff, recvItems, recvIdx, outPos, outIndex, outSizes, outOffsets, outData, tmp;
+  std::vector<long long> sendSegItem, recvSegItem;      // per segment: first item, items (pairs)
+  long long sendItemsTotal = 0, recvItemsTotal = 0;
+};
+
+namespace dgb {
+
+static unsigned var_ctas(long long n, int per = 1) { return unsigned(std::max(1ll, std::min((n*per + PACK_THREADS - 1)/PACK_THREADS, 4096ll))); }
+
+// exclusive prefix sum of n sizes into off[0..n] (off[n] = total)
+static int var_scan(dgb_commvar& h, const long long* sizes, long long* off, long long n, cudaStream_t stream) {
+  DGB_CUDA(cudaMemsetAsync(off, 0, sizeof(long long), stream));
+  if (n <= 0) return DGB_OK;
+  if (n >= (1ll << 31)) return fail(DGB_EARG, "variable-size communicate: more than 2^31 entities in one exchange");
+  size_t bytes = 0;
+  DGB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, sizes, off + 1, int(n), stream));
+  if (int rc = h.tmp.alloc(bytes)) return rc;
+  DGB_CUDA(cub::DeviceScan::InclusiveSum(h.tmp.p, bytes, sizes, off + 1, int(n), stream));
+  return DGB_OK;
+}
+
+// item ranges of the plan's segments from a device offsets array (synchronises the stream)
+static int var_segment_items(const std::vector<CommPlan::Segment>& segs, const long long* dOff, std::vector<long long>& out, long long total_slots,
+                             long long& total, cudaStream_t stream) {
+  std::vector<long long> edge(2*segs.size() + 1, 0);
+  for (std::size_t k = 0; k < segs.size(); ++k) {
+    DGB_CUDA(cudaMemcpyAsync(&edge[2*k], dOff + segs[k].offset, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+    DGB_CUDA(cudaMemcpyAsync(&edge[2*k+1], dOff + segs[k].offset + segs[k].count, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  }
+  DGB_CUDA(cudaMemcpyAsync(&edge[2*segs.size()], dOff + total_slots, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  DGB_CUDA(cudaStreamSynchronize(stream));
+  out.resize(2*segs.size());
+  for (std::size_t k = 0; k < segs.size(); ++k) { out[2*k] = edge[2*k]; out[2*k+1] = edge[2*k+1] - edge[2*k]; }
+  total = edge[2*segs.size()];
+  return DGB_OK;
+}
+
+static int var_create(dgb_grid* g, int level, const dgb_mapper& m, int iftype, int dir, const long long* csr, const double* data,
+                      cudaStream_t stream, dgb_commvar** out) {
+  if (level < 0 || level >= int(g->me.levels.size())) throw RangeError("level out of range");
+  for (int c = 0; c < 4; ++c) if (m.block[c] > 1) throw ArgError("variable-size communicate: the mapper layout must have block size 1 on the communicated codims");
+  if (!csr) throw ArgError("variable-size communicate: null offsets");
+  if (int rc = require_device()) return rc;
+  std::unique_ptr<dgb_commvar> h(new dgb_commvar);
+  h->g = g; h->myrank = g->me.rank; h->csr = csr; h->data = data;
+  const int32_t one[1] = {1};
+  if (int rc = get_plan(g, level, m, iftype, dir, one, 1, h->plan)) return rc;
+  CommPlan& P = *h->plan;
+  const long long ns = P.sendTotal, nr = P.recvTotal;
+  if (int rc = h->sendIdx.alloc(ns*8)) return rc;
+  if (int rc = h->sendSizes.alloc(ns*8)) return rc;
+  if (int rc = h->sendOff.alloc((ns+1)*8)) return rc;
+  if (int rc = h->recvSizes.alloc(nr*8)) return rc;
+  for (const PlanBox& b : P.hostSend)
+    if (b.count > 0) k_var_slots<<<var_ctas(b.count), PACK_THREADS, 0, stream>>>(b, csr, h->sendIdx.as<long long>(), h->sendSizes.as<long long>(), nullptr, 0);
+  DGB_CUDA(cudaGetLastError());
+  if (int rc = var_scan(*h, h->sendSizes.as<long long>(), h->sendOff.as<long long>(), ns, stream)) return rc;
+  if (int rc = var_segment_items(P.sendSeg, h->sendOff.as<long long>(), h->sendSegItem, ns, h->sendItemsTotal, stream)) return rc;
+  if (int rc = h->sendItems.alloc(h->sendItemsTotal*8)) return rc;
+  if (ns > 0 && h->sendItemsTotal > 0) {
+    if (!data) throw ArgError("variable-size communicate: null data");
+    k_var_copy<<<var_ctas(ns, 32), PACK_THREADS, 0, stream>>>(ns, h->sendSizes.as<long long>(), data, csr, h->sendIdx.as<long long>(),
+                                                             h->sendItems.as<double>(), h->sendOff.as<long long>(), nullptr);
+  }
+  DGB_CUDA(cudaGetLastError());
+  *out = h.release();
+  return DGB_OK;
+}
+
+static int var_sizes_received(dgb_commvar& h, cudaStream_t stream) {
+  if (h.stage != 0) return fail(DGB_EARG, "variable-size communicate: sizes were already received");
+  CommPlan& P = *h.plan;
+  const long long nr = P.recvTotal;
+  if (int rc = h.recvOff.alloc((nr+1)*8)) return rc;
+  if (int rc = var_scan(h, h.recvSizes.as<long long>(), h.recvOff.as<long long>(), nr, stream)) return rc;
+  if (int rc = var_segment_items(P.recvSeg, h.recvOff.as<long long>(), h.recvSegItem, nr, h.recvItemsTotal, stream)) return rc;
+  if (h.recvItemsTotal < 0) return fail(DGB_EARG, "variable-size communicate: negative size received");
+  if (int rc = h.recvItems.alloc(h.recvItemsTotal*8)) return rc;
+  h.stage = 1;
+  return DGB_OK;
+}
+
+// 8-byte words of the send buffer to the partners / from the partners into the receive buffer; `item` = false: the size round
+static int var_transport(dgb_commvar& h, bool item, dgb_comm* comm, cudaStream_t stream) {
+  CommPlan& P = *h.plan;
+  bool remote = false;
+  for (auto& s : P.sendSeg) if (s.peer != h.myrank) remote = true;
+  for (auto& s : P.recvSeg) if (s.peer != h.myrank) remote = true;
+  if (remote && !comm) return fail(DGB_EARG, "this exchange has remote partners: a dgb_comm is required");
+  if (remote) if (int rc = nccl_check_async(comm)) return rc;
+  const char* sb = item ? h.sendItems.as<char>() : h.sendSizes.as<char>();
+  char* rb = item ? h.recvItems.as<char>() : h.recvSizes.as<char>();
+  auto soff = [&](std::size_t k) { return item ? h.sendSegItem[2*k] : P.sendSeg[k].offset; };
+  auto scnt = [&](std::size_t k) { return item ? h.sendSegItem[2*k+1] : P.sendSeg[k].count; };
+  auto roff = [&](std::size_t k) { return item ? h.recvSegItem[2*k] : P.recvSeg[k].offset; };
+  auto rcnt = [&](std::size_t k) { return item ? h.recvSegItem[2*k+1] : P.recvSeg[k].count; };
+  int64_t bytes = 0;
+  if (remote) {
+    DGB_NCCL(g_nccl.GroupStart());
+    for (std::size_t k = 0; k < P.sendSeg.size(); ++k) if (P.sendSeg[k].peer != h.myrank) {
+      DGB_NCCL(g_nccl.Send(sb + 8*soff(k), size_t(scnt(k)), ncclInt64, P.sendSeg[k].peer, comm->comm, stream)); bytes += 8*scnt(k); }
+    for (std::size_t k = 0; k < P.recvSeg.size(); ++k) if (P.recvSeg[k].peer != h.myrank)
+      DGB_NCCL(g_nccl.Recv(rb + 8*roff(k), size_t(rcnt(k)), ncclInt64, P.recvSeg[k].peer, comm->comm, stream));
+    DGB_NCCL(g_nccl.GroupEnd());
+  }
+  for (std::size_t k = 0; k < P.sendSeg.size(); ++k) if (P.sendSeg[k].peer == h.myrank)
+    for (std::size_t j = 0; j < P.recvSeg.size(); ++j) if (P.recvSeg[j].peer == h.myrank) {
+      if (rcnt(j) != scnt(k)) return fail(DGB_EGRID, "local sends/receives do not match in exchange");
+      DGB_CUDA(cudaMemcpyAsync(rb + 8*roff(j), sb + 8*soff(k), size_t(8*scnt(k)), cudaMemcpyDeviceToDevice, stream));
+    }
+  if (item) h.g->lastBytesSent = bytes;
+  return DGB_OK;
+}
+
+static int var_finish(dgb_commvar& h, cudaStream_t stream) {
+  if (h.stage != 1) return fail(DGB_EARG, "variable-size communicate: finish before the sizes were received (or twice)");
+  CommPlan& P = *h.plan;
+  const long long nr = P.recvTotal;
+  if (int rc = h.recvIdx.alloc(nr*8)) return rc;
+  if (int rc = h.outPos.alloc(nr*8)) return rc;
+  if (int rc = h.outIndex.alloc(nr*8)) return rc;
+  if (int rc = h.outSizes.alloc(nr*8)) return rc;
+  if (int rc = h.outOffsets.alloc((nr+1)*8)) return rc;
+  if (int rc = h.outData.alloc(h.recvItemsTotal*8)) return rc;
+  // the reference scatters box after box in list order, codim dim..0 (yaspgrid.hh:1694-1729): position of a box's first entity there
+  std::vector<long long> base(P.hostRecv.size(), 0);
+  {
+    std::vector<std::size_t> order(P.hostRecv.size());
+    for (std::size_t k = 0; k < order.size(); ++k) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](std::size_t a, std::size_t b) { return P.hostRecv[a].list_pos < P.hostRecv[b].list_pos; });
+    long long at = 0;
+    for (std::size_t k : order) { base[k] = at; at += P.hostRecv[k].count; }
+  }
+  for (std::size_t k = 0; k < P.hostRecv.size(); ++k) {
+    const PlanBox& b = P.hostRecv[k];
+    if (b.count > 0) k_var_slots<<<var_ctas(b.count), PACK_THREADS, 0, stream>>>(b, nullptr, h.recvIdx.as<long long>(), nullptr, h.outPos.as<long long>(), base[k]);
+  }
+  if (nr > 0) k_var_permute<<<var_ctas(nr), PACK_THREADS, 0, stream>>>(nr, h.outPos.as<long long>(), h.recvIdx.as<long long>(), h.recvSizes.as<long long>(),
+                                                                      h.outIndex.as<long long>(), h.outSizes.as<long long>());
+  DGB_CUDA(cudaGetLastError());
+  if (int rc = var_scan(h, h.outSizes.as<long long>(), h.outOffsets.as<long long>(), nr, stream)) return rc;
+  if (nr > 0 && h.recvItemsTotal > 0)
+    k_var_copy<<<var_ctas(nr, 32), PACK_THREADS, 0, stream>>>(nr, h.recvSizes.as<long long>(), h.recvItems.as<double>(), h.recvOff.as<long long>(), nullptr,
+                                                             h.outData.as<double>(), h.outOffsets.as<long long>(), h.outPos.as<long long>());
+  DGB_CUDA(cudaGetLastError());
+  h.stage = 2;
+  return DGB_OK;
+}
+
 int CommPlan::enter(cudaStream_t stream) {
   std::lock_guard<std::mutex> lk(mtx);
   if (!busy) DGB_CUDA(cudaEventCreateWithFlags(&busy, cudaEventDisableTiming));
@@ -816,6 +1027,73 @@ int dgb_comm_unpack(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int
     return plan->leave((cudaStream_t)stream);
   });
 }
+
+/* ---- data handles of variable size ---- */
+int dgb_commvar_create(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int dir, const int64_t* d_send_offsets,
+                       const double* d_send_data, void* stream, dgb_commvar** out) {
+  return guarded([&]() -> int {
+    if (!g || !m || !out) throw ArgError("null argument");
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64_t");
+    return var_create(g, level, *m, iftype, dir, reinterpret_cast<const long long*>(d_send_offsets), d_send_data, (cudaStream_t)stream, out);
+  });
+}
+int dgb_commvar_exchange(dgb_commvar* h, dgb_comm* comm, void* stream) {
+  return guarded([&]() -> int {
+    if (!h) throw ArgError("null argument");
+    if (int rc = var_transport(*h, false, comm, (cudaStream_t)stream)) return rc;     // the sizes first (yaspgrid.hh:1566-1612)
+    if (int rc = var_sizes_received(*h, (cudaStream_t)stream)) return rc;
+    return var_transport(*h, true, comm, (cudaStream_t)stream);                        // then the data (:1637-1681)
+  });
+}
+int dgb_commvar_segments(dgb_commvar* h, int recv_side, int64_t* out, int cap) {
+  return guarded([&]() -> int {
+    if (!h || !out) throw ArgError("null argument");
+    const auto& segs = recv_side ? h->plan->recvSeg : h->plan->sendSeg;
+    const auto& items = recv_side ? h->recvSegItem : h->sendSegItem;
+    if (cap < 1 + 5*int(segs.size())) throw ArgError("segments: output too small");
+    out[0] = int64_t(segs.size());
+    for (std::size_t k = 0; k < segs.size(); ++k) {
+      int64_t* o = out + 1 + 5*k;
+      o[0] = segs[k].peer; o[1] = segs[k].offset; o[2] = segs[k].count;
+      o[3] = items.size() > 2*k ? items[2*k] : -1; o[4] = items.size() > 2*k ? items[2*k+1] : -1;
+    }
+    return DGB_OK;
+  });
+}
+int dgb_commvar_buffers(dgb_commvar* h, int64_t** d_send_sizes, double** d_send_items, int64_t** d_recv_sizes, double** d_recv_items) {
+  if (!h) return fail(DGB_EARG, "null argument");
+  if (d_send_sizes) *d_send_sizes = h->sendSizes.as<int64_t>();
+  if (d_send_items) *d_send_items = h->sendItems.as<double>();
+  if (d_recv_sizes) *d_recv_sizes = h->recvSizes.as<int64_t>();
+  if (d_recv_items) *d_recv_items = h->stage >= 1 ? h->recvItems.as<double>() : nullptr;
+  return DGB_OK;
+}
+int dgb_commvar_sizes_received(dgb_commvar* h, void* stream) {
+  return guarded([&]() -> int { if (!h) throw ArgError("null argument"); return var_sizes_received(*h, (cudaStream_t)stream); });
+}
+int dgb_commvar_finish(dgb_commvar* h, void* stream, int64_t* n_entities, int64_t* n_items) {
+  return guarded([&]() -> int {
+    if (!h) throw ArgError("null argument");
+    if (int rc = var_finish(*h, (cudaStream_t)stream)) return rc;
+    if (n_entities) *n_entities = h->plan->recvTotal;
+    if (n_items) *n_items = h->recvItemsTotal;
+    return DGB_OK;
+  });
+}
+int dgb_commvar_result(dgb_commvar* h, uint32_t* d_index, int64_t* d_offsets, double* d_data, void* stream_) {
+  return guarded([&]() -> int {
+    if (!h) throw ArgError("null argument");
+    if (h->stage != 2) throw ArgError("variable-size communicate: result before finish");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const long long nr = h->plan->recvTotal;
+    if (d_index && nr > 0) k_var_index32<<<var_ctas(nr), PACK_THREADS, 0, stream>>>(nr, h->outIndex.as<long long>(), d_index);
+    DGB_CUDA(cudaGetLastError());
+    if (d_offsets) DGB_CUDA(cudaMemcpyAsync(d_offsets, h->outOffsets.p, size_t(nr+1)*8, cudaMemcpyDeviceToDevice, stream));
+    if (d_data && h->recvItemsTotal > 0) DGB_CUDA(cudaMemcpyAsync(d_data, h->outData.p, size_t(h->recvItemsTotal)*8, cudaMemcpyDeviceToDevice, stream));
+    return DGB_OK;
+  });
+}
+int dgb_commvar_destroy(dgb_commvar* h) { delete h; return DGB_OK; }
 
 int dgb_allreduce_min(double* d_value, dgb_comm* comm, void* stream) { return nccl_allreduce(d_value, 0, comm, (cudaStream_t)stream); }
 int dgb_allreduce_max(double* d_value, dgb_comm* comm, void* stream) { return nccl_allreduce(d_value, 1, comm, (cudaStream_t)stream); }

@@ -24,6 +24,7 @@ struct PlanBox {
   int peer_origin[3], peer_of_origin[3], peer_of_size[3];
   int peer;
   int face;                         // 2*axis + (partner on the high side) if the partner is a FACE neighbour (one non-zero torus offset), else -1
+  int list_pos;                     // position in the reference's processing order (codim dim..0, list order): hostRecv is re-ordered by wave
 };
 struct CommPlan {
   struct Segment { int peer; long long offset, count; };     // doubles

@@ -367,6 +367,82 @@ __global__ void __launch_bounds__(BX) k_index_linear(const __grid_constant__ dgb
   }
 }
 
+// ---- K1c / K2c: mapper indices and sub-indices, 16-byte stores, ONE launch per call -------------------------------------------
+// Every stream of indices (a shift component of mapper.index, one sub-entity number of mapper.subIndex) is an affine function of
+// the position inside the swept box: value = val0 + i0*block + i1*rowStride + i2*planeStride (numbering of the enclosing
+// overlapfront array, ygrid.hh:472-479). A thread owns the 16-byte vectors g, g+BX, ... of the OUTPUT array (absolute positions,
+// so any stream offset is aligned); the four values of a vector are consecutive unless the vector straddles a row end (carry
+// walk) or the ends of the stream (scalar stores). The position advances by 4*BX entities with a carry; no division in the loop.
+struct IdxSeg { long long base, count; int s0, s1; uint32_t val0, rowStride, planeStride; unsigned firstBlock; };
+static constexpr int IDX_MAX_SEGS = 12;
+struct IdxSegs { int n; uint32_t block; IdxSeg s[IDX_MAX_SEGS]; };
+static constexpr int VEC_ITER = 8;
+
+__global__ void __launch_bounds__(BX) k_index_vec(const __grid_constant__ IdxSegs P, uint32_t* __restrict__ out) {
+  int k = 0;
+  while (k+1 < P.n && blockIdx.x >= P.s[k+1].firstBlock) ++k;
+  const IdxSeg& S = P.s[k];
+  const uint32_t block = P.block;
+  const long long g = (S.base >> 2) + (long long)(blockIdx.x - S.firstBlock)*(BX*VEC_ITER) + threadIdx.x;
+  long long e = 4*g - S.base;                      // entity of the vector's first lane; -3..-1 only for the first vector of a stream
+  if (e >= S.count) return;
+  const int s0 = S.s0, s1 = S.s1;
+  int i0, i1, i2;
+  {
+    const long long ee = e < 0 ? 0 : e, q = ee / s0;
+    i0 = int(ee - q*s0); i2 = int(q / s1); i1 = int(q - (long long)i2*s1);
+  }
+  uint32_t* p = out + (S.base + e);
+#pragma unroll 1
+  for (int j = 0; j < VEC_ITER; ++j) {
+    uint32_t val = S.val0 + uint32_t(i0)*block + uint32_t(i1)*S.rowStride + uint32_t(i2)*S.planeStride;
+    int adv = 4*BX;
+    if (e >= 0 && e + 3 < S.count && i0 + 3 < s0) {
+      *reinterpret_cast<uint4*>(p) = make_uint4(val, val + block, val + 2*block, val + 3*block);
+    } else {
+      int a0 = i0, a1 = i1, a2 = i2;
+      for (int l = 0; l < 4; ++l) {
+        const long long el = e + l;
+        if (el < 0) continue;                      // (a0,a1,a2) is entity 0 until el reaches it
+        if (el >= S.count) break;
+        p[l] = S.val0 + uint32_t(a0)*block + uint32_t(a1)*S.rowStride + uint32_t(a2)*S.planeStride;
+        if (++a0 == s0) { a0 = 0; if (++a1 == s1) { a1 = 0; ++a2; } }
+      }
+      if (e < 0) adv += int(e);                    // the walk state stood at entity 0, not at e
+    }
+    e += 4*BX; p += 4*BX;
+    if (e >= S.count) break;
+    i0 += adv;
+    if (i0 >= s0) {
+      if (s0 >= BX) { do { i0 -= s0; ++i1; } while (i0 >= s0); }
+      else { const int r = i0 / s0; i0 -= r*s0; i1 += r; }
+      if (i1 >= s1) { const int r = i1 / s1; i1 -= r*s1; i2 += r; }
+    }
+  }
+}
+
+// host side: one segment per stream; returns false if the call has more streams than a launch takes
+static bool idx_add_segment(IdxSegs& P, unsigned& blocks, const dgb_view& v, int comp, int kind, const dgb_box& walk, const int* move,
+                            long long base, uint32_t block, uint32_t offset) {
+  if (P.n >= IDX_MAX_SEGS) return false;
+  const dgb_component& c = v.comp[comp];
+  const dgb_box& of = c.box[DGB_BOX_OVERLAPFRONT];
+  long long count = 1; for (int i = 0; i < v.dim; ++i) count *= walk.size[i];
+  if (count <= 0) return true;
+  IdxSeg& S = P.s[P.n];
+  S.base = base; S.count = count; S.s0 = walk.size[0]; S.s1 = v.dim > 1 ? walk.size[1] : 1;
+  long long idx = c.index_offset[kind], stride = 1;
+  long long strides[3] = {0, 0, 0};
+  for (int i = 0; i < v.dim; ++i) { idx += (long long)(walk.origin[i] + move[i] - of.origin[i])*stride; strides[i] = stride; stride *= of.size[i]; }
+  S.val0 = uint32_t(idx)*block + offset;
+  S.rowStride = uint32_t(strides[1])*block; S.planeStride = uint32_t(strides[2])*block;
+  S.firstBlock = blocks;
+  const long long vectors = ((base + count + 3) >> 2) - (base >> 2);
+  blocks += unsigned((vectors + BX*VEC_ITER - 1)/(BX*VEC_ITER));
+  ++P.n;
+  return true;
+}
+
 // ---- K3b: intersection normals -----------------------------------------------------------------------------------------
 // YaspIntersection::{outerNormal,unitOuterNormal,centerUnitOuterNormal} = +-e_dir (yaspgridintersection.hh:163-182),
 // integrationOuterNormal = geometry().volume() * centerUnitOuterNormal() (:184-190): out[(k*dim+d)*n + cell]
@@ -724,6 +800,19 @@ int dgb_mapper_index(const dgb_view* v, const dgb_mapper* m, int codim, int pity
   EntityOut o{}; o.index = d_out; o.block = m->block[codim]; o.offset = m->offset[codim];
   static const int rows = [] { const char* e = getenv("DGB_IDX_ROWS"); const int r = e ? atoi(e) : 32; return r == 64 || r == 128 ? r : 32; }();      // measured (403 M faces): 32: 0.325 ms, 64: 0.365, 128: 0.396
   static const int linear = [] { const char* e = getenv("DGB_SWEEP_LINEAR"); return e ? atoi(e) : -1; }();
+  static const bool vec = [] { const char* e = getenv("DGB_IDX_VEC"); return !e || atoi(e) != 0; }();
+  if (vec && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {       // one launch, 16-byte stores (k_index_vec)
+    IdxSegs P; P.n = 0; P.block = o.block;
+    unsigned blocks = 0;
+    const int zero[3] = {0, 0, 0};
+    const int rc = for_each_component(*v, codim, pitype, rows, [&](const SweepGeom& s, dim3) {
+      idx_add_segment(P, blocks, *v, s.comp, s.kind, v->comp[s.comp].box[s.kind], zero, s.base, o.block, o.offset);
+    });
+    if (rc != DGB_OK) return rc;
+    if (blocks) k_index_vec<<<blocks, BX, 0, (cudaStream_t)stream>>>(P, d_out);
+    DGB_CUDA(cudaGetLastError());
+    return DGB_OK;
+  }
   return for_each_component(*v, codim, pitype, rows, [&](const SweepGeom& s, dim3 grid) {
     const dgb_box& b = v->comp[s.comp].box[s.kind];
     if (linear == 1 || (linear == -1 && b.size[0] % 32 != 0)) {
@@ -744,6 +833,24 @@ int dgb_mapper_subindex(const dgb_view* v, const dgb_mapper* m, int cc, int pity
   SubTable t; t.n = sub_entities(v->dim, cc);
   for (int i = 0; i < t.n; ++i) { t.shift[i] = (unsigned char)sub_shift(v->dim, i, cc); t.move[i] = (unsigned char)sub_move(v->dim, i, cc); }
   const uint32_t block = m->block[cc], offset = m->offset[cc];
+  static const bool vec = [] { const char* e = getenv("DGB_IDX_VEC"); return !e || atoi(e) != 0; }();
+  if (vec && t.n <= IDX_MAX_SEGS && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
+    // codim 0 has one component: one stream per sub-entity number, all in one launch of k_index_vec
+    IdxSegs P; P.n = 0; P.block = block;
+    unsigned blocks = 0;
+    const int rc = for_each_component(*v, 0, pitype, IDX_ROWS, [&](const SweepGeom& s, dim3) {
+      for (int i = 0; i < t.n; ++i) {
+        // yaspgridentity.hh:764-776: coord += move, component = shiftmapping[shift], index in the overlapfront numbering
+        const int move[3] = { t.move[i] & 1, t.move[i] >> 1 & 1, t.move[i] >> 2 & 1 };
+        idx_add_segment(P, blocks, *v, v->comp_begin[cc] + v->shiftmap[t.shift[i]], DGB_BOX_OVERLAPFRONT, v->comp[s.comp].box[s.kind], move,
+                        (long long)i*s.n + s.base, block, offset);
+      }
+    });
+    if (rc != DGB_OK) return rc;
+    if (blocks) k_index_vec<<<blocks, BX, 0, (cudaStream_t)stream>>>(P, d_out);
+    DGB_CUDA(cudaGetLastError());
+    return DGB_OK;
+  }
   return for_each_component(*v, 0, pitype, IDX_ROWS, [&](const SweepGeom& s, dim3 grid) {
     k_subindex_rows<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, t, cc, block, offset, d_out);
   });

@@ -462,6 +462,17 @@ class GridView:
                                   ptrs, items, len(arrays), comm, _stream()))
 
 
+    def communicateVariable(self, mapper, offsets, data, iftype, direction):
+        """gv.communicate(dataHandle, iftype, dir) for a data handle with fixedSize() == false (yaspgrid.hh:1562-1634):
+        size(e) = offsets[i+1]-offsets[i] and gather(e) = data[offsets[i]:offsets[i+1]] with i = mapper.index(e) (int64 / float64
+        CUDA tensors). Returns the scatter(buff, e, n) calls of the reference in its order as (index, recv_offsets, recv_data)."""
+        ex = VariableExchange(self, mapper, offsets, data, iftype, direction)
+        try:
+            ex.exchange()
+            return ex.result()
+        finally:
+            ex.close()
+
     # ---- the phases of communicate, for other transports and single-device rank emulation -----------------
     def _items(self, mapper, arrays, item_sizes):
         arrays = list(arrays)
@@ -509,19 +520,29 @@ class MultipleCodimMultipleGeomTypeMapper:
     def size(self):
         return int(self.m.size)
 
-    def index(self, codim=0, partition=All_Partition):
+    def index(self, codim=0, partition=All_Partition, out=None):
+        """mapper.index(e) of every entity of the range, in iteration order (mcmgmapper.hh:212-226). `out`: caller-owned int32
+        CUDA tensor (any 4-byte alignment; 16-byte aligned buffers take the vectorised kernel)."""
         _require_cuda()
         torch = _torch()
-        out = torch.empty(self.gv.size(codim, partition), dtype=torch.int32, device="cuda")
+        n = self.gv.size(codim, partition)
+        if out is None:
+            out = torch.empty(n, dtype=torch.int32, device="cuda")
+        elif out.dtype != torch.int32 or not out.is_cuda or not out.is_contiguous() or out.numel() != n:
+            raise ValueError(f"index: out must be a contiguous int32 CUDA tensor with {n} entries")
         check(lib.dgb_mapper_index(C.byref(self.gv.v), C.byref(self.m), codim, partition, _ptr(out), _stream()))
         return out
 
-    def subIndex(self, cc, partition=All_Partition):
+    def subIndex(self, cc, partition=All_Partition, out=None):
         _require_cuda()
         torch = _torch()
         from math import comb
         ns = comb(self.gv.dim, cc) << cc
-        out = torch.empty((ns, self.gv.size(0, partition)), dtype=torch.int32, device="cuda")
+        n = self.gv.size(0, partition)
+        if out is None:
+            out = torch.empty((ns, n), dtype=torch.int32, device="cuda")
+        elif out.dtype != torch.int32 or not out.is_cuda or not out.is_contiguous() or out.numel() != ns*n:
+            raise ValueError(f"subIndex: out must be a contiguous int32 CUDA tensor with {ns}x{n} entries")
         check(lib.dgb_mapper_subindex(C.byref(self.gv.v), C.byref(self.m), cc, partition, _ptr(out), _stream()))
         return out
 
@@ -539,6 +560,64 @@ class MultipleCodimMultipleGeomTypeMapper:
         _require_cuda()
         check(lib.dgb_field_restore(self.gv.grid.h, self.gv.v.level, C.byref(self.m), _ptr(array), item_size,
                                     str(filename).encode(), _stream()))
+
+
+class VariableExchange:
+    """dgb_commvar: one exchange of a variable-size data handle (dgb.h). exchange() runs both message rounds over NCCL; the
+    phase methods let another transport (or a test that emulates several ranks on one device) move the segments itself."""
+
+    def __init__(self, gv, mapper, offsets, data, iftype, direction):
+        _require_cuda()
+        torch = _torch()
+        if offsets.dtype != torch.int64 or not offsets.is_cuda or offsets.numel() != mapper.size + 1:
+            raise ValueError(f"offsets must be an int64 CUDA tensor with mapper.size+1 = {mapper.size + 1} entries")
+        if data.dtype != torch.float64 or not data.is_cuda:
+            raise ValueError("data must be a float64 CUDA tensor")
+        self.gv, self.keep = gv, (offsets.contiguous(), data.contiguous())
+        self.h = C.c_void_p()
+        check(lib.dgb_commvar_create(gv.grid.h, gv.level, C.byref(mapper.m), iftype, direction, _ptr(self.keep[0]), _ptr(self.keep[1]),
+                                     _stream(), C.byref(self.h)))
+
+    def exchange(self):
+        comm = self.gv.grid.comm.h if self.gv.grid.comm is not None else None
+        check(lib.dgb_commvar_exchange(self.h, comm, _stream()))
+
+    def segments(self, recv_side):
+        """list of (peer, first entity slot, entity slots, first item, items)"""
+        out = (C.c_int64 * 512)()
+        check(lib.dgb_commvar_segments(self.h, 1 if recv_side else 0, out, 512))
+        return [tuple(int(out[1 + 5 * k + j]) for j in range(5)) for k in range(out[0])]
+
+    def buffers(self):
+        """device addresses (send sizes, send items, recv sizes, recv items) of the library-owned buffers"""
+        p = [C.c_void_p() for _ in range(4)]
+        check(lib.dgb_commvar_buffers(self.h, *[C.byref(x) for x in p]))
+        return tuple(x.value or 0 for x in p)
+
+    def sizesReceived(self):
+        check(lib.dgb_commvar_sizes_received(self.h, _stream()))
+
+    def result(self):
+        torch = _torch()
+        ne, ni = C.c_int64(0), C.c_int64(0)
+        check(lib.dgb_commvar_finish(self.h, _stream(), C.byref(ne), C.byref(ni)))
+        index = torch.empty(ne.value, dtype=torch.int32, device="cuda")
+        offsets = torch.empty(ne.value + 1, dtype=torch.int64, device="cuda")
+        data = torch.empty(ni.value, dtype=torch.float64, device="cuda")
+        check(lib.dgb_commvar_result(self.h, _ptr(index), _ptr(offsets), _ptr(data), _stream()))
+        return index, offsets, data
+
+    def close(self):
+        if self.h:
+            _torch().cuda.synchronize()
+            lib.dgb_commvar_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def mcmgElementLayout(dim):

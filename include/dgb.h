@@ -266,6 +266,32 @@ int dgb_comm_pack(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int d
                   const int32_t* item_sizes, int narrays, double** d_sendbuf, double** d_recvbuf, void* stream);
 int dgb_comm_unpack(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int dir, int op, double* const* d_arrays,
                     const int32_t* item_sizes, int narrays, void* stream);
+/* Data handles of VARIABLE size: CommDataHandleIF::fixedSize(dim, codim) == false (common/datahandleif.hh:97-125;
+ * YaspGrid::communicateCodim, yaspgrid.hh:1562-1634: "variable size case: sender side determines the size"; the reference's own
+ * checkCommunication uses it, test/checkcommunicate.hh:96-102). Bulk form of the handle:
+ *   size(e)            = d_send_offsets[i+1] - d_send_offsets[i],  i = mapper.index(e)   (CSR, mapper.size()+1 entries)
+ *   gather(buff, e)    = the items d_send_data[d_send_offsets[i] ...]
+ *   scatter(buff, e, n): the calls the reference would make are RETURNED, in its order (codim dim..0, receive boxes in list
+ *                        order, entities x fastest): d_index[k] = mapper.index(e) of call k, its n = d_offsets[k+1]-d_offsets[k]
+ *                        items at d_data[d_offsets[k] ...]. What the handle does with them (set, add, append) is the caller's.
+ * The mapper layout must have block 0 or 1 per codim (contains(dim, codim) = block != 0). As in the reference there are two
+ * message rounds: per-entity sizes, then the items. Collective. Life cycle:
+ *   dgb_commvar_create (local: sizes, offsets and packed items of every send box) -> dgb_commvar_exchange (both rounds over
+ *   NCCL; device copies for messages to the own rank) -> dgb_commvar_finish (counts) -> dgb_commvar_result -> dgb_commvar_destroy.
+ * Other transports (the reference's MPI torus; tests that emulate several ranks on one device) replace dgb_commvar_exchange:
+ *   move the words of d_send_sizes segment by segment into the partners' d_recv_sizes (dgb_commvar_segments: out[0] = number of
+ *   segments, then per segment peer, first entity slot, entity slots, first item, items; receive side: the item columns are
+ *   valid after dgb_commvar_sizes_received), call dgb_commvar_sizes_received, move the items the same way, then finish. */
+typedef struct dgb_commvar dgb_commvar;
+int dgb_commvar_create(dgb_grid* g, int level, const dgb_mapper* m, int iftype, int dir, const int64_t* d_send_offsets,
+                       const double* d_send_data, void* stream, dgb_commvar** out);
+int dgb_commvar_exchange(dgb_commvar* h, dgb_comm* comm, void* stream);
+int dgb_commvar_segments(dgb_commvar* h, int recv_side, int64_t* out, int cap);
+int dgb_commvar_buffers(dgb_commvar* h, int64_t** d_send_sizes, double** d_send_items, int64_t** d_recv_sizes, double** d_recv_items);
+int dgb_commvar_sizes_received(dgb_commvar* h, void* stream);
+int dgb_commvar_finish(dgb_commvar* h, void* stream, int64_t* n_entities, int64_t* n_items);
+int dgb_commvar_result(dgb_commvar* h, uint32_t* d_index, int64_t* d_offsets, double* d_data, void* stream);
+int dgb_commvar_destroy(dgb_commvar* h);
 int dgb_allreduce_min(double* d_value, dgb_comm* comm, void* stream);  /* comm().min(x), yaspgrid.hh:1316 pattern */
 int dgb_allreduce_max(double* d_value, dgb_comm* comm, void* stream);
 /* bytes this rank sent in the most recent dgb_communicate / fv step exchange (for NVLink GB/s reporting) */

@@ -107,6 +107,8 @@ class OracleLib:
             "orc_geogrid_eval": (i64, [vp, i32, i32, i32, i32, pd, i32, pd, pd, pd, pd, pd, pd]),
             "orc_geogrid_intersections": (i64, [vp, i32, i32, i32, i32, pd, i32, pd, pd, pd, pd, pd, pd, pd, pd]),
             "orc_communicate": (i64, [vp, i32, pu32, i32, i32, i32, i32, ppd, pi]),
+            "orc_communicate_variable": (i64, [vp, i32, pu32, i32, i32, C.POINTER(C.POINTER(C.c_int64)), ppd, C.POINTER(C.c_int64),
+                                               C.POINTER(C.c_int64), C.POINTER(pu32), C.POINTER(C.POINTER(C.c_int64)), ppd]),
             "orc_global_index": (i64, [vp, i32, i32, C.POINTER(pi32)]),
             "orc_backup": (i32, [vp, i32, C.c_char_p, i32]),
             "orc_restore": (vp, [i32, i32, i32, C.POINTER(C.c_char_p)]),
@@ -376,6 +378,25 @@ class World:
         arr = self._pp(per_rank_arrays)
         items = (C.c_int * na)(*item_sizes)
         return self._chk(self.L.orc_communicate(self.h, level, _block(block), iftype, direction, op, na, arr, items))
+
+    def communicate_variable(self, level, block, iftype, direction, per_rank_offsets, per_rank_data):
+        """variable-size data handle on all ranks: returns per rank (index uint32[k], n int64[k], items float64[...]) = the
+        scatter(buff, e, n) calls in the reference's order"""
+        P = len(per_rank_offsets)
+        offs = [np.ascontiguousarray(o, dtype=np.int64) for o in per_rank_offsets]
+        dats = [np.ascontiguousarray(d, dtype=np.float64) for d in per_rank_data]
+        po = (C.POINTER(C.c_int64) * P)(*[o.ctypes.data_as(C.POINTER(C.c_int64)) for o in offs])
+        pdat = (C.POINTER(C.c_double) * P)(*[d.ctypes.data_as(C.POINTER(C.c_double)) for d in dats])
+        nc, ni = (C.c_int64 * P)(), (C.c_int64 * P)()
+        self._chk(self.L.orc_communicate_variable(self.h, level, _block(block), iftype, direction, po, pdat, nc, ni, None, None, None))
+        idx = [np.zeros(nc[p], dtype=np.uint32) for p in range(P)]
+        n = [np.zeros(nc[p], dtype=np.int64) for p in range(P)]
+        items = [np.zeros(ni[p], dtype=np.float64) for p in range(P)]
+        pi_ = (C.POINTER(C.c_uint32) * P)(*[a.ctypes.data_as(C.POINTER(C.c_uint32)) for a in idx])
+        pn = (C.POINTER(C.c_int64) * P)(*[a.ctypes.data_as(C.POINTER(C.c_int64)) for a in n])
+        pit = (C.POINTER(C.c_double) * P)(*[a.ctypes.data_as(C.POINTER(C.c_double)) for a in items])
+        self._chk(self.L.orc_communicate_variable(self.h, level, _block(block), iftype, direction, po, pdat, nc, ni, pi_, pn, pit))
+        return [(idx[p], n[p], items[p]) for p in range(P)]
 
     def fv_init(self, rank, level, problem, params):
         params = np.ascontiguousarray(params, dtype=np.float64)

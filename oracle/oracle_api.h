@@ -114,6 +114,15 @@ int64_t orc_geogrid_intersections(void* w, int rank, int level, int pitype, int 
  * doubles per mapper entry. op 0 = set (local = remote), 1 = add (local = local + remote). Returns doubles sent in total. */
 int64_t orc_communicate(void* w, int level, const uint32_t* block, int iftype, int dir, int op,
                         int narrays, double** arrays, const int* item_sizes);
+/* a10 with a data handle of VARIABLE size (CommDataHandleIF::fixedSize == false; yaspgrid.hh:1562-1634), on all ranks at once.
+ * The handle: contains(dim, codim) = block[codim] != 0 (block 0 or 1), size(e) = offsets[rank][i+1] - offsets[rank][i] and
+ * gather(e) = data[rank][offsets[rank][i] ...] with i = mapper.index(e). Every scatter(buff, e, n) call is RECORDED in call
+ * order: recv_index[rank][k] = mapper.index(e), recv_n[rank][k] = n, the n items appended to recv_data[rank]. n_calls[rank] /
+ * n_items[rank] always receive the counts; the three output tables may be NULL (counting pass). Returns the items sent in
+ * total, or -1. */
+int64_t orc_communicate_variable(void* w, int level, const uint32_t* block, int iftype, int dir,
+                                 const int64_t* const* offsets, const double* const* data, int64_t* n_calls, int64_t* n_items,
+                                 uint32_t** recv_index, int64_t** recv_n, double** recv_data);
 /* a11: FV transport. problem 0: constant velocity params[0..2], inflow value params[3], initial
  * shell centre params[4..6], radii params[7..8]; problem 1: rotation about (0.5,0.5) with angular speed params[0],
  * inflow params[3], same initial condition. c[rank] is indexed by the element index (All partition). */

@@ -569,6 +569,63 @@ struct World {
     return sent;
   }
 
+  // ---- a10, variable-size data handle (yaspgrid.hh:1562-1634: the sender asks data.size(e) per entity and sends the sizes ahead
+  // of the items, :1566-1612; the receiver scatters entity by entity with the sender's n, :1712-1722) ----------------------------
+  int64_t communicateVariable(int level, const uint32_t* block, int iftype, int dir, const int64_t* const* offsets, const double* const* data,
+                              int64_t* nCalls, int64_t* nItems, uint32_t** rIndex, int64_t** rN, double** rData) {
+    int sw, rw;
+    switch (iftype) { case 0: sw = 4; rw = 5; break; case 1: sw = 6; rw = 7; break; case 2: case 3: sw = 2; rw = 3; break; case 4: sw = 0; rw = 1; break;
+                      default: throw std::runtime_error("unknown interface"); }
+    if (dir == 1) std::swap(sw, rw);
+    for (int c = 0; c <= dim; ++c) if (block[c] > 1) throw std::runtime_error("variable-size handle: block must be 0 or 1");
+    int64_t sent = 0;
+    for (int p = 0; p < P; ++p) { nCalls[p] = 0; nItems[p] = 0; }
+    for (int codim = dim; codim >= 0; --codim) {
+      if (!block[codim]) continue;
+      std::vector<std::vector<std::vector<double>>> msgs(P);           // items
+      std::vector<std::vector<std::vector<std::size_t>>> sizes(P);     // the size message that travels first
+      for (int p = 0; p < P; ++p) {
+        const Level& g = lev(p, level); const Mapper m = mapper(p, level, block);
+        for (const ListItem& it : g.lists[sw][codim]) {
+          std::vector<double> buf; std::vector<std::size_t> sz;
+          forEachCoord(dim, it.grid, [&](const I3& c) {
+            const Box& of = g.comp[codim][g.shiftmap[codim][it.shift]].box[OF];
+            int idx = 0, inc = 1; for (int i = 0; i < dim; ++i) { idx += (c[i]-of.origin[i])*inc; inc *= of.size[i]; }
+            const uint32_t e = uint32_t(it.offset + idx)*m.block[codim] + m.offset[codim];
+            sz.push_back(std::size_t(offsets[p][e+1] - offsets[p][e]));
+            for (int64_t k = offsets[p][e]; k < offsets[p][e+1]; ++k) buf.push_back(data[p][k]);
+          });
+          sent += int64_t(buf.size());
+          msgs[p].push_back(std::move(buf)); sizes[p].push_back(std::move(sz));
+        }
+      }
+      for (int p = 0; p < P; ++p) {
+        const Level& g = lev(p, level); const Mapper m = mapper(p, level, block);
+        std::vector<int> taken(P, 0);
+        for (const ListItem& it : g.lists[rw][codim]) {
+          const Level& og = lev(it.rank, level);
+          int seen = 0; const std::vector<double>* buf = nullptr; const std::vector<std::size_t>* sz = nullptr;
+          for (std::size_t j = 0; j < og.lists[sw][codim].size(); ++j)
+            if (og.lists[sw][codim][j].rank == p) { if (seen == taken[it.rank]) { buf = &msgs[it.rank][j]; sz = &sizes[it.rank][j]; break; } ++seen; }
+          if (!buf) throw std::runtime_error("local sends/receives do not match in exchange");
+          ++taken[it.rank];
+          std::size_t pos = 0, ent = 0;
+          forEachCoord(dim, it.grid, [&](const I3& c) {
+            const Box& of = g.comp[codim][g.shiftmap[codim][it.shift]].box[OF];
+            int idx = 0, inc = 1; for (int i = 0; i < dim; ++i) { idx += (c[i]-of.origin[i])*inc; inc *= of.size[i]; }
+            const uint32_t e = uint32_t(it.offset + idx)*m.block[codim] + m.offset[codim];
+            const std::size_t n = (*sz)[ent++];
+            if (rIndex) rIndex[p][nCalls[p]] = e;
+            if (rN) rN[p][nCalls[p]] = int64_t(n);
+            for (std::size_t k = 0; k < n; ++k) { if (rData) rData[p][nItems[p]] = (*buf)[pos]; ++pos; ++nItems[p]; }
+            ++nCalls[p];
+          });
+        }
+      }
+    }
+    return sent;
+  }
+
   // ---- (f2) GlobalIndexSet (dune/grid/utility/globalindexset.hh:318-440), all ranks at once ---------------------------
   int64_t globalIndex(int level, int codim, int32_t** out) {
     if (codim < 0 || codim > dim) throw std::range_error("codim out of range");
@@ -938,6 +995,10 @@ int64_t orc_geogrid_eval(void* w, int rank, int level, int pitype, int deformati
 }
 int64_t orc_communicate(void* w, int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* item_sizes) {
   return guarded(int64_t(-1), [&]() -> int64_t { return W(w)->communicate(level, block, iftype, dir, op, narrays, arrays, item_sizes); });
+}
+int64_t orc_communicate_variable(void* w, int level, const uint32_t* block, int iftype, int dir, const int64_t* const* offsets,
+                                 const double* const* data, int64_t* n_calls, int64_t* n_items, uint32_t** recv_index, int64_t** recv_n, double** recv_data) {
+  return guarded(int64_t(-1), [&]() -> int64_t { return W(w)->communicateVariable(level, block, iftype, dir, offsets, data, n_calls, n_items, recv_index, recv_n, recv_data); });
 }
 // (f3) BackupRestoreFacility::backup, yaspgrid/backuprestore.hh:105-128 (equidistant, offset), :222-246 (tensor product:
 // TensorProductCoordinates::print of the rank's level-0 container, coordinates.hh:347-356); default ostream formatting

@@ -157,6 +157,8 @@ struct WorldBase {
   virtual int64_t geogridIntersections(int rank, int level, int pit, int def, const double* params, int nqp, const double* qp,
                                        double*, double*, double*, double*, double*, double*, double*) = 0;
   virtual int64_t communicate(int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* items) = 0;
+  virtual int64_t communicateVariable(int level, const uint32_t* block, int iftype, int dir, const int64_t* const* offsets, const double* const* data,
+                                      int64_t* nCalls, int64_t* nItems, uint32_t** rIndex, int64_t** rN, double** rData) = 0;
   virtual std::string backup(int rank) = 0;
   virtual int64_t globalIndex(int level, int codim, int32_t** out) = 0;
   virtual int fvInit(int rank, int level, int problem, const double* params, double* c) = 0;
@@ -234,6 +236,32 @@ public:
   mutable int64_t written;
 private:
   const Mapper& mapper_; const uint32_t* block_; int n_; double* const* arrays_; const int* items_; int op_; std::size_t itemSize_;
+};
+
+// a data handle of variable size (fixedSize() == false): the CSR arrays say how many items an entity carries; scatter records
+// the calls it receives (entity's mapper index, n, the n items) in call order
+template<class Mapper>
+class VarDataHandle : public Dune::CommDataHandleIF<VarDataHandle<Mapper>, double> {
+public:
+  VarDataHandle(const Mapper& m, const uint32_t* block, const int64_t* off, const double* data, uint32_t* rIndex, int64_t* rN, double* rData)
+    : written(0), calls(0), items(0), mapper_(m), block_(block), off_(off), data_(data), rIndex_(rIndex), rN_(rN), rData_(rData) {}
+  bool contains(int /*dim*/, int codim) const { return block_[codim] > 0; }
+  bool fixedSize(int, int) const { return false; }
+  template<class Entity> std::size_t size(const Entity& e) const { const auto i = mapper_.index(e); return std::size_t(off_[i+1] - off_[i]); }
+  template<class Buf, class Entity> void gather(Buf& buf, const Entity& e) const {
+    const auto i = mapper_.index(e);
+    for (int64_t k = off_[i]; k < off_[i+1]; ++k) { buf.write(data_[k]); ++written; }
+  }
+  template<class Buf, class Entity> void scatter(Buf& buf, const Entity& e, std::size_t n) {
+    if (rIndex_) rIndex_[calls] = uint32_t(mapper_.index(e));
+    if (rN_) rN_[calls] = int64_t(n);
+    for (std::size_t k = 0; k < n; ++k) { double x; buf.read(x); if (rData_) rData_[items] = x; ++items; }
+    ++calls;
+  }
+  mutable int64_t written;
+  int64_t calls, items;
+private:
+  const Mapper& mapper_; const uint32_t* block_; const int64_t* off_; const double* data_; uint32_t* rIndex_; int64_t* rN_; double* rData_;
 };
 
 template<int dim, class CC>
@@ -599,6 +627,20 @@ struct World : WorldBase {
     return s;
   }
 
+  int64_t communicateVariable(int level, const uint32_t* block, int iftype, int dir, const int64_t* const* offsets, const double* const* data,
+                              int64_t* nCalls, int64_t* nItems, uint32_t** rIndex, int64_t** rN, double** rData) override {
+    for (int c = 0; c <= dim; ++c) if (block[c] > 1) DUNE_THROW(Dune::GridError, "variable-size handle: block must be 0 or 1");
+    std::vector<int64_t> sent(P, 0);
+    on_all_ranks(P, [&](int p) {
+      Mapper m = makeMapper(p, level, block);
+      VarDataHandle<Mapper> dh(m, block, offsets[p], data[p], rIndex ? rIndex[p] : nullptr, rN ? rN[p] : nullptr, rData ? rData[p] : nullptr);
+      g(p).levelGridView(level).communicate(dh, Dune::InterfaceType(iftype), Dune::CommunicationDirection(dir));
+      sent[p] = dh.written; nCalls[p] = dh.calls; nItems[p] = dh.items;
+    });
+    int64_t s = 0; for (auto v : sent) s += v;
+    return s;
+  }
+
   // the reference's own GlobalIndexSet, constructed collectively on all rank threads
   int64_t globalIndex(int level, int codim, int32_t** out) override {
     std::vector<int64_t> sizes(P, 0);
@@ -807,6 +849,10 @@ int64_t orc_geogrid_intersections(void* w, int rank, int level, int pit, int def
 }
 int64_t orc_communicate(void* w, int level, const uint32_t* block, int iftype, int dir, int op, int narrays, double** arrays, const int* items) {
   return guarded(int64_t(-1), [&]{ return W(w)->communicate(level, block, iftype, dir, op, narrays, arrays, items); });
+}
+int64_t orc_communicate_variable(void* w, int level, const uint32_t* block, int iftype, int dir, const int64_t* const* offsets,
+                                 const double* const* data, int64_t* n_calls, int64_t* n_items, uint32_t** recv_index, int64_t** recv_n, double** recv_data) {
+  return guarded(int64_t(-1), [&]{ return W(w)->communicateVariable(level, block, iftype, dir, offsets, data, n_calls, n_items, recv_index, recv_n, recv_data); });
 }
 int64_t orc_global_index(void* w, int level, int codim, int32_t** out) {
   return guarded(int64_t(-1), [&] { return W(w)->globalIndex(level, codim, out); });

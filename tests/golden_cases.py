@@ -34,6 +34,19 @@ def comm_data(size, seed):
     return [rng.standard_normal(size), rng.standard_normal(size * 3)]
 
 
+def var_data(size, seed):
+    """a variable-size data handle as CSR arrays: entity i carries 0..3 items"""
+    rng = np.random.default_rng(seed)
+    n = rng.integers(0, 4, size=size)
+    off = np.zeros(size + 1, dtype=np.int64)
+    np.cumsum(n, out=off[1:])
+    return off, rng.standard_normal(int(off[-1]))
+
+
+def var_layout(layout):
+    return [min(1, b) for b in layout]
+
+
 def snapshot(o, name):
     """everything `o` (an oracle.OracleLib) computes for case `name`"""
     cfg, P, layout, fv = CASES[name]
@@ -89,6 +102,15 @@ def snapshot(o, name):
                 for r in range(P):
                     for a in range(2):
                         s[f"comm/i{iftype}d{direction}o{op}/r{r}a{a}"] = data[r][a]
+    # data handle of variable size (fixedSize() == false): the scatter calls each rank receives, in the reference's order
+    vl = var_layout(layout)
+    for iftype in range(5):
+        for direction in (0, 1):
+            vd = [var_data(w.mapper_size(r, lvl, vl), 2000 + 10 * r) for r in range(P)]
+            got = w.communicate_variable(lvl, vl, iftype, direction, [v[0] for v in vd], [v[1] for v in vd])
+            for r in range(P):
+                for q, a in zip(("index", "n", "items"), got[r]):
+                    s[f"commvar/i{iftype}d{direction}/r{r}/{q}"] = a
     if fv is not None:
         problem, params = fv
         c = [w.fv_init(r, lvl, problem, params) for r in range(P)]

@@ -104,6 +104,18 @@ def main():
                         if not np.array_equal(dev[a].cpu().numpy(), host[rank][a]):
                             failures += 1
                             print(f"rank {rank}: communicate mismatch cfg={cfg['N']} if={iftype} dir={direction} op={op}", flush=True)
+        # data handle of variable size (fixedSize() == false) through the public call: both message rounds over NCCL
+        from tests.golden_cases import var_data
+        for iftype in range(5):
+            for direction in (0, 1):
+                vd = [var_data(w.mapper_size(r, 0, layout), 500 + 10 * r + iftype) for r in range(world)]
+                ref = w.communicate_variable(0, layout, iftype, direction, [v[0] for v in vd], [v[1] for v in vd])[rank]
+                index, roff, items = gv.communicateVariable(m, torch.from_numpy(vd[rank][0]).cuda(), torch.from_numpy(vd[rank][1]).cuda(), iftype, direction)
+                torch.cuda.synchronize()
+                if not (np.array_equal(index.cpu().numpy().view(np.uint32), ref[0]) and np.array_equal(np.diff(roff.cpu().numpy()), ref[1])
+                        and np.array_equal(items.cpu().numpy(), ref[2])):
+                    failures += 1
+                    print(f"rank {rank}: variable-size communicate mismatch cfg={cfg['N']} if={iftype} dir={direction}", flush=True)
         # Dune::GlobalIndexSet of every codim (collective: all-gather of the counts, two exchanges)
         for codim in range(cfg["dim"] + 1):
             ref, n = w.global_index(0, codim)

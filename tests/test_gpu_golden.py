@@ -99,6 +99,29 @@ def test_communicate_against_golden(name):
                         assert np.array_equal(np_(dev[r][a]), gold[f"{key}/r{r}a{a}"]), (key, r, a)
 
 
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_communicate_variable_against_golden(name):
+    """the variable-size data handle (fixedSize() == false) against the scatter-call sequences the reference itself produced"""
+    import torch
+    import dune_grid_b200 as dg
+    from tests.golden_cases import var_data, var_layout
+    from tests.test_gpu_comm_fv import emulated_variable_exchange
+    cfg, P, layout, _ = CASES[name]
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    lvl = cfg["refine"]
+    grids = [product_grid(cfg, r, P) for r in range(P)]
+    views = [g.levelGridView(lvl) for g in grids]
+    mappers = [dg.MultipleCodimMultipleGeomTypeMapper(v, var_layout(layout)) for v in views]
+    for iftype in range(5):
+        for direction in (0, 1):
+            vd = [var_data(mappers[r].size, 2000 + 10 * r) for r in range(P)]
+            got = emulated_variable_exchange(views, mappers, [torch.from_numpy(v[0]).cuda() for v in vd], [torch.from_numpy(v[1]).cuda() for v in vd],
+                                             iftype, direction)
+            for r in range(P):
+                for q, a in zip(("index", "n", "items"), got[r]):
+                    assert np.array_equal(a, gold[f"commvar/i{iftype}d{direction}/r{r}/{q}"]), (iftype, direction, r, q)
+
+
 @pytest.mark.parametrize("name", sorted(n for n in CASES if CASES[n][3] is not None))
 def test_fv_against_golden(name):
     cfg, P, _, (problem, params) = CASES[name]

@@ -4,6 +4,8 @@ bit-exact; axis-aligned geometry is bit-exact too (same expressions, FMA contrac
 GeometryGrid's J^-T and the separable FV mode are checked to 1e-13 relative as north_star allows.
 The reference's own invariants (test/checkindexset.hh, checkintersectionit.hh, gridcheck.hh:844-925,
 checkpartition.hh) are re-expressed as bulk checks in test_gpu_invariants.py."""
+import math
+
 import numpy as np
 import pytest
 
@@ -89,6 +91,47 @@ def test_mapper_and_subindices(oracle, cfg, P):
             lay[cc] = 1
             m = dg.MultipleCodimMultipleGeomTypeMapper(gv, lay)
             assert np.array_equal(np_(m.subIndex(cc, 4)).view(np.uint32).T, w.subindices(r, lvl, cc, 4))
+    w.close()
+
+
+VEC_CASES = [
+    (make_cfg(dim=3, N=(131, 5, 3)), 1), (make_cfg(dim=3, N=(3, 70, 9), periodic=7, overlap=2), 1), (make_cfg(dim=3, N=(600, 3, 2)), 2),
+    (make_cfg(dim=2, N=(1030, 3)), 1), (make_cfg(dim=3, N=(33, 17, 6), periodic=2), 4), (make_cfg(dim=3, N=(64, 8, 8)), 1),
+]
+
+
+@pytest.mark.parametrize("cfg,P", VEC_CASES, ids=[f"vec{i}" for i in range(len(VEC_CASES))])
+def test_mapper_index_vector_kernel(oracle, cfg, P):
+    """k_index_vec (16-byte stores, one launch for all streams; taken for 16-byte aligned outputs) against the oracle AND against
+    the column / linear kernels (taken for an output that is only 4-byte aligned), over every codim, partition range and stream
+    alignment: rows longer and shorter than a CTA's 512 entities, rows that are no multiple of 4, one-wide boxes, streams that
+    start at any offset modulo 4, guard words either side of the output."""
+    import torch
+    import dune_grid_b200 as dg
+    w = oracle_world(oracle, cfg, P)
+    d = cfg["dim"]
+    for r in range(P):
+        gv = product_grid(cfg, r, P).leafGridView()
+        m = dg.MultipleCodimMultipleGeomTypeMapper(gv, [2, 1, 3, 1][:d + 1])
+        for codim in range(d + 1):
+            for pit in range(5):
+                for sub in (False, True):
+                    if sub and pit not in (0, 4):
+                        continue
+                    n = gv.size(0 if sub else codim, pit)
+                    ns = (math.comb(d, codim) << codim) if sub else 1
+                    ref = (w.mapper_subindex(r, 0, [2, 1, 3, 1][:d + 1], codim, pit).T if sub else
+                           w.mapper_index(r, 0, [2, 1, 3, 1][:d + 1], codim, pit)).reshape(-1)
+                    for misalign in (0, 1):
+                        buf = torch.full((ns * n + 16,), -7, dtype=torch.int32, device="cuda")
+                        out = buf[4 + misalign:4 + misalign + ns * n]
+                        if sub:
+                            m.subIndex(codim, pit, out=out)
+                        else:
+                            m.index(codim, pit, out=out)
+                        got = np_(buf)
+                        assert np.array_equal(got[4 + misalign:4 + misalign + ns * n].view(np.uint32), ref), (r, codim, pit, sub, misalign)
+                        assert (got[:4 + misalign] == -7).all() and (got[4 + misalign + ns * n:] == -7).all(), "wrote outside the output"
     w.close()
 
 
