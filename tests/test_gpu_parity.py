@@ -95,7 +95,7 @@ def test_mapper_and_subindices(oracle, cfg, P):
 
 
 VEC_CASES = [
-    (make_cfg(dim=3, N=(131, 5, 3)), 1), (make_cfg(dim=3, N=(3, 70, 9), periodic=7, overlap=2), 1), (make_cfg(dim=3, N=(600, 3, 2)), 2),
+    (make_cfg(dim=3, N=(131, 5, 3)), 1), (make_cfg(dim=3, N=(5, 70, 9), periodic=7, overlap=2), 1), (make_cfg(dim=3, N=(3, 70, 9), periodic=7), 1), (make_cfg(dim=3, N=(600, 3, 2)), 2),
     (make_cfg(dim=2, N=(1030, 3)), 1), (make_cfg(dim=3, N=(33, 17, 6), periodic=2), 4), (make_cfg(dim=3, N=(64, 8, 8)), 1),
 ]
 
