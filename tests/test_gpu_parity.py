@@ -157,6 +157,25 @@ def test_intersections(oracle, cfg, P):
     w.close()
 
 
+# more box shapes for the element / intersection sweeps: rows of 131 / 132 / 38 / 1030 / 33 / 3 entities (column and linear walks)
+QUAD_CASES = [
+    (make_cfg(dim=3, N=(131, 4, 4)), 1), (make_cfg(dim=3, N=(130, 6, 4), periodic=7), 1), (make_cfg(dim=3, N=(64, 8, 8)), 2),
+    (make_cfg(dim=2, N=(1030, 4)), 1), (make_cfg(dim=3, N=(36, 8, 4), periodic=1, mode=2), 1), (make_cfg(dim=3, N=(33, 16, 8), periodic=2, refine=1), 4),
+    (make_cfg(dim=3, N=(3, 4, 8), periodic=7), 1),
+]
+QUAD_IDS = [f"quad{i}" for i in range(len(QUAD_CASES))]
+
+
+@pytest.mark.parametrize("cfg,P", QUAD_CASES, ids=QUAD_IDS)
+def test_entities_row_shapes(oracle, cfg, P):
+    test_entities(oracle, cfg, P)
+
+
+@pytest.mark.parametrize("cfg,P", QUAD_CASES, ids=QUAD_IDS)
+def test_intersections_row_shapes(oracle, cfg, P):
+    test_intersections(oracle, cfg, P)
+
+
 def gauss_points(dim, n1d):
     x, wts = np.polynomial.legendre.leggauss(n1d)
     x = 0.5 * (x + 1.0)
