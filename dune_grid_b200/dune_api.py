@@ -178,6 +178,18 @@ class GridView:
     def globalIndexSet(self, codim):
         return self._gv.globalIndexSet(codim)
 
+    def geometries(self, codim=0, partition=None):
+        """the geometries of ALL entities of a codimension at once: the bulk form of `for e in view.entities(codim): e.geometry`,
+        with the vectorised method names of dune/python/grid/geometry.hh:214-349"""
+        return BulkGeometry(self, codim, _g.All_Partition if partition is None else partition.pitype if isinstance(partition, Partition) else partition)
+
+    def polygons(self):
+        """corner loops of the cells of a 2-D view, shape (n, 4, 2): numpy.hh:184-212 (corners 0 and 1 swapped, as there)"""
+        if self.dimension != 2:
+            raise ValueError("polygons: two-dimensional views only (numpy.hh:201)")
+        c = self.geometries(0).corners                                     # (4, 2, n)
+        return c[[1, 0, 2, 3]].permute(2, 0, 1).contiguous()
+
     def writeVTK(self, name, celldata=None, pointdata=None, **kw):
         """gridView.writeVTK(name, celldata={...}, pointdata={...}) of dune-python (python/dune/grid/grid_generator.py): arrays
         indexed by the element / vertex index"""
@@ -189,6 +201,76 @@ class GridView:
     overlapFrontPartition = property(lambda self: Partition(self, _g.OverlapFront_Partition))
     allPartition = property(lambda self: Partition(self, _g.All_Partition))
     ghostPartition = property(lambda self: Partition(self, _g.Ghost_Partition))
+
+
+class BulkGeometry:
+    """Geometry of every entity of one codimension of a view (dune/python/grid/geometry.hh:168-349, vectorised forms): local
+    points x are (mydim,) or (npoints, mydim) arrays; results are CUDA tensors whose LAST axis runs over the entities in
+    iteration order (the order of mapper.index). Axis-aligned cubes (yaspgrid/yaspgridgeometry.hh:30-77), so affine is True."""
+
+    affine = True
+
+    def __init__(self, view, codim, pitype):
+        self._view, self.codim, self._pit = view, codim, pitype
+        self.dimension = self.mydimension = view.dimension - codim
+        self.coorddimension = view.dimension
+
+    def _x(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        single = x.ndim <= 1
+        return np.ascontiguousarray(x.reshape(-1, max(1, self.mydimension))), single
+
+    def _eval(self, x, key):
+        qp, single = self._x(x)
+        r = self._view._gv.geometryCodim(self.codim, qp, self._pit)[key]
+        return r[0] if single else r
+
+    def toGlobal(self, x):                                       # geometry.hh:200-214
+        return self._eval(x, "global")
+
+    def integrationElement(self, x):                             # :232-250
+        return self._eval(x, "integrationElement")
+
+    def jacobianTransposed(self, x):                             # :268-279
+        return self._eval(x, "jacobianTransposed")
+
+    def jacobianInverseTransposed(self, x):                      # :289-300
+        return self._eval(x, "jacobianInverseTransposed")
+
+    def jacobian(self, x):                                       # :252-266: transpose of jacobianTransposed
+        jt = self.jacobianTransposed(x)
+        return jt.transpose(-3, -2)
+
+    def jacobianInverse(self, x):                                # :280-288
+        jit = self.jacobianInverseTransposed(x)
+        return jit.transpose(-3, -2)
+
+    def toLocal(self, y):
+        """local coordinates of ONE global point y in every cell: shape (d, n); AxisAlignedCubeGeometry::local = (y - lower) / (upper - lower)"""
+        if self.codim != 0:
+            raise NotImplementedError("toLocal: cells only")
+        torch = _g._torch()
+        e = self._view._gv.elements(0, self._pit)
+        y = torch.as_tensor(np.asarray(y, dtype=np.float64), device="cuda").reshape(-1, 1)
+        return (y - e["lower"]) / (e["upper"] - e["lower"])
+
+    @property
+    def center(self):                                            # (d, n)
+        return self._view._gv.elements(self.codim, self._pit)["center"]
+
+    @property
+    def volume(self):                                            # (n,)
+        return self._view._gv.elements(self.codim, self._pit)["volume"]
+
+    @property
+    def corners(self):
+        """corner(i) of every entity, reference-cube numbering: shape (2^mydim, d, n)"""
+        m = self.mydimension
+        ref = np.array([[(i >> k) & 1 for k in range(max(1, m))] for i in range(1 << m)], dtype=np.float64).reshape(1 << m, max(1, m))
+        return self._view._gv.geometryCodim(self.codim, ref, self._pit)["global"]
+
+    def __len__(self):
+        return self._view._gv.size(self.codim, self._pit)
 
 
 # registerMapperCommunicate instantiations (dune/python/grid/mapper.hh:196-249 and its callers): (from, to) -> interface;

@@ -124,6 +124,7 @@ template<int dim> class BulkYaspGridBase;
 template<int dim, class Coordinates> class BulkYaspGrid;
 template<int dim> class BulkGridView;
 template<int dim> class BulkMapper;
+template<int dim> struct BulkVariableDataHandle;
 
 // result of elements<codim>(): arrays in iteration order of the partition; vectors are component-major [d*n + e]
 struct ElementRange {
@@ -218,6 +219,7 @@ public:
   // communicate: the data handle is "arrays indexed by a mapper" with a combine operation
   template<class DataHandle>
   void communicate(DataHandle& dh, InterfaceType iftype, CommunicationDirection dir, cudaStream_t s = nullptr) const;
+  void communicate(BulkVariableDataHandle<dim>& dh, InterfaceType iftype, CommunicationDirection dir, cudaStream_t s = nullptr) const;
 private:
   std::pair<std::array<double,dim>, std::array<double,dim>> localFace(int k, int outside) const {
     double lo[3], hi[3]; check(dgb_intersection_local_geometry(dim, k, outside, lo, hi));
@@ -260,6 +262,19 @@ struct BulkDataHandle {
   std::vector<double*> arrays;
   std::vector<std::int32_t> itemSizes;
   CommOp op = CommOp::set;
+};
+
+// A data handle of VARIABLE size (CommDataHandleIF::fixedSize() == false, common/datahandleif.hh:97-125): size(e) and gather(e) are the
+// CSR pair (offsets by mapper index, items); after communicate() the scatter(buff, e, n) calls the reference would make are in
+// recvIndex / recvOffsets / recvData, in the reference's order (dgb.h, dgb_commvar_*)
+template<int dim>
+struct BulkVariableDataHandle {
+  const BulkMapper<dim>& mapper;
+  const std::int64_t* sendOffsets;       // device, mapper.size()+1 entries
+  const double* sendData;                // device
+  DeviceArray<std::uint32_t> recvIndex;
+  DeviceArray<std::int64_t> recvOffsets;
+  DeviceArray<double> recvData;
 };
 
 // everything that does not depend on the coordinate container; BulkYaspGrid<dim,Coordinates> below adds the constructor of its container
@@ -432,6 +447,21 @@ template<class DataHandle>
 void BulkGridView<dim>::communicate(DataHandle& dh, InterfaceType iftype, CommunicationDirection dir, cudaStream_t s) const {
   check(dgb_communicate(grid_->handle(), v_.level, &dh.mapper.descriptor(), iftype, dir, int(dh.op), dh.arrays.data(), dh.itemSizes.data(),
                         int(dh.arrays.size()), grid_->comm(), s));
+}
+
+template<int dim>
+void BulkGridView<dim>::communicate(BulkVariableDataHandle<dim>& dh, InterfaceType iftype, CommunicationDirection dir, cudaStream_t s) const {
+  dgb_commvar* h = nullptr;
+  check(dgb_commvar_create(grid_->handle(), v_.level, &dh.mapper.descriptor(), iftype, dir, dh.sendOffsets, dh.sendData, s, &h));
+  struct Guard { dgb_commvar* h; ~Guard() { cudaDeviceSynchronize(); dgb_commvar_destroy(h); } } guard{h};
+  check(dgb_commvar_exchange(h, grid_->comm(), s));
+  std::int64_t ne = 0, ni = 0;
+  check(dgb_commvar_finish(h, s, &ne, &ni));
+  dh.recvIndex = DeviceArray<std::uint32_t>(std::size_t(ne));
+  dh.recvOffsets = DeviceArray<std::int64_t>(std::size_t(ne)+1);
+  dh.recvData = DeviceArray<double>(std::size_t(ni));
+  check(dgb_commvar_result(h, dh.recvIndex.data(), dh.recvOffsets.data(), dh.recvData.data(), s));
+  cudaStreamSynchronize(s);
 }
 
 // the explicit upwind finite-volume transport functor (include/dgb.h)

@@ -119,6 +119,27 @@ void deviceChecks() {
   bool filled = true;
   for (std::int64_t e = 0; e < n; ++e) filled = filled && std::abs(after[e] - cen[e]) <= 1e-14;   // wrapped centres equal the images' (up to rounding of i*h + L)
   CHECK(filled);
+  // a data handle of variable size (fixedSize() == false): cell e carries (index mod 3) copies of its centre's x coordinate; every
+  // overlap cell must receive exactly the items of its interior image
+  {
+    std::vector<std::int64_t> off(n+1, 0);
+    std::vector<double> items;
+    for (std::int64_t e = 0; e < n; ++e) { const int k = int(idx[e] % 3); off[e+1] = off[e] + k; for (int j = 0; j < k; ++j) items.push_back(cen[e] + j); }
+    DeviceArray<std::int64_t> dOff(n+1); dOff.fromHost(off);
+    DeviceArray<double> dItems(items.size()); dItems.fromHost(items);
+    BulkVariableDataHandle<dim> vh{em, dOff.data(), dItems.data(), {}, {}, {}};
+    gv.communicate(vh, InteriorBorder_All_Interface, ForwardCommunication);
+    auto ri = vh.recvIndex.toHost(); auto ro = vh.recvOffsets.toHost(); auto rd = vh.recvData.toHost();
+    bool okv = ro.size() == ri.size()+1 && (ro.empty() || std::size_t(ro.back()) == rd.size());
+    std::int64_t received = 0;
+    for (std::size_t k = 0; k < ri.size() && okv; ++k) {
+      const std::int64_t e = ri[k];                               // element mapper: index == position in iteration order
+      okv = okv && pt[e] != InteriorEntity;
+      for (std::int64_t j = ro[k]; j < ro[k+1]; ++j) okv = okv && std::abs(rd[j] - (cen[e] + double(j-ro[k]))) <= 1e-14;
+      ++received;
+    }
+    CHECK(okv && received == n - gv.size(0, Interior_Partition));
+  }
   // GlobalIndexSet on one rank without periodic copies: a permutation of 0..size-1 (utility/globalindexset.hh)
   {
     BulkYaspGrid<dim> plain(L, s, std::bitset<dim>(), 1);

@@ -77,3 +77,53 @@ def test_mapper_communicate_through_the_facade():
         m.communicate(view.interiorPartition, view.ghostPartition, CommOp.set, np.zeros(len(m)))
     assert view.coordinates().shape == (view.size(3), 3)
     w.close()
+
+
+@pytest.mark.gpu
+def test_bulk_geometry_names_of_the_python_bindings():
+    """view.geometries(codim): toGlobal / jacobianTransposed / jacobianInverseTransposed / integrationElement / corners / center /
+    volume / toLocal with the (vectorised) names of dune/python/grid/geometry.hh:168-349, against the oracle's per-entity geometry;
+    coordinates() and polygons() of dune/python/grid/numpy.hh:46-70,184-212"""
+    import torch
+    o = best_oracle()
+    for view, cfg in [(yaspGrid(tensorProductCoordinates([[0, .25, .5, 1], [0, .5, 1, 1.5, 3]]), periodic=[True, False]),
+                       make_cfg(dim=2, N=(3, 4), mode=2, tensor=[np.array([0, .25, .5, 1.]), np.array([0, .5, 1., 1.5, 3.])], periodic=1)),
+                      (yaspGrid(equidistantCoordinates([1.0, 2.0, 3.0], [6, 5, 4])), make_cfg(dim=3, N=(6, 5, 4), upper=(1.0, 2.0, 3.0)))]:
+        w = oracle_world(o, cfg, 1)
+        d = cfg["dim"]
+        for codim in range(d + 1):
+            m = d - codim
+            geo = view.geometries(codim)
+            rng = np.random.default_rng(codim)
+            x = rng.random((3, max(1, m)))
+            ref = w.geometry_eval_codim(0, 0, codim, x)
+            assert len(geo) == ref["global"].shape[0] and geo.affine
+            assert np.array_equal(geo.toGlobal(x).cpu().numpy().transpose(2, 0, 1), ref["global"])
+            assert np.array_equal(geo.integrationElement(x).cpu().numpy().T, ref["detJ"])
+            if m > 0:
+                assert np.array_equal(geo.jacobianTransposed(x).cpu().numpy().transpose(3, 0, 1, 2), ref["jt"])
+                assert np.array_equal(geo.jacobianInverseTransposed(x).cpu().numpy().transpose(3, 0, 1, 2), ref["jit"])
+                assert np.array_equal(geo.jacobian(x).cpu().numpy().transpose(3, 0, 2, 1), ref["jt"])
+                assert np.array_equal(geo.jacobianInverse(x).cpu().numpy().transpose(3, 0, 2, 1), ref["jit"])
+                # the single-point form drops the point axis (geometry.hh: scalar overloads)
+                assert np.array_equal(geo.toGlobal(x[0]).cpu().numpy().T, ref["global"][:, 0])
+            e = w.entities(0, 0, codim, 4)
+            assert np.array_equal(geo.center.cpu().numpy().T, e["center"]) and np.array_equal(geo.volume.cpu().numpy(), e["volume"])
+            c = geo.corners.cpu().numpy()                                   # (2^m, d, n): corner 0 = lower, last = upper
+            assert c.shape == (1 << m, d, len(geo))
+            assert np.array_equal(c[0].T, e["lower"]) and np.array_equal(c[-1].T, e["upper"])
+        cells = view.geometries(0)
+        y = np.full(d, 0.3)
+        loc = cells.toLocal(y).cpu().numpy()
+        back = cells.toGlobal(np.zeros(d)).cpu().numpy() + loc * (cells.corners[-1] - cells.corners[0]).cpu().numpy()
+        assert np.abs(back - y[:, None]).max() <= 1e-13
+        assert np.array_equal(view.coordinates().cpu().numpy(), w.entities(0, 0, d, 4)["center"])
+        if d == 2:
+            poly = view.polygons().cpu().numpy()
+            cc = cells.corners.cpu().numpy()
+            assert poly.shape == (len(cells), 4, 2) and np.array_equal(poly[:, 0], cc[1].T) and np.array_equal(poly[:, 1], cc[0].T)
+        else:
+            with pytest.raises(ValueError):
+                view.polygons()
+        assert isinstance(cells.toGlobal(np.zeros(d)), torch.Tensor)
+        w.close()
