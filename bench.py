@@ -351,8 +351,9 @@ def run_gpu(args):
                        "the peers' memory while it computes, so only this exposed part costs time); nvlink_gbs = bytes_per_rank / exchange_ms",
                 "standalone": {"ms": comm_ms, "nvlink_gbs": max_sent / (comm_ms * 1e-3) / 1e9,
                                "frac_of_900": max_sent / (comm_ms * 1e-3) / 1e9 / NVLINK_GBS,
-                               "how": "dgb_communicate(InteriorBorder_All, Forward) of the same field alone: pack kernel + grouped "
-                                      "ncclSend/ncclRecv + unpack kernel, nothing overlapped"}}
+                               "how": "dgb_communicate(InteriorBorder_All, Forward) of the same field alone, nothing overlapped: pack kernel "
+                                      "that stores into the peers' receive buffers over NVLink + flag, unpack kernel that waits for the "
+                                      "flags (DGB_COMM_PEER=0: pack, grouped ncclSend/ncclRecv, unpack)"}}
         # the local steps left the overlap cells stale: refresh them before anything else uses the field
         gv.communicate(m, [c], dg.InteriorBorder_All_Interface, dg.ForwardCommunication, "set")
         barrier()

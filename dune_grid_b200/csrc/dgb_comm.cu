@@ -123,7 +123,7 @@ __device__ __forceinline__ bool halo_wait(const HaloWait& hw) {
   }
   __syncthreads();
   if (s_timed_out) return false;                                      // never scatter a buffer a peer has not completed
-  if (blockIdx.x == 0 && s == 0) {
+  if (blockIdx.x == 0 && s == 0 && hw.slot) {
     double m = 0.0;
     for (int r = 0; r < hw.nranks; ++r) m = fmax(m, *reinterpret_cast<volatile double*>(&hw.ctl->cfl[hw.parity][r]));
     *hw.slot = m;
@@ -145,6 +145,47 @@ __global__ void __launch_bounds__(PACK_THREADS) k_halo(const PlanBox* __restrict
   else
     halo_box<MODE, long long>(b, arrays, buffer, (long long)cta*PACK_THREADS + threadIdx.x, (long long)nctas*PACK_THREADS, total);
 }
+
+// ---- communicate over peer-mapped memory: the pack kernel stores every send box straight into its place in the RECEIVER's buffer
+// (CUDA IPC mapping of the partner's exchange block, the stores travel over NVLink), the last CTA of the exchange publishes the
+// epoch in every rank's control block, and the first unpack launch waits for the flags of all ranks (halo_wait). Two launches,
+// no NCCL call, no staging copy; the protocol (two receive buffers by exchange parity, flags = exchanges delivered) is the one
+// of the fused FV step (dgb_fv.cu).
+struct PeerSignal { const FusedPack* pack; unsigned total, epoch; };
+__global__ void __launch_bounds__(PACK_THREADS) k_halo_peer(const PlanBox* __restrict__ boxes, double* const* __restrict__ dst, const ArrayTable arrays,
+                                                            const __grid_constant__ HaloGroup grp, const PeerSignal sig) {
+  int bi = 0;
+  while (bi+1 < grp.nboxes && int(blockIdx.x) >= grp.start[bi+1]) ++bi;          // CTA-uniform
+  const PlanBox& b = boxes[bi];
+  double* buffer = dst[bi] - b.buf_offset;                                       // halo_box writes buffer + buf_offset + t
+  const long long total = b.count*arrays.per_entity;
+  const unsigned cta = blockIdx.x - unsigned(grp.start[bi]), nctas = unsigned(grp.start[bi+1]-grp.start[bi]);
+  if (total < (1ll << 31) - (long long)nctas*PACK_THREADS)
+    halo_box<0, unsigned>(b, arrays, buffer, cta*PACK_THREADS + threadIdx.x, nctas*PACK_THREADS, unsigned(total));
+  else
+    halo_box<0, long long>(b, arrays, buffer, (long long)cta*PACK_THREADS + threadIdx.x, (long long)nctas*PACK_THREADS, total);
+  __syncthreads();                                   // the CTA's peer stores are ordered before thread 0's fence
+  if (threadIdx.x == 0) {
+    const FusedPack& P = *sig.pack;
+    __threadfence_system();
+    if (atomicAdd(P.counter, 1u) == sig.total-1) {   // the last CTA of the exchange (the counter runs over all its launches)
+      atomicExch(P.counter, 0u);
+      __threadfence_system();
+      for (int r = 0; r < P.nranks; ++r) *reinterpret_cast<volatile unsigned*>(P.peerFlag[r]) = sig.epoch;
+    }
+  }
+}
+
+// a rank that sends nothing still publishes its epoch; a rank that receives nothing still waits for the others (every rank
+// leaves exchange n only after all ranks have delivered it: the buffers of exchange n+2 may then be written)
+__global__ void k_halo_signal(const PeerSignal sig) {
+  if (threadIdx.x == 0) {
+    const FusedPack& P = *sig.pack;
+    __threadfence_system();
+    for (int r = 0; r < P.nranks; ++r) *reinterpret_cast<volatile unsigned*>(P.peerFlag[r]) = sig.epoch;
+  }
+}
+__global__ void __launch_bounds__(64) k_halo_wait_only(const HaloWait hw) { halo_wait(hw); }
 
 // ---- data handles of variable size (CommDataHandleIF::fixedSize == false, yaspgrid.hh:1562-1634) ----------------------------------
 // The sender decides how many items an entity carries. Bulk form: the send side is a CSR pair (offsets by mapper index, items);
@@ -382,6 +423,57 @@ int plan_unpack(CommPlan& plan, int op, double* const* d_arrays, const int32_t* 
   return DGB_OK;
 }
 
+static int run_plan_peer(dgb_grid* g, CommPlan& plan, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays, cudaStream_t stream) {
+  FusedState& fs = *plan.peer;
+  if (fs.timed_out()) return fail(DGB_ENCCL, "communicate: a rank did not deliver an earlier exchange within 20 s (ranks out of step, or a peer has died)");
+  if (int rc = plan.upload()) return rc;
+  ArrayTable at; if (int rc = make_table(plan, d_arrays, item_sizes, narrays, at)) return rc;
+  const unsigned epoch = ++fs.epoch;
+  const int parity = int(epoch & 1u);
+  // pack: the launches of launch_boxes with the peer kernel; the counter of "CTAs done" runs over all of them
+  struct Launch { std::size_t first; HaloGroup grp; int per; };
+  std::vector<Launch> launches;
+  unsigned total = 0;
+  for (std::size_t k = 0; k < plan.hostSend.size();) {
+    Launch L; L.first = k; L.grp.nboxes = 0; L.grp.start[0] = 0; L.per = int(plan.hostSend[k].block)*plan.items;
+    std::size_t e = k;
+    while (e < plan.hostSend.size() && plan.hostSend[e].block == plan.hostSend[k].block && L.grp.nboxes < HALO_MAX_GROUP) {
+      L.grp.start[L.grp.nboxes+1] = L.grp.start[L.grp.nboxes] + halo_ctas(plan.hostSend[e].count*(long long)plan.hostSend[e].block*plan.items);
+      ++L.grp.nboxes; ++e;
+    }
+    total += unsigned(L.grp.start[L.grp.nboxes]);
+    launches.push_back(L);
+    k = e;
+  }
+  int64_t bytes = 0;
+  for (auto& sg : plan.sendSeg) if (sg.peer != g->me.rank) bytes += sg.count*8;
+  PeerSignal sig{fs.dPack + parity, total, epoch};
+  if (launches.empty()) {
+    // a rank without anything to send still has to publish its epoch: one CTA, no box
+    HaloGroup grp; grp.nboxes = 0; grp.start[0] = 0;
+    (void)grp;
+    sig.total = 1;
+    k_halo_signal<<<1, 32, 0, stream>>>(sig);
+    ++plan.launches;
+  }
+  for (auto& L : launches) {
+    ArrayTable t = at; t.per_entity = L.per;
+    k_halo_peer<<<unsigned(L.grp.start[L.grp.nboxes]), PACK_THREADS, 0, stream>>>(plan.dSendBoxes + L.first, fs.dDst[parity] + L.first, t, L.grp, sig);
+    ++plan.launches;
+  }
+  DGB_CUDA(cudaGetLastError());
+  if (plan.trace[0]) cudaEventRecord(plan.trace[0], stream);
+  g->lastBytesSent = bytes;
+  if (plan.trace[1]) cudaEventRecord(plan.trace[1], stream);
+  HaloWait hw{fs.ctl, fs.hostPack[0].nranks, epoch, parity, nullptr, fs.dTimeout};
+  int rc = DGB_OK;
+  if (plan.nRecvBoxes) rc = plan_unpack_from(plan, fs.recv[parity], op, d_arrays, item_sizes, narrays, stream, &hw);
+  else { k_halo_wait_only<<<1, 64, 0, stream>>>(hw); ++plan.launches; }       // stay in step with the ranks that do receive
+  if (plan.trace[2]) cudaEventRecord(plan.trace[2], stream);
+  DGB_CUDA(cudaGetLastError());
+  return rc;
+}
+
 // the exchange itself; `arrays` are device pointers
 int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_arrays, const int32_t* item_sizes, int narrays,
              dgb_comm* comm, cudaStream_t stream, bool packed) {
@@ -391,6 +483,24 @@ int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_a
   if (remote && !comm) return fail(DGB_EARG, "this exchange has remote partners: a dgb_comm is required");
   if (remote) if (int rc = nccl_check_async(comm)) return rc;
   if (int rc = plan.enter(stream)) return rc;
+  if (!packed) {
+    // peer-memory form (default; DGB_COMM_PEER=0 keeps the NCCL form): set up collectively at the first use of the plan - every
+    // rank runs the same sequence of communicate calls (the contract of the call), so every rank is here with the same plan
+    static const bool wantPeer = [] { const char* e = getenv("DGB_COMM_PEER"); return !e || atoi(e) != 0; }();
+    // (a single-rank periodic exchange keeps the copy form: measured 0.049 vs 0.057 ms for two 1 M-cell faces, nothing travels)
+    if (wantPeer && remote && !plan.peerTried) {
+      plan.peerTried = true;
+      int nranks = 1; if (comm) nranks = comm->nranks;
+      auto fs = std::make_shared<FusedState>();
+      if (int rc = fused_setup(plan, myrank, nranks, comm, stream, *fs, true, 1 << 20)) return rc;
+      if (fs->on) plan.peer = fs;
+    }
+    if (plan.peer && plan.peer->on) {
+      const int rc = run_plan_peer(g, plan, op, d_arrays, item_sizes, narrays, stream);
+      if (int rc2 = plan.leave(stream)) return rc2;
+      return rc;
+    }
+  }
   if (packed) { if (int rc = plan.upload()) return rc; }
   else if (int rc = plan_pack(plan, d_arrays, item_sizes, narrays, stream)) return rc;
   if (plan.trace[0]) cudaEventRecord(plan.trace[0], stream);
@@ -481,14 +591,14 @@ int fused_teardown(FusedState& fs, dgb_comm* comm, cudaStream_t stream) {
   return rc;
 }
 
-int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs, bool local_ok) {
+int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs, bool local_ok, int max_boxes) {
   fs.on = false;
   if (nranks > 64) return DGB_OK;                              // FusedCtl capacity (same verdict on every rank)
   const bool multi = nranks > 1;
   if (multi && !comm) return DGB_OK;
   // Every rank takes part in BOTH collectives below (all-gather of the handles, all-reduce of the verdict) whatever fails
   // locally: a local failure only turns this rank's vote into "no", it never leaves the peers blocked in a collective.
-  bool ok = local_ok && plan.nSendBoxes <= 32;                 // FUSED_MAX_BOXES of the step kernels
+  bool ok = local_ok && plan.nSendBoxes <= max_boxes;          // FUSED_MAX_BOXES of the step kernels
   std::string why;
   auto soft = [&](cudaError_t e, const char* what) { if (e != cudaSuccess) { cudaGetLastError(); if (ok) why = std::string(what) + ": " + cudaGetErrorString(e); ok = false; } return e == cudaSuccess; };
   if (plan.upload() != DGB_OK) ok = false;

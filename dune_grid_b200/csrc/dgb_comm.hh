@@ -26,8 +26,12 @@ struct PlanBox {
   int face;                         // 2*axis + (partner on the high side) if the partner is a FACE neighbour (one non-zero torus offset), else -1
   int list_pos;                     // position in the reference's processing order (codim dim..0, list order): hostRecv is re-ordered by wave
 };
+struct FusedState;
 struct CommPlan {
   struct Segment { int peer; long long offset, count; };     // doubles
+  // peer-memory form of run_plan (see dgb_comm.cu, "communicate over peer-mapped memory"): set up collectively at the first use
+  std::shared_ptr<FusedState> peer;
+  bool peerTried = false;
   std::vector<Segment> sendSeg, recvSeg;
   long long sendTotal = 0, recvTotal = 0, maxSendBox = 0, maxRecvBox = 0;
   int nSendBoxes = 0, nRecvBoxes = 0, items = 0;
@@ -129,7 +133,8 @@ struct FusedState {
 // peer mapping is not available on every rank - the caller then keeps the NCCL path.
 // `local_ok` = false vetoes the fused form for ALL ranks (e.g. a rank without interior cells launches no step kernel and
 // could never signal)
-int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs, bool local_ok = true);
+// `max_boxes`: most send boxes the user of the state can handle (the FV step kernels keep them in their parameter space)
+int fused_setup(CommPlan& plan, int myrank, int nranks, dgb_comm* comm, cudaStream_t stream, FusedState& fs, bool local_ok = true, int max_boxes = 32);
 // collective teardown of a fused state shared between processes: every rank closes its imported mappings, all ranks meet in
 // a barrier (all-reduce on the communicator), only then the exported blocks are freed
 int fused_teardown(FusedState& fs, dgb_comm* comm, cudaStream_t stream);
