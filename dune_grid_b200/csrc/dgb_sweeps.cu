@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(BX) k_geogrid(const __grid_constant__ dgb_view
 // yaspgridintersection.hh:195-209), the face geometry is the multilinear map over them (centre, volume), and the normals at a
 // face-local point come from the ELEMENT's Jacobian at x = geometryInInside().global(local): outerNormal = J^-T n_ref,
 // integrationOuterNormal = J^-T n_ref |det J|, unitOuterNormal = outerNormal / |outerNormal|.
-struct FacePoints { int n; double x[16*2]; };
+struct FacePoints { int n; int center; double x[16*2]; };     // center: index of a point that IS the face centre (its unit normal is centerUnitOuterNormal), -1 if none
 struct GeoFaceOut { double *corners, *center, *volume, *ion, *on, *uon, *cuon; };
 
 template<int DIM>
@@ -696,16 +696,18 @@ __global__ void __launch_bounds__(BX) k_geogrid_faces(const __grid_constant__ dg
     }
     for (int p = 0; p < q.n; ++p) {
       double vI[DIM], vO[DIM], vU[DIM];
-      geoface_normals<DIM>(c, dir, side, q.x + p*(DIM-1), o.ion ? vI : nullptr, o.on ? vO : nullptr, o.uon ? vU : nullptr);
+      const bool isCenter = o.cuon && p == q.center;             // same expression, same point: no second evaluation for centerUnitOuterNormal
+      geoface_normals<DIM>(c, dir, side, q.x + p*(DIM-1), o.ion ? vI : nullptr, o.on ? vO : nullptr, (o.uon || isCenter) ? vU : nullptr);
 #pragma unroll
       for (int d = 0; d < DIM; ++d) {
         const long long at = ((long long)(f*q.n + p)*DIM + d)*s.n + pos;
         if (o.ion) o.ion[at] = vI[d];
         if (o.on) o.on[at] = vO[d];
         if (o.uon) o.uon[at] = vU[d];
+        if (isCenter) o.cuon[((long long)f*DIM + d)*s.n + pos] = vU[d];
       }
     }
-    if (o.cuon) {
+    if (o.cuon && q.center < 0) {
       double vU[DIM];
       geoface_normals<DIM>(c, dir, side, half, nullptr, nullptr, vU);
 #pragma unroll
@@ -953,6 +955,12 @@ int dgb_geogrid_intersections(const dgb_view* v, int pitype, int deformation, co
   if (deformation < 0 || deformation > 1) return fail(DGB_EARG, "unknown deformation id");
   FacePoints q; q.n = nqp;
   for (int i = 0; i < nqp*(v->dim-1); ++i) q.x[i] = qp_face_host[i];
+  q.center = -1;
+  for (int p = 0; p < nqp && q.center < 0; ++p) {
+    bool c = true;
+    for (int i = 0; i < v->dim-1; ++i) c = c && qp_face_host[p*(v->dim-1)+i] == 0.5;
+    if (c) q.center = p;
+  }
   Deformation def; def.id = deformation;
   for (int i = 0; i < 4; ++i) def.p[i] = (params_host && i < nparams) ? params_host[i] : 0.0;
   GeoFaceOut o{d_corners, d_center, d_volume, d_integrationOuterNormal, d_outerNormal, d_unitOuterNormal, d_centerUnitOuterNormal};

@@ -292,6 +292,12 @@ def test_geometrygrid_intersections(cfg):
         total = (ion * wt[None, :, None, None]).sum(dim=(0, 1))                                 # (d, n)
         area = got["volume"].sum(0)
         assert float((total.abs().max(dim=0).values / area).max()) <= 1e-13
+        # the face centre among the points: centerUnitOuterNormal is taken from that point's evaluation - identical values
+        qc = np.vstack([qp[:1], np.full((1, d - 1), 0.5), qp[1:]])
+        got_c = gv.geometryGridIntersections(deformation, params, qc, dg.All_Partition)
+        assert torch.equal(got_c["centerUnitOuterNormal"], got["centerUnitOuterNormal"])
+        assert torch.equal(got_c["unitOuterNormal"][:, 1], got["centerUnitOuterNormal"])
+        assert torch.equal(got_c["unitOuterNormal"][:, 2:], got["unitOuterNormal"][:, 1:]) and torch.equal(got_c["corners"], got["corners"])
         if deformation == 0:                                                                     # identity: the host's own normals
             for k in range(2 * d):
                 e = np.zeros(d); e[k // 2] = 1.0 if k % 2 else -1.0

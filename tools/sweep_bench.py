@@ -101,6 +101,13 @@ def main():
            timeit(lambda: gv5.geometryGrid(1, [0.05], qp, dg.All_Partition, corners=False), 3), nbytes(out), {"bytes_per_cell": nbytes(out) / n})
     del out
     torch.cuda.empty_cache()
+    # GeometryGrid intersections (a9): face corners, centre, volume, three normals at the face centre + centerUnitOuterNormal
+    for label, fq in (("face centre", np.array([[0.5, 0.5]])), ("2x2 Gauss points", np.stack([x.T.reshape(-1) for x in np.meshgrid(gauss, gauss, indexing="ij")], axis=1))):
+        out = gv5.geometryGridIntersections(1, [0.05], fq, dg.All_Partition)
+        report(f"k_geogrid_faces (corners, centre, volume, normals at {label})", "GeometryGrid over 256^3",
+               timeit(lambda: gv5.geometryGridIntersections(1, [0.05], fq, dg.All_Partition), 3), nbytes(out), {"bytes_per_cell": nbytes(out) / n})
+        del out
+        torch.cuda.empty_cache()
     ms = timeit(lambda: gv5.geometryGridVolume(1, [0.05], qp, wts, dg.All_Partition), 5)
     vol = gv5.geometryGridVolume(1, [0.05], qp, wts, dg.All_Partition).item()
     print(json.dumps({"kernel": "k_geogrid_volume (reduction)", "config": "GeometryGrid over 256^3", "ms": ms, "cells_per_s": n / ms * 1e3,
