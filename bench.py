@@ -95,7 +95,7 @@ class ClockSampler:
             os.close(fd)
             q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "5",
                                           "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -104,6 +104,18 @@ class ClockSampler:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.proc:
             return out
+        # a timed region shorter than the sampling period (20 steps of 0.35 ms) may have seen no sample: wait for the next one - the
+        # clocks right after the region - and say so
+        late = False
+        t0 = time.time()
+        while time.time() - t0 < 0.2:
+            try:
+                if sum(1 for _ in open(self.path)) > getattr(self, "skip", 0):
+                    break
+            except Exception:
+                break
+            late = True
+            time.sleep(0.005)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -130,6 +142,8 @@ class ClockSampler:
         if sm:
             sm.sort()
             out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            if late:
+                out["note"] = "the timed region was shorter than the sampling period: first sample after it"
         return out
 
 

@@ -384,35 +384,37 @@ __global__ void __launch_bounds__(BX) k_index_vec(const __grid_constant__ IdxSeg
   const IdxSeg& S = P.s[k];
   const uint32_t block = P.block;
   const long long g = (S.base >> 2) + (long long)(blockIdx.x - S.firstBlock)*(BX*VEC_ITER) + threadIdx.x;
-  long long e = 4*g - S.base;                      // entity of the vector's first lane; -3..-1 only for the first vector of a stream
-  if (e >= S.count) return;
+  const long long e0 = 4*g - S.base;               // entity of the vector's first lane; -3..-1 only for the first vector of a stream
+  if (e0 >= S.count) return;
   const int s0 = S.s0, s1 = S.s1;
   int i0, i1, i2;
   {
-    const long long ee = e < 0 ? 0 : e, q = ee / s0;
+    const long long ee = e0 < 0 ? 0 : e0, q = ee / s0;
     i0 = int(ee - q*s0); i2 = int(q / s1); i1 = int(q - (long long)i2*s1);
   }
-  uint32_t* p = out + (S.base + e);
-#pragma unroll 1
+  uint32_t* p = out + (S.base + e0);
+  // 32-bit bookkeeping inside the loop (ncu: the 64-bit form was issue bound at 72 instructions per vector): `left` = entities from
+  // lane 0 of the current vector to the end of the stream, clamped (a thread advances by VEC_ITER*4*BX entities at most)
+  const long long leftLL = S.count - e0;
+  int left = leftLL > (1ll << 30) ? (1 << 30) : int(leftLL);
+  int skip = e0 < 0 ? int(-e0) : 0;                // lanes of the stream's first vector that lie before the stream
+#pragma unroll 2
   for (int j = 0; j < VEC_ITER; ++j) {
-    uint32_t val = S.val0 + uint32_t(i0)*block + uint32_t(i1)*S.rowStride + uint32_t(i2)*S.planeStride;
-    int adv = 4*BX;
-    if (e >= 0 && e + 3 < S.count && i0 + 3 < s0) {
+    const uint32_t val = S.val0 + uint32_t(i0)*block + uint32_t(i1)*S.rowStride + uint32_t(i2)*S.planeStride;
+    if (skip == 0 && left >= 4 && i0 + 3 < s0) {
       *reinterpret_cast<uint4*>(p) = make_uint4(val, val + block, val + 2*block, val + 3*block);
     } else {
-      int a0 = i0, a1 = i1, a2 = i2;
-      for (int l = 0; l < 4; ++l) {
-        const long long el = e + l;
-        if (el < 0) continue;                      // (a0,a1,a2) is entity 0 until el reaches it
-        if (el >= S.count) break;
+      int a0 = i0, a1 = i1, a2 = i2;               // (a0,a1,a2) is entity 0 until the lane reaches it
+      for (int l = skip; l < 4 && l < left; ++l) {
         p[l] = S.val0 + uint32_t(a0)*block + uint32_t(a1)*S.rowStride + uint32_t(a2)*S.planeStride;
         if (++a0 == s0) { a0 = 0; if (++a1 == s1) { a1 = 0; ++a2; } }
       }
-      if (e < 0) adv += int(e);                    // the walk state stood at entity 0, not at e
     }
-    e += 4*BX; p += 4*BX;
-    if (e >= S.count) break;
-    i0 += adv;
+    left -= 4*BX;
+    if (left <= 0) break;
+    p += 4*BX;
+    i0 += 4*BX - skip;                             // the walk state stood at entity 0, not at e0, in the stream's first vector
+    skip = 0;
     if (i0 >= s0) {
       if (s0 >= BX) { do { i0 -= s0; ++i1; } while (i0 >= s0); }
       else { const int r = i0 / s0; i0 -= r*s0; i1 += r; }
