@@ -339,6 +339,55 @@ __global__ void __launch_bounds__(BX) k_intersections_linear(const __grid_consta
   }
 }
 
+// entities of one component in linear order (boxes whose rows are not a multiple of 32 entities): the form of k_intersections_linear
+__global__ void __launch_bounds__(BX) k_entities_linear(const __grid_constant__ dgb_view v, const SweepGeom s, const EntityOut o, long long count) {
+  const dgb_component& c = v.comp[s.comp];
+  const dgb_box& b = c.box[s.kind];
+  const int dim = v.dim;
+  long long e = (long long)blockIdx.x*(BX*LIN_ROWS) + threadIdx.x;
+  if (e >= count) return;
+  LinWalk w; w.init(e, b, dim);
+  const bool geo = o.lower || o.upper || o.center || o.volume;
+  double ll[3] = {0, 0, 0}, ur[3] = {0, 0, 0};
+  int coord[3] = { b.origin[0]+w.i0, b.origin[1]+w.i1, dim > 2 ? b.origin[2]+w.i2 : 0 };
+  // yaspgridentity.hh:270-274 (no wrap for 0 < codim), :491-514 (codim 0 wraps), AxisAlignedCubeGeometry
+  auto axis = [&](int i) {
+    if (!geo) return;
+    const bool ext = c.shift >> i & 1u;
+    ll[i] = vertex_coord(v, i, coord[i]);
+    ur[i] = ext ? vertex_coord(v, i, coord[i]+1) : ll[i];
+    if (c.codim == 0) { const double sh = periodic_shift(v, i, coord[i]); if (sh != 0.0) { ll[i] += sh; ur[i] += sh; } }
+  };
+  axis(0); if (dim > 1) axis(1); if (dim > 2) axis(2);
+  for (int j = 0; j < LIN_ROWS; ++j) {
+    const long long pos = s.base + e;
+    if (o.index) o.index[pos] = entity_index(v, c, s.kind, coord)*o.block + o.offset;
+    if (o.ptype) o.ptype[pos] = partition_type(v, c, coord);
+    if (o.coord) { long long p = pos; for (int i = 0; i < dim; ++i) { o.coord[p] = coord[i]; p += s.n; } }
+    if (geo) {
+      double vol = 1.0;
+      long long p = pos;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i < dim) {
+          if (o.lower) o.lower[p] = ll[i];
+          if (o.upper) o.upper[p] = ur[i];
+          if (o.center) o.center[p] = 0.5*(ll[i]+ur[i]);
+          if (c.shift >> i & 1u) vol *= ur[i]-ll[i];
+          p += s.n;
+        }
+      }
+      if (o.volume) o.volume[pos] = vol;
+    }
+    e += BX;
+    if (e >= count) break;
+    const int ch = w.step();
+    coord[0] = b.origin[0]+w.i0; axis(0);
+    if (ch & 1) { coord[1] = b.origin[1]+w.i1; axis(1); }
+    if (ch & 2) { coord[2] = b.origin[2]+w.i2; axis(2); }
+  }
+}
+
 // mapper indices of one component in linear order (see above): two adds per entity, every warp store aligned
 __global__ void __launch_bounds__(BX) k_index_linear(const __grid_constant__ dgb_view v, const SweepGeom s, uint32_t block, uint32_t offset,
                                                      uint32_t* __restrict__ out, long long count) {
@@ -864,7 +913,20 @@ int dgb_elements_materialize(const dgb_view* v, int codim, int pitype, uint32_t*
                              double* d_lower, double* d_upper, double* d_center, double* d_volume, void* stream) {
   if ((d_lower || d_upper || d_center || d_volume)) if (int rc = check_tensor(*v)) return rc;
   EntityOut o{d_index, d_ptype, d_coord, d_lower, d_upper, d_center, d_volume, 1u, 0u};
+  static const int linear = [] { const char* e = getenv("DGB_SWEEP_LINEAR"); return e ? atoi(e) : -1; }();      // -1 automatic, 0 never, 1 always
   return for_each_component(*v, codim, pitype, ENT_ROWS, [&](const SweepGeom& s, dim3 grid) {
+    const dgb_box& b = v->comp[s.comp].box[s.kind];
+    // rows that do not keep the warps aligned: linear walk - where it was measured to win (tools/entities_probe.py, 384^3, fraction of
+    // the copy peak, column walk -> linear walk: cells 0.82 -> 0.98 (tensor, x periodic); faces 0.93 -> 1.06 / 0.81 -> 0.97; edges
+    // 0.84 -> 1.02 equidistant but 0.78 -> 0.55 with tensor-product tables; vertices 0.75 -> 0.67 / 0.76 -> 0.58)
+    const int cd = v->comp[s.comp].codim;
+    const bool pays = cd <= 1 || (cd == 2 && v->coord_mode != DGB_COORD_TENSORPRODUCT);
+    if (linear == 1 || (linear == -1 && b.size[0] % 32 != 0 && pays)) {
+      long long count = 1; for (int i = 0; i < v->dim; ++i) count *= b.size[i];
+      const unsigned nb = unsigned((count + BX*LIN_ROWS - 1)/(BX*LIN_ROWS));
+      k_entities_linear<<<nb, BX, 0, (cudaStream_t)stream>>>(*v, s, o, count);
+      return;
+    }
     k_entities<<<grid, BX, 0, (cudaStream_t)stream>>>(*v, s, o);
   });
 }
