@@ -340,6 +340,16 @@ std::shared_ptr<CommPlan> build_plan(dgb_grid* g, int level, const dgb_mapper& m
     plan->recvWaveEnd.push_back(int(ordered.size()));
   }
   plan->hostSend = sb; plan->hostRecv = ordered;
+  for (std::size_t r = 0; r < g->all.size() && !plan->anyRemote; ++r) {
+    std::vector<ListEntry> l;
+    for (int codim = dim; codim >= 0 && !plan->anyRemote; --codim) {
+      if (m.block[codim] == 0) continue;
+      for (int which : { sendWhich, recvWhich }) {
+        comm_list(g->all[r], g->all, level, codim, which, l);
+        for (const ListEntry& e : l) if (e.rank != int(r)) plan->anyRemote = true;
+      }
+    }
+  }
   return plan;
 }
 
@@ -488,7 +498,9 @@ int run_plan(dgb_grid* g, CommPlan& plan, int myrank, int op, double* const* d_a
     // rank runs the same sequence of communicate calls (the contract of the call), so every rank is here with the same plan
     static const bool wantPeer = [] { const char* e = getenv("DGB_COMM_PEER"); return !e || atoi(e) != 0; }();
     // (a single-rank periodic exchange keeps the copy form: measured 0.049 vs 0.057 ms for two 1 M-cell faces, nothing travels)
-    if (wantPeer && remote && !plan.peerTried) {
+    if (remote && !plan.anyRemote) return fail(DGB_EGRID, "communicate: the ranks disagree on the partners of this exchange");
+    if (plan.anyRemote && !comm) return fail(DGB_EARG, "this exchange has remote partners on some rank: a dgb_comm is required on every rank");
+    if (wantPeer && plan.anyRemote && comm && !plan.peerTried) {
       plan.peerTried = true;
       int nranks = 1; if (comm) nranks = comm->nranks;
       auto fs = std::make_shared<FusedState>();

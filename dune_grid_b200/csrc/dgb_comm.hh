@@ -32,6 +32,9 @@ struct CommPlan {
   // peer-memory form of run_plan (see dgb_comm.cu, "communicate over peer-mapped memory"): set up collectively at the first use
   std::shared_ptr<FusedState> peer;
   bool peerTried = false;
+  // does ANY rank exchange with another rank under this plan (evaluated for every rank from its integer descriptors, so all
+  // ranks agree)? The peer-memory form is collective: it is taken by all ranks or by none
+  bool anyRemote = false;
   std::vector<Segment> sendSeg, recvSeg;
   long long sendTotal = 0, recvTotal = 0, maxSendBox = 0, maxRecvBox = 0;
   int nSendBoxes = 0, nRecvBoxes = 0, items = 0;
