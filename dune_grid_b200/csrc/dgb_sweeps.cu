@@ -299,6 +299,15 @@ __global__ void __launch_bounds__(BX) k_intersections_linear(const __grid_consta
   };
   axis(0); if (dim > 1) axis(1); if (dim > 2) axis(2);
   for (int j = 0; j < LIN_ROWS; ++j) {
+    // the x coordinates of the NEXT entity are requested before this entity's 48 stores are issued: with tensor-product tables the
+    // loop waited on these two loads every iteration (ncu: long scoreboard 13 cycles per issue, DRAM 72 %)
+    const bool more = j+1 < LIN_ROWS && e + BX < count;
+    int ch = 0;
+    double nx0 = 0.0, nx1 = 0.0;
+    if (more) {
+      ch = w.step();
+      if (geo) { nx0 = vertex_coord(v, 0, b.origin[0]+w.i0); nx1 = vertex_coord(v, 0, b.origin[0]+w.i0+1); }
+    }
     const long long pos = s.base + e;
     const int inside = int(entity_index(v, c, s.kind, coord));
     long long pf = pos, pc = pos;
@@ -330,10 +339,16 @@ __global__ void __launch_bounds__(BX) k_intersections_linear(const __grid_consta
         }
       }
     }
+    if (!more) break;
     e += BX;
-    if (e >= count) break;
-    const int ch = w.step();
-    coord[0] = b.origin[0]+w.i0; axis(0);
+    coord[0] = b.origin[0]+w.i0;
+    if (geo) {
+      const double sh = periodic_shift(v, 0, coord[0]);
+      ll[0] = nx0; ur[0] = nx1;
+      if (sh != 0.0) { ll[0] += sh; ur[0] += sh; }
+    }
+    nb[0] = face_neighbor(v, coord, 0, 0); nb[1] = face_neighbor(v, coord, 0, 1);
+    bd[0] = face_boundary(v, coord, 0, 0); bd[1] = face_boundary(v, coord, 0, 1);
     if (ch & 1) { coord[1] = b.origin[1]+w.i1; axis(1); }
     if (ch & 2) { coord[2] = b.origin[2]+w.i2; axis(2); }
   }
@@ -359,7 +374,16 @@ __global__ void __launch_bounds__(BX) k_entities_linear(const __grid_constant__ 
     if (c.codim == 0) { const double sh = periodic_shift(v, i, coord[i]); if (sh != 0.0) { ll[i] += sh; ur[i] += sh; } }
   };
   axis(0); if (dim > 1) axis(1); if (dim > 2) axis(2);
+  const bool ext0 = c.shift & 1u;
   for (int j = 0; j < LIN_ROWS; ++j) {
+    // the x coordinates of the next entity are requested before this entity's stores (see k_intersections_linear)
+    const bool more = j+1 < LIN_ROWS && e + BX < count;
+    int ch = 0;
+    double nx0 = 0.0, nx1 = 0.0;
+    if (more) {
+      ch = w.step();
+      if (geo) { nx0 = vertex_coord(v, 0, b.origin[0]+w.i0); if (ext0) nx1 = vertex_coord(v, 0, b.origin[0]+w.i0+1); }
+    }
     const long long pos = s.base + e;
     if (o.index) o.index[pos] = entity_index(v, c, s.kind, coord)*o.block + o.offset;
     if (o.ptype) o.ptype[pos] = partition_type(v, c, coord);
@@ -379,10 +403,13 @@ __global__ void __launch_bounds__(BX) k_entities_linear(const __grid_constant__ 
       }
       if (o.volume) o.volume[pos] = vol;
     }
+    if (!more) break;
     e += BX;
-    if (e >= count) break;
-    const int ch = w.step();
-    coord[0] = b.origin[0]+w.i0; axis(0);
+    coord[0] = b.origin[0]+w.i0;
+    if (geo) {
+      ll[0] = nx0; ur[0] = ext0 ? nx1 : nx0;
+      if (c.codim == 0) { const double sh = periodic_shift(v, 0, coord[0]); if (sh != 0.0) { ll[0] += sh; ur[0] += sh; } }
+    }
     if (ch & 1) { coord[1] = b.origin[1]+w.i1; axis(1); }
     if (ch & 2) { coord[2] = b.origin[2]+w.i2; axis(2); }
   }
