@@ -620,6 +620,60 @@ class VariableExchange:
             pass
 
 
+class VTKSequenceWriter:
+    """Dune::VTKSequenceWriter(gridView, name, path, extendpath) (io/file/vtk/vtksequencewriter.hh, vtksequencewriterbase.hh:105-151):
+    one VTK file per write(time, ...) named `name-%05d` through the view's writer, and - on rank 0 - the ParaView collection
+    `name.pvd` that lists every time step written so far (same text as the reference's). With a non-empty `extendpath` on several
+    ranks the pieces AND the .pvtu header go to path/extendpath, which is where the collection points; the reference's pwrite
+    puts the header into `path` (vtkwriter.hh:1079) while its collection names path/extendpath (vtksequencewriterbase.hh:140-141)."""
+
+    def __init__(self, gv, name, path="", extendpath=""):
+        self.gv, self.name, self.path, self.extendpath = gv, str(name), str(path), str(extendpath)
+        self.timesteps = []
+
+    def _seq(self, count):                                   # seqName, :190-196
+        return f"{self.name}-{count:05d}"
+
+    @staticmethod
+    def _concat(base, p):                                    # the cases of concatPaths the writer meets
+        if not base:
+            return p
+        if not p:
+            return base
+        return base + p if base.endswith("/") else base + "/" + p
+
+    def getTimeSteps(self):
+        return list(self.timesteps)
+
+    def setTimeSteps(self, timesteps):
+        """continue a sequence after a restart (:176-185)"""
+        self.timesteps = [float(t) for t in timesteps]
+
+    def write(self, time, celldata=None, pointdata=None, outputType="ascii", float64=False):
+        g = self.gv.grid
+        count = len(self.timesteps)
+        self.timesteps.append(float(time))
+        piecepath = self.path if g.nranks == 1 else self._concat(self.path, self.extendpath)
+        written = self.gv.writeVTK(self._seq(count), celldata=celldata, pointdata=pointdata, path=piecepath, float64=float64, outputType=outputType)
+        if g.rank == 0:
+            lines = ['<?xml version="1.0"?> \n', '<VTKFile type="Collection" version="0.1" byte_order="LittleEndian"> \n', "<Collection> \n"]
+            for i, t in enumerate(self.timesteps):
+                if g.nranks == 1:
+                    full = self._concat(piecepath, self._seq(i) + ".vtu")
+                else:
+                    full = self._concat(piecepath, f"s{g.nranks:04d}-{self._seq(i)}.pvtu")
+                lines.append(f'<DataSet timestep="{_cxx_double(t)}" group="" part="0" name="" file="{full}"/> \n')
+            lines += ["</Collection> \n", "</VTKFile> \n"]
+            with open(self.name + ".pvd", "w") as f:
+                f.write("".join(lines))
+        return written
+
+
+def _cxx_double(x):
+    """operator<<(std::ostream&, double) with the default precision 6 (%g)"""
+    return "%g" % x
+
+
 def mcmgElementLayout(dim):
     return [1] + [0] * dim
 

@@ -183,3 +183,38 @@ def test_field_files_match_the_reference_writer(tmp_path, float64):
     p = torch.from_numpy(rng.integers(-64, 64, gv.size(3)) / 2.0).cuda()
     arrs = check_against_reference_writer(gv, tmp_path, celldata={"c": c, "velocity": vel}, pointdata={"p": p}, float64=float64)
     assert [a[1] for a in arrs] == ["p", "c", "velocity", "Coordinates", "connectivity", "offsets", "types"]
+
+
+def test_sequence_writer_files_and_collection(tmp_path, monkeypatch):
+    """VTKSequenceWriter (io/file/vtk/vtksequencewriterbase.hh:105-151): files `name-%05d.vtu` (serial) / `s####-name-%05d.pvtu` +
+    pieces (parallel) and the .pvd collection rank 0 rewrites at every step, character for character; setTimeSteps continues a
+    sequence after a restart"""
+    import dune_grid_b200 as dg
+    monkeypatch.chdir(tmp_path)
+    cfg = make_cfg(dim=2, N=(8, 4))
+    gv = product_grid(cfg, 0, 1).leafGridView()
+    w = dg.VTKSequenceWriter(gv, "run", path="out")
+    os.makedirs("out")
+    for t in (0.0, 0.125, 1e-7):
+        w.write(t)
+    assert sorted(os.listdir("out")) == ["run-00000.vtu", "run-00001.vtu", "run-00002.vtu"]
+    expect = ('<?xml version="1.0"?> \n<VTKFile type="Collection" version="0.1" byte_order="LittleEndian"> \n<Collection> \n'
+              '<DataSet timestep="0" group="" part="0" name="" file="out/run-00000.vtu"/> \n'
+              '<DataSet timestep="0.125" group="" part="0" name="" file="out/run-00001.vtu"/> \n'
+              '<DataSet timestep="1e-07" group="" part="0" name="" file="out/run-00002.vtu"/> \n'
+              '</Collection> \n</VTKFile> \n')
+    assert open("run.pvd").read() == expect
+    check_grid("out/run-00001.vtu", gv, 2)
+    # restart: a new writer continues the numbering
+    w2 = dg.VTKSequenceWriter(gv, "run", path="out")
+    w2.setTimeSteps(w.getTimeSteps())
+    assert w2.write(2.5) == "out/run-00003.vtu" and open("run.pvd").read().count("<DataSet") == 4
+    # two ranks: pieces + header per step under path/extendpath, the collection names the headers
+    ws = [dg.VTKSequenceWriter(product_grid(cfg, r, 2).leafGridView(), "par", path="out", extendpath="pieces") for r in range(2)]
+    os.makedirs("out/pieces")
+    for t in (0.0, 1.0):
+        for x in ws:
+            x.write(t)
+    assert sorted(os.listdir("out/pieces")) == ["s0002-p0000-par-00000.vtu", "s0002-p0000-par-00001.vtu", "s0002-p0001-par-00000.vtu",
+                                                "s0002-p0001-par-00001.vtu", "s0002-par-00000.pvtu", "s0002-par-00001.pvtu"]
+    assert 'file="out/pieces/s0002-par-00001.pvtu"' in open("par.pvd").read()
