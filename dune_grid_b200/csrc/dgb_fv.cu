@@ -740,10 +740,21 @@ struct FvPairLane {
   bool active, loader, side;                  // side duty (hybrid exchange): one 8-byte x halo cell per plane from the exchange buffer
 };
 
-template<int D, int BX, int BY, int MODE, bool ZPARAM>
+// MODE 9 (problems whose velocity depends on z: column_invariant == false): nothing is hoisted out of the z loop - every plane
+// evaluates the velocity functor at its six face centres and takes the upwind decisions there, in the order and with the
+// expressions of k_fv_march (same bits). Per-thread operands re-use the lane: f0..f3 = llx, urx, lly, ury; tbx, tby = xcx, xcy;
+// un5 = rwx; S.alt0 = rwy; S.flags: bit m = face m has a stored neighbour, bit 4+m = face m lies on the physical boundary.
+struct FvGeneral {
+  const FvProblem* q;
+  const double* xvz; const double* xcz;     // z vertex / centre tables, entry 0 = first plane of the chunk
+  int cz0, ovz0, ovz1, nz; bool perz;
+  double sum;                                // max over the planes of the outflow sum (CFL)
+};
+
+template<int D, int BX, int BY, int MODE, bool ZPARAM, int PROBLEM = 0>
 __device__ __forceinline__ void fv_pair_loop(FvPairLane L, const FvRingSlow S, const long long sz, const double* rwz, const FvZTable& zt,
                                              const int zbase, const int zn, const int kload, const int kmain,
-                                             const char* lo, const char* hi) {
+                                             const char* lo, const char* hi, FvGeneral* G = nullptr) {
   constexpr int R = D+2, PX = BX+4, PY = BY+2;
   constexpr unsigned SLOTB = (PX*PY + 2*PY)*8u, LASTB = (R-1)*SLOTB, ROWB = PX*8u;       // + 2*PY side cells (x halo from the exchange buffer)
   static_assert(R % 2 == 0, "even and odd planes must keep their slots");
@@ -752,6 +763,17 @@ __device__ __forceinline__ void fv_pair_loop(FvPairLane L, const FvRingSlow S, c
   double c_below = L.c_below, c_here = 0.0;
   const bool self4 = S.un4 >= 0.0, self5 = L.un5 >= 0.0;
   unsigned uPrev = LASTB, uCur = 0u, uNxt = SLOTB;       // CTA-uniform: slot of plane k-1 (free), k, k+1
+  /* one face of the general mode: the expressions and the order of DGB_FACE in k_fv_march (separable) */
+#define DGB_GFACE(DIRX, SIDE, FCX, FCY, FCZ, RW, NB, BD, CJ)                                                   \
+      {                                                                                                        \
+        const double fc[3] = { FCX, FCY, FCZ };                                                                \
+        double u[3]; fv_velocity3<PROBLEM>(*G->q, fc, u);                                                      \
+        const double un = (SIDE) ? u[DIRX] : -u[DIRX];                                                         \
+        const double factor = un*(RW);                                                                         \
+        if (factor >= 0.0) { sum += factor; upd -= c_here*factor; }                                            \
+        else if (NB) upd -= (CJ)*factor;                                                                       \
+        else if (BD) upd -= fv_boundary(*G->q, fc)*factor;                                                     \
+      }
 #define DGB_PAIR_CELL(GUARD, K, AOWN, AX, AY, ANXT, GL, XL, XR)                                               \
   {                                                                                                            \
     cp_async_wait<D-1>();                                                                                      \
@@ -777,6 +799,21 @@ __device__ __forceinline__ void fv_pair_loop(FvPairLane L, const FvRingSlow S, c
       if (!DY) upd -= L.tby;                                                                                   \
       upd -= (DZ ? c_below : c_here)*(-f5);                                                                    \
       upd -= (DZ ? c_here : c_above)*f5;                                                                       \
+    } else if (MODE == 9) {                                                                                    \
+      const unsigned own = uCur + (AOWN);                                                                      \
+      const int cz = G->cz0 + (K);                                                                             \
+      const double llz = __ldg(G->xvz + (K)), urz = __ldg(G->xvz + (K) + 1), xcz = __ldg(G->xcz + (K));         \
+      const bool nbz0 = cz > G->ovz0 && cz <= G->ovz1, nbz1 = cz+1 > G->ovz0 && cz+1 <= G->ovz1;                \
+      const bool bdz0 = !G->perz && cz == 0, bdz1 = !G->perz && cz+1 == G->nz;                                  \
+      double sum = 0.0;                                                                                        \
+      upd = 0.0;                                                                                               \
+      DGB_GFACE(0, 0, L.f0, L.tby, xcz, L.un5, S.flags & 1u, S.flags & 16u, lds_f64(uCur + (XL)))             \
+      DGB_GFACE(0, 1, L.f1, L.tby, xcz, L.un5, S.flags & 2u, S.flags & 32u, lds_f64(uCur + (XR)))             \
+      DGB_GFACE(1, 0, L.tbx, L.f2, xcz, S.alt0, S.flags & 4u, S.flags & 64u, lds_f64(own - ROWB + (AY)))      \
+      DGB_GFACE(1, 1, L.tbx, L.f3, xcz, S.alt0, S.flags & 8u, S.flags & 128u, lds_f64(own + ROWB + (AY)))     \
+      DGB_GFACE(2, 0, L.tbx, L.tby, llz, rw, nbz0, bdz0, c_below)                                              \
+      DGB_GFACE(2, 1, L.tbx, L.tby, urz, rw, nbz1, bdz1, c_above)                                              \
+      G->sum = fmax(G->sum, sum);                                                                              \
     } else {                                                                                                   \
       /* slow path: AY is the phase step (in bytes) towards the rows above and below */                       \
       const unsigned own = uCur + (AOWN);                                                                      \
@@ -810,6 +847,7 @@ __device__ __forceinline__ void fv_pair_loop(FvPairLane L, const FvRingSlow S, c
     if (k+1 < zn) DGB_PAIR_CELL(true, k+1, L.aO, L.xO, L.yO, L.aE, L.glE, S.xlO, S.xrO)
   }
 #undef DGB_PAIR_CELL
+#undef DGB_GFACE
 }
 
 template<int PROBLEM, int D, int BX, int BY, int MINB, bool ZPARAM, int STG = 0>      // STG: 0 8-byte staging, 1 aligned pairs, 2 phase-aware pairs
@@ -841,6 +879,9 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   double sum_max = 0.0;
   double f0 = 0, f1 = 0, f2 = 0, f3 = 0, un4 = 0, un5 = 0, alt0 = 0, alt1 = 0, alt2 = 0, alt3 = 0;
   unsigned flags = 0;                 // bit m: face m flows out; 4+m: upwind value is a stored neighbour; 8+m: boundary value
+  unsigned gflags = 0;                // general mode: bit m: face m has a stored neighbour; 4+m: face m lies on the physical boundary
+  constexpr bool GENERAL = !FvProblemById<PROBLEM>::type::column_invariant;
+  double g_llx = 0, g_urx = 0, g_lly = 0, g_ury = 0, g_xcx = 0, g_xcy = 0, g_rwx = 0, g_rwy = 0;
   const dgb_box& of = v.comp[0].box[DGB_BOX_OVERLAPFRONT];
   const dgb_box& ov = v.comp[0].box[DGB_BOX_OVERLAP];
   const int sy = of.size[0];
@@ -856,6 +897,7 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     const double lly = __ldg(a.tab.xv[1]+tty), ury = __ldg(a.tab.xv[1]+tty+1), xcy = __ldg(a.tab.xc[1]+tty), rwy = __ldg(a.tab.rw[1]+tty);
     const double xcz = __ldg(a.tab.xc[2]+(cz0-a.tab.first[2]));
     const bool perx = v.periodic & 1u, pery = v.periodic >> 1 & 1u;
+    if (GENERAL) { g_llx = llx; g_urx = urx; g_lly = lly; g_ury = ury; g_xcx = xcx; g_xcy = xcy; g_rwx = rwx; g_rwy = rwy; }
     double sxy = 0.0;
 #define DGB_COLFACE(K, F, ALT, DIRX, SIDE, FCX, FCY, RW, NB, BD)                                               \
     {                                                                                                          \
@@ -863,6 +905,8 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
       double u[3]; fv_velocity3<PROBLEM>(a.problem, fc, u);                                                    \
       const double un = (SIDE) ? u[DIRX] : -u[DIRX];                                                           \
       F = un*(RW);                                                                                             \
+      if (NB) gflags |= 1u << K;                                                                               \
+      if (BD) gflags |= 16u << K;                                                                              \
       if (F >= 0.0) { sxy += F; flags |= 1u << K; }                                                            \
       else if (NB) flags |= 16u << K;                                                                          \
       else if (BD) { ALT = bval; flags |= 256u << K; }                                                         \
@@ -902,7 +946,7 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   const int cand = s_pat[0];
   if (dx == 2 || dy == 2 || dx*4 + dy*2 + dz != cand) s_pat[1] = 0;
   __syncthreads();
-  const int pat = s_pat[1] ? cand : 8;
+  const int pat = (s_pat[1] && !GENERAL) ? cand : 8;    // general problems: all halo sides are staged, decisions per plane
 
   const double zlow = (!perz && ovz0 == 0) ? bval : 0.0;
   const long long idx0 = (long long)(cz0-of.origin[2])*sz + (long long)(cy-of.origin[1])*sy + (cx-of.origin[0]);
@@ -1003,6 +1047,12 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     int kmain = max(0, min(zn, kload-D));
     if (cz0 + kload >= of.origin[2]+of.size[2]-1) kmain = max(0, min(kmain, kload-D-1));
     if (sideLo || sideHi) kmain = max(0, min(kmain, zn-D-1));
+    if constexpr (GENERAL) {
+      L.f0 = g_llx; L.f1 = g_urx; L.f2 = g_lly; L.f3 = g_ury; L.tbx = g_xcx; L.tby = g_xcy; L.un5 = g_rwx; S.alt0 = g_rwy; S.flags = gflags;
+      FvGeneral G{ &a.problem, a.tab.xv[2] + zbase, a.tab.xc[2] + zbase, cz0, ovz0, ovz1, v.N[2], perz, 0.0 };
+      fv_pair_loop<D, BX, BY, 9, ZPARAM, PROBLEM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi, &G);
+      sum_max = G.sum;
+    } else
     switch (pat) {
       case 0: fv_pair_loop<D, BX, BY, 0, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
       case 1: fv_pair_loop<D, BX, BY, 1, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, kmain, lo, hi); break;
@@ -1202,6 +1252,13 @@ static int auto_zchunk(const int* size, int bx, int by, bool packs) {
   return zc;
 }
 
+// the ring kernel of a registered problem; problems whose velocity depends on z exist in the phase-aware pair form only
+template<int D, int BX, int BY, int MINB, bool ZP, int STG>
+static auto ring_kernel(int pb) -> decltype(&k_fv_ring<0, D, BX, BY, MINB, ZP, STG>) {
+  if constexpr (STG == 2) { if (pb == 2) return &k_fv_ring<2, D, BX, BY, MINB, ZP, 2>; }
+  return pb == 1 ? &k_fv_ring<1, D, BX, BY, MINB, ZP, STG> : &k_fv_ring<0, D, BX, BY, MINB, ZP, STG>;
+}
+
 template<bool REDUCE_ONLY>
 static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
   const dgb_view& v = fv->view;
@@ -1230,7 +1287,12 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     const int pb = fv->problem.id;
     // the ring kernel evaluates the x/y face factors once per COLUMN: only for problems that declare a z-independent velocity and a
     // constant inflow value (column_invariant); every other registered problem runs on the general z-march kernel
-    const bool ring = !exact && !(REDUCE_ONLY || a.update || !a.cnew) && variant != 99 && fv_problem_column_invariant(pb);
+    // (round 2: problems that do not declare it run on the same kernel in its general mode - velocity functor and upwind decisions
+    // per plane, phase-aware pair staging - instead of the z-march kernel: 1.10 -> see DESIGN.md 4.1)
+    static const bool generalRing = [] { const char* e = getenv("DGB_FV_GENERAL_RING"); return !e || atoi(e) != 0; }();
+    const bool invariant = fv_problem_column_invariant(pb);
+    const bool ring = !exact && !(REDUCE_ONLY || a.update || !a.cnew) && variant != 99 && (invariant || generalRing);
+    if (ring && !invariant) stg = 2;
     if (!REDUCE_ONLY) {
       int bx = 128, by = 4;                                                   // the z-march kernels
       if (ring) switch (variant) { case 2: bx = 64; by = 4; break; case 3: case 7: bx = 128; by = 4; break; case 9: bx = 64; by = 8; break; default: bx = 32; by = 8; }
@@ -1248,7 +1310,7 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     else if (!ring) DGB_MARCH_ANY(DGB_FV_SEPARABLE)
     else {
 #define DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, ZP_, STG_)                                                              \
-    { auto kf = pb ? k_fv_ring<1, D_, BX_, BY_, MINB_, ZP_, STG_> : k_fv_ring<0, D_, BX_, BY_, MINB_, ZP_, STG_>;        \
+    { auto kf = ring_kernel<D_, BX_, BY_, MINB_, ZP_, STG_>(pb);                                                     \
       DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));                    \
       kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); }
 #define DGB_RING(D_, BX_, BY_, MINB_, WITH8_, WITHA16_)                                                             \

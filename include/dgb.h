@@ -304,9 +304,10 @@ enum { DGB_FV_EXACT = 0,           /* per-cell arithmetic in the reference order
        DGB_FV_SEPARABLE = 1 };     /* tensor-product factorised face factors: <= 1e-13 relative */
 /* `problem` selects a compiled-in transport problem (velocity, inflow value, initial value: the FV registry of
  * csrc/dgb_functors.cuh): 0 constant velocity, 1 rotation in the x-y plane, 2 shear flow with a z-dependent velocity. The
- * production kernel k_fv_ring evaluates the x/y face factors once per COLUMN of cells, so it REQUIRES a velocity that does not
- * depend on z and a constant inflow value (`column_invariant` in the registry; problems 0 and 1); any other problem is routed to
- * the general kernel k_fv_march, which evaluates the functor per face. All problems must be time independent: the CFL bound
+ * production kernel k_fv_ring evaluates the x/y face factors once per COLUMN of cells where the problem allows it: a velocity that
+ * does not depend on z and a constant inflow value (`column_invariant` in the registry; problems 0 and 1). Any other problem runs
+ * on the same kernel in its general mode, which evaluates the functor at every face of every plane (same results as the z-march
+ * kernel k_fv_march, which remains the kernel of DGB_FV_EXACT). All problems must be time independent: the CFL bound
  * reduced while step n runs is the one step n+2 uses. */
 int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host, int nparams, int mode,
                   dgb_comm* comm, dgb_fv** out);

@@ -316,8 +316,8 @@ def test_fv_separable_mode_within_1e13(cfg, P, problem, params):
     ref = [w.fv_init(r, lvl, problem, params) for r in range(P)]
     ref_dts = [w.fv_step(lvl, problem, params, ref) for _ in range(steps)]
     got, dts, _, infos = run_fv(cfg, P, problem, params, "separable", steps, want_info=True)
-    if cfg["dim"] == 3:         # registry routing: column-invariant problems on the ring kernel, the others on the general one
-        assert all(i["kind"] == ("march" if problem == 2 else "ring") for i in infos), infos
+    if cfg["dim"] == 3:         # every registered problem runs on the ring kernel: column-invariant ones with hoisted x/y face factors,
+        assert all(i["kind"] == "ring" for i in infos), infos      # the others (problem 2) in its general mode (velocity functor per plane)
     for a, b in zip(dts, ref_dts):
         assert abs(a - b) <= 1e-13 * abs(b)
     scale = max(np.abs(x).max() for x in ref)
@@ -516,6 +516,43 @@ def test_fv_ring_kernels_equal_general_kernel_bitwise(problem, params, monkeypat
             for key, val in res.items():
                 assert val[1] == res[("99", "pair")][1]
                 assert torch.equal(val[0], res[("99", "pair")][0]), (cfg["N"], misalign, key)
+
+
+def test_fv_ring_general_mode_equals_march_kernel_bitwise(monkeypatch):
+    """a problem whose velocity depends on z (problem 2, column_invariant = false) on the ring kernel's general mode - the
+    velocity functor and the upwind decisions evaluated per plane, both tile shapes, aligned and misaligned fields, partial
+    tiles, periodic wraps, odd strides, every flow direction inside one grid - against the z-march kernel (DGB_FV_VARIANT=99): same bits"""
+    import torch
+    import dune_grid_b200 as dg
+    params = [1.3, -0.4, 0.9, 0.35, 0.5, 0.5, 0.5, 0.1, 0.45]          # u = (1.3 (z-0.5), -0.4, 0.9 (x-0.5)): all sign patterns occur
+    cfgs = (make_cfg(dim=3, N=(150, 37, 70), mode=2), make_cfg(dim=3, N=(70, 45, 33), periodic=3, upper=(1.0, 0.7, 1.3)),
+            make_cfg(dim=3, N=(131, 21, 19), periodic=7, upper=(1.0, 0.2, 0.2)), make_cfg(dim=3, N=(259, 10, 18), periodic=1, upper=(1.0, 0.05, 0.1)),
+            make_cfg(dim=3, N=(260, 14, 40), upper=(1.0, 0.05, 0.15)))
+    for cfg in cfgs:
+        g = product_grid(cfg, 0, 1)
+        n = g.leafGridView().size(0)
+        for misalign in (0, 1):
+            buf0 = torch.zeros(n + 2, dtype=torch.float64, device="cuda")
+            buf1 = torch.zeros(n + 2, dtype=torch.float64, device="cuda")
+            c0 = torch.from_numpy(np.random.default_rng(5).uniform(0.0, 1.0, n)).cuda()
+            res = {}
+            for variant, zchunk in (("99", "16"), ("0", "16"), ("3", "16"), ("3", "7"), ("0", "256")):
+                monkeypatch.setenv("DGB_FV_VARIANT", variant)
+                monkeypatch.setenv("DGB_FV_ZCHUNK", zchunk)
+                monkeypatch.setenv("DGB_FV_FUSED", "0")
+                monkeypatch.setenv("DGB_FV_NO_SPLIT", "1")
+                fv = dg.FiniteVolume(g, 0, 2, params, "separable")
+                c, cn = buf0[misalign:misalign + n], buf1[misalign:misalign + n]
+                c.copy_(c0)
+                for _ in range(3):
+                    fv.step(c, cn)
+                    c, cn = cn, c
+                info = fv.kernel_info()
+                assert info["kind"] == ("march" if variant == "99" else "ring") and (variant == "99" or info["staging_bytes"] == 16), info
+                res[(variant, zchunk)] = (c.clone(), fv.last_dt())
+            for key, val in res.items():
+                assert val[1] == res[("99", "16")][1], (cfg["N"], misalign, key)
+                assert torch.equal(val[0], res[("99", "16")][0]), (cfg["N"], misalign, key)
 
 
 @pytest.mark.parametrize("mode", ["exact", "separable"])
