@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <cuda.h>
 #include "dgb_internal.hh"
 #include "dgb_device.cuh"
 #include "dgb_functors.cuh"
@@ -850,9 +851,134 @@ __device__ __forceinline__ void fv_pair_loop(FvPairLane L, const FvRingSlow S, c
 #undef DGB_GFACE
 }
 
-template<int PROBLEM, int D, int BX, int BY, int MINB, bool ZPARAM, int STG = 0>      // STG: 0 8-byte staging, 1 aligned pairs, 2 phase-aware pairs
+// ---- tensor-map staging (STG = 3) ------------------------------------------------------------------------------------
+// Boxes whose row and plane strides are multiples of 16 bytes (even row length, 16-byte aligned field: the single-GPU 512^3
+// box) can be described to the TMA engine as a 3-D tensor of doubles. ONE thread of the CTA then stages a whole plane tile
+// (+ its x neighbours and the y neighbour row of the inflow side: a box of (BX+4) x (BY+1) cells; (BX+4) x (BY+2) where
+// the CTA's columns do not share a flow direction) with ONE cp.async.bulk.tensor instruction per plane. A box may start at
+// any EVEN column (its first byte must be 16-byte aligned - an odd start raises an illegal-instruction error, tools/probes/
+// tma_probe.cu), any row and plane, also outside the array: cells beyond the array are zero filled (they are never read: the neighbour flags of
+// the column decide). The other 511 threads issue no staging instruction at all. Completion is a transaction count on one
+// mbarrier per ring slot; the barrier of iteration k that frees the slot of plane k-1 stays a __syncthreads.
+struct FvTmaMaps { alignas(64) unsigned char inflow[128]; alignas(64) unsigned char full[128]; };   // two CUtensorMap objects
+struct FvNoTma {};
+template<int STG> struct FvTmaParam { typedef FvNoTma type; };
+template<> struct FvTmaParam<3> { typedef FvTmaMaps type; };
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra WAIT_%=;\n}\n"
+               :: "r"(bar), "r"(parity) : "memory");
+}
+// arm the slot's barrier with the box size and start the copy of the box at (x, y, z) of the tensor
+__device__ __forceinline__ void tma_stage_plane(unsigned dst, const void* map, int x, int y, int z, unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+               :: "r"(dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  unsigned p;
+  asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}\n" : "=r"(p));
+  return p != 0u;
+}
+struct FvTmaLane {
+  double f0, f1, f2, f3, tbx, tby, un5, dt;   // as FvRingLane
+  double c_below, zhigh;
+  char* w;                                    // own column in cnew
+  unsigned aOwn, aX, aY;                      // shared address of the own cell / the upwind x / y neighbour in slot 0 (= own cell if none)
+  bool active, issuer;                        // issuer: the warp that stages (one elected lane)
+};
+
+template<int D, int BX, int BY, int MODE, bool ZPARAM>
+__device__ __forceinline__ void fv_tma_loop(FvTmaLane L, const FvRingSlow S, const long long sz, const double* rwz, const FvZTable& zt,
+                                            const int zbase, const int zn, const int kload, const void* map, const unsigned bar0,
+                                            const unsigned ringBase, const int bx0, const int by0, const int bz0, const unsigned bytes) {
+  constexpr int R = D+2;
+  static_assert((R & (R-1)) == 0, "ring slots: a power of two");
+  constexpr int LOGR = R == 8 ? 3 : R == 4 ? 2 : R == 16 ? 4 : 1;
+  constexpr unsigned ROWB = (BX+4)*8u;
+  constexpr bool DX = MODE & 4, DY = MODE & 2, DZ = MODE & 1;
+  const long long sz8 = sz*8;
+  constexpr unsigned SLOTB = unsigned(((BX+4)*(BY+2)*8 + 127)/128*128), LASTB = (R-1)*SLOTB;
+  double c_below = L.c_below, c_here = 0.0;
+  const bool self4 = S.un4 >= 0.0, self5 = L.un5 >= 0.0;
+#define DGB_TMA_CELL(GUARD, K, UPREV, UCUR, UNXT, BARW, PARW, BARI)                                           \
+  {                                                                                                            \
+    if (!(GUARD) || (K)+1 <= kload) mbar_wait(bar0 + (BARW), (PARW));                                          \
+    __syncthreads();                                                                                           \
+    if (L.issuer && (!(GUARD) || (K)+1+D <= kload)) {                                                          \
+      if (elect_one()) tma_stage_plane(ringBase + (UPREV), map, bx0, by0, bz0 + (K)+1+D, bar0 + (BARI), bytes); \
+    }                                                                                                          \
+    const double c_above = (!(GUARD) || (K)+1 <= kload) ? lds_f64((UNXT) + L.aOwn) : L.zhigh;                  \
+    const double rw = ZPARAM ? zt.rw[zbase + (K)] : __ldg(rwz + (K));                                          \
+    double upd;                                                                                                \
+    if (MODE < 8) {                                                                                            \
+      const double f5 = L.un5*rw;                                                                              \
+      const double nx = lds_f64((UCUR) + L.aX), ny = lds_f64((UCUR) + L.aY);                                   \
+      upd = 0.0 - (DX ? nx : c_here)*L.f0;                                                                     \
+      if (DX) upd -= L.tbx;                                                                                    \
+      upd -= (DX ? c_here : nx)*L.f1;                                                                          \
+      if (!DX) upd -= L.tbx;                                                                                   \
+      upd -= (DY ? ny : c_here)*L.f2;                                                                          \
+      if (DY) upd -= L.tby;                                                                                    \
+      upd -= (DY ? c_here : ny)*L.f3;                                                                          \
+      if (!DY) upd -= L.tby;                                                                                   \
+      upd -= (DZ ? c_below : c_here)*(-f5);                                                                    \
+      upd -= (DZ ? c_here : c_above)*f5;                                                                       \
+    } else {                                                                                                   \
+      const unsigned own = (UCUR) + L.aOwn;                                                                    \
+      double val;                                                                                              \
+      val = S.alt0; if (S.flags & 16u) val = lds_f64(own - 8u);     if (S.flags & 1u) val = c_here; upd = 0.0 - val*L.f0;  \
+      val = S.alt1; if (S.flags & 32u) val = lds_f64(own + 8u);     if (S.flags & 2u) val = c_here; upd -= val*L.f1;       \
+      val = S.alt2; if (S.flags & 64u) val = lds_f64(own - ROWB);   if (S.flags & 4u) val = c_here; upd -= val*L.f2;       \
+      val = S.alt3; if (S.flags & 128u) val = lds_f64(own + ROWB);  if (S.flags & 8u) val = c_here; upd -= val*L.f3;       \
+      upd -= (self4 ? c_here : c_below)*(S.un4*rw);                                                            \
+      upd -= (self5 ? c_here : c_above)*(L.un5*rw);                                                            \
+    }                                                                                                          \
+    if (L.active) __stcs(reinterpret_cast<double*>(L.w), c_here + L.dt*upd);                                   \
+    c_below = c_here; c_here = c_above;                                                                        \
+    L.w += sz8;                                                                                                \
+  }
+  /* slot s of the ring: compile-time offsets while the plane number is a multiple of R at s = 0 */            
+#define DGB_TMA_FIXED(K, S_)                                                                                   \
+  DGB_TMA_CELL(false, (K)+(S_), unsigned(((S_)+R-1) % R)*SLOTB, unsigned(S_)*SLOTB, unsigned(((S_)+1) % R)*SLOTB,  \
+               unsigned(((S_)+1) % R)*8u, ((S_) == R-1 ? par ^ 1u : par), unsigned(((S_)+R-1) % R)*8u)
+  mbar_wait(bar0, 0u);                                   // plane 0 (always stored: the chunk starts on an interior plane)
+  c_here = lds_f64(L.aOwn);
+  const int kmain = max(0, min(zn, kload-D));            // cells whose staging and reads all hit stored planes
+  int k = 0;
+  unsigned par = 0u;                                     // parity of the use of the slots by the planes k .. k+R-1
+  if constexpr (R == 8) {
+#pragma unroll 1
+    for (; k+R <= kmain; k += R) {
+      DGB_TMA_FIXED(k, 0) DGB_TMA_FIXED(k, 1) DGB_TMA_FIXED(k, 2) DGB_TMA_FIXED(k, 3)
+      DGB_TMA_FIXED(k, 4) DGB_TMA_FIXED(k, 5) DGB_TMA_FIXED(k, 6) DGB_TMA_FIXED(k, 7)
+      par ^= 1u;
+    }
+  }
+  unsigned uPrev = unsigned((k+R-1) & (R-1))*SLOTB, uCur = unsigned(k & (R-1))*SLOTB, uNxt = unsigned((k+1) & (R-1))*SLOTB;
+#define DGB_TMA_ROTATE uPrev = uCur; uCur = uNxt; uNxt = (uNxt == LASTB) ? 0u : uNxt + SLOTB;
+#pragma unroll 1
+  for (; k < kmain; ++k) {
+    DGB_TMA_CELL(false, k, uPrev, uCur, uNxt, unsigned((k+1) & (R-1))*8u, unsigned((k+1) >> LOGR) & 1u, unsigned((k+1+D) & (R-1))*8u)
+    DGB_TMA_ROTATE
+  }
+#pragma unroll 1
+  for (; k < zn; ++k) {
+    DGB_TMA_CELL(true, k, uPrev, uCur, uNxt, unsigned((k+1) & (R-1))*8u, unsigned((k+1) >> LOGR) & 1u, unsigned((k+1+D) & (R-1))*8u)
+    DGB_TMA_ROTATE
+  }
+#undef DGB_TMA_ROTATE
+#undef DGB_TMA_FIXED
+#undef DGB_TMA_CELL
+}
+
+template<int PROBLEM, int D, int BX, int BY, int MINB, bool ZPARAM, int STG = 0>      // STG: 0 8-byte staging, 1 aligned pairs, 2 phase-aware pairs, 3 tensor map (TMA)
 __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__ dgb_view v, const __grid_constant__ FvArgs a,
-                                                         const __grid_constant__ FvZTable zt, const int zc) {
+                                                         const __grid_constant__ FvZTable zt, const int zc,
+                                                         const __grid_constant__ typename FvTmaParam<STG>::type tmaps) {
   constexpr bool A16 = STG == 1;
   constexpr int PX = STG ? BX+4 : BX+2, PY = BY+2, SLOT = PX*PY, XO = STG ? 2 : 1;      // XO: column of the tile's first cell
   static_assert(2*BX + 2*BY <= BX*BY, "one halo cell per thread");
@@ -1066,6 +1192,64 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
     }
     cp_async_wait<0>();
     if (active && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = L.dt;
+  } else if constexpr (STG == 3) {
+    constexpr int R = D+2, PXT = BX+4;                    // the box starts at an even column (16-byte aligned start: a TMA rule for 8-byte elements)
+    constexpr unsigned SLOTB = ((PXT*(BY+2)*8u + 127u)/128u)*128u;      // TMA destinations: 128-byte aligned
+    FvTmaLane L; FvRingSlow S;
+    L.active = active;
+    L.f0 = f0; L.f1 = f1; L.f2 = f2; L.f3 = f3; L.un5 = un5; L.tbx = 0.0; L.tby = 0.0;
+    S.alt0 = alt0; S.alt1 = alt1; S.alt2 = alt2; S.alt3 = alt3; S.un4 = un4; S.flags = flags;
+    S.xlE = S.xlO = S.xrE = S.xrO = 0u;
+    L.zhigh = (!perz && ovz1+1 == v.N[2]) ? bval : 0.0;
+    L.dt = 0.99*(1.0/(*a.slotIn));
+    L.w = reinterpret_cast<char*>(a.cnew + idx0);
+    const int t = ty*BX + tx;
+    const int tx0 = a.region.origin[0]+blockIdx.x*BX, ty0 = a.region.origin[1]+by*BY;
+    const int nxv = min(BX, a.region.size[0]-(int)blockIdx.x*BX), nyv = min(BY, a.region.size[1]-by*BY);
+    const unsigned ring0 = ((unsigned)__cvta_generic_to_shared(ring) + 127u) & ~127u;
+    const unsigned bar0 = ring0 + R*SLOTB;
+    // fast path: the box holds the tile rows and the y neighbour row of the inflow side; otherwise both neighbour rows
+    const bool full = pat >= 8, lowRow = full || (pat & 2);
+    const int rowO = min(ty, nyv-1) + (lowRow ? 1 : 0), ctx = min(tx, nxv-1);
+    const int bx0 = (tx0-of.origin[0]-1) & ~1;           // even column at or below the tile's left neighbour (-2 at the array's edge)
+    L.aOwn = ring0 + unsigned(rowO*PXT + (tx0-of.origin[0]-bx0) + ctx)*8u;
+    L.aX = L.aOwn; L.aY = L.aOwn;
+    if (pat < 8) {
+      const int mx = dx ? 0 : 1, my = dy ? 2 : 3;
+      int ox = dx ? -8 : 8, oy = dy ? -PXT*8 : PXT*8;
+      if (!(flags >> (4+mx) & 1u) && !(flags >> mx & 1u)) { ox = 0; L.tbx = (flags >> (8+mx) & 1u) ? bval*(dx ? f0 : f1) : 0.0; if (dx) L.f0 = 0.0; else L.f1 = 0.0; }
+      if (!(flags >> (4+my) & 1u) && !(flags >> my & 1u)) { oy = 0; L.tby = (flags >> (8+my) & 1u) ? bval*(dy ? f2 : f3) : 0.0; if (dy) L.f2 = 0.0; else L.f3 = 0.0; }
+      if (flags >> mx & 1u) ox = 0;
+      if (flags >> my & 1u) oy = 0;
+      L.aX = unsigned(int(L.aOwn) + ox); L.aY = unsigned(int(L.aOwn) + oy);
+    }
+    L.issuer = t < 32;                                     // warp 0; one elected lane issues
+    const void* map = full ? static_cast<const void*>(tmaps.full) : static_cast<const void*>(tmaps.inflow);
+    const unsigned bytes = PXT*(full ? BY+2 : BY+1)*8u;
+    const int by0 = ty0-of.origin[1]-(lowRow ? 1 : 0), bz0 = cz0-of.origin[2];
+    if (t == 0) {
+#pragma unroll
+      for (int s = 0; s < R; ++s) mbar_init(bar0 + 8u*s, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+#pragma unroll
+      for (int j = 0; j <= D; ++j)
+        if (j <= kload) tma_stage_plane(ring0 + j*SLOTB, map, bx0, by0, bz0+j, bar0 + 8u*j, bytes);
+    }
+    __syncthreads();                                       // the barriers exist before anybody waits on them
+    L.c_below = (cz0 > ovz0) ? __ldg(a.c + idx0 - sz) : zlow;
+    switch (pat) {
+      case 0: fv_tma_loop<D, BX, BY, 0, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, map, bar0, ring0, bx0, by0, bz0, bytes); break;
+      case 1: fv_tma_loop<D, BX, BY, 1, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, map, bar0, ring0, bx0, by0, bz0, bytes); break;
+      case 2: fv_tma_loop<D, BX, BY, 2, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, map, bar0, ring0, bx0, by0, bz0, bytes); break;
+      case 3: fv_tma_loop<D, BX, BY, 3, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, map, bar0, ring0, bx0, by0, bz0, bytes); break;
+      case 4: fv_tma_loop<D, BX, BY, 4, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, map, bar0, ring0, bx0, by0, bz0, bytes); break;
+      case 5: fv_tma_loop<D, BX, BY, 5, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, map, bar0, ring0, bx0, by0, bz0, bytes); break;
+      case 6: fv_tma_loop<D, BX, BY, 6, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, map, bar0, ring0, bx0, by0, bz0, bytes); break;
+      case 7: fv_tma_loop<D, BX, BY, 7, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, map, bar0, ring0, bx0, by0, bz0, bytes); break;
+      default: fv_tma_loop<D, BX, BY, 8, ZPARAM>(L, S, sz, rwz, zt, zbase, zn, kload, map, bar0, ring0, bx0, by0, bz0, bytes); break;
+    }
+    if (active && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = L.dt;
   } else {
   FvRingLane L; FvRingSlow S;
   L.active = active;
@@ -1194,7 +1378,8 @@ struct dgb_fv {
   int level = 0, mode = 0;
   int zchunk = 0;                // planes marched by one CTA of the 3-D kernel; 0 = auto (DGB_FV_ZCHUNK overrides)
   int variant = -1;              // tuning variant of the 3-D kernel; -1 = automatic (DGB_FV_VARIANT overrides)
-  int staging = 3;               // staging of the ring kernel: 3 automatic (default), 2 phase-aware pairs, 1 aligned pairs, 0 8 bytes per cell (DGB_FV_STAGING=auto|pair|a16|8)
+  int staging = 3;               // staging of the ring kernel: 3 automatic (default), 4 tensor map (TMA) where possible, 2 phase-aware pairs, 1 aligned pairs, 0 8 bytes per cell (DGB_FV_STAGING=auto|tma|pair|a16|8)
+  std::vector<std::pair<const double*, dgb::FvTmaMaps>> tmaCache;   // tensor maps of the arrays the time loop alternates between
   std::unique_ptr<dgb::FvZTable> ztab;   // reciprocal z widths for the kernel parameter space (ring kernel)
   bool zparam = false;
   dgb_view view;
@@ -1259,6 +1444,41 @@ static auto ring_kernel(int pb) -> decltype(&k_fv_ring<0, D, BX, BY, MINB, ZP, S
   return pb == 1 ? &k_fv_ring<1, D, BX, BY, MINB, ZP, STG> : &k_fv_ring<0, D, BX, BY, MINB, ZP, STG>;
 }
 
+// ---- tensor maps of the TMA staging form (cuTensorMapEncodeTiled through the runtime's driver entry point: no link to libcuda) ----
+template<int STG> struct FvTmaArg { static FvNoTma get(const FvTmaMaps&) { return FvNoTma{}; } };
+template<> struct FvTmaArg<3> { static const FvTmaMaps& get(const FvTmaMaps& m) { return m; } };
+static constexpr size_t fv_tma_slot_bytes(int bx, int by) { return (size_t(bx+4)*(by+2)*8 + 127)/128*128; }
+typedef CUresult (*tmap_encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_t tmap_encoder() {
+  static tmap_encode_t fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<tmap_encode_t>(p);
+  }();
+  return fn;
+}
+// the stored box of `base` as a tensor of doubles (x fastest); boxes of (FBX+4) x (FBY+1) and (FBX+4) x (FBY+2) cells of one plane
+static int fv_tma_maps(dgb_fv* fv, const double* base, const dgb_box& of, FvTmaMaps& out) {
+  static_assert(sizeof(CUtensorMap) == 128, "FvTmaMaps holds two CUtensorMap objects");
+  for (auto& e : fv->tmaCache) if (e.first == base) { out = e.second; return DGB_OK; }
+  const cuuint64_t dims[3] = { cuuint64_t(of.size[0]), cuuint64_t(of.size[1]), cuuint64_t(of.size[2]) };
+  const cuuint64_t strides[2] = { dims[0]*8, dims[0]*dims[1]*8 };
+  const cuuint32_t estr[3] = { 1, 1, 1 };
+  for (int m = 0; m < 2; ++m) {
+    const cuuint32_t box[3] = { cuuint32_t(FBX+4), cuuint32_t(m ? FBY+2 : FBY+1), 1 };
+    CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(m ? out.full : out.inflow);
+    const CUresult r = tmap_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DGB_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")");
+  }
+  if (fv->tmaCache.size() >= 8) fv->tmaCache.erase(fv->tmaCache.begin());
+  fv->tmaCache.emplace_back(base, out);
+  return DGB_OK;
+}
+
 template<bool REDUCE_ONLY>
 static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
   const dgb_view& v = fv->view;
@@ -1277,8 +1497,13 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     // 0.360 phase-aware pairs vs 0.360 8-byte), phase-aware pairs win on the odd rank boxes of a partitioned grid (513^3: 0.382 vs 0.391)
     const bool a16ok = variant == 3 && fv->zparam && (reinterpret_cast<uintptr_t>(a.c) & 15u) == 0 && ofb.size[0] % 2 == 0
                        && (a.region.origin[0]-ofb.origin[0]) % 2 == 0 && a.region.size[0] % 2 == 0;
+    // tensor-map staging (kernel form 3): strides that are multiples of 16 bytes, no side cells (hybrid exchange)
+    const bool tmaok = variant == 3 && fv->zparam && (reinterpret_cast<uintptr_t>(a.c) & 15u) == 0 && ofb.size[0] % 2 == 0
+                       && !fv->wantPair && !a.xh[0] && !a.xh[1] && tmap_encoder() != nullptr;
     int stg = fv->staging;
+    if (stg == 4) stg = tmaok ? 33 : 3;                 // DGB_FV_STAGING=tma where possible
     if (stg == 3) stg = a16ok ? 1 : 2;                  // automatic
+    if (stg == 33) stg = 3;
     if (fv->wantPair) stg = 2;
     if (stg == 1 && !a16ok) stg = 0;
     if (stg == 0 && !(variant == 0 || variant == 3)) stg = 2;
@@ -1296,7 +1521,8 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     if (!REDUCE_ONLY) {
       int bx = 128, by = 4;                                                   // the z-march kernels
       if (ring) switch (variant) { case 2: bx = 64; by = 4; break; case 3: case 7: bx = 128; by = 4; break; case 9: bx = 64; by = 8; break; default: bx = 32; by = 8; }
-      const int info[8] = { ring ? DGB_FV_KERNEL_RING : DGB_FV_KERNEL_MARCH, ring ? variant : 99, bx, by, ring ? (stg ? 16 : 8) : 0, zc, a.pack ? 1 : 0, ring ? stg : 0 };
+      const int info[8] = { ring ? DGB_FV_KERNEL_RING : DGB_FV_KERNEL_MARCH, ring ? variant : 99, bx, by,
+                            ring ? (stg == 3 ? (bx+4)*(by+1)*8 : stg ? 16 : 8) : 0, zc, a.pack ? 1 : 0, ring ? stg : 0 };
       for (int k = 0; k < 8; ++k) fv->kinfo[k] = info[k];
     }
 #define DGB_MARCH(MODE_, PROB_, PF_, BX_, BY_)                                                                       \
@@ -1309,15 +1535,19 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     if (exact) DGB_MARCH_ANY(DGB_FV_EXACT)
     else if (!ring) DGB_MARCH_ANY(DGB_FV_SEPARABLE)
     else {
+      FvTmaMaps tmaps{};
+      if (stg == 3) { if (int rc = fv_tma_maps(fv, a.c, ofb, tmaps)) return rc; }
 #define DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, ZP_, STG_)                                                              \
     { auto kf = ring_kernel<D_, BX_, BY_, MINB_, ZP_, STG_>(pb);                                                     \
       DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));                    \
-      kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc); }
+      kf<<<mgrid, mblock, smem, stream>>>(v, a, *fv->ztab, zc, FvTmaArg<STG_>::get(tmaps)); }
 #define DGB_RING(D_, BX_, BY_, MINB_, WITH8_, WITHA16_)                                                             \
     { dim3 mblock(BX_, BY_, 1);                                                                                      \
       dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
-      const size_t smem = size_t(D_+2)*((BX_+(stg ? 4 : 2))*(BY_+2) + (stg == 2 ? 2*(BY_+2) : 0))*sizeof(double);  \
-      if (WITHA16_ && stg == 1) DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, true, (WITHA16_ ? 1 : 2))                       \
+      const size_t smem = stg == 3 ? size_t(D_+2)*(fv_tma_slot_bytes(BX_, BY_) + 8) + 128                          \
+                          : size_t(D_+2)*((BX_+(stg ? 4 : 2))*(BY_+2) + (stg == 2 ? 2*(BY_+2) : 0))*sizeof(double);  \
+      if (WITHA16_ && stg == 3) DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, true, (WITHA16_ ? 3 : 2))                       \
+      else if (WITHA16_ && stg == 1) DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, true, (WITHA16_ ? 1 : 2))                  \
       else if (WITH8_ && stg == 0) { if (fv->zparam) DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, true, (WITH8_ ? 0 : 2))    \
                                      else DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, false, (WITH8_ ? 0 : 2)) }            \
       else if (fv->zparam) DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, true, 2)                                             \
@@ -1436,7 +1666,7 @@ int dgb_fv_create(dgb_grid* g, int level, int problem, const double* params_host
     fv->grid = g; fv->comm = comm; fv->level = level; fv->mode = mode;
     if (const char* e = getenv("DGB_FV_ZCHUNK")) { int z = atoi(e); if (z > 0) fv->zchunk = z; }
     if (const char* e = getenv("DGB_FV_VARIANT")) fv->variant = atoi(e);
-    if (const char* e = getenv("DGB_FV_STAGING")) fv->staging = !strcmp(e, "8") ? 0 : !strcmp(e, "a16") ? 1 : !strcmp(e, "pair") ? 2 : 3;
+    if (const char* e = getenv("DGB_FV_STAGING")) fv->staging = !strcmp(e, "8") ? 0 : !strcmp(e, "a16") ? 1 : !strcmp(e, "pair") ? 2 : !strcmp(e, "tma") ? 4 : 3;
     if (int rc = make_view(g, level, &fv->view)) return rc;
     if (g->me.nranks > 1 && !comm) throw ArgError("a dgb_comm is required on a multi-rank grid");
     const uint32_t block[4] = {1,0,0,0};

@@ -745,11 +745,13 @@ class FiniteVolume:
             pass
 
     def kernel_info(self):
-        """which kernel the last step ran: dict(kind='ring'|'ring_bulk'|'march'|'step2d', variant, tile, staging_bytes, zchunk, packs)"""
+        """which kernel the last step ran: dict(kind='ring'|'ring_bulk'|'march'|'step2d', variant, tile, staging_bytes, zchunk, packs,
+        staging='8'|'a16'|'pair'|'tma')"""
         a = (C.c_int32 * 8)()
         check(lib.dgb_fv_kernel_info(self.h, a))
         return {"kind": ("none", "step2d", "march", "ring", "ring_bulk")[a[0]], "variant": a[1], "tile": (a[2], a[3]),
-                "staging_bytes": a[4], "zchunk": a[5], "packs": bool(a[6])}
+                "staging_bytes": a[4], "zchunk": a[5], "packs": bool(a[6]),
+                "staging": ("8", "a16", "pair", "tma")[a[7]] if a[0] >= 3 else "none"}
 
     def initial(self):
         torch = _torch()

@@ -359,8 +359,9 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
 int dgb_fv_host_path(const dgb_fv* fv, int* path);
 int dgb_fv_launch_count(const dgb_fv* fv, int64_t* kernels);           /* kernels launched by this object so far */
 /* which kernel the last step launched for the (bulk of the) interior cells: info8 = { kind, tuning variant, tile width, tile
- * height, bytes per staging copy (16 = paired cp.async, 8 = per cell, 0 = not a ring kernel), z planes per CTA, 1 if the
- * launch packed the send boxes into the peers' memory (fused exchange), 0 } */
+ * height, bytes per staging copy (16 = paired cp.async, 8 = per cell, 5280 = one TMA box per plane tile, 0 = not a ring kernel),
+ * z planes per CTA, 1 if the launch packed the send boxes into the peers' memory (fused exchange), staging form of the ring
+ * kernel (0 8-byte cp.async, 1 aligned 16-byte pairs, 2 phase-aware 16-byte pairs, 3 tensor map / TMA) } */
 enum { DGB_FV_KERNEL_NONE = 0, DGB_FV_KERNEL_STEP2D = 1, DGB_FV_KERNEL_MARCH = 2, DGB_FV_KERNEL_RING = 3, DGB_FV_KERNEL_RING_BULK = 4 };
 int dgb_fv_kernel_info(const dgb_fv* fv, int32_t* info8);
 /* how the last dgb_fv_step refreshed the overlap cells: */

@@ -481,7 +481,9 @@ def test_fv_ring_kernels_equal_general_kernel_bitwise(problem, params, monkeypat
     cfgs = (make_cfg(dim=3, N=(150, 37, 70), mode=2),                                        # even rows, odd offsets nowhere
             make_cfg(dim=3, N=(70, 45, 33), periodic=3, upper=(1.0, 0.7, 1.3)),              # 72 x 47: even row, odd plane stride... (72*47 even)
             make_cfg(dim=3, N=(131, 21, 19), periodic=7, upper=(1.0, 0.2, 0.2)),             # 133 x 23 x 21: odd rows, odd planes, interior at offset 1
-            make_cfg(dim=3, N=(259, 10, 18), periodic=1, upper=(1.0, 0.05, 0.1)))            # 261 wide: the 128x4 tile with a partial last tile
+            make_cfg(dim=3, N=(259, 10, 18), periodic=1, upper=(1.0, 0.05, 0.1)),            # 261 wide: the 128x4 tile with a partial last tile
+            make_cfg(dim=3, N=(258, 11, 21), periodic=5, upper=(1.0, 0.05, 0.1)),            # 260 x 11 x 23: even rows, three tiles, interior at offset 1 (tensor-map staging)
+            make_cfg(dim=3, N=(384, 9, 150), upper=(1.0, 0.03, 0.4)))                        # long columns: the ring wraps many times
     for ci, cfg in enumerate(cfgs):
         g = product_grid(cfg, 0, 1)
         n = g.leafGridView().size(0)
@@ -491,12 +493,12 @@ def test_fv_ring_kernels_equal_general_kernel_bitwise(problem, params, monkeypat
             c0 = torch.from_numpy(np.random.default_rng(3).uniform(0.0, 1.0, n)).cuda()
             res = {}
             for variant, staging in (("99", "pair"), ("0", "pair"), ("3", "pair"), ("0", "8"), ("3", "8"), ("3", "a16"), ("7", "pair"),
-                                     ("2", "pair"), ("9", "pair")):
-                if misalign and (variant, staging) not in (("99", "pair"), ("0", "pair"), ("3", "pair"), ("3", "a16")):
+                                     ("2", "pair"), ("9", "pair"), ("3", "tma"), ("3", "tma:64")):
+                if misalign and (variant, staging) not in (("99", "pair"), ("0", "pair"), ("3", "pair"), ("3", "a16"), ("3", "tma")):
                     continue
                 monkeypatch.setenv("DGB_FV_VARIANT", variant)
-                monkeypatch.setenv("DGB_FV_STAGING", staging)
-                monkeypatch.setenv("DGB_FV_ZCHUNK", "16")
+                monkeypatch.setenv("DGB_FV_STAGING", staging.split(":")[0])
+                monkeypatch.setenv("DGB_FV_ZCHUNK", staging.split(":")[1] if ":" in staging else "16")
                 monkeypatch.setenv("DGB_FV_FUSED", "0")         # the serial exchange: the step kernel alone is compared here
                 monkeypatch.setenv("DGB_FV_NO_SPLIT", "1")
                 fv = dg.FiniteVolume(g, 0, problem, params, "separable")
@@ -512,6 +514,9 @@ def test_fv_ring_kernels_equal_general_kernel_bitwise(problem, params, monkeypat
                         assert info["staging_bytes"] == 16
                     if staging == "8":
                         assert info["staging_bytes"] == 8
+                    if staging.startswith("tma"):      # tensor-map staging needs 16-byte strides and an aligned field; else the automatic choice
+                        box = g.leafGridView().boxes(0)[0]["overlapfront"][1]
+                        assert info["staging"] == ("tma" if box[0] % 2 == 0 and not misalign else "pair"), (info, box)
                 res[(variant, staging)] = (c.clone(), fv.last_dt())
             for key, val in res.items():
                 assert val[1] == res[("99", "pair")][1]

@@ -66,14 +66,23 @@ def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     quick = len(sys.argv) > 2 and sys.argv[2] == "quick"
     g1 = dg.YaspGrid(dim=3, N=(512, 512, 512), upper=(1.0, 1.0, 1.0), overlap=1)
-    for st in ("pair", "a16", "8"):
+    for st in ("pair", "a16", "8", "tma", "a16", "tma"):
         run("512^3 single rank (config 2)", g1, st, reps, False)
     del g1
+    if len(sys.argv) > 2 and sys.argv[2] == "tma":              # the boxes tensor-map staging applies to: 512^3 and the even rank boxes of P = 4
+        for r in (0, 1):
+            g = dg.YaspGrid(dim=3, N=(1024, 1024, 1024), upper=(1.0, 1.0, 1.0), overlap=1, rank=r, nranks=4)
+            g.comm = _FakeComm()
+            for st in ("pair", "tma"):
+                run(f"1024^3 rank {r} of 4 {g.torusDims()} (config 3), kernel only", g, st, max(10, reps // 2), True)
+            del g
+            torch.cuda.empty_cache()
+        return
     for P, ranks in (((8, (7,)), (2, (1,)), (4, (1,))) if quick else ((8, (0, 7)), (2, (0, 1)), (4, (0, 1)))):
         for r in ranks:
             g = dg.YaspGrid(dim=3, N=(1024, 1024, 1024), upper=(1.0, 1.0, 1.0), overlap=1, rank=r, nranks=P)
             g.comm = _FakeComm()
-            for st in ("pair", "8"):
+            for st in (("pair", "8", "tma") if P == 4 else ("pair", "8")):
                 run(f"1024^3 rank {r} of {P} {g.torusDims()} (config 3), kernel only", g, st, max(10, reps // (8 // P)), True)
             del g
             torch.cuda.empty_cache()
