@@ -163,7 +163,7 @@ __device__ __forceinline__ void fv_fused_pack(const FvArgs& a, const dgb_box& of
 // Tile row of a CTA of the 3-D step kernels. With the fused exchange the LAST tile row is scheduled first: a y-face is
 // BX x 1 x ZC cells of one CTA, the heaviest pack, and must not sit in the kernel's tail.
 __device__ __forceinline__ int fv_tile_row(const FvArgs& a) {
-  if (!a.pack) return int(blockIdx.y);
+  if (!a.pack || (a.debugSkipFaces & 0x200u)) return int(blockIdx.y);
   return blockIdx.y == 0 ? int(gridDim.y)-1 : int(blockIdx.y)-1;
 }
 // Called by ONE thread per CTA after a __syncthreads that follows fv_fused_pack and the CTA's CFL atomic: the last CTA of
@@ -174,9 +174,12 @@ __device__ __forceinline__ void fv_fused_signal(const FvArgs& a, const FusedItem
   // peer memory needs no system-scope fence (it would only wait for its own streaming stores to drain: measured ~14 us per step)
   bool stored = false;
   for (int b = 0; b < a.send.n; ++b) stored = stored || items[b].n > 0;
-  if (stored) __threadfence_system(); else __threadfence();
+  if (stored) __threadfence_system(); else if (!(a.debugSkipFaces & 0x100u)) __threadfence();
   if (!a.packSignal) return;                         // an earlier slab launch of the step: the last launch signals for all
   const unsigned total = gridDim.x*gridDim.y*gridDim.z;
+  // (tried in round 2: counting with a reduction that returns nothing + one publishing CTA that waits for the count, so that no CTA
+  // idles for the round trip of the returning atomic - no measurable difference on the periodic proxy, 0.4216 vs 0.4248 ms within
+  // the box-to-box spread; the simpler form stays)
   if (atomicAdd(P.counter, 1u) == total-1) {
     atomicExch(P.counter, 0u);
     __threadfence();
@@ -1062,9 +1065,10 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   fv_peer_wait_finish(a, rankBoundary, ty*BX + tx, peerFlag);
   // fused exchange: which send boxes this CTA's tile x chunk meets (read at the very end; the barriers below publish it)
   __shared__ FusedItem s_items[FUSED_MAX_BOXES];
-  if (a.pack)
+  if (a.pack && !(a.debugSkipFaces & 0x400u))
     fv_fused_prepare(a, of, s_items, a.region.origin[0]+blockIdx.x*BX, min(BX, a.region.size[0]-(int)blockIdx.x*BX),
                      a.region.origin[1]+by*BY, min(BY, a.region.size[1]-by*BY), cz0, zn, ty*BX + tx);
+  else if (a.pack && ty*BX + tx < FUSED_MAX_BOXES) s_items[ty*BX + tx].n = 0;
   // one code path per CTA (the loop contains barriers): fast only if every thread agrees on the directions
   __shared__ int s_pat[2];
   if (tx == 0 && ty == 0) { s_pat[0] = dx*4 + dy*2 + dz; s_pat[1] = 1; }
@@ -1323,7 +1327,7 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
   if (active && a.dtOut && i0 == 0 && i1 == 0 && z0 == 0) *a.dtOut = L.dt;
   }
   const int tid = ty*BX + tx;
-  if (a.pack) fv_fused_pack<BX*BY>(a, of, s_items, tid);
+  if (a.pack && !(a.debugSkipFaces & 0x400u)) fv_fused_pack<BX*BY>(a, of, s_items, tid);
   for (int o = 16; o > 0; o >>= 1) sum_max = fmax(sum_max, __shfl_down_sync(0xffffffffu, sum_max, o));
   __shared__ double part[BX*BY/32];
   if ((tid & 31) == 0) part[tid >> 5] = sum_max;
@@ -1855,6 +1859,8 @@ int dgb_fv_step(dgb_fv* fv, const double* d_c_in, double* d_c_out, void* stream_
     if (slot < 0) fill_send_boxes(a, *fv->plan, fs.hostDst[parity], nullptr, nullptr);
     else if (hybrid) fill_send_boxes(a, *fv->plan, fs.direct[slot].hDstH[parity], &fs.direct[slot].hRowH, &fs.direct[slot].hPlaneH);
     else fill_send_boxes(a, *fv->plan, fs.direct[slot].hDst, &fs.direct[slot].hRow, &fs.direct[slot].hPlane);
+    static const bool debugNoWait = [] { const char* e = getenv("DGB_FV_DEBUG_NOWAIT"); return e && atoi(e) != 0; }();   // developer knob (timing only)
+    if (fv->waitPending && debugNoWait) fv->waitPending = false;
     if (fv->waitPending) {                               // the previous registered step left its flag wait to this kernel's boundary CTAs
       a.waitCtl = fs.ctl; a.waitEpoch = fv->waitEpoch; a.waitParity = fv->waitParity; a.waitRanks = fv->view.nranks;
       a.waitSlot = fv->dSlots + fv->waitSlot; a.waitTimeout = fs.dTimeout;
