@@ -264,7 +264,7 @@ def parity_check(dg, torch, dist, rank, world, comm, dims, mode):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return {"grid": list(N), "partition": list(dims), "steps": steps, "max_rel": t[0].item(), "dt_rel": t[1].item(), "tol": tol,
             "ok": t[2].item() == 0.0, "oracle": "reference" if kind == "ref" else "port", "exchange": xmode,
-            "kernel": f"{info['kind']} {info['tile'][0]}x{info['tile'][1]} staging {info['staging_bytes']} B"}
+            "kernel": f"{info['kind']} {info['tile'][0]}x{info['tile'][1]} staging {info['staging']} ({info['staging_bytes']} B)"}
 
 
 def run_gpu(args):
@@ -417,7 +417,7 @@ def run_gpu(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
                 "fv_mode": args.mode, "partition": list(g.torusDims()),
-                "kernel": {"kind": kinfo["kind"], "tile": list(kinfo["tile"]), "staging_bytes": kinfo["staging_bytes"],
+                "kernel": {"kind": kinfo["kind"], "tile": list(kinfo["tile"]), "staging": kinfo["staging"], "staging_bytes": kinfo["staging_bytes"],
                            "zchunk": kinfo["zchunk"], "exchange": xmode, "registered_fields": bool(world > 1 and not args.no_register)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic[0] if traffic else None,

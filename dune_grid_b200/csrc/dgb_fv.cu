@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <cmath>
 #include <cuda.h>
 #include "dgb_internal.hh"
 #include "dgb_device.cuh"
@@ -960,6 +961,15 @@ __device__ __forceinline__ void fv_tma_loop(FvTmaLane L, const FvRingSlow S, con
       DGB_TMA_FIXED(k, 4) DGB_TMA_FIXED(k, 5) DGB_TMA_FIXED(k, 6) DGB_TMA_FIXED(k, 7)
       par ^= 1u;
     }
+  } else if constexpr (R == 16) {
+#pragma unroll 1
+    for (; k+R <= kmain; k += R) {
+      DGB_TMA_FIXED(k, 0) DGB_TMA_FIXED(k, 1) DGB_TMA_FIXED(k, 2) DGB_TMA_FIXED(k, 3)
+      DGB_TMA_FIXED(k, 4) DGB_TMA_FIXED(k, 5) DGB_TMA_FIXED(k, 6) DGB_TMA_FIXED(k, 7)
+      DGB_TMA_FIXED(k, 8) DGB_TMA_FIXED(k, 9) DGB_TMA_FIXED(k, 10) DGB_TMA_FIXED(k, 11)
+      DGB_TMA_FIXED(k, 12) DGB_TMA_FIXED(k, 13) DGB_TMA_FIXED(k, 14) DGB_TMA_FIXED(k, 15)
+      par ^= 1u;
+    }
   }
   unsigned uPrev = unsigned((k+R-1) & (R-1))*SLOTB, uCur = unsigned(k & (R-1))*SLOTB, uNxt = unsigned((k+1) & (R-1))*SLOTB;
 #define DGB_TMA_ROTATE uPrev = uCur; uCur = uNxt; uNxt = (uNxt == LASTB) ? 0u : uNxt + SLOTB;
@@ -984,8 +994,8 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
                                                          const __grid_constant__ typename FvTmaParam<STG>::type tmaps) {
   constexpr bool A16 = STG == 1;
   constexpr int PX = STG ? BX+4 : BX+2, PY = BY+2, SLOT = PX*PY, XO = STG ? 2 : 1;      // XO: column of the tile's first cell
-  static_assert(2*BX + 2*BY <= BX*BY, "one halo cell per thread");
-  static_assert(PY*(PX/2) <= BX*BY, "one pair per thread");
+  static_assert(STG == 3 || 2*BX + 2*BY <= BX*BY, "one halo cell per thread");
+  static_assert(STG == 3 || PY*(PX/2) <= BX*BY, "one pair per thread");
   extern __shared__ __align__(16) double ring[];       // [R][PY][PX]
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i0 = blockIdx.x*BX + tx;
@@ -1383,6 +1393,7 @@ struct dgb_fv {
   int zchunk = 0;                // planes marched by one CTA of the 3-D kernel; 0 = auto (DGB_FV_ZCHUNK overrides)
   int variant = -1;              // tuning variant of the 3-D kernel; -1 = automatic (DGB_FV_VARIANT overrides)
   int staging = 3;               // staging of the ring kernel: 3 automatic (default), 4 tensor map (TMA) where possible, 2 phase-aware pairs, 1 aligned pairs, 0 8 bytes per cell (DGB_FV_STAGING=auto|tma|pair|a16|8)
+  int tmaTile[2] = {0, 0};       // tile shape the cached tensor maps were built for
   std::vector<std::pair<const double*, dgb::FvTmaMaps>> tmaCache;   // tensor maps of the arrays the time loop alternates between
   std::unique_ptr<dgb::FvZTable> ztab;   // reciprocal z widths for the kernel parameter space (ring kernel)
   bool zparam = false;
@@ -1441,6 +1452,20 @@ static int auto_zchunk(const int* size, int bx, int by, bool packs) {
   return zc;
 }
 
+// planes per CTA of the tensor-map form (14 planes in flight). Measured on 512^3 (512 tiles, 296 resident CTAs): chunks of equal
+// length leave a ragged last wave (2 x 256: 0.357 ms, 4 x 128: 0.348, 3 x 171: 0.352); a short last chunk - dispatched last - fills it
+// (3 x 160 + 32: 0.342, 2 x 224 + 64: 0.344, 3 x 144 + 80: 0.345). m full chunks of ~170 planes and a remainder of a fifth of a chunk.
+static int tma_zchunk(const int* size, int bx, int by) {
+  const long long tiles = (long long)((size[0]+bx-1)/bx)*((size[1]+by-1)/by);
+  const int resident = 148*1024/(bx*by);
+  const int nz = size[2];
+  const int m = std::max(1, (nz + 85)/170);
+  int zc = (int(std::ceil(nz/(m + 0.2))) + 7)/8*8;
+  zc = std::max(16, std::min(zc, nz));
+  while (zc > 16 && tiles*((nz+zc-1)/zc) < 2*resident) zc /= 2;
+  return zc;
+}
+
 // the ring kernel of a registered problem; problems whose velocity depends on z exist in the phase-aware pair form only
 template<int D, int BX, int BY, int MINB, bool ZP, int STG>
 static auto ring_kernel(int pb) -> decltype(&k_fv_ring<0, D, BX, BY, MINB, ZP, STG>) {
@@ -1463,15 +1488,16 @@ static tmap_encode_t tmap_encoder() {
   }();
   return fn;
 }
-// the stored box of `base` as a tensor of doubles (x fastest); boxes of (FBX+4) x (FBY+1) and (FBX+4) x (FBY+2) cells of one plane
-static int fv_tma_maps(dgb_fv* fv, const double* base, const dgb_box& of, FvTmaMaps& out) {
+// the stored box of `base` as a tensor of doubles (x fastest); boxes of (bx+4) x (by+1) and (bx+4) x (by+2) cells of one plane
+static int fv_tma_maps(dgb_fv* fv, const double* base, const dgb_box& of, int bx, int by, FvTmaMaps& out) {
   static_assert(sizeof(CUtensorMap) == 128, "FvTmaMaps holds two CUtensorMap objects");
+  if (fv->tmaTile[0] != bx || fv->tmaTile[1] != by) { fv->tmaCache.clear(); fv->tmaTile[0] = bx; fv->tmaTile[1] = by; }
   for (auto& e : fv->tmaCache) if (e.first == base) { out = e.second; return DGB_OK; }
   const cuuint64_t dims[3] = { cuuint64_t(of.size[0]), cuuint64_t(of.size[1]), cuuint64_t(of.size[2]) };
   const cuuint64_t strides[2] = { dims[0]*8, dims[0]*dims[1]*8 };
   const cuuint32_t estr[3] = { 1, 1, 1 };
   for (int m = 0; m < 2; ++m) {
-    const cuuint32_t box[3] = { cuuint32_t(FBX+4), cuuint32_t(m ? FBY+2 : FBY+1), 1 };
+    const cuuint32_t box[3] = { cuuint32_t(bx+4), cuuint32_t(m ? by+2 : by+1), 1 };
     CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(m ? out.full : out.inflow);
     const CUresult r = tmap_encoder()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1504,14 +1530,22 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     // tensor-map staging (kernel form 3): strides that are multiples of 16 bytes, no side cells (hybrid exchange)
     const bool tmaok = variant == 3 && fv->zparam && (reinterpret_cast<uintptr_t>(a.c) & 15u) == 0 && ofb.size[0] % 2 == 0
                        && !fv->wantPair && !a.xh[0] && !a.xh[1] && tmap_encoder() != nullptr;
+    // measured on the 512^3 box (profiles/r02_fv_tma_probe.md): tensor-map staging with 14 planes in flight and chunks of 160 planes
+    // 0.342 ms, aligned pairs 0.352 ms; the automatic choice takes it for launches without exchange (with side cells - hybrid
+    // exchange - the form is not eligible, and the launches that pack keep the forms their chunk rule was measured with)
     int stg = fv->staging;
     if (stg == 4) stg = tmaok ? 33 : 3;                 // DGB_FV_STAGING=tma where possible
-    if (stg == 3) stg = a16ok ? 1 : 2;                  // automatic
+    // (not for thin z-slabs - the pipelined host path launches 16-plane slabs, where a ring of 16 slots never turns over: its
+    // end-to-end rate fell from 5.70 to 5.5 Gcell/s with the tensor-map form)
+    if (stg == 3) stg = (tmaok && !a.pack && a.region.size[2] >= 64) ? 33 : a16ok ? 1 : 2;      // automatic
     if (stg == 33) stg = 3;
     if (fv->wantPair) stg = 2;
     if (stg == 1 && !a16ok) stg = 0;
     if (stg == 0 && !(variant == 0 || variant == 3)) stg = 2;
-    const int zc = fv->zchunk > 0 ? fv->zchunk : auto_zchunk(a.region.size, wide ? 128 : 32, wide ? 4 : 8, a.pack != nullptr);
+    static const int tmaShape = [] { const char* e = getenv("DGB_FV_TMA_SHAPE"); return e ? atoi(e) : 1; }();
+    const int zc = fv->zchunk > 0 ? fv->zchunk
+                   : (stg == 3 && !a.pack && tmaShape == 1) ? tma_zchunk(a.region.size, 128, 4)
+                   : auto_zchunk(a.region.size, wide ? 128 : 32, wide ? 4 : 8, a.pack != nullptr);
     const bool exact = fv->mode == DGB_FV_EXACT;
     const int pb = fv->problem.id;
     // the ring kernel evaluates the x/y face factors once per COLUMN: only for problems that declare a z-independent velocity and a
@@ -1540,7 +1574,9 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     else if (!ring) DGB_MARCH_ANY(DGB_FV_SEPARABLE)
     else {
       FvTmaMaps tmaps{};
-      if (stg == 3) { if (int rc = fv_tma_maps(fv, a.c, ofb, tmaps)) return rc; }
+      // shapes of the tensor-map form (DGB_FV_TMA_SHAPE): 1 = 128x4 tile, 14 planes in flight (default); 0 = 6 planes in flight
+      // (a 256x2 tile would need a 260-cell box row: cuTensorMapEncodeTiled refuses box dimensions above 256)
+      if (stg == 3) { if (int rc = fv_tma_maps(fv, a.c, ofb, 128, 4, tmaps)) return rc; }
 #define DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, ZP_, STG_)                                                              \
     { auto kf = ring_kernel<D_, BX_, BY_, MINB_, ZP_, STG_>(pb);                                                     \
       DGB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));                    \
@@ -1556,6 +1592,13 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
                                      else DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, false, (WITH8_ ? 0 : 2)) }            \
       else if (fv->zparam) DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, true, 2)                                             \
       else DGB_RING_LAUNCH(D_, BX_, BY_, MINB_, false, 2) }
+#define DGB_RING_TMA(D_, BX_, BY_)                                                                                  \
+    { dim3 mblock(BX_, BY_, 1);                                                                                      \
+      dim3 mgrid((a.region.size[0]+BX_-1)/BX_, (a.region.size[1]+BY_-1)/BY_, (a.region.size[2]+zc-1)/zc);          \
+      const size_t smem = size_t(D_+2)*(fv_tma_slot_bytes(BX_, BY_) + 8) + 128;                                     \
+      DGB_RING_LAUNCH(D_, BX_, BY_, 2, true, 3) }
+      if (stg == 3 && tmaShape == 1) DGB_RING_TMA(14, 128, 4)
+      else
       switch (variant) {                      // tuning variants: ring depth, tile, occupancy target (tools/fv_sweep.py)
         default:
         case 0: DGB_RING(8, 32, 8, 4, true, false) break;                  // production choice, narrow regions
@@ -1564,6 +1607,7 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
         case 7: DGB_RING(8, 128, 4, 2, false, false) break;
         case 9: DGB_RING(8, 64, 8, 2, false, false) break;
       }
+#undef DGB_RING_TMA
 #undef DGB_RING
 #undef DGB_RING_LAUNCH
     }

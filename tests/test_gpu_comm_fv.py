@@ -388,7 +388,7 @@ def test_fv_production_kernel_against_oracle_at_baseline_size():
             c, cn = cn, c
         info = fv.kernel_info()
         if mode == "separable":       # the production selection, not a small-grid variant
-            assert info["kind"] == "ring" and info["tile"] == (128, 4) and info["staging_bytes"] == 16, info
+            assert info["kind"] == "ring" and info["tile"] == (128, 4) and info["staging"] == "tma", info
         else:
             assert info["kind"] == "march", info
         dt = fv.last_dt()
