@@ -1448,6 +1448,13 @@ static int auto_zchunk(const int* size, int bx, int by, bool packs) {
   // measured with the exchange (tools/fused_proxy.py): 513^3 rank box (512 tiles): 128 planes 0.423 ms, 256 planes 0.433; 510x1024x1024
   // (1024 tiles): 128 planes 1.634 ms, 256 planes 1.567 - long columns as soon as they still give >= 2048 CTAs (~7 waves)
   int zc = (bx >= 128 && (!packs || tiles*((size[2]+255)/256) >= 2048)) ? 256 : 128;
+  // round 2, session 3: chunks of equal length leave a ragged last wave; m chunks of ~224 planes and a SHORT last chunk (dispatched
+  // last) fill it. Periodic 513^3 proxy with the hybrid exchange: 4 x 128 planes 0.423 ms, 2 x 256 0.429, 224 + 224 + 63 0.411,
+  // 240 + 240 + 31 0.413, 208 + 208 + 95 0.417 (profiles/r02_fv_tma_probe.md)
+  if (packs && bx >= 128 && zc == 128 && size[2] >= 256) {
+    const int m = std::max(1, (size[2] + 112)/224);
+    zc = std::max(32, int(size[2]/(m + 0.28))/8*8);
+  }
   while (zc > 16 && tiles*((size[2]+zc-1)/zc) < 2*resident) zc /= 2;
   return zc;
 }
@@ -1606,6 +1613,7 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
         case 3: DGB_RING(6, 128, 4, 2, true, true) break;                  // production choice, wide regions
         case 7: DGB_RING(8, 128, 4, 2, false, false) break;
         case 9: DGB_RING(8, 64, 8, 2, false, false) break;
+        // (tried: the phase-aware pair form with 14 planes in flight, 128x4 - 0.454 ms kernel only on the 513^3 box against 0.384 with 6)
       }
 #undef DGB_RING_TMA
 #undef DGB_RING
