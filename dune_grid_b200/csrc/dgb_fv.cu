@@ -1245,7 +1245,9 @@ __global__ void __launch_bounds__(BX*BY, MINB) k_fv_ring(const __grid_constant__
 #pragma unroll
       for (int s = 0; s < R; ++s) mbar_init(bar0 + 8u*s, 1u);
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      // the barriers (shared memory) for the async proxy; and - registered fields - the halo cells peers stored into c through the
+      // generic proxy, acquired by fv_peer_wait_finish above, before the TMA engine (async proxy) reads them
+      asm volatile("fence.proxy.async;\n" ::: "memory");
 #pragma unroll
       for (int j = 0; j <= D; ++j)
         if (j <= kload) tma_stage_plane(ring0 + j*SLOTB, map, bx0, by0, bz0+j, bar0 + 8u*j, bytes);
@@ -1538,13 +1540,13 @@ static int launch_step(dgb_fv* fv, const FvArgs& a, cudaStream_t stream) {
     const bool tmaok = variant == 3 && fv->zparam && (reinterpret_cast<uintptr_t>(a.c) & 15u) == 0 && ofb.size[0] % 2 == 0
                        && !fv->wantPair && !a.xh[0] && !a.xh[1] && tmap_encoder() != nullptr;
     // measured on the 512^3 box (profiles/r02_fv_tma_probe.md): tensor-map staging with 14 planes in flight and chunks of 160 planes
-    // 0.342 ms, aligned pairs 0.352 ms; the automatic choice takes it for launches without exchange (with side cells - hybrid
-    // exchange - the form is not eligible, and the launches that pack keep the forms their chunk rule was measured with)
+    // 0.342 ms, aligned pairs 0.352 ms; periodic 512^3-stored box with the in-kernel pack 0.4626 against 0.4757 ms. The automatic
+    // choice takes it wherever it is eligible (not with side cells - hybrid exchange)
     int stg = fv->staging;
     if (stg == 4) stg = tmaok ? 33 : 3;                 // DGB_FV_STAGING=tma where possible
     // (not for thin z-slabs - the pipelined host path launches 16-plane slabs, where a ring of 16 slots never turns over: its
     // end-to-end rate fell from 5.70 to 5.5 Gcell/s with the tensor-map form)
-    if (stg == 3) stg = (tmaok && !a.pack && a.region.size[2] >= 64) ? 33 : a16ok ? 1 : 2;      // automatic
+    if (stg == 3) stg = (tmaok && a.region.size[2] >= 64) ? 33 : a16ok ? 1 : 2;      // automatic
     if (stg == 33) stg = 3;
     if (fv->wantPair) stg = 2;
     if (stg == 1 && !a16ok) stg = 0;

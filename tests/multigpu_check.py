@@ -32,9 +32,13 @@ def main():
         (make_cfg(dim=3, N=(36, 22, 26), periodic=7, overlap=2), 0, [0.6, -1.0, 0.8, 0.0, 0.5, 0.5, 0.5, 0.1, 0.45]),
         # wide and tall rank boxes: the 128x4 tile with odd row strides, and z extents that take the pipelined host path
         (make_cfg(dim=3, N=(520, 12, 300), upper=(1.0, 0.05, 0.6)), 0, [1.0, -0.05, 0.4, 0.2, 0.5, 0.02, 0.3, 0.01, 0.2]),
+        # split along z only: rank boxes with EVEN rows (16-byte strides) -> the tensor-map (TMA) staging form together with the
+        # in-kernel pack, peers storing straight into the registered arrays (no x faces: no side cells)
+        (make_cfg(dim=3, N=(256, 8, 130 * max(2, world)), upper=(1.0, 0.03, 0.5 * max(2, world))), 0, [0.3, -0.05, 1.0, 0.2, 0.5, 0.02, 0.3, 0.01, 0.2]),
     ]
     failures = 0
     modes = set()
+    stagings = set()
     host_paths = set()
     for cfg, problem, params in cases:
         w = oracle_world(o, cfg, world)
@@ -67,6 +71,7 @@ def main():
             else:
                 ok = ok and np.abs(got - ref[rank]).max() <= 1e-13 * scale           # tolerance: 1e-13 relative
             modes.add(fv.exchange_mode())
+            stagings.add(fv.kernel_info()["staging"])
             if not ok:
                 failures += 1
                 print(f"rank {rank}: FV mismatch cfg={cfg['N']} mode={mode} registered={registered} exchange={fv.exchange_mode()} "
@@ -128,7 +133,7 @@ def main():
     dist.all_reduce(t)
     if rank == 0:
         print(f"multigpu_check world={world}: {'OK' if t.item() == 0 else 'FAILED'} ({int(t.item())} mismatches), "
-              f"FV exchange modes on rank 0: {sorted(modes)}, host paths: {sorted(host_paths)}", flush=True)
+              f"FV exchange modes on rank 0: {sorted(modes)}, staging forms: {sorted(stagings)}, host paths: {sorted(host_paths)}", flush=True)
     dist.barrier()
     comm.close()
     dist.destroy_process_group()

@@ -433,11 +433,12 @@ def test_fv_wide_rank_boxes_with_odd_row_stride_against_oracle(mode):
     w.close()
 
 
-@pytest.mark.parametrize("N,periodic", [((511, 24, 40), 7), ((510, 21, 37), 5), ((255, 40, 33), 3)])
+@pytest.mark.parametrize("N,periodic", [((511, 24, 40), 7), ((510, 21, 37), 5), ((255, 40, 33), 3), ((510, 10, 70), 5), ((256, 9, 66), 7)])
 def test_fv_fused_exchange_on_wide_odd_boxes_against_oracle(N, periodic):
     """the fused step (in-kernel pack + peer stores + flags) on single-rank periodic grids whose stored boxes are 513 / 512
     / 257 cells wide with the interior starting at offset 1 - the shapes of the 2x2x2, 4x1x1 and 2x1x1 rank boxes of
-    config 3 - in production (separable) mode against the oracle within 1e-13, and in exact mode bit for bit"""
+    config 3 - and on 512- / 256-wide boxes of at least 64 planes (tensor-map staging together with the pack) in production
+    (separable) mode against the oracle within 1e-13, and in exact mode bit for bit"""
     import torch
     import dune_grid_b200 as dg
     cfg = make_cfg(dim=3, N=N, periodic=periodic, upper=(1.0, 0.1, 0.1))
@@ -461,6 +462,8 @@ def test_fv_fused_exchange_on_wide_odd_boxes_against_oracle(N, periodic):
         assert info["packs"]
         if mode == "separable" and N[0] >= 256:
             assert info["kind"] == "ring" and info["tile"] == (128, 4), info
+        if mode == "separable" and N[0] >= 256 and N[0] % 2 == 0 and N[2] >= 64:        # even rows, tall enough: tensor-map staging + pack
+            assert info["staging"] == "tma", info
         if mode == "exact":
             assert np.array_equal(np_(c), ref[0])
         else:
