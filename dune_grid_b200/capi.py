@@ -116,6 +116,7 @@ _SIG = {
     "dgb_fv_register_fields": (_i, [_vp, C.POINTER(_vp), _i, _vp]), "dgb_fv_registered_fields": (_i, [_vp, C.POINTER(_i)]),
     "dgb_fv_fence": (_i, [_vp, _vp]),
     "dgb_fv_kernel_info": (_i, [_vp, C.POINTER(C.c_int32)]), "dgb_fv_host_path": (_i, [_vp, C.POINTER(_i)]),
+    "dgb_fv_chunk_rule": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i)]),
     "dgb_fv_step": (_i, [_vp, _vp, _vp, _vp]), "dgb_fv_last_dt": (_i, [_vp, C.POINTER(C.c_double), _vp]),
     "dgb_fv_update": (_i, [_vp, _vp, _vp, _vp]),
     "dgb_fv_step_local": (_i, [_vp, _vp, _vp, C.POINTER(_vp), _vp]),

@@ -2212,6 +2212,12 @@ int dgb_fv_step_host(dgb_fv* fv, const double* h_c_in, double* h_c_out, double* 
 
 int dgb_fv_host_path(const dgb_fv* fv, int* path) { *path = fv->hostPath; return DGB_OK; }
 int dgb_fv_kernel_info(const dgb_fv* fv, int32_t* info8) { for (int k = 0; k < 8; ++k) info8[k] = fv->kinfo[k]; return DGB_OK; }
+int dgb_fv_chunk_rule(int nx, int ny, int nz, int packs, int tensor_map, int* zchunk) {
+  if (nx <= 0 || ny <= 0 || nz <= 0 || !zchunk) return fail(DGB_EARG, "dgb_fv_chunk_rule: positive extents and a result pointer");
+  const int size[3] = { nx, ny, nz };
+  *zchunk = (tensor_map && !packs) ? tma_zchunk(size, 128, 4) : auto_zchunk(size, 128, 4, packs != 0);
+  return DGB_OK;
+}
 int dgb_fv_launch_count(const dgb_fv* fv, int64_t* kernels) { *kernels = fv->launches; return DGB_OK; }
 int dgb_fv_exchange_mode(const dgb_fv* fv, int* mode) { *mode = fv->exchangeMode; return DGB_OK; }
 

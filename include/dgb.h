@@ -364,6 +364,10 @@ int dgb_fv_launch_count(const dgb_fv* fv, int64_t* kernels);           /* kernel
  * kernel (0 8-byte cp.async, 1 aligned 16-byte pairs, 2 phase-aware 16-byte pairs, 3 tensor map / TMA) } */
 enum { DGB_FV_KERNEL_NONE = 0, DGB_FV_KERNEL_STEP2D = 1, DGB_FV_KERNEL_MARCH = 2, DGB_FV_KERNEL_RING = 3, DGB_FV_KERNEL_RING_BULK = 4 };
 int dgb_fv_kernel_info(const dgb_fv* fv, int32_t* info8);
+/* host arithmetic only (no device needed): the z planes one CTA of the 3-D ring kernel (128 x 4 tile) marches for a region of
+ * nx x ny x nz interior cells - packs: the launch also packs the send boxes; tensor_map: the tensor-map staging form. Chunks of
+ * equal length leave a ragged last wave on the 148 SMs, so the rules take m long chunks and a short last one. */
+int dgb_fv_chunk_rule(int nx, int ny, int nz, int packs, int tensor_map, int* zchunk);
 /* how the last dgb_fv_step refreshed the overlap cells: */
 #define DGB_FV_EXCHANGE_NONE 0      /* no step yet, or nothing to exchange */
 #define DGB_FV_EXCHANGE_SERIAL 1    /* step kernel, then communicate() (2-D, or no room for a shell/bulk split) */

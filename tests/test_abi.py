@@ -45,3 +45,30 @@ def test_no_cpu_fallback_without_a_device():
     out = (ctypes.c_uint32 * 32)()
     rc = capi.lib.dgb_mapper_index(ctypes.byref(g.leafGridView().v), ctypes.byref(m.m), 0, 4, out, None)
     assert rc == -4 and b"no CPU fallback" in capi.lib.dgb_last_error()     # DGB_ECUDA
+
+
+def test_fv_chunk_rule_host_arithmetic():
+    """the z-chunk rules of the 3-D step kernel (host arithmetic, no device): a short LAST chunk fills the ragged last wave -
+    512^3 single GPU (tensor-map form): 160 + 160 + 160 + 32; 512^3 interior of a rank of 1024^3 / 8 with the in-kernel pack:
+    224 + 224 + 64; boxes with >= 2048 CTAs at 256 planes keep 256; small grids are cut until two waves of CTAs exist"""
+    import ctypes as C
+    from dune_grid_b200 import capi
+
+    def rule(nx, ny, nz, packs, tma):
+        z = C.c_int(0)
+        assert capi.lib.dgb_fv_chunk_rule(nx, ny, nz, packs, tma, C.byref(z)) == 0
+        return z.value
+    assert rule(512, 512, 512, 0, 1) == 160
+    assert rule(512, 512, 512, 0, 0) == 256
+    assert rule(512, 512, 512, 1, 0) == 224
+    assert rule(511, 511, 511, 1, 0) == 224
+    assert rule(256, 1024, 1024, 1, 0) == 256          # rank box of 1024^3 / 4: 2048 CTAs at 256 planes
+    assert rule(512, 1024, 1024, 1, 0) == 256          # rank box of 1024^3 / 2
+    for nx, ny, nz, packs, tma in ((256, 8, 64, 0, 1), (256, 8, 32, 1, 0), (300, 40, 100, 0, 0), (1024, 1024, 1024, 0, 1)):
+        z = rule(nx, ny, nz, packs, tma)
+        assert 1 <= z <= max(nz, 16), (nx, ny, nz, z)
+        chunks = -(-nz // z)
+        assert chunks * z >= nz
+        if tma and nz >= 512:                           # the last chunk is the short one
+            assert nz - (chunks - 1) * z <= z // 2, (nz, z)
+    assert capi.lib.dgb_fv_chunk_rule(0, 1, 1, 0, 0, None) != 0
